@@ -1,0 +1,194 @@
+// az_device.cuh -- device-side parameter blocks and pair-interaction functions (sm_100a).
+//
+// No device function pointers and no god-struct: the reference makes two indirect calls per
+// pair through md->funcCoul / vdw->feng (src/cuPairs.cu:131,141-146); here the (vdW kind,
+// Coulomb kind) combination is a template parameter and all scalars travel by value in a
+// __grid_constant__ parameter block.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/aztot_b200.h"
+
+#define AZ_VK_MIXED 8 /* template value: per-pair switch over the table's kinds */
+
+struct AzVdw {     // one entry of the nSpec x nSpec table (cudaVdW, src/cuStruct.h:50-63)
+    float p0, p1, p2, p3;
+    float p4, r2cut, chprod; // chprod = q_i*q_j (md->chProd, src/cuStruct.h:381)
+    int kind;                // az_vdw_kind, 0 = no entry
+};
+
+struct AzGrid {
+    int n[3];      // global cell counts (cNumber)
+    int nl[3];     // local grid dims (== n on one GPU; owned + ghost layers when decomposed)
+    int goff[3];   // global cell coordinate of local index 0 (0 when not decomposed)
+    int dec[3];    // 1 = axis is decomposed across ranks (no local wrap; ghosts carry images)
+    int olo[3], ohi[3]; // owned local cell range [olo, ohi)
+    int sten[3];   // stencil half widths (cell_dist_int, src/cuCellList.cu:98-132)
+    float csize[3], crev[3];
+    int ncell_local;
+};
+
+struct AzParams {
+    int n_local;        // atoms resident on this GPU that take part as i-atoms (owned)
+    int nspec;
+    float L[3], revL[3];
+    float tSt;
+    float r2max;
+    float efield[3];
+    int has_efield;
+    // Coulomb scalars (md->alpha, daipi2, elC1, elC2, rElec; src/cuInit.cu:951-957)
+    float alpha, daipi2, elC1, elC2, rElec;
+    // per-species tables
+    float mass[AZ_MAX_SPECIES], charge[AZ_MAX_SPECIES], rMasshdT[AZ_MAX_SPECIES];
+    float radA[AZ_MAX_SPECIES], radB[AZ_MAX_SPECIES], mxEng[AZ_MAX_SPECIES];
+    int frozen[AZ_MAX_SPECIES];
+    // thermostat
+    int tstat;
+    float teKin;
+    uint32_t seed_lo, seed_hi;
+    AzGrid g;
+};
+
+#define AZ_FCOUL_SCALE 14.3996f // d_Fcoul_scale, src/main.cu:40
+#define AZ_SQRTPI 1.772453f     // d_sqrtpi, src/main.cu:41
+#define AZ_REV_LIGHT 3.33567e-5f // revLight, src/cuTemp.cu:225
+#define AZ_NUM_PI 3.14159f       // numPi, src/cuTemp.cu:228
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10, identical to oracle/az_oracle.c
+__device__ __forceinline__ void az_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                          uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pair functions.  Each returns F/r and adds the pair energy.  Arithmetic follows the
+// reference forms; 1/x and x/y use the hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of
+// the IEEE division sequence -- inside the 1e-5 relative force tolerance of the parity tests.
+__device__ __forceinline__ float az_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float az_fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int VK>
+__device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r, bool have_r,
+                                             float rad1, float rad2, float& eng)
+{
+    if (VK == AZ_VDW_LJ) { // cu_fe_lj, src/cuVdW.cu:37-47
+        float r2i = az_fast_rcp(r2);
+        float sr2 = v.p1 * r2i;
+        float sr6 = sr2 * sr2 * sr2;
+        eng += v.p0 * sr6 * (sr6 - 1.f);
+        return v.p2 * r2i * sr6 * (2.f * sr6 - 1.f);
+    } else if (VK == AZ_VDW_BUCK) { // cu_fe(r)_buck, src/cuVdW.cu:69-91
+        float r2i = az_fast_rcp(r2);
+        float r4i = r2i * r2i;
+        if (!have_r) r = sqrtf(r2);
+        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        eng += ex - v.p2 * r4i * r2i;
+        return ex * az_fast_rcp(r) * az_fast_rcp(v.p1) - 6.f * v.p2 * r4i * r4i;
+    } else if (VK == AZ_VDW_BMH) { // cu_fe(r)_bmh, src/cuVdW.cu:115-136
+        float r2i = az_fast_rcp(r2);
+        float r4i = r2i * r2i;
+        if (!have_r) r = sqrtf(r2);
+        float ex = v.p0 * __expf(v.p1 * (v.p2 - r));
+        eng += ex - v.p3 * r4i * r2i - v.p4 * r4i * r4i;
+        return v.p1 * ex * az_fast_rcp(r) - 6.f * v.p3 * r4i * r4i - 8.f * v.p4 * r4i * r4i * r2i;
+    } else if (VK == AZ_VDW_ELIN) { // cu_fe(r)_elin, src/cuVdW.cu:162-179
+        if (!have_r) r = sqrtf(r2);
+        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        float ir = az_fast_rcp(r);
+        eng += ex + v.p2 * r;
+        return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir;
+    } else if (VK == AZ_VDW_EINV) { // cu_fe(r)_einv, src/cuVdW.cu:200-217
+        if (!have_r) r = sqrtf(r2);
+        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        float ir = az_fast_rcp(r);
+        eng += ex - v.p2 * ir;
+        return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir * az_fast_rcp(r2);
+    } else if (VK == AZ_VDW_SURK) { // surk_pot, src/cuVdW.cu:236-257
+        float c2ir = v.p1 * az_fast_rcp(v.p2 * rad1 + v.p3 * rad2);
+        float r_prod = rad1 * rad2;
+        float c1ab2 = r_prod * r_prod * v.p0;
+        float r2i = az_fast_rcp(r2);
+        float ir6 = r2i * r2i * r2i;
+        float ir = rsqrtf(r2);
+        eng += r_prod * ir6 * (c1ab2 * ir - c2ir);
+        return r_prod * ir6 * r2i * (7.f * c1ab2 * ir - 6.f * c2ir);
+    }
+    return 0.f;
+}
+
+__device__ __forceinline__ float az_vdw_feng_any(const AzVdw& v, float r2, float& r, bool have_r,
+                                                 float rad1, float rad2, float& eng)
+{
+    switch (v.kind) {
+    case AZ_VDW_LJ: return az_vdw_feng<AZ_VDW_LJ>(v, r2, r, have_r, rad1, rad2, eng);
+    case AZ_VDW_BUCK: return az_vdw_feng<AZ_VDW_BUCK>(v, r2, r, have_r, rad1, rad2, eng);
+    case AZ_VDW_BMH: return az_vdw_feng<AZ_VDW_BMH>(v, r2, r, have_r, rad1, rad2, eng);
+    case AZ_VDW_ELIN: return az_vdw_feng<AZ_VDW_ELIN>(v, r2, r, have_r, rad1, rad2, eng);
+    case AZ_VDW_EINV: return az_vdw_feng<AZ_VDW_EINV>(v, r2, r, have_r, rad1, rad2, eng);
+    case AZ_VDW_SURK: return az_vdw_feng<AZ_VDW_SURK>(v, r2, r, have_r, rad1, rad2, eng);
+    default: return 0.f;
+    }
+}
+
+// Coulomb: returns F/r, writes r (the reference passes r on to the vdW *_r variants).
+template <int CK>
+__device__ __forceinline__ float az_coul_feng(const AzParams& P, float r2, float& r, float chprd, float& eng)
+{
+    if (CK == AZ_ELEC_DIRECT) { // direct_coul, src/cuElec.cu:27-37
+        float kqq = chprd * AZ_FCOUL_SCALE;
+        float ir = rsqrtf(r2);
+        r = r2 * ir;
+        eng += kqq * ir;
+        return kqq * ir * ir * ir;
+    } else if (CK == AZ_ELEC_EWALD) { // real_ewald, src/cuElec.cu:94-113
+        float kqq = chprd * AZ_FCOUL_SCALE;
+        float ir = rsqrtf(r2);
+        r = r2 * ir;
+        float ar = P.alpha * r;
+        float erfcar = erfcf(ar);
+        eng += kqq * erfcar * ir;
+        return kqq * ir * ir * ir * (erfcar + 2.f * ar * (1.f / AZ_SQRTPI) * __expf(-ar * ar));
+    } else if (CK == AZ_ELEC_FENNEL) { // fennel, src/cuElec.cu:115-134
+        float kqq = chprd * AZ_FCOUL_SCALE;
+        float ir = rsqrtf(r2);
+        r = r2 * ir;
+        float ar = P.alpha * r;
+        float erfcar = erfcf(ar);
+        eng += kqq * (erfcar * ir - P.elC1 + P.elC2 * (r - P.rElec));
+        return kqq * ir * ((erfcar * ir * ir + P.daipi2 * __expf(-ar * ar) * ir) - P.elC2);
+    }
+    return 0.f;
+}
+
+// pair_1 (src/cuPairs.cu:117-167) for one (i,j) candidate already inside r2 <= r2Max.
+template <int VK, int CK>
+__device__ __forceinline__ float az_pair(const AzParams& P, const AzVdw& v, float r2, float rad_i,
+                                         float rad_j, bool same_type, float& evdw, float& ecoul)
+{
+    float f = 0.f, r = 0.f;
+    if (CK != AZ_ELEC_NONE) f += az_coul_feng<CK>(P, r2, r, v.chprod, ecoul);
+    if (VK != AZ_VDW_NONE) {
+        if ((VK == AZ_VK_MIXED ? v.kind != AZ_VDW_NONE : true) && r2 <= v.r2cut) {
+            float ra = rad_i, rb = rad_j;
+            if ((VK == AZ_VDW_SURK || VK == AZ_VK_MIXED) && same_type) { // symmetric same-species surk
+                float lo = fminf(ra, rb), hi = fmaxf(ra, rb); ra = lo; rb = hi;
+            }
+            if (VK == AZ_VK_MIXED) f += az_vdw_feng_any(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, evdw);
+            else f += az_vdw_feng<VK>(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, evdw);
+        }
+    }
+    // force_autocap, src/cuPairs.cu:94-115 (NaN passes through like the reference)
+    f = (f > AZ_MX_FRC) ? AZ_MX_FRC : ((f < -AZ_MX_FRC) ? -AZ_MX_FRC : f);
+    return f;
+}

@@ -1,0 +1,413 @@
+// az_kernels.cuh -- bin / scan / reorder / integrate / thermostat kernels (sm_100a).
+//
+// Data layout in HBM (per atom, SoA streams, 16-byte aligned, LDG.128/STG.128):
+//   pos[i]   = float4 (x, y, z, bitcast(type))
+//   vel[i]   = float4 (vx, vy, vz, 0)
+//   frc[i]   = float4 (fx, fy, fz, 0)          current (sorted) order only
+//   therm[i] = float2 (U thermal energy, radius)  radiative thermostat / surk only
+//   id[i]    = int     persistent id (index in atoms.xyz)
+// One thread per atom, coalesced -- the reference gives each thread `atPerThread`
+// consecutive AoS atoms (src/cuInit.cu:963-972), i.e. uncoalesced.
+#pragma once
+#include "az_device.cuh"
+
+#define AZ_TPB 256
+
+__device__ __forceinline__ double az_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of up to NV doubles; result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void az_block_sum(double (&v)[NV], double* smem /* [NV*32] */)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = az_warp_sum(v[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; k++) smem[k * 32 + w] = v[k];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double t = lane < nw ? smem[k * 32 + lane] : 0.0;
+            v[k] = az_warp_sum(t);
+        }
+    }
+    __syncthreads();
+}
+
+// Device-resident step scalars (what reset_quantities / calc_quantities keep in cudaMD).
+struct AzScalars {
+    double posMom[3], negMom[3];              // cumulative (src/cuMDfunc.cu:72-104)
+    int acPos[AZ_MAX_SPECIES][3], acNeg[AZ_MAX_SPECIES][3];
+    double engElecField;                      // per step
+    double engKin, engVdW, engCoul1, engTemp; // per step, reduced
+    float engKin_f;                           // after after_tscale
+    float posMomBuf[AZ_N_MOM][3], negMomBuf[AZ_N_MOM][3];
+    int iMom;
+    float pressure, engTot, engPot;
+    int step;
+    int overflow; // sticky error flags
+    float tscale_k;
+};
+
+// ---------------------------------------------------------------------------------------
+// K1: verlet_1stage (src/cuMDfunc.cu:333-518) + put_periodic (:35-106) + count_cell
+// (src/cuSort.cu:114-128).  BIN=false is the stale-cell variant used between rebuilds.
+template <bool BIN>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, float4* __restrict__ vel,
+                 const float4* __restrict__ frc, int* __restrict__ cellOf, int* __restrict__ slotOf,
+                 int* __restrict__ cellCount, AzScalars* __restrict__ sc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double eF = 0.0;
+    if (i < P.n_local) {
+        float4 p = pos[i], v = vel[i], f = frc[i];
+        int t = __float_as_int(p.w);
+        float h = P.rMasshdT[t];
+        v.x += h * f.x; v.y += h * f.y; v.z += h * f.z;
+        if (!P.frozen[t]) { p.x += v.x * P.tSt; p.y += v.y * P.tSt; p.z += v.z * P.tSt; }
+        if (BIN) {
+            float m = P.mass[t];
+            float* pc[3] = { &p.x, &p.y, &p.z };
+            float vc[3] = { v.x, v.y, v.z };
+            int ci[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                int nx = (int)floor((double)*pc[a] * (double)P.revL[a]); // the reference's double floor
+                float x = *pc[a] - (float)nx * P.L[a];
+                if (x >= P.L[a]) x = 0.f;
+                *pc[a] = x;
+                if (nx > 0) { atomicAdd(&sc->acPos[t][a], 1); atomicAdd(&sc->posMom[a], (double)(m * vc[a])); }
+                else if (nx < 0) { atomicAdd(&sc->acNeg[t][a], 1); atomicAdd(&sc->negMom[a], (double)(m * (-vc[a]))); }
+                int c = (int)floor((double)x * (double)P.g.crev[a]);
+                c = max(0, min(c, P.g.n[a] - 1));
+                ci[a] = c;
+            }
+            // local cell id (== global id on one GPU: x*cnYZ + y*cNumber.z + z)
+            int lc = ((ci[0] - P.g.goff[0]) * P.g.nl[1] + (ci[1] - P.g.goff[1])) * P.g.nl[2] + (ci[2] - P.g.goff[2]);
+            cellOf[i] = lc;
+            slotOf[i] = atomicAdd(&cellCount[lc], 1);
+        }
+        pos[i] = p; vel[i] = v;
+        if (P.has_efield) {
+            float q = P.charge[t];
+            eF = (double)(q * (p.x * P.efield[0] + p.y * P.efield[1] + p.z * P.efield[2]));
+        }
+    }
+    if (P.has_efield) {
+        __shared__ double sm[32];
+        double v1[1] = { eF };
+        az_block_sum<1>(v1, sm);
+        if (threadIdx.x == 0) atomicAdd(&sc->engElecField, v1[0]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: exclusive scan of nAtInCell -> firstAtomInCell (calc_firstAtomInCell, src/cuSort.cu:130-143,
+// a single-thread loop in the reference).  Two launches: tile sums, then each tile adds the
+// sums of the tiles before it and scans its own items.
+#define AZ_SCAN_TPB 256
+#define AZ_SCAN_IPT 8
+#define AZ_SCAN_TILE (AZ_SCAN_TPB * AZ_SCAN_IPT)
+
+__global__ void __launch_bounds__(AZ_SCAN_TPB)
+az_k_scan_tiles(const int* __restrict__ count, int n, int* __restrict__ tileSum)
+{
+    int base = blockIdx.x * AZ_SCAN_TILE;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < AZ_SCAN_IPT; k++) {
+        int idx = base + k * AZ_SCAN_TPB + threadIdx.x;
+        if (idx < n) s += count[idx];
+    }
+    __shared__ int sm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = threadIdx.x < (AZ_SCAN_TPB / 32) ? sm[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) tileSum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(AZ_SCAN_TPB)
+az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ tileSum,
+                int* __restrict__ first /* [n+1] */)
+{
+    __shared__ int sm[32];
+    __shared__ int s_off;
+    // offset of this tile = sum of the tile sums before it
+    int off = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += AZ_SCAN_TPB) off += tileSum[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_down_sync(0xffffffffu, off, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = off;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < AZ_SCAN_TPB / 32; k++) t += sm[k]; s_off = t; }
+    __syncthreads();
+    int base = blockIdx.x * AZ_SCAN_TILE + threadIdx.x * AZ_SCAN_IPT; // thread owns IPT consecutive cells
+    int v[AZ_SCAN_IPT], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < AZ_SCAN_IPT; k++) { v[k] = (base + k < n) ? count[base + k] : 0; tsum += v[k]; }
+    // block exclusive scan of tsum
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; k++) woff += sm[k];
+    int run = s_off + woff + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < AZ_SCAN_IPT; k++) {
+        if (base + k < n) first[base + k] = run;
+        run += v[k];
+    }
+    if (base <= n - 1 && n - 1 < base + AZ_SCAN_IPT) first[n] = run; // total, after the last cell
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: sort_atoms (src/cuSort.cu:145-197) made deterministic.  Phase a drops each atom's
+// persistent id into its cell segment at the atomicAdd slot (arbitrary order); phase b ranks the
+// atom inside its cell by id (cells hold ~10-20 atoms) and scatters the payload streams, so the
+// within-cell order is canonical (ascending id) whatever the atomics did.
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_sort_keys(int n, const int* __restrict__ cellOf, const int* __restrict__ slotOf,
+               const int* __restrict__ first, const int* __restrict__ id, int* __restrict__ keyTmp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keyTmp[first[cellOf[i]] + slotOf[i]] = id[i];
+}
+
+template <bool THERM>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_sort_scatter(int n, const int* __restrict__ cellOf, const int* __restrict__ first,
+                  const int* __restrict__ count, const int* __restrict__ keyTmp,
+                  const float4* __restrict__ pos, const float4* __restrict__ vel,
+                  const int* __restrict__ id, const float2* __restrict__ therm,
+                  float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o,
+                  float2* __restrict__ therm_o, int* __restrict__ cell_o)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cellOf[i];
+    int b = first[c], m = count[c];
+    int my = id[i];
+    int rank = 0;
+    for (int k = 0; k < m; k++) rank += (keyTmp[b + k] < my);
+    int d = b + rank;
+    pos_o[d] = pos[i];
+    vel_o[d] = vel[i];
+    id_o[d] = my;
+    cell_o[d] = c;
+    if (THERM) therm_o[d] = therm[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Radiative thermostat for one atom: tstat_radi9 body (src/cuTemp.cu:709-763) with
+// adsorb_rand_photon (:484-507), radiate_photon3 (:631-685) and get_angled_vector (:395-453).
+__device__ __forceinline__ float az_f3sqr(float x, float y, float z) { return x * x + y * y + z * z; }
+
+__device__ __forceinline__ void az_angled_vector(float ix, float iy, float iz, float cos_phi, float theta,
+                                                 float& ox, float& oy, float& oz)
+{
+    float l1 = sqrtf(az_f3sqr(ix, iy, iz));
+    float v1x = ix / l1, v1y = iy / l1, v1z = iz / l1;
+    float v2x, v2y, v2z;
+    if (v1x != 0.f) { v2y = 1.f; v2z = 1.f; v2x = -(v1y * v2y + v1z * v2z) / v1x; }
+    else if (v1y != 0.f) { v2x = 1.f; v2z = 1.f; v2y = -(v1z * v2z) / v1y; }
+    else { v2x = 1.f; v2y = 0.f; v2z = 0.f; }
+    float v3x = v1y * v2z - v1z * v2y;
+    float v3y = -v1x * v2z + v1z * v2x;
+    float v3z = v1x * v2y - v1y * v2x;
+    float l2 = sqrtf(az_f3sqr(v2x, v2y, v2z)), l3 = sqrtf(az_f3sqr(v3x, v3y, v3z));
+    v2x /= l2; v2y /= l2; v2z /= l2;
+    v3x /= l3; v3y /= l3; v3z /= l3;
+    float sinPhi = sqrtf(1 - cos_phi * cos_phi);
+    float sinTh, cosTh;
+    sincosf(theta, &sinTh, &cosTh);
+    ox = v1x * cos_phi + sinPhi * (cosTh * v2x + sinTh * v3x);
+    oy = v1y * cos_phi + sinPhi * (cosTh * v2y + sinTh * v3y);
+    oz = v1z * cos_phi + sinPhi * (cosTh * v2z + sinTh * v3z);
+}
+
+__device__ __forceinline__ void az_tstat_radi_atom(const AzParams& P, int step, int pid, int tp, float pe,
+                                                   const float* __restrict__ uv, float& vx, float& vy,
+                                                   float& vz, float& U, float& rad)
+{
+    float mass = P.mass[tp];
+    uint32_t rn[4];
+    az_philox((uint32_t)pid, (uint32_t)step, 0x52414449u, 0u, P.seed_lo, P.seed_hi, rn);
+    const float* u = uv + 3 * (rn[1] % AZ_N_UVECT);
+    float ux = u[0], uy = u[1], uz = u[2];
+    { // adsorb_rand_photon
+        float v02 = az_f3sqr(vx, vy, vz);
+        float ermc = pe * AZ_REV_LIGHT / mass;
+        vx += ermc * ux; vy += ermc * uy; vz += ermc * uz;
+        float v12 = az_f3sqr(vx, vy, vz);
+        U += pe + 0.5f * mass * (v02 - v12);
+    }
+    if ((double)U > 1e-4) { // radiate_photon3
+        float u0 = U;
+        float v02 = az_f3sqr(vx, vy, vz);
+        float v0 = sqrtf(v02);
+        float ph_eng = 0.9f * u0;
+        float ermc = ph_eng * AZ_REV_LIGHT / mass;
+        float ermcv0 = ermc / v0;
+        float rx, ry, rz;
+        if (!(ermcv0 < 1.f)) {
+            if (v0 > 0.f) { rx = -vx / v0; ry = -vy / v0; rz = -vz / v0; }
+            else { rx = ux; ry = uy; rz = uz; }
+        } else {
+            float cos_phi = (float)(rn[2] % 2048u) / 1024.f * (1.f - ermcv0);
+            cos_phi -= 1.f;
+            float theta = (float)(rn[3] % 2048u) / 1024.f * AZ_NUM_PI;
+            az_angled_vector(vx, vy, vz, cos_phi, theta, rx, ry, rz);
+        }
+        vx += ermc * rx; vy += ermc * ry; vz += ermc * rz;
+        float v12 = az_f3sqr(vx, vy, vz);
+        U -= (ph_eng + 0.5f * mass * (v12 - v02));
+    }
+    float restrE = fminf(U, P.mxEng[tp]);
+    rad = P.radA[tp] / (P.radB[tp] - restrE);
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: verlet_2stage (src/cuMDfunc.cu:521-599) with the kinetic-energy reduction, and -- when
+// TSTAT -- tstat_radi9 fused behind it (the reference's KE is taken before the thermostat acts).
+// Partial sums go to per-block slots; az_k_finalize reduces them in a fixed order.
+template <bool TSTAT>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __restrict__ pos,
+                 float4* __restrict__ vel, const float4* __restrict__ frc, const int* __restrict__ id,
+                 float2* __restrict__ therm, const float* __restrict__ photons,
+                 const float* __restrict__ uv, double* __restrict__ partKE, double* __restrict__ partU)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double ke = 0.0, ut = 0.0;
+    if (i < P.n_local) {
+        float4 v = vel[i], f = frc[i];
+        int t = __float_as_int(pos[i].w);
+        float h = P.rMasshdT[t];
+        v.x += h * f.x; v.y += h * f.y; v.z += h * f.z;
+        ke = (double)((v.x * v.x + v.y * v.y + v.z * v.z) * P.mass[t]);
+        if (TSTAT) {
+            float2 th = therm[i];
+            az_tstat_radi_atom(P, step, id[i], t, photons[i], uv, v.x, v.y, v.z, th.x, th.y);
+            therm[i] = th;
+            ut = (double)th.x;
+        }
+        vel[i] = v;
+    }
+    __shared__ double sm[64];
+    double vv[2] = { ke, ut };
+    az_block_sum<2>(vv, sm);
+    if (threadIdx.x == 0) { partKE[blockIdx.x] = 0.5 * vv[0]; if (TSTAT) partU[blockIdx.x] = vv[1]; }
+}
+
+// temp_scale (src/cuTemp.cu:77-107) [+ tstat_radi9] on an equilibration step.
+template <bool TSTAT>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restrict__ pos,
+            float4* __restrict__ vel, const int* __restrict__ id, float2* __restrict__ therm,
+            const float* __restrict__ photons, const float* __restrict__ uv,
+            const AzScalars* __restrict__ sc, double* __restrict__ partU)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double ut = 0.0;
+    float k = sc->tscale_k;
+    if (i < P.n_local) {
+        float4 v = vel[i];
+        v.x *= k; v.y *= k; v.z *= k;
+        if (TSTAT) {
+            int t = __float_as_int(pos[i].w);
+            float2 th = therm[i];
+            az_tstat_radi_atom(P, step, id[i], t, photons[i], uv, v.x, v.y, v.z, th.x, th.y);
+            therm[i] = th;
+            ut = (double)th.x;
+        }
+        vel[i] = v;
+    }
+    if (TSTAT) {
+        __shared__ double sm[32];
+        double vv[1] = { ut };
+        az_block_sum<1>(vv, sm);
+        if (threadIdx.x == 0) partU[blockIdx.x] = vv[0];
+    }
+}
+
+// Fixed-order reduction of the per-block partials.  mode bits: 1 = KE, 2 = pair energies,
+// 4 = thermal energy, 8 = this is an equilibration T-scale step (computes tscale_k, after_tscale),
+// 16 = calc_quantities (src/main.cu:121-162) and publish.
+__global__ void __launch_bounds__(1024)
+az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const double* __restrict__ partKE, int nKE,
+              const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
+              const double* __restrict__ partU, int nU, AzScalars* __restrict__ sc,
+              float revAx, float revAy, float revAz)
+{
+    __shared__ double sm[4 * 32];
+    double v[4] = { 0, 0, 0, 0 };
+    if (mode & 1) for (int k = threadIdx.x; k < nKE; k += blockDim.x) v[0] += partKE[k];
+    if (mode & 2) for (int k = threadIdx.x; k < nPair; k += blockDim.x) { v[1] += partV[k]; v[2] += partC[k]; }
+    if (mode & 4) for (int k = threadIdx.x; k < nU; k += blockDim.x) v[3] += partU[k];
+    az_block_sum<4>(v, sm);
+    if (threadIdx.x != 0) return;
+    if (mode & 1) { sc->engKin = v[0]; sc->engKin_f = (float)v[0]; }
+    if (mode & 2) { sc->engVdW = v[1]; sc->engCoul1 = v[2]; }
+    if (mode & 4) sc->engTemp = v[3];
+    if (mode & 8) {
+        float k = 1.f;
+        if (sc->engKin_f != 0.f) {
+            float c = (P.tstat == AZ_TSTAT_RADI) ? 0.25f : 1.f;
+            k = sqrtf(c * P.teKin / sc->engKin_f);
+        }
+        sc->tscale_k = k;
+        sc->engKin_f = P.teKin; sc->engKin = (double)P.teKin; // after_tscale, src/cuTemp.cu:109-113
+    }
+    if (mode & 16) {
+        float engCoulTot = (float)sc->engCoul1;
+        sc->engPot = engCoulTot + (float)sc->engVdW;
+        sc->engTot = sc->engPot + sc->engKin_f;
+        float pm[3] = { (float)sc->posMom[0], (float)sc->posMom[1], (float)sc->posMom[2] };
+        float nm[3] = { (float)sc->negMom[0], (float)sc->negMom[1], (float)sc->negMom[2] };
+        float ra[3] = { revAx, revAy, revAz };
+        if (step >= AZ_N_MOM - 1) {
+            int i = sc->iMom;
+            float k = (float)(2.f * 1.58e6 / (double)(P.tSt * (float)(AZ_N_MOM - 1)));
+            float tot = 0.f, pp[3], np[3];
+            for (int a = 0; a < 3; a++) {
+                pp[a] = k * (pm[a] - sc->posMomBuf[i][a]) * ra[a];
+                np[a] = k * (nm[a] - sc->negMomBuf[i][a]) * ra[a];
+            }
+            i--; if (i < 0) i = AZ_N_MOM - 1;
+            for (int a = 0; a < 3; a++) { sc->posMomBuf[i][a] = pm[a]; sc->negMomBuf[i][a] = nm[a]; }
+            sc->iMom++; if (sc->iMom >= AZ_N_MOM) sc->iMom = 0;
+            tot = (pp[0] + pp[1] + pp[2] + np[0] + np[1] + np[2]) / 6.f;
+            sc->pressure = tot;
+        } else if (step >= 0) {
+            for (int a = 0; a < 3; a++) { sc->posMomBuf[step][a] = pm[a]; sc->negMomBuf[step][a] = nm[a]; }
+        }
+        sc->step = step;
+    }
+}
+
+__global__ void az_k_reset_step(AzScalars* sc) { sc->engElecField = 0.0; } // reset_quantities
+
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_gather_by_id(int n, const int* __restrict__ id, const float4* __restrict__ src, float4* __restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[id[i]] = src[i];
+}

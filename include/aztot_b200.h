@@ -1,0 +1,260 @@
+/*
+ * aztot_b200.h -- C ABI of the B200-native azTotMD hot-path engine.
+ *
+ * This is the drop-in boundary for the per-step MD hot path of raadyn/aztotmd
+ * (bin + reorder -> short-range pair forces -> velocity Verlet + radiative
+ * thermostat + kinetic-energy reduction).  The reference has no FFI; its internal
+ * seam is the host->device translation layer:
+ *
+ *   az_engine_create    replaces  init_cudaMD          src/cuInit.cu:756-1199
+ *                                 define_global_func   src/main.cu:196-226
+ *                                 define_vdw_func      src/cuVdW.cu:260-302
+ *   az_engine_step      replaces  the loop body        src/main.cu:281-383
+ *                                 iter_fastCellList    src/cuPairs.cu:2519-2568
+ *                                 apply_tstat          src/cuTemp.cu:775-803
+ *   az_engine_stats     replaces  write_stat/copy_stat src/cuStat.cu:17-71
+ *                                 calc_quantities      src/main.cu:121-162
+ *   az_engine_download  replaces  md_to_host           src/cuInit.cu:1212-1261
+ *                                 out_thermalchar (device part)  src/main.cu:51-66
+ *   az_engine_debug_dump  (new; parity tests)  cellIndexes/firstAtomInCell/nAtInCell
+ *                                              of src/cuStruct.h:342-349 + forces
+ *   az_engine_destroy   replaces  free_device_md       src/cuInit.cu:1263-1373
+ *
+ * Plain C: POD structs, plain pointers and sizes.  Host arrays passed in are
+ * borrowed for the duration of the call only; outputs are caller-allocated.
+ * One engine = one GPU = one owning host thread.  No exceptions cross the ABI
+ * and the library never calls exit(); every entry point returns an az_status
+ * (0 = ok, negative = error) and az_last_error() explains the last failure.
+ * There is NO CPU fallback: without a CUDA device az_engine_create fails.
+ */
+#ifndef AZTOT_B200_H
+#define AZTOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ABI_VERSION 1
+#define AZ_MAX_SPECIES 15   /* MX_SPEC, src/defines.h:15 */
+#define AZ_N_UVECT 3072     /* nUvect, src/cuTemp.h:4-6 = 3 * 32 * 16 * 2 */
+#define AZ_N_MOM 20         /* nMom, src/cuInit.cu:921 (pressure ring length) */
+#define AZ_MX_FRC 1.0e4f    /* MX_FRC, src/defines.h:10 (AUTO_CAP) */
+
+typedef enum az_status {
+    AZ_OK = 0,
+    AZ_ERR_INVALID = -1,     /* bad argument / inconsistent description          */
+    AZ_ERR_NO_DEVICE = -2,   /* no CUDA device (there is no CPU fallback)        */
+    AZ_ERR_CUDA = -3,        /* a CUDA runtime call or kernel failed             */
+    AZ_ERR_UNSUPPORTED = -4, /* feature outside the hot path (Ewald k-space ...) */
+    AZ_ERR_OVERFLOW = -5,    /* a fixed-capacity device buffer overflowed        */
+    AZ_ERR_COMM = -6,        /* NCCL / multi-GPU plumbing failed                 */
+    AZ_ERR_IO = -7           /* deck file missing or unparsable                  */
+} az_status;
+
+/* van der Waals kinds: numeric values are the reference's type ids, src/vdw.h:15-21 */
+typedef enum az_vdw_kind {
+    AZ_VDW_NONE = 0,
+    AZ_VDW_LJ = 1,    /* lnjs  U = 4e[(s/r)^12-(s/r)^6]       src/cuVdW.cu:25-47   */
+    AZ_VDW_BUCK = 2,  /* buck  U = A exp(-r/ro) - C/r^6       src/cuVdW.cu:69-91   */
+    AZ_VDW_P746 = 3,  /* p746  host-only in the reference (src/vdw.cpp); rejected   */
+    AZ_VDW_BMH = 4,   /* bmhs  U = A exp[B(s-r)]-C/r^6-D/r^8  src/cuVdW.cu:115-136 */
+    AZ_VDW_ELIN = 5,  /* elin  U = A exp(-r/ro) + C r         src/cuVdW.cu:162-179 */
+    AZ_VDW_EINV = 6,  /* einv  U = A exp(-r/ro) - C/r         src/cuVdW.cu:200-217 */
+    AZ_VDW_SURK = 7   /* surk  radius/temperature dependent   src/cuVdW.cu:236-257 */
+} az_vdw_kind;
+
+/* electrostatics kinds: values are tpElec* of src/dataStruct.h */
+typedef enum az_elec_kind {
+    AZ_ELEC_NONE = 0,   /* no_coul      src/cuElec.cu:20     */
+    AZ_ELEC_DIRECT = 1, /* direct_coul  src/cuElec.cu:27-37  */
+    AZ_ELEC_EWALD = 2,  /* real_ewald   src/cuElec.cu:94-113 (real-space part only) */
+    AZ_ELEC_FENNEL = 3  /* fennel (DSF) src/cuElec.cu:115-134 */
+} az_elec_kind;
+
+/* thermostat kinds: values are tpTerm* of src/dataStruct.h */
+typedef enum az_tstat_kind {
+    AZ_TSTAT_NONE = 0,
+    AZ_TSTAT_NOSE = 1, /* not on the hot path yet -> AZ_ERR_UNSUPPORTED */
+    AZ_TSTAT_RADI = 2  /* tstat_radi9  src/cuTemp.cu:689-773 */
+} az_tstat_kind;
+
+/* One species; mirror of the fields of Spec that init_cudaMD reads
+ * (src/cuInit.cu:843-866).  Internal units (mass already * m_scale). */
+typedef struct az_species {
+    char name[8];
+    double mass;
+    double charge;
+    int frozen;
+    int reserved;
+    double radA, radB, mxEng; /* 'radii' section, src/sys_init.cpp:468-480 */
+} az_species;
+
+/* One entry of the nSpec x nSpec pair-potential table, already prepared the
+ * way read_vdw leaves it (src/vdw.cpp:261-299): LJ p0=4e p1=s^2 p2=24e,
+ * r2cut = rcut^2.  kind == AZ_VDW_NONE means "no entry" (NULL in the reference). */
+typedef struct az_vdw_entry {
+    int kind;
+    int use_radii;
+    double p0, p1, p2, p3, p4;
+    double r2cut;
+} az_vdw_entry;
+
+/* Everything init_cudaMD reads from Atoms/Field/Sim/TStat/Box/Elec. */
+typedef struct az_system_desc {
+    int abi_version; /* = AZ_ABI_VERSION */
+    int n_atoms;
+    int n_species;
+    int reserved0;
+    /* atoms (SoA doubles as in struct Atoms, src/dataStruct.h); narrowed to
+     * float exactly like src/cuInit.cu:775-779.  vxs.. / fxs.. may be NULL (=0). */
+    const double *xs, *ys, *zs;
+    const double *vxs, *vys, *vzs;
+    const double *fxs, *fys, *fzs;
+    const int *types;
+    /* rectangular periodic box, src/box.cpp:9-27 */
+    double la, lb, lc;
+    const az_species *species;   /* [n_species] */
+    const az_vdw_entry *vdw;     /* [n_species*n_species], row-major [ti][tj] */
+    double max_r_vdw;            /* Field::maxRvdw, src/vdw.cpp:264 */
+    /* electrostatics after prepare_elec, src/elec.cpp:371-406 */
+    int elec_kind;
+    int reserved1;
+    double r_real;   /* Elec::rReal (kept even when the kind was downgraded) */
+    double alpha;
+    double daipi2;   /* 2 alpha / sqrt(pi) */
+    double el_c1;    /* Elec::scale  = erfc(a rc)/rc                         */
+    double el_c2;    /* Elec::scale2 = erfc(a rc)/rc^2 + daipi2 exp(-a^2rc^2)/rc */
+    double eps;      /* permittivity (parsed, unused by the reference kernels) */
+    /* thermostat, src/temperature.cpp:91-259, src/cuTemp.cu:11-62 */
+    int tstat_kind;
+    int reserved2;
+    double temperature;
+    double t_kin;              /* TStat::tKin, src/sys_init.cpp:1099-1106 */
+    const double *photons;     /* [n_atoms] photon energies or NULL if not radi */
+    const double *uvect_x, *uvect_y, *uvect_z; /* [AZ_N_UVECT] or NULL -> built-in table */
+    const float *init_radii;   /* [n_atoms] or NULL -> 0.577 + u*1e-4 (seeded)  */
+    const float *init_engs;    /* [n_atoms] or NULL -> 0                        */
+    uint64_t seed;             /* counter-based RNG key (the reference is unseeded) */
+    /* simulation scalars, src/cuInit.cu:951-961 */
+    double timestep;           /* Sim::tSt */
+    int n_equil, eq_freq;      /* Sim::nEq, Sim::freqEq */
+    double r2_max;             /* Sim::r2Max, src/sys_init.cpp:1059-1072 */
+    double cell_size;          /* Sim::desired_cell_size ('cell_list') */
+    double efield[3];          /* Sim::Ux,Uy,Uz */
+} az_system_desc;
+
+/* cuda.txt-level options plus the multi-GPU layout.  Zero-initialise for defaults. */
+typedef struct az_cuda_opts {
+    int device;          /* CUDA device ordinal                                       */
+    int rebuild_every;   /* 0/1 = reference behaviour (bin + sort every step)         */
+    float skin;          /* extra cell width when rebuild_every > 1 (Angstrom)        */
+    int use_graph;       /* 1 = capture the steady-state step in a CUDA graph         */
+    int pair_variant;    /* 0 = auto; tuning knob for the pair kernel                 */
+    int cells_per_block; /* 0 = auto; z-run length a CTA owns in the pair kernel      */
+    /* spatial domain decomposition (new functionality) */
+    int rank, n_ranks;
+    int pgrid[3];        /* ranks along x,y,z; product = n_ranks; 0 -> {n_ranks,1,1}  */
+    int ghost_slots;     /* fixed slots per ghost cell in halo messages; 0 = auto     */
+    const void *nccl_id; /* ncclUniqueId bytes (128) shared by all ranks, or NULL     */
+    int reserved[8];
+} az_cuda_opts;
+
+/* Scalars of stat.dat / msd.dat for the last completed step
+ * (src/cuStat.cu:232-298; float like the reference, reduced in double). */
+typedef struct az_stats {
+    int step;            /* iStep of the sample */
+    int n_atoms_total;
+    float engTot, engKin, engVdW, engCoul1, engCoul2, engTemp, engElecField, engPot;
+    float posMom[3], negMom[3]; /* cumulative face momenta, src/cuMDfunc.cu:72-104 */
+    float pressure;
+    float reserved;
+    int specAcBoxPos[AZ_MAX_SPECIES][3]; /* face crossing counters */
+    int specAcBoxNeg[AZ_MAX_SPECIES][3];
+    double engKin_d, engVdW_d, engCoul1_d, engTemp_d; /* unrounded accumulators */
+} az_stats;
+
+#define AZ_ORDER_SORTED 0   /* cell-sorted order, what md_to_host hands back */
+#define AZ_ORDER_ORIGINAL 1 /* order of atoms.xyz (by persistent id)         */
+
+/* Caller-allocated outputs; any pointer may be NULL to skip that array. */
+typedef struct az_atoms_out {
+    int n_atoms;      /* capacity of the arrays = desc.n_atoms (global count on 1 GPU) */
+    int n_written;    /* out: atoms written (owned atoms of this rank on multi-GPU)    */
+    double *xs, *ys, *zs;
+    double *vxs, *vys, *vzs;
+    int *types;
+    int *ids;         /* persistent ids (index in the original atoms.xyz) */
+    float *engs;      /* radiative thermostat: thermal energy U */
+    float *radii;     /* radiative thermostat: radius           */
+} az_atoms_out;
+
+/* Parity-test dump, sorted order.  Any pointer may be NULL. */
+typedef struct az_dump {
+    int n_atoms, n_cells;      /* capacities in; actual sizes out */
+    int cnum[3];               /* out: cNumber */
+    float csize[3], crev[3];   /* out: cSize, cRevSize (src/cuCellList.cu:21-22) */
+    int *cell_indexes;         /* [n_atoms]  cell of sorted atom i       */
+    int *first_atom_in_cell;   /* [n_cells]                              */
+    int *n_at_in_cell;         /* [n_cells]                              */
+    int *ids;                  /* [n_atoms]  persistent id of sorted atom i */
+    float *fx, *fy, *fz;       /* [n_atoms]  forces after the pair kernel */
+    float *x, *y, *z;          /* [n_atoms]  float positions              */
+    float *vx, *vy, *vz;       /* [n_atoms]                               */
+} az_dump;
+
+typedef struct az_engine az_engine;
+
+/* library / environment */
+int az_abi_version(void);
+const char *az_last_error(const az_engine *e); /* e may be NULL: error of the last failed create */
+int az_device_count(void);
+
+/* life cycle */
+int az_engine_create(const az_system_desc *desc, const az_cuda_opts *opts, az_engine **out);
+void az_engine_destroy(az_engine *e); /* idempotent on NULL */
+
+/* Advance nsteps steps; first_step is the reference's iStep of the first one
+ * (it gates equilibration scaling and keys the thermostat RNG).  Asynchronous on the
+ * engine's stream; az_engine_sync / stats / download synchronise. */
+int az_engine_step(az_engine *e, int first_step, int nsteps);
+int az_engine_sync(az_engine *e);
+void *az_engine_stream(az_engine *e); /* cudaStream_t of the engine (for external timing) */
+
+int az_engine_stats(az_engine *e, az_stats *out);
+int az_engine_download(az_engine *e, az_atoms_out *out, int order);
+int az_engine_debug_dump(az_engine *e, az_dump *out);
+/* Replace positions/velocities (original order, doubles, host memory) without
+ * re-creating the engine; forces are zeroed like a fresh create. */
+int az_engine_upload(az_engine *e, const double *xs, const double *ys, const double *zs,
+                     const double *vxs, const double *vys, const double *vzs);
+
+/* Per-kernel device timers (CUDA events on the engine stream). */
+#define AZ_TIMER_INTEGRATE_A 0 /* kick+drift+wrap+bin  (verlet_1stage)     */
+#define AZ_TIMER_SCAN 1        /* calc_firstAtomInCell                     */
+#define AZ_TIMER_SORT 2        /* sort_atoms                               */
+#define AZ_TIMER_PAIR 3        /* cell_list5a + cell_list4b_noshared       */
+#define AZ_TIMER_INTEGRATE_B 4 /* verlet_2stage + thermostat + quantities  */
+#define AZ_TIMER_HALO 5        /* multi-GPU halo / migration               */
+#define AZ_N_TIMERS 6
+int az_engine_profile(az_engine *e, int enable);
+int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
+long long az_engine_launch_count(az_engine *e); /* kernels launched since create */
+
+/* ---- deck surface (host side, libaztot_host): the reference's input files ---- */
+typedef struct az_deck az_deck;
+/* Parse atoms.xyz, field.txt, control.txt, cuda.txt from `dir` with the reference's
+ * token-scan semantics (src/utils.cpp:87-195, src/sys_init.cpp:174-988). */
+int az_deck_load(const char *dir, uint64_t seed, az_deck **out);
+const az_system_desc *az_deck_desc(const az_deck *d);
+const az_cuda_opts *az_deck_opts(const az_deck *d);
+int az_deck_nsteps(const az_deck *d);
+int az_deck_stat_period(const az_deck *d);
+const char *az_deck_error(const az_deck *d);
+void az_deck_free(az_deck *d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZTOT_B200_H */

@@ -1,0 +1,797 @@
+/*
+ * az_oracle.c -- CPU restatement of azTotMD's per-step hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this file.  The product (libaztot_b200.so) never links or calls it and has no
+ * CPU fallback.
+ *
+ * It restates, in plain C with float32 wherever the reference's device code is float32,
+ * the algorithm of the reference's CUDA build (paths into /root/reference):
+ *   grid geometry        split_cells            src/cuCellList.cu:9-34
+ *   cell-pair existence  cell_dist_int          src/cuCellList.cu:98-132
+ *                        pair_exists_shift      src/cuCellList.cu:213-240
+ *   binning              count_cell             src/cuSort.cu:114-128
+ *   scan                 calc_firstAtomInCell   src/cuSort.cu:130-143
+ *   reorder              sort_atoms             src/cuSort.cu:145-197
+ *   stage 1              verlet_1stage          src/cuMDfunc.cu:333-518
+ *   PBC + face stats     put_periodic           src/cuMDfunc.cu:35-106
+ *   pair gate / cap      pair_1, force_autocap  src/cuPairs.cu:94-167
+ *   vdW forms            cu_fe(r)_lj/buck/bmh/elin/einv, surk_pot   src/cuVdW.cu:25-257
+ *   Coulomb forms        direct_coul, real_ewald, fennel            src/cuElec.cu:27-134
+ *   stage 2              verlet_2stage          src/cuMDfunc.cu:521-599
+ *   T-scale              temp_scale/after_tscale  src/cuTemp.cu:77-113, gate :777-785
+ *   radiative thermostat tstat_radi9, adsorb_rand_photon, radiate_photon3,
+ *                        get_angled_vector      src/cuTemp.cu:395-453,484-507,631-773
+ *   derived quantities   calc_quantities        src/main.cu:121-162
+ *   host narrowing       init_cudaMD            src/cuInit.cu:768-791,934-961
+ *                        init_cuda_tstat        src/cuTemp.cu:11-62
+ *   unit vectors         read_tstat             src/temperature.cpp:164-223
+ *
+ * Deliberate, documented divergences from reference behaviour:
+ *   - within-cell order is canonical (ascending persistent id) instead of atomicAdd
+ *     arrival order (src/cuSort.cu:126);
+ *   - per-atom radii/engs follow the atom through the sort (reference bug, src/cuSort.cu:96);
+ *   - the thermostat RNG is counter based: Philox4x32-10 keyed by (seed), counter
+ *     (atom id, step); the reference's xorshift state is uninitialised and racy
+ *     (src/cuTemp.cu:701,770, src/cuUtils.cu:89-105);
+ *   - photon energy of atom i is engPhotons[sorted index i], the in-order-block case of
+ *     src/cuTemp.cu:697-722;
+ *   - radiate_photon3 with e/(m c v0) >= 1 uses the anti-parallel unit vector instead of an
+ *     uninitialised one (src/cuTemp.cu:663-675);
+ *   - count_cell indices are clamped into the grid (src/cuSort.cu:119-126 has no clamp);
+ *   - posMomBuf/negMomBuf are real float3[nMom] rings, face counters start at zero
+ *     (src/cuInit.cu:927-928,986-987);
+ *   - same-species surk with k != l: radii are ordered (min,max) so the pair term is symmetric.
+ * Energies and momenta are accumulated in double from float pair terms.
+ *
+ * PARITY PINNING: the reference ships no golden vectors.  This oracle is
+ * pinned (tests/test_oracle_pinning.py) against (a) the analytic known answers listed in
+ * SURVEY.md 8c and (b) forces/energies of the reference's own serial build compiled from
+ * /root/reference into oracle/_ref (oracle/build_ref.sh), committed as tests/golden/ fixtures.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "../include/aztot_b200.h"
+
+#if defined(__GNUC__)
+#pragma STDC FP_CONTRACT OFF
+#endif
+
+/* ------------------------------------------------------------------ RNG ---- */
+/* Philox4x32-10 (Salmon et al., SC'11), the same function the CUDA path uses. */
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                          uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void azo_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                uint32_t *out) { philox4x32_10(c0, c1, c2, c3, k0, k1, out); }
+
+/* uniform in [0,1) used for default initial radii: 0.577 + u*1e-4 (src/cuTemp.cu:41) */
+static float seeded_unit(uint64_t seed, uint32_t id)
+{
+    uint32_t o[4];
+    philox4x32_10(id, 0xA5A5A5A5u, 0, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    return (float)(o[0] % 10000u) / 10000.0f; /* rand01(), src/utils.cpp:197-201 */
+}
+
+/* ------------------------------------------------------------- geometry ---- */
+typedef struct {
+    int cnum[3];
+    float csize[3], crev[3];
+    int cnYZ, ncell;
+} azo_grid;
+
+/* split_cells, div_type 1 (src/cuCellList.cu:9-34, called from src/cuInit.cu:979) */
+void azo_split_cells(float lx, float ly, float lz, float r, int *cnum, float *csize, float *crev)
+{
+    float L[3] = { lx, ly, lz };
+    for (int a = 0; a < 3; a++) {
+        float q = L[a] / r;
+        int n = (int)floorf(q);
+        if (n < 1) n = 1; /* reference would divide by zero; keep one cell */
+        cnum[a] = n;
+        csize[a] = L[a] / (float)n;
+        crev[a] = (float)n / L[a];
+    }
+}
+
+/* count_cell index formula (src/cuSort.cu:119) with the clamp divergence. */
+int azo_cell_index(float x, float y, float z, const float *crev, const int *cnum)
+{
+    int ix = (int)floor((double)x * (double)crev[0]);
+    int iy = (int)floor((double)y * (double)crev[1]);
+    int iz = (int)floor((double)z * (double)crev[2]);
+    if (ix < 0) ix = 0; if (ix >= cnum[0]) ix = cnum[0] - 1;
+    if (iy < 0) iy = 0; if (iy >= cnum[1]) iy = cnum[1] - 1;
+    if (iz < 0) iz = 0; if (iz >= cnum[2]) iz = cnum[2] - 1;
+    return ix * (cnum[1] * cnum[2]) + iy * cnum[2] + iz;
+}
+
+/* Stencil half width along one axis: largest delt with rmin=(delt-1)*csize <= rc
+ * (cell_dist_int, src/cuCellList.cu:98-132), capped at n/2 because each cell pair
+ * exists once with the image chosen by "delt > mx/2" (integer division). */
+int azo_stencil_half(int n, float csize, float rc)
+{
+    int s = 1;
+    while ((float)s * csize <= rc && s < n) s++;
+    if (s > n / 2) s = n / 2;
+    return s;
+}
+
+/* Is offset o from cell coordinate c a distinct neighbour (reference image rule)?
+ * Returns 1 and writes the wrapped coordinate and the image shift sign (-1,0,+1). */
+int azo_neighbor(int n, int c, int o, int *cn, int *sh)
+{
+    int t = c + o;
+    int ao = o < 0 ? -o : o;
+    *sh = 0;
+    if (ao > n / 2) return 0;
+    if (t < 0) { t += n; *sh = -1; }
+    else if (t >= n) { t -= n; *sh = 1; }
+    if ((n % 2) == 0 && ao == n / 2 && *sh != 0) return 0; /* even grid: unwrapped image only */
+    if (ao != 0 && t == c) return 0;
+    *cn = t;
+    return 1;
+}
+
+/* ------------------------------------------------------- pair potentials ---- */
+typedef struct { int kind, use_radii; float p0, p1, p2, p3, p4, r2cut; } azo_vdw;
+
+#define FCOUL_SCALE 14.3996f /* d_Fcoul_scale, src/main.cu:40 */
+#define SQRTPI_F 1.772453f   /* d_sqrtpi,      src/main.cu:41 */
+
+/* returns F/r, adds the energy; `r` is the "known r" in/out of the *_r variants. */
+static float vdw_feng(const azo_vdw *v, float r2, float *r, int use_coul, float rad1, float rad2,
+                      float *eng)
+{
+    switch (v->kind) {
+    case AZ_VDW_LJ: { /* src/cuVdW.cu:25-47 */
+        float r2i = 1.f / r2;
+        float sr2 = v->p1 * r2i;
+        float sr6 = sr2 * sr2 * sr2;
+        *eng += v->p0 * sr6 * (sr6 - 1.f);
+        return v->p2 * r2i * sr6 * (2.f * sr6 - 1.f);
+    }
+    case AZ_VDW_BUCK: { /* src/cuVdW.cu:69-91 */
+        float r2i = 1.f / r2;
+        float r4i = r2i * r2i;
+        float rr;
+        if (use_coul) { if (*r == 0.f) *r = sqrtf(r2); rr = *r; } else rr = sqrtf(r2);
+        *eng += v->p0 * expf(-rr / v->p1) - v->p2 * r4i * r2i;
+        if (use_coul)
+            return v->p0 * expf(-rr / v->p1) / rr / v->p1 - 6.f * v->p2 * r4i * r4i;
+        /* cu_fe_buck has a stray double constant, src/cuVdW.cu:90 */
+        return (float)((double)(v->p0 * expf(-rr / v->p1) / rr / v->p1) - 6.0 * (double)v->p2 * (double)r4i * (double)r4i);
+    }
+    case AZ_VDW_BMH: { /* src/cuVdW.cu:115-136 */
+        float r2i = 1.f / r2;
+        float r4i = r2i * r2i;
+        float rr;
+        if (use_coul) { if (*r == 0.f) *r = sqrtf(r2); rr = *r; } else rr = sqrtf(r2);
+        *eng += v->p0 * expf(v->p1 * (v->p2 - rr)) - v->p3 * r4i * r2i - v->p4 * r4i * r4i;
+        return v->p0 * v->p1 * expf(v->p1 * (v->p2 - rr)) / rr - 6.f * v->p3 * r4i * r4i - 8.f * v->p4 * r4i * r4i * r2i;
+    }
+    case AZ_VDW_ELIN: { /* src/cuVdW.cu:162-179 */
+        float rr;
+        if (use_coul) { if (*r == 0.f) *r = sqrtf(r2); rr = *r; } else rr = sqrtf(r2);
+        *eng += v->p0 * expf(-rr / v->p1) + v->p2 * rr;
+        return v->p0 * expf(-rr / v->p1) / rr / v->p1 - v->p2 / rr;
+    }
+    case AZ_VDW_EINV: { /* src/cuVdW.cu:200-217 */
+        float rr;
+        if (use_coul) { if (*r == 0.f) *r = sqrtf(r2); rr = *r; } else rr = sqrtf(r2);
+        *eng += v->p0 * expf(-rr / v->p1) - v->p2 / rr;
+        return v->p0 * expf(-rr / v->p1) / rr / v->p1 - v->p2 / rr / r2;
+    }
+    case AZ_VDW_SURK: { /* surk_pot, src/cuVdW.cu:236-257 */
+        float c2ir = v->p1 / (v->p2 * rad1 + v->p3 * rad2);
+        float r_prod = rad1 * rad2;
+        float c1ab2 = r_prod * r_prod * v->p0;
+        float r6 = r2 * r2 * r2;
+        float rr = sqrtf(r2);
+        float ir6 = 1.f / r6;
+        float ir = 1.f / rr;
+        float val = r_prod * ir6 * (c1ab2 * ir - c2ir);
+        *eng += val;
+        return r_prod * ir6 / r2 * (7.f * c1ab2 * ir - 6.f * c2ir);
+    }
+    default:
+        return 0.f;
+    }
+}
+
+typedef struct { int kind; float alpha, daipi2, elC1, elC2, rElec; } azo_elec;
+
+static float coul_feng(const azo_elec *e, float r2, float *r, float chprd, float *eng)
+{
+    switch (e->kind) {
+    case AZ_ELEC_DIRECT: { /* src/cuElec.cu:27-37 */
+        float kqq = chprd * FCOUL_SCALE;
+        *r = sqrtf(r2);
+        *eng += kqq / *r;
+        return kqq / *r / r2;
+    }
+    case AZ_ELEC_EWALD: { /* src/cuElec.cu:94-113 */
+        float kqq = chprd * FCOUL_SCALE;
+        *r = sqrtf(r2);
+        float ar = e->alpha * *r;
+        float erfcar = erfcf(ar);
+        *eng += kqq * erfcar / *r;
+        return kqq / *r / r2 * (erfcar + 2 * ar / SQRTPI_F * expf(-ar * ar));
+    }
+    case AZ_ELEC_FENNEL: { /* src/cuElec.cu:115-134, with its double intermediates */
+        float kqq = chprd * FCOUL_SCALE;
+        *r = sqrtf(r2);
+        double ir = 1.f / *r;
+        float ar = e->alpha * *r;
+        float erfcar = erfcf(ar);
+        *eng += (float)(kqq * (erfcar * ir - e->elC1 + e->elC2 * (*r - e->rElec)));
+        return (float)(kqq * ir * ((erfcar / r2 + e->daipi2 * expf(-ar * ar) * ir) - e->elC2));
+    }
+    default:
+        return 0.f;
+    }
+}
+
+/* Exposed single-pair evaluation for known-answer tests (pair_1 without the geometry). */
+float azo_pair_eval(int vdw_kind, const float *p /*p0..p4*/, float r2cut, int elec_kind,
+                    float alpha, float daipi2, float elC1, float elC2, float rElec, float chprd,
+                    float r2, float r2max, float rad1, float rad2, float *e_vdw, float *e_coul)
+{
+    azo_vdw v = { vdw_kind, vdw_kind == AZ_VDW_SURK, p[0], p[1], p[2], p[3], p[4], r2cut };
+    azo_elec el = { elec_kind, alpha, daipi2, elC1, elC2, rElec };
+    float f = 0.f, r = 0.f;
+    *e_vdw = 0.f; *e_coul = 0.f;
+    if (!(r2 <= r2max)) return 0.f;
+    if (elec_kind) f += coul_feng(&el, r2, &r, chprd, e_coul);
+    if (vdw_kind != AZ_VDW_NONE && r2 <= r2cut) f += vdw_feng(&v, r2, &r, elec_kind != 0, rad1, rad2, e_vdw);
+    if (f > AZ_MX_FRC) f = AZ_MX_FRC; else if (f < -AZ_MX_FRC) f = -AZ_MX_FRC;
+    return f;
+}
+
+/* ---------------------------------------------------------------- state ---- */
+typedef struct azo_state {
+    int n, nspec;
+    float L[3], revL[3], revArea[3];
+    float tSt;
+    float efield[3];
+    float r2max;
+    int nEq, freqEq;
+    int tstat; float teKin;
+    uint64_t seed;
+    /* species */
+    float mass[AZ_MAX_SPECIES], charge[AZ_MAX_SPECIES], rMasshdT[AZ_MAX_SPECIES];
+    int frozen[AZ_MAX_SPECIES];
+    float radA[AZ_MAX_SPECIES], radB[AZ_MAX_SPECIES], mxEng[AZ_MAX_SPECIES];
+    azo_vdw vdw[AZ_MAX_SPECIES][AZ_MAX_SPECIES];
+    float chprod[AZ_MAX_SPECIES][AZ_MAX_SPECIES];
+    azo_elec elec;
+    azo_grid g;
+    int sten[3];
+    /* atoms, current (sorted) order */
+    float *x, *y, *z, *vx, *vy, *vz, *fx, *fy, *fz, *eng, *rad, *fscale;
+    int *type, *id, *cell;
+    float *photons, *uv; /* uv[3*AZ_N_UVECT] */
+    int *first, *count;
+    /* scratch for the sort */
+    float *t_f[11]; int *t_i[2]; int *order;
+    /* step scalars */
+    double engKin, engVdW, engCoul1, engTemp, engElecField;
+    float engKin_f; /* value after after_tscale */
+    double posMom[3], negMom[3];
+    int acPos[AZ_MAX_SPECIES][3], acNeg[AZ_MAX_SPECIES][3];
+    float posMomBuf[AZ_N_MOM][3], negMomBuf[AZ_N_MOM][3];
+    int iMom;
+    float pressure, engTot, engPot;
+    int last_step;
+    long long n_pairs_in_range; /* unique in-cutoff pairs of the last force evaluation */
+} azo_state;
+
+static void *xmalloc(size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) { fprintf(stderr, "azo: oom\n"); abort(); } return p; }
+
+void azo_default_uvects(double *ux, double *uy, double *uz);
+
+azo_state *azo_create(const az_system_desc *d)
+{
+    if (!d || d->n_atoms <= 0 || d->n_species <= 0 || d->n_species > AZ_MAX_SPECIES) return NULL;
+    azo_state *s = (azo_state *)xmalloc(sizeof(azo_state));
+    int n = d->n_atoms;
+    s->n = n; s->nspec = d->n_species;
+    s->L[0] = (float)d->la; s->L[1] = (float)d->lb; s->L[2] = (float)d->lc;
+    for (int a = 0; a < 3; a++) s->revL[a] = 1.f / s->L[a];
+    /* edgeArea / revEdgeArea, src/cuInit.cu:943-946 */
+    { float ax = s->L[1] * s->L[2], ay = s->L[0] * s->L[2], az = s->L[0] * s->L[1];
+      s->revArea[0] = 1.f / ax; s->revArea[1] = 1.f / ay; s->revArea[2] = 1.f / az; }
+    s->tSt = (float)d->timestep;
+    for (int a = 0; a < 3; a++) s->efield[a] = (float)d->efield[a];
+    s->r2max = (float)d->r2_max;
+    s->nEq = d->n_equil; s->freqEq = d->eq_freq;
+    s->tstat = d->tstat_kind; s->teKin = (float)d->t_kin;
+    s->seed = d->seed;
+    for (int i = 0; i < s->nspec; i++) {
+        s->mass[i] = (float)d->species[i].mass;
+        s->charge[i] = (float)d->species[i].charge;
+        s->frozen[i] = d->species[i].frozen;
+        s->rMasshdT[i] = 0.5f * (float)d->timestep / s->mass[i]; /* src/cuInit.cu:779 */
+        s->radA[i] = (float)d->species[i].radA; s->radB[i] = (float)d->species[i].radB;
+        s->mxEng[i] = (float)d->species[i].mxEng;
+        for (int j = 0; j < s->nspec; j++) {
+            const az_vdw_entry *v = &d->vdw[i * s->nspec + j];
+            azo_vdw *o = &s->vdw[i][j];
+            o->kind = v->kind; o->use_radii = v->use_radii;
+            o->p0 = (float)v->p0; o->p1 = (float)v->p1; o->p2 = (float)v->p2;
+            o->p3 = (float)v->p3; o->p4 = (float)v->p4; o->r2cut = (float)v->r2cut;
+            s->chprod[i][j] = (float)(d->species[i].charge * d->species[j].charge); /* src/cuInit.cu:823 */
+        }
+    }
+    s->elec.kind = d->elec_kind; s->elec.alpha = (float)d->alpha; s->elec.daipi2 = (float)d->daipi2;
+    s->elec.elC1 = (float)d->el_c1; s->elec.elC2 = (float)d->el_c2; s->elec.rElec = (float)d->r_real;
+    azo_split_cells(s->L[0], s->L[1], s->L[2], (float)d->cell_size, s->g.cnum, s->g.csize, s->g.crev);
+    s->g.cnYZ = s->g.cnum[1] * s->g.cnum[2];
+    s->g.ncell = s->g.cnum[0] * s->g.cnYZ;
+    { float rc = sqrtf(s->r2max);
+      for (int a = 0; a < 3; a++) s->sten[a] = azo_stencil_half(s->g.cnum[a], s->g.csize[a], rc); }
+
+    float **fa[] = { &s->x, &s->y, &s->z, &s->vx, &s->vy, &s->vz, &s->fx, &s->fy, &s->fz, &s->eng, &s->rad, &s->fscale };
+    for (unsigned k = 0; k < sizeof(fa) / sizeof(fa[0]); k++) *fa[k] = (float *)xmalloc(sizeof(float) * n);
+    for (int k = 0; k < 11; k++) s->t_f[k] = (float *)xmalloc(sizeof(float) * n);
+    s->type = (int *)xmalloc(sizeof(int) * n); s->id = (int *)xmalloc(sizeof(int) * n);
+    s->cell = (int *)xmalloc(sizeof(int) * n); s->order = (int *)xmalloc(sizeof(int) * n);
+    s->t_i[0] = (int *)xmalloc(sizeof(int) * n); s->t_i[1] = (int *)xmalloc(sizeof(int) * n);
+    s->first = (int *)xmalloc(sizeof(int) * (s->g.ncell + 1)); s->count = (int *)xmalloc(sizeof(int) * (s->g.ncell + 1));
+    for (int i = 0; i < n; i++) {
+        s->x[i] = (float)d->xs[i]; s->y[i] = (float)d->ys[i]; s->z[i] = (float)d->zs[i];
+        s->vx[i] = d->vxs ? (float)d->vxs[i] : 0.f; s->vy[i] = d->vys ? (float)d->vys[i] : 0.f; s->vz[i] = d->vzs ? (float)d->vzs[i] : 0.f;
+        s->fx[i] = d->fxs ? (float)d->fxs[i] : 0.f; s->fy[i] = d->fys ? (float)d->fys[i] : 0.f; s->fz[i] = d->fzs ? (float)d->fzs[i] : 0.f;
+        s->type[i] = d->types[i]; s->id[i] = i;
+        s->eng[i] = d->init_engs ? d->init_engs[i] : 0.f;
+        s->rad[i] = d->init_radii ? d->init_radii[i] : 0.577f + seeded_unit(d->seed, (uint32_t)i) * 0.0001f;
+    }
+    if (s->tstat == AZ_TSTAT_RADI) {
+        s->photons = (float *)xmalloc(sizeof(float) * n);
+        for (int i = 0; i < n; i++) s->photons[i] = d->photons ? (float)d->photons[i] : 0.f;
+        s->uv = (float *)xmalloc(sizeof(float) * 3 * AZ_N_UVECT);
+        double *ux = (double *)xmalloc(sizeof(double) * 3 * AZ_N_UVECT), *uy = ux + AZ_N_UVECT, *uz = uy + AZ_N_UVECT;
+        if (d->uvect_x && d->uvect_y && d->uvect_z) {
+            memcpy(ux, d->uvect_x, sizeof(double) * AZ_N_UVECT); memcpy(uy, d->uvect_y, sizeof(double) * AZ_N_UVECT);
+            memcpy(uz, d->uvect_z, sizeof(double) * AZ_N_UVECT);
+        } else azo_default_uvects(ux, uy, uz);
+        for (int k = 0; k < AZ_N_UVECT; k++) { s->uv[3 * k] = (float)ux[k]; s->uv[3 * k + 1] = (float)uy[k]; s->uv[3 * k + 2] = (float)uz[k]; }
+        free(ux);
+    }
+    s->last_step = -1;
+    return s;
+}
+
+void azo_destroy(azo_state *s)
+{
+    if (!s) return;
+    float *fa[] = { s->x, s->y, s->z, s->vx, s->vy, s->vz, s->fx, s->fy, s->fz, s->eng, s->rad, s->fscale, s->photons, s->uv };
+    for (unsigned k = 0; k < sizeof(fa) / sizeof(fa[0]); k++) free(fa[k]);
+    for (int k = 0; k < 11; k++) free(s->t_f[k]);
+    free(s->type); free(s->id); free(s->cell); free(s->order); free(s->t_i[0]); free(s->t_i[1]);
+    free(s->first); free(s->count);
+    free(s);
+}
+
+/* The 3072 preset unit vectors of read_tstat (src/temperature.cpp:164-223). */
+void azo_default_uvects(double *ux, double *uy, double *uz)
+{
+    const double pi = 3.14159265359, twopi = 2.0 * pi; /* src/const.h:11-12 */
+    const int nTh = 16, nPhi = 32;
+    int k = 0;
+    for (int perm = 0; perm < 3; perm++)
+        for (int i = 0; i < nPhi; i++) {
+            double phi = (double)i / nPhi * twopi;
+            for (int j = 0; j < nTh; j++) {
+                double theta = (double)j / nTh * pi;
+                double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+                double a, b, c; /* (x,y,z) of this variant */
+                if (perm == 0) { c = st; b = sp * ct; a = cp * ct; }        /* z=sin th, y=sin ph cos th, x=cos ph cos th */
+                else if (perm == 1) { b = st; c = sp * ct; a = cp * ct; }   /* y=sin th, z=sin ph cos th, x=cos ph cos th */
+                else { a = st; b = sp * ct; c = cp * ct; }                  /* x=sin th, y=sin ph cos th, z=cos ph cos th */
+                ux[k] = a; uy[k] = b; uz[k] = c;
+                ux[k + 1] = -a; uy[k + 1] = -b; uz[k + 1] = -c;
+                k += 2;
+            }
+        }
+}
+
+/* ------------------------------------------------------------- stage 1 ---- */
+static void put_periodic(azo_state *s, int i)
+{
+    float *c[3] = { &s->x[i], &s->y[i], &s->z[i] };
+    float v[3] = { s->vx[i], s->vy[i], s->vz[i] };
+    int t = s->type[i];
+    float m = s->mass[t];
+    for (int a = 0; a < 3; a++) {
+        int nx = (int)floor((double)*c[a] * (double)s->revL[a]);
+        *c[a] -= (float)((float)nx * s->L[a]);
+        if (*c[a] >= s->L[a]) *c[a] = 0.f;
+        if (nx > 0) { s->acPos[t][a]++; s->posMom[a] += (double)(m * v[a]); }
+        else if (nx < 0) { s->acNeg[t][a]++; s->negMom[a] += (double)(m * (-v[a])); }
+    }
+}
+
+static void stage1(azo_state *s)
+{
+    for (int i = 0; i < s->n; i++) {
+        int t = s->type[i];
+        float q = s->charge[t], h = s->rMasshdT[t];
+        s->vx[i] += h * s->fx[i]; s->vy[i] += h * s->fy[i]; s->vz[i] += h * s->fz[i];
+        if (!s->frozen[t]) {
+            s->x[i] += s->vx[i] * s->tSt; s->y[i] += s->vy[i] * s->tSt; s->z[i] += s->vz[i] * s->tSt;
+        }
+        put_periodic(s, i);
+        s->cell[i] = azo_cell_index(s->x[i], s->y[i], s->z[i], s->g.crev, s->g.cnum);
+        s->engElecField += (double)(q * (s->x[i] * s->efield[0] + s->y[i] * s->efield[1] + s->z[i] * s->efield[2]));
+        s->fx[i] = -q * s->efield[0]; s->fy[i] = -q * s->efield[1]; s->fz[i] = -q * s->efield[2];
+    }
+}
+
+/* ---------------------------------------------------------------- sort ---- */
+static void sort_atoms(azo_state *s)
+{
+    int n = s->n, nc = s->g.ncell;
+    memset(s->count, 0, sizeof(int) * (nc + 1));
+    for (int i = 0; i < n; i++) s->count[s->cell[i]]++;
+    int acc = 0;
+    for (int c = 0; c < nc; c++) { s->first[c] = acc; acc += s->count[c]; }
+    s->first[nc] = acc;
+    /* canonical order: by cell, then ascending persistent id (insertion into cell ranges) */
+    int *fill = s->t_i[0];
+    memset(fill, 0, sizeof(int) * n);
+    int *cursor = (int *)xmalloc(sizeof(int) * (nc + 1));
+    memcpy(cursor, s->first, sizeof(int) * (nc + 1));
+    for (int i = 0; i < n; i++) s->order[cursor[s->cell[i]]++] = i;
+    free(cursor);
+    for (int c = 0; c < nc; c++) { /* insertion sort by id inside each cell */
+        int b = s->first[c], e = b + s->count[c];
+        for (int k = b + 1; k < e; k++) {
+            int v = s->order[k], kk = k - 1;
+            while (kk >= b && s->id[s->order[kk]] > s->id[v]) { s->order[kk + 1] = s->order[kk]; kk--; }
+            s->order[kk + 1] = v;
+        }
+    }
+    float *src[11] = { s->x, s->y, s->z, s->vx, s->vy, s->vz, s->fx, s->fy, s->fz, s->eng, s->rad };
+    for (int k = 0; k < 11; k++) {
+        for (int j = 0; j < n; j++) s->t_f[k][j] = src[k][s->order[j]];
+        memcpy(src[k], s->t_f[k], sizeof(float) * n);
+    }
+    int *isrc[3] = { s->type, s->id, s->cell };
+    for (int k = 0; k < 3; k++) {
+        for (int j = 0; j < n; j++) s->t_i[0][j] = isrc[k][s->order[j]];
+        memcpy(isrc[k], s->t_i[0], sizeof(int) * n);
+    }
+}
+
+/* -------------------------------------------------------------- forces ---- */
+/* pair_1 (src/cuPairs.cu:117-167) evaluated from atom i's side against atom j whose
+ * cell image is displaced by `sh` (delta = xi - xj - shift, src/cuPairs.cu:19-24).
+ * Full-list evaluation: every unordered pair is seen twice with bitwise-negated delta, so
+ * the per-atom sums equal the reference's f_A += f*delta / f_B -= f*delta. */
+static inline void pair_accum(azo_state *s, int i, int j, const float sh[3],
+                              double *fxi, double *fyi, double *fzi, double *fsc,
+                              double *evdw, double *ecoul, long long *npairs)
+{
+    float dx = s->x[i] - s->x[j] - sh[0];
+    float dy = s->y[i] - s->y[j] - sh[1];
+    float dz = s->z[i] - s->z[j] - sh[2];
+    float r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 <= s->r2max) {
+        float f = 0.f, r = 0.f, ev = 0.f, ec = 0.f;
+        int ti = s->type[i], tj = s->type[j];
+        if (s->elec.kind) f += coul_feng(&s->elec, r2, &r, s->chprod[ti][tj], &ec);
+        const azo_vdw *v = &s->vdw[ti][tj];
+        if (v->kind != AZ_VDW_NONE && r2 <= v->r2cut) {
+            float ra = s->rad[i], rb = s->rad[j];
+            if (v->use_radii && ti == tj) { float lo = ra < rb ? ra : rb, hi = ra < rb ? rb : ra; ra = lo; rb = hi; }
+            f += vdw_feng(v, r2, &r, s->elec.kind != 0, ra, rb, &ev);
+        }
+        if (f > AZ_MX_FRC) f = AZ_MX_FRC; else if (f < -AZ_MX_FRC) f = -AZ_MX_FRC; /* force_autocap */
+        *fxi += (double)(f * dx); *fyi += (double)(f * dy); *fzi += (double)(f * dz);
+        *fsc += fabs((double)(f * dx)) + fabs((double)(f * dy)) + fabs((double)(f * dz));
+        *evdw += 0.5 * (double)ev; *ecoul += 0.5 * (double)ec;
+        (*npairs)++;
+    }
+}
+
+static void forces(azo_state *s)
+{
+    const azo_grid *g = &s->g;
+    double evdw = 0, ecoul = 0;
+    long long npairs = 0;
+    float rc2 = s->r2max;
+    for (int cx = 0; cx < g->cnum[0]; cx++)
+    for (int cy = 0; cy < g->cnum[1]; cy++)
+    for (int cz = 0; cz < g->cnum[2]; cz++) {
+        int c = cx * g->cnYZ + cy * g->cnum[2] + cz;
+        int ib = s->first[c], ie = ib + s->count[c];
+        if (ib == ie) continue;
+        for (int i = ib; i < ie; i++) {
+            double fxi = 0, fyi = 0, fzi = 0, fsc = 0;
+            for (int ox = -s->sten[0]; ox <= s->sten[0]; ox++) {
+                int nx, shx; if (!azo_neighbor(g->cnum[0], cx, ox, &nx, &shx)) continue;
+                int aox = ox < 0 ? -ox : ox; float mx = aox ? (float)(aox - 1) * g->csize[0] : 0.f;
+                for (int oy = -s->sten[1]; oy <= s->sten[1]; oy++) {
+                    int ny, shy; if (!azo_neighbor(g->cnum[1], cy, oy, &ny, &shy)) continue;
+                    int aoy = oy < 0 ? -oy : oy; float my = aoy ? (float)(aoy - 1) * g->csize[1] : 0.f;
+                    for (int oz = -s->sten[2]; oz <= s->sten[2]; oz++) {
+                        int nz, shz; if (!azo_neighbor(g->cnum[2], cz, oz, &nz, &shz)) continue;
+                        int aoz = oz < 0 ? -oz : oz; float mz = aoz ? (float)(aoz - 1) * g->csize[2] : 0.f;
+                        if ((double)mx * mx + (double)my * my + (double)mz * mz > (double)rc2) continue;
+                        int nc = nx * g->cnYZ + ny * g->cnum[2] + nz;
+                        float sh[3] = { (float)shx * s->L[0], (float)shy * s->L[1], (float)shz * s->L[2] };
+                        int jb = s->first[nc], je = jb + s->count[nc];
+                        for (int j = jb; j < je; j++) {
+                            if (j == i) continue;
+                            pair_accum(s, i, j, sh, &fxi, &fyi, &fzi, &fsc, &evdw, &ecoul, &npairs);
+                        }
+                    }
+                }
+            }
+            s->fx[i] += (float)fxi; s->fy[i] += (float)fyi; s->fz[i] += (float)fzi;
+            s->fscale[i] = (float)fsc;
+        }
+    }
+    s->engVdW += evdw; s->engCoul1 += ecoul;
+    s->n_pairs_in_range = npairs / 2;
+}
+
+/* -------------------------------------------------------------- stage 2 ---- */
+static void stage2(azo_state *s)
+{
+    double ke = 0;
+    for (int i = 0; i < s->n; i++) {
+        int t = s->type[i]; float h = s->rMasshdT[t];
+        s->vx[i] += h * s->fx[i]; s->vy[i] += h * s->fy[i]; s->vz[i] += h * s->fz[i];
+        ke += (double)((s->vx[i] * s->vx[i] + s->vy[i] * s->vy[i] + s->vz[i] * s->vz[i]) * s->mass[t]);
+    }
+    s->engKin = 0.5 * ke;
+    s->engKin_f = (float)s->engKin;
+}
+
+/* ----------------------------------------------------------- thermostat ---- */
+#define REV_LIGHT 3.33567e-5f /* src/cuTemp.cu:225 */
+#define NUM_PI 3.14159f       /* src/cuTemp.cu:228 */
+
+static float f3len(const float *v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+static float f3sqr(const float *v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; }
+
+/* get_angled_vector, src/cuTemp.cu:395-453 */
+void azo_angled_vector(const float *invec, float cos_phi, float theta, float *out)
+{
+    float v1[3], v2[3], v3[3];
+    float l1 = f3len(invec);
+    v1[0] = invec[0] / l1; v1[1] = invec[1] / l1; v1[2] = invec[2] / l1;
+    if (v1[0] != 0.f) { v2[1] = 1.f; v2[2] = 1.f; v2[0] = -(v1[1] * v2[1] + v1[2] * v2[2]) / v1[0]; }
+    else if (v1[1] != 0.f) { v2[0] = 1.f; v2[2] = 1.f; v2[1] = -(v1[2] * v2[2]) / v1[1]; }
+    else { v2[0] = 1.f; v2[1] = 0.f; v2[2] = 0.f; }
+    v3[0] = v1[1] * v2[2] - v1[2] * v2[1];
+    v3[1] = -v1[0] * v2[2] + v1[2] * v2[0];
+    v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+    float l2 = f3len(v2), l3 = f3len(v3);
+    for (int a = 0; a < 3; a++) { v2[a] /= l2; v3[a] /= l3; }
+    float sinPhi = sqrtf(1 - cos_phi * cos_phi);
+    float sinTh = sinf(theta), cosTh = cosf(theta);
+    for (int a = 0; a < 3; a++) out[a] = v1[a] * cos_phi + sinPhi * (cosTh * v2[a] + sinTh * v3[a]);
+}
+
+static void tstat_radi(azo_state *s, int step)
+{
+    double teng = 0;
+    for (int i = 0; i < s->n; i++) {
+        int tp = s->type[i];
+        float mass = s->mass[tp];
+        float pe = s->photons[i]; /* sorted index, in-order case of src/cuTemp.cu:715-722 */
+        uint32_t rn[4];
+        philox4x32_10((uint32_t)s->id[i], (uint32_t)step, 0x52414449u /* "RADI" */, 0,
+                      (uint32_t)s->seed, (uint32_t)(s->seed >> 32), rn);
+        /* rn[0] is the burnt draw of src/cuTemp.cu:738 */
+        float v[3] = { s->vx[i], s->vy[i], s->vz[i] };
+        float U = s->eng[i];
+        { /* adsorb_rand_photon, src/cuTemp.cu:484-507 */
+            float v02 = f3sqr(v);
+            const float *u = &s->uv[3 * (rn[1] % AZ_N_UVECT)];
+            float ermc = pe * REV_LIGHT / mass;
+            v[0] += ermc * u[0]; v[1] += ermc * u[1]; v[2] += ermc * u[2];
+            float v12 = f3sqr(v);
+            U += pe + 0.5f * mass * (v02 - v12);
+        }
+        if ((double)U > 1e-4) { /* radiate_photon3, src/cuTemp.cu:631-685 */
+            float u0 = U;
+            float v02 = f3sqr(v);
+            float v0 = sqrtf(v02);
+            float ph_eng = 0.9f * u0;
+            float ermc = ph_eng * REV_LIGHT / mass;
+            float ermcv0 = ermc / v0;
+            float rv[3];
+            if (!(ermcv0 < 1.f)) { /* fix of the uninitialised vector: anti-parallel to v */
+                if (v0 > 0.f) { rv[0] = -v[0] / v0; rv[1] = -v[1] / v0; rv[2] = -v[2] / v0; }
+                else { const float *u = &s->uv[3 * (rn[1] % AZ_N_UVECT)]; rv[0] = u[0]; rv[1] = u[1]; rv[2] = u[2]; }
+            } else {
+                float cos_phi = (float)(rn[2] % 2048u) / 1024.f * (1.f - ermcv0);
+                cos_phi -= 1.f;
+                float theta = (float)(rn[3] % 2048u) / 1024.f * NUM_PI;
+                azo_angled_vector(v, cos_phi, theta, rv);
+            }
+            v[0] += ermc * rv[0]; v[1] += ermc * rv[1]; v[2] += ermc * rv[2];
+            float v12 = f3sqr(v);
+            U -= (ph_eng + 0.5f * mass * (v12 - v02));
+        }
+        s->vx[i] = v[0]; s->vy[i] = v[1]; s->vz[i] = v[2];
+        s->eng[i] = U;
+        float restrE = U < s->mxEng[tp] ? U : s->mxEng[tp];
+        s->rad[i] = s->radA[tp] / (s->radB[tp] - restrE);
+        teng += (double)U;
+    }
+    s->engTemp += teng;
+}
+
+static void apply_tstat(azo_state *s, int step)
+{
+    if (s->nEq && step <= s->nEq && s->freqEq > 0 && (step % s->freqEq) == 0) {
+        if (s->engKin_f != 0.f) { /* temp_scale, src/cuTemp.cu:77-107 */
+            float c = (s->tstat == AZ_TSTAT_RADI) ? 0.25f : 1.f;
+            float k = sqrtf(c * s->teKin / s->engKin_f);
+            for (int i = 0; i < s->n; i++) { s->vx[i] *= k; s->vy[i] *= k; s->vz[i] *= k; }
+        }
+        s->engKin_f = s->teKin; /* after_tscale, src/cuTemp.cu:109-113 */
+        s->engKin = (double)s->teKin;
+    }
+    if (s->tstat == AZ_TSTAT_RADI) tstat_radi(s, step);
+}
+
+/* calc_quantities, src/main.cu:121-162 */
+static void calc_quantities(azo_state *s, int step)
+{
+    float engCoulTot = (float)s->engCoul1;
+    s->engPot = engCoulTot + (float)s->engVdW;
+    s->engTot = s->engPot + s->engKin_f;
+    float pm[3] = { (float)s->posMom[0], (float)s->posMom[1], (float)s->posMom[2] };
+    float nm[3] = { (float)s->negMom[0], (float)s->negMom[1], (float)s->negMom[2] };
+    if (step >= AZ_N_MOM - 1) {
+        int i = s->iMom;
+        float k = (float)(2.f * 1.58e6 / (double)(s->tSt * (float)(AZ_N_MOM - 1)));
+        float pp[3], np[3];
+        for (int a = 0; a < 3; a++) {
+            pp[a] = k * (pm[a] - s->posMomBuf[i][a]) * s->revArea[a];
+            np[a] = k * (nm[a] - s->negMomBuf[i][a]) * s->revArea[a];
+        }
+        i--; if (i < 0) i = AZ_N_MOM - 1;
+        for (int a = 0; a < 3; a++) { s->posMomBuf[i][a] = pm[a]; s->negMomBuf[i][a] = nm[a]; }
+        s->iMom++; if (s->iMom >= AZ_N_MOM) s->iMom = 0;
+        s->pressure = (pp[0] + pp[1] + pp[2] + np[0] + np[1] + np[2]) / 6.f;
+    } else {
+        for (int a = 0; a < 3; a++) { s->posMomBuf[step][a] = pm[a]; s->negMomBuf[step][a] = nm[a]; }
+    }
+}
+
+/* One iteration of the loop body src/main.cu:281-383 */
+int azo_step(azo_state *s, int first_step, int nsteps)
+{
+    for (int k = 0; k < nsteps; k++) {
+        int step = first_step + k;
+        s->engCoul1 = 0; s->engVdW = 0; s->engTemp = 0; s->engElecField = 0; /* reset_quantities */
+        stage1(s);
+        sort_atoms(s);
+        forces(s);
+        stage2(s);
+        apply_tstat(s, step);
+        calc_quantities(s, step);
+        s->last_step = step;
+    }
+    return 0;
+}
+
+/* Force evaluation only, on the current positions (bins + sorts first; no integration).
+ * Used to pin the oracle against the reference's serial build and by the parity tests. */
+int azo_forces_only(azo_state *s)
+{
+    s->engCoul1 = 0; s->engVdW = 0;
+    for (int i = 0; i < s->n; i++) {
+        s->cell[i] = azo_cell_index(s->x[i], s->y[i], s->z[i], s->g.crev, s->g.cnum);
+        int t = s->type[i]; float q = s->charge[t];
+        s->fx[i] = -q * s->efield[0]; s->fy[i] = -q * s->efield[1]; s->fz[i] = -q * s->efield[2];
+    }
+    sort_atoms(s);
+    forces(s);
+    return 0;
+}
+
+int azo_stats(azo_state *s, az_stats *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->step = s->last_step; o->n_atoms_total = s->n;
+    o->engTot = s->engTot; o->engKin = s->engKin_f; o->engVdW = (float)s->engVdW;
+    o->engCoul1 = (float)s->engCoul1; o->engCoul2 = 0.f; o->engTemp = (float)s->engTemp;
+    o->engElecField = (float)s->engElecField; o->engPot = s->engPot;
+    for (int a = 0; a < 3; a++) { o->posMom[a] = (float)s->posMom[a]; o->negMom[a] = (float)s->negMom[a]; }
+    o->pressure = s->pressure;
+    for (int t = 0; t < s->nspec; t++) for (int a = 0; a < 3; a++) {
+        o->specAcBoxPos[t][a] = s->acPos[t][a]; o->specAcBoxNeg[t][a] = s->acNeg[t][a];
+    }
+    o->engKin_d = s->engKin; o->engVdW_d = s->engVdW; o->engCoul1_d = s->engCoul1; o->engTemp_d = s->engTemp;
+    return 0;
+}
+
+int azo_download(azo_state *s, az_atoms_out *o, int order)
+{
+    if (o->n_atoms < s->n) return AZ_ERR_INVALID;
+    for (int i = 0; i < s->n; i++) {
+        int k = (order == AZ_ORDER_ORIGINAL) ? s->id[i] : i;
+        if (o->xs) { o->xs[k] = s->x[i]; o->ys[k] = s->y[i]; o->zs[k] = s->z[i]; }
+        if (o->vxs) { o->vxs[k] = s->vx[i]; o->vys[k] = s->vy[i]; o->vzs[k] = s->vz[i]; }
+        if (o->types) o->types[k] = s->type[i];
+        if (o->ids) o->ids[k] = s->id[i];
+        if (o->engs) o->engs[k] = s->eng[i];
+        if (o->radii) o->radii[k] = s->rad[i];
+    }
+    o->n_written = s->n;
+    return 0;
+}
+
+int azo_dump(azo_state *s, az_dump *o)
+{
+    if (o->n_atoms < s->n || o->n_cells < s->g.ncell) return AZ_ERR_INVALID;
+    o->n_atoms = s->n; o->n_cells = s->g.ncell;
+    for (int a = 0; a < 3; a++) { o->cnum[a] = s->g.cnum[a]; o->csize[a] = s->g.csize[a]; o->crev[a] = s->g.crev[a]; }
+    for (int i = 0; i < s->n; i++) {
+        if (o->cell_indexes) o->cell_indexes[i] = s->cell[i];
+        if (o->ids) o->ids[i] = s->id[i];
+        if (o->fx) { o->fx[i] = s->fx[i]; o->fy[i] = s->fy[i]; o->fz[i] = s->fz[i]; }
+        if (o->x) { o->x[i] = s->x[i]; o->y[i] = s->y[i]; o->z[i] = s->z[i]; }
+        if (o->vx) { o->vx[i] = s->vx[i]; o->vy[i] = s->vy[i]; o->vz[i] = s->vz[i]; }
+    }
+    for (int c = 0; c < s->g.ncell; c++) {
+        if (o->first_atom_in_cell) o->first_atom_in_cell[c] = s->first[c];
+        if (o->n_at_in_cell) o->n_at_in_cell[c] = s->count[c];
+    }
+    return 0;
+}
+
+/* per-atom sum of |f*delta| of the last force evaluation (the fp32 tolerance scale) */
+int azo_force_scale(azo_state *s, float *out) { memcpy(out, s->fscale, sizeof(float) * s->n); return 0; }
+long long azo_pairs_in_range(azo_state *s) { return s->n_pairs_in_range; }
+int azo_stencil(azo_state *s, int *out) { out[0] = s->sten[0]; out[1] = s->sten[1]; out[2] = s->sten[2]; return 0; }
+
+/* Minimum-image all-pairs reference (O(N^2), double accumulation) for small systems:
+ * an independent check of the cell-stencil traversal above. */
+int azo_forces_allpairs(azo_state *s, float *fx, float *fy, float *fz, double *evdw_out, double *ecoul_out)
+{
+    double evdw = 0, ecoul = 0; long long np = 0;
+    for (int i = 0; i < s->n; i++) {
+        double ax = 0, ay = 0, az = 0, sc = 0;
+        for (int j = 0; j < s->n; j++) {
+            if (i == j) continue;
+            float sh[3];
+            float d[3] = { s->x[i] - s->x[j], s->y[i] - s->y[j], s->z[i] - s->z[j] };
+            for (int a = 0; a < 3; a++) {
+                float h = 0.5f * s->L[a];
+                sh[a] = d[a] > h ? s->L[a] : (d[a] < -h ? -s->L[a] : 0.f);
+            }
+            pair_accum(s, i, j, sh, &ax, &ay, &az, &sc, &evdw, &ecoul, &np);
+        }
+        int t = s->type[i]; float q = s->charge[t];
+        fx[i] = (float)((double)(-q * s->efield[0]) + ax);
+        fy[i] = (float)((double)(-q * s->efield[1]) + ay);
+        fz[i] = (float)((double)(-q * s->efield[2]) + az);
+    }
+    *evdw_out = evdw; *ecoul_out = ecoul;
+    return 0;
+}
