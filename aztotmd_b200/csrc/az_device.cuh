@@ -5,7 +5,18 @@
 // Coulomb kind) combination is a template parameter and all scalars travel by value in a
 // __grid_constant__ parameter block.
 #pragma once
+#ifdef AZ_EMU
+#include "cuda_emu.h" // tests/emu: host stand-in for the CUDA execution model (test builds only)
+#define AZ_DYN_SMEM(T, name) T* name = (T*)az_emu_dyn_smem()
+#define AZ_LAUNCH(kern, grid, block, smem, stream, ...) \
+    az_emu_launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#else
 #include <cuda_runtime.h>
+#define AZ_DYN_SMEM(T, name) \
+    extern __shared__ __align__(16) unsigned char az_dyn_smem_raw[]; \
+    T* name = reinterpret_cast<T*>(az_dyn_smem_raw)
+#define AZ_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 #include "../../include/aztot_b200.h"
 
@@ -33,7 +44,9 @@ struct AzParams {
     int nspec;
     float L[3], revL[3];
     float tSt;
-    float r2max;
+    float r2max;        // pair gate (md->r2Max)
+    float r2list;       // cell-pair existence radius^2 = (sqrt(r2max)+skin)^2; == r2max when skin == 0
+    float skin;
     float efield[3];
     int has_efield;
     // Coulomb scalars (md->alpha, daipi2, elC1, elC2, rElec; src/cuInit.cu:951-957)
@@ -76,7 +89,13 @@ __device__ __forceinline__ void az_philox(uint32_t c0, uint32_t c1, uint32_t c2,
 // reference forms; 1/x and x/y use the hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of
 // the IEEE division sequence -- inside the 1e-5 relative force tolerance of the parity tests.
 __device__ __forceinline__ float az_rcp(float x) { return __frcp_rn(x); }
+#ifdef AZ_EMU
+__device__ __forceinline__ float az_fast_rcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ float az_fast_exp(float x) { return expf(x); }
+#else
+__device__ __forceinline__ float az_fast_exp(float x) { return __expf(x); }
 __device__ __forceinline__ float az_fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 
 template <int VK>
 __device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r, bool have_r,
@@ -92,25 +111,25 @@ __device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r,
         float r2i = az_fast_rcp(r2);
         float r4i = r2i * r2i;
         if (!have_r) r = sqrtf(r2);
-        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        float ex = v.p0 * az_fast_exp(-r * az_fast_rcp(v.p1));
         eng += ex - v.p2 * r4i * r2i;
         return ex * az_fast_rcp(r) * az_fast_rcp(v.p1) - 6.f * v.p2 * r4i * r4i;
     } else if (VK == AZ_VDW_BMH) { // cu_fe(r)_bmh, src/cuVdW.cu:115-136
         float r2i = az_fast_rcp(r2);
         float r4i = r2i * r2i;
         if (!have_r) r = sqrtf(r2);
-        float ex = v.p0 * __expf(v.p1 * (v.p2 - r));
+        float ex = v.p0 * az_fast_exp(v.p1 * (v.p2 - r));
         eng += ex - v.p3 * r4i * r2i - v.p4 * r4i * r4i;
         return v.p1 * ex * az_fast_rcp(r) - 6.f * v.p3 * r4i * r4i - 8.f * v.p4 * r4i * r4i * r2i;
     } else if (VK == AZ_VDW_ELIN) { // cu_fe(r)_elin, src/cuVdW.cu:162-179
         if (!have_r) r = sqrtf(r2);
-        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        float ex = v.p0 * az_fast_exp(-r * az_fast_rcp(v.p1));
         float ir = az_fast_rcp(r);
         eng += ex + v.p2 * r;
         return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir;
     } else if (VK == AZ_VDW_EINV) { // cu_fe(r)_einv, src/cuVdW.cu:200-217
         if (!have_r) r = sqrtf(r2);
-        float ex = v.p0 * __expf(-r * az_fast_rcp(v.p1));
+        float ex = v.p0 * az_fast_exp(-r * az_fast_rcp(v.p1));
         float ir = az_fast_rcp(r);
         eng += ex - v.p2 * ir;
         return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir * az_fast_rcp(r2);
@@ -158,7 +177,7 @@ __device__ __forceinline__ float az_coul_feng(const AzParams& P, float r2, float
         float ar = P.alpha * r;
         float erfcar = erfcf(ar);
         eng += kqq * erfcar * ir;
-        return kqq * ir * ir * ir * (erfcar + 2.f * ar * (1.f / AZ_SQRTPI) * __expf(-ar * ar));
+        return kqq * ir * ir * ir * (erfcar + 2.f * ar * (1.f / AZ_SQRTPI) * az_fast_exp(-ar * ar));
     } else if (CK == AZ_ELEC_FENNEL) { // fennel, src/cuElec.cu:115-134
         float kqq = chprd * AZ_FCOUL_SCALE;
         float ir = rsqrtf(r2);
@@ -166,7 +185,7 @@ __device__ __forceinline__ float az_coul_feng(const AzParams& P, float r2, float
         float ar = P.alpha * r;
         float erfcar = erfcf(ar);
         eng += kqq * (erfcar * ir - P.elC1 + P.elC2 * (r - P.rElec));
-        return kqq * ir * ((erfcar * ir * ir + P.daipi2 * __expf(-ar * ar) * ir) - P.elC2);
+        return kqq * ir * ((erfcar * ir * ir + P.daipi2 * az_fast_exp(-ar * ar) * ir) - P.elC2);
     }
     return 0.f;
 }

@@ -1,0 +1,635 @@
+// az_engine.cu -- the C ABI of include/aztot_b200.h: engine life cycle, the per-step launch
+// sequence and the host<->device plumbing.  This file replaces the reference's host->device seam
+// (init_cudaMD src/cuInit.cu:756-1199, the loop body src/main.cu:281-383, iter_fastCellList
+// src/cuPairs.cu:2519-2568, apply_tstat src/cuTemp.cu:775-803, md_to_host src/cuInit.cu:1212-1261,
+// free_device_md src/cuInit.cu:1263-1373).  There is no CPU fallback: without a CUDA device
+// az_engine_create fails with AZ_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "az_engine.h"
+
+// ----------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+#define AZ_SET_ERR(e, ...)                                   \
+    do {                                                     \
+        char buf_[512];                                      \
+        snprintf(buf_, sizeof(buf_), __VA_ARGS__);           \
+        if (e) (e)->err = buf_; else g_create_error = buf_;  \
+    } while (0)
+
+#define AZ_CUDA(e, call)                                                                       \
+    do {                                                                                       \
+        cudaError_t err_ = (call);                                                             \
+        if (err_ != cudaSuccess) {                                                             \
+            AZ_SET_ERR(e, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, __LINE__); \
+            return AZ_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static void host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// The 3072 preset photon directions of read_tstat (src/temperature.cpp:164-223): three axis
+// permutations x 32 azimuths x 16 polar angles, each followed by its opposite.
+static void default_uvects(float* uv)
+{
+    const double pi = 3.14159265359, twopi = 2.0 * pi; // src/const.h:11-12
+    int k = 0;
+    for (int perm = 0; perm < 3; perm++)
+        for (int i = 0; i < 32; i++) {
+            double phi = (double)i / 32 * twopi;
+            for (int j = 0; j < 16; j++) {
+                double theta = (double)j / 16 * pi;
+                double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+                double a, b, c;
+                if (perm == 0) { c = st; b = sp * ct; a = cp * ct; }
+                else if (perm == 1) { b = st; c = sp * ct; a = cp * ct; }
+                else { a = st; b = sp * ct; c = cp * ct; }
+                uv[3 * k] = (float)a; uv[3 * k + 1] = (float)b; uv[3 * k + 2] = (float)c;
+                uv[3 * k + 3] = (float)-a; uv[3 * k + 4] = (float)-b; uv[3 * k + 5] = (float)-c;
+                k += 2;
+            }
+        }
+}
+
+// split_cells, div_type 1 (src/cuCellList.cu:9-34 as called from src/cuInit.cu:979)
+static void split_cells(const float L[3], float r, int cnum[3], float csize[3], float crev[3])
+{
+    for (int a = 0; a < 3; a++) {
+        int n = (int)floorf(L[a] / r);
+        if (n < 1) n = 1;
+        cnum[a] = n;
+        csize[a] = L[a] / (float)n;
+        crev[a] = (float)n / L[a];
+    }
+}
+
+// largest cell offset whose minimal distance (delt-1)*csize is still inside rc, capped at n/2
+// (cell_dist_int, src/cuCellList.cu:98-132)
+static int stencil_half(int n, float csize, float rc)
+{
+    int s = 1;
+    while ((float)s * csize <= rc && s < n) s++;
+    if (s > n / 2) s = n / 2;
+    return s;
+}
+
+template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
+{
+    AZ_CUDA(e, cudaMalloc(p, (count ? count : 1) * sizeof(T)));
+    AZ_CUDA(e, cudaMemset(*p, 0, (count ? count : 1) * sizeof(T)));
+    e->dev_bytes += (count ? count : 1) * sizeof(T);
+    return AZ_OK;
+}
+#define AZ_ALLOC(e, p, n) do { int rc_ = dev_alloc(e, &(p), (size_t)(n)); if (rc_) return rc_; } while (0)
+
+// ---------------------------------------------------------------------------------------- ABI
+extern "C" int az_abi_version(void) { return AZ_ABI_VERSION; }
+
+extern "C" const char* az_last_error(const az_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int az_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static int build_params(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
+{
+    AzParams& P = e->P;
+    memset(&P, 0, sizeof(P));
+    P.n_local = d->n_atoms;
+    P.nspec = d->n_species;
+    P.L[0] = (float)d->la; P.L[1] = (float)d->lb; P.L[2] = (float)d->lc; // src/cuInit.cu:936
+    for (int a = 0; a < 3; a++) {
+        if (!(P.L[a] > 0.f)) { AZ_SET_ERR(e, "box edge %d is not positive", a); return AZ_ERR_INVALID; }
+        P.revL[a] = 1.f / P.L[a];
+    }
+    e->revArea[0] = 1.f / (P.L[1] * P.L[2]); // revEdgeArea, src/cuInit.cu:939-942
+    e->revArea[1] = 1.f / (P.L[0] * P.L[2]);
+    e->revArea[2] = 1.f / (P.L[0] * P.L[1]);
+    P.tSt = (float)d->timestep;
+    P.r2max = (float)d->r2_max;
+    P.skin = (o && o->rebuild_every > 1) ? o->skin : 0.f;
+    if (P.skin < 0.f) { AZ_SET_ERR(e, "negative skin"); return AZ_ERR_INVALID; }
+    float rc = sqrtf(P.r2max);
+    P.r2list = P.skin > 0.f ? (rc + P.skin) * (rc + P.skin) : P.r2max;
+    for (int a = 0; a < 3; a++) P.efield[a] = (float)d->efield[a];
+    P.has_efield = (P.efield[0] != 0.f || P.efield[1] != 0.f || P.efield[2] != 0.f);
+    P.alpha = (float)d->alpha; P.daipi2 = (float)d->daipi2; P.elC1 = (float)d->el_c1; P.elC2 = (float)d->el_c2;
+    P.rElec = (float)d->r_real;
+    for (int i = 0; i < P.nspec; i++) {
+        const az_species& s = d->species[i];
+        P.mass[i] = (float)s.mass;
+        if (!(P.mass[i] > 0.f)) { AZ_SET_ERR(e, "species %d has non-positive mass", i); return AZ_ERR_INVALID; }
+        P.charge[i] = (float)s.charge;
+        P.rMasshdT[i] = 0.5f * (float)d->timestep / P.mass[i]; // src/cuInit.cu:779
+        P.radA[i] = (float)s.radA; P.radB[i] = (float)s.radB; P.mxEng[i] = (float)s.mxEng;
+        P.frozen[i] = s.frozen;
+    }
+    P.tstat = d->tstat_kind;
+    P.teKin = (float)d->t_kin;
+    P.seed_lo = (uint32_t)d->seed; P.seed_hi = (uint32_t)(d->seed >> 32);
+
+    // cell grid (split_cells) and stencil
+    AzGrid& g = P.g;
+    if (!(d->cell_size > 0.0)) { AZ_SET_ERR(e, "cell_list size must be positive (the CUDA path needs 'cell_list')"); return AZ_ERR_INVALID; }
+    split_cells(P.L, (float)d->cell_size, g.n, g.csize, g.crev);
+    float rlist = sqrtf(P.r2list);
+    for (int a = 0; a < 3; a++) {
+        g.sten[a] = stencil_half(g.n[a], g.csize[a], rlist);
+        g.nl[a] = g.n[a]; g.goff[a] = 0; g.dec[a] = 0; g.olo[a] = 0; g.ohi[a] = g.n[a];
+    }
+    long long nc = (long long)g.n[0] * g.n[1] * g.n[2];
+    if (nc > 0x7fffffff / 2) { AZ_SET_ERR(e, "too many cells (%lld)", nc); return AZ_ERR_INVALID; }
+    g.ncell_local = (int)nc;
+    return AZ_OK;
+}
+
+static int pick_pair_config(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
+{
+    const AzGrid& g = e->P.g;
+    int ns = d->n_species;
+    // table of prepared entries (cudaVdW + chProd, src/cuInit.cu:794-904)
+    e->h_table.assign((size_t)ns * ns, AzVdw());
+    bool any_radii = false, all_same = true, any = false;
+    int kind0 = -1;
+    for (int i = 0; i < ns; i++)
+        for (int j = 0; j < ns; j++) {
+            const az_vdw_entry& v = d->vdw[i * ns + j];
+            AzVdw& t = e->h_table[i * ns + j];
+            t.p0 = (float)v.p0; t.p1 = (float)v.p1; t.p2 = (float)v.p2; t.p3 = (float)v.p3; t.p4 = (float)v.p4;
+            t.r2cut = (float)v.r2cut;
+            t.kind = v.kind;
+            t.chprod = (float)(d->species[i].charge * d->species[j].charge); // src/cuInit.cu:823
+            if (v.kind == AZ_VDW_P746) { AZ_SET_ERR(e, "vdw kind p746 exists only in the reference's serial build"); return AZ_ERR_UNSUPPORTED; }
+            if (v.kind < 0 || v.kind > AZ_VDW_SURK) { AZ_SET_ERR(e, "unknown vdw kind %d", v.kind); return AZ_ERR_INVALID; }
+            if (v.kind != AZ_VDW_NONE) {
+                any = true;
+                if (kind0 < 0) kind0 = v.kind; else if (kind0 != v.kind) all_same = false;
+                if (v.kind == AZ_VDW_SURK || v.use_radii) any_radii = true;
+            } else all_same = all_same && false;
+        }
+    if (!any) all_same = false;
+    e->pair_radii = any_radii;
+    e->pair_single = (ns == 1);
+    e->pair_ck = d->elec_kind;
+    if (e->pair_ck < 0 || e->pair_ck > AZ_ELEC_FENNEL) { AZ_SET_ERR(e, "unknown elec kind %d", e->pair_ck); return AZ_ERR_INVALID; }
+    // fast paths: one kind everywhere; everything else goes through the per-pair switch
+    if (all_same && kind0 == AZ_VDW_LJ && e->pair_ck == AZ_ELEC_NONE) e->pair_vk = AZ_VDW_LJ;
+    else if (all_same && kind0 == AZ_VDW_BUCK) { e->pair_vk = AZ_VDW_BUCK; e->pair_single = false; }
+    else if (all_same && kind0 == AZ_VDW_SURK && e->pair_ck == AZ_ELEC_NONE) e->pair_vk = AZ_VDW_SURK;
+    else { e->pair_vk = AZ_VK_MIXED; e->pair_single = false; }
+
+    // CTA shape: a z-run of cells holding about one thread block of atoms
+    double avg = (double)d->n_atoms / (double)g.ncell_local;
+    int zc = (o && o->cells_per_block > 0) ? o->cells_per_block : (int)floor((double)AZ_PAIR_TPB / (avg > 0.05 ? avg : 0.05));
+    int zmax = AZ_PAIR_MAXW - 2 * g.sten[2];
+    if (zmax < 1) { AZ_SET_ERR(e, "cell size too small for the cutoff: z stencil half width %d", g.sten[2]); return AZ_ERR_UNSUPPORTED; }
+    if (zc > zmax) zc = zmax;
+    int onz = g.ohi[2] - g.olo[2];
+    if (zc > onz) zc = onz;
+    if (zc < 1) zc = 1;
+    e->pair_zc = zc;
+    e->pair_nruns = (onz + zc - 1) / zc;
+    e->pair_nblocks = (g.ohi[0] - g.olo[0]) * (g.ohi[1] - g.olo[1]) * e->pair_nruns;
+    double want = (zc + 2 * g.sten[2]) * avg * 3.0 + 64.0;
+    int cap = 512;
+    while (cap < want && cap < 8192) cap *= 2;
+    e->pair_tile_cap = cap;
+    e->pair_smem = (size_t)cap * sizeof(float4) + (e->pair_radii ? (size_t)cap * sizeof(float) : 0);
+    return AZ_OK;
+}
+
+extern "C" int az_engine_create(const az_system_desc* d, const az_cuda_opts* o, az_engine** out)
+{
+    g_create_error.clear();
+    if (!out) { AZ_SET_ERR((az_engine*)0, "out is NULL"); return AZ_ERR_INVALID; }
+    *out = nullptr;
+    if (!d) { AZ_SET_ERR((az_engine*)0, "desc is NULL"); return AZ_ERR_INVALID; }
+    if (d->abi_version != AZ_ABI_VERSION) { AZ_SET_ERR((az_engine*)0, "abi_version %d != %d", d->abi_version, AZ_ABI_VERSION); return AZ_ERR_INVALID; }
+    if (d->n_atoms <= 0 || d->n_species <= 0 || d->n_species > AZ_MAX_SPECIES) { AZ_SET_ERR((az_engine*)0, "bad n_atoms/n_species"); return AZ_ERR_INVALID; }
+    if (!d->xs || !d->ys || !d->zs || !d->types || !d->species || !d->vdw) { AZ_SET_ERR((az_engine*)0, "missing atom/species/vdw arrays"); return AZ_ERR_INVALID; }
+    if (d->tstat_kind == AZ_TSTAT_NOSE) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat is outside the hot path (SURVEY 8f)"); return AZ_ERR_UNSUPPORTED; }
+    if (d->tstat_kind != AZ_TSTAT_NONE && d->tstat_kind != AZ_TSTAT_RADI) { AZ_SET_ERR((az_engine*)0, "unknown thermostat kind"); return AZ_ERR_INVALID; }
+    if (d->tstat_kind == AZ_TSTAT_RADI && !d->photons) { AZ_SET_ERR((az_engine*)0, "radiative thermostat needs photon energies"); return AZ_ERR_INVALID; }
+    for (int i = 0; i < d->n_atoms; i++)
+        if (d->types[i] < 0 || d->types[i] >= d->n_species) { AZ_SET_ERR((az_engine*)0, "atom %d has type %d", i, d->types[i]); return AZ_ERR_INVALID; }
+    int ndev = az_device_count();
+    if (ndev <= 0) { AZ_SET_ERR((az_engine*)0, "no CUDA device (there is no CPU fallback)"); return AZ_ERR_NO_DEVICE; }
+    int dev = o ? o->device : 0;
+    if (dev < 0 || dev >= ndev) { AZ_SET_ERR((az_engine*)0, "device %d out of range (%d devices)", dev, ndev); return AZ_ERR_INVALID; }
+
+    az_engine* e = new az_engine();
+    e->device = dev;
+    int rc = az_engine_init(e, d, o);
+    if (rc != AZ_OK) {
+        g_create_error = e->err;
+        az_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return AZ_OK;
+}
+
+int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
+{
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    AZ_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
+    e->n_sm = prop.multiProcessorCount;
+    e->n = d->n_atoms;
+    e->n_global = d->n_atoms;
+    e->rebuild_every = (o && o->rebuild_every > 1) ? o->rebuild_every : 1;
+    e->n_ranks = (o && o->n_ranks > 1) ? o->n_ranks : 1;
+    e->rank = o ? o->rank : 0;
+    if (e->n_ranks > 1) { AZ_SET_ERR(e, "multi-GPU decomposition: use az_engine_create through the halo build"); return AZ_ERR_UNSUPPORTED; }
+    int rc = build_params(e, d, o);
+    if (rc) return rc;
+    rc = pick_pair_config(e, d, o);
+    if (rc) return rc;
+    e->n_eq = d->n_equil; e->eq_freq = d->eq_freq;
+    e->use_therm = (d->tstat_kind == AZ_TSTAT_RADI) || e->pair_radii;
+
+    AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2 * AZ_N_TIMERS; k++) AZ_CUDA(e, cudaEventCreate(&e->ev[k]));
+
+    const int n = e->n, nc = e->P.g.ncell_local;
+    e->cap = n;
+    for (int k = 0; k < 2; k++) {
+        AZ_ALLOC(e, e->pos[k], n); AZ_ALLOC(e, e->vel[k], n); AZ_ALLOC(e, e->id[k], n);
+        if (e->use_therm) AZ_ALLOC(e, e->therm[k], n);
+    }
+    AZ_ALLOC(e, e->frc, n);
+    AZ_ALLOC(e, e->cellOf, n); AZ_ALLOC(e, e->slotOf, n); AZ_ALLOC(e, e->cellSorted, n); AZ_ALLOC(e, e->keyTmp, n);
+    AZ_ALLOC(e, e->cellCount, nc + 1); AZ_ALLOC(e, e->first, nc + 1);
+    e->n_scan_tiles = (nc + AZ_SCAN_TILE - 1) / AZ_SCAN_TILE;
+    AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
+    e->n_atom_blocks = (n + AZ_TPB - 1) / AZ_TPB;
+    AZ_ALLOC(e, e->partKE, e->n_atom_blocks); AZ_ALLOC(e, e->partU, e->n_atom_blocks);
+    AZ_ALLOC(e, e->partV, e->pair_nblocks); AZ_ALLOC(e, e->partC, e->pair_nblocks);
+    AZ_ALLOC(e, e->sc, 1);
+    AZ_ALLOC(e, e->table, e->h_table.size());
+    AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
+    if (d->tstat_kind == AZ_TSTAT_RADI) {
+        AZ_ALLOC(e, e->photons, n); AZ_ALLOC(e, e->uv, 3 * AZ_N_UVECT);
+        std::vector<float> ph(n);
+        for (int i = 0; i < n; i++) ph[i] = (float)d->photons[i]; // src/cuTemp.cu:24-33
+        AZ_CUDA(e, cudaMemcpy(e->photons, ph.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+        std::vector<float> uv(3 * AZ_N_UVECT);
+        if (d->uvect_x && d->uvect_y && d->uvect_z)
+            for (int k = 0; k < AZ_N_UVECT; k++) { uv[3 * k] = (float)d->uvect_x[k]; uv[3 * k + 1] = (float)d->uvect_y[k]; uv[3 * k + 2] = (float)d->uvect_z[k]; }
+        else default_uvects(uv.data());
+        AZ_CUDA(e, cudaMemcpy(e->uv, uv.data(), sizeof(float) * uv.size(), cudaMemcpyHostToDevice));
+    }
+
+    // atoms: double -> float narrowing exactly like src/cuInit.cu:775-779
+    std::vector<float4> hp(n), hv(n), hf(n);
+    std::vector<int> hid(n);
+    std::vector<float2> hth(e->use_therm ? n : 0);
+    for (int i = 0; i < n; i++) {
+        hp[i] = make_float4((float)d->xs[i], (float)d->ys[i], (float)d->zs[i], __int_as_float_host(d->types[i]));
+        hv[i] = make_float4(d->vxs ? (float)d->vxs[i] : 0.f, d->vys ? (float)d->vys[i] : 0.f, d->vzs ? (float)d->vzs[i] : 0.f, 0.f);
+        hf[i] = make_float4(d->fxs ? (float)d->fxs[i] : 0.f, d->fys ? (float)d->fys[i] : 0.f, d->fzs ? (float)d->fzs[i] : 0.f, 0.f);
+        hid[i] = i;
+        if (e->use_therm) {
+            uint32_t r[4];
+            host_philox((uint32_t)i, 0xA5A5A5A5u, 0, 0, (uint32_t)d->seed, (uint32_t)(d->seed >> 32), r);
+            float u = (float)(r[0] % 10000u) / 10000.0f; // rand01(), src/utils.cpp:197-201
+            hth[i].x = d->init_engs ? d->init_engs[i] : 0.f;                      // engs = 0, src/cuTemp.cu:40
+            hth[i].y = d->init_radii ? d->init_radii[i] : 0.577f + u * 0.0001f;   // src/cuTemp.cu:41
+        }
+    }
+    AZ_CUDA(e, cudaMemcpy(e->pos[0], hp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->vel[0], hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->frc, hf.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->id[0], hid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    if (e->use_therm) AZ_CUDA(e, cudaMemcpy(e->therm[0], hth.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    e->cur = 0;
+    e->binned = false;
+    e->since_rebuild = 0;
+    e->last_step = -1;
+    return AZ_OK;
+}
+
+extern "C" void az_engine_destroy(az_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
+    cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
+    cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC);
+    cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
+    for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+// ---------------------------------------------------------------------------------------- step
+namespace {
+struct Timer {
+    az_engine* e; int k;
+    Timer(az_engine* e_, int k_) : e(e_), k(k_) { if (e->profile) cudaEventRecord(e->ev[2 * k], e->stream); }
+    ~Timer()
+    {
+        if (!e->profile) return;
+        cudaEventRecord(e->ev[2 * k + 1], e->stream);
+        cudaEventSynchronize(e->ev[2 * k + 1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]);
+        e->t_ms[k] += ms;
+    }
+};
+} // namespace
+
+#define AZ_COUNT(e, k, nl) do { (e)->launches += (nl); (e)->t_launch[k] += (nl); } while (0)
+
+static int one_step(az_engine* e, int step, bool want_energy)
+{
+    const AzParams& P = e->P;
+    const int n = e->n, nc = P.g.ncell_local;
+    cudaStream_t st = e->stream;
+    const bool rebuild = !e->binned || e->rebuild_every <= 1 || e->since_rebuild + 1 >= e->rebuild_every;
+    const bool radi = (P.tstat == AZ_TSTAT_RADI);
+    const bool eq_step = e->n_eq && step <= e->n_eq && e->eq_freq > 0 && (step % e->eq_freq) == 0; // src/cuTemp.cu:777-779
+    const int nb = e->n_atom_blocks;
+    int c = e->cur;
+
+    { // K1: half kick + drift (+ wrap + bin)
+        Timer t(e, AZ_TIMER_INTEGRATE_A);
+        if (P.has_efield) { AZ_LAUNCH(az_k_reset_step, 1, 1, 0, st, e->sc); AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1); }
+        if (rebuild) {
+            AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist
+            AZ_LAUNCH(az_k_integrate_a<true>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+        } else {
+            AZ_LAUNCH(az_k_integrate_a<false>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+        }
+        AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1);
+    }
+    if (rebuild) {
+        {
+            Timer t(e, AZ_TIMER_SCAN);
+            AZ_LAUNCH(az_k_scan_tiles, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum);
+            AZ_LAUNCH(az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum, e->first);
+            AZ_COUNT(e, AZ_TIMER_SCAN, 2);
+        }
+        {
+            Timer t(e, AZ_TIMER_SORT);
+            AZ_LAUNCH(az_k_sort_keys, nb, AZ_TPB, 0, st, n, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
+            if (e->use_therm)
+                AZ_LAUNCH(az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
+                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted);
+            else
+                AZ_LAUNCH(az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
+                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted);
+            AZ_COUNT(e, AZ_TIMER_SORT, 2);
+        }
+        c = e->cur = 1 - c; // refresh_arrays (src/cuSort.cu:74-100): host-side ping-pong
+        e->binned = true;
+        e->since_rebuild = 0;
+    } else {
+        e->since_rebuild++;
+    }
+    { // K4: pair forces
+        Timer t(e, AZ_TIMER_PAIR);
+        AzPairArgs A;
+        memset(&A, 0, sizeof(A));
+        A.pos = e->pos[c]; A.therm = e->therm[c]; A.cellOfSorted = e->cellSorted; A.first = e->first; A.count = e->cellCount;
+        A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.flags = &e->sc->overflow;
+        A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
+        A.single = e->h_table[0]; A.table = e->table;
+        int rc = az_launch_pair(e, A, want_energy);
+        if (rc) return rc;
+        AZ_COUNT(e, AZ_TIMER_PAIR, 1);
+    }
+    { // K5: half kick + KE (+ thermostat) + derived quantities
+        Timer t(e, AZ_TIMER_INTEGRATE_B);
+        const int drift_mode = rebuild ? 32 : 64;
+        const int emode = want_energy ? 2 : 0;
+        if (!eq_step) {
+            if (radi) {
+                AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                          e->revArea[0], e->revArea[1], e->revArea[2]);
+            } else {
+                AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                          e->revArea[0], e->revArea[1], e->revArea[2]);
+            }
+            AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
+        } else {
+            // equilibration step: the scale factor needs this step's kinetic energy first
+            AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                      e->revArea[0], e->revArea[1], e->revArea[2]);
+            if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
+            else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                      e->revArea[0], e->revArea[1], e->revArea[2]);
+            AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
+        }
+    }
+    e->last_step = step;
+    e->energy_valid = want_energy;
+    return AZ_OK;
+}
+
+extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
+{
+    if (!e) return AZ_ERR_INVALID;
+    if (nsteps < 0) { AZ_SET_ERR(e, "nsteps < 0"); return AZ_ERR_INVALID; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    for (int k = 0; k < nsteps; k++) {
+        // potential energies are reduced on the last step of the call (the one az_engine_stats reports)
+        int rc = one_step(e, first_step + k, e->energy_every_step || k == nsteps - 1);
+        if (rc) return rc;
+    }
+    AZ_CUDA(e, cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_engine_sync(az_engine* e)
+{
+    if (!e) return AZ_ERR_INVALID;
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" void* az_engine_stream(az_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+static int fetch_scalars(az_engine* e, AzScalars* h)
+{
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AZ_CUDA(e, cudaMemcpyAsync(h, e->sc, sizeof(AzScalars), cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaGetLastError());
+    if (h->overflow & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
+    if (h->overflow & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
+    if (h->overflow & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a ghost cell overflowed its halo slots"); return AZ_ERR_OVERFLOW; }
+    return AZ_OK;
+}
+
+extern "C" int az_engine_stats(az_engine* e, az_stats* o)
+{
+    if (!e || !o) return AZ_ERR_INVALID;
+    AzScalars h;
+    int rc = fetch_scalars(e, &h);
+    if (rc) return rc;
+    memset(o, 0, sizeof(*o));
+    o->step = e->last_step;
+    o->n_atoms_total = e->n_global;
+    o->engTot = h.engTot; o->engKin = h.engKin_f; o->engVdW = (float)h.engVdW; o->engCoul1 = (float)h.engCoul1;
+    o->engCoul2 = 0.f; o->engTemp = (float)h.engTemp; o->engElecField = (float)h.engElecField; o->engPot = h.engPot;
+    for (int a = 0; a < 3; a++) { o->posMom[a] = (float)h.posMom[a]; o->negMom[a] = (float)h.negMom[a]; }
+    o->pressure = h.pressure;
+    for (int t = 0; t < e->P.nspec; t++)
+        for (int a = 0; a < 3; a++) { o->specAcBoxPos[t][a] = h.acPos[t][a]; o->specAcBoxNeg[t][a] = h.acNeg[t][a]; }
+    o->engKin_d = h.engKin; o->engVdW_d = h.engVdW; o->engCoul1_d = h.engCoul1; o->engTemp_d = h.engTemp;
+    return AZ_OK;
+}
+
+// wrap one coordinate into [0, L) the way put_periodic does (used for downloads between rebuilds)
+static float wrap_host(float x, float L, float revL)
+{
+    int n = (int)floor((double)x * (double)revL);
+    x -= (float)n * L;
+    if (x >= L) x = 0.f;
+    return x;
+}
+
+extern "C" int az_engine_download(az_engine* e, az_atoms_out* o, int order)
+{
+    if (!e || !o) return AZ_ERR_INVALID;
+    if (o->n_atoms < e->n) { AZ_SET_ERR(e, "output capacity %d < %d atoms", o->n_atoms, e->n); return AZ_ERR_INVALID; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    const int n = e->n, c = e->cur;
+    std::vector<float4> hp(n), hv(n);
+    std::vector<int> hid(n);
+    std::vector<float2> hth(e->use_therm ? n : 0);
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaMemcpy(hp.data(), e->pos[c], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    AZ_CUDA(e, cudaMemcpy(hv.data(), e->vel[c], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    AZ_CUDA(e, cudaMemcpy(hid.data(), e->id[c], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (e->use_therm) AZ_CUDA(e, cudaMemcpy(hth.data(), e->therm[c], sizeof(float2) * n, cudaMemcpyDeviceToHost));
+    const bool wrap = e->rebuild_every > 1;
+    for (int i = 0; i < n; i++) {
+        int k = (order == AZ_ORDER_ORIGINAL) ? hid[i] : i;
+        float x = hp[i].x, y = hp[i].y, z = hp[i].z;
+        if (wrap) { x = wrap_host(x, e->P.L[0], e->P.revL[0]); y = wrap_host(y, e->P.L[1], e->P.revL[1]); z = wrap_host(z, e->P.L[2], e->P.revL[2]); }
+        if (o->xs) o->xs[k] = x;
+        if (o->ys) o->ys[k] = y;
+        if (o->zs) o->zs[k] = z;
+        if (o->vxs) o->vxs[k] = hv[i].x;
+        if (o->vys) o->vys[k] = hv[i].y;
+        if (o->vzs) o->vzs[k] = hv[i].z;
+        if (o->types) { int t; memcpy(&t, &hp[i].w, 4); o->types[k] = t; }
+        if (o->ids) o->ids[k] = hid[i];
+        if (o->engs) o->engs[k] = e->use_therm ? hth[i].x : 0.f;
+        if (o->radii) o->radii[k] = e->use_therm ? hth[i].y : 0.f;
+    }
+    o->n_written = n;
+    return AZ_OK;
+}
+
+extern "C" int az_engine_debug_dump(az_engine* e, az_dump* o)
+{
+    if (!e || !o) return AZ_ERR_INVALID;
+    const int n = e->n, nc = e->P.g.ncell_local, c = e->cur;
+    if (o->n_atoms < n || o->n_cells < nc) { AZ_SET_ERR(e, "dump capacity too small (%d atoms, %d cells needed)", n, nc); return AZ_ERR_INVALID; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    o->n_atoms = n; o->n_cells = nc;
+    for (int a = 0; a < 3; a++) { o->cnum[a] = e->P.g.n[a]; o->csize[a] = e->P.g.csize[a]; o->crev[a] = e->P.g.crev[a]; }
+    if (o->cell_indexes) AZ_CUDA(e, cudaMemcpy(o->cell_indexes, e->cellSorted, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (o->first_atom_in_cell) AZ_CUDA(e, cudaMemcpy(o->first_atom_in_cell, e->first, sizeof(int) * nc, cudaMemcpyDeviceToHost));
+    if (o->n_at_in_cell) AZ_CUDA(e, cudaMemcpy(o->n_at_in_cell, e->cellCount, sizeof(int) * nc, cudaMemcpyDeviceToHost));
+    if (o->ids) AZ_CUDA(e, cudaMemcpy(o->ids, e->id[c], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    std::vector<float4> h(n);
+    struct { float4* src; float *x, *y, *z; } sets[3] = { { e->frc, o->fx, o->fy, o->fz }, { e->pos[c], o->x, o->y, o->z }, { e->vel[c], o->vx, o->vy, o->vz } };
+    for (auto& s : sets) {
+        if (!s.x && !s.y && !s.z) continue;
+        AZ_CUDA(e, cudaMemcpy(h.data(), s.src, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) { if (s.x) s.x[i] = h[i].x; if (s.y) s.y[i] = h[i].y; if (s.z) s.z[i] = h[i].z; }
+    }
+    return AZ_OK;
+}
+
+extern "C" int az_engine_upload(az_engine* e, const double* xs, const double* ys, const double* zs,
+                                const double* vxs, const double* vys, const double* vzs)
+{
+    if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    const int n = e->n, c = e->cur;
+    std::vector<float4> hp(n), hv(n);
+    std::vector<int> hid(n);
+    AZ_CUDA(e, cudaMemcpy(hp.data(), e->pos[c], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    AZ_CUDA(e, cudaMemcpy(hid.data(), e->id[c], sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        int k = hid[i]; // slot i currently holds the atom with persistent id k
+        hp[i].x = (float)xs[k]; hp[i].y = (float)ys[k]; hp[i].z = (float)zs[k];
+        hv[i] = make_float4(vxs ? (float)vxs[k] : 0.f, vys ? (float)vys[k] : 0.f, vzs ? (float)vzs[k] : 0.f, 0.f);
+    }
+    AZ_CUDA(e, cudaMemcpy(e->pos[c], hp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->vel[c], hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemset(e->frc, 0, sizeof(float4) * n));
+    e->binned = false;
+    return AZ_OK;
+}
+
+extern "C" int az_engine_profile(az_engine* e, int enable)
+{
+    if (!e) return AZ_ERR_INVALID;
+    e->profile = enable != 0;
+    for (int k = 0; k < AZ_N_TIMERS; k++) { e->t_ms[k] = 0.0; e->t_launch[k] = 0; }
+    return AZ_OK;
+}
+
+extern "C" int az_engine_timers(az_engine* e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS])
+{
+    if (!e) return AZ_ERR_INVALID;
+    for (int k = 0; k < AZ_N_TIMERS; k++) { if (ms_sum) ms_sum[k] = e->t_ms[k]; if (launches) launches[k] = e->t_launch[k]; }
+    return AZ_OK;
+}
+
+extern "C" long long az_engine_launch_count(az_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
+{
+    if (!e || !key) return AZ_ERR_INVALID;
+    if (!strcmp(key, "energy_every_step")) { e->energy_every_step = value != 0.0; return AZ_OK; }
+    AZ_SET_ERR(e, "unknown option '%s'", key);
+    return AZ_ERR_INVALID;
+}
+
+extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
+{
+    if (!e || !o) return AZ_ERR_INVALID;
+    memset(o, 0, sizeof(*o));
+    const AzGrid& g = e->P.g;
+    for (int a = 0; a < 3; a++) { o->cnum[a] = g.n[a]; o->stencil[a] = g.sten[a]; o->csize[a] = g.csize[a]; o->crev[a] = g.crev[a]; }
+    o->n_cells = g.ncell_local; o->n_atoms = e->n;
+    o->pair_blocks = e->pair_nblocks; o->pair_threads = AZ_PAIR_TPB; o->pair_smem_bytes = (int)e->pair_smem;
+    o->pair_zc = e->pair_zc; o->pair_vk = e->pair_vk; o->pair_ck = e->pair_ck;
+    o->n_sm = e->n_sm; o->device_bytes = (long long)e->dev_bytes;
+    return AZ_OK;
+}

@@ -1,0 +1,54 @@
+// az_engine.h -- internal: engine state shared by az_engine.cu and the pair-kernel instantiation units.
+#pragma once
+#include <string>
+#include <vector>
+#include <string.h>
+#include "az_pair.cuh"
+
+static inline float __int_as_float_host(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+struct az_engine {
+    std::string err;
+    int device = 0, n_sm = 0;
+    int n = 0, n_global = 0, cap = 0;
+    int rank = 0, n_ranks = 1;
+    AzParams P;
+    float revArea[3] = { 0, 0, 0 };
+    int n_eq = 0, eq_freq = 0;
+    int rebuild_every = 1, since_rebuild = 0;
+    bool binned = false, use_therm = false, profile = false, energy_every_step = false, energy_valid = false;
+    int last_step = -1;
+    // pair kernel configuration
+    int pair_vk = 0, pair_ck = 0;
+    bool pair_single = false, pair_radii = false;
+    int pair_zc = 1, pair_nruns = 1, pair_nblocks = 1, pair_tile_cap = 512;
+    size_t pair_smem = 0;
+    std::vector<AzVdw> h_table;
+    // device state
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2 * AZ_N_TIMERS] = {};
+    int cur = 0;
+    float4 *pos[2] = { nullptr, nullptr }, *vel[2] = { nullptr, nullptr }, *frc = nullptr;
+    int* id[2] = { nullptr, nullptr };
+    float2* therm[2] = { nullptr, nullptr };
+    int *cellOf = nullptr, *slotOf = nullptr, *cellSorted = nullptr, *keyTmp = nullptr;
+    int *cellCount = nullptr, *first = nullptr, *tileSum = nullptr;
+    int n_scan_tiles = 0, n_atom_blocks = 0;
+    double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
+    AzScalars* sc = nullptr;
+    AzVdw* table = nullptr;
+    float *photons = nullptr, *uv = nullptr;
+    size_t dev_bytes = 0;
+    // accounting
+    long long launches = 0;
+    double t_ms[AZ_N_TIMERS] = {};
+    long long t_launch[AZ_N_TIMERS] = {};
+};
+
+int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
+// launches the pair kernel instantiation chosen at create time (az_pair_inst_*.cu)
+int az_launch_pair(az_engine* e, const AzPairArgs& A, bool energy);
+int az_launch_pair_lj(az_engine* e, const AzPairArgs& A, bool energy);
+int az_launch_pair_buck(az_engine* e, const AzPairArgs& A, bool energy);
+int az_launch_pair_surk(az_engine* e, const AzPairArgs& A, bool energy);
+int az_launch_pair_mixed(az_engine* e, const AzPairArgs& A, bool energy);

@@ -52,9 +52,15 @@ struct AzScalars {
     int iMom;
     float pressure, engTot, engPot;
     int step;
-    int overflow; // sticky error flags
+    int overflow; // sticky error flags: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots
     float tscale_k;
+    unsigned vmax2_bits; // max |v|^2 of the current step (float bits; stale-cell steps only)
+    float drift;         // upper bound of any atom's displacement since the last rebuild
 };
+#define AZ_FLAG_SKIN 1
+#define AZ_FLAG_TILE 2
+#define AZ_FLAG_NAN 4
+#define AZ_FLAG_HALO 8
 
 // ---------------------------------------------------------------------------------------
 // K1: verlet_1stage (src/cuMDfunc.cu:333-518) + put_periodic (:35-106) + count_cell
@@ -67,12 +73,15 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double eF = 0.0;
+    float v2 = 0.f;
     if (i < P.n_local) {
         float4 p = pos[i], v = vel[i], f = frc[i];
         int t = __float_as_int(p.w);
         float h = P.rMasshdT[t];
-        v.x += h * f.x; v.y += h * f.y; v.z += h * f.z;
-        if (!P.frozen[t]) { p.x += v.x * P.tSt; p.y += v.y * P.tSt; p.z += v.z * P.tSt; }
+        // explicit FMAs: what nvcc contracts the reference's `v += rMasshdT * f; x += v * tSt` into
+        v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
+        if (!P.frozen[t]) { p.x = fmaf(v.x, P.tSt, p.x); p.y = fmaf(v.y, P.tSt, p.y); p.z = fmaf(v.z, P.tSt, p.z); }
+        v2 = v.x * v.x + v.y * v.y + v.z * v.z;
         if (BIN) {
             float m = P.mass[t];
             float* pc[3] = { &p.x, &p.y, &p.z };
@@ -101,6 +110,11 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
             eF = (double)(q * (p.x * P.efield[0] + p.y * P.efield[1] + p.z * P.efield[2]));
         }
     }
+    if (!BIN) { // stale cells: bound the drift since the last rebuild by the fastest atom
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));
+        if ((threadIdx.x & 31) == 0 && v2 > 0.f) atomicMax(&sc->vmax2_bits, __float_as_uint(v2));
+    }
     if (P.has_efield) {
         __shared__ double sm[32];
         double v1[1] = { eF };
@@ -117,7 +131,7 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
 #define AZ_SCAN_IPT 8
 #define AZ_SCAN_TILE (AZ_SCAN_TPB * AZ_SCAN_IPT)
 
-__global__ void __launch_bounds__(AZ_SCAN_TPB)
+static __global__ void __launch_bounds__(AZ_SCAN_TPB)
 az_k_scan_tiles(const int* __restrict__ count, int n, int* __restrict__ tileSum)
 {
     int base = blockIdx.x * AZ_SCAN_TILE;
@@ -140,7 +154,7 @@ az_k_scan_tiles(const int* __restrict__ count, int n, int* __restrict__ tileSum)
     }
 }
 
-__global__ void __launch_bounds__(AZ_SCAN_TPB)
+static __global__ void __launch_bounds__(AZ_SCAN_TPB)
 az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ tileSum,
                 int* __restrict__ first /* [n+1] */)
 {
@@ -183,7 +197,7 @@ az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ ti
 // persistent id into its cell segment at the atomicAdd slot (arbitrary order); phase b ranks the
 // atom inside its cell by id (cells hold ~10-20 atoms) and scatters the payload streams, so the
 // within-cell order is canonical (ascending id) whatever the atomics did.
-__global__ void __launch_bounds__(AZ_TPB)
+static __global__ void __launch_bounds__(AZ_TPB)
 az_k_sort_keys(int n, const int* __restrict__ cellOf, const int* __restrict__ slotOf,
                const int* __restrict__ first, const int* __restrict__ id, int* __restrict__ keyTmp)
 {
@@ -301,7 +315,7 @@ az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __r
         float4 v = vel[i], f = frc[i];
         int t = __float_as_int(pos[i].w);
         float h = P.rMasshdT[t];
-        v.x += h * f.x; v.y += h * f.y; v.z += h * f.z;
+        v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
         ke = (double)((v.x * v.x + v.y * v.y + v.z * v.z) * P.mass[t]);
         if (TSTAT) {
             float2 th = therm[i];
@@ -350,8 +364,8 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 
 // Fixed-order reduction of the per-block partials.  mode bits: 1 = KE, 2 = pair energies,
 // 4 = thermal energy, 8 = this is an equilibration T-scale step (computes tscale_k, after_tscale),
-// 16 = calc_quantities (src/main.cu:121-162) and publish.
-__global__ void __launch_bounds__(1024)
+// 16 = calc_quantities (src/main.cu:121-162) and publish, 32 = rebuild step, 64 = stale-cell step.
+static __global__ void __launch_bounds__(1024)
 az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
               const double* __restrict__ partU, int nU, AzScalars* __restrict__ sc,
@@ -364,6 +378,13 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
     if (mode & 4) for (int k = threadIdx.x; k < nU; k += blockDim.x) v[3] += partU[k];
     az_block_sum<4>(v, sm);
     if (threadIdx.x != 0) return;
+    if (mode & 32) { sc->drift = 0.f; sc->vmax2_bits = 0u; } // rebuild step: cells are exact again
+    if (mode & 64) { // stale-cell step: every atom moved by at most vmax*dt
+        sc->drift += sqrtf(__uint_as_float(sc->vmax2_bits)) * P.tSt;
+        sc->vmax2_bits = 0u;
+        if (2.f * sc->drift > P.skin) sc->overflow |= AZ_FLAG_SKIN;
+    }
+    if ((mode & 1) && !(v[0] == v[0])) sc->overflow |= AZ_FLAG_NAN;
     if (mode & 1) { sc->engKin = v[0]; sc->engKin_f = (float)v[0]; }
     if (mode & 2) { sc->engVdW = v[1]; sc->engCoul1 = v[2]; }
     if (mode & 4) sc->engTemp = v[3];
@@ -403,9 +424,9 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
     }
 }
 
-__global__ void az_k_reset_step(AzScalars* sc) { sc->engElecField = 0.0; } // reset_quantities
+static __global__ void az_k_reset_step(AzScalars* sc) { sc->engElecField = 0.0; } // reset_quantities
 
-__global__ void __launch_bounds__(AZ_TPB)
+static __global__ void __launch_bounds__(AZ_TPB)
 az_k_gather_by_id(int n, const int* __restrict__ id, const float4* __restrict__ src, float4* __restrict__ dst)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

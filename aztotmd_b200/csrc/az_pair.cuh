@@ -5,35 +5,36 @@
 // consecutive z-cells of one (x,y) column; its atoms are contiguous in the sorted streams
 // (cell id = x*cnYZ + y*cNumber.z + z, z fastest) and each thread keeps one i-atom in
 // registers.  For every (x,y) neighbour column of the stencil the z-window of cells
-// [z0-S, z0+zc-1+S] is staged once into shared memory as float4 (x,y,z,type) -- because z is
-// the fastest cell index a window is at most a few contiguous pieces of the sorted stream --
-// and every thread sweeps the sub-range of the window that belongs to its own cell's
-// neighbours.  Full neighbour list, no Newton-3 atomics: each unordered pair is evaluated
-// from both sides with a bitwise-negated delta, so per-atom sums equal the reference's
-// f_A += f*delta / atomicAdd(f_B, -f*delta) up to summation order, with no atomics and a
-// deterministic result.  The periodic shift is applied per cell pair exactly like the
-// reference's secShifts (src/cuCellList.cu:209,238): delta = (x_i - x_j) - shift.
+// [z0-Sz, z0+zc-1+Sz] is staged once into shared memory as float4 (x,y,z,type) and swept cell by
+// cell: all lanes of a warp read the same j-atom (shared-memory broadcast), the lane's own
+// cell-pair existence (cell_dist_int / pair_exists_shift, src/cuCellList.cu:98-132,213-240) is a
+// predicate, so the inner loop is warp-uniform and branch-free.  Full neighbour list, no
+// Newton-3 atomics: each unordered pair is evaluated from both sides with a bitwise-negated
+// delta, so per-atom sums equal the reference's f_A += f*delta / atomicAdd(f_B, -f*delta) up to
+// summation order, with no atomics and a deterministic result.  The periodic shift is applied
+// per cell pair exactly like the reference's secShifts (src/cuCellList.cu:209,238):
+// delta = (x_i - x_j) - shift.
 #pragma once
 #include "az_kernels.cuh"
 
 #define AZ_PAIR_TPB 128
-#define AZ_PAIR_MAXW 96      // window entries (zc + 2*Sz) a CTA can index
-#define AZ_PAIR_MAXPIECE AZ_PAIR_MAXW // contiguous pieces of one window (wraps / ghost layers)
+#define AZ_PAIR_MAXW 64 // window entries (zc + 2*Sz) a CTA can index
 
 struct AzPairArgs {
-    const float4* pos;      // sorted positions (+type) of owned and ghost atoms
-    const float2* therm;    // (U, radius) or NULL
-    const int* cellOfSorted;// cell id of sorted atom (owned atoms)
-    const int* first;       // [ncell_local+1]
-    const int* count;       // [ncell_local]
-    float4* frc;            // out
-    double* partV;          // per-CTA energy partials
+    const float4* pos;       // sorted positions (+type) of owned and ghost atoms
+    const float2* therm;     // (U, radius) or NULL
+    const int* cellOfSorted; // local cell id of sorted atom (owned atoms)
+    const int* first;        // [ncell_local+1]
+    const int* count;        // [ncell_local]
+    float4* frc;             // out
+    double* partV;           // per-CTA energy partials
     double* partC;
-    int zc;                 // z-run length per CTA
-    int nruns;              // ceil(owned nz / zc)
-    int tile_cap;           // float4 slots in the dynamic shared tile
-    AzVdw single;           // the only table entry when nspec == 1
-    const AzVdw* table;     // nspec*nspec entries (device memory) otherwise
+    int* flags;              // sticky error flags (AzScalars::overflow)
+    int zc;                  // z-run length per CTA
+    int nruns;               // ceil(owned nz / zc)
+    int tile_cap;            // atoms the dynamic shared tile holds
+    AzVdw single;            // the only table entry when nspec == 1
+    const AzVdw* table;      // nspec*nspec entries (device memory) otherwise
 };
 
 // Unwrapped neighbour coordinate -> storage coordinate + image sign; reference image rule
@@ -42,6 +43,7 @@ __device__ __forceinline__ bool az_neighbor(const AzGrid& g, int a, int cglob, i
 {
     int n = g.n[a];
     int ao = o < 0 ? -o : o;
+    sh = 0; store = 0;
     if (ao > n / 2) return false;
     int u = cglob + o;
     sh = (u < 0) ? -1 : ((u >= n) ? 1 : 0);
@@ -52,22 +54,20 @@ __device__ __forceinline__ bool az_neighbor(const AzGrid& g, int a, int cglob, i
     return true;
 }
 
-template <int VK, int CK, bool SINGLE, bool RADII>
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 __global__ void __launch_bounds__(AZ_PAIR_TPB)
 az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
-    extern __shared__ float4 s_tile[];
-    __shared__ float s_rad[1]; // placeholder to keep layout simple when !RADII
-    __shared__ int s_cs[AZ_PAIR_MAXW + 1];     // prefix of atom counts over window entries
-    __shared__ float s_shz[AZ_PAIR_MAXW];      // z image shift of each window entry
-    __shared__ int s_pc_g[AZ_PAIR_MAXPIECE], s_pc_c[AZ_PAIR_MAXPIECE], s_pc_n[AZ_PAIR_MAXPIECE];
-    __shared__ int s_np;
+    AZ_DYN_SMEM(float4, s_tile);
+    __shared__ int s_cs[AZ_PAIR_MAXW + 1]; // prefix of atom counts over window entries
+    __shared__ int s_g[AZ_PAIR_MAXW];      // global index of the first atom of each window entry
+    __shared__ float s_shz[AZ_PAIR_MAXW];  // z image shift of each window entry
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
     __shared__ double s_red[64];
-    (void)s_rad;
 
     const AzGrid& g = P.g;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     // CTA -> (owned column, z-run)
     const int ony = g.ohi[1] - g.olo[1];
     const int run = blockIdx.x % A.nruns;
@@ -94,12 +94,14 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
         const int i = ib + tid;
         const bool act = i < iEnd;
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
-        int lzi = lz0, ti = 0;
+        int lzi = lz0, ti = 0, rank_i = 0;
         float radi = 0.f;
         if (act) {
             pi = A.pos[i];
             ti = __float_as_int(pi.w);
-            lzi = A.cellOfSorted[i] % g.nl[2];
+            int ci = A.cellOfSorted[i];
+            lzi = ci % g.nl[2];
+            rank_i = i - A.first[ci];
             if (RADII) radi = A.therm[i].y;
         }
         const int gzi = lzi + g.goff[2];
@@ -116,121 +118,114 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                 const int aoy = oy < 0 ? -oy : oy;
                 const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
                 const float mxy2 = mx * mx + my * my;
-                if (mxy2 > P.r2max) continue;
+                if (mxy2 > P.r2list) continue;
                 const float shx = (float)shxi * P.L[0], shy = (float)shyi * P.L[1];
                 const bool centre = (ox == 0 && oy == 0);
                 const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
 
                 __syncthreads(); // previous tile fully consumed; window tables free
-                // ---- window table: entry w <-> unwrapped z = gz0 - Sz + w
+                // ---- window table: entry w <-> unwrapped global z  u = gz0 - Sz + w
                 if (tid < W) {
-                    int u = gz0 - Sz + tid;
-                    int n = g.n[2];
-                    int sh = 0, cnt = 0;
-                    // images beyond one box length cannot be valid neighbours (|o| <= n/2)
-                    if (u < -n || u >= 2 * n) { sh = 0; cnt = 0; }
-                    else {
+                    const int u = gz0 - Sz + tid;
+                    const int n = g.n[2];
+                    int sh = 0, cnt = 0, gi = 0;
+                    if (u >= -n && u < 2 * n) { // farther images are never valid neighbours
                         sh = (u < 0) ? -1 : ((u >= n) ? 1 : 0);
-                        int st = g.dec[2] ? (u - g.goff[2]) : (u - sh * n);
-                        if (st >= 0 && st < g.nl[2]) cnt = A.count[colbase + st];
+                        const int st = g.dec[2] ? (u - g.goff[2]) : (u - sh * n);
+                        if (st >= 0 && st < g.nl[2]) { cnt = A.count[colbase + st]; gi = A.first[colbase + st]; }
                     }
                     s_cs[tid + 1] = cnt;
+                    s_g[tid] = gi;
                     s_shz[tid] = (float)sh * P.L[2];
                 }
-                if (tid == 0) s_cs[0] = 0;
                 __syncthreads();
-                if (tid == 0) {
-                    // prefix + contiguous pieces (consecutive storage z => contiguous in memory)
-                    int acc = 0, np = 0;
-                    int prev_st = -1000000;
-                    for (int w = 0; w < W; w++) {
-                        int cnt = s_cs[w + 1];
-                        int u = gz0 - Sz + w, n = g.n[2];
-                        int sh = (u < 0) ? -1 : ((u >= n) ? 1 : 0);
-                        int st = g.dec[2] ? (u - g.goff[2]) : (u - sh * n);
-                        bool valid = !(u < -n || u >= 2 * n) && st >= 0 && st < g.nl[2];
-                        if (valid && cnt > 0) {
-                            if (np > 0 && st == prev_st + 1 && s_pc_g[np - 1] + s_pc_n[np - 1] == A.first[colbase + st]) {
-                                s_pc_n[np - 1] += cnt;
-                            } else {
-                                s_pc_g[np] = A.first[colbase + st]; s_pc_c[np] = acc; s_pc_n[np] = cnt; np++;
-                            }
-                            prev_st = st;
-                        }
-                        s_cs[w] = acc;
-                        acc += cnt;
+                if (warp == 0) { // inclusive scan of the counts (W <= 64: two items per lane)
+                    int a0 = (lane < W) ? s_cs[lane + 1] : 0;
+                    int a1 = (lane + 32 < W) ? s_cs[lane + 33] : 0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t0 = __shfl_up_sync(0xffffffffu, a0, o);
+                        int t1 = __shfl_up_sync(0xffffffffu, a1, o);
+                        if (lane >= o) { a0 += t0; a1 += t1; }
                     }
-                    s_cs[W] = acc;
-                    s_np = np;
+                    int tot0 = __shfl_sync(0xffffffffu, a0, 31);
+                    if (lane < W) s_cs[lane + 1] = a0;
+                    if (lane + 32 < W) s_cs[lane + 33] = a1 + tot0;
+                    if (lane == 0) s_cs[0] = 0;
                 }
                 __syncthreads();
-                const int tot = s_cs[W];
-                // this lane's sub-range of the window: its cell's z neighbours
-                int lo = 0, hi = 0, selfj = -1;
-                if (act) {
-                    int wl = -1, wh = -1;
-                    for (int oz = -Sz; oz <= Sz; oz++) {
-                        int st, sh;
-                        if (!az_neighbor(g, 2, gzi, oz, st, sh)) continue;
-                        // cell-pair existence: sum of per-axis rmin^2 <= rmax^2 (pair_exists_shift)
-                        int aoz = oz < 0 ? -oz : oz;
-                        float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
-                        if (mxy2 + mz * mz > P.r2max) continue;
-                        int w = (gzi + oz) - (gz0 - Sz);
-                        if (wl < 0) wl = w;
-                        wh = w;
+
+                // ---- stage the window (in chunks of whole cells if it exceeds the tile) and sweep
+                int w0 = 0;
+                while (w0 < W) {
+                    const int base = s_cs[w0];
+                    int w1 = w0;
+                    while (w1 < W && s_cs[w1 + 1] - base <= A.tile_cap) w1++;
+                    if (w1 == w0) { // one cell larger than the tile: report, skip it
+                        if (tid == 0) atomicOr(A.flags, 2);
+                        w0++;
+                        continue;
                     }
-                    if (wl >= 0) { lo = s_cs[wl]; hi = s_cs[wh + 1]; }
-                    if (centre) selfj = s_cs[gzi - (gz0 - Sz)] + (i - A.first[A.cellOfSorted[i]]);
-                }
-                // ---- stage the window in chunks of tile_cap atoms and sweep
-                for (int c0 = 0; c0 < tot; c0 += A.tile_cap) {
-                    if (c0 > 0) __syncthreads();
-                    const int c1 = min(tot, c0 + A.tile_cap);
-                    for (int p = 0; p < s_np; p++) {
-                        int pc = s_pc_c[p], pn = s_pc_n[p], pg = s_pc_g[p];
-                        int a = max(pc, c0), b = min(pc + pn, c1);
-                        for (int k = a + tid; k < b; k += AZ_PAIR_TPB) {
-                            s_tile[k - c0] = A.pos[pg + (k - pc)];
-                            if (RADII) s_tile_rad[k - c0] = A.therm[pg + (k - pc)].y;
+                    for (int w = w0 + warp; w < w1; w += AZ_PAIR_TPB / 32) {
+                        const int b = s_cs[w] - base, cnt = s_cs[w + 1] - s_cs[w], gi = s_g[w];
+                        for (int k = lane; k < cnt; k += 32) {
+                            s_tile[b + k] = A.pos[gi + k];
+                            if (RADII) s_tile_rad[b + k] = A.therm[gi + k].y;
                         }
                     }
                     __syncthreads();
-                    const int jl = max(lo, c0), jh = min(hi, c1);
-                    // window entry of jl, to track the z shift as j advances
-                    int w = 0;
-                    if (jl < jh) { while (s_cs[w + 1] <= jl) w++; }
-                    int wend = (jl < jh) ? s_cs[w + 1] : 0;
-                    float shz = (jl < jh) ? s_shz[w] : 0.f;
-                    for (int j = jl; j < jh; j++) {
-                        while (j >= wend) { w++; wend = s_cs[w + 1]; shz = s_shz[w]; }
-                        const float4 pj = s_tile[j - c0];
-                        const float dx = pi.x - pj.x - shx;
-                        const float dy = pi.y - pj.y - shy;
-                        const float dz = pi.z - pj.z - shz;
-                        const float r2 = dx * dx + dy * dy + dz * dz;
-                        if (r2 <= P.r2max && j != selfj) {
-                            const int tj = __float_as_int(pj.w);
-                            float radj = 0.f;
-                            if (RADII) radj = s_tile_rad[j - c0];
-                            float f;
-                            if (SINGLE) f = az_pair<VK, CK>(P, A.single, r2, radi, radj, true, ev, ec);
-                            else f = az_pair<VK, CK>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, ev, ec);
-                            fx += f * dx; fy += f * dy; fz += f * dz;
+                    for (int w = w0; w < w1; w++) {
+                        const int jb = s_cs[w] - base, je = s_cs[w + 1] - base;
+                        if (jb == je) continue;
+                        // does the cell pair (lane's cell, window entry w) exist?
+                        const int oz = (gz0 - Sz + w) - gzi;
+                        bool valid = false;
+                        if (act) {
+                            int st, sh;
+                            if (az_neighbor(g, 2, gzi, oz, st, sh)) {
+                                const int aoz = oz < 0 ? -oz : oz;
+                                const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+                                valid = (mxy2 + mz * mz <= P.r2list);
+                            }
+                        }
+                        if (!__any_sync(0xffffffffu, valid)) continue;
+                        const float shz = s_shz[w];
+                        const int self = (centre && oz == 0 && valid) ? jb + rank_i : -1;
+                        for (int j = jb; j < je; j++) {
+                            const float4 pj = s_tile[j];
+                            const float dx = pi.x - pj.x - shx;
+                            const float dy = pi.y - pj.y - shy;
+                            const float dz = pi.z - pj.z - shz;
+                            const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); // nvcc's contraction of dx*dx+dy*dy+dz*dz
+                            if (valid && r2 <= P.r2max && j != self) {
+                                const int tj = __float_as_int(pj.w);
+                                float radj = 0.f;
+                                if (RADII) radj = s_tile_rad[j];
+                                float e1 = 0.f, e2 = 0.f;
+                                float f;
+                                if (SINGLE) f = az_pair<VK, CK>(P, A.single, r2, radi, radj, true, e1, e2);
+                                else f = az_pair<VK, CK>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+                                fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+                                if (ENERGY) { ev += e1; ec += e2; }
+                            }
                         }
                     }
+                    w0 = w1;
+                    if (w0 < W) __syncthreads(); // tile is about to be overwritten
                 }
             }
         }
         if (act) {
-            float q = P.charge[ti];
+            const float q = P.charge[ti];
             // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
             A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
             eV += (double)ev; eC += (double)ec;
         }
     }
-    __syncthreads();
-    double vv[2] = { 0.5 * eV, 0.5 * eC }; // every pair was visited from both sides
-    az_block_sum<2>(vv, s_red);
-    if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; }
+    if (ENERGY) {
+        __syncthreads();
+        double vv[2] = { 0.5 * eV, 0.5 * eC }; // every pair was visited from both sides
+        az_block_sum<2>(vv, s_red);
+        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; }
+    }
 }

@@ -1,0 +1,349 @@
+"""Python host side of the B200 engine: system description + thin wrapper over the C ABI.
+
+``System`` mirrors what the reference's host layer (``init_md`` src/sys_init.cpp:1036-1119,
+``read_vdw`` src/vdw.cpp:234-308, ``prepare_elec`` src/elec.cpp:371-406) hands to
+``init_cudaMD``; ``Engine`` calls ``az_engine_*`` of include/aztot_b200.h.  All compute happens in
+the CUDA library: if it is missing, or no GPU is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+
+# unit factors of the reference, src/const.h:16-49
+E_SI = 1.60217733e-19
+M_SCALE = 1.6605402e-27 / (E_SI * 1.0e-12 * 1.0e-12 / 1.0e-10 / 1.0e-10)  # amu -> internal mass
+KB = 1.3806488e-23 / 1.60217733e-19  # eV/K
+PI = 3.14159265359  # src/const.h:11 (not math.pi: the reference's truncated literal)
+SQRTPI = math.sqrt(PI)
+
+
+class AzError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("%s: %s" % (abi.STATUS_NAMES.get(status, str(status)), message))
+        self.status = status
+
+
+@dataclass
+class Species:
+    name: str
+    mass_amu: float
+    charge: float = 0.0
+    frozen: int = 0
+    radA: float = 0.0
+    radB: float = 0.0
+    mxEng: float = 0.0
+
+
+def prepare_vdw(kind: str, rcut: float, params: Sequence[float]) -> dict:
+    """One 'vdw' line -> prepared entry, following read_vdw (src/vdw.cpp:261-299); r/E scales are 1."""
+    k = abi.VDW_BY_NAME[kind]
+    p = list(params) + [0.0] * (5 - len(params))
+    if k == abi.VDW_LJ:  # vdw_scale0 = 4: p0 = 4e; p1 = s^2; p2 = 6*p0 = 24e
+        p[0] = 4.0 * p[0]
+        p[1] = p[1] * p[1]
+        p[2] = 6.0 * p[0]
+    return dict(kind=k, use_radii=1 if k == abi.VDW_SURK else 0, p=p, r2cut=rcut * rcut, rcut=rcut)
+
+
+@dataclass
+class System:
+    """Everything az_system_desc carries, in Python terms (positions in Angstrom, time in ps)."""
+    pos: np.ndarray                 # [N,3] float64
+    types: np.ndarray               # [N] int32
+    box: Sequence[float]            # la, lb, lc
+    species: Sequence[Species]
+    vdw: dict = field(default_factory=dict)   # (i,j) -> prepare_vdw(...) entry; symmetric fill like read_vdw
+    vel: Optional[np.ndarray] = None
+    timestep: float = 0.001
+    cell_size: float = 0.0
+    elec_kind: int = abi.ELEC_NONE
+    r_real: float = 0.0
+    alpha: float = 0.0
+    eps: float = 1.0
+    tstat_kind: int = abi.TSTAT_NONE
+    temperature: float = 0.0
+    n_equil: int = 0
+    eq_freq: int = 0
+    efield: Sequence[float] = (0.0, 0.0, 0.0)
+    photons: Optional[np.ndarray] = None
+    init_radii: Optional[np.ndarray] = None
+    init_engs: Optional[np.ndarray] = None
+    seed: int = 12345
+    n_bonds: int = 0
+
+    def set_vdw(self, i: int, j: int, kind: str, rcut: float, params: Sequence[float]):
+        e = prepare_vdw(kind, rcut, params)
+        self.vdw[(i, j)] = e
+        if e["kind"] != abi.VDW_SURK:
+            self.vdw[(j, i)] = e  # src/vdw.cpp:306-307
+        elif i != j:
+            # the reference leaves [j][i] empty (asymmetric, src/vdw.cpp:292-298,306); a full
+            # neighbour list needs the mirrored entry with k and l swapped so both sides agree
+            m = dict(e)
+            m["p"] = [e["p"][0], e["p"][1], e["p"][3], e["p"][2], e["p"][4]]
+            self.vdw[(j, i)] = m
+
+    # ---- derived quantities exactly as init_md computes them
+    @property
+    def max_r_vdw(self) -> float:
+        return max([v["rcut"] for v in self.vdw.values()], default=0.0)
+
+    @property
+    def charged(self) -> bool:
+        return any(s.charge != 0.0 for s in self.species)
+
+    @property
+    def effective_elec_kind(self) -> int:
+        # read_elec downgrades to 'none' when no species is charged (src/elec.cpp:52-57)
+        return self.elec_kind if self.charged else abi.ELEC_NONE
+
+    @property
+    def r_max(self) -> float:  # src/sys_init.cpp:1059-1072
+        return self.r_real if self.effective_elec_kind else self.max_r_vdw
+
+    @property
+    def deg_free(self) -> int:  # src/sys_init.cpp:1099-1102
+        return 3 * len(self.pos) - self.n_bonds - (1 if self.tstat_kind else 0)
+
+    @property
+    def t_kin(self) -> float:  # src/sys_init.cpp:1106
+        return 0.5 * self.temperature * KB * self.deg_free
+
+    def gauss_velocities(self, seed: int) -> np.ndarray:
+        """Maxwell velocities at `temperature` with zero total momentum (what 'init_vel gaus' asks for;
+        the reference draws them from the time-seeded rand(), src/md_utils.cpp:7-26)."""
+        rng = np.random.default_rng(seed)
+        m = np.array([s.mass_amu * M_SCALE for s in self.species])[self.types]
+        v = rng.standard_normal((len(self.pos), 3)) * np.sqrt(KB * self.temperature / m)[:, None]
+        v -= (v * m[:, None]).sum(0) / m.sum()
+        ke = 0.5 * (m[:, None] * v * v).sum()
+        if ke > 0:
+            v *= math.sqrt(0.5 * KB * self.temperature * 3 * len(self.pos) / ke)
+        return v
+
+
+def photon_energies(n: int, temperature: float, seed: int) -> np.ndarray:
+    """Photon energies with density ~ e^4 exp(-e/kT) on 0..1 eV (what photon_engs samples by
+    bisection of a series CDF from rand01(), src/temperature.cpp:28-89).  Sampled here as a
+    Gamma(5, kT) variate truncated to 1 eV; seeded, unlike the reference."""
+    rng = np.random.default_rng(seed)
+    kt = KB * temperature
+    out = rng.gamma(5.0, kt, size=n)
+    bad = out > 1.0
+    while bad.any():
+        out[bad] = rng.gamma(5.0, kt, size=int(bad.sum()))
+        bad = out > 1.0
+    return out
+
+
+class DescHolder:
+    """Builds az_system_desc and keeps every referenced numpy buffer alive."""
+
+    def __init__(self, s: System):
+        n = len(s.pos)
+        self.n = n
+        self.keep = []
+
+        def dbl(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self.keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_double))
+
+        d = abi.az_system_desc()
+        d.abi_version = abi.AZ_ABI_VERSION
+        d.n_atoms = n
+        d.n_species = len(s.species)
+        pos = np.asarray(s.pos, dtype=np.float64)
+        d.xs, d.ys, d.zs = dbl(pos[:, 0]), dbl(pos[:, 1]), dbl(pos[:, 2])
+        if s.vel is not None:
+            vel = np.asarray(s.vel, dtype=np.float64)
+            d.vxs, d.vys, d.vzs = dbl(vel[:, 0]), dbl(vel[:, 1]), dbl(vel[:, 2])
+        types = np.ascontiguousarray(s.types, dtype=np.int32)
+        self.keep.append(types)
+        d.types = types.ctypes.data_as(C.POINTER(C.c_int))
+        d.la, d.lb, d.lc = [float(x) for x in s.box]
+        ns = len(s.species)
+        sp = (abi.az_species * ns)()
+        for i, x in enumerate(s.species):
+            sp[i].name = x.name.encode()[:7]
+            sp[i].mass = x.mass_amu * M_SCALE  # src/sys_init.cpp read_spec: mass *= m_scale
+            sp[i].charge = x.charge
+            sp[i].frozen = x.frozen
+            sp[i].radA, sp[i].radB, sp[i].mxEng = x.radA, x.radB, x.mxEng
+        self.keep.append(sp)
+        d.species = sp
+        tab = (abi.az_vdw_entry * (ns * ns))()
+        for (i, j), e in s.vdw.items():
+            t = tab[i * ns + j]
+            t.kind, t.use_radii = e["kind"], e["use_radii"]
+            t.p0, t.p1, t.p2, t.p3, t.p4 = e["p"]
+            t.r2cut = e["r2cut"]
+        self.keep.append(tab)
+        d.vdw = tab
+        d.max_r_vdw = s.max_r_vdw
+        ek = s.effective_elec_kind
+        d.elec_kind = ek
+        d.r_real, d.alpha, d.eps = s.r_real, s.alpha, s.eps
+        if ek in (abi.ELEC_EWALD, abi.ELEC_FENNEL):
+            d.daipi2 = 2.0 * s.alpha / SQRTPI
+        if ek == abi.ELEC_FENNEL:  # src/elec.cpp:399-405
+            arc = s.alpha * s.r_real
+            d.el_c1 = math.erfc(arc) / s.r_real
+            d.el_c2 = math.erfc(arc) / (s.r_real * s.r_real) + d.daipi2 * math.exp(-arc * arc) / s.r_real
+        d.tstat_kind = s.tstat_kind
+        d.temperature = s.temperature
+        d.t_kin = s.t_kin
+        if s.tstat_kind == abi.TSTAT_RADI:
+            ph = s.photons if s.photons is not None else photon_energies(n, s.temperature, s.seed)
+            d.photons = dbl(ph)
+        if s.init_radii is not None:
+            a = np.ascontiguousarray(s.init_radii, dtype=np.float32)
+            self.keep.append(a)
+            d.init_radii = a.ctypes.data_as(C.POINTER(C.c_float))
+        if s.init_engs is not None:
+            a = np.ascontiguousarray(s.init_engs, dtype=np.float32)
+            self.keep.append(a)
+            d.init_engs = a.ctypes.data_as(C.POINTER(C.c_float))
+        d.seed = s.seed
+        d.timestep = s.timestep
+        d.n_equil, d.eq_freq = s.n_equil, s.eq_freq
+        d.r2_max = s.r_max * s.r_max
+        d.cell_size = s.cell_size
+        for a in range(3):
+            d.efield[a] = float(s.efield[a])
+        self.desc = d
+
+
+class Engine:
+    """One engine = one GPU.  ``lib`` defaults to the nvcc-built library (no fallback)."""
+
+    def __init__(self, system, *, device: int = 0, rebuild_every: int = 1, skin: float = 0.0,
+                 cells_per_block: int = 0, pair_variant: int = 0, lib=None, opts: Optional[abi.az_cuda_opts] = None):
+        self.lib = lib if lib is not None else abi.load_library()
+        if isinstance(system, System):
+            self._holder = DescHolder(system)
+            desc = self._holder.desc
+        else:  # a ctypes az_system_desc (e.g. from az_deck_desc)
+            self._holder = None
+            desc = system
+        self.n = desc.n_atoms
+        self.nspec = desc.n_species
+        if opts is None:
+            opts = abi.az_cuda_opts()
+            opts.device = device
+            opts.rebuild_every = rebuild_every
+            opts.skin = skin
+            opts.cells_per_block = cells_per_block
+            opts.pair_variant = pair_variant
+        self._h = C.c_void_p()
+        rc = self.lib.az_engine_create(C.byref(desc), C.byref(opts), C.byref(self._h))
+        if rc != abi.AZ_OK:
+            msg = self.lib.az_last_error(None)
+            raise AzError(rc, msg.decode() if msg else "")
+        self.info = abi.az_engine_info_t()
+        self._check(self.lib.az_engine_info(self._h, C.byref(self.info)))
+        self.n_cells = self.info.n_cells
+
+    def _check(self, rc: int):
+        if rc != abi.AZ_OK:
+            msg = self.lib.az_last_error(self._h)
+            raise AzError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.az_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self, first_step: int, nsteps: int = 1):
+        self._check(self.lib.az_engine_step(self._h, first_step, nsteps))
+
+    def sync(self):
+        self._check(self.lib.az_engine_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.az_engine_stream(self._h) or 0)
+
+    def set_option(self, key: str, value: float):
+        self._check(self.lib.az_engine_set_option(self._h, key.encode(), float(value)))
+
+    def stats(self) -> abi.az_stats:
+        st = abi.az_stats()
+        self._check(self.lib.az_engine_stats(self._h, C.byref(st)))
+        return st
+
+    def download(self, order: int = abi.ORDER_ORIGINAL) -> dict:
+        n = self.n
+        out = abi.az_atoms_out()
+        out.n_atoms = n
+        arr = {k: np.zeros(n, dtype=np.float64) for k in ("xs", "ys", "zs", "vxs", "vys", "vzs")}
+        for k, a in arr.items():
+            setattr(out, k, a.ctypes.data_as(C.POINTER(C.c_double)))
+        types = np.zeros(n, dtype=np.int32)
+        ids = np.zeros(n, dtype=np.int32)
+        engs = np.zeros(n, dtype=np.float32)
+        radii = np.zeros(n, dtype=np.float32)
+        out.types = types.ctypes.data_as(C.POINTER(C.c_int))
+        out.ids = ids.ctypes.data_as(C.POINTER(C.c_int))
+        out.engs = engs.ctypes.data_as(C.POINTER(C.c_float))
+        out.radii = radii.ctypes.data_as(C.POINTER(C.c_float))
+        self._check(self.lib.az_engine_download(self._h, C.byref(out), order))
+        k = out.n_written
+        return dict(pos=np.stack([arr["xs"], arr["ys"], arr["zs"]], 1)[:k], vel=np.stack([arr["vxs"], arr["vys"], arr["vzs"]], 1)[:k],
+                    types=types[:k], ids=ids[:k], engs=engs[:k], radii=radii[:k])
+
+    def dump(self) -> dict:
+        n, nc = self.n, self.n_cells
+        d = abi.az_dump()
+        d.n_atoms, d.n_cells = n, nc
+        ints = {k: np.zeros(m, dtype=np.int32) for k, m in (("cell_indexes", n), ("first_atom_in_cell", nc), ("n_at_in_cell", nc), ("ids", n))}
+        for k, a in ints.items():
+            setattr(d, k, a.ctypes.data_as(C.POINTER(C.c_int)))
+        fl = {k: np.zeros(n, dtype=np.float32) for k in ("fx", "fy", "fz", "x", "y", "z", "vx", "vy", "vz")}
+        for k, a in fl.items():
+            setattr(d, k, a.ctypes.data_as(C.POINTER(C.c_float)))
+        self._check(self.lib.az_engine_debug_dump(self._h, C.byref(d)))
+        n2, nc2 = d.n_atoms, d.n_cells
+        return dict(cnum=tuple(d.cnum), csize=tuple(d.csize), crev=tuple(d.crev),
+                    cell=ints["cell_indexes"][:n2], first=ints["first_atom_in_cell"][:nc2], count=ints["n_at_in_cell"][:nc2],
+                    ids=ints["ids"][:n2],
+                    frc=np.stack([fl["fx"], fl["fy"], fl["fz"]], 1)[:n2], pos=np.stack([fl["x"], fl["y"], fl["z"]], 1)[:n2],
+                    vel=np.stack([fl["vx"], fl["vy"], fl["vz"]], 1)[:n2])
+
+    def upload(self, pos: np.ndarray, vel: Optional[np.ndarray] = None):
+        cols = [np.ascontiguousarray(pos[:, a], dtype=np.float64) for a in range(3)]
+        vcols = [np.ascontiguousarray(vel[:, a], dtype=np.float64) for a in range(3)] if vel is not None else [None] * 3
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+        self._check(self.lib.az_engine_upload(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
+
+    def profile(self, enable: bool = True):
+        self._check(self.lib.az_engine_profile(self._h, 1 if enable else 0))
+
+    def timers(self) -> dict:
+        ms = (C.c_double * abi.AZ_N_TIMERS)()
+        ln = (C.c_longlong * abi.AZ_N_TIMERS)()
+        self._check(self.lib.az_engine_timers(self._h, ms, ln))
+        return {nm: dict(ms=ms[k], launches=ln[k]) for k, nm in enumerate(abi.TIMER_NAMES)}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.az_engine_launch_count(self._h))

@@ -242,6 +242,23 @@ int az_engine_profile(az_engine *e, int enable);
 int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
 long long az_engine_launch_count(az_engine *e); /* kernels launched since create */
 
+/* Engine options by name ("energy_every_step": reduce potential energies on every step, not only
+ * on the last step of each az_engine_step call). */
+int az_engine_set_option(az_engine *e, const char *key, double value);
+
+/* Geometry and launch plan chosen at create time (what split_cells / init_cellList decided,
+ * src/cuCellList.cu:9-34,583-636). */
+typedef struct az_engine_info_t {
+    int n_atoms, n_cells;
+    int cnum[3], stencil[3];
+    float csize[3], crev[3];
+    int pair_blocks, pair_threads, pair_smem_bytes, pair_zc, pair_vk, pair_ck;
+    int n_sm;
+    int reserved;
+    long long device_bytes;
+} az_engine_info_t;
+int az_engine_info(az_engine *e, az_engine_info_t *out);
+
 /* ---- deck surface (host side, libaztot_host): the reference's input files ---- */
 typedef struct az_deck az_deck;
 /* Parse atoms.xyz, field.txt, control.txt, cuda.txt from `dir` with the reference's

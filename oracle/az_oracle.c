@@ -433,9 +433,11 @@ static void stage1(azo_state *s)
     for (int i = 0; i < s->n; i++) {
         int t = s->type[i];
         float q = s->charge[t], h = s->rMasshdT[t];
-        s->vx[i] += h * s->fx[i]; s->vy[i] += h * s->fy[i]; s->vz[i] += h * s->fz[i];
+        /* nvcc contracts the reference's `vls += rMasshdT * frs` and `xyz += vls * tSt`
+         * (src/cuMDfunc.cu:352-368) into FMAs; restated explicitly */
+        s->vx[i] = fmaf(h, s->fx[i], s->vx[i]); s->vy[i] = fmaf(h, s->fy[i], s->vy[i]); s->vz[i] = fmaf(h, s->fz[i], s->vz[i]);
         if (!s->frozen[t]) {
-            s->x[i] += s->vx[i] * s->tSt; s->y[i] += s->vy[i] * s->tSt; s->z[i] += s->vz[i] * s->tSt;
+            s->x[i] = fmaf(s->vx[i], s->tSt, s->x[i]); s->y[i] = fmaf(s->vy[i], s->tSt, s->y[i]); s->z[i] = fmaf(s->vz[i], s->tSt, s->z[i]);
         }
         put_periodic(s, i);
         s->cell[i] = azo_cell_index(s->x[i], s->y[i], s->z[i], s->g.crev, s->g.cnum);
@@ -492,7 +494,9 @@ static inline void pair_accum(azo_state *s, int i, int j, const float sh[3],
     float dx = s->x[i] - s->x[j] - sh[0];
     float dy = s->y[i] - s->y[j] - sh[1];
     float dz = s->z[i] - s->z[j] - sh[2];
-    float r2 = dx * dx + dy * dy + dz * dz;
+    /* delta.x*delta.x + delta.y*delta.y + delta.z*delta.z (src/cuPairs.cu:19-24) as nvcc -fmad
+     * compiles it for sm_100a: FMUL(dy,dy), FFMA(dx,dx,.), FFMA(dz,dz,.) */
+    float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
     if (r2 <= s->r2max) {
         float f = 0.f, r = 0.f, ev = 0.f, ec = 0.f;
         int ti = s->type[i], tj = s->type[j];
@@ -559,7 +563,7 @@ static void stage2(azo_state *s)
     double ke = 0;
     for (int i = 0; i < s->n; i++) {
         int t = s->type[i]; float h = s->rMasshdT[t];
-        s->vx[i] += h * s->fx[i]; s->vy[i] += h * s->fy[i]; s->vz[i] += h * s->fz[i];
+        s->vx[i] = fmaf(h, s->fx[i], s->vx[i]); s->vy[i] = fmaf(h, s->fy[i], s->vy[i]); s->vz[i] = fmaf(h, s->fz[i], s->vz[i]);
         ke += (double)((s->vx[i] * s->vx[i] + s->vy[i] * s->vy[i] + s->vz[i] * s->vz[i]) * s->mass[t]);
     }
     s->engKin = 0.5 * ke;

@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+# Build the TEST-ONLY emulator library: the engine + kernel sources compiled by g++ against
+# tests/emu/cuda_emu.h.  Output: tests/emu/_build/libaztot_emu.so (git-ignored).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+SRC="$ROOT/aztotmd_b200/csrc"
+OUT="$HERE/_build"
+mkdir -p "$OUT"
+CXX="${CXX:-g++}"
+FLAGS="-O2 -g -std=c++17 -fPIC -DAZ_EMU -ffp-contract=off -I$HERE -I$SRC -I$ROOT/include -Wall -Wno-unused-function -Wno-unknown-pragmas -Wno-unused-variable"
+pids=()
+for f in az_engine az_pair_inst_lj az_pair_inst_buck az_pair_inst_surk az_pair_inst_mixed ${AZ_EMU_EXTRA:-}; do
+  if [ ! -f "$OUT/$f.o" ] || [ -n "$(find "$SRC" "$HERE" "$ROOT/include" -newer "$OUT/$f.o" \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' \) -print -quit)" ]; then
+    $CXX $FLAGS -x c++ -c "$SRC/$f.cu" -o "$OUT/$f.o" &
+    pids+=($!)
+  fi
+done
+if [ ! -f "$OUT/cuda_emu.o" ] || [ "$HERE/cuda_emu.cpp" -nt "$OUT/cuda_emu.o" ] || [ "$HERE/cuda_emu.h" -nt "$OUT/cuda_emu.o" ]; then
+  $CXX $FLAGS -c "$HERE/cuda_emu.cpp" -o "$OUT/cuda_emu.o" &
+  pids+=($!)
+fi
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+$CXX -shared -o "$OUT/libaztot_emu.so" "$OUT"/*.o -lpthread -lm
+echo "built $OUT/libaztot_emu.so"

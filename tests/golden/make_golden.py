@@ -1,0 +1,85 @@
+"""Generate tests/golden/ref_serial_*.npz by running the reference's OWN serial build
+(oracle/_ref/ref_serial_harness, compiled from /root/reference/src by oracle/build_ref.sh) on
+small synthetic decks.  Run in the development container (the reference tree is not on the GPU
+box); the fixtures are committed.  Each fixture holds the deck parameters, the positions exactly as
+the reference parsed them, and the reference's double-precision forces and energies.
+
+usage: python tests/golden/make_golden.py
+"""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from aztotmd_b200 import decks  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_serial_harness")
+
+
+def read_dump(path):
+    out = {}
+    with open(path, "rb") as f:
+        while True:
+            tag = f.read(8)
+            if len(tag) < 8:
+                break
+            tag = tag.rstrip(b"\0").decode()
+            (n,) = struct.unpack("i", f.read(4))
+            e = np.frombuffer(f.read(32), dtype=np.float64)
+            arrs = [np.frombuffer(f.read(8 * n), dtype=np.float64) for _ in range(9)]
+            out[tag] = dict(engVdW=e[0], engCoul=e[1], engKin=e[2], engTot=e[3], pos=np.stack(arrs[0:3], 1),
+                            vel=np.stack(arrs[3:6], 1), frc=np.stack(arrs[6:9], 1))
+    return out
+
+
+def run(deckdir, nsteps, mode):
+    dump = os.path.join(deckdir, "dump.bin")
+    r = subprocess.run([HARNESS, str(nsteps), mode, dump, "1"], cwd=deckdir, stdin=subprocess.DEVNULL,
+                       capture_output=True, text=True, check=True)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return read_dump(dump), line
+
+
+def main():
+    if not os.path.exists(HARNESS):
+        subprocess.run(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")], check=True)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        # LJ argon, all-pairs path of the serial twin (3 cells per axis: serial falls back to all_pair)
+        d = os.path.join(tmp, "lj5")
+        info = decks.lj_argon_deck(d, 5, nstep=2, init_vel="zero")
+        cases.append(("lj_fcc5_allpairs", d, "full", dict(kind="lj", ncell=5, rc=info["rc"], box=[float(x) for x in info["box"]])))
+        # LJ argon, linked-cell path of the serial twin (4 cells per axis)
+        d = os.path.join(tmp, "lj6")
+        info = decks.lj_argon_deck(d, 6, nstep=2, init_vel="zero")
+        cases.append(("lj_fcc6_celllist", d, "fast", dict(kind="lj", ncell=6, rc=info["rc"], box=[float(x) for x in info["box"]])))
+        # rock salt, Buckingham + damped-shifted-force Coulomb / direct Coulomb
+        for elec in ("fenn", "dir"):
+            d = os.path.join(tmp, "nacl_" + elec)
+            info = decks.nacl_deck(d, 5, rc_vdw=9.0, r_real=9.0, alpha=0.2, elec=elec, init_vel="zero", nstep=2)
+            cases.append(("nacl5_buck_" + elec, d, "full", dict(kind="nacl", ncell=5, elec=elec, rc_vdw=9.0, r_real=9.0,
+                                                                alpha=0.2, box=[float(x) for x in info["box"]])))
+        for name, d, mode, meta in cases:
+            dumps, line = run(d, 0, mode)
+            init = dumps["init"]
+            names = [l.split()[0] for l in open(os.path.join(d, "atoms.xyz")).read().splitlines()[2:] if l.strip()]
+            uniq = []
+            for nm in names:
+                if nm not in uniq:
+                    uniq.append(nm)
+            types = np.array([uniq.index(nm) for nm in names], dtype=np.int32)
+            out = os.path.join(HERE, "ref_serial_%s.npz" % name)
+            np.savez_compressed(out, pos=init["pos"], frc=init["frc"], types=types, engVdW=init["engVdW"],
+                                engCoul=init["engCoul"], meta=np.array(repr(meta)), harness=np.array(line))
+            print(name, line)
+            print("  ->", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,311 @@
+"""Parity cases shared by the emulator tests (CPU, logic) and the GPU tests (the real thing).
+
+Every case builds a seeded synthetic system, advances the CPU oracle (oracle/az_oracle.c) and an
+engine behind the C ABI by the same steps and compares:
+  * cell assignment, per-cell counts, first-atom offsets and the sorted permutation: bit-exact;
+  * per-atom forces: |df| <= FORCE_TOL * sum_j |f_ij * delta_ij| (1e-5 relative, the north-star
+    bound for fp32 after identical ordering);
+  * energies / kinetic energy / thermal energy: ENERGY_TOL relative;
+  * thermostat state (U, radius), velocities, positions: STATE_TOL relative to their scale.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import azt
+from aztotmd_b200 import abi
+from aztotmd_b200.engine import AzError, Engine, Species, System
+
+FORCE_TOL = 1e-5
+ENERGY_TOL = 2e-6
+STATE_TOL = 2e-5
+
+
+def assert_cells_equal(do, de):
+    assert do["cnum"] == de["cnum"]
+    assert do["crev"] == de["crev"] and do["csize"] == de["csize"]
+    assert np.array_equal(do["count"], de["count"]), "nAtInCell differs"
+    assert np.array_equal(do["first"], de["first"]), "firstAtomInCell differs"
+    assert np.array_equal(do["cell"], de["cell"]), "cell index of sorted atoms differs"
+    assert np.array_equal(do["ids"], de["ids"]), "sorted permutation differs"
+
+
+def assert_forces_close(o, do, de, tol=FORCE_TOL):
+    sc = np.maximum(o.force_scale(), 1e-10)
+    err = np.abs(do["frc"].astype(np.float64) - de["frc"].astype(np.float64)).max(1)
+    worst = float((err / sc).max())
+    assert worst <= tol, "force error %.3g of the pair-term scale (tol %.1g)" % (worst, tol)
+
+
+def rel(a, b, floor=1e-12):
+    return abs(a - b) / max(abs(a), abs(b), floor)
+
+
+def assert_stats_close(so, se, tol=ENERGY_TOL, thermo=False, escale=None):
+    floor = escale if escale is not None else max(abs(so.engKin_d), abs(so.engVdW_d), abs(so.engCoul1_d), 1e-6)
+    for k in ("engKin_d", "engVdW_d", "engCoul1_d") + (("engTemp_d",) if thermo else ()):
+        a, b = getattr(so, k), getattr(se, k)
+        assert abs(a - b) <= tol * max(abs(a), floor), "%s: oracle %r engine %r" % (k, a, b)
+    assert abs(so.engTot - se.engTot) <= 4 * tol * max(abs(so.engTot), floor)
+
+
+def run_parity(lib, system: System, nsteps=3, first_step=0, thermo=False, check_state=True, force_tol=FORCE_TOL,
+               energy_tol=ENERGY_TOL, state_tol=STATE_TOL, **engine_kw):
+    o = azt.Oracle(system)
+    e = Engine(system, lib=lib, **engine_kw)
+    try:
+        e.set_option("energy_every_step", 1)
+        for k in range(nsteps):
+            step = first_step + k
+            o.step(step, 1)
+            e.step(step, 1)
+            do, de = o.dump(), e.dump()
+            assert_cells_equal(do, de)
+            assert_forces_close(o, do, de, force_tol)
+            assert_stats_close(o.stats(), e.stats(), energy_tol, thermo=thermo)
+            if check_state:
+                vs = max(float(np.abs(do["vel"]).max()), 1e-6)
+                assert np.abs(do["vel"] - de["vel"]).max() <= state_tol * vs, "velocities differ at step %d" % step
+                assert np.abs(do["pos"] - de["pos"]).max() <= state_tol * max(system.box), "positions differ"
+        if thermo:
+            ao, ae = o.download(abi.ORDER_ORIGINAL), e.download(abi.ORDER_ORIGINAL)
+            us = max(float(np.abs(ao["engs"]).max()), 1e-4)
+            assert np.abs(ao["engs"] - ae["engs"]).max() <= 20 * state_tol * us, "thermal energies differ"
+            assert np.abs(ao["radii"] - ae["radii"]).max() <= 20 * state_tol * float(np.abs(ao["radii"]).max())
+        return o, e
+    except Exception:
+        e.close()
+        raise
+
+
+# ---------------------------------------------------------------------------------------- cases
+def case_lj_basic(lib):
+    o, e = run_parity(lib, azt.lj_system(ncell=(5, 5, 5)), nsteps=3)
+    assert o.pairs_in_range() > 10000
+    e.close()
+
+
+def case_lj_anisotropic_even_odd_grid(lib):
+    s = azt.lj_system(ncell=(6, 5, 7), seed=4)
+    o, e = run_parity(lib, s, nsteps=2)
+    assert tuple(e.info.cnum) == (4, 3, 4)
+    e.close()
+
+
+def case_lj_two_cells_per_axis_no_wrap(lib):
+    # 2 cells per axis: the reference pairs cells 0 and 1 once, with no periodic image
+    # (delt > mx/2 is false, src/cuCellList.cu:111); 1 cell: only intra-cell pairs
+    o, e = run_parity(lib, azt.lj_system(ncell=(4, 4, 4), seed=5), nsteps=2)
+    assert tuple(e.info.cnum) == (2, 2, 2)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(2, 2, 3), seed=6, cell_size=20.0), nsteps=2)
+    assert tuple(e.info.cnum) == (1, 1, 1)
+    e.close()
+
+
+def case_lj_small_cells_wide_stencil(lib):
+    s = azt.lj_system(ncell=(5, 5, 5), seed=7, cell_size=4.3)
+    o, e = run_parity(lib, s, nsteps=2)
+    assert tuple(e.info.cnum) == (6, 6, 6) and tuple(e.info.stencil) == (2, 2, 2)
+    e.close()
+    s = azt.lj_system(ncell=(5, 5, 5), seed=8, cell_size=2.9)  # 9 cells, stencil 3 (case study 2 geometry)
+    o, e = run_parity(lib, s, nsteps=1)
+    assert tuple(e.info.stencil) == (3, 3, 3)
+    e.close()
+
+
+def case_lj_many_atoms_per_cell(lib):
+    # 864 atoms in 1 cell / 8 cells: several i-batches per CTA
+    s = azt.lj_system(ncell=(6, 6, 6), seed=9, cell_size=40.0)
+    o, e = run_parity(lib, s, nsteps=1)
+    assert tuple(e.info.cnum) == (1, 1, 1)
+    e.close()
+    s = azt.lj_system(ncell=(6, 6, 6), seed=9, cell_size=17.0)
+    o, e = run_parity(lib, s, nsteps=1)
+    e.close()
+
+
+def case_ionic(lib, elec, kind="buck"):
+    s = azt.nacl_system(ncell=(5, 5, 5), elec=elec, kind=kind)
+    o, e = run_parity(lib, s, nsteps=2)
+    e.close()
+
+
+def case_ionic_efield_frozen(lib):
+    s = azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_DIRECT)
+    s.efield = (0.01, 0.0, -0.02)
+    s.species[1].frozen = 1
+    o, e = run_parity(lib, s, nsteps=2)
+    so, se = o.stats(), e.stats()
+    assert so.engElecField != 0.0
+    assert abs(so.engElecField - se.engElecField) <= 1e-5 * abs(so.engElecField)
+    # frozen chlorines did not move
+    a0 = np.asarray(s.pos, dtype=np.float32)
+    a1 = e.download(abi.ORDER_ORIGINAL)["pos"]
+    cl = np.asarray(s.types) == 1
+    assert np.array_equal(a1[cl].astype(np.float32), a0[cl])
+    e.close()
+
+
+def case_surk_radiative(lib):
+    # case study 2 in miniature: surk + radiative thermostat; equilibration scaling on steps 2 and 4
+    s = azt.surk_system(n_side=6, n_equil=4, eq_freq=2)
+    o, e = run_parity(lib, s, nsteps=5, thermo=True, state_tol=1e-4)
+    st = e.stats()
+    assert st.engTemp > 0.0
+    e.close()
+
+
+def case_lj_radiative(lib):
+    # case study 1 flavour: LJ + radiative thermostat, zero initial velocities
+    s = azt.lj_system(ncell=(5, 5, 5), seed=11, vel=False, tstat=abi.TSTAT_RADI, temperature=298.0)
+    s.species[0].radA, s.species[0].radB, s.species[0].mxEng = 2.73, 4.731, 0.2
+    o, e = run_parity(lib, s, nsteps=3, thermo=True, state_tol=1e-4)
+    e.close()
+
+
+def case_equilibration_scaling(lib):
+    s = azt.lj_system(ncell=(5, 5, 5), seed=12, n_equil=10, eq_freq=1, temperature=120.0)
+    o, e = run_parity(lib, s, nsteps=3, first_step=1)
+    st = e.stats()
+    assert st.engKin == np.float32(s.t_kin)  # after_tscale: engKin := teKin (src/cuTemp.cu:109-113)
+    e.close()
+
+
+def case_face_crossings_and_pressure(lib):
+    # hot, fast atoms: many face crossings in 24 steps -> counters, cumulative momenta, pressure ring
+    s = azt.lj_system(ncell=(5, 5, 5), seed=13, temperature=3000.0)
+    s.timestep = 0.004
+    a = s.box[0] / 5
+    s.pos = (s.pos + 0.25 * a - 0.1) % np.asarray(s.box)  # park a lattice plane 0.1 A inside each upper face
+    o = azt.Oracle(s)
+    e = Engine(s, lib=lib)
+    o.step(0, 24); e.step(0, 24)
+    so, se = o.stats(), e.stats()
+    assert sum(so.specAcBoxPos[0]) + sum(so.specAcBoxNeg[0]) > 20
+    # trajectories agree to rounding for these few steps, so the integer counters must be equal
+    assert list(so.specAcBoxPos[0]) == list(se.specAcBoxPos[0]) and list(so.specAcBoxNeg[0]) == list(se.specAcBoxNeg[0])
+    for a in range(3):
+        assert abs(so.posMom[a] - se.posMom[a]) <= 1e-4 * max(abs(so.posMom[a]), 1e-3)
+        assert abs(so.negMom[a] - se.negMom[a]) <= 1e-4 * max(abs(so.negMom[a]), 1e-3)
+    assert so.pressure != 0.0 and abs(so.pressure - se.pressure) <= 1e-3 * abs(so.pressure)
+    e.close()
+
+
+def case_rebuild_interval_equals_every_step(lib):
+    """Extension (BASELINE config 3): binning every R steps with a skin gives the same forces and
+    energies as binning every step."""
+    s = azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3)  # 3 cells of 11.4 >= rc + skin
+    e1 = Engine(s, lib=lib)
+    e2 = Engine(s, lib=lib, rebuild_every=5, skin=0.8)
+    o = azt.Oracle(s)
+    for eng in (e1, e2):
+        eng.set_option("energy_every_step", 1)
+    for step in range(8):
+        e1.step(step, 1); e2.step(step, 1); o.step(step, 1)
+        s1, s2 = e1.stats(), e2.stats()
+        assert abs(s1.engVdW_d - s2.engVdW_d) <= 1e-5 * abs(s1.engVdW_d)
+        assert abs(s1.engKin_d - s2.engKin_d) <= 1e-5 * abs(s1.engKin_d)
+    a1, a2 = e1.download(abi.ORDER_ORIGINAL), e2.download(abi.ORDER_ORIGINAL)
+    assert np.abs(a1["pos"] - a2["pos"]).max() < 1e-3 and np.abs(a1["vel"] - a2["vel"]).max() < 1e-3 * np.abs(a1["vel"]).max()
+    ao = o.download(abi.ORDER_ORIGINAL)
+    assert np.abs(ao["pos"] - a2["pos"]).max() < 1e-3
+    e1.close(); e2.close()
+
+
+def case_skin_violation_is_reported(lib):
+    s = azt.lj_system(ncell=(6, 6, 6), seed=15, cell_size=9.3, temperature=5000.0)
+    s.timestep = 0.005
+    e = Engine(s, lib=lib, rebuild_every=50, skin=0.05)
+    e.step(0, 20)
+    try:
+        e.stats()
+    except AzError as err:
+        assert err.status == abi.AZ_ERR_OVERFLOW
+    else:
+        raise AssertionError("skin violation not reported")
+    e.close()
+
+
+def case_download_upload_roundtrip(lib):
+    s = azt.lj_system(ncell=(5, 5, 5), seed=16)
+    o = azt.Oracle(s)
+    e = Engine(s, lib=lib)
+    o.step(0, 2); e.step(0, 2)
+    for order in (abi.ORDER_SORTED, abi.ORDER_ORIGINAL):
+        ao, ae = o.download(order), e.download(order)
+        assert np.array_equal(ao["ids"], ae["ids"]) and np.array_equal(ao["types"], ae["types"])
+        assert np.abs(ao["pos"] - ae["pos"]).max() <= 1e-5 * max(s.box)
+    ae = e.download(abi.ORDER_ORIGINAL)
+    assert np.array_equal(ae["ids"], np.arange(len(s.pos)))
+    # upload the initial state again: the next step must reproduce step 0 of a fresh engine
+    e.upload(np.asarray(s.pos), np.asarray(s.vel))
+    e.step(0, 1)
+    f = Engine(s, lib=lib)
+    f.step(0, 1)
+    d1, d2 = azt.sort_by_id(e.dump()), azt.sort_by_id(f.dump())
+    assert np.array_equal(d1["pos"], d2["pos"]) and np.array_equal(d1["cell"], d2["cell"])
+    assert np.abs(d1["frc"] - d2["frc"]).max() <= 1e-6 * np.abs(d2["frc"]).max()
+    e.close(); f.close()
+
+
+def case_determinism(lib):
+    """No float atomics on the force path: two runs are bitwise identical."""
+    s = azt.nacl_system(ncell=(5, 5, 5))
+    outs = []
+    for _ in range(2):
+        e = Engine(s, lib=lib)
+        e.step(0, 3)
+        d = e.dump()
+        outs.append((d["frc"].copy(), d["pos"].copy(), d["vel"].copy(), e.stats().engVdW_d))
+        e.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+
+
+def case_error_paths(lib):
+    s = azt.lj_system(ncell=(3, 3, 3))
+    s.cell_size = 0.0
+    for mutate, status in ((lambda x: setattr(x, "cell_size", 0.0), abi.AZ_ERR_INVALID),
+                           (lambda x: setattr(x, "tstat_kind", abi.TSTAT_NOSE), abi.AZ_ERR_UNSUPPORTED),
+                           (lambda x: setattr(x, "box", (0.0, 10.0, 10.0)), abi.AZ_ERR_INVALID)):
+        t = azt.lj_system(ncell=(3, 3, 3))
+        mutate(t)
+        try:
+            Engine(t, lib=lib)
+        except AzError as err:
+            assert err.status == status, (err.status, status)
+        else:
+            raise AssertionError("expected failure")
+    t = azt.lj_system(ncell=(3, 3, 3))
+    t.types = t.types.copy(); t.types[5] = 3
+    try:
+        Engine(t, lib=lib)
+    except AzError as err:
+        assert err.status == abi.AZ_ERR_INVALID
+    else:
+        raise AssertionError("expected failure")
+
+
+ALL_CASES = [
+    ("lj_basic", case_lj_basic),
+    ("lj_anisotropic_grid", case_lj_anisotropic_even_odd_grid),
+    ("lj_tiny_grids", case_lj_two_cells_per_axis_no_wrap),
+    ("lj_wide_stencil", case_lj_small_cells_wide_stencil),
+    ("lj_many_atoms_per_cell", case_lj_many_atoms_per_cell),
+    ("ionic_buck_dsf", lambda lib: case_ionic(lib, abi.ELEC_FENNEL)),
+    ("ionic_buck_direct", lambda lib: case_ionic(lib, abi.ELEC_DIRECT)),
+    ("ionic_buck_ewald_real", lambda lib: case_ionic(lib, abi.ELEC_EWALD)),
+    ("ionic_buck_nocoul", lambda lib: case_ionic(lib, abi.ELEC_NONE)),
+    ("ionic_mixed_table_dsf", lambda lib: case_ionic(lib, abi.ELEC_FENNEL, kind="mixed")),
+    ("ionic_efield_frozen", case_ionic_efield_frozen),
+    ("surk_radiative_equil", case_surk_radiative),
+    ("lj_radiative", case_lj_radiative),
+    ("equilibration_scaling", case_equilibration_scaling),
+    ("face_crossings_pressure", case_face_crossings_and_pressure),
+    ("rebuild_interval", case_rebuild_interval_equals_every_step),
+    ("skin_violation", case_skin_violation_is_reported),
+    ("download_upload", case_download_upload_roundtrip),
+    ("determinism", case_determinism),
+    ("error_paths", case_error_paths),
+]

@@ -1,0 +1,211 @@
+"""Pin the CPU oracle (oracle/az_oracle.c) before anything trusts it.
+
+The reference ships no golden vectors, so the oracle is pinned against
+  (a) forces/energies produced by the reference's OWN serial build (oracle/_ref, compiled from
+      /root/reference/src) and committed as tests/golden/ref_serial_*.npz (tests/golden/make_golden.py);
+  (b) the analytic known answers listed in SURVEY.md 8(c);
+  (c) an independent O(N^2) minimum-image evaluation of the same pair functions.
+"""
+import ast
+import ctypes as C
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+import azt
+from aztotmd_b200 import abi
+from aztotmd_b200.engine import KB, M_SCALE, Species, System
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_fp = C.POINTER(C.c_float)
+
+
+def system_from_fixture(path):
+    z = np.load(path)
+    meta = ast.literal_eval(str(z["meta"]))
+    pos, types = z["pos"], z["types"]
+    if meta["kind"] == "lj":
+        s = System(pos=pos, types=types, box=meta["box"], species=[Species("Ar", azt.AR_MASS)], cell_size=meta["rc"])
+        s.set_vdw(0, 0, "lnjs", meta["rc"], [azt.AR_EPS, azt.AR_SIGMA])
+    else:
+        ek = {"fenn": abi.ELEC_FENNEL, "dir": abi.ELEC_DIRECT}[meta["elec"]]
+        s = System(pos=pos, types=types, box=meta["box"], species=[Species("Na", 22.99, 1.0), Species("Cl", 35.45, -1.0)],
+                   cell_size=max(meta["r_real"], meta["rc_vdw"]), elec_kind=ek, r_real=meta["r_real"], alpha=meta["alpha"])
+        s.set_vdw(0, 0, "buck", meta["rc_vdw"], [424.097, 0.317, 1.05])
+        s.set_vdw(0, 1, "buck", meta["rc_vdw"], [1256.31, 0.317, 7.00])
+        s.set_vdw(1, 1, "buck", meta["rc_vdw"], [3488.998, 0.317, 72.40])
+    return s, z
+
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLD, "ref_serial_*.npz")))
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 4
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[11:-4] for p in FIXTURES])
+def test_oracle_matches_reference_serial_build(path):
+    """float32 oracle vs the reference's double-precision serial forces: 1e-5 relative to the
+    per-atom sum of |pair terms| (the fp32 noise floor), energies to 2e-6 relative."""
+    s, z = system_from_fixture(path)
+    o = azt.Oracle(s)
+    o.forces_only()
+    d = azt.sort_by_id(o.dump())
+    scale = np.zeros(o.n, dtype=np.float32)
+    scale[o.dump()["ids"]] = o.force_scale()
+    err = np.abs(d["frc"].astype(np.float64) - z["frc"]).max(1)
+    assert (err <= 1e-5 * np.maximum(scale, 1e-12)).all(), float((err / np.maximum(scale, 1e-12)).max())
+    st = o.stats()
+    assert st.engVdW_d == pytest.approx(float(z["engVdW"]), rel=2e-6)
+    # the serial twin's direct/DSF real-space energy (Sim::engElec3)
+    if float(z["engCoul"]) != 0.0:
+        assert st.engCoul1_d == pytest.approx(float(z["engCoul"]), rel=5e-6)
+
+
+def pair(kind, p, r, rc=100.0, elec=0, alpha=0.0, q=0.0, rad=(0.0, 0.0), r_real=0.0):
+    lib = azt.oracle_lib()
+    pp = (C.c_float * 5)(*(list(p) + [0.0] * (5 - len(p))))
+    ev, ec = C.c_float(), C.c_float()
+    daipi2 = 2 * alpha / math.sqrt(3.14159265359)
+    c1 = c2 = 0.0
+    if elec == abi.ELEC_FENNEL:
+        arc = alpha * r_real
+        c1 = math.erfc(arc) / r_real
+        c2 = math.erfc(arc) / r_real ** 2 + daipi2 * math.exp(-arc * arc) / r_real
+    rmax2 = max(rc, r_real) ** 2 if elec else rc * rc
+    f = lib.azo_pair_eval(kind, pp, rc * rc, elec, alpha, daipi2, c1, c2, r_real, q, r * r, rmax2, rad[0], rad[1],
+                          C.byref(ev), C.byref(ec))
+    return f, ev.value, ec.value
+
+
+def test_lj_known_answers():
+    eps, sig = azt.AR_EPS, azt.AR_SIGMA
+    p = [4 * eps, sig * sig, 24 * eps]
+    f, e, _ = pair(abi.VDW_LJ, p, sig)                       # U(sigma) = 0, F/r = 24 eps / sigma^2
+    assert abs(e) < 1e-8 and f == pytest.approx(24 * eps / sig ** 2, rel=1e-5)
+    f, e, _ = pair(abi.VDW_LJ, p, 2 ** (1 / 6) * sig)        # minimum: U = -eps, F = 0
+    assert e == pytest.approx(-eps, rel=1e-5) and abs(f) < 1e-7
+    f, e, _ = pair(abi.VDW_LJ, p, 2.5 * sig, rc=2.5 * sig + 1e-4)  # at the cutoff: plain truncation
+    assert e == pytest.approx(4 * eps * (2.5 ** -12 - 2.5 ** -6), rel=1e-4)
+    f, e, _ = pair(abi.VDW_LJ, p, 2.5 * sig + 0.01, rc=2.5 * sig)  # beyond it: nothing
+    assert f == 0.0 and e == 0.0
+
+
+def test_autocap_clamps_f_over_r():
+    eps, sig = azt.AR_EPS, azt.AR_SIGMA
+    f, _, _ = pair(abi.VDW_LJ, [4 * eps, sig * sig, 24 * eps], 0.5)  # deep overlap -> MX_FRC (src/cuPairs.cu:94-115)
+    assert f == abi.AZ_MX_FRC
+
+
+def test_dsf_force_vanishes_at_cutoff():
+    f, _, ec = pair(abi.VDW_NONE, [0] * 5, 12.0 - 1e-4, elec=abi.ELEC_FENNEL, alpha=0.2, q=-1.0, r_real=12.0)
+    assert abs(f) < 1e-6 and abs(ec) < 1e-6
+    f2, _, _ = pair(abi.VDW_NONE, [0] * 5, 3.0, elec=abi.ELEC_FENNEL, alpha=0.2, q=-1.0, r_real=12.0)
+    assert f2 < 0  # opposite charges attract (F/r negative)
+
+
+def test_direct_coulomb_known_answer():
+    f, _, ec = pair(abi.VDW_NONE, [0] * 5, 2.0, elec=abi.ELEC_DIRECT, q=1.0, r_real=9.0)
+    assert ec == pytest.approx(14.3996 / 2.0, rel=1e-6) and f == pytest.approx(14.3996 / 8.0, rel=1e-6)
+
+
+def test_buckingham_with_and_without_coulomb_agree():
+    p = [1256.31, 0.317, 7.0]
+    f0, e0, _ = pair(abi.VDW_BUCK, p, 2.8, rc=9.0)
+    f1, e1, ec = pair(abi.VDW_BUCK, p, 2.8, rc=9.0, elec=abi.ELEC_DIRECT, q=0.0, r_real=9.0)
+    assert f0 == pytest.approx(f1, rel=1e-6) and e0 == pytest.approx(e1, rel=1e-6) and ec == 0.0
+    r = 2.8
+    assert e0 == pytest.approx(p[0] * math.exp(-r / p[1]) - p[2] / r ** 6, rel=1e-5)
+    assert f0 == pytest.approx(p[0] * math.exp(-r / p[1]) / r / p[1] - 6 * p[2] / r ** 8, rel=1e-5)
+
+
+def test_surk_at_initial_radii():
+    # case study 2: surk 6.0 75.0 8.0 1.0 1.0 with a = b = 2.73/4.731 (radii at U = 0)
+    a = 2.73 / 4.731
+    assert a == pytest.approx(0.5770, abs=1e-4)
+    c1, c2, k, l = 75.0, 8.0, 1.0, 1.0
+    r = 3.0
+    f, e, _ = pair(abi.VDW_SURK, [c1, c2, k, l], r, rc=6.0, rad=(a, a))
+    assert e == pytest.approx(a * a / r ** 6 * (c1 * a ** 4 / r - c2 / (k * a + l * a)), rel=1e-5)
+    assert f == pytest.approx(a * a / r ** 8 * (7 * c1 * a ** 4 / r - 6 * c2 / (k * a + l * a)), rel=1e-5)
+
+
+def test_grid_of_the_case_studies():
+    lib = azt.oracle_lib()
+    cn = (C.c_int * 3)(); cs = (C.c_float * 3)(); cr = (C.c_float * 3)()
+    lib.azo_split_cells(1141.5, 1141.5, 1141.5, 85.0, cn, cs, cr)  # case study 1: 13^3 cells of 87.81
+    assert tuple(cn) == (13, 13, 13) and cs[0] == pytest.approx(87.8077, rel=1e-6)
+    lib.azo_split_cells(35.0, 35.0, 35.0, 2.7, cn, cs, cr)         # case study 2: 12^3 cells
+    assert tuple(cn) == (12, 12, 12)
+    assert cr[0] == np.float32(12) / np.float32(35.0)
+
+
+def test_cell_index_uses_double_floor_and_clamps():
+    lib = azt.oracle_lib()
+    cn = (C.c_int * 3)(3, 3, 3); cr = (C.c_float * 3)(*[np.float32(3) / np.float32(28.5)] * 3)
+    assert lib.azo_cell_index(0.0, 0.0, 0.0, cr, cn) == 0
+    assert lib.azo_cell_index(28.4999, 0.0, 9.6, cr, cn) == 2 * 9 + 1
+    assert lib.azo_cell_index(28.5, 28.5, 28.5, cr, cn) == 26  # x*crev rounds to n: clamped (reference has no clamp)
+
+
+def test_tkin_formula():
+    s = azt.lj_system(ncell=(3, 3, 3), temperature=298.0, tstat=abi.TSTAT_RADI, vel=False)
+    n = len(s.pos)
+    assert s.t_kin == pytest.approx(0.5 * 298.0 * KB * (3 * n - 1))
+    assert M_SCALE == pytest.approx(1.0364e-4, rel=1e-3)
+
+
+def test_unit_vectors_are_unit_and_paired():
+    lib = azt.oracle_lib()
+    ux, uy, uz = (np.zeros(abi.AZ_N_UVECT) for _ in range(3))
+    dp = C.POINTER(C.c_double)
+    lib.azo_default_uvects(ux.ctypes.data_as(dp), uy.ctypes.data_as(dp), uz.ctypes.data_as(dp))
+    nrm = np.sqrt(ux ** 2 + uy ** 2 + uz ** 2)
+    assert np.allclose(nrm, 1.0, atol=1e-9)
+    assert np.allclose(ux[0::2], -ux[1::2]) and np.allclose(uz[0::2], -uz[1::2])
+
+
+def test_philox_known_answer():
+    # Random123 known-answer test for philox4x32-10: counter = key = 0
+    lib = azt.oracle_lib()
+    out = (C.c_uint32 * 4)()
+    lib.azo_philox(0, 0, 0, 0, 0, 0, out)
+    assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    lib.azo_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out)
+    assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+@pytest.mark.parametrize("maker", [lambda: azt.lj_system(ncell=(5, 5, 5)), lambda: azt.nacl_system(ncell=(5, 5, 5)),
+                                   lambda: azt.nacl_system(ncell=(5, 5, 5), kind="mixed", elec=abi.ELEC_EWALD),
+                                   lambda: azt.surk_system(n_side=6, tstat=abi.TSTAT_NONE)],
+                         ids=["lj", "buck_dsf", "mixed_ewald", "surk"])
+def test_cell_traversal_equals_all_pairs(maker):
+    """The stencil traversal (reference image rule) against a plain minimum-image O(N^2) sweep."""
+    s = maker()
+    o = azt.Oracle(s)
+    o.forces_only()
+    d = o.dump()
+    f2, ev, ec = o.forces_allpairs()
+    sc = np.maximum(o.force_scale(), 1e-12)
+    assert (np.abs(d["frc"] - f2).max(1) <= 2e-6 * sc).all()
+    st = o.stats()
+    assert st.engVdW_d == pytest.approx(ev, rel=1e-9, abs=1e-9) and st.engCoul1_d == pytest.approx(ec, rel=1e-9, abs=1e-9)
+
+
+def test_case_study_1_has_no_pair_inside_cutoff():
+    """in the shipped 40 000-atom deck the minimum distance (4.008 A) exceeds rc = 4.0 A,
+    so the initial potential energy is exactly zero.  Checked on a 4 000-atom cut of the same recipe:
+    a dilute gas placed on a jittered lattice with spacing > rc."""
+    rng = np.random.default_rng(7)
+    g = (np.arange(16) + 0.5) * 6.0
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:4000] + rng.uniform(-0.9, 0.9, (4000, 3))
+    s = System(pos=pos, types=np.zeros(4000, dtype=np.int32), box=(96.0, 96.0, 96.0), species=[Species("Ar", 39.9)],
+               cell_size=8.0)
+    s.set_vdw(0, 0, "lnjs", 4.0, [0.01006, 3.3952])
+    o = azt.Oracle(s)
+    o.forces_only()
+    assert o.pairs_in_range() == 0 and o.stats().engVdW_d == 0.0 and not o.dump()["frc"].any()
