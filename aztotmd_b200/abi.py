@@ -77,7 +77,8 @@ class az_stats(C.Structure):
                 ("engCoul2", C.c_float), ("engTemp", C.c_float), ("engElecField", C.c_float), ("engPot", C.c_float),
                 ("posMom", C.c_float * 3), ("negMom", C.c_float * 3), ("pressure", C.c_float), ("reserved", C.c_float),
                 ("specAcBoxPos", (C.c_int * 3) * AZ_MAX_SPECIES), ("specAcBoxNeg", (C.c_int * 3) * AZ_MAX_SPECIES),
-                ("engKin_d", C.c_double), ("engVdW_d", C.c_double), ("engCoul1_d", C.c_double), ("engTemp_d", C.c_double)]
+                ("engKin_d", C.c_double), ("engVdW_d", C.c_double), ("engCoul1_d", C.c_double), ("engTemp_d", C.c_double),
+                ("n_pairs", C.c_longlong)]
 
 
 class az_atoms_out(C.Structure):
@@ -116,6 +117,10 @@ ENGINE_SYMBOLS = {
     "az_engine_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "az_engine_timers": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     "az_engine_launch_count": (C.c_longlong, [C.c_void_p]),
+    "az_engine_step_timed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "az_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "az_host_free": (None, [C.c_void_p]),
+    "az_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "az_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "az_engine_info": (C.c_int, [C.c_void_p, C.POINTER(az_engine_info_t)]),
 }
@@ -126,6 +131,9 @@ DECK_SYMBOLS = {
     "az_deck_nsteps": (C.c_int, [C.c_void_p]),
     "az_deck_stat_period": (C.c_int, [C.c_void_p]),
     "az_deck_error": (C.c_char_p, [C.c_void_p]),
+    "az_deck_warnings": (C.c_char_p, [C.c_void_p]),
+    "az_deck_nstep_stat": (C.c_int, [C.c_void_p]),
+    "az_deck_species_count": (C.c_int, [C.c_void_p, C.c_int]),
     "az_deck_free": (None, [C.c_void_p]),
 }
 
@@ -145,6 +153,7 @@ def bind(lib: C.CDLL, symbols=None, strict: bool = True) -> C.CDLL:
     return lib
 
 
+STRICT_DECK = True
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libaztot_b200.so")
 _lib = None
 
@@ -157,5 +166,5 @@ def load_library() -> C.CDLL:
             raise RuntimeError(
                 "libaztot_b200.so is missing (%s): build it with `python -m aztotmd_b200.build` "
                 "(needs nvcc; the engine is CUDA-only and has no CPU fallback)" % LIB_PATH)
-        _lib = bind(C.CDLL(LIB_PATH))
+        _lib = bind(C.CDLL(LIB_PATH), strict=STRICT_DECK)
     return _lib

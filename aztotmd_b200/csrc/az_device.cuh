@@ -133,15 +133,16 @@ __device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r,
         float ir = az_fast_rcp(r);
         eng += ex - v.p2 * ir;
         return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir * az_fast_rcp(r2);
-    } else if (VK == AZ_VDW_SURK) { // surk_pot, src/cuVdW.cu:236-257
-        float c2ir = v.p1 * az_fast_rcp(v.p2 * rad1 + v.p3 * rad2);
+    } else if (VK == AZ_VDW_SURK) { // surk_pot, src/cuVdW.cu:236-257 (IEEE divisions: r^-8 amplifies rcp.approx error past 1e-5)
+        float c2ir = v.p1 / (v.p2 * rad1 + v.p3 * rad2);
         float r_prod = rad1 * rad2;
         float c1ab2 = r_prod * r_prod * v.p0;
-        float r2i = az_fast_rcp(r2);
-        float ir6 = r2i * r2i * r2i;
-        float ir = rsqrtf(r2);
+        float r6 = r2 * r2 * r2;
+        float rr = sqrtf(r2);
+        float ir6 = 1.f / r6;
+        float ir = 1.f / rr;
         eng += r_prod * ir6 * (c1ab2 * ir - c2ir);
-        return r_prod * ir6 * r2i * (7.f * c1ab2 * ir - 6.f * c2ir);
+        return r_prod * ir6 / r2 * (7.f * c1ab2 * ir - 6.f * c2ir);
     }
     return 0.f;
 }

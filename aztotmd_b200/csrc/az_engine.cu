@@ -268,6 +268,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
 
     AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) AZ_CUDA(e, cudaEventCreate(&e->ev[k]));
+    for (int k = 0; k < 2; k++) AZ_CUDA(e, cudaEventCreate(&e->ev_step[k]));
 
     const int n = e->n, nc = e->P.g.ncell_local;
     e->cap = n;
@@ -282,7 +283,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
     e->n_atom_blocks = (n + AZ_TPB - 1) / AZ_TPB;
     AZ_ALLOC(e, e->partKE, e->n_atom_blocks); AZ_ALLOC(e, e->partU, e->n_atom_blocks);
-    AZ_ALLOC(e, e->partV, e->pair_nblocks); AZ_ALLOC(e, e->partC, e->pair_nblocks);
+    AZ_ALLOC(e, e->partV, e->pair_nblocks); AZ_ALLOC(e, e->partC, e->pair_nblocks); AZ_ALLOC(e, e->partN, e->pair_nblocks);
     AZ_ALLOC(e, e->sc, 1);
     AZ_ALLOC(e, e->table, e->h_table.size());
     AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
@@ -335,26 +336,38 @@ extern "C" void az_engine_destroy(az_engine* e)
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
     cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
-    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage);
     cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
+    for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
 // ---------------------------------------------------------------------------------------- step
 namespace {
+// profile 1: synchronous per-section timing; profile 2: events are only recorded (no host sync
+// inside the step loop) and resolved by az_engine_timers after the stream has drained.
 struct Timer {
-    az_engine* e; int k;
-    Timer(az_engine* e_, int k_) : e(e_), k(k_) { if (e->profile) cudaEventRecord(e->ev[2 * k], e->stream); }
+    az_engine* e; int k; cudaEvent_t a = nullptr, b = nullptr;
+    Timer(az_engine* e_, int k_) : e(e_), k(k_)
+    {
+        if (e->profile == 1) cudaEventRecord(e->ev[2 * k], e->stream);
+        else if (e->profile == 2) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e->stream); }
+    }
     ~Timer()
     {
-        if (!e->profile) return;
-        cudaEventRecord(e->ev[2 * k + 1], e->stream);
-        cudaEventSynchronize(e->ev[2 * k + 1]);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]);
-        e->t_ms[k] += ms;
+        if (e->profile == 1) {
+            cudaEventRecord(e->ev[2 * k + 1], e->stream);
+            cudaEventSynchronize(e->ev[2 * k + 1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]);
+            e->t_ms[k] += ms;
+        } else if (e->profile == 2) {
+            cudaEventRecord(b, e->stream);
+            e->pending.push_back({ a, b, k });
+        }
     }
 };
 } // namespace
@@ -412,7 +425,7 @@ static int one_step(az_engine* e, int step, bool want_energy)
         AzPairArgs A;
         memset(&A, 0, sizeof(A));
         A.pos = e->pos[c]; A.therm = e->therm[c]; A.cellOfSorted = e->cellSorted; A.first = e->first; A.count = e->cellCount;
-        A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.flags = &e->sc->overflow;
+        A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.partN = e->partN; A.flags = &e->sc->overflow;
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
         int rc = az_launch_pair(e, A, want_energy);
@@ -426,22 +439,22 @@ static int one_step(az_engine* e, int step, bool want_energy)
         if (!eq_step) {
             if (radi) {
                 AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
             } else {
                 AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
             }
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
             AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
             else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
         }
@@ -504,6 +517,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     for (int t = 0; t < e->P.nspec; t++)
         for (int a = 0; a < 3; a++) { o->specAcBoxPos[t][a] = h.acPos[t][a]; o->specAcBoxNeg[t][a] = h.acNeg[t][a]; }
     o->engKin_d = h.engKin; o->engVdW_d = h.engVdW; o->engCoul1_d = h.engCoul1; o->engTemp_d = h.engTemp;
+    o->n_pairs = (long long)h.nPairs;
     return AZ_OK;
 }
 
@@ -578,28 +592,87 @@ extern "C" int az_engine_upload(az_engine* e, const double* xs, const double* ys
 {
     if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
     AZ_CUDA(e, cudaSetDevice(e->device));
-    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     const int n = e->n, c = e->cur;
-    std::vector<float4> hp(n), hv(n);
-    std::vector<int> hid(n);
-    AZ_CUDA(e, cudaMemcpy(hp.data(), e->pos[c], sizeof(float4) * n, cudaMemcpyDeviceToHost));
-    AZ_CUDA(e, cudaMemcpy(hid.data(), e->id[c], sizeof(int) * n, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n; i++) {
-        int k = hid[i]; // slot i currently holds the atom with persistent id k
-        hp[i].x = (float)xs[k]; hp[i].y = (float)ys[k]; hp[i].z = (float)zs[k];
-        hv[i] = make_float4(vxs ? (float)vxs[k] : 0.f, vys ? (float)vys[k] : 0.f, vzs ? (float)vzs[k] : 0.f, 0.f);
+    if (!e->stage) AZ_ALLOC(e, e->stage, (size_t)6 * n);
+    const double* src[6] = { xs, ys, zs, vxs, vys, vzs };
+    double* dst[6];
+    for (int k = 0; k < 6; k++) {
+        dst[k] = src[k] ? e->stage + (size_t)k * n : nullptr;
+        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     }
-    AZ_CUDA(e, cudaMemcpy(e->pos[c], hp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemcpy(e->vel[c], hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemset(e->frc, 0, sizeof(float4) * n));
+    AZ_LAUNCH(az_k_upload, e->n_atom_blocks, AZ_TPB, 0, e->stream, n, e->id[c], dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
+              e->pos[c], e->vel[c], e->frc);
+    e->launches++;
+    // the caller's arrays are borrowed for the call only
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaGetLastError());
     e->binned = false;
+    return AZ_OK;
+}
+
+extern "C" int az_engine_step_timed(az_engine* e, int first_step, int nsteps, float* ms)
+{
+    if (!e || !ms) return AZ_ERR_INVALID;
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaEventRecord(e->ev_step[0], e->stream));
+    int rc = az_engine_step(e, first_step, nsteps);
+    if (rc) return rc;
+    AZ_CUDA(e, cudaEventRecord(e->ev_step[1], e->stream));
+    AZ_CUDA(e, cudaEventSynchronize(e->ev_step[1]));
+    AZ_CUDA(e, cudaEventElapsedTime(ms, e->ev_step[0], e->ev_step[1]));
+    AZ_CUDA(e, cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" void* az_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" void az_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int az_measure_fp32_peak(int device, double* tflops, double* sm_mhz_effective)
+{
+    if (!tflops) return AZ_ERR_INVALID;
+    if (az_device_count() <= device || device < 0) return AZ_ERR_NO_DEVICE;
+    az_engine* e = nullptr;
+    AZ_CUDA(e, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AZ_CUDA(e, cudaGetDeviceProperties(&prop, device));
+    float* out = nullptr;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    AZ_CUDA(e, cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaStream_t st;
+    AZ_CUDA(e, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t a, b;
+    AZ_CUDA(e, cudaEventCreate(&a)); AZ_CUDA(e, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        AZ_CUDA(e, cudaEventRecord(a, st));
+        AZ_LAUNCH(az_k_ffma_probe, blocks, threads, 0, st, out, iters, 0.999f, 0.001f);
+        AZ_CUDA(e, cudaEventRecord(b, st));
+        AZ_CUDA(e, cudaEventSynchronize(b));
+        float ms = 0.f;
+        AZ_CUDA(e, cudaEventElapsedTime(&ms, a, b));
+        double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads; // 64 FMAs per iteration per thread
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    if (sm_mhz_effective) *sm_mhz_effective = best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st); cudaFree(out);
     return AZ_OK;
 }
 
 extern "C" int az_engine_profile(az_engine* e, int enable)
 {
     if (!e) return AZ_ERR_INVALID;
-    e->profile = enable != 0;
+    e->profile = enable;
+    for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    e->pending.clear();
     for (int k = 0; k < AZ_N_TIMERS; k++) { e->t_ms[k] = 0.0; e->t_launch[k] = 0; }
     return AZ_OK;
 }
@@ -607,6 +680,16 @@ extern "C" int az_engine_profile(az_engine* e, int enable)
 extern "C" int az_engine_timers(az_engine* e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS])
 {
     if (!e) return AZ_ERR_INVALID;
+    if (!e->pending.empty()) {
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        for (auto& p : e->pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p.a, p.b);
+            e->t_ms[p.k] += ms;
+            cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+        }
+        e->pending.clear();
+    }
     for (int k = 0; k < AZ_N_TIMERS; k++) { if (ms_sum) ms_sum[k] = e->t_ms[k]; if (launches) launches[k] = e->t_launch[k]; }
     return AZ_OK;
 }

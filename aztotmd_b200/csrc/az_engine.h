@@ -16,7 +16,10 @@ struct az_engine {
     float revArea[3] = { 0, 0, 0 };
     int n_eq = 0, eq_freq = 0;
     int rebuild_every = 1, since_rebuild = 0;
-    bool binned = false, use_therm = false, profile = false, energy_every_step = false, energy_valid = false;
+    bool binned = false, use_therm = false, energy_every_step = false, energy_valid = false;
+    int profile = 0; // 0 off, 1 synchronous sections, 2 recorded events resolved later
+    struct PendingEv { cudaEvent_t a, b; int k; };
+    std::vector<PendingEv> pending;
     int last_step = -1;
     // pair kernel configuration
     int pair_vk = 0, pair_ck = 0;
@@ -27,6 +30,7 @@ struct az_engine {
     // device state
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * AZ_N_TIMERS] = {};
+    cudaEvent_t ev_step[2] = {};
     int cur = 0;
     float4 *pos[2] = { nullptr, nullptr }, *vel[2] = { nullptr, nullptr }, *frc = nullptr;
     int* id[2] = { nullptr, nullptr };
@@ -35,6 +39,8 @@ struct az_engine {
     int *cellCount = nullptr, *first = nullptr, *tileSum = nullptr;
     int n_scan_tiles = 0, n_atom_blocks = 0;
     double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
+    unsigned long long* partN = nullptr;
+    double* stage = nullptr; // 6*n doubles: az_engine_upload staging
     AzScalars* sc = nullptr;
     AzVdw* table = nullptr;
     float *photons = nullptr, *uv = nullptr;

@@ -54,6 +54,7 @@ struct AzScalars {
     int step;
     int overflow; // sticky error flags: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots
     float tscale_k;
+    unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
     unsigned vmax2_bits; // max |v|^2 of the current step (float bits; stale-cell steps only)
     float drift;         // upper bound of any atom's displacement since the last rebuild
 };
@@ -113,7 +114,8 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
     if (!BIN) { // stale cells: bound the drift since the last rebuild by the fastest atom
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));
-        if ((threadIdx.x & 31) == 0 && v2 > 0.f) atomicMax(&sc->vmax2_bits, __float_as_uint(v2));
+        // one atomic per warp only while the running maximum is still smaller (a handful per launch)
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(v2) > *(volatile unsigned*)&sc->vmax2_bits) atomicMax(&sc->vmax2_bits, __float_as_uint(v2));
     }
     if (P.has_efield) {
         __shared__ double sm[32];
@@ -368,7 +370,7 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 static __global__ void __launch_bounds__(1024)
 az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
-              const double* __restrict__ partU, int nU, AzScalars* __restrict__ sc,
+              const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, AzScalars* __restrict__ sc,
               float revAx, float revAy, float revAz)
 {
     __shared__ double sm[4 * 32];
@@ -377,6 +379,12 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
     if (mode & 2) for (int k = threadIdx.x; k < nPair; k += blockDim.x) { v[1] += partV[k]; v[2] += partC[k]; }
     if (mode & 4) for (int k = threadIdx.x; k < nU; k += blockDim.x) v[3] += partU[k];
     az_block_sum<4>(v, sm);
+    if (mode & 2) { // pair visits (both sides) -> unique pairs; exact in double up to 2^53
+        double c[1] = { 0.0 };
+        for (int k = threadIdx.x; k < nPair; k += blockDim.x) c[0] += (double)partN[k];
+        az_block_sum<1>(c, sm);
+        if (threadIdx.x == 0) sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25);
+    }
     if (threadIdx.x != 0) return;
     if (mode & 32) { sc->drift = 0.f; sc->vmax2_bits = 0u; } // rebuild step: cells are exact again
     if (mode & 64) { // stale-cell step: every atom moved by at most vmax*dt
@@ -431,4 +439,40 @@ az_k_gather_by_id(int n, const int* __restrict__ id, const float4* __restrict__ 
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[id[i]] = src[i];
+}
+
+
+// ---------------------------------------------------------------------------------------
+// az_engine_upload on the device: host SoA doubles (struct Atoms layout) staged in HBM are
+// narrowed to float exactly like src/cuInit.cu:775-777 and gathered into the slot that
+// currently holds each persistent id; forces are zeroed like a fresh init_cudaMD.
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_upload(int n, const int* __restrict__ id, const double* __restrict__ xs, const double* __restrict__ ys,
+            const double* __restrict__ zs, const double* __restrict__ vxs, const double* __restrict__ vys,
+            const double* __restrict__ vzs, float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ frc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = id[i];
+    float4 p = pos[i];
+    p.x = (float)xs[k]; p.y = (float)ys[k]; p.z = (float)zs[k];
+    pos[i] = p;
+    vel[i] = make_float4(vxs ? (float)vxs[k] : 0.f, vys ? (float)vys[k] : 0.f, vzs ? (float)vzs[k] : 0.f, 0.f);
+    frc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// FP32 FMA throughput probe: 8 independent FMA chains per thread, no memory traffic.
+static __global__ void __launch_bounds__(256)
+az_k_ffma_probe(float* out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }

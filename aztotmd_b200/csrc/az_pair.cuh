@@ -29,6 +29,7 @@ struct AzPairArgs {
     float4* frc;             // out
     double* partV;           // per-CTA energy partials
     double* partC;
+    unsigned long long* partN; // per-CTA count of in-range pair visits (ENERGY passes only)
     int* flags;              // sticky error flags (AzScalars::overflow)
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
@@ -63,7 +64,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
     __shared__ int s_g[AZ_PAIR_MAXW];      // global index of the first atom of each window entry
     __shared__ float s_shz[AZ_PAIR_MAXW];  // z image shift of each window entry
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
-    __shared__ double s_red[64];
+    __shared__ double s_red[96];
 
     const AzGrid& g = P.g;
     const int tid = threadIdx.x;
@@ -90,6 +91,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
     float* s_tile_rad = (float*)(s_tile + A.tile_cap); // radii of the staged atoms (RADII only)
 
     double eV = 0.0, eC = 0.0;
+    unsigned long long nHit = 0;
     for (int ib = iBeg; ib < iEnd; ib += AZ_PAIR_TPB) {
         const int i = ib + tid;
         const bool act = i < iEnd;
@@ -106,6 +108,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
         }
         const int gzi = lzi + g.goff[2];
         float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
+        int hits = 0;
 
         for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
             int sx, shxi;
@@ -206,7 +209,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                                 if (SINGLE) f = az_pair<VK, CK>(P, A.single, r2, radi, radj, true, e1, e2);
                                 else f = az_pair<VK, CK>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
                                 fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
-                                if (ENERGY) { ev += e1; ec += e2; }
+                                if (ENERGY) { ev += e1; ec += e2; hits++; }
                             }
                         }
                     }
@@ -219,13 +222,13 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
             const float q = P.charge[ti];
             // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
             A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
-            eV += (double)ev; eC += (double)ec;
+            eV += (double)ev; eC += (double)ec; nHit += (unsigned long long)hits;
         }
     }
     if (ENERGY) {
         __syncthreads();
-        double vv[2] = { 0.5 * eV, 0.5 * eC }; // every pair was visited from both sides
-        az_block_sum<2>(vv, s_red);
-        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; }
+        double vv[3] = { 0.5 * eV, 0.5 * eC, (double)nHit }; // every pair was visited from both sides
+        az_block_sum<3>(vv, s_red);
+        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
     }
 }

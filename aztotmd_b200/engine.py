@@ -276,6 +276,12 @@ class Engine:
     def step(self, first_step: int, nsteps: int = 1):
         self._check(self.lib.az_engine_step(self._h, first_step, nsteps))
 
+    def step_timed(self, first_step: int, nsteps: int) -> float:
+        """Advance nsteps; returns the device time in ms (CUDA events on the engine's stream)."""
+        ms = C.c_float()
+        self._check(self.lib.az_engine_step_timed(self._h, first_step, nsteps, C.byref(ms)))
+        return float(ms.value)
+
     def sync(self):
         self._check(self.lib.az_engine_sync(self._h))
 
@@ -335,8 +341,9 @@ class Engine:
         ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
         self._check(self.lib.az_engine_upload(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
 
-    def profile(self, enable: bool = True):
-        self._check(self.lib.az_engine_profile(self._h, 1 if enable else 0))
+    def profile(self, mode: int = 1):
+        """0 off, 1 synchronous per-section timing, 2 recorded events (no host sync in the loop)."""
+        self._check(self.lib.az_engine_profile(self._h, int(mode)))
 
     def timers(self) -> dict:
         ms = (C.c_double * abi.AZ_N_TIMERS)()

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the MD hot path (bin+reorder -> pair forces -> Verlet+thermostat).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one MD time step (one pass of the whole hot path) over the workload's atoms.
+N = 1 workload: BASELINE.json configs[2], synthetic fcc LJ argon, 4 000 000 atoms, rc = 2.5 sigma,
+cell-list rebuild every 10 steps (seeded synthetic lattice + Maxwell velocities; no dataset exists).
+`value`   : atoms * K / device time of K steps (CUDA events on the engine's stream), state resident in HBM.
+`e2e`     : the same metric through the C ABI with HOST buffers: every step uploads positions and
+            velocities from pinned host memory (az_engine_upload), advances one step and reads the
+            step's statistics back (az_engine_stats); host wall clock around the loop.
+`roofline`: the dominant kernel (pair forces) against the FP32 FMA peak measured in the same run
+            (az_measure_fp32_peak; MEASURED_PEAKS.json has no FP32 figure), plus `roofline_hbm`
+            for the bandwidth-bound remainder (integrate / sort) against the measured HBM copy peak.
+`cpu_baseline` / --impl reference: the reference's own serial twin (oracle/_ref/ref_serial_harness,
+            compiled from the reference's sources) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 30.0          # flops per unique in-cutoff LJ pair (both partners' updates)
+FLOP_PER_ATOM_INTEGRATE = 40.0
+HBM_BYTES_PER_ATOM_STEP = 112.0   # pos/frc through the pair kernel + two integrate passes
+HBM_BYTES_PER_ATOM_SORT = 72.0    # per rebuild
+
+WORKLOADS = {
+    # name: (fcc cells per edge, description)
+    "lj4m": (100, "synthetic fcc LJ argon, 4,000,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    "lj500k": (50, "synthetic fcc LJ argon, 500,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    "lj4k": (10, "synthetic fcc LJ argon, 4,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    "lj32k": (20, "synthetic fcc LJ argon, 32,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+}
+AR_EPS, AR_SIGMA, AR_MASS = 0.01006, 3.3952, 39.9
+
+
+def lj_system(ncell, rebuild, skin, seed=12345):
+    from aztotmd_b200.decks import fcc_positions
+    from aztotmd_b200.engine import Species, System
+    a = (4.0 / 0.8442) ** (1.0 / 3.0) * AR_SIGMA
+    pos, box = fcc_positions((ncell,) * 3, a, jitter=0.05, seed=1)
+    rc = 2.5 * AR_SIGMA
+    s = System(pos=pos, types=np.zeros(len(pos), dtype=np.int32), box=box, species=[Species("Ar", AR_MASS)],
+               timestep=0.001, cell_size=rc + (skin if rebuild > 1 else 0.0), temperature=86.6, seed=seed)
+    s.set_vdw(0, 0, "lnjs", rc, [AR_EPS, AR_SIGMA])
+    s.vel = s.gauss_velocities(seed)
+    return s
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- reference arm
+def sample_cells_for(seconds, steps, rate=2.7e5):
+    n_target = max(4000.0, min(256000.0, seconds * rate / max(1, steps)))
+    m = int(round((n_target / 4.0) ** (1.0 / 3.0)))
+    return max(12, m)  # >= 12 fcc cells: >= 8 linked cells per axis for the serial twin
+
+
+def run_reference_sample(steps, warmup, budget_s=25.0):
+    """Time the reference's serial twin (1 thread: the code is serial) on a bounded fcc LJ sample of
+    the benchmark workload (same density, cutoff, potential; fewer atoms)."""
+    from aztotmd_b200 import decks
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_serial_harness")
+    m = sample_cells_for(budget_s, steps + warmup)
+    if os.path.exists(harness):
+        with tempfile.TemporaryDirectory() as tmp:
+            d = os.path.join(tmp, "deck")
+            info = decks.lj_argon_deck(d, m, nstep=steps, init_vel="gaus")
+            if warmup > 0:
+                subprocess.run([harness, str(warmup), "fast", "-", "1"], cwd=d, stdin=subprocess.DEVNULL, capture_output=True, text=True)
+            r = subprocess.run([harness, str(steps), "fast", "-", "1"], cwd=d, stdin=subprocess.DEVNULL, capture_output=True, text=True)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and line:
+                j = json.loads(line[-1])
+                return dict(value=j["atom_steps_per_s"], ms_per_step=j["s_per_step"] * 1e3, kind="reference", cores=1,
+                            n_atoms=info["n_atoms"],
+                            sample="%d-atom fcc LJ argon cut of the workload (same density/cutoff), %d steps, "
+                                   "reference serial twin (aztot_serial sources, g++ -O2), 1 thread" % (info["n_atoms"], steps))
+    # the reference binary is absent: time the C restatement (oracle port) instead
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import azt
+    s = azt.lj_system(ncell=(m, m, m))
+    o = azt.Oracle(s)
+    o.step(0, max(1, warmup))
+    t0 = time.perf_counter()
+    o.step(warmup, steps)
+    dt = time.perf_counter() - t0
+    return dict(value=len(s.pos) * steps / dt, ms_per_step=dt / steps * 1e3, kind="port", cores=1, n_atoms=len(s.pos),
+                sample="%d-atom fcc LJ argon cut of the workload, %d steps, oracle/az_oracle.c, 1 thread" % (len(s.pos), steps))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lj4m", choices=sorted(WORKLOADS))
+    ap.add_argument("--rebuild", type=int, default=10)
+    ap.add_argument("--skin", type=float, default=0.4)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncell, desc = WORKLOADS[args.workload]
+    n_atoms = 4 * ncell ** 3
+    config = {"workload": "%s; cell_list = rc%s; rebuild every %d steps; dt = 1 fs; NVE" % (
+        desc, " + skin %.2f A" % args.skin if args.rebuild > 1 else "", args.rebuild),
+        "n_atoms": n_atoms, "rebuild_every": args.rebuild, "skin": args.skin if args.rebuild > 1 else 0.0,
+        "l2": "inputs larger than L2 (%.0f MB of pos/vel/frc streams vs 126 MB)" % (n_atoms * 48 / 1e6)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference_sample(args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "metric": "atom-steps/s", "value": r["value"], "unit": "atom-steps/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": r["value"], "unit": "atom-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if world > 1 or args.gpus > 1:
+        from aztotmd_b200 import multi
+        multi.bench_main(args, config)
+        return
+
+    from aztotmd_b200 import abi
+    from aztotmd_b200.engine import Engine
+    lib = abi.load_library()
+    if lib.az_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    hbm_peak, hbm_src = load_peaks()
+    tf, mhz = C.c_double(), C.c_double()
+    assert lib.az_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)) == 0
+    fp32_peak = tf.value
+
+    s = lj_system(ncell, args.rebuild, args.skin)
+    e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0)
+    K, W = args.steps, args.warmup
+    e.step(0, W)
+    st = e.stats()  # also surfaces skin/overflow errors early
+    pairs = st.n_pairs
+    launches0 = e.launch_count
+    clocks = ClockSampler()
+    clocks.start()
+    e.profile(2)  # per-section events are only recorded inside the loop (no host sync)
+    ms = e.step_timed(W, K)
+    tm = e.timers()
+    e.profile(0)
+    clk = clocks.stop()
+    launches = e.launch_count - launches0
+    st = e.stats()
+    value = n_atoms * K / (ms * 1e-3)
+
+    pair_ms = tm["pair"]["ms"] / max(1, tm["pair"]["launches"])
+    rest_ms = (tm["integrate_a"]["ms"] + tm["integrate_b"]["ms"] + tm["scan"]["ms"] + tm["sort"]["ms"]) / K
+    flops_per_launch = FLOP_PER_PAIR * st.n_pairs
+    achieved_tf = flops_per_launch / (pair_ms * 1e-3) / 1e12
+    nreb = max(1, math.ceil(K / args.rebuild))
+    hbm_bytes_step = n_atoms * ((HBM_BYTES_PER_ATOM_STEP - 32.0) + HBM_BYTES_PER_ATOM_SORT * nreb / K)
+    achieved_gbs = hbm_bytes_step / (rest_ms * 1e-3) / 1e9 if rest_ms > 0 else 0.0
+
+    # ---- end to end through the C ABI with host buffers
+    n = n_atoms
+    hp = lib.az_host_alloc(6 * 8 * n)
+    assert hp, "pinned allocation failed"
+    host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(6, n))
+    a = e.download()
+    host[0:3] = a["pos"].T
+    host[3:6] = a["vel"].T
+    dp = C.POINTER(C.c_double)
+    ptr = [C.cast(hp + 8 * n * k, dp) for k in range(6)]
+    ne = max(1, args.e2e_steps)
+    first = W + K
+    for _ in range(2):  # warm the path
+        assert lib.az_engine_upload(e._h, *ptr) == 0
+        e.step(first, 1); e.stats(); first += 1
+    e.sync()
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        assert lib.az_engine_upload(e._h, *ptr) == 0
+        e.step(first, 1)
+        e.stats()
+        first += 1
+    t1 = time.perf_counter()
+    e2e_value = n * ne / (t1 - t0)
+    lib.az_host_free(hp)
+
+    out = {"metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config, "clocks": clk,
+           "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": 6 * 8 * n,
+                   "d2h_bytes_per_step": C.sizeof(abi.az_stats), "steps": ne, "timer": "host wall clock"},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "fp32", "kernel": "az_k_pair", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+                        "peak_source": "az_measure_fp32_peak in this run (FFMA chains; effective %.0f MHz x 148 SM x 128 lanes)" % mhz.value,
+                        "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch" % (FLOP_PER_PAIR, st.n_pairs),
+                        "avg_launch_ms": pair_ms, "share_of_step": pair_ms / (ms / K)},
+           "roofline_hbm": {"bound": "hbm", "kernels": "integrate_a + scan + sort + integrate_b", "achieved": achieved_gbs,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                            "avg_ms_per_step": rest_ms, "algorithmic_bytes_per_step": hbm_bytes_step},
+           "kernel_ms_per_step": {k: v["ms"] / K for k, v in tm.items()},
+           "energy": {"engKin": st.engKin_d, "engVdW": st.engVdW_d, "pairs_in_cutoff": st.n_pairs}}
+    if not args.no_cpu_baseline:
+        r = run_reference_sample(steps=10, warmup=2, budget_s=15.0)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "atom-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    e.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,7 @@
 #ifndef AZTOT_B200_H
 #define AZTOT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,6 +174,7 @@ typedef struct az_stats {
     int specAcBoxPos[AZ_MAX_SPECIES][3]; /* face crossing counters */
     int specAcBoxNeg[AZ_MAX_SPECIES][3];
     double engKin_d, engVdW_d, engCoul1_d, engTemp_d; /* unrounded accumulators */
+    long long n_pairs;   /* unique pairs inside r2Max seen by the last energy-reducing force pass */
 } az_stats;
 
 #define AZ_ORDER_SORTED 0   /* cell-sorted order, what md_to_host hands back */
@@ -230,7 +232,9 @@ int az_engine_debug_dump(az_engine *e, az_dump *out);
 int az_engine_upload(az_engine *e, const double *xs, const double *ys, const double *zs,
                      const double *vxs, const double *vys, const double *vzs);
 
-/* Per-kernel device timers (CUDA events on the engine stream). */
+/* Per-kernel device timers (CUDA events on the engine stream).  az_engine_profile(e, 1) times each
+ * section synchronously; (e, 2) only records events inside the step loop (no host sync) and
+ * az_engine_timers resolves them once the stream has drained; (e, 0) switches timing off. */
 #define AZ_TIMER_INTEGRATE_A 0 /* kick+drift+wrap+bin  (verlet_1stage)     */
 #define AZ_TIMER_SCAN 1        /* calc_firstAtomInCell                     */
 #define AZ_TIMER_SORT 2        /* sort_atoms                               */
@@ -241,6 +245,18 @@ int az_engine_upload(az_engine *e, const double *xs, const double *ys, const dou
 int az_engine_profile(az_engine *e, int enable);
 int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
 long long az_engine_launch_count(az_engine *e); /* kernels launched since create */
+
+/* az_engine_step bracketed by CUDA events on the engine stream: *ms = device time of the nsteps. */
+int az_engine_step_timed(az_engine *e, int first_step, int nsteps, float *ms);
+
+/* Pinned host memory for the arrays handed to az_engine_create / az_engine_upload (optional;
+ * pageable memory works, pinned memory lets the copies run at full PCIe speed). */
+void *az_host_alloc(size_t bytes);
+void az_host_free(void *p);
+
+/* Measured FP32 FMA throughput of the device in TFLOP/s (2 flops per FMA): the roofline
+ * denominator of the pair kernel (MEASURED_PEAKS.json carries no FP32 figure). */
+int az_measure_fp32_peak(int device, double *tflops, double *sm_mhz_effective);
 
 /* Engine options by name ("energy_every_step": reduce potential energies on every step, not only
  * on the last step of each az_engine_step call). */
@@ -263,12 +279,15 @@ int az_engine_info(az_engine *e, az_engine_info_t *out);
 typedef struct az_deck az_deck;
 /* Parse atoms.xyz, field.txt, control.txt, cuda.txt from `dir` with the reference's
  * token-scan semantics (src/utils.cpp:87-195, src/sys_init.cpp:174-988). */
-int az_deck_load(const char *dir, uint64_t seed, az_deck **out);
+int az_deck_load(const char *dir, uint64_t seed, az_deck **out); /* on failure *out still carries the message: free it */
 const az_system_desc *az_deck_desc(const az_deck *d);
 const az_cuda_opts *az_deck_opts(const az_deck *d);
 int az_deck_nsteps(const az_deck *d);
 int az_deck_stat_period(const az_deck *d);
-const char *az_deck_error(const az_deck *d);
+const char *az_deck_error(const az_deck *d);      /* d may be NULL: error of the last failed load */
+const char *az_deck_warnings(const az_deck *d);   /* the WARNING[...] lines the reference would print */
+int az_deck_nstep_stat(const az_deck *d);         /* cuda.txt 'nstep stat' (flush granularity)       */
+int az_deck_species_count(const az_deck *d, int species);
 void az_deck_free(az_deck *d);
 
 #ifdef __cplusplus
