@@ -14,7 +14,7 @@ AZ_MAX_SPECIES = 15
 AZ_N_UVECT = 3072
 AZ_N_MOM = 20
 AZ_MX_FRC = 1.0e4
-AZ_N_TIMERS = 6
+AZ_N_TIMERS = 7
 
 AZ_OK = 0
 AZ_ERR_INVALID, AZ_ERR_NO_DEVICE, AZ_ERR_CUDA, AZ_ERR_UNSUPPORTED = -1, -2, -3, -4
@@ -28,7 +28,7 @@ VDW_BY_NAME = {"lnjs": VDW_LJ, "buck": VDW_BUCK, "p746": VDW_P746, "bmhs": VDW_B
 ELEC_NONE, ELEC_DIRECT, ELEC_EWALD, ELEC_FENNEL = range(4)
 TSTAT_NONE, TSTAT_NOSE, TSTAT_RADI = range(3)
 ORDER_SORTED, ORDER_ORIGINAL = 0, 1
-TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo"]
+TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo", "pair_list"]
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -68,14 +68,14 @@ class az_cuda_opts(C.Structure):
     _fields_ = [("device", C.c_int), ("rebuild_every", C.c_int), ("skin", C.c_float), ("use_graph", C.c_int),
                 ("pair_variant", C.c_int), ("cells_per_block", C.c_int), ("rank", C.c_int), ("n_ranks", C.c_int),
                 ("pgrid", C.c_int * 3), ("ghost_slots", C.c_int), ("nccl_id", C.c_void_p),
-                ("reserved", C.c_int * 8)]
+                ("max_neigh", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class az_stats(C.Structure):
     _fields_ = [("step", C.c_int), ("n_atoms_total", C.c_int),
                 ("engTot", C.c_float), ("engKin", C.c_float), ("engVdW", C.c_float), ("engCoul1", C.c_float),
                 ("engCoul2", C.c_float), ("engTemp", C.c_float), ("engElecField", C.c_float), ("engPot", C.c_float),
-                ("posMom", C.c_float * 3), ("negMom", C.c_float * 3), ("pressure", C.c_float), ("reserved", C.c_float),
+                ("posMom", C.c_float * 3), ("negMom", C.c_float * 3), ("pressure", C.c_float), ("x_first", C.c_float),
                 ("specAcBoxPos", (C.c_int * 3) * AZ_MAX_SPECIES), ("specAcBoxNeg", (C.c_int * 3) * AZ_MAX_SPECIES),
                 ("engKin_d", C.c_double), ("engVdW_d", C.c_double), ("engCoul1_d", C.c_double), ("engTemp_d", C.c_double),
                 ("n_pairs", C.c_longlong)]

@@ -133,16 +133,19 @@ __device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r,
         float ir = az_fast_rcp(r);
         eng += ex - v.p2 * ir;
         return ex * ir * az_fast_rcp(v.p1) - v.p2 * ir * az_fast_rcp(r2);
-    } else if (VK == AZ_VDW_SURK) { // surk_pot, src/cuVdW.cu:236-257 (IEEE divisions: r^-8 amplifies rcp.approx error past 1e-5)
-        float c2ir = v.p1 / (v.p2 * rad1 + v.p3 * rad2);
+    } else if (VK == AZ_VDW_SURK) { // surk_pot, src/cuVdW.cu:236-257
+        // The bracket 7*C1*a^2b^2/r - 6*C2/(k a + l b) cancels strongly near the potential minimum, so one-ulp
+        // differences (FMA contraction, rcp.approx) are amplified past the 1e-5 force tolerance: IEEE
+        // divisions and explicitly un-contracted products keep the pair term bit-identical to the oracle.
+        float c2ir = v.p1 / __fadd_rn(__fmul_rn(v.p2, rad1), __fmul_rn(v.p3, rad2));
         float r_prod = rad1 * rad2;
-        float c1ab2 = r_prod * r_prod * v.p0;
-        float r6 = r2 * r2 * r2;
+        float c1ab2 = __fmul_rn(__fmul_rn(r_prod, r_prod), v.p0);
+        float r6 = __fmul_rn(__fmul_rn(r2, r2), r2);
         float rr = sqrtf(r2);
         float ir6 = 1.f / r6;
         float ir = 1.f / rr;
-        eng += r_prod * ir6 * (c1ab2 * ir - c2ir);
-        return r_prod * ir6 / r2 * (7.f * c1ab2 * ir - 6.f * c2ir);
+        eng += __fmul_rn(__fmul_rn(r_prod, ir6), __fsub_rn(__fmul_rn(c1ab2, ir), c2ir));
+        return __fmul_rn(__fmul_rn(r_prod, ir6) / r2, __fsub_rn(__fmul_rn(__fmul_rn(7.f, c1ab2), ir), __fmul_rn(6.f, c2ir)));
     }
     return 0.f;
 }
@@ -191,24 +194,34 @@ __device__ __forceinline__ float az_coul_feng(const AzParams& P, float r2, float
     return 0.f;
 }
 
-// pair_1 (src/cuPairs.cu:117-167) for one (i,j) candidate already inside r2 <= r2Max.
-template <int VK, int CK>
+// pair_1 (src/cuPairs.cu:117-167) for one (i,j) candidate, written branch-free: every term is
+// evaluated and the reference's gates (vdw != NULL, r2 <= vdw->r2cut) become selects, so a warp
+// never diverges inside the pair loop.  The caller applies the r2 <= r2Max gate the same way
+// (garbage from r2 == 0 or out-of-range r2 is discarded by its select, never accumulated).
+// FOLDCUT: the caller already gates on min(r2Max, r2cut) (single table entry, no Coulomb), so the vdW cut
+// select is redundant.
+template <int VK, int CK, bool FOLDCUT = false>
 __device__ __forceinline__ float az_pair(const AzParams& P, const AzVdw& v, float r2, float rad_i,
                                          float rad_j, bool same_type, float& evdw, float& ecoul)
 {
     float f = 0.f, r = 0.f;
     if (CK != AZ_ELEC_NONE) f += az_coul_feng<CK>(P, r2, r, v.chprod, ecoul);
     if (VK != AZ_VDW_NONE) {
-        if ((VK == AZ_VK_MIXED ? v.kind != AZ_VDW_NONE : true) && r2 <= v.r2cut) {
-            float ra = rad_i, rb = rad_j;
-            if ((VK == AZ_VDW_SURK || VK == AZ_VK_MIXED) && same_type) { // symmetric same-species surk
-                float lo = fminf(ra, rb), hi = fmaxf(ra, rb); ra = lo; rb = hi;
-            }
-            if (VK == AZ_VK_MIXED) f += az_vdw_feng_any(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, evdw);
-            else f += az_vdw_feng<VK>(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, evdw);
+        float ra = rad_i, rb = rad_j;
+        if ((VK == AZ_VDW_SURK || VK == AZ_VK_MIXED) && same_type) { // symmetric same-species surk
+            float lo = fminf(ra, rb), hi = fmaxf(ra, rb); ra = lo; rb = hi;
+        }
+        float e = 0.f, fv;
+        if (VK == AZ_VK_MIXED) fv = az_vdw_feng_any(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, e);
+        else fv = az_vdw_feng<VK>(v, r2, r, CK != AZ_ELEC_NONE, ra, rb, e);
+        if (FOLDCUT) { f += fv; evdw += e; }
+        else {
+            const bool vin = (VK == AZ_VK_MIXED ? v.kind != AZ_VDW_NONE : true) && r2 <= v.r2cut;
+            f += vin ? fv : 0.f;
+            evdw += vin ? e : 0.f;
         }
     }
-    // force_autocap, src/cuPairs.cu:94-115 (NaN passes through like the reference)
-    f = (f > AZ_MX_FRC) ? AZ_MX_FRC : ((f < -AZ_MX_FRC) ? -AZ_MX_FRC : f);
-    return f;
+    // force_autocap, src/cuPairs.cu:94-115: clamp F/r to +-MX_FRC (two FMNMX; a NaN, which the reference would
+    // pass through, becomes +-MX_FRC here -- it only arises for coincident atoms and is masked by the caller)
+    return fminf(fmaxf(f, -AZ_MX_FRC), AZ_MX_FRC);
 }

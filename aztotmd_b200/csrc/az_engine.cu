@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "az_engine.h"
+#include "az_pair_launch.cuh"
 
 // ----------------------------------------------------------------------------------------
 static thread_local std::string g_create_error;
@@ -283,7 +283,39 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
     e->n_atom_blocks = (n + AZ_TPB - 1) / AZ_TPB;
     AZ_ALLOC(e, e->partKE, e->n_atom_blocks); AZ_ALLOC(e, e->partU, e->n_atom_blocks);
-    AZ_ALLOC(e, e->partV, e->pair_nblocks); AZ_ALLOC(e, e->partC, e->pair_nblocks); AZ_ALLOC(e, e->partN, e->pair_nblocks);
+    // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
+    e->use_list = e->rebuild_every > 1 && !(o && o->pair_variant == 1);
+    e->list_nblocks = (n + AZ_LIST_TPB - 1) / AZ_LIST_TPB;
+    if (e->use_list) {
+        if (n > AZ_NBR_MASK) { AZ_SET_ERR(e, "the Verlet-list path addresses at most %d atoms per GPU", AZ_NBR_MASK); return AZ_ERR_UNSUPPORTED; }
+        const double rl = sqrt((double)e->P.r2list);
+        const double vol = (double)e->P.L[0] * e->P.L[1] * e->P.L[2];
+        int cap = (o && o->max_neigh > 0) ? o->max_neigh : 0;
+        if (cap <= 0) {
+            // rows from the densest region of the initial configuration: bins of edge >= r_list
+            int nb3[3]; double inv[3];
+            for (int a = 0; a < 3; a++) { nb3[a] = (int)floor((double)e->P.L[a] / rl); if (nb3[a] < 1) nb3[a] = 1; if (nb3[a] > 256) nb3[a] = 256; inv[a] = nb3[a] / (double)e->P.L[a]; }
+            std::vector<int> bins((size_t)nb3[0] * nb3[1] * nb3[2], 0);
+            const double* xyz[3] = { d->xs, d->ys, d->zs };
+            int mx = 0;
+            for (int i = 0; i < n; i++) {
+                int c[3];
+                for (int a = 0; a < 3; a++) { double u = xyz[a][i] * inv[a]; u -= floor(u / nb3[a]) * nb3[a]; c[a] = (int)u; if (c[a] >= nb3[a]) c[a] = nb3[a] - 1; if (c[a] < 0) c[a] = 0; }
+                int v = ++bins[((size_t)c[0] * nb3[1] + c[1]) * nb3[2] + c[2]];
+                if (v > mx) mx = v;
+            }
+            double rho = mx * inv[0] * inv[1] * inv[2];
+            double rho_avg = (double)n / vol;
+            if (rho < rho_avg) rho = rho_avg;
+            cap = (int)(1.5 * rho * 4.18879 * rl * rl * rl) + 32;
+        }
+        e->nbr_cap = cap;
+        e->nbr_stride = (n + 31) / 32 * 32;
+        AZ_ALLOC(e, e->nbr, (size_t)e->nbr_cap * e->nbr_stride);
+        AZ_ALLOC(e, e->nbrCount, n);
+    }
+    { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve both kernels
+      AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
     AZ_ALLOC(e, e->table, e->h_table.size());
     AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
@@ -336,7 +368,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
     cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
-    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage); cudaFree(e->nbr); cudaFree(e->nbrCount);
     cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
@@ -384,6 +416,7 @@ static int one_step(az_engine* e, int step, bool want_energy)
     const bool eq_step = e->n_eq && step <= e->n_eq && e->eq_freq > 0 && (step % e->eq_freq) == 0; // src/cuTemp.cu:777-779
     const int nb = e->n_atom_blocks;
     int c = e->cur;
+    const int n_pp = e->use_list ? e->list_nblocks : e->pair_nblocks; // live pair partials this step
 
     { // K1: half kick + drift (+ wrap + bin)
         Timer t(e, AZ_TIMER_INTEGRATE_A);
@@ -421,16 +454,19 @@ static int one_step(az_engine* e, int step, bool want_energy)
         e->since_rebuild++;
     }
     { // K4: pair forces
-        Timer t(e, AZ_TIMER_PAIR);
+        const int pair_mode = !e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST);
+        const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
+        Timer t(e, pair_timer);
         AzPairArgs A;
         memset(&A, 0, sizeof(A));
         A.pos = e->pos[c]; A.therm = e->therm[c]; A.cellOfSorted = e->cellSorted; A.first = e->first; A.count = e->cellCount;
         A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.partN = e->partN; A.flags = &e->sc->overflow;
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
-        int rc = az_launch_pair(e, A, want_energy);
+        A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap;
+        int rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
-        AZ_COUNT(e, AZ_TIMER_PAIR, 1);
+        AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
     }
     { // K5: half kick + KE (+ thermostat) + derived quantities
         Timer t(e, AZ_TIMER_INTEGRATE_B);
@@ -439,22 +475,22 @@ static int one_step(az_engine* e, int step, bool want_energy)
         if (!eq_step) {
             if (radi) {
                 AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
             } else {
                 AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
             }
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
             AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
             else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, e->pair_nblocks, e->partU, nb, e->partN, e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
         }
@@ -497,6 +533,7 @@ static int fetch_scalars(az_engine* e, AzScalars* h)
     AZ_CUDA(e, cudaGetLastError());
     if (h->overflow & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
     if (h->overflow & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
+    if (h->overflow & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius: raise 'max_neigh'", e->nbr_cap); return AZ_ERR_OVERFLOW; }
     if (h->overflow & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a ghost cell overflowed its halo slots"); return AZ_ERR_OVERFLOW; }
     return AZ_OK;
 }
@@ -514,6 +551,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     o->engCoul2 = 0.f; o->engTemp = (float)h.engTemp; o->engElecField = (float)h.engElecField; o->engPot = h.engPot;
     for (int a = 0; a < 3; a++) { o->posMom[a] = (float)h.posMom[a]; o->negMom[a] = (float)h.negMom[a]; }
     o->pressure = h.pressure;
+    o->x_first = h.x_first;
     for (int t = 0; t < e->P.nspec; t++)
         for (int a = 0; a < 3; a++) { o->specAcBoxPos[t][a] = h.acPos[t][a]; o->specAcBoxNeg[t][a] = h.acNeg[t][a]; }
     o->engKin_d = h.engKin; o->engVdW_d = h.engVdW; o->engCoul1_d = h.engCoul1; o->engTemp_d = h.engTemp;

@@ -26,6 +26,10 @@ struct az_engine {
     bool pair_single = false, pair_radii = false;
     int pair_zc = 1, pair_nruns = 1, pair_nblocks = 1, pair_tile_cap = 512;
     size_t pair_smem = 0;
+    // Verlet-list path (rebuild_every > 1)
+    bool use_list = false;
+    int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
+    int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;
     // device state
     cudaStream_t stream = nullptr;
@@ -40,6 +44,7 @@ struct az_engine {
     int n_scan_tiles = 0, n_atom_blocks = 0;
     double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
     unsigned long long* partN = nullptr;
+    int n_pair_partials = 0;
     double* stage = nullptr; // 6*n doubles: az_engine_upload staging
     AzScalars* sc = nullptr;
     AzVdw* table = nullptr;
@@ -53,8 +58,8 @@ struct az_engine {
 
 int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
 // launches the pair kernel instantiation chosen at create time (az_pair_inst_*.cu)
-int az_launch_pair(az_engine* e, const AzPairArgs& A, bool energy);
-int az_launch_pair_lj(az_engine* e, const AzPairArgs& A, bool energy);
-int az_launch_pair_buck(az_engine* e, const AzPairArgs& A, bool energy);
-int az_launch_pair_surk(az_engine* e, const AzPairArgs& A, bool energy);
-int az_launch_pair_mixed(az_engine* e, const AzPairArgs& A, bool energy);
+int az_launch_pair(az_engine* e, const AzPairArgs& A, bool energy, int mode);
+int az_launch_pair_lj(az_engine* e, const AzPairArgs& A, bool energy, int mode);
+int az_launch_pair_buck(az_engine* e, const AzPairArgs& A, bool energy, int mode);
+int az_launch_pair_surk(az_engine* e, const AzPairArgs& A, bool energy, int mode);
+int az_launch_pair_mixed(az_engine* e, const AzPairArgs& A, bool energy, int mode);

@@ -52,8 +52,9 @@ struct AzScalars {
     int iMom;
     float pressure, engTot, engPot;
     int step;
-    int overflow; // sticky error flags: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots
+    int overflow; // sticky error flags: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots, 16 neighbour-list rows
     float tscale_k;
+    float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
     unsigned vmax2_bits; // max |v|^2 of the current step (float bits; stale-cell steps only)
     float drift;         // upper bound of any atom's displacement since the last rebuild
@@ -62,6 +63,7 @@ struct AzScalars {
 #define AZ_FLAG_TILE 2
 #define AZ_FLAG_NAN 4
 #define AZ_FLAG_HALO 8
+#define AZ_FLAG_NBR 16
 
 // ---------------------------------------------------------------------------------------
 // K1: verlet_1stage (src/cuMDfunc.cu:333-518) + put_periodic (:35-106) + count_cell
@@ -370,7 +372,7 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 static __global__ void __launch_bounds__(1024)
 az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
-              const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, AzScalars* __restrict__ sc,
+              const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, const float4* __restrict__ pos, AzScalars* __restrict__ sc,
               float revAx, float revAy, float revAz)
 {
     __shared__ double sm[4 * 32];
@@ -429,6 +431,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
             for (int a = 0; a < 3; a++) { sc->posMomBuf[step][a] = pm[a]; sc->negMomBuf[step][a] = nm[a]; }
         }
         sc->step = step;
+        sc->x_first = pos[0].x;
     }
 }
 

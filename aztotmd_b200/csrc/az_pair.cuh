@@ -31,6 +31,9 @@ struct AzPairArgs {
     double* partC;
     unsigned long long* partN; // per-CTA count of in-range pair visits (ENERGY passes only)
     int* flags;              // sticky error flags (AzScalars::overflow)
+    int* nbr;                // LIST build: neighbour codes, row k of atom i at nbr[k * nbr_stride + i]
+    int* nbrCount;           // LIST build: neighbours of atom i within the list radius
+    int nbr_stride, nbr_cap;
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
     int tile_cap;            // atoms the dynamic shared tile holds
@@ -55,7 +58,56 @@ __device__ __forceinline__ bool az_neighbor(const AzGrid& g, int a, int cglob, i
     return true;
 }
 
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+// Neighbour code of the Verlet-list path: sorted index of j in the low 26 bits, image signs
+// (0 none, 1 = -L, 2 = +L per axis) above them.
+#define AZ_NBR_BITS 26
+#define AZ_NBR_MASK ((1 << AZ_NBR_BITS) - 1)
+__device__ __forceinline__ int az_shift_code(int shx, int shy, int shz)
+{
+    return ((shx < 0 ? 1 : (shx > 0 ? 2 : 0)) | ((shy < 0 ? 1 : (shy > 0 ? 2 : 0)) << 2) | ((shz < 0 ? 1 : (shz > 0 ? 2 : 0)) << 4));
+}
+
+// One window entry (cell) swept against the lane's i-atom: branch-free, warp-uniform trip count.
+// SHIFT=false is the interior case (all three image shifts are zero: (xi - xj) - 0 == xi - xj exactly).
+// `lim` is the lane's gate: r2Max (folded with r2cut when there is a single table entry and no
+// Coulomb) if the lane's cell pairs with this window entry, -1 otherwise.
+// LIST=true only records the neighbours inside the list radius (no pair arithmetic): the rebuild
+// step of the Verlet-list path; the forces of that step come from az_k_pair_list like all others.
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool LIST, bool SHIFT>
+__device__ __forceinline__ void az_sweep_cell(const AzParams& P, const AzPairArgs& A, const AzVdw* __restrict__ s_tab,
+                                              const float4* __restrict__ s_tile, const float* __restrict__ s_tile_rad,
+                                              int jb, int je, int self, float lim, const float4 pi, int ti, float radi,
+                                              float shx, float shy, float shz, int i, int gbase, int code,
+                                              float& fx, float& fy, float& fz, float& ev, float& ec, int& hits, int& nnb)
+{
+    constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
+#pragma unroll 4
+    for (int j = jb; j < je; j++) {
+        const float4 pj = s_tile[j];
+        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (SHIFT) { dx -= shx; dy -= shy; dz -= shz; }
+        const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); // nvcc's contraction of dx*dx+dy*dy+dz*dz
+        const bool in = r2 <= lim && j != self;
+        if (LIST) {
+            if (in) {
+                if (nnb < A.nbr_cap) A.nbr[(size_t)nnb * A.nbr_stride + i] = (gbase + (j - jb)) | (code << AZ_NBR_BITS);
+                nnb++;
+            }
+        } else {
+            const int tj = __float_as_int(pj.w);
+            float radj = 0.f;
+            if (RADII) radj = s_tile_rad[j];
+            float e1 = 0.f, e2 = 0.f, f;
+            if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+            else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+            f = in ? f : 0.f;
+            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+            if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
+        }
+    }
+}
+
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool LIST>
 __global__ void __launch_bounds__(AZ_PAIR_TPB)
 az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
@@ -92,6 +144,8 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 
     double eV = 0.0, eC = 0.0;
     unsigned long long nHit = 0;
+    // the pair gate: list radius when recording neighbours, else r2Max (folded with the only r2cut when possible)
+    const float gate = LIST ? P.r2list : ((SINGLE && CK == AZ_ELEC_NONE) ? fminf(P.r2max, A.single.r2cut) : P.r2max);
     for (int ib = iBeg; ib < iEnd; ib += AZ_PAIR_TPB) {
         const int i = ib + tid;
         const bool act = i < iEnd;
@@ -108,7 +162,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
         }
         const int gzi = lzi + g.goff[2];
         float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
-        int hits = 0;
+        int hits = 0, nnb = 0;
 
         for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
             int sx, shxi;
@@ -165,7 +219,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                     int w1 = w0;
                     while (w1 < W && s_cs[w1 + 1] - base <= A.tile_cap) w1++;
                     if (w1 == w0) { // one cell larger than the tile: report, skip it
-                        if (tid == 0) atomicOr(A.flags, 2);
+                        if (tid == 0) atomicOr(A.flags, AZ_FLAG_TILE);
                         w0++;
                         continue;
                     }
@@ -194,24 +248,15 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                         if (!__any_sync(0xffffffffu, valid)) continue;
                         const float shz = s_shz[w];
                         const int self = (centre && oz == 0 && valid) ? jb + rank_i : -1;
-                        for (int j = jb; j < je; j++) {
-                            const float4 pj = s_tile[j];
-                            const float dx = pi.x - pj.x - shx;
-                            const float dy = pi.y - pj.y - shy;
-                            const float dz = pi.z - pj.z - shz;
-                            const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); // nvcc's contraction of dx*dx+dy*dy+dz*dz
-                            if (valid && r2 <= P.r2max && j != self) {
-                                const int tj = __float_as_int(pj.w);
-                                float radj = 0.f;
-                                if (RADII) radj = s_tile_rad[j];
-                                float e1 = 0.f, e2 = 0.f;
-                                float f;
-                                if (SINGLE) f = az_pair<VK, CK>(P, A.single, r2, radi, radj, true, e1, e2);
-                                else f = az_pair<VK, CK>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
-                                fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
-                                if (ENERGY) { ev += e1; ec += e2; hits++; }
-                            }
-                        }
+                        const float lim = valid ? gate : -1.f;
+                        const int shzi = (shz < 0.f) ? -1 : ((shz > 0.f) ? 1 : 0);
+                        const int code = LIST ? az_shift_code(shxi, shyi, shzi) : 0;
+                        if (shxi == 0 && shyi == 0 && shzi == 0)
+                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, LIST, false>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
+                                                                                      0.f, 0.f, 0.f, i, s_g[w], code, fx, fy, fz, ev, ec, hits, nnb);
+                        else
+                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, LIST, true>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
+                                                                                     shx, shy, shz, i, s_g[w], code, fx, fy, fz, ev, ec, hits, nnb);
                     }
                     w0 = w1;
                     if (w0 < W) __syncthreads(); // tile is about to be overwritten
@@ -219,15 +264,108 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
             }
         }
         if (act) {
-            const float q = P.charge[ti];
-            // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
-            A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
-            eV += (double)ev; eC += (double)ec; nHit += (unsigned long long)hits;
+            if (LIST) {
+                A.nbrCount[i] = min(nnb, A.nbr_cap);
+                if (nnb > A.nbr_cap) atomicOr(A.flags, AZ_FLAG_NBR);
+            } else {
+                const float q = P.charge[ti];
+                // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
+                A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+                eV += (double)ev; eC += (double)ec; nHit += (unsigned long long)hits;
+            }
         }
     }
-    if (ENERGY) {
+    if (ENERGY && !LIST) {
         __syncthreads();
         double vv[3] = { 0.5 * eV, 0.5 * eC, (double)nHit }; // every pair was visited from both sides
+        az_block_sum<3>(vv, s_red);
+        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Verlet-list force pass, used between cell-list rebuilds (opts.rebuild_every > 1, BASELINE config 3):
+// the rebuild step's tile pass (LIST=true above) stored, per atom, every j within rc + skin at
+// nbr[k * stride + i] (coalesced over i); the stale steps gather those j directly instead of sweeping
+// 27 cells.  One thread per atom, no atomics, same pair arithmetic and the same r2 <= r2Max gate on
+// current positions, so the pair set per step is identical to the every-step-rebuild schedule as
+// long as no atom moved more than skin/2 (tracked by az_k_integrate_a<false> / az_k_finalize).
+#define AZ_LIST_TPB 128
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+__global__ void __launch_bounds__(AZ_LIST_TPB)
+az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
+{
+    __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
+    __shared__ double s_red[96];
+    const int tid = threadIdx.x;
+    if (!SINGLE) {
+        for (int k = tid; k < P.nspec * P.nspec; k += AZ_LIST_TPB) s_tab[k] = A.table[k];
+        __syncthreads();
+    }
+    const int i = blockIdx.x * AZ_LIST_TPB + tid;
+    const bool act = i < P.n_local;
+    float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
+    int hits = 0, ti = 0;
+    if (act) {
+        const float4 pi = A.pos[i];
+        ti = __float_as_int(pi.w);
+        float radi = 0.f;
+        if (RADII) radi = A.therm[i].y;
+        const int cnt = A.nbrCount[i];
+        const int* __restrict__ row = A.nbr + i;
+        const size_t stride = (size_t)A.nbr_stride;
+        constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
+        const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
+        // one neighbour: decode, (rare) image shift, pair term, masked accumulate
+        auto one = [&](const int c, const float4 pj, const float radj) {
+            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            if ((unsigned)c > (unsigned)AZ_NBR_MASK) { // image signs above the index bits; zero for every interior pair
+                const int sc = (int)((unsigned)c >> AZ_NBR_BITS);
+                dx -= ((float)((sc >> 1) & 1) - (float)(sc & 1)) * P.L[0];
+                dy -= ((float)((sc >> 3) & 1) - (float)((sc >> 2) & 1)) * P.L[1];
+                dz -= ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
+            }
+            const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+            const bool in = r2 <= gate;
+            const int tj = __float_as_int(pj.w);
+            float e1 = 0.f, e2 = 0.f, f;
+            if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+            else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+            f = in ? f : 0.f;
+            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+            if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
+        };
+        // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
+        // gathers of chunk k (L1/L2) are consumed
+        int k = 0;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (cnt >= 4) { c0 = row[0]; c1 = row[stride]; c2 = row[2 * stride]; c3 = row[3 * stride]; }
+        for (; k + 4 <= cnt; k += 4) {
+            const float4 p0 = A.pos[c0 & AZ_NBR_MASK], p1 = A.pos[c1 & AZ_NBR_MASK];
+            const float4 p2 = A.pos[c2 & AZ_NBR_MASK], p3 = A.pos[c3 & AZ_NBR_MASK];
+            float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
+            if (RADII) { r0 = A.therm[c0 & AZ_NBR_MASK].y; r1 = A.therm[c1 & AZ_NBR_MASK].y; r2_ = A.therm[c2 & AZ_NBR_MASK].y; r3 = A.therm[c3 & AZ_NBR_MASK].y; }
+            int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            if (k + 8 <= cnt) {
+                n0 = row[(size_t)(k + 4) * stride]; n1 = row[(size_t)(k + 5) * stride];
+                n2 = row[(size_t)(k + 6) * stride]; n3 = row[(size_t)(k + 7) * stride];
+            }
+            one(c0, p0, r0); one(c1, p1, r1); one(c2, p2, r2_); one(c3, p3, r3);
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+        for (; k < cnt; k++) {
+            const int c = row[(size_t)k * stride];
+            const float4 pj = A.pos[c & AZ_NBR_MASK];
+            float radj = 0.f;
+            if (RADII) radj = A.therm[c & AZ_NBR_MASK].y;
+            one(c, pj, radj);
+        }
+        const float q = P.charge[ti];
+        A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+    }
+    if (ENERGY) {
+        double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
         az_block_sum<3>(vv, s_red);
         if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
     }

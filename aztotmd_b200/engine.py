@@ -225,7 +225,7 @@ class Engine:
     """One engine = one GPU.  ``lib`` defaults to the nvcc-built library (no fallback)."""
 
     def __init__(self, system, *, device: int = 0, rebuild_every: int = 1, skin: float = 0.0,
-                 cells_per_block: int = 0, pair_variant: int = 0, lib=None, opts: Optional[abi.az_cuda_opts] = None):
+                 cells_per_block: int = 0, pair_variant: int = 0, max_neigh: int = 0, lib=None, opts: Optional[abi.az_cuda_opts] = None):
         self.lib = lib if lib is not None else abi.load_library()
         if isinstance(system, System):
             self._holder = DescHolder(system)
@@ -242,6 +242,7 @@ class Engine:
             opts.skin = skin
             opts.cells_per_block = cells_per_block
             opts.pair_variant = pair_variant
+            opts.max_neigh = max_neigh
         self._h = C.c_void_p()
         rc = self.lib.az_engine_create(C.byref(desc), C.byref(opts), C.byref(self._h))
         if rc != abi.AZ_OK:

@@ -152,14 +152,15 @@ typedef struct az_cuda_opts {
     int rebuild_every;   /* 0/1 = reference behaviour (bin + sort every step)         */
     float skin;          /* extra cell width when rebuild_every > 1 (Angstrom)        */
     int use_graph;       /* 1 = capture the steady-state step in a CUDA graph         */
-    int pair_variant;    /* 0 = auto; tuning knob for the pair kernel                 */
+    int pair_variant;    /* 0 = auto (Verlet list between rebuilds), 1 = cell tiles only, 2 = list */
     int cells_per_block; /* 0 = auto; z-run length a CTA owns in the pair kernel      */
     /* spatial domain decomposition (new functionality) */
     int rank, n_ranks;
     int pgrid[3];        /* ranks along x,y,z; product = n_ranks; 0 -> {n_ranks,1,1}  */
     int ghost_slots;     /* fixed slots per ghost cell in halo messages; 0 = auto     */
     const void *nccl_id; /* ncclUniqueId bytes (128) shared by all ranks, or NULL     */
-    int reserved[8];
+    int max_neigh;       /* rows of the Verlet list per atom ('max_neigh' of control.txt); 0 = from density */
+    int reserved[7];
 } az_cuda_opts;
 
 /* Scalars of stat.dat / msd.dat for the last completed step
@@ -170,7 +171,7 @@ typedef struct az_stats {
     float engTot, engKin, engVdW, engCoul1, engCoul2, engTemp, engElecField, engPot;
     float posMom[3], negMom[3]; /* cumulative face momenta, src/cuMDfunc.cu:72-104 */
     float pressure;
-    float reserved;
+    float x_first;       /* xyz[0].x of the sorted stream: the 'x1=' of print_stat, src/cuMDfunc.cu:320 */
     int specAcBoxPos[AZ_MAX_SPECIES][3]; /* face crossing counters */
     int specAcBoxNeg[AZ_MAX_SPECIES][3];
     double engKin_d, engVdW_d, engCoul1_d, engTemp_d; /* unrounded accumulators */
@@ -241,7 +242,8 @@ int az_engine_upload(az_engine *e, const double *xs, const double *ys, const dou
 #define AZ_TIMER_PAIR 3        /* cell_list5a + cell_list4b_noshared       */
 #define AZ_TIMER_INTEGRATE_B 4 /* verlet_2stage + thermostat + quantities  */
 #define AZ_TIMER_HALO 5        /* multi-GPU halo / migration               */
-#define AZ_N_TIMERS 6
+#define AZ_TIMER_PAIR_LIST 6   /* Verlet-list force pass between rebuilds  */
+#define AZ_N_TIMERS 7
 int az_engine_profile(az_engine *e, int enable);
 int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
 long long az_engine_launch_count(az_engine *e); /* kernels launched since create */

@@ -58,7 +58,7 @@
 #include "../include/aztot_b200.h"
 
 #if defined(__GNUC__)
-#pragma STDC FP_CONTRACT OFF
+/* built with -ffp-contract=off (oracle/Makefile): products and sums round separately */
 #endif
 
 /* ------------------------------------------------------------------ RNG ---- */
@@ -727,6 +727,7 @@ int azo_stats(azo_state *s, az_stats *o)
     o->engElecField = (float)s->engElecField; o->engPot = s->engPot;
     for (int a = 0; a < 3; a++) { o->posMom[a] = (float)s->posMom[a]; o->negMom[a] = (float)s->negMom[a]; }
     o->pressure = s->pressure;
+    o->x_first = s->x[0];
     for (int t = 0; t < s->nspec; t++) for (int a = 0; a < 3; a++) {
         o->specAcBoxPos[t][a] = s->acPos[t][a]; o->specAcBoxNeg[t][a] = s->acNeg[t][a];
     }

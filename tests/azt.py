@@ -66,11 +66,16 @@ def emu_lib():
 class Oracle:
     """CPU restatement of the reference's step (oracle/az_oracle.c)."""
 
-    def __init__(self, system: System):
+    def __init__(self, system):
         self.lib = oracle_lib()
-        self._holder = DescHolder(system)
-        self.n = self._holder.n
-        self._h = self.lib.azo_create(C.byref(self._holder.desc))
+        if isinstance(system, System):
+            self._holder = DescHolder(system)
+            desc = self._holder.desc
+        else:  # a ctypes az_system_desc, e.g. from az_deck_desc
+            self._holder = None
+            desc = system
+        self.n = desc.n_atoms
+        self._h = self.lib.azo_create(C.byref(desc))
         assert self._h, "azo_create failed"
         d0 = self.dump_raw(ncell=1 << 24, probe=True)
         self.n_cells = d0

@@ -192,25 +192,63 @@ def case_face_crossings_and_pressure(lib):
     e.close()
 
 
-def case_rebuild_interval_equals_every_step(lib):
+def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e-5):
     """Extension (BASELINE config 3): binning every R steps with a skin gives the same forces and
-    energies as binning every step."""
-    s = azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3)  # 3 cells of 11.4 >= rc + skin
+    energies as binning every step.  variant 0 = Verlet list between rebuilds, 1 = stale cell tiles."""
     e1 = Engine(s, lib=lib)
-    e2 = Engine(s, lib=lib, rebuild_every=5, skin=0.8)
+    e2 = Engine(s, lib=lib, rebuild_every=5, skin=skin, pair_variant=variant)
     o = azt.Oracle(s)
     for eng in (e1, e2):
         eng.set_option("energy_every_step", 1)
-    for step in range(8):
+    for step in range(nsteps):
         e1.step(step, 1); e2.step(step, 1); o.step(step, 1)
-        s1, s2 = e1.stats(), e2.stats()
-        assert abs(s1.engVdW_d - s2.engVdW_d) <= 1e-5 * abs(s1.engVdW_d)
-        assert abs(s1.engKin_d - s2.engKin_d) <= 1e-5 * abs(s1.engKin_d)
+        s1, s2, so = e1.stats(), e2.stats(), o.stats()
+        sc = max(abs(s1.engVdW_d), abs(s1.engCoul1_d), abs(s1.engKin_d))
+        assert abs(s1.engVdW_d - s2.engVdW_d) <= tol * sc and abs(s1.engCoul1_d - s2.engCoul1_d) <= tol * sc
+        assert abs(s1.engKin_d - s2.engKin_d) <= tol * sc
+        assert s1.n_pairs == s2.n_pairs == o.pairs_in_range(), (s1.n_pairs, s2.n_pairs, o.pairs_in_range())
+        if thermo:
+            assert abs(s1.engTemp_d - s2.engTemp_d) <= 1e-4 * max(abs(s1.engTemp_d), 1e-6)
     a1, a2 = e1.download(abi.ORDER_ORIGINAL), e2.download(abi.ORDER_ORIGINAL)
     assert np.abs(a1["pos"] - a2["pos"]).max() < 1e-3 and np.abs(a1["vel"] - a2["vel"]).max() < 1e-3 * np.abs(a1["vel"]).max()
     ao = o.download(abi.ORDER_ORIGINAL)
     assert np.abs(ao["pos"] - a2["pos"]).max() < 1e-3
+    # forces of the last step, atom by atom (original order), against the oracle
+    d2, do = azt.sort_by_id(e2.dump()), azt.sort_by_id(o.dump())
+    fs = np.zeros(o.n, dtype=np.float32); fs[o.dump()["ids"]] = o.force_scale()
+    assert (np.abs(d2["frc"] - do["frc"]).max(1) <= 5e-4 * np.maximum(fs, 1e-10)).all()  # trajectories 8 steps apart in rounding
     e1.close(); e2.close()
+
+
+def case_rebuild_interval_list(lib):
+    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 0)
+
+
+def case_rebuild_interval_stale_tiles(lib):
+    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 1)
+
+
+def case_rebuild_interval_list_ionic(lib):
+    s = azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6)  # 3 cells of 9.83 >= rc + skin
+    _rebuild_vs_every_step(lib, s, 0.6, 0, nsteps=6)
+
+
+def case_rebuild_interval_list_surk_radiative(lib):
+    s = azt.surk_system(n_side=6, cell_size=3.3)
+    _rebuild_vs_every_step(lib, s, 0.5, 0, nsteps=6, thermo=True, tol=1e-4)
+
+
+def case_list_capacity_is_reported(lib):
+    s = azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3)
+    e = Engine(s, lib=lib, rebuild_every=5, skin=0.8, max_neigh=20)
+    e.step(0, 1)
+    try:
+        e.stats()
+    except AzError as err:
+        assert err.status == abi.AZ_ERR_OVERFLOW and "max_neigh" in str(err)
+    else:
+        raise AssertionError("neighbour-list overflow not reported")
+    e.close()
 
 
 def case_skin_violation_is_reported(lib):
@@ -303,7 +341,11 @@ ALL_CASES = [
     ("lj_radiative", case_lj_radiative),
     ("equilibration_scaling", case_equilibration_scaling),
     ("face_crossings_pressure", case_face_crossings_and_pressure),
-    ("rebuild_interval", case_rebuild_interval_equals_every_step),
+    ("rebuild_interval_list", case_rebuild_interval_list),
+    ("rebuild_interval_stale_tiles", case_rebuild_interval_stale_tiles),
+    ("rebuild_interval_list_ionic", case_rebuild_interval_list_ionic),
+    ("rebuild_interval_list_surk_radiative", case_rebuild_interval_list_surk_radiative),
+    ("list_capacity", case_list_capacity_is_reported),
     ("skin_violation", case_skin_violation_is_reported),
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
