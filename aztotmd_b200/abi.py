@@ -97,7 +97,8 @@ class az_engine_info_t(C.Structure):
     _fields_ = [("n_atoms", C.c_int), ("n_cells", C.c_int), ("cnum", C.c_int * 3), ("stencil", C.c_int * 3),
                 ("csize", C.c_float * 3), ("crev", C.c_float * 3), ("pair_blocks", C.c_int), ("pair_threads", C.c_int),
                 ("pair_smem_bytes", C.c_int), ("pair_zc", C.c_int), ("pair_vk", C.c_int), ("pair_ck", C.c_int),
-                ("n_sm", C.c_int), ("reserved", C.c_int), ("device_bytes", C.c_longlong)]
+                ("n_sm", C.c_int), ("max_neigh_seen", C.c_int), ("device_bytes", C.c_longlong),
+                ("list_rows", C.c_int), ("flags", C.c_int)]
 
 
 # every symbol include/aztot_b200.h declares: name -> (restype, argtypes)

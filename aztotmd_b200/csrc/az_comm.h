@@ -1,0 +1,35 @@
+// az_comm.h -- internal: the point-to-point plumbing of the spatial domain decomposition.
+// The reference has no communication layer at all (no NCCL/MPI, device 0 hard-coded);
+// this is new functionality.  One implementation ships: NCCL over NVLink/NVSwitch
+// (az_comm_nccl.cpp, libnccl loaded with dlopen so that single-GPU use needs no NCCL).  The emulator
+// build of tests/emu links an in-process mailbox instead (test infrastructure).
+#pragma once
+#include <stddef.h>
+#include <vector>
+#include <string>
+
+#ifdef AZ_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+struct AzP2P { // one exchange with a peer; either side may be empty
+    int peer;
+    const void* send; size_t send_bytes;
+    void* recv; size_t recv_bytes;
+};
+
+struct AzComm {
+    int rank = 0, nranks = 1;
+    std::string err;
+    virtual ~AzComm() {}
+    // All sends are posted in the order given; all receives in the order given.  Between one pair of
+    // ranks the k-th send matches the k-th receive.  Asynchronous on `st`.
+    virtual int exchange(const std::vector<AzP2P>& ops, cudaStream_t st) = 0;
+    virtual int allreduce_sum(double* dev, int n, cudaStream_t st) = 0;
+};
+
+// id: 128 bytes shared by all ranks (ncclUniqueId for the NCCL implementation).
+int az_comm_create(const void* id, int rank, int nranks, int device, AzComm** out, std::string* err);
+int az_comm_make_id(void* id128, std::string* err);

@@ -1,0 +1,96 @@
+// az_comm_nccl.cpp -- AzComm over NCCL (NVLink 5 / NVSwitch inside one box).  libnccl is loaded
+// with dlopen at the first multi-GPU create, so the single-GPU library has no NCCL dependency and
+// a process that already loaded NCCL (e.g. through torch) shares that copy.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include <nccl.h>
+
+#include "az_comm.h"
+#include "../../include/aztot_b200.h"
+
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_api;
+
+bool load_api(std::string* err)
+{
+    if (g_api.h) return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { if (err) *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define AZ_SYM(field, name) *(void**)(&g_api.field) = dlsym(h, name); if (!g_api.field) { if (err) *err = std::string("libnccl lacks ") + name; return false; }
+    AZ_SYM(GetUniqueId, "ncclGetUniqueId") AZ_SYM(CommInitRank, "ncclCommInitRank") AZ_SYM(CommDestroy, "ncclCommDestroy")
+    AZ_SYM(Send, "ncclSend") AZ_SYM(Recv, "ncclRecv") AZ_SYM(GroupStart, "ncclGroupStart") AZ_SYM(GroupEnd, "ncclGroupEnd")
+    AZ_SYM(AllReduce, "ncclAllReduce") AZ_SYM(GetErrorString, "ncclGetErrorString")
+#undef AZ_SYM
+    g_api.h = h;
+    return true;
+}
+
+struct NcclComm : AzComm {
+    ncclComm_t comm = nullptr;
+    ~NcclComm() override { if (comm) g_api.CommDestroy(comm); }
+    int fail(const char* what, ncclResult_t r)
+    {
+        err = std::string(what) + ": " + g_api.GetErrorString(r);
+        return AZ_ERR_COMM;
+    }
+    int exchange(const std::vector<AzP2P>& ops, cudaStream_t st) override
+    {
+        ncclResult_t r = g_api.GroupStart();
+        if (r != ncclSuccess) return fail("ncclGroupStart", r);
+        for (const AzP2P& o : ops)
+            if (o.send_bytes) { r = g_api.Send(o.send, o.send_bytes, ncclChar, o.peer, comm, st); if (r != ncclSuccess) { g_api.GroupEnd(); return fail("ncclSend", r); } }
+        for (const AzP2P& o : ops)
+            if (o.recv_bytes) { r = g_api.Recv(o.recv, o.recv_bytes, ncclChar, o.peer, comm, st); if (r != ncclSuccess) { g_api.GroupEnd(); return fail("ncclRecv", r); } }
+        r = g_api.GroupEnd();
+        if (r != ncclSuccess) return fail("ncclGroupEnd", r);
+        return AZ_OK;
+    }
+    int allreduce_sum(double* dev, int n, cudaStream_t st) override
+    {
+        ncclResult_t r = g_api.AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, comm, st);
+        if (r != ncclSuccess) return fail("ncclAllReduce", r);
+        return AZ_OK;
+    }
+};
+} // namespace
+
+int az_comm_make_id(void* id128, std::string* err)
+{
+    if (!load_api(err)) return AZ_ERR_COMM;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_api.GetUniqueId(&id);
+    if (r != ncclSuccess) { if (err) *err = std::string("ncclGetUniqueId: ") + g_api.GetErrorString(r); return AZ_ERR_COMM; }
+    memcpy(id128, &id, 128);
+    return AZ_OK;
+}
+
+int az_comm_create(const void* id, int rank, int nranks, int device, AzComm** out, std::string* err)
+{
+    if (!id) { if (err) *err = "multi-GPU create needs opts.nccl_id (128 bytes from az_comm_unique_id, shared by all ranks)"; return AZ_ERR_INVALID; }
+    if (!load_api(err)) return AZ_ERR_COMM;
+    if (cudaSetDevice(device) != cudaSuccess) { if (err) *err = "cudaSetDevice failed"; return AZ_ERR_CUDA; }
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    NcclComm* c = new NcclComm();
+    c->rank = rank; c->nranks = nranks;
+    ncclResult_t r = g_api.CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != ncclSuccess) { if (err) *err = std::string("ncclCommInitRank: ") + g_api.GetErrorString(r); delete c; return AZ_ERR_COMM; }
+    *out = c;
+    return AZ_OK;
+}

@@ -37,7 +37,13 @@ struct AzGrid {
     int sten[3];   // stencil half widths (cell_dist_int, src/cuCellList.cu:98-132)
     float csize[3], crev[3];
     int ncell_local;
+    // storage numbering of local cells: owned cells first (z fastest inside the owned block), ghost cells
+    // after them.  NULL on one GPU (identity: storage id == x*cnYZ + y*cNumber.z + z).
+    const int* cellmap;
 };
+
+// linear local coordinate (including ghost layers) -> storage cell id
+__device__ __forceinline__ int az_cell_id(const AzGrid& g, int lin) { return g.cellmap ? g.cellmap[lin] : lin; }
 
 struct AzParams {
     int n_local;        // atoms resident on this GPU that take part as i-atoms (owned)

@@ -91,7 +91,10 @@ static int stencil_half(int n, float csize, float rc)
 template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
 {
     AZ_CUDA(e, cudaMalloc(p, (count ? count : 1) * sizeof(T)));
+    // the engine's stream is non-blocking: a memset on the legacy stream is not ordered against it,
+    // so the clear is finished before the buffer can be used anywhere
     AZ_CUDA(e, cudaMemset(*p, 0, (count ? count : 1) * sizeof(T)));
+    AZ_CUDA(e, cudaStreamSynchronize(0));
     e->dev_bytes += (count ? count : 1) * sizeof(T);
     return AZ_OK;
 }
@@ -309,6 +312,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
             if (rho < rho_avg) rho = rho_avg;
             cap = (int)(1.5 * rho * 4.18879 * rl * rl * rl) + 32;
         }
+        if (cap >= (1 << AZ_NBR_CNT_BITS) / 2) { AZ_SET_ERR(e, "max_neigh %d is beyond the list format (%d rows)", cap, (1 << AZ_NBR_CNT_BITS) / 2 - 1); return AZ_ERR_INVALID; }
         e->nbr_cap = cap;
         e->nbr_stride = (n + 31) / 32 * 32;
         AZ_ALLOC(e, e->nbr, (size_t)e->nbr_cap * e->nbr_stride);
@@ -423,9 +427,9 @@ static int one_step(az_engine* e, int step, bool want_energy)
         if (P.has_efield) { AZ_LAUNCH(az_k_reset_step, 1, 1, 0, st, e->sc); AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1); }
         if (rebuild) {
             AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist
-            AZ_LAUNCH(az_k_integrate_a<true>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_BIN>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         } else {
-            AZ_LAUNCH(az_k_integrate_a<false>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_STALE>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         }
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1);
     }
@@ -533,7 +537,7 @@ static int fetch_scalars(az_engine* e, AzScalars* h)
     AZ_CUDA(e, cudaGetLastError());
     if (h->overflow & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
     if (h->overflow & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
-    if (h->overflow & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius: raise 'max_neigh'", e->nbr_cap); return AZ_ERR_OVERFLOW; }
+    if (h->overflow & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius (worst row: %d): raise 'max_neigh'", e->nbr_cap, h->dbg_count); return AZ_ERR_OVERFLOW; }
     if (h->overflow & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a ghost cell overflowed its halo slots"); return AZ_ERR_OVERFLOW; }
     return AZ_OK;
 }
@@ -738,6 +742,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
 {
     if (!e || !key) return AZ_ERR_INVALID;
     if (!strcmp(key, "energy_every_step")) { e->energy_every_step = value != 0.0; return AZ_OK; }
+    if (!strcmp(key, "list_pipe")) { e->list_pipe = (int)value; return AZ_OK; }
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;
 }
@@ -752,5 +757,20 @@ extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
     o->pair_blocks = e->pair_nblocks; o->pair_threads = AZ_PAIR_TPB; o->pair_smem_bytes = (int)e->pair_smem;
     o->pair_zc = e->pair_zc; o->pair_vk = e->pair_vk; o->pair_ck = e->pair_ck;
     o->n_sm = e->n_sm; o->device_bytes = (long long)e->dev_bytes;
+    o->list_rows = e->nbr_cap;
+    if (e->sc) {
+        AZ_CUDA(e, cudaSetDevice(e->device));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        AzScalars h;
+        AZ_CUDA(e, cudaMemcpy(&h, e->sc, sizeof(h), cudaMemcpyDeviceToHost));
+        o->flags = h.overflow;
+        if (e->use_list && e->binned) {
+            std::vector<int> cnt(e->n);
+            AZ_CUDA(e, cudaMemcpy(cnt.data(), e->nbrCount, sizeof(int) * e->n, cudaMemcpyDeviceToHost));
+            int mx = 0;
+            for (int v : cnt) { int t = (v & ((1 << AZ_NBR_CNT_BITS) - 1)) + (v >> AZ_NBR_CNT_BITS); if (t > mx) mx = t; }
+            o->max_neigh_seen = mx;
+        }
+    }
     return AZ_OK;
 }

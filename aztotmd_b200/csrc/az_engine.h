@@ -29,6 +29,7 @@ struct az_engine {
     // Verlet-list path (rebuild_every > 1)
     bool use_list = false;
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
+    int list_pipe = 0; // software-pipeline depth of the list force pass (0, 2, 4 neighbours per stage)
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;
     // device state

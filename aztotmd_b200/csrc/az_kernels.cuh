@@ -52,7 +52,8 @@ struct AzScalars {
     int iMom;
     float pressure, engTot, engPot;
     int step;
-    int overflow; // sticky error flags: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots, 16 neighbour-list rows
+    int overflow, dbg_count, dbg_atom; // sticky error flags (+ worst list row count and the atom it belongs to)
+    // flags:: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots, 16 neighbour-list rows
     float tscale_k;
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
@@ -67,8 +68,12 @@ struct AzScalars {
 
 // ---------------------------------------------------------------------------------------
 // K1: verlet_1stage (src/cuMDfunc.cu:333-518) + put_periodic (:35-106) + count_cell
-// (src/cuSort.cu:114-128).  BIN=false is the stale-cell variant used between rebuilds.
-template <bool BIN>
+// (src/cuSort.cu:114-128).  MODE 0: stale cells between rebuilds (no wrap, no bin); 1: wrap + bin
+// (one GPU); 2: wrap only (domain decomposition: migration comes between wrap and bin, az_k_bin bins).
+#define AZ_IA_STALE 0
+#define AZ_IA_BIN 1
+#define AZ_IA_WRAP 2
+template <int MODE>
 __global__ void __launch_bounds__(AZ_TPB)
 az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, float4* __restrict__ vel,
                  const float4* __restrict__ frc, int* __restrict__ cellOf, int* __restrict__ slotOf,
@@ -85,7 +90,7 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
         v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
         if (!P.frozen[t]) { p.x = fmaf(v.x, P.tSt, p.x); p.y = fmaf(v.y, P.tSt, p.y); p.z = fmaf(v.z, P.tSt, p.z); }
         v2 = v.x * v.x + v.y * v.y + v.z * v.z;
-        if (BIN) {
+        if (MODE != AZ_IA_STALE) {
             float m = P.mass[t];
             float* pc[3] = { &p.x, &p.y, &p.z };
             float vc[3] = { v.x, v.y, v.z };
@@ -102,10 +107,11 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
                 c = max(0, min(c, P.g.n[a] - 1));
                 ci[a] = c;
             }
-            // local cell id (== global id on one GPU: x*cnYZ + y*cNumber.z + z)
-            int lc = ((ci[0] - P.g.goff[0]) * P.g.nl[1] + (ci[1] - P.g.goff[1])) * P.g.nl[2] + (ci[2] - P.g.goff[2]);
-            cellOf[i] = lc;
-            slotOf[i] = atomicAdd(&cellCount[lc], 1);
+            if (MODE == AZ_IA_BIN) { // storage cell id (== global id on one GPU: x*cnYZ + y*cNumber.z + z)
+                int lc = ((ci[0] - P.g.goff[0]) * P.g.nl[1] + (ci[1] - P.g.goff[1])) * P.g.nl[2] + (ci[2] - P.g.goff[2]);
+                cellOf[i] = lc;
+                slotOf[i] = atomicAdd(&cellCount[lc], 1);
+            }
         }
         pos[i] = p; vel[i] = v;
         if (P.has_efield) {
@@ -113,7 +119,7 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
             eF = (double)(q * (p.x * P.efield[0] + p.y * P.efield[1] + p.z * P.efield[2]));
         }
     }
-    if (!BIN) { // stale cells: bound the drift since the last rebuild by the fastest atom
+    if (MODE == AZ_IA_STALE) { // stale cells: bound the drift since the last rebuild by the fastest atom
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));
         // one atomic per warp only while the running maximum is still smaller (a handful per launch)

@@ -31,7 +31,7 @@ struct AzPairArgs {
     double* partC;
     unsigned long long* partN; // per-CTA count of in-range pair visits (ENERGY passes only)
     int* flags;              // sticky error flags (AzScalars::overflow)
-    int* nbr;                // LIST build: neighbour codes, row k of atom i at nbr[k * nbr_stride + i]
+    int* nbr;                // Verlet list, blocked by warp: row k of atom i at nbr[((i >> 5) * nbr_cap + k) * 32 + (i & 31)]
     int* nbrCount;           // LIST build: neighbours of atom i within the list radius
     int nbr_stride, nbr_cap;
     int zc;                  // z-run length per CTA
@@ -59,7 +59,7 @@ __device__ __forceinline__ bool az_neighbor(const AzGrid& g, int a, int cglob, i
 }
 
 // Neighbour code of the Verlet-list path: sorted index of j in the low 26 bits, image signs
-// (0 none, 1 = -L, 2 = +L per axis) above them.
+// (0 none, 1 = -L, 2 = +L per axis) above them (imaged neighbours only, see az_k_build_list).
 #define AZ_NBR_BITS 26
 #define AZ_NBR_MASK ((1 << AZ_NBR_BITS) - 1)
 __device__ __forceinline__ int az_shift_code(int shx, int shy, int shz)
@@ -71,14 +71,12 @@ __device__ __forceinline__ int az_shift_code(int shx, int shy, int shz)
 // SHIFT=false is the interior case (all three image shifts are zero: (xi - xj) - 0 == xi - xj exactly).
 // `lim` is the lane's gate: r2Max (folded with r2cut when there is a single table entry and no
 // Coulomb) if the lane's cell pairs with this window entry, -1 otherwise.
-// LIST=true only records the neighbours inside the list radius (no pair arithmetic): the rebuild
-// step of the Verlet-list path; the forces of that step come from az_k_pair_list like all others.
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool LIST, bool SHIFT>
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool SHIFT>
 __device__ __forceinline__ void az_sweep_cell(const AzParams& P, const AzPairArgs& A, const AzVdw* __restrict__ s_tab,
                                               const float4* __restrict__ s_tile, const float* __restrict__ s_tile_rad,
                                               int jb, int je, int self, float lim, const float4 pi, int ti, float radi,
-                                              float shx, float shy, float shz, int i, int gbase, int code,
-                                              float& fx, float& fy, float& fz, float& ev, float& ec, int& hits, int& nnb)
+                                              float shx, float shy, float shz,
+                                              float& fx, float& fy, float& fz, float& ev, float& ec, int& hits)
 {
     constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
 #pragma unroll 4
@@ -88,26 +86,19 @@ __device__ __forceinline__ void az_sweep_cell(const AzParams& P, const AzPairArg
         if (SHIFT) { dx -= shx; dy -= shy; dz -= shz; }
         const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); // nvcc's contraction of dx*dx+dy*dy+dz*dz
         const bool in = r2 <= lim && j != self;
-        if (LIST) {
-            if (in) {
-                if (nnb < A.nbr_cap) A.nbr[(size_t)nnb * A.nbr_stride + i] = (gbase + (j - jb)) | (code << AZ_NBR_BITS);
-                nnb++;
-            }
-        } else {
-            const int tj = __float_as_int(pj.w);
-            float radj = 0.f;
-            if (RADII) radj = s_tile_rad[j];
-            float e1 = 0.f, e2 = 0.f, f;
-            if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
-            else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
-            f = in ? f : 0.f;
-            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
-            if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
-        }
+        const int tj = __float_as_int(pj.w);
+        float radj = 0.f;
+        if (RADII) radj = s_tile_rad[j];
+        float e1 = 0.f, e2 = 0.f, f;
+        if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+        else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+        f = in ? f : 0.f;
+        fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+        if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
     }
 }
 
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool LIST>
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 __global__ void __launch_bounds__(AZ_PAIR_TPB)
 az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
@@ -136,7 +127,9 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
         for (int k = tid; k < P.nspec * P.nspec; k += AZ_PAIR_TPB) s_tab[k] = A.table[k];
     }
 
-    const int cell0 = (lcx * g.nl[1] + lcy) * g.nl[2] + lz0;
+    // owned cells are numbered first, z fastest inside the owned block: the run's cells and atoms are contiguous
+    const int onz = g.ohi[2] - g.olo[2];
+    const int cell0 = ((lcx - g.olo[0]) * ony + (lcy - g.olo[1])) * onz + (lz0 - g.olo[2]);
     const int iBeg = A.first[cell0];
     const int iEnd = A.first[cell0 + zcnt - 1] + A.count[cell0 + zcnt - 1];
 
@@ -144,8 +137,8 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 
     double eV = 0.0, eC = 0.0;
     unsigned long long nHit = 0;
-    // the pair gate: list radius when recording neighbours, else r2Max (folded with the only r2cut when possible)
-    const float gate = LIST ? P.r2list : ((SINGLE && CK == AZ_ELEC_NONE) ? fminf(P.r2max, A.single.r2cut) : P.r2max);
+    // the pair gate: r2Max (folded with the only r2cut when possible)
+    const float gate = (SINGLE && CK == AZ_ELEC_NONE) ? fminf(P.r2max, A.single.r2cut) : P.r2max;
     for (int ib = iBeg; ib < iEnd; ib += AZ_PAIR_TPB) {
         const int i = ib + tid;
         const bool act = i < iEnd;
@@ -156,13 +149,13 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
             pi = A.pos[i];
             ti = __float_as_int(pi.w);
             int ci = A.cellOfSorted[i];
-            lzi = ci % g.nl[2];
+            lzi = g.olo[2] + ci % onz;
             rank_i = i - A.first[ci];
             if (RADII) radi = A.therm[i].y;
         }
         const int gzi = lzi + g.goff[2];
         float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
-        int hits = 0, nnb = 0;
+        int hits = 0;
 
         for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
             int sx, shxi;
@@ -189,7 +182,7 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                     if (u >= -n && u < 2 * n) { // farther images are never valid neighbours
                         sh = (u < 0) ? -1 : ((u >= n) ? 1 : 0);
                         const int st = g.dec[2] ? (u - g.goff[2]) : (u - sh * n);
-                        if (st >= 0 && st < g.nl[2]) { cnt = A.count[colbase + st]; gi = A.first[colbase + st]; }
+                        if (st >= 0 && st < g.nl[2]) { const int cid = az_cell_id(g, colbase + st); cnt = A.count[cid]; gi = A.first[cid]; }
                     }
                     s_cs[tid + 1] = cnt;
                     s_g[tid] = gi;
@@ -249,14 +242,12 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
                         const float shz = s_shz[w];
                         const int self = (centre && oz == 0 && valid) ? jb + rank_i : -1;
                         const float lim = valid ? gate : -1.f;
-                        const int shzi = (shz < 0.f) ? -1 : ((shz > 0.f) ? 1 : 0);
-                        const int code = LIST ? az_shift_code(shxi, shyi, shzi) : 0;
-                        if (shxi == 0 && shyi == 0 && shzi == 0)
-                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, LIST, false>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
-                                                                                      0.f, 0.f, 0.f, i, s_g[w], code, fx, fy, fz, ev, ec, hits, nnb);
+                        if (shxi == 0 && shyi == 0 && shz == 0.f)
+                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, false>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
+                                                                                0.f, 0.f, 0.f, fx, fy, fz, ev, ec, hits);
                         else
-                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, LIST, true>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
-                                                                                     shx, shy, shz, i, s_g[w], code, fx, fy, fz, ev, ec, hits, nnb);
+                            az_sweep_cell<VK, CK, SINGLE, RADII, ENERGY, true>(P, A, s_tab, s_tile, s_tile_rad, jb, je, self, lim, pi, ti, radi,
+                                                                               shx, shy, shz, fx, fy, fz, ev, ec, hits);
                     }
                     w0 = w1;
                     if (w0 < W) __syncthreads(); // tile is about to be overwritten
@@ -264,18 +255,13 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
             }
         }
         if (act) {
-            if (LIST) {
-                A.nbrCount[i] = min(nnb, A.nbr_cap);
-                if (nnb > A.nbr_cap) atomicOr(A.flags, AZ_FLAG_NBR);
-            } else {
-                const float q = P.charge[ti];
-                // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
-                A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
-                eV += (double)ev; eC += (double)ec; nHit += (unsigned long long)hits;
-            }
+            const float q = P.charge[ti];
+            // verlet_1stage leaves f = -q*E before the pair kernels add to it (src/cuMDfunc.cu:474)
+            A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+            eV += (double)ev; eC += (double)ec; nHit += (unsigned long long)hits;
         }
     }
-    if (ENERGY && !LIST) {
+    if (ENERGY) {
         __syncthreads();
         double vv[3] = { 0.5 * eV, 0.5 * eC, (double)nHit }; // every pair was visited from both sides
         az_block_sum<3>(vv, s_red);
@@ -285,14 +271,117 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 
 
 // ---------------------------------------------------------------------------------------
-// Verlet-list force pass, used between cell-list rebuilds (opts.rebuild_every > 1, BASELINE config 3):
-// the rebuild step's tile pass (LIST=true above) stored, per atom, every j within rc + skin at
-// nbr[k * stride + i] (coalesced over i); the stale steps gather those j directly instead of sweeping
-// 27 cells.  One thread per atom, no atomics, same pair arithmetic and the same r2 <= r2Max gate on
-// current positions, so the pair set per step is identical to the every-step-rebuild schedule as
-// long as no atom moved more than skin/2 (tracked by az_k_integrate_a<false> / az_k_finalize).
+// Verlet-list path (opts.rebuild_every > 1, BASELINE config 3).  Layout: atoms are taken in blocks of
+// 32 (one warp); row k of atom i lives at nbr[((i >> 5) * cap + k) * 32 + (i & 31)], so a warp reads
+// one 128-byte line per row and streams through ONE contiguous region of cap * 128 bytes (a layout
+// with row stride n_atoms touches a different DRAM page for every row).  Neighbours that need no
+// periodic image fill the rows from 0 upwards and hold the bare sorted index of j; the few that do
+// (atoms next to a box face) fill the rows from cap-1 downwards and carry the image signs above the
+// index bits, so the hot loop of the force pass never looks at a shift.
+// nbrCount[i] = plain | imaged << 16.
+//
+// az_k_build_list: the rebuild step.  One thread per atom walks the cells of its stencil straight
+// from the sorted stream (neighbouring lanes sit in the same or the next cell, so the float4 loads
+// are L1 broadcasts); runs of cells that are adjacent in memory (the z neighbours of one column) are
+// merged into one j-range.  delta and r2 are formed exactly like the force pass forms them, so with
+// skin == 0 the recorded set is the in-range set.
 #define AZ_LIST_TPB 128
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+#define AZ_NBR_CNT_BITS 16
+
+__device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)(i >> 5) * (size_t)cap) * 32 + (size_t)(i & 31); }
+
+static __global__ void __launch_bounds__(AZ_LIST_TPB)
+az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
+{
+    const AzGrid& g = P.g;
+    const int i = blockIdx.x * AZ_LIST_TPB + threadIdx.x;
+    if (i >= P.n_local) return;
+    const float4 pi = A.pos[i];
+    // owned cells are numbered first, z fastest inside the owned block
+    const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+    const int ci = A.cellOfSorted[i];
+    const int cxy = ci / onz;
+    const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+    const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+    const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+    const int cap = A.nbr_cap;
+    int* __restrict__ rows = A.nbr + az_nbr_base(i, cap);
+#ifndef AZ_EMU
+    asm volatile("" : "+l"(rows)); // keep the row base in a register pair: one IMAD.WIDE per store instead of re-deriving it
+#endif
+    int nA = 0, nB = 0;
+    const float lim = P.r2list;
+
+    // all j of one contiguous range against atom i
+    auto sweep = [&](const int rb, const int re, const int code) {
+        if (code == 0) {
+            const int room = cap - nB;
+#pragma unroll 4
+            for (int j = rb; j < re; j++) {
+                const float4 pj = __ldg(A.pos + j);
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                const bool hit = (r2 <= lim) & (j != i);
+                if (hit & (nA < room)) rows[nA * 32] = j;
+                nA += hit ? 1 : 0;
+            }
+        } else {
+            const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
+            const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
+            const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
+            const int room = cap - nA;
+            for (int j = rb; j < re; j++) {
+                const float4 pj = __ldg(A.pos + j);
+                const float dx = (pi.x - pj.x) - shx, dy = (pi.y - pj.y) - shy, dz = (pi.z - pj.z) - shz;
+                const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                const bool hit = (r2 <= lim) & (j != i);
+                if (hit & (nB < room)) rows[(cap - 1 - nB) * 32] = j | (code << AZ_NBR_BITS);
+                nB += hit ? 1 : 0;
+            }
+        }
+    };
+
+    int rb = 0, re = 0, rcode = 0; // pending range
+    for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
+        int sx, shxi;
+        if (!az_neighbor(g, 0, gcx, ox, sx, shxi)) continue;
+        const int aox = ox < 0 ? -ox : ox;
+        const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+        for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
+            int sy, shyi;
+            if (!az_neighbor(g, 1, gcy, oy, sy, shyi)) continue;
+            const int aoy = oy < 0 ? -oy : oy;
+            const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+            const float mxy2 = mx * mx + my * my;
+            if (mxy2 > lim) continue;
+            const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
+            for (int oz = -g.sten[2]; oz <= g.sten[2]; oz++) {
+                int sz, shzi;
+                if (!az_neighbor(g, 2, gcz, oz, sz, shzi)) continue;
+                const int aoz = oz < 0 ? -oz : oz;
+                const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+                if (mxy2 + mz * mz > lim) continue;
+                const int cid = az_cell_id(g, colbase + sz);
+                const int jb = A.first[cid], je = jb + A.count[cid];
+                const int code = az_shift_code(shxi, shyi, shzi);
+                if (jb == re && code == rcode) re = je;
+                else {
+                    if (re > rb) sweep(rb, re, rcode);
+                    rb = jb; re = je; rcode = code;
+                }
+            }
+        }
+    }
+    if (re > rb) sweep(rb, re, rcode);
+    if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }
+    A.nbrCount[i] = nA | (nB << AZ_NBR_CNT_BITS);
+}
+
+// az_k_pair_list: the force pass of every step of the list path (the rebuild step's forces come from
+// it too).  One thread per atom, no atomics, same pair arithmetic and the same r2 <= r2Max gate on
+// current positions as the cell sweep, so the pair set per step is identical to the every-step-rebuild
+// schedule as long as no atom moved more than skin/2 (tracked by az_k_integrate_a / az_k_finalize).
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, int PIPE>
 __global__ void __launch_bounds__(AZ_LIST_TPB)
 az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
@@ -312,20 +401,13 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         ti = __float_as_int(pi.w);
         float radi = 0.f;
         if (RADII) radi = A.therm[i].y;
-        const int cnt = A.nbrCount[i];
-        const int* __restrict__ row = A.nbr + i;
-        const size_t stride = (size_t)A.nbr_stride;
+        const int cnt2 = A.nbrCount[i];
+        const int cnt = cnt2 & ((1 << AZ_NBR_CNT_BITS) - 1), cntB = cnt2 >> AZ_NBR_CNT_BITS;
+        constexpr int stride = 32; // ints between consecutive rows of one atom (one 128-byte line per warp and row)
         constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
         const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
-        // one neighbour: decode, (rare) image shift, pair term, masked accumulate
-        auto one = [&](const int c, const float4 pj, const float radj) {
-            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-            if ((unsigned)c > (unsigned)AZ_NBR_MASK) { // image signs above the index bits; zero for every interior pair
-                const int sc = (int)((unsigned)c >> AZ_NBR_BITS);
-                dx -= ((float)((sc >> 1) & 1) - (float)(sc & 1)) * P.L[0];
-                dy -= ((float)((sc >> 3) & 1) - (float)((sc >> 2) & 1)) * P.L[1];
-                dz -= ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
-            }
+        // one neighbour: pair term from the finished delta, masked accumulate
+        auto one = [&](const float dx, const float dy, const float dz, const float4 pj, const float radj) {
             const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             const bool in = r2 <= gate;
             const int tj = __float_as_int(pj.w);
@@ -336,30 +418,90 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
             if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
         };
-        // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
-        // gathers of chunk k (L1/L2) are consumed
+        auto plain = [&](const float4 pj, const float radj) { one(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z, pj, radj); };
+        const int* __restrict__ const rows = A.nbr + az_nbr_base(i, A.nbr_cap);
+        const int* __restrict__ row = rows;
         int k = 0;
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (cnt >= 4) { c0 = row[0]; c1 = row[stride]; c2 = row[2 * stride]; c3 = row[3 * stride]; }
-        for (; k + 4 <= cnt; k += 4) {
-            const float4 p0 = A.pos[c0 & AZ_NBR_MASK], p1 = A.pos[c1 & AZ_NBR_MASK];
-            const float4 p2 = A.pos[c2 & AZ_NBR_MASK], p3 = A.pos[c3 & AZ_NBR_MASK];
-            float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
-            if (RADII) { r0 = A.therm[c0 & AZ_NBR_MASK].y; r1 = A.therm[c1 & AZ_NBR_MASK].y; r2_ = A.therm[c2 & AZ_NBR_MASK].y; r3 = A.therm[c3 & AZ_NBR_MASK].y; }
-            int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-            if (k + 8 <= cnt) {
-                n0 = row[(size_t)(k + 4) * stride]; n1 = row[(size_t)(k + 5) * stride];
-                n2 = row[(size_t)(k + 6) * stride]; n3 = row[(size_t)(k + 7) * stride];
+        if (PIPE == 0) {
+            // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
+            // gathers of chunk k (L1/L2) are consumed
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (cnt >= 4) { c0 = row[0]; c1 = row[stride]; c2 = row[2 * stride]; c3 = row[3 * stride]; }
+            for (; k + 4 <= cnt; k += 4) {
+                row += 4 * stride;
+                const float4 p0 = __ldg(A.pos + c0), p1 = __ldg(A.pos + c1), p2 = __ldg(A.pos + c2), p3 = __ldg(A.pos + c3);
+                float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
+                if (RADII) { r0 = A.therm[c0].y; r1 = A.therm[c1].y; r2_ = A.therm[c2].y; r3 = A.therm[c3].y; }
+                int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                if (k + 8 <= cnt) { n0 = row[0]; n1 = row[stride]; n2 = row[2 * stride]; n3 = row[3 * stride]; }
+                plain(p0, r0); plain(p1, r1); plain(p2, r2_); plain(p3, r3);
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }
-            one(c0, p0, r0); one(c1, p1, r1); one(c2, p2, r2_); one(c3, p3, r3);
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        } else {
+            // two-deep pipeline: indices run two chunks ahead of the arithmetic, gathered positions one chunk
+            constexpr int U = PIPE > 0 ? PIPE : 1;
+            const int nfull = cnt / U;
+            int ic[U], in_[U];
+            float4 pc[U];
+            float rc_[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { ic[u] = 0; in_[u] = 0; pc[u] = make_float4(0.f, 0.f, 0.f, 0.f); rc_[u] = 0.f; }
+            if (nfull > 0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) ic[u] = row[u * stride];
+                row += U * stride;
+            }
+            if (nfull > 1) {
+#pragma unroll
+                for (int u = 0; u < U; u++) in_[u] = row[u * stride];
+                row += U * stride;
+            }
+            if (nfull > 0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) { pc[u] = __ldg(A.pos + ic[u]); if (RADII) rc_[u] = A.therm[ic[u]].y; }
+            }
+            for (int c = 0; c < nfull; c++) {
+                float4 pn[U];
+                float rn[U];
+                int i2[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { pn[u] = pc[u]; rn[u] = 0.f; i2[u] = 0; }
+                if (c + 1 < nfull) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) { pn[u] = __ldg(A.pos + in_[u]); if (RADII) rn[u] = A.therm[in_[u]].y; }
+                }
+                if (c + 2 < nfull) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) i2[u] = row[u * stride];
+                    row += U * stride;
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) plain(pc[u], rc_[u]);
+#pragma unroll
+                for (int u = 0; u < U; u++) { pc[u] = pn[u]; rc_[u] = rn[u]; in_[u] = i2[u]; }
+            }
+            k = nfull * U;
+            row = rows + k * stride;
         }
         for (; k < cnt; k++) {
-            const int c = row[(size_t)k * stride];
-            const float4 pj = A.pos[c & AZ_NBR_MASK];
+            const int c = *row; row += stride;
+            const float4 pj = __ldg(A.pos + c);
             float radj = 0.f;
-            if (RADII) radj = A.therm[c & AZ_NBR_MASK].y;
-            one(c, pj, radj);
+            if (RADII) radj = A.therm[c].y;
+            plain(pj, radj);
+        }
+        // neighbours through a periodic face: rows cap-1 downwards, image signs above the index bits
+        const int* __restrict__ rowB = rows + (A.nbr_cap - 1) * stride;
+        for (int kb = 0; kb < cntB; kb++) {
+            const int c = *rowB; rowB -= stride;
+            const int j = c & AZ_NBR_MASK, sc = (int)((unsigned)c >> AZ_NBR_BITS);
+            const float4 pj = __ldg(A.pos + j);
+            float radj = 0.f;
+            if (RADII) radj = A.therm[j].y;
+            const float sx = ((float)((sc >> 1) & 1) - (float)(sc & 1)) * P.L[0];
+            const float sy = ((float)((sc >> 3) & 1) - (float)((sc >> 2) & 1)) * P.L[1];
+            const float sz = ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
+            one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
         const float q = P.charge[ti];
         A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);

@@ -7,26 +7,28 @@
 #define AZ_PAIR_MODE_TILE_LIST 1
 #define AZ_PAIR_MODE_LIST 2
 
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool LIST>
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_go(az_engine* e, const AzPairArgs& A)
 {
 #ifndef AZ_EMU
     static size_t attr_smem[16] = {};
     if (e->pair_smem > 48 * 1024 && e->pair_smem > attr_smem[e->device & 15]) {
-        cudaError_t err = cudaFuncSetAttribute(az_k_pair<VK, CK, SINGLE, RADII, ENERGY, LIST>,
+        cudaError_t err = cudaFuncSetAttribute(az_k_pair<VK, CK, SINGLE, RADII, ENERGY>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pair_smem);
         if (err != cudaSuccess) { e->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err); return AZ_ERR_CUDA; }
         attr_smem[e->device & 15] = e->pair_smem;
     }
 #endif
-    AZ_LAUNCH((az_k_pair<VK, CK, SINGLE, RADII, ENERGY, LIST>), e->pair_nblocks, AZ_PAIR_TPB, e->pair_smem, e->stream, e->P, A);
+    AZ_LAUNCH((az_k_pair<VK, CK, SINGLE, RADII, ENERGY>), e->pair_nblocks, AZ_PAIR_TPB, e->pair_smem, e->stream, e->P, A);
     return AZ_OK;
 }
 
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 {
-    AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    if (e->list_pipe == 4) AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 4>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    else if (e->list_pipe == 2) AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 2>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    else AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 0>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
 }
 
@@ -36,9 +38,8 @@ static int az_pair_go_e(az_engine* e, const AzPairArgs& A, bool energy, int mode
     if (mode == AZ_PAIR_MODE_LIST)
         return energy ? az_pair_list_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_list_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_TILE_LIST) { // record the neighbours, then take this step's forces from the list like every other step
-        int rc = az_pair_go<VK, CK, SINGLE, RADII, false, true>(e, A);
-        if (rc) return rc;
+        AZ_LAUNCH(az_k_build_list, e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
         return energy ? az_pair_list_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_list_go<VK, CK, SINGLE, RADII, false>(e, A);
     }
-    return energy ? az_pair_go<VK, CK, SINGLE, RADII, true, false>(e, A) : az_pair_go<VK, CK, SINGLE, RADII, false, false>(e, A);
+    return energy ? az_pair_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_go<VK, CK, SINGLE, RADII, false>(e, A);
 }

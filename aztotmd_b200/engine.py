@@ -274,6 +274,10 @@ class Engine:
     def __exit__(self, *a):
         self.close()
 
+    def refresh_info(self) -> abi.az_engine_info_t:
+        self._check(self.lib.az_engine_info(self._h, C.byref(self.info)))
+        return self.info
+
     def step(self, first_step: int, nsteps: int = 1):
         self._check(self.lib.az_engine_step(self._h, first_step, nsteps))
 

@@ -49,14 +49,14 @@ WORKLOADS = {
 AR_EPS, AR_SIGMA, AR_MASS = 0.01006, 3.3952, 39.9
 
 
-def lj_system(ncell, rebuild, skin, seed=12345):
+def lj_system(ncell, rebuild, skin, seed=12345, cell_div=1):
     from aztotmd_b200.decks import fcc_positions
     from aztotmd_b200.engine import Species, System
     a = (4.0 / 0.8442) ** (1.0 / 3.0) * AR_SIGMA
     pos, box = fcc_positions((ncell,) * 3, a, jitter=0.05, seed=1)
     rc = 2.5 * AR_SIGMA
     s = System(pos=pos, types=np.zeros(len(pos), dtype=np.int32), box=box, species=[Species("Ar", AR_MASS)],
-               timestep=0.001, cell_size=rc + (skin if rebuild > 1 else 0.0), temperature=86.6, seed=seed)
+               timestep=0.001, cell_size=(rc + (skin if rebuild > 1 else 0.0)) / cell_div, temperature=86.6, seed=seed)
     s.set_vdw(0, 0, "lnjs", rc, [AR_EPS, AR_SIGMA])
     s.vel = s.gauss_velocities(seed)
     return s
@@ -165,8 +165,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lj4m", choices=sorted(WORKLOADS))
     ap.add_argument("--rebuild", type=int, default=10)
-    ap.add_argument("--skin", type=float, default=0.4)
+    ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--pair-variant", type=int, default=0, help="0 auto (Verlet list between rebuilds), 1 cell tiles only")
+    ap.add_argument("--list-pipe", type=int, default=-1, help="software-pipeline depth of the list force pass (experiment)")
+    ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -208,8 +210,10 @@ def main():
     assert lib.az_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)) == 0
     fp32_peak = tf.value
 
-    s = lj_system(ncell, args.rebuild, args.skin)
+    s = lj_system(ncell, args.rebuild, args.skin, cell_div=args.cell_div)
     e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0, pair_variant=args.pair_variant)
+    if args.list_pipe >= 0:
+        e.set_option("list_pipe", args.list_pipe)
     K, W = args.steps, args.warmup
     e.step(0, W)
     st = e.stats()  # also surfaces skin/overflow errors early

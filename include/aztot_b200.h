@@ -272,8 +272,9 @@ typedef struct az_engine_info_t {
     float csize[3], crev[3];
     int pair_blocks, pair_threads, pair_smem_bytes, pair_zc, pair_vk, pair_ck;
     int n_sm;
-    int reserved;
+    int max_neigh_seen;  /* largest Verlet-list row count of the last rebuild (0 without a list) */
     long long device_bytes;
+    int list_rows, flags;  /* list capacity per atom; raw sticky device flags */
 } az_engine_info_t;
 int az_engine_info(az_engine *e, az_engine_info_t *out);
 

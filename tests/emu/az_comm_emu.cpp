@@ -1,0 +1,78 @@
+// az_comm_emu.cpp -- TEST INFRASTRUCTURE: AzComm as an in-process mailbox, so that the domain
+// decomposition logic can run as N engines on N host threads of one process (tests/emu only).
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string.h>
+#include "az_comm.h"
+#include "../../include/aztot_b200.h"
+
+namespace {
+struct Msg { std::vector<char> data; };
+struct World {
+    std::mutex m; std::condition_variable cv;
+    std::map<std::pair<int, int>, std::deque<Msg>> box; // (src,dst) -> FIFO
+    int nranks = 0;
+    // allreduce state
+    int ar_arrived = 0; unsigned ar_gen = 0; std::vector<double> ar_sum, ar_out;
+};
+std::mutex g_m;
+std::map<std::string, World*> g_worlds;
+
+struct EmuComm : AzComm {
+    World* w = nullptr;
+    int exchange(const std::vector<AzP2P>& ops, cudaStream_t) override
+    {
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            for (const AzP2P& o : ops)
+                if (o.send_bytes) { Msg msg; msg.data.assign((const char*)o.send, (const char*)o.send + o.send_bytes); w->box[{ rank, o.peer }].push_back(std::move(msg)); }
+        }
+        w->cv.notify_all();
+        for (const AzP2P& o : ops)
+            if (o.recv_bytes) {
+                std::unique_lock<std::mutex> lk(w->m);
+                auto& q = w->box[{ o.peer, rank }];
+                if (!w->cv.wait_for(lk, std::chrono::seconds(60), [&] { return !q.empty(); })) { err = "emu comm: receive timed out"; return AZ_ERR_COMM; }
+                Msg msg = std::move(q.front()); q.pop_front();
+                if (msg.data.size() != o.recv_bytes) { err = "emu comm: message size mismatch"; return AZ_ERR_COMM; }
+                memcpy(o.recv, msg.data.data(), o.recv_bytes);
+            }
+        return AZ_OK;
+    }
+    int allreduce_sum(double* dev, int n, cudaStream_t) override
+    {
+        std::unique_lock<std::mutex> lk(w->m);
+        unsigned g = w->ar_gen;
+        if (w->ar_arrived == 0) w->ar_sum.assign(n, 0.0);
+        for (int k = 0; k < n; k++) w->ar_sum[k] += dev[k];
+        if (++w->ar_arrived == w->nranks) { w->ar_out = w->ar_sum; w->ar_arrived = 0; w->ar_gen++; w->cv.notify_all(); }
+        else if (!w->cv.wait_for(lk, std::chrono::seconds(60), [&] { return w->ar_gen != g; })) { err = "emu comm: allreduce timed out"; return AZ_ERR_COMM; }
+        for (int k = 0; k < n; k++) dev[k] = w->ar_out[k];
+        return AZ_OK;
+    }
+};
+} // namespace
+
+int az_comm_make_id(void* id128, std::string*)
+{
+    static int counter = 0;
+    std::lock_guard<std::mutex> lk(g_m);
+    memset(id128, 0, 128);
+    snprintf((char*)id128, 128, "emu-world-%d", ++counter);
+    return AZ_OK;
+}
+
+int az_comm_create(const void* id, int rank, int nranks, int, AzComm** out, std::string* err)
+{
+    if (!id) { if (err) *err = "multi-rank create needs an id"; return AZ_ERR_INVALID; }
+    std::string key((const char*)id, strnlen((const char*)id, 128));
+    std::lock_guard<std::mutex> lk(g_m);
+    World*& w = g_worlds[key];
+    if (!w) { w = new World(); w->nranks = nranks; }
+    EmuComm* c = new EmuComm();
+    c->rank = rank; c->nranks = nranks; c->w = w;
+    *out = c;
+    return AZ_OK;
+}

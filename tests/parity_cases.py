@@ -50,7 +50,13 @@ def assert_stats_close(so, se, tol=ENERGY_TOL, thermo=False, escale=None):
 
 
 def run_parity(lib, system: System, nsteps=3, first_step=0, thermo=False, check_state=True, force_tol=FORCE_TOL,
-               energy_tol=ENERGY_TOL, state_tol=STATE_TOL, **engine_kw):
+               later_force_tol=None, energy_tol=ENERGY_TOL, state_tol=STATE_TOL, **engine_kw):
+    """`force_tol` is the bound for the first step, where both sides start from bit-identical inputs
+    (the north-star 1e-5).  On later steps the inputs themselves differ by propagated fp32 rounding
+    (positions, and for surk the per-atom radii the thermostat recomputed); `later_force_tol` covers
+    potentials whose pair terms cancel strongly (surk near its minimum amplifies one ulp of radius ~100x)."""
+    if later_force_tol is None:
+        later_force_tol = force_tol
     o = azt.Oracle(system)
     e = Engine(system, lib=lib, **engine_kw)
     try:
@@ -61,7 +67,7 @@ def run_parity(lib, system: System, nsteps=3, first_step=0, thermo=False, check_
             e.step(step, 1)
             do, de = o.dump(), e.dump()
             assert_cells_equal(do, de)
-            assert_forces_close(o, do, de, force_tol)
+            assert_forces_close(o, do, de, force_tol if k == 0 else later_force_tol)
             assert_stats_close(o.stats(), e.stats(), energy_tol, thermo=thermo)
             if check_state:
                 vs = max(float(np.abs(do["vel"]).max()), 1e-6)
@@ -150,7 +156,7 @@ def case_ionic_efield_frozen(lib):
 def case_surk_radiative(lib):
     # case study 2 in miniature: surk + radiative thermostat; equilibration scaling on steps 2 and 4
     s = azt.surk_system(n_side=6, n_equil=4, eq_freq=2)
-    o, e = run_parity(lib, s, nsteps=5, thermo=True, state_tol=1e-4)
+    o, e = run_parity(lib, s, nsteps=5, thermo=True, state_tol=1e-4, later_force_tol=1e-4)
     st = e.stats()
     assert st.engTemp > 0.0
     e.close()
@@ -192,7 +198,7 @@ def case_face_crossings_and_pressure(lib):
     e.close()
 
 
-def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e-5):
+def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e-5, pipe=0):
     """Extension (BASELINE config 3): binning every R steps with a skin gives the same forces and
     energies as binning every step.  variant 0 = Verlet list between rebuilds, 1 = stale cell tiles."""
     e1 = Engine(s, lib=lib)
@@ -200,6 +206,8 @@ def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e
     o = azt.Oracle(s)
     for eng in (e1, e2):
         eng.set_option("energy_every_step", 1)
+    if pipe:
+        e2.set_option("list_pipe", pipe)
     for step in range(nsteps):
         e1.step(step, 1); e2.step(step, 1); o.step(step, 1)
         s1, s2, so = e1.stats(), e2.stats(), o.stats()
@@ -222,6 +230,12 @@ def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e
 
 def case_rebuild_interval_list(lib):
     _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 0)
+
+
+def case_rebuild_interval_list_pipelined(lib):
+    # the software-pipelined variants of the list force pass (2 and 4 neighbours per stage)
+    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 0, nsteps=6, pipe=4)
+    _rebuild_vs_every_step(lib, azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6), 0.6, 0, nsteps=6, pipe=2)
 
 
 def case_rebuild_interval_stale_tiles(lib):
@@ -342,6 +356,7 @@ ALL_CASES = [
     ("equilibration_scaling", case_equilibration_scaling),
     ("face_crossings_pressure", case_face_crossings_and_pressure),
     ("rebuild_interval_list", case_rebuild_interval_list),
+    ("rebuild_interval_list_pipelined", case_rebuild_interval_list_pipelined),
     ("rebuild_interval_stale_tiles", case_rebuild_interval_stale_tiles),
     ("rebuild_interval_list_ionic", case_rebuild_interval_list_ionic),
     ("rebuild_interval_list_surk_radiative", case_rebuild_interval_list_surk_radiative),
