@@ -61,6 +61,7 @@ class az_system_desc(C.Structure):
         ("init_radii", _fp), ("init_engs", _fp), ("seed", C.c_uint64),
         ("timestep", C.c_double), ("n_equil", C.c_int), ("eq_freq", C.c_int),
         ("r2_max", C.c_double), ("cell_size", C.c_double), ("efield", C.c_double * 3),
+        ("global_ids", _ip), ("n_atoms_global", C.c_longlong),
     ]
 
 
@@ -98,7 +99,7 @@ class az_engine_info_t(C.Structure):
                 ("csize", C.c_float * 3), ("crev", C.c_float * 3), ("pair_blocks", C.c_int), ("pair_threads", C.c_int),
                 ("pair_smem_bytes", C.c_int), ("pair_zc", C.c_int), ("pair_vk", C.c_int), ("pair_ck", C.c_int),
                 ("n_sm", C.c_int), ("max_neigh_seen", C.c_int), ("device_bytes", C.c_longlong),
-                ("list_rows", C.c_int), ("flags", C.c_int)]
+                ("list_rows", C.c_int), ("flags", C.c_int), ("capacity", C.c_int), ("n_ranks", C.c_int)]
 
 
 # every symbol include/aztot_b200.h declares: name -> (restype, argtypes)
@@ -124,6 +125,7 @@ ENGINE_SYMBOLS = {
     "az_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "az_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "az_engine_info": (C.c_int, [C.c_void_p, C.POINTER(az_engine_info_t)]),
+    "az_comm_unique_id": (C.c_int, [C.c_void_p]),
 }
 DECK_SYMBOLS = {
     "az_deck_load": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),

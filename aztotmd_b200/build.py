@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas"
 
 CU_SOURCES = ["az_engine.cu", "az_pair_inst_lj.cu", "az_pair_inst_buck.cu", "az_pair_inst_surk.cu",
               "az_pair_inst_mixed.cu"]
-HOST_SOURCES = ["az_deck.cpp"]
+HOST_SOURCES = ["az_deck.cpp", "az_comm_nccl.cpp"]  # NCCL is loaded with dlopen at the first multi-GPU create
 
 
 def nvcc_path() -> str:
@@ -77,12 +77,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if force or _newer(deps, obj):
             jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-                         "-c", path, "-o", obj])
+                         "-I", os.path.join(os.path.dirname(os.path.dirname(nvcc)), "include"), "-c", path, "-o", obj])
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
         list(ex.map(lambda c: _run(c, log), jobs))
     lib = os.path.join(LIBDIR, "libaztot_b200.so")
     if jobs or not os.path.exists(lib):
-        _run([nvcc, *ARCH, "-shared", "-o", lib, *objs, "-Xlinker", "-soname,libaztot_b200.so"], log)
+        _run([nvcc, *ARCH, "-shared", "-o", lib, *objs, "-ldl", "-Xlinker", "-soname,libaztot_b200.so"], log)
     main_src = os.path.join(CSRC, "az_main.cpp")
     exe = os.path.join(LIBDIR, "aztotmd")
     if os.path.exists(main_src) and (jobs or _newer([main_src], exe)):

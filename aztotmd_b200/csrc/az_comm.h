@@ -27,7 +27,7 @@ struct AzComm {
     // All sends are posted in the order given; all receives in the order given.  Between one pair of
     // ranks the k-th send matches the k-th receive.  Asynchronous on `st`.
     virtual int exchange(const std::vector<AzP2P>& ops, cudaStream_t st) = 0;
-    virtual int allreduce_sum(double* dev, int n, cudaStream_t st) = 0;
+    virtual int allreduce(double* dev, int n, bool take_max, cudaStream_t st) = 0; // in place: sum or max
 };
 
 // id: 128 bytes shared by all ranks (ncclUniqueId for the NCCL implementation).

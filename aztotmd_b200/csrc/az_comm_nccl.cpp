@@ -60,9 +60,9 @@ struct NcclComm : AzComm {
         if (r != ncclSuccess) return fail("ncclGroupEnd", r);
         return AZ_OK;
     }
-    int allreduce_sum(double* dev, int n, cudaStream_t st) override
+    int allreduce(double* dev, int n, bool take_max, cudaStream_t st) override
     {
-        ncclResult_t r = g_api.AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, comm, st);
+        ncclResult_t r = g_api.AllReduce(dev, dev, (size_t)n, ncclDouble, take_max ? ncclMax : ncclSum, comm, st);
         if (r != ncclSuccess) return fail("ncclAllReduce", r);
         return AZ_OK;
     }
@@ -82,7 +82,7 @@ int az_comm_make_id(void* id128, std::string* err)
 
 int az_comm_create(const void* id, int rank, int nranks, int device, AzComm** out, std::string* err)
 {
-    if (!id) { if (err) *err = "multi-GPU create needs opts.nccl_id (128 bytes from az_comm_unique_id, shared by all ranks)"; return AZ_ERR_INVALID; }
+    if (!id) { if (err) *err = "multi-GPU create needs opts.nccl_id (128 bytes from az_comm_unique_id, the same on all ranks)"; return AZ_ERR_INVALID; }
     if (!load_api(err)) return AZ_ERR_COMM;
     if (cudaSetDevice(device) != cudaSuccess) { if (err) *err = "cudaSetDevice failed"; return AZ_ERR_CUDA; }
     ncclUniqueId uid;

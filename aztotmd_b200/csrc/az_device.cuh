@@ -46,7 +46,8 @@ struct AzGrid {
 __device__ __forceinline__ int az_cell_id(const AzGrid& g, int lin) { return g.cellmap ? g.cellmap[lin] : lin; }
 
 struct AzParams {
-    int n_local;        // atoms resident on this GPU that take part as i-atoms (owned)
+    int n_local;        // atoms resident on this GPU that take part as i-atoms (owned); launch bound when n_dyn is set
+    const int* n_dyn;   // domain decomposition: device-resident owned-atom count (AzDDCounts::n_owned), else NULL
     int nspec;
     float L[3], revL[3];
     float tSt;
@@ -67,6 +68,8 @@ struct AzParams {
     uint32_t seed_lo, seed_hi;
     AzGrid g;
 };
+
+__device__ __forceinline__ int az_n_owned(const AzParams& P) { return P.n_dyn ? *P.n_dyn : P.n_local; }
 
 #define AZ_FCOUL_SCALE 14.3996f // d_Fcoul_scale, src/main.cu:40
 #define AZ_SQRTPI 1.772453f     // d_sqrtpi, src/main.cu:41

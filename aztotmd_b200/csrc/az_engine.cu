@@ -100,6 +100,19 @@ template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
 }
 #define AZ_ALLOC(e, p, n) do { int rc_ = dev_alloc(e, &(p), (size_t)(n)); if (rc_) return rc_; } while (0)
 
+static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
+static int dd_alloc(az_engine* e);
+static int dd_store_keep(az_engine* e, const az_system_desc* d);
+static void dd_free(az_engine* e);
+static int dd_rebuild(az_engine* e, int c);
+static int dd_refresh_ghosts(az_engine* e, int c);
+static int dd_init_counts(az_engine* e, int n_keep);
+static int dd_reduce_stats(az_engine* e, az_stats* o, int* flags);
+static int dd_owned_count(az_engine* e, int* n);
+static const std::vector<int>* dd_keep(az_engine* e);
+static int dd_global_tscale(az_engine* e);
+static int dd_upload(az_engine* e, const double* xs, const double* ys, const double* zs, const double* vxs, const double* vys, const double* vzs);
+
 // ---------------------------------------------------------------------------------------- ABI
 extern "C" int az_abi_version(void) { return AZ_ABI_VERSION; }
 
@@ -200,7 +213,8 @@ static int pick_pair_config(az_engine* e, const az_system_desc* d, const az_cuda
     else { e->pair_vk = AZ_VK_MIXED; e->pair_single = false; }
 
     // CTA shape: a z-run of cells holding about one thread block of atoms
-    double avg = (double)d->n_atoms / (double)g.ncell_local;
+    const double owned_cells = (double)(g.ohi[0] - g.olo[0]) * (g.ohi[1] - g.olo[1]) * (g.ohi[2] - g.olo[2]);
+    double avg = (double)e->n / owned_cells;
     int zc = (o && o->cells_per_block > 0) ? o->cells_per_block : (int)floor((double)AZ_PAIR_TPB / (avg > 0.05 ? avg : 0.05));
     int zmax = AZ_PAIR_MAXW - 2 * g.sten[2];
     if (zmax < 1) { AZ_SET_ERR(e, "cell size too small for the cutoff: z stencil half width %d", g.sten[2]); return AZ_ERR_UNSUPPORTED; }
@@ -256,41 +270,47 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     cudaDeviceProp prop;
     AZ_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
     e->n_sm = prop.multiProcessorCount;
+    if (o && o->n_ranks > 1 && d->tstat_kind == AZ_TSTAT_RADI && !d->photons) { AZ_SET_ERR(e, "radiative thermostat needs photon energies"); return AZ_ERR_INVALID; }
     e->n = d->n_atoms;
-    e->n_global = d->n_atoms;
+    e->n_global = d->n_atoms_global > 0 ? (int)d->n_atoms_global : d->n_atoms;
     e->rebuild_every = (o && o->rebuild_every > 1) ? o->rebuild_every : 1;
     e->n_ranks = (o && o->n_ranks > 1) ? o->n_ranks : 1;
     e->rank = o ? o->rank : 0;
-    if (e->n_ranks > 1) { AZ_SET_ERR(e, "multi-GPU decomposition: use az_engine_create through the halo build"); return AZ_ERR_UNSUPPORTED; }
+    AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2 * AZ_N_TIMERS; k++) AZ_CUDA(e, cudaEventCreate(&e->ev[k]));
+    for (int k = 0; k < 2; k++) AZ_CUDA(e, cudaEventCreate(&e->ev_step[k]));
     int rc = build_params(e, d, o);
     if (rc) return rc;
+    if (e->n_ranks > 1) { // the global grid of build_params becomes this rank's brick + ghost shell
+        rc = dd_setup(e, d, o);
+        if (rc) return rc;
+        e->n = (int)dd_keep(e)->size();
+    }
     rc = pick_pair_config(e, d, o);
     if (rc) return rc;
     e->n_eq = d->n_equil; e->eq_freq = d->eq_freq;
     e->use_therm = (d->tstat_kind == AZ_TSTAT_RADI) || e->pair_radii;
 
-    AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2 * AZ_N_TIMERS; k++) AZ_CUDA(e, cudaEventCreate(&e->ev[k]));
-    for (int k = 0; k < 2; k++) AZ_CUDA(e, cudaEventCreate(&e->ev_step[k]));
-
+    // capacities: on one GPU exactly the atoms; on a brick the agreed owned / owned+ghost capacities
     const int n = e->n, nc = e->P.g.ncell_local;
-    e->cap = n;
+    const int capo = e->dd ? e->P.n_local : n, capt = e->dd ? e->cap_total_dd : n;
+    e->cap = capt;
     for (int k = 0; k < 2; k++) {
-        AZ_ALLOC(e, e->pos[k], n); AZ_ALLOC(e, e->vel[k], n); AZ_ALLOC(e, e->id[k], n);
-        if (e->use_therm) AZ_ALLOC(e, e->therm[k], n);
+        AZ_ALLOC(e, e->pos[k], capt); AZ_ALLOC(e, e->vel[k], capt); AZ_ALLOC(e, e->id[k], capt);
+        if (e->use_therm) AZ_ALLOC(e, e->therm[k], capt);
     }
-    AZ_ALLOC(e, e->frc, n);
-    AZ_ALLOC(e, e->cellOf, n); AZ_ALLOC(e, e->slotOf, n); AZ_ALLOC(e, e->cellSorted, n); AZ_ALLOC(e, e->keyTmp, n);
+    AZ_ALLOC(e, e->frc, capo);
+    AZ_ALLOC(e, e->cellOf, capt); AZ_ALLOC(e, e->slotOf, capt); AZ_ALLOC(e, e->cellSorted, capt); AZ_ALLOC(e, e->keyTmp, capt);
     AZ_ALLOC(e, e->cellCount, nc + 1); AZ_ALLOC(e, e->first, nc + 1);
     e->n_scan_tiles = (nc + AZ_SCAN_TILE - 1) / AZ_SCAN_TILE;
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
-    e->n_atom_blocks = (n + AZ_TPB - 1) / AZ_TPB;
+    e->n_atom_blocks = (capo + AZ_TPB - 1) / AZ_TPB;
     AZ_ALLOC(e, e->partKE, e->n_atom_blocks); AZ_ALLOC(e, e->partU, e->n_atom_blocks);
     // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
     e->use_list = e->rebuild_every > 1 && !(o && o->pair_variant == 1);
-    e->list_nblocks = (n + AZ_LIST_TPB - 1) / AZ_LIST_TPB;
+    e->list_nblocks = (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB;
     if (e->use_list) {
-        if (n > AZ_NBR_MASK) { AZ_SET_ERR(e, "the Verlet-list path addresses at most %d atoms per GPU", AZ_NBR_MASK); return AZ_ERR_UNSUPPORTED; }
+        if (capt > AZ_NBR_MASK) { AZ_SET_ERR(e, "the Verlet-list path addresses at most %d atoms per GPU", AZ_NBR_MASK); return AZ_ERR_UNSUPPORTED; }
         const double rl = sqrt((double)e->P.r2list);
         const double vol = (double)e->P.L[0] * e->P.L[1] * e->P.L[2];
         int cap = (o && o->max_neigh > 0) ? o->max_neigh : 0;
@@ -301,33 +321,37 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
             std::vector<int> bins((size_t)nb3[0] * nb3[1] * nb3[2], 0);
             const double* xyz[3] = { d->xs, d->ys, d->zs };
             int mx = 0;
-            for (int i = 0; i < n; i++) {
+            for (int i = 0; i < d->n_atoms; i++) {
                 int c[3];
                 for (int a = 0; a < 3; a++) { double u = xyz[a][i] * inv[a]; u -= floor(u / nb3[a]) * nb3[a]; c[a] = (int)u; if (c[a] >= nb3[a]) c[a] = nb3[a] - 1; if (c[a] < 0) c[a] = 0; }
                 int v = ++bins[((size_t)c[0] * nb3[1] + c[1]) * nb3[2] + c[2]];
                 if (v > mx) mx = v;
             }
             double rho = mx * inv[0] * inv[1] * inv[2];
-            double rho_avg = (double)n / vol;
+            double rho_avg = (double)e->n_global / vol;
             if (rho < rho_avg) rho = rho_avg;
             cap = (int)(1.5 * rho * 4.18879 * rl * rl * rl) + 32;
         }
         if (cap >= (1 << AZ_NBR_CNT_BITS) / 2) { AZ_SET_ERR(e, "max_neigh %d is beyond the list format (%d rows)", cap, (1 << AZ_NBR_CNT_BITS) / 2 - 1); return AZ_ERR_INVALID; }
         e->nbr_cap = cap;
-        e->nbr_stride = (n + 31) / 32 * 32;
+        e->nbr_stride = (capo + 31) / 32 * 32;
         AZ_ALLOC(e, e->nbr, (size_t)e->nbr_cap * e->nbr_stride);
-        AZ_ALLOC(e, e->nbrCount, n);
+        AZ_ALLOC(e, e->nbrCount, capo);
     }
     { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve both kernels
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
     AZ_ALLOC(e, e->table, e->h_table.size());
     AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
+    if (e->dd) { rc = dd_alloc(e); if (rc) return rc; rc = dd_store_keep(e, d); if (rc) return rc; }
+    const std::vector<int>* keep = dd_keep(e); // NULL on one GPU: every atom, in input order
+    auto src = [&](int k) { return keep ? (*keep)[k] : k; };
     if (d->tstat_kind == AZ_TSTAT_RADI) {
-        AZ_ALLOC(e, e->photons, n); AZ_ALLOC(e, e->uv, 3 * AZ_N_UVECT);
-        std::vector<float> ph(n);
-        for (int i = 0; i < n; i++) ph[i] = (float)d->photons[i]; // src/cuTemp.cu:24-33
-        AZ_CUDA(e, cudaMemcpy(e->photons, ph.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+        AZ_ALLOC(e, e->photons, capo); AZ_ALLOC(e, e->uv, 3 * AZ_N_UVECT);
+        std::vector<float> ph(capo);
+        // src/cuTemp.cu:24-33; a brick has more slots than photons: the table repeats
+        for (int i = 0; i < capo; i++) ph[i] = (float)d->photons[n > 0 ? src(i % n) : 0];
+        AZ_CUDA(e, cudaMemcpy(e->photons, ph.data(), sizeof(float) * capo, cudaMemcpyHostToDevice));
         std::vector<float> uv(3 * AZ_N_UVECT);
         if (d->uvect_x && d->uvect_y && d->uvect_z)
             for (int k = 0; k < AZ_N_UVECT; k++) { uv[3 * k] = (float)d->uvect_x[k]; uv[3 * k + 1] = (float)d->uvect_y[k]; uv[3 * k + 2] = (float)d->uvect_z[k]; }
@@ -339,24 +363,29 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     std::vector<float4> hp(n), hv(n), hf(n);
     std::vector<int> hid(n);
     std::vector<float2> hth(e->use_therm ? n : 0);
-    for (int i = 0; i < n; i++) {
-        hp[i] = make_float4((float)d->xs[i], (float)d->ys[i], (float)d->zs[i], __int_as_float_host(d->types[i]));
-        hv[i] = make_float4(d->vxs ? (float)d->vxs[i] : 0.f, d->vys ? (float)d->vys[i] : 0.f, d->vzs ? (float)d->vzs[i] : 0.f, 0.f);
-        hf[i] = make_float4(d->fxs ? (float)d->fxs[i] : 0.f, d->fys ? (float)d->fys[i] : 0.f, d->fzs ? (float)d->fzs[i] : 0.f, 0.f);
-        hid[i] = i;
+    for (int k = 0; k < n; k++) {
+        const int i = src(k);
+        const int gid = d->global_ids ? d->global_ids[i] : i;
+        hp[k] = make_float4((float)d->xs[i], (float)d->ys[i], (float)d->zs[i], __int_as_float_host(d->types[i]));
+        hv[k] = make_float4(d->vxs ? (float)d->vxs[i] : 0.f, d->vys ? (float)d->vys[i] : 0.f, d->vzs ? (float)d->vzs[i] : 0.f, 0.f);
+        hf[k] = make_float4(d->fxs ? (float)d->fxs[i] : 0.f, d->fys ? (float)d->fys[i] : 0.f, d->fzs ? (float)d->fzs[i] : 0.f, 0.f);
+        hid[k] = gid;
         if (e->use_therm) {
             uint32_t r[4];
-            host_philox((uint32_t)i, 0xA5A5A5A5u, 0, 0, (uint32_t)d->seed, (uint32_t)(d->seed >> 32), r);
+            host_philox((uint32_t)gid, 0xA5A5A5A5u, 0, 0, (uint32_t)d->seed, (uint32_t)(d->seed >> 32), r);
             float u = (float)(r[0] % 10000u) / 10000.0f; // rand01(), src/utils.cpp:197-201
-            hth[i].x = d->init_engs ? d->init_engs[i] : 0.f;                      // engs = 0, src/cuTemp.cu:40
-            hth[i].y = d->init_radii ? d->init_radii[i] : 0.577f + u * 0.0001f;   // src/cuTemp.cu:41
+            hth[k].x = d->init_engs ? d->init_engs[i] : 0.f;                      // engs = 0, src/cuTemp.cu:40
+            hth[k].y = d->init_radii ? d->init_radii[i] : 0.577f + u * 0.0001f;   // src/cuTemp.cu:41
         }
     }
-    AZ_CUDA(e, cudaMemcpy(e->pos[0], hp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemcpy(e->vel[0], hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemcpy(e->frc, hf.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemcpy(e->id[0], hid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-    if (e->use_therm) AZ_CUDA(e, cudaMemcpy(e->therm[0], hth.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    if (n > 0) {
+        AZ_CUDA(e, cudaMemcpy(e->pos[0], hp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->vel[0], hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->frc, hf.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->id[0], hid.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        if (e->use_therm) AZ_CUDA(e, cudaMemcpy(e->therm[0], hth.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    }
+    if (e->dd) { rc = dd_init_counts(e, n); if (rc) return rc; }
     e->cur = 0;
     e->binned = false;
     e->since_rebuild = 0;
@@ -369,6 +398,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    dd_free(e);
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
     cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
@@ -410,6 +440,8 @@ struct Timer {
 
 #define AZ_COUNT(e, k, nl) do { (e)->launches += (nl); (e)->t_launch[k] += (nl); } while (0)
 
+#include "az_engine_dd.cuh"
+
 static int one_step(az_engine* e, int step, bool want_energy)
 {
     const AzParams& P = e->P;
@@ -425,7 +457,9 @@ static int one_step(az_engine* e, int step, bool want_energy)
     { // K1: half kick + drift (+ wrap + bin)
         Timer t(e, AZ_TIMER_INTEGRATE_A);
         if (P.has_efield) { AZ_LAUNCH(az_k_reset_step, 1, 1, 0, st, e->sc); AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1); }
-        if (rebuild) {
+        if (rebuild && e->dd) { // bricks: wrap only; migration comes between the wrap and the binning
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_WRAP>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+        } else if (rebuild) {
             AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist
             AZ_LAUNCH(az_k_integrate_a<AZ_IA_BIN>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         } else {
@@ -433,7 +467,13 @@ static int one_step(az_engine* e, int step, bool want_energy)
         }
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1);
     }
-    if (rebuild) {
+    if (rebuild && e->dd) {
+        int rc = dd_rebuild(e, c);
+        if (rc) return rc;
+        c = e->cur = 1 - c;
+        e->binned = true;
+        e->since_rebuild = 0;
+    } else if (rebuild) {
         {
             Timer t(e, AZ_TIMER_SCAN);
             AZ_LAUNCH(az_k_scan_tiles, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum);
@@ -442,13 +482,13 @@ static int one_step(az_engine* e, int step, bool want_energy)
         }
         {
             Timer t(e, AZ_TIMER_SORT);
-            AZ_LAUNCH(az_k_sort_keys, nb, AZ_TPB, 0, st, n, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
+            AZ_LAUNCH(az_k_sort_keys, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
             if (e->use_therm)
-                AZ_LAUNCH(az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted);
+                AZ_LAUNCH(az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
+                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, (int*)nullptr);
             else
-                AZ_LAUNCH(az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted);
+                AZ_LAUNCH(az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
+                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, (int*)nullptr);
             AZ_COUNT(e, AZ_TIMER_SORT, 2);
         }
         c = e->cur = 1 - c; // refresh_arrays (src/cuSort.cu:74-100): host-side ping-pong
@@ -456,6 +496,7 @@ static int one_step(az_engine* e, int step, bool want_energy)
         e->since_rebuild = 0;
     } else {
         e->since_rebuild++;
+        if (e->dd) { int rc = dd_refresh_ghosts(e, c); if (rc) return rc; }
     }
     { // K4: pair forces
         const int pair_mode = !e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST);
@@ -467,7 +508,7 @@ static int one_step(az_engine* e, int step, bool want_energy)
         A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.partN = e->partN; A.flags = &e->sc->overflow;
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
-        A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap;
+        A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg;
         int rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
@@ -490,8 +531,9 @@ static int one_step(az_engine* e, int step, bool want_energy)
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
             AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | 8 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
+            if (e->dd) { int rc = dd_global_tscale(e); if (rc) return rc; }
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
             else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
             AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
@@ -535,10 +577,15 @@ static int fetch_scalars(az_engine* e, AzScalars* h)
     AZ_CUDA(e, cudaMemcpyAsync(h, e->sc, sizeof(AzScalars), cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     AZ_CUDA(e, cudaGetLastError());
-    if (h->overflow & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
-    if (h->overflow & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
-    if (h->overflow & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius (worst row: %d): raise 'max_neigh'", e->nbr_cap, h->dbg_count); return AZ_ERR_OVERFLOW; }
-    if (h->overflow & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a ghost cell overflowed its halo slots"); return AZ_ERR_OVERFLOW; }
+    return AZ_OK;
+}
+
+static int check_flags(az_engine* e, int flags, int worst_row)
+{
+    if (flags & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
+    if (flags & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
+    if (flags & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius (worst row: %d): raise 'max_neigh'", e->nbr_cap, worst_row); return AZ_ERR_OVERFLOW; }
+    if (flags & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a halo / migration message or the brick's atom capacity overflowed, or an atom crossed more than one ghost shell in a step"); return AZ_ERR_OVERFLOW; }
     return AZ_OK;
 }
 
@@ -548,6 +595,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     AzScalars h;
     int rc = fetch_scalars(e, &h);
     if (rc) return rc;
+    if (!e->dd) { rc = check_flags(e, h.overflow, h.dbg_count); if (rc) return rc; }
     memset(o, 0, sizeof(*o));
     o->step = e->last_step;
     o->n_atoms_total = e->n_global;
@@ -559,7 +607,14 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     for (int t = 0; t < e->P.nspec; t++)
         for (int a = 0; a < 3; a++) { o->specAcBoxPos[t][a] = h.acPos[t][a]; o->specAcBoxNeg[t][a] = h.acNeg[t][a]; }
     o->engKin_d = h.engKin; o->engVdW_d = h.engVdW; o->engCoul1_d = h.engCoul1; o->engTemp_d = h.engTemp;
-    o->n_pairs = (long long)h.nPairs;
+    o->n_pairs = e->dd ? (long long)h.nVisits : (long long)h.nPairs;
+    if (e->dd) { // collective: every rank reduces, then every rank sees the OR of the flags
+        int flags = h.overflow;
+        rc = dd_reduce_stats(e, o, &flags);
+        if (rc) return rc;
+        rc = check_flags(e, flags, h.dbg_count);
+        if (rc) return rc;
+    }
     return AZ_OK;
 }
 
@@ -575,9 +630,11 @@ static float wrap_host(float x, float L, float revL)
 extern "C" int az_engine_download(az_engine* e, az_atoms_out* o, int order)
 {
     if (!e || !o) return AZ_ERR_INVALID;
-    if (o->n_atoms < e->n) { AZ_SET_ERR(e, "output capacity %d < %d atoms", o->n_atoms, e->n); return AZ_ERR_INVALID; }
     AZ_CUDA(e, cudaSetDevice(e->device));
-    const int n = e->n, c = e->cur;
+    int n = e->n;
+    if (e->dd) { int rc = dd_owned_count(e, &n); if (rc) return rc; if (order == AZ_ORDER_ORIGINAL) order = AZ_ORDER_SORTED; } // a brick hands back the atoms it owns, with their ids
+    if (o->n_atoms < n) { AZ_SET_ERR(e, "output capacity %d < %d atoms", o->n_atoms, n); return AZ_ERR_INVALID; }
+    const int c = e->cur;
     std::vector<float4> hp(n), hv(n);
     std::vector<int> hid(n);
     std::vector<float2> hth(e->use_therm ? n : 0);
@@ -609,7 +666,9 @@ extern "C" int az_engine_download(az_engine* e, az_atoms_out* o, int order)
 extern "C" int az_engine_debug_dump(az_engine* e, az_dump* o)
 {
     if (!e || !o) return AZ_ERR_INVALID;
-    const int n = e->n, nc = e->P.g.ncell_local, c = e->cur;
+    int n = e->n;
+    const int nc = e->P.g.ncell_local, c = e->cur;
+    if (e->dd) { int rc = dd_owned_count(e, &n); if (rc) return rc; }
     if (o->n_atoms < n || o->n_cells < nc) { AZ_SET_ERR(e, "dump capacity too small (%d atoms, %d cells needed)", n, nc); return AZ_ERR_INVALID; }
     AZ_CUDA(e, cudaSetDevice(e->device));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -634,6 +693,7 @@ extern "C" int az_engine_upload(az_engine* e, const double* xs, const double* ys
 {
     if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
     AZ_CUDA(e, cudaSetDevice(e->device));
+    if (e->dd) return dd_upload(e, xs, ys, zs, vxs, vys, vzs);
     const int n = e->n, c = e->cur;
     if (!e->stage) AZ_ALLOC(e, e->stage, (size_t)6 * n);
     const double* src[6] = { xs, ys, zs, vxs, vys, vzs };
@@ -743,6 +803,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!e || !key) return AZ_ERR_INVALID;
     if (!strcmp(key, "energy_every_step")) { e->energy_every_step = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_pipe")) { e->list_pipe = (int)value; return AZ_OK; }
+    if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;
 }
@@ -758,6 +819,7 @@ extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
     o->pair_zc = e->pair_zc; o->pair_vk = e->pair_vk; o->pair_ck = e->pair_ck;
     o->n_sm = e->n_sm; o->device_bytes = (long long)e->dev_bytes;
     o->list_rows = e->nbr_cap;
+    o->capacity = e->dd ? e->P.n_local : e->n; o->n_ranks = e->n_ranks;
     if (e->sc) {
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -7,10 +7,13 @@
 
 static inline float __int_as_float_host(int i) { float f; memcpy(&f, &i, 4); return f; }
 
+struct AzDDHost;
+
 struct az_engine {
     std::string err;
+    AzDDHost* dd = nullptr; // spatial domain decomposition (n_ranks > 1), az_engine_dd.cuh
     int device = 0, n_sm = 0;
-    int n = 0, n_global = 0, cap = 0;
+    int n = 0, n_global = 0, cap = 0, cap_total_dd = 0;
     int rank = 0, n_ranks = 1;
     AzParams P;
     float revArea[3] = { 0, 0, 0 };
@@ -29,6 +32,7 @@ struct az_engine {
     // Verlet-list path (rebuild_every > 1)
     bool use_list = false;
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
+    int list_dbg = 0;
     int list_pipe = 0; // software-pipeline depth of the list force pass (0, 2, 4 neighbours per stage)
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;

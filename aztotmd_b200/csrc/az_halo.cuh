@@ -2,20 +2,46 @@
 // the reference is single-GPU).  The periodic box is cut into px*py*pz bricks aligned to the cell
 // grid of split_cells; a rank owns the atoms whose cell (count_cell's formula, bit-exact) lies in its
 // brick and keeps read-only ghost copies of the atoms in the sten[a] cell layers around it.  Every
-// message goes straight to one of the <= 26 neighbouring bricks (no forwarding), so a step needs one
-// pack kernel, one grouped exchange and one unpack kernel.
+// message goes straight to one of the <= 26 neighbouring bricks (no forwarding).
 //
-//   rebuild step : wrap -> classify/migrate leavers -> select + exchange ghosts -> bin all -> sort
-//                  (owned cells are numbered first, so owned atoms stay a contiguous prefix) ->
-//                  remap the send lists / ghost slots through the sort permutation
+// Nothing here needs the host: every count lives in device memory (AzDDCounts) and travels in the
+// header entry of its message, the messages have a fixed capacity per direction (agreed between the
+// ranks at create time), and kernels are launched over capacities.  A step is therefore a fixed
+// sequence of launches and NCCL calls on one stream -- no host synchronisation, CUDA-graph friendly.
+//
+//   rebuild step : wrap -> classify leavers, pack, exchange, append arrivals -> select ghosts of the
+//                  new owned set, pack, exchange, append ghosts -> bin all live atoms -> scan ->
+//                  sort (owned cells are numbered first, so owned atoms are a contiguous prefix) ->
+//                  remap the send lists and the ghost slots through the sort permutation
 //   other steps  : pack current positions of the listed atoms -> exchange -> overwrite ghost slots
+//
+// Message layout for direction d: entries [off[d], off[d+1]), entry off[d] is the header (count in
+// the bits of .x), entries off[d]+1+k carry atom k.  Lists (send indices, ghost slots) use the same
+// offsets so that message entry t and list entry t describe the same atom.
 #pragma once
 #include "az_kernels.cuh"
 
 #define AZ_NDIR 27
 #define AZ_DIR_SELF 13
 
-struct AzDirTable { int off[AZ_NDIR + 1]; }; // prefix offsets of the per-direction segments
+struct AzDDCounts { // device resident
+    int n_owned;      // owned atoms: contiguous prefix of the sorted streams (must stay the first member)
+    int n_tot;        // owned + ghost atoms
+    int n_arrived;    // migrants received in the current rebuild
+    int ghost_base;   // index of the first ghost before the sort (= old owned + arrived)
+    int migCount[AZ_NDIR];
+    int sendCount[AZ_NDIR]; // ghosts sent per direction, fixed until the next rebuild
+    int recvCount[AZ_NDIR]; // ghosts received per direction
+};
+
+struct AzDD { // by-value kernel parameter, fixed at create time
+    int gs[AZ_NDIR + 1]; // ghost messages I send: entry offsets (capacity[d] + 1 entries each)
+    int gr[AZ_NDIR + 1]; // ghost messages I receive from direction d (= the peer's send layout for 26-d)
+    int ms[AZ_NDIR + 1]; // migration messages, send side
+    int mr[AZ_NDIR + 1]; // migration messages, receive side
+    int cap_owned, cap_total;
+    AzDDCounts* cnt;
+};
 
 struct AzMigRec { // one migrating atom
     float4 pos;   // w = type bits
@@ -34,47 +60,63 @@ __device__ __forceinline__ void az_global_cell(const AzParams& P, const float4 p
     }
 }
 
-// which neighbouring brick (if any) owns the atom after this step's move
-static __global__ void __launch_bounds__(AZ_TPB)
-az_k_mig_classify(const __grid_constant__ AzParams P, int n_owned, const float4* __restrict__ pos,
-                  int* __restrict__ migCount, int* __restrict__ migList, int migCap, int* __restrict__ stay, int* __restrict__ flags)
+// entry t of a message layout -> direction (k = t - off[d]; k == 0 is the header)
+__device__ __forceinline__ int az_dir_of(const int* off, int t)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_owned) return;
+    int d = 0;
+#pragma unroll 1
+    while (d < AZ_NDIR - 1 && t >= off[d + 1]) d++;
+    return d;
+}
+__device__ __forceinline__ int az_hdr_count(float x, int capacity) { return max(0, min(__float_as_int(x), capacity)); }
+
+// cell coordinate relative to the first owned cell of the brick, folded into (-n/2, n/2]-ish around it
+__device__ __forceinline__ int az_rel_cell(const AzGrid& g, int a, int c)
+{
+    const int n = g.n[a], clo = g.goff[a] + g.olo[a], owned = g.ohi[a] - g.olo[a];
+    int rel = c - clo;
+    if (rel < 0) rel += n; // 0 .. n-1 from the brick's first cell
+    if (rel >= owned && n - rel <= rel - owned + 1) rel -= n; // nearer to the low face: negative
+    return rel;
+}
+
+// Which neighbouring brick (if any) owns the atom after this step's move.
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_mig_classify(const __grid_constant__ AzParams P, const __grid_constant__ AzDD D, const float4* __restrict__ pos,
+                  int* __restrict__ migList, int* __restrict__ stay, int* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.cnt->n_owned) return;
     int ci[3];
     az_global_cell(P, pos[i], ci);
     int d[3] = { 0, 0, 0 };
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         if (!P.g.dec[a]) continue;
-        const int n = P.g.n[a], clo = P.g.goff[a] + P.g.olo[a], owned = P.g.ohi[a] - P.g.olo[a];
-        int delta = ci[a] - clo;
-        if (delta < 0) delta += n; // 0 .. n-1 relative to the brick's first cell
-        if (delta >= owned) d[a] = (delta - owned < n - delta) ? 1 : -1; // nearer face decides
+        const int owned = P.g.ohi[a] - P.g.olo[a];
+        const int rel = az_rel_cell(P.g, a, ci[a]);
+        d[a] = rel < 0 ? -1 : (rel >= owned ? 1 : 0);
     }
     const int dir = (d[0] + 1) * 9 + (d[1] + 1) * 3 + (d[2] + 1);
     if (dir == AZ_DIR_SELF) { stay[i] = 1; return; }
-    stay[i] = 0;
-    const int slot = atomicAdd(&migCount[dir], 1);
-    if (slot < migCap) migList[dir * migCap + slot] = i; else atomicOr(flags, AZ_FLAG_HALO);
-}
-
-__device__ __forceinline__ int az_dir_of(const AzDirTable& T, int t)
-{
-    int d = 0;
-#pragma unroll 1
-    while (d < AZ_NDIR - 1 && t >= T.off[d + 1]) d++;
-    return d;
+    const int slot = atomicAdd(&D.cnt->migCount[dir], 1);
+    const int capacity = D.ms[dir + 1] - D.ms[dir] - 1;
+    if (slot < capacity) { stay[i] = 0; migList[D.ms[dir] + 1 + slot] = i; }
+    else { stay[i] = 0; atomicOr(flags, AZ_FLAG_HALO); } // the atom is lost: reported through the sticky flag
 }
 
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_mig_pack(const __grid_constant__ AzDirTable T, const int* __restrict__ migList, int migCap, const float4* __restrict__ pos,
+az_k_mig_pack(const __grid_constant__ AzDD D, const int* __restrict__ migList, const float4* __restrict__ pos,
               const float4* __restrict__ vel, const int* __restrict__ id, const float2* __restrict__ therm, AzMigRec* __restrict__ out)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T.off[AZ_NDIR]) return;
-    const int d = az_dir_of(T, t);
-    const int i = migList[d * migCap + (t - T.off[d])];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.ms[AZ_NDIR]) return;
+    const int d = az_dir_of(D.ms, t), k = t - D.ms[d];
+    const int capacity = D.ms[d + 1] - D.ms[d] - 1;
+    const int cnt = min(D.cnt->migCount[d], capacity);
+    if (k == 0) { AzMigRec h; memset(&h, 0, sizeof(h)); h.pos.x = __int_as_float(cnt); out[t] = h; return; }
+    if (k - 1 >= cnt) return;
+    const int i = migList[t];
     AzMigRec r;
     r.pos = pos[i];
     r.vel = vel[i]; r.vel.w = __int_as_float(id[i]);
@@ -83,122 +125,141 @@ az_k_mig_pack(const __grid_constant__ AzDirTable T, const int* __restrict__ migL
     out[t] = r;
 }
 
-// stayers and arrivals are appended to the other ping-pong buffers in arbitrary order (the sort that
-// follows orders by cell and persistent id)
+// arrivals are appended behind the owned atoms in message order
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_mig_compact(int n_owned, const int* __restrict__ stay, const float4* __restrict__ pos, const float4* __restrict__ vel,
-                 const int* __restrict__ id, const float2* __restrict__ therm, int* __restrict__ counter,
-                 float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o, float2* __restrict__ therm_o)
+az_k_mig_unpack(const __grid_constant__ AzDD D, const AzMigRec* __restrict__ in, float4* __restrict__ pos, float4* __restrict__ vel,
+                int* __restrict__ id, float2* __restrict__ therm, int* __restrict__ stay, int* __restrict__ flags)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_owned || !stay[i]) return;
-    const int d = atomicAdd(counter, 1);
-    pos_o[d] = pos[i]; vel_o[d] = vel[i]; id_o[d] = id[i];
-    if (therm) therm_o[d] = therm[i];
-}
-
-static __global__ void __launch_bounds__(AZ_TPB)
-az_k_mig_unpack(int n_in, const AzMigRec* __restrict__ in, int* __restrict__ counter, int cap, float4* __restrict__ pos_o,
-                float4* __restrict__ vel_o, int* __restrict__ id_o, float2* __restrict__ therm_o, int* __restrict__ flags)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_in) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.mr[AZ_NDIR]) return;
+    const int d = az_dir_of(D.mr, t), k = t - D.mr[d];
+    int before = 0, total = 0;
+    for (int q = 0; q < AZ_NDIR; q++) {
+        const int capq = D.mr[q + 1] - D.mr[q] - 1;
+        if (capq <= 0) continue;
+        const int c = az_hdr_count(in[D.mr[q]].pos.x, capq);
+        if (q < d) before += c;
+        total += c;
+    }
+    if (t == 0) D.cnt->n_arrived = total;
+    if (k == 0) return;
+    const int capacity = D.mr[d + 1] - D.mr[d] - 1;
+    if (k - 1 >= az_hdr_count(in[D.mr[d]].pos.x, capacity)) return;
+    const int dst = D.cnt->n_owned + before + (k - 1);
+    if (dst >= D.cap_owned) { atomicOr(flags, AZ_FLAG_HALO); return; }
     const AzMigRec r = in[t];
-    const int d = atomicAdd(counter, 1);
-    if (d >= cap) { atomicOr(flags, AZ_FLAG_HALO); return; }
-    pos_o[d] = r.pos;
-    id_o[d] = __float_as_int(r.vel.w);
-    vel_o[d] = make_float4(r.vel.x, r.vel.y, r.vel.z, 0.f);
-    if (therm_o) therm_o[d] = r.therm;
+    pos[dst] = r.pos;
+    id[dst] = __float_as_int(r.vel.w);
+    vel[dst] = make_float4(r.vel.x, r.vel.y, r.vel.z, 0.f);
+    if (therm) therm[dst] = r.therm;
+    stay[dst] = 1;
 }
 
-// owned atoms inside the sten[a] outermost cell layers go to the bricks that need them as ghosts
+// Owned atoms inside the sten[a] outermost cell layers go to the bricks that need them as ghosts.
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_ghost_select(const __grid_constant__ AzParams P, int n_owned, const float4* __restrict__ pos, int* __restrict__ sendCount,
-                  int* __restrict__ sendList, int cap, int* __restrict__ flags)
+az_k_ghost_select(const __grid_constant__ AzParams P, const __grid_constant__ AzDD D, const float4* __restrict__ pos,
+                  const int* __restrict__ stay, int* __restrict__ sendList, int* __restrict__ flags)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_owned) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(D.cnt->n_owned + D.cnt->n_arrived, D.cap_owned) || !stay[i]) return;
     int ci[3];
     az_global_cell(P, pos[i], ci);
     bool lo[3], hi[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const int clo = P.g.goff[a] + P.g.olo[a], owned = P.g.ohi[a] - P.g.olo[a];
-        const int lc = ci[a] - clo;
-        lo[a] = P.g.dec[a] && lc < P.g.sten[a];
-        hi[a] = P.g.dec[a] && lc >= owned - P.g.sten[a];
+        const int owned = P.g.ohi[a] - P.g.olo[a];
+        const int rel = az_rel_cell(P.g, a, ci[a]);
+        lo[a] = P.g.dec[a] && rel < P.g.sten[a];
+        hi[a] = P.g.dec[a] && rel >= owned - P.g.sten[a];
     }
     if (!(lo[0] | hi[0] | lo[1] | hi[1] | lo[2] | hi[2])) return;
     for (int dir = 0; dir < AZ_NDIR; dir++) {
-        if (dir == AZ_DIR_SELF) continue;
+        const int capacity = D.gs[dir + 1] - D.gs[dir] - 1;
+        if (dir == AZ_DIR_SELF || capacity <= 0) continue;
         const int d[3] = { dir / 9 - 1, (dir / 3) % 3 - 1, dir % 3 - 1 };
         bool ok = true;
 #pragma unroll
         for (int a = 0; a < 3; a++) ok = ok && (d[a] == 0 || (d[a] < 0 ? lo[a] : hi[a]));
         if (!ok) continue;
-        const int slot = atomicAdd(&sendCount[dir], 1);
-        if (slot < cap) sendList[dir * cap + slot] = i; else atomicOr(flags, AZ_FLAG_HALO);
+        const int slot = atomicAdd(&D.cnt->sendCount[dir], 1);
+        if (slot < capacity) sendList[D.gs[dir] + 1 + slot] = i; else atomicOr(flags, AZ_FLAG_HALO);
     }
 }
 
-// compact the per-direction lists [dir*cap + k] into one list with the prefix offsets of T
-static __global__ void __launch_bounds__(AZ_TPB)
-az_k_list_compact(const __grid_constant__ AzDirTable T, const int* __restrict__ lists, int cap, int* __restrict__ out)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T.off[AZ_NDIR]) return;
-    const int d = az_dir_of(T, t);
-    out[t] = lists[d * cap + (t - T.off[d])];
-}
-
-// message = float4 position (w = type) per listed atom, plus (id, radius) when FULL
+// message = float4 position (w = type) per listed atom, plus (id, radius) in the aux stream.
+// FULL (rebuild) also writes the headers.
 template <bool FULL>
 __global__ void __launch_bounds__(AZ_TPB)
-az_k_ghost_pack(int total, const int* __restrict__ sendIdx, const float4* __restrict__ pos, const int* __restrict__ id,
+az_k_ghost_pack(const __grid_constant__ AzDD D, const int* __restrict__ sendList, const float4* __restrict__ pos, const int* __restrict__ id,
                 const float2* __restrict__ therm, float4* __restrict__ out_pos, float2* __restrict__ out_aux)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int i = sendIdx[t];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.gs[AZ_NDIR]) return;
+    const int d = az_dir_of(D.gs, t), k = t - D.gs[d];
+    const int capacity = D.gs[d + 1] - D.gs[d] - 1;
+    const int cnt = min(D.cnt->sendCount[d], capacity);
+    if (k == 0) { if (FULL) out_pos[t] = make_float4(__int_as_float(cnt), 0.f, 0.f, 0.f); return; }
+    if (k - 1 >= cnt) return;
+    const int i = sendList[t];
     out_pos[t] = pos[i];
     if (FULL) out_aux[t] = make_float2(__int_as_float(id[i]), therm ? therm[i].y : 0.f);
     else if (therm) out_aux[t] = make_float2(0.f, therm[i].y);
 }
 
-// rebuild: ghosts are appended behind the owned atoms in message order
+// rebuild: ghosts are appended behind owned + arrived atoms in message order
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_ghost_append(int total, int base, const float4* __restrict__ in_pos, const float2* __restrict__ in_aux, float4* __restrict__ pos,
-                  float4* __restrict__ vel, int* __restrict__ id, float2* __restrict__ therm)
+az_k_ghost_append(const __grid_constant__ AzDD D, const float4* __restrict__ in_pos, const float2* __restrict__ in_aux, float4* __restrict__ pos,
+                  float4* __restrict__ vel, int* __restrict__ id, float2* __restrict__ therm, int* __restrict__ stay, int* __restrict__ flags)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    pos[base + t] = in_pos[t];
-    vel[base + t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    id[base + t] = __float_as_int(in_aux[t].x);
-    if (therm) therm[base + t] = make_float2(0.f, in_aux[t].y);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.gr[AZ_NDIR]) return;
+    const int d = az_dir_of(D.gr, t), k = t - D.gr[d];
+    int before = 0, total = 0;
+    for (int q = 0; q < AZ_NDIR; q++) {
+        const int capq = D.gr[q + 1] - D.gr[q] - 1;
+        if (capq <= 0) continue;
+        const int c = az_hdr_count(in_pos[D.gr[q]].x, capq);
+        if (q < d) before += c;
+        total += c;
+    }
+    const int base = min(D.cnt->n_owned + D.cnt->n_arrived, D.cap_owned);
+    const int capacity = D.gr[d + 1] - D.gr[d] - 1;
+    const int cnt = capacity > 0 ? az_hdr_count(in_pos[D.gr[d]].x, capacity) : 0;
+    if (t == 0) { D.cnt->ghost_base = base; D.cnt->n_tot = min(base + total, D.cap_total); }
+    if (k == 0) { D.cnt->recvCount[d] = cnt; return; }
+    if (k - 1 >= cnt) return;
+    const int dst = base + before + (k - 1);
+    if (dst >= D.cap_total) { atomicOr(flags, AZ_FLAG_HALO); return; }
+    pos[dst] = in_pos[t];
+    vel[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    id[dst] = __float_as_int(in_aux[t].x);
+    if (therm) therm[dst] = make_float2(0.f, in_aux[t].y);
+    stay[dst] = 1;
 }
 
 // other steps: overwrite the slots the ghosts were sorted into
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_ghost_update(int total, const int* __restrict__ slot, const float4* __restrict__ in_pos, const float2* __restrict__ in_aux,
-                  float4* __restrict__ pos, float2* __restrict__ therm)
+az_k_ghost_update(const __grid_constant__ AzDD D, const int* __restrict__ ghostSlot, const float4* __restrict__ in_pos,
+                  const float2* __restrict__ in_aux, float4* __restrict__ pos, float2* __restrict__ therm)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int s = slot[t];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.gr[AZ_NDIR]) return;
+    const int d = az_dir_of(D.gr, t), k = t - D.gr[d];
+    if (k == 0 || k - 1 >= D.cnt->recvCount[d]) return;
+    const int s = ghostSlot[t];
     pos[s] = in_pos[t];
     if (therm) therm[s].y = in_aux[t].y;
 }
 
-// count_cell for owned and ghost atoms of a brick: global cell from the (wrapped) position, then the
-// periodic image that falls inside the local grid
+// count_cell for the owned and ghost atoms of a brick: global cell from the (wrapped) position, then the
+// periodic image that falls inside the local grid.  Leavers (stay == 0) are dead: cell -1, skipped by the sort.
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_bin(const __grid_constant__ AzParams P, int n_tot, const float4* __restrict__ pos, int* __restrict__ cellOf,
-         int* __restrict__ slotOf, int* __restrict__ cellCount, int* __restrict__ flags)
+az_k_bin(const __grid_constant__ AzParams P, const __grid_constant__ AzDD D, const float4* __restrict__ pos, const int* __restrict__ stay,
+         int* __restrict__ cellOf, int* __restrict__ slotOf, int* __restrict__ cellCount, int* __restrict__ flags)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_tot) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.cnt->n_tot) return;
+    if (!stay[i]) { cellOf[i] = -1; return; }
     int ci[3], l[3];
     az_global_cell(P, pos[i], ci);
     bool ok = true;
@@ -209,22 +270,43 @@ az_k_bin(const __grid_constant__ AzParams P, int n_tot, const float4* __restrict
         ok = ok && v >= 0 && v < P.g.nl[a];
         l[a] = v;
     }
-    if (!ok) { atomicOr(flags, AZ_FLAG_HALO); cellOf[i] = 0; slotOf[i] = atomicAdd(&cellCount[0], 1); return; }
+    if (!ok) { atomicOr(flags, AZ_FLAG_HALO); cellOf[i] = -1; return; } // moved farther than the ghost shell
     const int cid = az_cell_id(P.g, (l[0] * P.g.nl[1] + l[1]) * P.g.nl[2] + l[2]);
     cellOf[i] = cid;
     slotOf[i] = atomicAdd(&cellCount[cid], 1);
 }
 
-// send lists and ghost slots follow the atoms through the sort
+
+// send lists and ghost slots follow the atoms through the sort; then publish the new counts
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_remap(int n, int* __restrict__ list, const int* __restrict__ newIndex)
+az_k_dd_remap(const __grid_constant__ AzDD D, const int* __restrict__ newIndex, int* __restrict__ sendList, int* __restrict__ ghostSlot)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) list[t] = newIndex[list[t]];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < D.gs[AZ_NDIR]) {
+        const int d = az_dir_of(D.gs, t), k = t - D.gs[d];
+        const int capacity = D.gs[d + 1] - D.gs[d] - 1;
+        if (k >= 1 && k - 1 < min(D.cnt->sendCount[d], capacity)) sendList[t] = newIndex[sendList[t]];
+    }
+    if (t < D.gr[AZ_NDIR]) {
+        const int d = az_dir_of(D.gr, t), k = t - D.gr[d];
+        if (k >= 1 && k - 1 < D.cnt->recvCount[d]) {
+            int before = 0;
+            for (int q = 0; q < d; q++) before += D.cnt->recvCount[q];
+            ghostSlot[t] = newIndex[D.cnt->ghost_base + before + (k - 1)];
+        }
+    }
 }
-static __global__ void __launch_bounds__(AZ_TPB)
-az_k_ghost_slots(int n_ghost, int base, const int* __restrict__ newIndex, int* __restrict__ slot)
+
+static __global__ void az_k_dd_publish(const __grid_constant__ AzDD D, const int* __restrict__ first, int n_owned_cells, int n_cells)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_ghost) slot[t] = newIndex[base + t];
+    D.cnt->n_owned = first[n_owned_cells];
+    D.cnt->n_tot = first[n_cells];
+    D.cnt->n_arrived = 0;
+}
+
+static __global__ void az_k_dd_begin_rebuild(const __grid_constant__ AzDD D)
+{
+    const int t = threadIdx.x;
+    if (t < AZ_NDIR) { D.cnt->migCount[t] = 0; D.cnt->sendCount[t] = 0; D.cnt->recvCount[t] = 0; }
+    if (t == 0) D.cnt->n_arrived = 0;
 }

@@ -57,6 +57,7 @@ struct AzScalars {
     float tscale_k;
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
+    unsigned long long nVisits; // the same, counted from both sides (a brick sees cross-brick pairs from one side only)
     unsigned vmax2_bits; // max |v|^2 of the current step (float bits; stale-cell steps only)
     float drift;         // upper bound of any atom's displacement since the last rebuild
 };
@@ -82,7 +83,7 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double eF = 0.0;
     float v2 = 0.f;
-    if (i < P.n_local) {
+    if (i < az_n_owned(P)) {
         float4 p = pos[i], v = vel[i], f = frc[i];
         int t = __float_as_int(p.w);
         float h = P.rMasshdT[t];
@@ -208,25 +209,28 @@ az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ ti
 // atom inside its cell by id (cells hold ~10-20 atoms) and scatters the payload streams, so the
 // within-cell order is canonical (ascending id) whatever the atomics did.
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_sort_keys(int n, const int* __restrict__ cellOf, const int* __restrict__ slotOf,
+az_k_sort_keys(int n, const int* __restrict__ n_dyn, const int* __restrict__ cellOf, const int* __restrict__ slotOf,
                const int* __restrict__ first, const int* __restrict__ id, int* __restrict__ keyTmp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keyTmp[first[cellOf[i]] + slotOf[i]] = id[i];
+    if (n_dyn) n = *n_dyn;
+    if (i < n && cellOf[i] >= 0) keyTmp[first[cellOf[i]] + slotOf[i]] = id[i]; // cell -1: the atom left this brick
 }
 
 template <bool THERM>
 __global__ void __launch_bounds__(AZ_TPB)
-az_k_sort_scatter(int n, const int* __restrict__ cellOf, const int* __restrict__ first,
+az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ cellOf, const int* __restrict__ first,
                   const int* __restrict__ count, const int* __restrict__ keyTmp,
                   const float4* __restrict__ pos, const float4* __restrict__ vel,
                   const int* __restrict__ id, const float2* __restrict__ therm,
                   float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o,
-                  float2* __restrict__ therm_o, int* __restrict__ cell_o)
+                  float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dyn) n = *n_dyn;
     if (i >= n) return;
     int c = cellOf[i];
+    if (c < 0) return;
     int b = first[c], m = count[c];
     int my = id[i];
     int rank = 0;
@@ -237,6 +241,7 @@ az_k_sort_scatter(int n, const int* __restrict__ cellOf, const int* __restrict__
     id_o[d] = my;
     cell_o[d] = c;
     if (THERM) therm_o[d] = therm[i];
+    if (newIndex) newIndex[i] = d; // domain decomposition: send lists and ghost slots follow the atoms
 }
 
 // ---------------------------------------------------------------------------------------
@@ -321,7 +326,7 @@ az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __r
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0, ut = 0.0;
-    if (i < P.n_local) {
+    if (i < az_n_owned(P)) {
         float4 v = vel[i], f = frc[i];
         int t = __float_as_int(pos[i].w);
         float h = P.rMasshdT[t];
@@ -352,7 +357,7 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ut = 0.0;
     float k = sc->tscale_k;
-    if (i < P.n_local) {
+    if (i < az_n_owned(P)) {
         float4 v = vel[i];
         v.x *= k; v.y *= k; v.z *= k;
         if (TSTAT) {
@@ -391,7 +396,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
         double c[1] = { 0.0 };
         for (int k = threadIdx.x; k < nPair; k += blockDim.x) c[0] += (double)partN[k];
         az_block_sum<1>(c, sm);
-        if (threadIdx.x == 0) sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25);
+        if (threadIdx.x == 0) { sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25); sc->nVisits = (unsigned long long)(c[0] + 0.5); }
     }
     if (threadIdx.x != 0) return;
     if (mode & 32) { sc->drift = 0.f; sc->vmax2_bits = 0u; } // rebuild step: cells are exact again

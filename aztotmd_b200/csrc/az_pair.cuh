@@ -34,6 +34,7 @@ struct AzPairArgs {
     int* nbr;                // Verlet list, blocked by warp: row k of atom i at nbr[((i >> 5) * nbr_cap + k) * 32 + (i & 31)]
     int* nbrCount;           // LIST build: neighbours of atom i within the list radius
     int nbr_stride, nbr_cap;
+    int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
     int tile_cap;            // atoms the dynamic shared tile holds
@@ -295,7 +296,7 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
 {
     const AzGrid& g = P.g;
     const int i = blockIdx.x * AZ_LIST_TPB + threadIdx.x;
-    if (i >= P.n_local) return;
+    if (i >= az_n_owned(P)) return;
     const float4 pi = A.pos[i];
     // owned cells are numbered first, z fastest inside the owned block
     const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
@@ -393,7 +394,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         __syncthreads();
     }
     const int i = blockIdx.x * AZ_LIST_TPB + tid;
-    const bool act = i < P.n_local;
+    const bool act = i < az_n_owned(P);
     float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
     int hits = 0, ti = 0;
     if (act) {
@@ -426,14 +427,17 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
             // gathers of chunk k (L1/L2) are consumed
             int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            if (cnt >= 4) { c0 = row[0]; c1 = row[stride]; c2 = row[2 * stride]; c3 = row[3 * stride]; }
+            const int dbg = A.dbg;
+            auto ldidx = [&](const int* p, int kk) { return dbg == 2 ? max(0, min(az_n_owned(P) - 1, i + kk - (cnt >> 1))) : *p; };
+            auto ldpos = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : __ldg(A.pos + c); };
+            if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
             for (; k + 4 <= cnt; k += 4) {
                 row += 4 * stride;
-                const float4 p0 = __ldg(A.pos + c0), p1 = __ldg(A.pos + c1), p2 = __ldg(A.pos + c2), p3 = __ldg(A.pos + c3);
+                const float4 p0 = ldpos(c0), p1 = ldpos(c1), p2 = ldpos(c2), p3 = ldpos(c3);
                 float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
                 if (RADII) { r0 = A.therm[c0].y; r1 = A.therm[c1].y; r2_ = A.therm[c2].y; r3 = A.therm[c3].y; }
                 int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-                if (k + 8 <= cnt) { n0 = row[0]; n1 = row[stride]; n2 = row[2 * stride]; n3 = row[3 * stride]; }
+                if (k + 8 <= cnt) { n0 = ldidx(row, k + 4); n1 = ldidx(row + stride, k + 5); n2 = ldidx(row + 2 * stride, k + 6); n3 = ldidx(row + 3 * stride, k + 7); }
                 plain(p0, r0); plain(p1, r1); plain(p2, r2_); plain(p3, r3);
                 c0 = n0; c1 = n1; c2 = n2; c3 = n3;
             }

@@ -77,6 +77,9 @@ class System:
     init_engs: Optional[np.ndarray] = None
     seed: int = 12345
     n_bonds: int = 0
+    # domain decomposition, distributed input: this rank's share of the system with its persistent ids
+    global_ids: Optional[np.ndarray] = None
+    n_atoms_global: int = 0
 
     def set_vdw(self, i: int, j: int, kind: str, rcut: float, params: Sequence[float]):
         e = prepare_vdw(kind, rcut, params)
@@ -110,7 +113,8 @@ class System:
 
     @property
     def deg_free(self) -> int:  # src/sys_init.cpp:1099-1102
-        return 3 * len(self.pos) - self.n_bonds - (1 if self.tstat_kind else 0)
+        n = self.n_atoms_global if self.n_atoms_global > 0 else len(self.pos)
+        return 3 * n - self.n_bonds - (1 if self.tstat_kind else 0)
 
     @property
     def t_kin(self) -> float:  # src/sys_init.cpp:1106
@@ -218,14 +222,32 @@ class DescHolder:
         d.cell_size = s.cell_size
         for a in range(3):
             d.efield[a] = float(s.efield[a])
+        if s.global_ids is not None:
+            gi = np.ascontiguousarray(s.global_ids, dtype=np.int32)
+            self.keep.append(gi)
+            d.global_ids = gi.ctypes.data_as(C.POINTER(C.c_int))
+        d.n_atoms_global = int(s.n_atoms_global)
         self.desc = d
+
+
+def unique_comm_id(lib=None) -> bytes:
+    """128 bytes that identify one multi-GPU job (az_comm_unique_id); rank 0 creates them and every
+    rank passes the same bytes to Engine(..., comm_id=...)."""
+    lib = lib if lib is not None else abi.load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.az_comm_unique_id(buf)
+    if rc != abi.AZ_OK:
+        msg = lib.az_last_error(None)
+        raise AzError(rc, msg.decode() if msg else "")
+    return buf.raw
 
 
 class Engine:
     """One engine = one GPU.  ``lib`` defaults to the nvcc-built library (no fallback)."""
 
     def __init__(self, system, *, device: int = 0, rebuild_every: int = 1, skin: float = 0.0,
-                 cells_per_block: int = 0, pair_variant: int = 0, max_neigh: int = 0, lib=None, opts: Optional[abi.az_cuda_opts] = None):
+                 cells_per_block: int = 0, pair_variant: int = 0, max_neigh: int = 0, lib=None, opts: Optional[abi.az_cuda_opts] = None,
+                 rank: int = 0, n_ranks: int = 1, pgrid: Sequence[int] = (0, 0, 0), comm_id: Optional[bytes] = None):
         self.lib = lib if lib is not None else abi.load_library()
         if isinstance(system, System):
             self._holder = DescHolder(system)
@@ -243,6 +265,14 @@ class Engine:
             opts.cells_per_block = cells_per_block
             opts.pair_variant = pair_variant
             opts.max_neigh = max_neigh
+            opts.rank, opts.n_ranks = rank, n_ranks
+            for a in range(3):
+                opts.pgrid[a] = int(pgrid[a])
+            if n_ranks > 1:
+                if comm_id is None or len(comm_id) != 128:
+                    raise ValueError("n_ranks > 1 needs comm_id: the 128 bytes of unique_comm_id(), the same on every rank")
+                self._comm_id = C.create_string_buffer(bytes(comm_id), 128)
+                opts.nccl_id = C.cast(self._comm_id, C.c_void_p)
         self._h = C.c_void_p()
         rc = self.lib.az_engine_create(C.byref(desc), C.byref(opts), C.byref(self._h))
         if rc != abi.AZ_OK:
@@ -251,6 +281,7 @@ class Engine:
         self.info = abi.az_engine_info_t()
         self._check(self.lib.az_engine_info(self._h, C.byref(self.info)))
         self.n_cells = self.info.n_cells
+        self.n = max(self.n, self.info.capacity)  # a brick may come to own more atoms than it was given
 
     def _check(self, rc: int):
         if rc != abi.AZ_OK:

@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--pair-variant", type=int, default=0, help="0 auto (Verlet list between rebuilds), 1 cell tiles only")
     ap.add_argument("--list-pipe", type=int, default=-1, help="software-pipeline depth of the list force pass (experiment)")
+    ap.add_argument("--list-dbg", type=int, default=0, help="diagnostic variants of the list pass (results are NOT physical)")
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -214,6 +215,8 @@ def main():
     e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0, pair_variant=args.pair_variant)
     if args.list_pipe >= 0:
         e.set_option("list_pipe", args.list_pipe)
+    if args.list_dbg:
+        e.set_option("list_dbg", args.list_dbg)
     K, W = args.steps, args.warmup
     e.step(0, W)
     st = e.stats()  # also surfaces skin/overflow errors early

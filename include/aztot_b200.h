@@ -144,6 +144,12 @@ typedef struct az_system_desc {
     double r2_max;             /* Sim::r2Max, src/sys_init.cpp:1059-1072 */
     double cell_size;          /* Sim::desired_cell_size ('cell_list') */
     double efield[3];          /* Sim::Ux,Uy,Uz */
+    /* Domain decomposition only (az_cuda_opts.n_ranks > 1; new functionality, the reference is
+     * single-GPU).  global_ids == NULL: every rank passes the whole system (persistent id = index)
+     * and keeps the atoms of its own brick.  Otherwise the rank passes a share of the system (any
+     * atoms within one brick of its own) with these persistent ids; t_kin is the global value. */
+    const int *global_ids;
+    long long n_atoms_global;  /* 0 = n_atoms */
 } az_system_desc;
 
 /* cuda.txt-level options plus the multi-GPU layout.  Zero-initialise for defaults. */
@@ -157,8 +163,8 @@ typedef struct az_cuda_opts {
     /* spatial domain decomposition (new functionality) */
     int rank, n_ranks;
     int pgrid[3];        /* ranks along x,y,z; product = n_ranks; 0 -> {n_ranks,1,1}  */
-    int ghost_slots;     /* fixed slots per ghost cell in halo messages; 0 = auto     */
-    const void *nccl_id; /* ncclUniqueId bytes (128) shared by all ranks, or NULL     */
+    int ghost_slots;     /* reserved                                                   */
+    const void *nccl_id; /* 128 bytes from az_comm_unique_id, the same on all ranks   */
     int max_neigh;       /* rows of the Verlet list per atom ('max_neigh' of control.txt); 0 = from density */
     int reserved[7];
 } az_cuda_opts;
@@ -213,6 +219,13 @@ typedef struct az_engine az_engine;
 int az_abi_version(void);
 const char *az_last_error(const az_engine *e); /* e may be NULL: error of the last failed create */
 int az_device_count(void);
+
+/* Multi-GPU: one process (or thread) per GPU, one engine per rank.  Rank 0 calls az_comm_unique_id
+ * and hands the 128 bytes to every rank (e.g. torch.distributed broadcast, MPI_Bcast, a file); all
+ * ranks then call az_engine_create with opts.rank / n_ranks / pgrid / nccl_id.  az_engine_create,
+ * az_engine_step, az_engine_stats and az_engine_destroy are collective: every rank calls them with the
+ * same arguments.  az_engine_download returns the atoms the rank owns. */
+int az_comm_unique_id(void *id128);
 
 /* life cycle */
 int az_engine_create(const az_system_desc *desc, const az_cuda_opts *opts, az_engine **out);
@@ -275,6 +288,8 @@ typedef struct az_engine_info_t {
     int max_neigh_seen;  /* largest Verlet-list row count of the last rebuild (0 without a list) */
     long long device_bytes;
     int list_rows, flags;  /* list capacity per atom; raw sticky device flags */
+    int capacity;          /* most atoms az_engine_download / az_engine_debug_dump can hand back (a brick's owned capacity) */
+    int n_ranks;
 } az_engine_info_t;
 int az_engine_info(az_engine *e, az_engine_info_t *out);
 

@@ -1,0 +1,202 @@
+"""Domain-decomposition cases shared by the emulator tests (CPU, logic; tests/test_emu_bricks.py) and the
+GPU tests (NCCL between real devices; tests/test_gpu_bricks.py).  N engines run as N host threads of one
+process (ctypes releases the GIL; NCCL and the emulator mailbox both support one communicator rank per
+thread); the result is compared, atom by atom through the persistent ids, with ONE engine holding the
+whole system and with the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+import azt
+from aztotmd_b200 import abi
+from aztotmd_b200.engine import AzError, Engine, unique_comm_id
+
+
+def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=None, **kw):
+    """Advance `system` on n_ranks bricks; returns per-rank results gathered after the last step."""
+    cid = unique_comm_id(lib)
+    out = [None] * n_ranks
+    err = [None] * n_ranks
+    barrier = threading.Barrier(n_ranks)
+
+    def work(r):
+        try:
+            s = system
+            if distributed:  # every rank passes only the atoms of its own slab along the first decomposed axis, with ids
+                s = slab_share(system, r, n_ranks, pgrid)
+            e = Engine(s, lib=lib, rank=r, n_ranks=n_ranks, pgrid=pgrid, comm_id=cid,
+                       device=(devices[r] if devices else 0), **kw)
+            e.set_option("energy_every_step", 1)
+            stats = []
+            for k in range(nsteps):
+                e.step(k, 1)
+                stats.append(e.stats())
+            d = e.dump()
+            a = e.download(abi.ORDER_SORTED)
+            out[r] = dict(stats=stats, dump=d, atoms=a, info=e.info)
+            barrier.wait()
+            e.close()
+        except Exception as ex:  # noqa: BLE001
+            err[r] = ex
+            try:
+                barrier.abort()
+            except Exception:
+                pass
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n_ranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    real = [ex for ex in err if ex is not None and not isinstance(ex, threading.BrokenBarrierError)]
+    if real:
+        raise real[0]
+    for ex in err:
+        if ex is not None:
+            raise ex
+    return out
+
+
+def gather_by_id(results, n, key_src="dump"):
+    frc = np.zeros((n, 3), dtype=np.float32)
+    pos = np.zeros((n, 3), dtype=np.float64)
+    vel = np.zeros((n, 3), dtype=np.float64)
+    seen = np.zeros(n, dtype=np.int32)
+    for r in results:
+        ids = r["dump"]["ids"]
+        frc[ids] = r["dump"]["frc"]
+        seen[ids] += 1
+        pos[r["atoms"]["ids"]] = r["atoms"]["pos"]
+        vel[r["atoms"]["ids"]] = r["atoms"]["vel"]
+    return frc, pos, vel, seen
+
+
+def check_against_single(lib, system, n_ranks, pgrid, nsteps=3, tol=2e-5, distributed=False, devices=None, **kw):
+    res = run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=distributed, devices=devices, **kw)
+    e1 = Engine(system, lib=lib, **kw)
+    e1.set_option("energy_every_step", 1)
+    o = azt.Oracle(system)
+    n = len(system.pos)
+    for k in range(nsteps):
+        e1.step(k, 1)
+        o.step(k, 1)
+        s1 = e1.stats()
+        for r in res:  # every rank reports the same global scalars
+            sr = r["stats"][k]
+            sc = max(abs(s1.engVdW_d), abs(s1.engCoul1_d), abs(s1.engKin_d), 1e-9)
+            assert abs(sr.engVdW_d - s1.engVdW_d) <= tol * sc, (k, sr.engVdW_d, s1.engVdW_d)
+            assert abs(sr.engCoul1_d - s1.engCoul1_d) <= tol * sc
+            assert abs(sr.engKin_d - s1.engKin_d) <= tol * sc
+            assert sr.n_pairs == s1.n_pairs == o.pairs_in_range(), (sr.n_pairs, s1.n_pairs)
+    frc, pos, vel, seen = gather_by_id(res, n)
+    assert (seen == 1).all(), "every atom is owned by exactly one brick (%d missing, %d duplicated)" % ((seen == 0).sum(), (seen > 1).sum())
+    d1 = azt.sort_by_id(e1.dump())
+    do = azt.sort_by_id(o.dump())
+    fs = np.zeros(n, dtype=np.float32)
+    fs[o.dump()["ids"]] = o.force_scale()
+    fs = np.maximum(fs, 1e-10)
+    assert (np.abs(frc - d1["frc"]).max(1) <= 1e-4 * fs).all(), "brick forces differ from the single-GPU engine"
+    assert (np.abs(frc - do["frc"]).max(1) <= 1e-4 * fs).all(), "brick forces differ from the oracle"
+    a1 = e1.download(abi.ORDER_ORIGINAL)
+    L = np.asarray(system.box)
+    dp = np.abs(pos - a1["pos"])
+    dp = np.minimum(dp, L - dp)
+    assert dp.max() <= 1e-4
+    assert np.abs(vel - a1["vel"]).max() <= 1e-4 * max(np.abs(a1["vel"]).max(), 1e-9)
+    e1.close()
+    return res
+
+
+def case_two_bricks_along_x_match_single_engine(lib, devices=None):
+    s = azt.lj_system(ncell=(8, 5, 5), seed=21)  # 5 x 3 x 3 cells of >= rc: bricks of 2 and 3 cells
+    res = check_against_single(lib, s, 2, (2, 1, 1), nsteps=3, devices=devices)
+    assert sum(len(r["dump"]["ids"]) for r in res) == len(s.pos)
+
+
+def case_two_bricks_along_z_and_y(lib, devices=None):
+    s = azt.lj_system(ncell=(5, 5, 8), seed=22)
+    check_against_single(lib, s, 2, (1, 1, 2), nsteps=2, devices=devices)
+    s = azt.lj_system(ncell=(5, 8, 5), seed=23)
+    check_against_single(lib, s, 2, (1, 2, 1), nsteps=2, devices=devices)
+
+
+def case_four_bricks_2x2(lib, devices=None):
+    s = azt.lj_system(ncell=(8, 8, 5), seed=24)
+    check_against_single(lib, s, 4, (2, 2, 1), nsteps=3, devices=devices)
+
+
+def case_eight_bricks_2x2x2_ionic(lib, devices=None):
+    s = azt.nacl_system(ncell=(7, 7, 7), elec=abi.ELEC_FENNEL, r_real=9.0, rc_vdw=9.0, cell_size=9.0)
+    check_against_single(lib, s, 8, (2, 2, 2), nsteps=2, devices=devices)
+
+
+def case_bricks_verlet_list_between_rebuilds(lib, devices=None):
+    s = azt.lj_system(ncell=(8, 5, 5), seed=25, cell_size=9.3)
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=7, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
+
+
+def case_bricks_migration_hot_atoms(lib, devices=None):
+    # hot and fast: atoms cross brick faces every few steps
+    s = azt.lj_system(ncell=(8, 5, 5), seed=26, temperature=3000.0)
+    s.timestep = 0.004
+    res = run_bricks(lib, s, 2, (2, 1, 1), nsteps=12, devices=devices)
+    n = len(s.pos)
+    frc, pos, vel, seen = gather_by_id(res, n)
+    assert (seen == 1).all()
+    e1 = Engine(s, lib=lib)
+    e1.step(0, 12)
+    a1 = e1.download(abi.ORDER_ORIGINAL)
+    L = np.asarray(s.box)
+    dp = np.abs(pos - a1["pos"])
+    dp = np.minimum(dp, L - dp)
+    assert dp.max() <= 2e-3  # 12 steps of chaotic divergence from rounding-order differences
+    st = res[0]["stats"][-1]
+    s1 = e1.stats()
+    assert sum(st.specAcBoxPos[0]) + sum(st.specAcBoxNeg[0]) == sum(s1.specAcBoxPos[0]) + sum(s1.specAcBoxNeg[0])
+    e1.close()
+
+
+def case_brick_layout_errors(lib, devices=None):
+    s = azt.lj_system(ncell=(4, 4, 4), seed=27)  # 2 cells per axis: too fine for two bricks
+    cid = unique_comm_id(lib)
+    with pytest.raises(AzError) as ei:
+        Engine(s, lib=lib, rank=0, n_ranks=2, pgrid=(2, 1, 1), comm_id=cid)
+    assert ei.value.status == abi.AZ_ERR_UNSUPPORTED
+    with pytest.raises(AzError) as ei:
+        Engine(azt.lj_system(ncell=(8, 5, 5)), lib=lib, rank=0, n_ranks=2, pgrid=(3, 1, 1), comm_id=cid)
+    assert ei.value.status == abi.AZ_ERR_INVALID
+
+
+def slab_share(system, r, n_ranks, pgrid):
+    """Distributed input: rank r passes the atoms whose coordinate along the first decomposed axis falls
+    in its 1/P slab of the box (NOT the engine's cell-aligned brick: stragglers migrate in the first step)."""
+    import copy
+    ax = [a for a in range(3) if pgrid[a] > 1][0]
+    P = pgrid[ax]
+    pc = (r // (pgrid[1] * pgrid[2]), (r // pgrid[2]) % pgrid[1], r % pgrid[2])
+    L = system.box[ax]
+    x = np.asarray(system.pos)[:, ax] % L
+    mine = (x >= L * pc[ax] / P) & (x < L * (pc[ax] + 1) / P)
+    for a in range(3):  # other decomposed axes: exact halves as well
+        if a != ax and pgrid[a] > 1:
+            y = np.asarray(system.pos)[:, a] % system.box[a]
+            mine &= (y >= system.box[a] * pc[a] / pgrid[a]) & (y < system.box[a] * (pc[a] + 1) / pgrid[a])
+    s = copy.copy(system)
+    idx = np.nonzero(mine)[0]
+    s.pos = np.asarray(system.pos)[idx]
+    s.types = np.asarray(system.types)[idx]
+    s.vel = np.asarray(system.vel)[idx] if system.vel is not None else None
+    s.global_ids = idx.astype(np.int32)
+    s.n_atoms_global = len(system.pos)
+    return s
+
+
+def case_distributed_input_with_ids(lib, devices=None):
+    s = azt.lj_system(ncell=(8, 5, 5), seed=28)
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=2, distributed=True, devices=devices)
+    s = azt.lj_system(ncell=(8, 8, 5), seed=29)
+    check_against_single(lib, s, 4, (2, 2, 1), nsteps=2, distributed=True, devices=devices)
+
+
+ALL_CASES = [(n[5:], f) for n, f in sorted(globals().items()) if n.startswith("case_") and callable(f)]

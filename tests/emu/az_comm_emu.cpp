@@ -1,5 +1,7 @@
 // az_comm_emu.cpp -- TEST INFRASTRUCTURE: AzComm as an in-process mailbox, so that the domain
 // decomposition logic can run as N engines on N host threads of one process (tests/emu only).
+#include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -41,12 +43,12 @@ struct EmuComm : AzComm {
             }
         return AZ_OK;
     }
-    int allreduce_sum(double* dev, int n, cudaStream_t) override
+    int allreduce(double* dev, int n, bool take_max, cudaStream_t) override
     {
         std::unique_lock<std::mutex> lk(w->m);
         unsigned g = w->ar_gen;
-        if (w->ar_arrived == 0) w->ar_sum.assign(n, 0.0);
-        for (int k = 0; k < n; k++) w->ar_sum[k] += dev[k];
+        if (w->ar_arrived == 0) w->ar_sum.assign(dev, dev + n);
+        else for (int k = 0; k < n; k++) w->ar_sum[k] = take_max ? std::max(w->ar_sum[k], dev[k]) : w->ar_sum[k] + dev[k];
         if (++w->ar_arrived == w->nranks) { w->ar_out = w->ar_sum; w->ar_arrived = 0; w->ar_gen++; w->cv.notify_all(); }
         else if (!w->cv.wait_for(lk, std::chrono::seconds(60), [&] { return w->ar_gen != g; })) { err = "emu comm: allreduce timed out"; return AZ_ERR_COMM; }
         for (int k = 0; k < n; k++) dev[k] = w->ar_out[k];

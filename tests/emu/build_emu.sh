@@ -16,6 +16,10 @@ for f in az_engine az_pair_inst_lj az_pair_inst_buck az_pair_inst_surk az_pair_i
     pids+=($!)
   fi
 done
+if [ ! -f "$OUT/az_comm_emu.o" ] || [ "$HERE/az_comm_emu.cpp" -nt "$OUT/az_comm_emu.o" ] || [ "$SRC/az_comm.h" -nt "$OUT/az_comm_emu.o" ] || [ "$HERE/cuda_emu.h" -nt "$OUT/az_comm_emu.o" ]; then
+  $CXX $FLAGS -I"$SRC" -c "$HERE/az_comm_emu.cpp" -o "$OUT/az_comm_emu.o" &
+  pids+=($!)
+fi
 if [ ! -f "$OUT/cuda_emu.o" ] || [ "$HERE/cuda_emu.cpp" -nt "$OUT/cuda_emu.o" ] || [ "$HERE/cuda_emu.h" -nt "$OUT/cuda_emu.o" ]; then
   $CXX $FLAGS -c "$HERE/cuda_emu.cpp" -o "$OUT/cuda_emu.o" &
   pids+=($!)
