@@ -118,10 +118,12 @@ static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o
     AzDDHost* h = e->dd = new AzDDHost();
     AzParams& P = e->P;
     AzGrid& g = P.g;
-    std::string cerr;
-    int rc = az_comm_create(o->nccl_id, e->rank, e->n_ranks, e->device, &h->comm, &cerr);
-    if (rc) { e->err = cerr; return rc; }
+    int rc = AZ_OK;
+    // Every check that can fail comes BEFORE the communicator is created: the checks depend only on
+    // arguments that are the same on all ranks, so either every rank fails here or none does (a rank
+    // that entered ncclCommInitRank alone would wait for the others forever).
     if (e->rank < 0 || e->rank >= e->n_ranks) { AZ_SET_ERR(e, "rank %d outside 0..%d", e->rank, e->n_ranks - 1); return AZ_ERR_INVALID; }
+    if (!o->nccl_id) { AZ_SET_ERR(e, "multi-GPU create needs opts.nccl_id (128 bytes from az_comm_unique_id, the same on all ranks)"); return AZ_ERR_INVALID; }
 
     if (o->pgrid[0] > 0 && o->pgrid[0] * o->pgrid[1] * o->pgrid[2] == e->n_ranks) { for (int a = 0; a < 3; a++) h->pg[a] = o->pgrid[a]; }
     else if (o->pgrid[0] > 0) { AZ_SET_ERR(e, "pgrid %dx%dx%d does not match %d ranks", o->pgrid[0], o->pgrid[1], o->pgrid[2], e->n_ranks); return AZ_ERR_INVALID; }
@@ -148,6 +150,11 @@ static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o
     }
     long long ncl = (long long)g.nl[0] * g.nl[1] * g.nl[2];
     if (ncl > 0x3fffffff) { AZ_SET_ERR(e, "too many local cells (%lld)", ncl); return AZ_ERR_INVALID; }
+    {
+        std::string cerr;
+        rc = az_comm_create(o->nccl_id, e->rank, e->n_ranks, e->device, &h->comm, &cerr);
+        if (rc) { e->err = cerr; return rc; }
+    }
     g.ncell_local = (int)ncl;
     const int on[3] = { g.ohi[0] - g.olo[0], g.ohi[1] - g.olo[1], g.ohi[2] - g.olo[2] };
     h->n_owned_cells = on[0] * on[1] * on[2];

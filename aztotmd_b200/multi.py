@@ -66,6 +66,11 @@ def bench_main(args, config):
         raise SystemExit("bench.py --gpus %d must be launched with %d ranks (torchrun); WORLD_SIZE is %d" % (args.gpus, args.gpus, world))
     if world not in BRICKS:
         raise SystemExit("bench.py: supported GPU counts are 1, 2, 4, 8")
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    import sys
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -165,7 +170,10 @@ def bench_main(args, config):
                "kernel_ms_per_step": {k: v["ms"] / K for k, v in tm.items()},
                "energy": {"engKin": st.engKin_d, "engVdW": st.engVdW_d, "pairs_in_cutoff": st.n_pairs},
                "hbm_peak": {"value": hbm_peak, "source": hbm_src}}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     dist.barrier()
     e.close()
     dist.destroy_process_group()

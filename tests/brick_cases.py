@@ -27,6 +27,10 @@ def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=N
                 s = slab_share(system, r, n_ranks, pgrid)
             e = Engine(s, lib=lib, rank=r, n_ranks=n_ranks, pgrid=pgrid, comm_id=cid,
                        device=(devices[r] if devices else 0), **kw)
+            # all engines exist before any rank starts communicating: in ONE process a cudaMalloc on one
+            # device can wait for a peer device whose NCCL kernel waits for this rank (NCCL's documented
+            # multi-thread caveat); with one process per GPU (bench.py, production) this cannot happen
+            barrier.wait()
             e.set_option("energy_every_step", 1)
             stats = []
             for k in range(nsteps):
