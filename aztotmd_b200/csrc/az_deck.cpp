@@ -303,6 +303,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     if (scan_first(f, " elecfield %lf ", &U[0])) { if (fscanf(f, " %lf %lf ", &U[1], &U[2]) != 2) { U[1] = U[2] = 0.0; } }
     else U[0] = 0.0;
     if (scan_number(f, " reset_vels %d ") != 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'reset_vels' is outside the hot path (SURVEY 8f)");
+    { int mn; if (scan_first(f, " max_neigh %d ", &mn) && mn > 0) d->opts.max_neigh = mn; } // rows of the Verlet list per atom
     double cell_size = 0.0;
     if (!scan_first(f, " cell_list %lf ", &cell_size)) DECK_FAIL(AZ_ERR_IO, "'cell_list' is required by the CUDA path (desired_cell_size, src/cuInit.cu:979)");
     { double r; if (!scan_first(f, " rdf %lf ", &r)) DECK_WARN("note: no 'rdf' directive (the reference demands one, ERROR[408]); RDF sampling is outside the hot path anyway"); }
