@@ -442,28 +442,40 @@ struct Timer {
 
 #include "az_engine_dd.cuh"
 
-static int one_step(az_engine* e, int step, bool want_energy)
+static bool step_rebuilds(const az_engine* e) { return !e->binned || e->rebuild_every <= 1 || e->since_rebuild + 1 >= e->rebuild_every; }
+
+static bool is_eq_step(const az_engine* e, int step)
+{
+    return e->n_eq && step <= e->n_eq && e->eq_freq > 0 && (step % e->eq_freq) == 0; // src/cuTemp.cu:777-779
+}
+
+// One MD step.  skip_a: this step's first half kick + drift was already done by the fused kernel of the
+// previous step.  fuse_next: do the second half kick of this step and the first half kick + drift of the
+// next one in one pass (az_k_integrate_ba).  `slot` = parity of the step count: which vmax2 slot this
+// step's drift bookkeeping uses.
+static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool fuse_next)
 {
     const AzParams& P = e->P;
     const int n = e->n, nc = P.g.ncell_local;
     cudaStream_t st = e->stream;
-    const bool rebuild = !e->binned || e->rebuild_every <= 1 || e->since_rebuild + 1 >= e->rebuild_every;
+    const bool rebuild = step_rebuilds(e);
     const bool radi = (P.tstat == AZ_TSTAT_RADI);
-    const bool eq_step = e->n_eq && step <= e->n_eq && e->eq_freq > 0 && (step % e->eq_freq) == 0; // src/cuTemp.cu:777-779
+    const bool eq_step = is_eq_step(e, step);
     const int nb = e->n_atom_blocks;
     int c = e->cur;
     const int n_pp = e->use_list ? e->list_nblocks : e->pair_nblocks; // live pair partials this step
+    const int slot = (int)(e->steps_done & 1);
 
-    { // K1: half kick + drift (+ wrap + bin)
+    if (!skip_a) { // K1: half kick + drift (+ wrap + bin)
         Timer t(e, AZ_TIMER_INTEGRATE_A);
         if (P.has_efield) { AZ_LAUNCH(az_k_reset_step, 1, 1, 0, st, e->sc); AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1); }
         if (rebuild && e->dd) { // bricks: wrap only; migration comes between the wrap and the binning
-            AZ_LAUNCH(az_k_integrate_a<AZ_IA_WRAP>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_WRAP>, nb, AZ_TPB, 0, st, P, slot, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         } else if (rebuild) {
             AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist
-            AZ_LAUNCH(az_k_integrate_a<AZ_IA_BIN>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_BIN>, nb, AZ_TPB, 0, st, P, slot, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         } else {
-            AZ_LAUNCH(az_k_integrate_a<AZ_IA_STALE>, nb, AZ_TPB, 0, st, P, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
+            AZ_LAUNCH(az_k_integrate_a<AZ_IA_STALE>, nb, AZ_TPB, 0, st, P, slot, e->pos[c], e->vel[c], e->frc, e->cellOf, e->slotOf, e->cellCount, e->sc);
         }
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1);
     }
@@ -517,30 +529,44 @@ static int one_step(az_engine* e, int step, bool want_energy)
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         const int drift_mode = rebuild ? 32 : 64;
         const int emode = want_energy ? 2 : 0;
+        float2* th = radi ? e->therm[c] : nullptr;
+        const float* ph = radi ? e->photons : nullptr;
+        const float* uv = radi ? e->uv : nullptr;
         if (!eq_step) {
-            if (radi) {
+            if (fuse_next) {
+                // the next step's kick + drift rides on this pass; its mode follows the next step's schedule
+                const bool rb_next = step_rebuilds(e);
+                const int ns = 1 - slot;
+#define AZ_BA(TS, MODE) AZ_LAUNCH((az_k_integrate_ba<TS, MODE>), nb, AZ_TPB, 0, st, P, step, ns, e->pos[c], e->vel[c], e->frc, e->id[c], th, ph, uv, \
+                                  e->partKE, e->partU, e->cellOf, e->slotOf, e->cellCount, e->sc)
+                if (rb_next && e->dd) { if (radi) AZ_BA(true, AZ_IA_WRAP); else AZ_BA(false, AZ_IA_WRAP); }
+                else if (rb_next) {
+                    AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist (the pair pass has read the counts)
+                    if (radi) AZ_BA(true, AZ_IA_BIN); else AZ_BA(false, AZ_IA_BIN);
+                } else { if (radi) AZ_BA(true, AZ_IA_STALE); else AZ_BA(false, AZ_IA_STALE); }
+#undef AZ_BA
+            } else if (radi) {
                 AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 4 | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
-                          e->revArea[0], e->revArea[1], e->revArea[2]);
             } else {
                 AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | emode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
-                          e->revArea[0], e->revArea[1], e->revArea[2]);
             }
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | (radi ? 4 : 0) | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                      e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
             AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (e->dd) { int rc = dd_global_tscale(e); if (rc) return rc; }
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
             else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
         }
     }
+    e->steps_done++;
     e->last_step = step;
     e->energy_valid = want_energy;
     return AZ_OK;
@@ -551,10 +577,18 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
     if (!e) return AZ_ERR_INVALID;
     if (nsteps < 0) { AZ_SET_ERR(e, "nsteps < 0"); return AZ_ERR_INVALID; }
     AZ_CUDA(e, cudaSetDevice(e->device));
+    bool a_done = false; // the fused kernel of the previous step already did this step's kick + drift
     for (int k = 0; k < nsteps; k++) {
+        const int step = first_step + k;
+        // Consecutive steps of one call share a pass over the atoms (second half kick of step n + first half
+        // kick and drift of step n+1) unless something must happen in between: an equilibration rescale, or the
+        // external field's per-step energy reset.  The last step of the call ends on a plain second half kick,
+        // so downloads and statistics always see the state "after step n".
+        const bool fuse = e->fuse_integrate && k + 1 < nsteps && !is_eq_step(e, step) && !e->P.has_efield;
         // potential energies are reduced on the last step of the call (the one az_engine_stats reports)
-        int rc = one_step(e, first_step + k, e->energy_every_step || k == nsteps - 1);
+        int rc = one_step(e, step, e->energy_every_step || k == nsteps - 1, a_done, fuse);
         if (rc) return rc;
+        a_done = fuse;
     }
     AZ_CUDA(e, cudaGetLastError());
     return AZ_OK;
@@ -803,6 +837,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!e || !key) return AZ_ERR_INVALID;
     if (!strcmp(key, "energy_every_step")) { e->energy_every_step = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_pipe")) { e->list_pipe = (int)value; return AZ_OK; }
+    if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;

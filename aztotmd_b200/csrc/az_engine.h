@@ -24,6 +24,8 @@ struct az_engine {
     struct PendingEv { cudaEvent_t a, b; int k; };
     std::vector<PendingEv> pending;
     int last_step = -1;
+    long long steps_done = 0;
+    bool fuse_integrate = true; // second half kick of step n and kick + drift of step n+1 in one pass
     // pair kernel configuration
     int pair_vk = 0, pair_ck = 0;
     bool pair_single = false, pair_radii = false;

@@ -44,6 +44,7 @@ __device__ __forceinline__ void az_block_sum(double (&v)[NV], double* smem /* [N
 // Device-resident step scalars (what reset_quantities / calc_quantities keep in cudaMD).
 struct AzScalars {
     double posMom[3], negMom[3];              // cumulative (src/cuMDfunc.cu:72-104)
+    double posMomPend[2][3], negMomPend[2][3]; // crossings of the step in flight (slot = step parity); az_k_finalize folds them in
     int acPos[AZ_MAX_SPECIES][3], acNeg[AZ_MAX_SPECIES][3];
     double engElecField;                      // per step
     double engKin, engVdW, engCoul1, engTemp; // per step, reduced
@@ -58,7 +59,8 @@ struct AzScalars {
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
     unsigned long long nVisits; // the same, counted from both sides (a brick sees cross-brick pairs from one side only)
-    unsigned vmax2_bits; // max |v|^2 of the current step (float bits; stale-cell steps only)
+    unsigned vmax2_bits[2]; // max |v|^2 of a stale-cell step (float bits), slot = step & 1: the fused kick+drift kernel
+                            // writes the next step's slot before this step's az_k_finalize has consumed its own
     float drift;         // upper bound of any atom's displacement since the last rebuild
 };
 #define AZ_FLAG_SKIN 1
@@ -74,57 +76,56 @@ struct AzScalars {
 #define AZ_IA_STALE 0
 #define AZ_IA_BIN 1
 #define AZ_IA_WRAP 2
+// per-atom body: returns |v|^2 after the kick; eF receives q * (x . E)
 template <int MODE>
-__global__ void __launch_bounds__(AZ_TPB)
-az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, float4* __restrict__ vel,
-                 const float4* __restrict__ frc, int* __restrict__ cellOf, int* __restrict__ slotOf,
-                 int* __restrict__ cellCount, AzScalars* __restrict__ sc)
+__device__ __forceinline__ float az_kick_drift(const AzParams& P, int i, int slot, float4& p, float4& v, const float4 f, int* __restrict__ cellOf,
+                                               int* __restrict__ slotOf, int* __restrict__ cellCount, AzScalars* __restrict__ sc, double& eF)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double eF = 0.0;
-    float v2 = 0.f;
-    if (i < az_n_owned(P)) {
-        float4 p = pos[i], v = vel[i], f = frc[i];
-        int t = __float_as_int(p.w);
-        float h = P.rMasshdT[t];
-        // explicit FMAs: what nvcc contracts the reference's `v += rMasshdT * f; x += v * tSt` into
-        v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
-        if (!P.frozen[t]) { p.x = fmaf(v.x, P.tSt, p.x); p.y = fmaf(v.y, P.tSt, p.y); p.z = fmaf(v.z, P.tSt, p.z); }
-        v2 = v.x * v.x + v.y * v.y + v.z * v.z;
-        if (MODE != AZ_IA_STALE) {
-            float m = P.mass[t];
-            float* pc[3] = { &p.x, &p.y, &p.z };
-            float vc[3] = { v.x, v.y, v.z };
-            int ci[3];
+    int t = __float_as_int(p.w);
+    float h = P.rMasshdT[t];
+    // explicit FMAs: what nvcc contracts the reference's `v += rMasshdT * f; x += v * tSt` into
+    v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
+    if (!P.frozen[t]) { p.x = fmaf(v.x, P.tSt, p.x); p.y = fmaf(v.y, P.tSt, p.y); p.z = fmaf(v.z, P.tSt, p.z); }
+    const float v2 = v.x * v.x + v.y * v.y + v.z * v.z;
+    if (MODE != AZ_IA_STALE) {
+        float m = P.mass[t];
+        float* pc[3] = { &p.x, &p.y, &p.z };
+        float vc[3] = { v.x, v.y, v.z };
+        int ci[3];
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                int nx = (int)floor((double)*pc[a] * (double)P.revL[a]); // the reference's double floor
-                float x = *pc[a] - (float)nx * P.L[a];
-                if (x >= P.L[a]) x = 0.f;
-                *pc[a] = x;
-                if (nx > 0) { atomicAdd(&sc->acPos[t][a], 1); atomicAdd(&sc->posMom[a], (double)(m * vc[a])); }
-                else if (nx < 0) { atomicAdd(&sc->acNeg[t][a], 1); atomicAdd(&sc->negMom[a], (double)(m * (-vc[a]))); }
-                int c = (int)floor((double)x * (double)P.g.crev[a]);
-                c = max(0, min(c, P.g.n[a] - 1));
-                ci[a] = c;
-            }
-            if (MODE == AZ_IA_BIN) { // storage cell id (== global id on one GPU: x*cnYZ + y*cNumber.z + z)
-                int lc = ((ci[0] - P.g.goff[0]) * P.g.nl[1] + (ci[1] - P.g.goff[1])) * P.g.nl[2] + (ci[2] - P.g.goff[2]);
-                cellOf[i] = lc;
-                slotOf[i] = atomicAdd(&cellCount[lc], 1);
-            }
+        for (int a = 0; a < 3; a++) {
+            int nx = (int)floor((double)*pc[a] * (double)P.revL[a]); // the reference's double floor
+            float x = *pc[a] - (float)nx * P.L[a];
+            if (x >= P.L[a]) x = 0.f;
+            *pc[a] = x;
+            if (nx > 0) { atomicAdd(&sc->acPos[t][a], 1); atomicAdd(&sc->posMomPend[slot][a], (double)(m * vc[a])); }
+            else if (nx < 0) { atomicAdd(&sc->acNeg[t][a], 1); atomicAdd(&sc->negMomPend[slot][a], (double)(m * (-vc[a]))); }
+            int c = (int)floor((double)x * (double)P.g.crev[a]);
+            c = max(0, min(c, P.g.n[a] - 1));
+            ci[a] = c;
         }
-        pos[i] = p; vel[i] = v;
-        if (P.has_efield) {
-            float q = P.charge[t];
-            eF = (double)(q * (p.x * P.efield[0] + p.y * P.efield[1] + p.z * P.efield[2]));
+        if (MODE == AZ_IA_BIN) { // storage cell id (== global id on one GPU: x*cnYZ + y*cNumber.z + z)
+            int lc = ((ci[0] - P.g.goff[0]) * P.g.nl[1] + (ci[1] - P.g.goff[1])) * P.g.nl[2] + (ci[2] - P.g.goff[2]);
+            cellOf[i] = lc;
+            slotOf[i] = atomicAdd(&cellCount[lc], 1);
         }
     }
-    if (MODE == AZ_IA_STALE) { // stale cells: bound the drift since the last rebuild by the fastest atom
+    if (P.has_efield) {
+        float q = P.charge[t];
+        eF = (double)(q * (p.x * P.efield[0] + p.y * P.efield[1] + p.z * P.efield[2]));
+    }
+    return v2;
+}
+
+// block-level tails: the fastest atom bounds the drift since the last rebuild (stale cells); field energy
+template <int MODE>
+__device__ __forceinline__ void az_kick_drift_tail(const AzParams& P, float v2, double eF, int slot, AzScalars* __restrict__ sc)
+{
+    if (MODE == AZ_IA_STALE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));
         // one atomic per warp only while the running maximum is still smaller (a handful per launch)
-        if ((threadIdx.x & 31) == 0 && __float_as_uint(v2) > *(volatile unsigned*)&sc->vmax2_bits) atomicMax(&sc->vmax2_bits, __float_as_uint(v2));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(v2) > *(volatile unsigned*)&sc->vmax2_bits[slot]) atomicMax(&sc->vmax2_bits[slot], __float_as_uint(v2));
     }
     if (P.has_efield) {
         __shared__ double sm[32];
@@ -132,6 +133,23 @@ az_k_integrate_a(const __grid_constant__ AzParams P, float4* __restrict__ pos, f
         az_block_sum<1>(v1, sm);
         if (threadIdx.x == 0) atomicAdd(&sc->engElecField, v1[0]);
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_integrate_a(const __grid_constant__ AzParams P, int slot, float4* __restrict__ pos, float4* __restrict__ vel,
+                 const float4* __restrict__ frc, int* __restrict__ cellOf, int* __restrict__ slotOf,
+                 int* __restrict__ cellCount, AzScalars* __restrict__ sc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double eF = 0.0;
+    float v2 = 0.f;
+    if (i < az_n_owned(P)) {
+        float4 p = pos[i], v = vel[i];
+        v2 = az_kick_drift<MODE>(P, i, slot, p, v, frc[i], cellOf, slotOf, cellCount, sc, eF);
+        pos[i] = p; vel[i] = v;
+    }
+    az_kick_drift_tail<MODE>(P, v2, eF, slot, sc);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -346,6 +364,43 @@ az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __r
     if (threadIdx.x == 0) { partKE[blockIdx.x] = 0.5 * vv[0]; if (TSTAT) partU[blockIdx.x] = vv[1]; }
 }
 
+// K5 of step n fused with K1 of step n+1 (same arithmetic in the same order, so the trajectory is bitwise
+// the one of the separate kernels): one pass reads pos, vel, frc (48 B) and writes pos, vel (32 B) instead
+// of 64 B + 80 B for the two passes.  Used inside az_engine_step for consecutive steps of one call.
+template <bool TSTAT, int MODE>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_integrate_ba(const __grid_constant__ AzParams P, int step, int slot_next, float4* __restrict__ pos, float4* __restrict__ vel,
+                  const float4* __restrict__ frc, const int* __restrict__ id, float2* __restrict__ therm,
+                  const float* __restrict__ photons, const float* __restrict__ uv, double* __restrict__ partKE,
+                  double* __restrict__ partU, int* __restrict__ cellOf, int* __restrict__ slotOf, int* __restrict__ cellCount,
+                  AzScalars* __restrict__ sc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double ke = 0.0, ut = 0.0, eF = 0.0;
+    float v2 = 0.f;
+    if (i < az_n_owned(P)) {
+        float4 p = pos[i], v = vel[i];
+        const float4 f = frc[i];
+        int t = __float_as_int(p.w);
+        float h = P.rMasshdT[t];
+        v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z); // verlet_2stage of step n
+        ke = (double)((v.x * v.x + v.y * v.y + v.z * v.z) * P.mass[t]);
+        if (TSTAT) {
+            float2 th = therm[i];
+            az_tstat_radi_atom(P, step, id[i], t, photons[i], uv, v.x, v.y, v.z, th.x, th.y);
+            therm[i] = th;
+            ut = (double)th.x;
+        }
+        v2 = az_kick_drift<MODE>(P, i, slot_next, p, v, f, cellOf, slotOf, cellCount, sc, eF); // verlet_1stage of step n + 1
+        pos[i] = p; vel[i] = v;
+    }
+    __shared__ double sm[64];
+    double vv[2] = { ke, ut };
+    az_block_sum<2>(vv, sm);
+    if (threadIdx.x == 0) { partKE[blockIdx.x] = 0.5 * vv[0]; if (TSTAT) partU[blockIdx.x] = vv[1]; }
+    az_kick_drift_tail<MODE>(P, v2, eF, slot_next, sc);
+}
+
 // temp_scale (src/cuTemp.cu:77-107) [+ tstat_radi9] on an equilibration step.
 template <bool TSTAT>
 __global__ void __launch_bounds__(AZ_TPB)
@@ -381,7 +436,7 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 // 4 = thermal energy, 8 = this is an equilibration T-scale step (computes tscale_k, after_tscale),
 // 16 = calc_quantities (src/main.cu:121-162) and publish, 32 = rebuild step, 64 = stale-cell step.
 static __global__ void __launch_bounds__(1024)
-az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const double* __restrict__ partKE, int nKE,
+az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
               const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, const float4* __restrict__ pos, AzScalars* __restrict__ sc,
               float revAx, float revAy, float revAz)
@@ -399,10 +454,16 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int mode, const doub
         if (threadIdx.x == 0) { sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25); sc->nVisits = (unsigned long long)(c[0] + 0.5); }
     }
     if (threadIdx.x != 0) return;
-    if (mode & 32) { sc->drift = 0.f; sc->vmax2_bits = 0u; } // rebuild step: cells are exact again
+    if (mode & (32 | 64)) { // this step's face crossings join the cumulative momenta (put_periodic, src/cuMDfunc.cu:72-104)
+        for (int a = 0; a < 3; a++) {
+            sc->posMom[a] += sc->posMomPend[slot][a]; sc->posMomPend[slot][a] = 0.0;
+            sc->negMom[a] += sc->negMomPend[slot][a]; sc->negMomPend[slot][a] = 0.0;
+        }
+    }
+    if (mode & 32) { sc->drift = 0.f; sc->vmax2_bits[slot] = 0u; } // rebuild step: cells are exact again
     if (mode & 64) { // stale-cell step: every atom moved by at most vmax*dt
-        sc->drift += sqrtf(__uint_as_float(sc->vmax2_bits)) * P.tSt;
-        sc->vmax2_bits = 0u;
+        sc->drift += sqrtf(__uint_as_float(sc->vmax2_bits[slot])) * P.tSt;
+        sc->vmax2_bits[slot] = 0u;
         if (2.f * sc->drift > P.skin) sc->overflow |= AZ_FLAG_SKIN;
     }
     if ((mode & 1) && !(v[0] == v[0])) sc->overflow |= AZ_FLAG_NAN;

@@ -315,6 +315,35 @@ def case_determinism(lib):
     assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
 
 
+def case_fused_kick_drift_is_bitwise_the_separate_kernels(lib):
+    """Inside one az_engine_step call the second half kick of step n and the kick + drift of step n+1 share
+    a pass over the atoms; the trajectory must be bitwise the one of single-step calls (separate kernels)."""
+    systems = [(azt.lj_system(ncell=(6, 6, 6), seed=31, temperature=800.0), {}),
+               (azt.lj_system(ncell=(6, 6, 6), seed=32, cell_size=9.3), dict(rebuild_every=4, skin=0.8)),
+               (azt.surk_system(n_side=6, n_equil=4, eq_freq=2), {}),
+               (azt.lj_system(ncell=(5, 5, 5), seed=33, vel=False, tstat=abi.TSTAT_RADI, temperature=298.0), dict(rebuild_every=3, skin=0.6, _rad=True))]
+    for s, kw in systems:
+        kw = dict(kw)
+        if kw.pop("_rad", False):
+            s.species[0].radA, s.species[0].radB, s.species[0].mxEng = 2.73, 4.731, 0.2
+        a, b = Engine(s, lib=lib, **kw), Engine(s, lib=lib, **kw)
+        a.step(0, 11)
+        for k in range(11):
+            b.step(k, 1)
+        da, db = a.dump(), b.dump()
+        for key in ("pos", "vel", "frc", "ids", "cell"):
+            assert np.array_equal(da[key], db[key]), key
+        sa, sb = a.stats(), b.stats()
+        for key in ("engKin_d", "engVdW_d", "engTemp_d", "n_pairs", "pressure"):
+            assert getattr(sa, key) == getattr(sb, key), key
+        assert list(sa.posMom) == list(sb.posMom) and list(sa.specAcBoxPos[0]) == list(sb.specAcBoxPos[0])
+        c = Engine(s, lib=lib, **kw)
+        c.set_option("fuse_integrate", 0)
+        c.step(0, 11)
+        assert np.array_equal(c.dump()["pos"], da["pos"])
+        a.close(); b.close(); c.close()
+
+
 def case_error_paths(lib):
     s = azt.lj_system(ncell=(3, 3, 3))
     s.cell_size = 0.0
@@ -364,5 +393,6 @@ ALL_CASES = [
     ("skin_violation", case_skin_violation_is_reported),
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
+    ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
     ("error_paths", case_error_paths),
 ]
