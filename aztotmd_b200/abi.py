@@ -116,6 +116,7 @@ ENGINE_SYMBOLS = {
     "az_engine_download": (C.c_int, [C.c_void_p, C.POINTER(az_atoms_out), C.c_int]),
     "az_engine_debug_dump": (C.c_int, [C.c_void_p, C.POINTER(az_dump)]),
     "az_engine_upload": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "az_engine_upload_async": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
     "az_engine_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "az_engine_timers": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     "az_engine_launch_count": (C.c_longlong, [C.c_void_p]),

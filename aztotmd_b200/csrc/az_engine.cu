@@ -111,7 +111,8 @@ static int dd_reduce_stats(az_engine* e, az_stats* o, int* flags);
 static int dd_owned_count(az_engine* e, int* n);
 static const std::vector<int>* dd_keep(az_engine* e);
 static int dd_global_tscale(az_engine* e);
-static int dd_upload(az_engine* e, const double* xs, const double* ys, const double* zs, const double* vxs, const double* vys, const double* vzs);
+static int stage_upload(az_engine* e, const double* const src[6], int len, double* dst[6], int* slot_out);
+static int dd_upload(az_engine* e, const double* const src[6], double* dst[6], int* slot);
 
 // ---------------------------------------------------------------------------------------- ABI
 extern "C" int az_abi_version(void) { return AZ_ABI_VERSION; }
@@ -402,11 +403,13 @@ extern "C" void az_engine_destroy(az_engine* e)
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
     cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
-    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage); cudaFree(e->nbr); cudaFree(e->nbrCount);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
     cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
     for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (int k = 0; k < 2; k++) { if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]); if (e->ev_unpacked[k]) cudaEventDestroy(e->ev_unpacked[k]); }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -722,28 +725,71 @@ extern "C" int az_engine_debug_dump(az_engine* e, az_dump* o)
     return AZ_OK;
 }
 
-extern "C" int az_engine_upload(az_engine* e, const double* xs, const double* ys, const double* zs,
-                                const double* vxs, const double* vys, const double* vzs)
+// H2D staging shared by the single-GPU and the brick upload: the six arrays (each `len` doubles) are copied
+// on a copy stream into one of two staging buffers; the engine's stream waits for the copy.  With
+// async == false the call returns after the data has left the caller's arrays (borrowed for the call only).
+static int stage_upload(az_engine* e, const double* const src[6], int len, double* dst[6], int* slot_out)
+{
+    if (!e->copy_stream) {
+        AZ_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            AZ_CUDA(e, cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming));
+            AZ_CUDA(e, cudaEventCreateWithFlags(&e->ev_unpacked[k], cudaEventDisableTiming));
+            AZ_ALLOC(e, e->stage2[k], (size_t)6 * len);
+            AZ_CUDA(e, cudaEventRecord(e->ev_unpacked[k], e->stream));
+        }
+    }
+    const int b = e->up_slot;
+    e->up_slot ^= 1;
+    AZ_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->ev_unpacked[b], 0)); // the kernel that last read this buffer is done
+    for (int k = 0; k < 6; k++) {
+        dst[k] = src[k] ? e->stage2[b] + (size_t)k * len : nullptr;
+        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], sizeof(double) * len, cudaMemcpyHostToDevice, e->copy_stream));
+    }
+    AZ_CUDA(e, cudaEventRecord(e->ev_copied[b], e->copy_stream));
+    AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_copied[b], 0));
+    *slot_out = b;
+    return AZ_OK;
+}
+
+static int upload_impl(az_engine* e, const double* xs, const double* ys, const double* zs,
+                       const double* vxs, const double* vys, const double* vzs, bool async)
 {
     if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
     AZ_CUDA(e, cudaSetDevice(e->device));
-    if (e->dd) return dd_upload(e, xs, ys, zs, vxs, vys, vzs);
-    const int n = e->n, c = e->cur;
-    if (!e->stage) AZ_ALLOC(e, e->stage, (size_t)6 * n);
     const double* src[6] = { xs, ys, zs, vxs, vys, vzs };
     double* dst[6];
-    for (int k = 0; k < 6; k++) {
-        dst[k] = src[k] ? e->stage + (size_t)k * n : nullptr;
-        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    int b = 0;
+    if (e->dd) {
+        int rc = dd_upload(e, src, dst, &b);
+        if (rc) return rc;
+    } else {
+        const int n = e->n, c = e->cur;
+        int rc = stage_upload(e, src, n, dst, &b);
+        if (rc) return rc;
+        AZ_LAUNCH(az_k_upload, e->n_atom_blocks, AZ_TPB, 0, e->stream, n, e->id[c], dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
+                  e->pos[c], e->vel[c], e->frc);
+        e->launches++;
     }
-    AZ_LAUNCH(az_k_upload, e->n_atom_blocks, AZ_TPB, 0, e->stream, n, e->id[c], dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
-              e->pos[c], e->vel[c], e->frc);
-    e->launches++;
-    // the caller's arrays are borrowed for the call only
-    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
-    AZ_CUDA(e, cudaGetLastError());
+    AZ_CUDA(e, cudaEventRecord(e->ev_unpacked[b], e->stream));
+    if (!async) { // the caller's arrays are borrowed for the call only
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        AZ_CUDA(e, cudaGetLastError());
+    }
     e->binned = false;
     return AZ_OK;
+}
+
+extern "C" int az_engine_upload(az_engine* e, const double* xs, const double* ys, const double* zs,
+                                const double* vxs, const double* vys, const double* vzs)
+{
+    return upload_impl(e, xs, ys, zs, vxs, vys, vzs, false);
+}
+
+extern "C" int az_engine_upload_async(az_engine* e, const double* xs, const double* ys, const double* zs,
+                                      const double* vxs, const double* vys, const double* vzs)
+{
+    return upload_impl(e, xs, ys, zs, vxs, vys, vzs, true);
 }
 
 extern "C" int az_engine_step_timed(az_engine* e, int first_step, int nsteps, float* ms)

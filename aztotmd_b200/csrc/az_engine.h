@@ -52,7 +52,13 @@ struct az_engine {
     double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
     unsigned long long* partN = nullptr;
     int n_pair_partials = 0;
-    double* stage = nullptr; // 6*n doubles: az_engine_upload staging
+    double* stage = nullptr; // unused alias kept for the emulator build
+    // az_engine_upload staging: two buffers of 6*n doubles filled on a copy stream, so that the H2D copy of the
+    // next upload overlaps the kernels of the current step (az_engine_upload_async)
+    double* stage2[2] = { nullptr, nullptr };
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {}, ev_unpacked[2] = {};
+    int up_slot = 0;
     AzScalars* sc = nullptr;
     AzVdw* table = nullptr;
     float *photons = nullptr, *uv = nullptr;

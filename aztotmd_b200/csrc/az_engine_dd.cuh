@@ -279,6 +279,11 @@ az_k_upload_dd(int n, const int* __restrict__ src, const int* __restrict__ gid, 
     frc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+static __global__ void az_k_dd_set_counts(const __grid_constant__ AzDD D, int n)
+{
+    D.cnt->n_owned = n; D.cnt->n_tot = n; D.cnt->n_arrived = 0;
+}
+
 static int dd_store_keep(az_engine* e, const az_system_desc* d)
 {
     AzDDHost* h = e->dd;
@@ -294,25 +299,17 @@ static int dd_store_keep(az_engine* e, const az_system_desc* d)
     return AZ_OK;
 }
 
-static int dd_upload(az_engine* e, const double* xs, const double* ys, const double* zs, const double* vxs, const double* vys, const double* vzs)
+static int dd_upload(az_engine* e, const double* const src[6], double* dst[6], int* slot)
 {
     AzDDHost* h = e->dd;
     if (e->use_therm) { AZ_SET_ERR(e, "az_engine_upload on bricks does not carry the thermostat state"); return AZ_ERR_UNSUPPORTED; }
     const int nc = h->n_create, n = (int)h->keep.size(), c = e->cur;
-    if (!e->stage) AZ_ALLOC(e, e->stage, (size_t)6 * nc);
-    const double* src[6] = { xs, ys, zs, vxs, vys, vzs };
-    double* dst[6];
-    for (int k = 0; k < 6; k++) {
-        dst[k] = src[k] ? e->stage + (size_t)k * nc : nullptr;
-        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream));
-    }
+    int rc = stage_upload(e, src, nc, dst, slot);
+    if (rc) return rc;
     AZ_LAUNCH(az_k_upload_dd, (n + AZ_TPB - 1) / AZ_TPB, AZ_TPB, 0, e->stream, n, h->keepSrc, h->keepGid, h->keepType, dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
               e->pos[c], e->vel[c], e->id[c], e->frc);
-    e->launches++;
-    AZ_CUDA(e, cudaStreamSynchronize(e->stream)); // the caller's arrays are borrowed for the call only
-    int rc = dd_init_counts(e, n);
-    if (rc) return rc;
-    e->binned = false;
+    AZ_LAUNCH(az_k_dd_set_counts, 1, 1, 0, e->stream, h->D, n); // stream ordered: the previous step may still be running
+    e->launches += 2;
     return AZ_OK;
 }
 

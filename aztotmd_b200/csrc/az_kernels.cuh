@@ -290,7 +290,15 @@ __device__ __forceinline__ void az_angled_vector(float ix, float iy, float iz, f
     oz = v1z * cos_phi + sinPhi * (cosTh * v2z + sinTh * v3z);
 }
 
-__device__ __forceinline__ void az_tstat_radi_atom(const AzParams& P, int step, int pid, int tp, float pe,
+// Not inlined on purpose: az_k_integrate_b, az_k_integrate_ba and az_k_tscale then run the SAME machine code, so a
+// step gives bitwise the same velocities / radii whichever kernel hosts it (inlined copies get different FMA
+// contractions from their surroundings).  Once per atom and step: the call costs nothing measurable.
+#ifdef AZ_EMU
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void az_tstat_radi_atom(const AzParams& P, int step, int pid, int tp, float pe,
                                                    const float* __restrict__ uv, float& vx, float& vy,
                                                    float& vz, float& U, float& rad)
 {

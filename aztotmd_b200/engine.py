@@ -371,11 +371,14 @@ class Engine:
                     frc=np.stack([fl["fx"], fl["fy"], fl["fz"]], 1)[:n2], pos=np.stack([fl["x"], fl["y"], fl["z"]], 1)[:n2],
                     vel=np.stack([fl["vx"], fl["vy"], fl["vz"]], 1)[:n2])
 
-    def upload(self, pos: np.ndarray, vel: Optional[np.ndarray] = None):
+    def upload(self, pos: np.ndarray, vel: Optional[np.ndarray] = None, asynchronous: bool = False):
         cols = [np.ascontiguousarray(pos[:, a], dtype=np.float64) for a in range(3)]
         vcols = [np.ascontiguousarray(vel[:, a], dtype=np.float64) for a in range(3)] if vel is not None else [None] * 3
         ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
-        self._check(self.lib.az_engine_upload(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
+        fn = self.lib.az_engine_upload_async if asynchronous else self.lib.az_engine_upload
+        if asynchronous:
+            self._pending_upload = (cols, vcols)  # the arrays must outlive the copy
+        self._check(fn(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
 
     def profile(self, mode: int = 1):
         """0 off, 1 synchronous per-section timing, 2 recorded events (no host sync in the loop)."""

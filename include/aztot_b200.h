@@ -245,6 +245,12 @@ int az_engine_debug_dump(az_engine *e, az_dump *out);
  * re-creating the engine; forces are zeroed like a fresh create. */
 int az_engine_upload(az_engine *e, const double *xs, const double *ys, const double *zs,
                      const double *vxs, const double *vys, const double *vzs);
+/* The same without the final synchronisation: the copies run on the engine's copy stream into one of two
+ * staging buffers, so the H2D transfer of the next input overlaps the kernels of the step in flight.  The
+ * arrays (pinned memory from az_host_alloc, or the copy is not asynchronous) must stay unchanged until the
+ * next az_engine_sync / az_engine_stats / az_engine_download. */
+int az_engine_upload_async(az_engine *e, const double *xs, const double *ys, const double *zs,
+                           const double *vxs, const double *vys, const double *vzs);
 
 /* Per-kernel device timers (CUDA events on the engine stream).  az_engine_profile(e, 1) times each
  * section synchronously; (e, 2) only records events inside the step loop (no host sync) and

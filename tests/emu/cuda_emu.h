@@ -242,6 +242,7 @@ typedef AzEmuEvent* cudaEvent_t;
 #define cudaMemcpyDefault 4
 #define cudaStreamNonBlocking 1
 #define cudaEventDefault 0
+#define cudaEventDisableTiming 2
 struct cudaDeviceProp { char name[256]; int multiProcessorCount; int major, minor; size_t sharedMemPerBlockOptin; size_t totalGlobalMem; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }

@@ -298,7 +298,17 @@ def case_download_upload_roundtrip(lib):
     d1, d2 = azt.sort_by_id(e.dump()), azt.sort_by_id(f.dump())
     assert np.array_equal(d1["pos"], d2["pos"]) and np.array_equal(d1["cell"], d2["cell"])
     assert np.abs(d1["frc"] - d2["frc"]).max() <= 1e-6 * np.abs(d2["frc"]).max()
-    e.close(); f.close()
+    # pipelined uploads (double-buffered staging): upload k+1 is issued while step k is still in flight
+    g = Engine(s, lib=lib)
+    pos0, vel0 = np.asarray(s.pos), np.asarray(s.vel)
+    g.upload(pos0, vel0, asynchronous=True)
+    for k in range(3):
+        g.step(0, 1)
+        g.upload(pos0, vel0, asynchronous=True)
+    g.step(0, 1)
+    d3 = azt.sort_by_id(g.dump())
+    assert np.array_equal(d3["pos"], d2["pos"]) and np.array_equal(d3["frc"], d2["frc"])
+    e.close(); f.close(); g.close()
 
 
 def case_determinism(lib):
