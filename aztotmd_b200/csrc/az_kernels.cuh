@@ -296,7 +296,7 @@ __device__ __forceinline__ void az_angled_vector(float ix, float iy, float iz, f
 #ifdef AZ_EMU
 __device__ __forceinline__
 #else
-__device__ __noinline__
+static __device__ __noinline__
 #endif
 void az_tstat_radi_atom(const AzParams& P, int step, int pid, int tp, float pe,
                                                    const float* __restrict__ uv, float& vx, float& vy,
