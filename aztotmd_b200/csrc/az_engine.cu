@@ -310,6 +310,8 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
     e->use_list = e->rebuild_every > 1 && !(o && o->pair_variant == 1);
     e->list_nblocks = (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB;
+    e->list_fast = true;
+    for (int a = 0; a < 3; a++) if (e->P.g.n[a] < 2 * e->P.g.sten[a] + 1) e->list_fast = false;
     if (e->use_list) {
         if (capt > AZ_NBR_MASK) { AZ_SET_ERR(e, "the Verlet-list path addresses at most %d atoms per GPU", AZ_NBR_MASK); return AZ_ERR_UNSUPPORTED; }
         const double rl = sqrt((double)e->P.r2list);
@@ -885,6 +887,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "list_pipe")) { e->list_pipe = (int)value; return AZ_OK; }
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
+    if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;
 }

@@ -35,6 +35,7 @@ struct az_engine {
     bool use_list = false;
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
     int list_dbg = 0;
+    bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
     int list_pipe = 0; // software-pipeline depth of the list force pass (0, 2, 4 neighbours per stage)
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;

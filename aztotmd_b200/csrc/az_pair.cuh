@@ -291,7 +291,11 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 
 __device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)(i >> 5) * (size_t)cap) * 32 + (size_t)(i & 31); }
 
-static __global__ void __launch_bounds__(AZ_LIST_TPB)
+// FAST (every axis has more than 2*sten cells, so every stencil offset is a distinct valid cell): cells are
+// pruned by the distance from the ATOM (not from its cell) to the neighbouring cell, and the z-cells of one
+// column that survive form an interval whose atoms are one contiguous range [first[lo], first[hi + 1]).
+template <bool FAST>
+__global__ void __launch_bounds__(AZ_LIST_TPB)
 az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     const AzGrid& g = P.g;
@@ -343,6 +347,53 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
     };
 
     int rb = 0, re = 0, rcode = 0; // pending range
+    auto add_range = [&](const int jb, const int je, const int code) {
+        if (jb == re && code == rcode) re = je;
+        else {
+            if (re > rb) sweep(rb, re, rcode);
+            rb = jb; re = je; rcode = code;
+        }
+    };
+    if (FAST) {
+        const float eps = 1e-3f; // Angstrom: covers the float rounding of the atom's offset inside its cell
+        const float fx = pi.x - (float)gcx * g.csize[0], fy = pi.y - (float)gcy * g.csize[1], fz = pi.z - (float)gcz * g.csize[2];
+        const int nz = g.n[2];
+        for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
+            const int ux = gcx + ox;
+            const int shxi = (ux < 0) ? -1 : ((ux >= g.n[0]) ? 1 : 0);
+            const int sx = g.dec[0] ? (ux - g.goff[0]) : (ux - shxi * g.n[0]);
+            const float dx = fmaxf(0.f, (ox > 0 ? (float)ox * g.csize[0] - fx : (ox < 0 ? fx + (float)(-ox - 1) * g.csize[0] : 0.f)) - eps);
+            for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
+                const int uy = gcy + oy;
+                const int shyi = (uy < 0) ? -1 : ((uy >= g.n[1]) ? 1 : 0);
+                const int sy = g.dec[1] ? (uy - g.goff[1]) : (uy - shyi * g.n[1]);
+                const float dy = fmaxf(0.f, (oy > 0 ? (float)oy * g.csize[1] - fy : (oy < 0 ? fy + (float)(-oy - 1) * g.csize[1] : 0.f)) - eps);
+                const float dxy2 = dx * dx + dy * dy;
+                if (dxy2 > lim) continue;
+                const float dzmax = sqrtf(lim - dxy2) + eps;
+                // oz > 0 reaches the atom's sphere iff oz*csize - fz <= dzmax; oz < 0 iff fz + (|oz|-1)*csize <= dzmax
+                const int khi = max(0, min(g.sten[2], (int)floorf((dzmax + fz) * g.crev[2])));
+                const int klo = max(0, min(g.sten[2], (int)floorf((dzmax - fz) * g.crev[2] + 1.f)));
+                const int ua = gcz - klo, ub = gcz + khi;
+                const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
+#pragma unroll 1
+                for (int shzi = -1; shzi <= 1; shzi++) { // the interval, split where it crosses a periodic face
+                    const int a = max(ua, shzi * nz), b = min(ub, shzi * nz + nz - 1);
+                    if (a > b) continue;
+                    const int off = g.dec[2] ? g.goff[2] : shzi * nz;
+                    const int cid_a = az_cell_id(g, colbase + a - off), cid_b = az_cell_id(g, colbase + b - off);
+                    const int code = az_shift_code(shxi, shyi, shzi);
+                    if (cid_b - cid_a == b - a) add_range(A.first[cid_a], A.first[cid_b + 1], code);
+                    else
+                        for (int u = a; u <= b; u++) { // ghost cells of a brick are not numbered along z
+                            const int cid = az_cell_id(g, colbase + u - off);
+                            const int jb = A.first[cid];
+                            add_range(jb, jb + A.count[cid], code);
+                        }
+                }
+            }
+        }
+    } else {
     for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
         int sx, shxi;
         if (!az_neighbor(g, 0, gcx, ox, sx, shxi)) continue;
@@ -364,14 +415,10 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
                 if (mxy2 + mz * mz > lim) continue;
                 const int cid = az_cell_id(g, colbase + sz);
                 const int jb = A.first[cid], je = jb + A.count[cid];
-                const int code = az_shift_code(shxi, shyi, shzi);
-                if (jb == re && code == rcode) re = je;
-                else {
-                    if (re > rb) sweep(rb, re, rcode);
-                    rb = jb; re = je; rcode = code;
-                }
+                add_range(jb, je, az_shift_code(shxi, shyi, shzi));
             }
         }
+    }
     }
     if (re > rb) sweep(rb, re, rcode);
     if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }

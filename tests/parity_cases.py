@@ -238,6 +238,22 @@ def case_rebuild_interval_list_pipelined(lib):
     _rebuild_vs_every_step(lib, azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6), 0.6, 0, nsteps=6, pipe=2)
 
 
+def case_rebuild_interval_list_wide_stencils(lib):
+    # half- and third-size cells (stencil 2 and 3): the list build prunes cells by the atom's own position and walks
+    # z-intervals of the columns; every in-range pair must still be found (pair counts equal the oracle's)
+    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(7, 7, 7), seed=17, cell_size=4.7), 0.6, 0, nsteps=5)
+    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 7, 8), seed=18, cell_size=3.2), 0.5, 0, nsteps=4)
+    # the generic cell walk (tiny grids use it) gives the same list as the fast one
+    s = azt.lj_system(ncell=(7, 7, 7), seed=17, cell_size=4.7)
+    a, b = Engine(s, lib=lib, rebuild_every=4, skin=0.6), Engine(s, lib=lib, rebuild_every=4, skin=0.6)
+    b.set_option("list_fast", 0)
+    a.step(0, 6); b.step(0, 6)
+    da, db = a.dump(), b.dump()
+    assert np.array_equal(da["pos"], db["pos"]) and np.abs(da["frc"] - db["frc"]).max() <= 1e-5 * np.abs(db["frc"]).max()
+    assert a.stats().n_pairs == b.stats().n_pairs
+    a.close(); b.close()
+
+
 def case_rebuild_interval_stale_tiles(lib):
     _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 1)
 
@@ -396,6 +412,7 @@ ALL_CASES = [
     ("face_crossings_pressure", case_face_crossings_and_pressure),
     ("rebuild_interval_list", case_rebuild_interval_list),
     ("rebuild_interval_list_pipelined", case_rebuild_interval_list_pipelined),
+    ("rebuild_interval_list_wide_stencils", case_rebuild_interval_list_wide_stencils),
     ("rebuild_interval_stale_tiles", case_rebuild_interval_stale_tiles),
     ("rebuild_interval_list_ionic", case_rebuild_interval_list_ionic),
     ("rebuild_interval_list_surk_radiative", case_rebuild_interval_list_surk_radiative),
