@@ -341,7 +341,12 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
         AZ_ALLOC(e, e->nbr, (size_t)e->nbr_cap * e->nbr_stride);
         AZ_ALLOC(e, e->nbrCount, capo);
     }
-    { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve both kernels
+    // pair_variant: 0 auto (list between rebuilds; warp-per-atom sweep on the every-step schedule), 1 = shared-memory
+    // cell tiles only, 2 = list, 3 = warp-per-atom sweep
+    e->warp_nblocks = (capo + (AZ_WARP_TPB / 32) - 1) / (AZ_WARP_TPB / 32);
+    e->use_warp = !e->use_list && !(o && o->pair_variant == 1);
+    { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve all pair kernels
+      if (e->warp_nblocks > np) np = e->warp_nblocks;
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
     AZ_ALLOC(e, e->table, e->h_table.size());
@@ -468,7 +473,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const bool eq_step = is_eq_step(e, step);
     const int nb = e->n_atom_blocks;
     int c = e->cur;
-    const int n_pp = e->use_list ? e->list_nblocks : e->pair_nblocks; // live pair partials this step
+    const int n_pp = e->use_list ? e->list_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks); // live pair partials this step
     const int slot = (int)(e->steps_done & 1);
 
     if (!skip_a) { // K1: half kick + drift (+ wrap + bin)
@@ -516,7 +521,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         if (e->dd) { int rc = dd_refresh_ghosts(e, c); if (rc) return rc; }
     }
     { // K4: pair forces
-        const int pair_mode = !e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST);
+        const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
         Timer t(e, pair_timer);
         AzPairArgs A;

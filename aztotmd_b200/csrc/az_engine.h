@@ -34,6 +34,8 @@ struct az_engine {
     // Verlet-list path (rebuild_every > 1)
     bool use_list = false;
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
+    int warp_nblocks = 0;     // az_k_pair_warp: one warp per owned atom
+    bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
     bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
     int list_pipe = 0; // software-pipeline depth of the list force pass (0, 2, 4 neighbours per stage)

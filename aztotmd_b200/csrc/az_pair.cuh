@@ -291,9 +291,12 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 
 __device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)(i >> 5) * (size_t)cap) * 32 + (size_t)(i & 31); }
 
-// FAST (every axis has more than 2*sten cells, so every stencil offset is a distinct valid cell): cells are
-// pruned by the distance from the ATOM (not from its cell) to the neighbouring cell, and the z-cells of one
-// column that survive form an interval whose atoms are one contiguous range [first[lo], first[hi + 1]).
+// FAST (every axis has more than 2*sten cells, so every stencil offset is a distinct valid cell): the z-cells of
+// one column that can hold neighbours form an interval whose atoms are one contiguous range
+// [first[lo], first[hi + 1]) -- two loads per column instead of two per cell.  Cells are kept or dropped by the
+// cell-to-cell distance of the reference (cell_dist_int), NOT by the atom's own position: measured on B200, pruning
+// per atom makes the lanes of a warp (atoms of one cell) walk different ranges, which costs more in divergence
+// and lost L1 broadcasts (22 active lanes per instruction instead of 30) than the 30 % fewer candidates save.
 template <bool FAST>
 __global__ void __launch_bounds__(AZ_LIST_TPB)
 az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
@@ -355,25 +358,26 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
         }
     };
     if (FAST) {
-        const float eps = 1e-3f; // Angstrom: covers the float rounding of the atom's offset inside its cell
-        const float fx = pi.x - (float)gcx * g.csize[0], fy = pi.y - (float)gcy * g.csize[1], fz = pi.z - (float)gcz * g.csize[2];
         const int nz = g.n[2];
         for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
             const int ux = gcx + ox;
             const int shxi = (ux < 0) ? -1 : ((ux >= g.n[0]) ? 1 : 0);
             const int sx = g.dec[0] ? (ux - g.goff[0]) : (ux - shxi * g.n[0]);
-            const float dx = fmaxf(0.f, (ox > 0 ? (float)ox * g.csize[0] - fx : (ox < 0 ? fx + (float)(-ox - 1) * g.csize[0] : 0.f)) - eps);
+            const int aox = ox < 0 ? -ox : ox;
+            const float dx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
             for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
                 const int uy = gcy + oy;
                 const int shyi = (uy < 0) ? -1 : ((uy >= g.n[1]) ? 1 : 0);
                 const int sy = g.dec[1] ? (uy - g.goff[1]) : (uy - shyi * g.n[1]);
-                const float dy = fmaxf(0.f, (oy > 0 ? (float)oy * g.csize[1] - fy : (oy < 0 ? fy + (float)(-oy - 1) * g.csize[1] : 0.f)) - eps);
+                const int aoy = oy < 0 ? -oy : oy;
+                const float dy = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
                 const float dxy2 = dx * dx + dy * dy;
                 if (dxy2 > lim) continue;
-                const float dzmax = sqrtf(lim - dxy2) + eps;
-                // oz > 0 reaches the atom's sphere iff oz*csize - fz <= dzmax; oz < 0 iff fz + (|oz|-1)*csize <= dzmax
-                const int khi = max(0, min(g.sten[2], (int)floorf((dzmax + fz) * g.crev[2])));
-                const int klo = max(0, min(g.sten[2], (int)floorf((dzmax - fz) * g.crev[2] + 1.f)));
+                // |oz| = k is kept iff dxy2 + ((k-1)*csize)^2 <= lim  (checked exactly below: sqrt and floor round)
+                int kz = min(g.sten[2], 1 + (int)floorf(sqrtf(lim - dxy2) * g.crev[2]));
+                while (kz < g.sten[2] && dxy2 + ((float)kz * g.csize[2]) * ((float)kz * g.csize[2]) <= lim) kz++;
+                while (kz > 0 && dxy2 + ((float)(kz - 1) * g.csize[2]) * ((float)(kz - 1) * g.csize[2]) > lim) kz--;
+                const int khi = kz, klo = kz;
                 const int ua = gcz - klo, ub = gcz + khi;
                 const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
 #pragma unroll 1
@@ -554,6 +558,118 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             const float sz = ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
             one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
+        const float q = P.charge[ti];
+        A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+    }
+    if (ENERGY) {
+        double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
+        az_block_sum<3>(vv, s_red);
+        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// az_k_pair_warp: the reference schedule (bin + sort every step, no list) with one WARP per atom.  The lanes
+// stride over the atoms of the stencil cells straight from the sorted stream (coalesced float4 loads; z-adjacent
+// cells are merged into one range), every lane accumulates its share of the force on atom i and a shuffle
+// tree adds the 32 shares.  Same cell-pair rules (az_neighbor), same pair arithmetic and per-cell-pair image
+// shift as az_k_pair.  Why it exists: the case-study decks hold 4 000 / 40 000 atoms -- one thread per atom is
+// 125 / 1 250 warps on 148 SMs and each thread walks 500-800 candidates serially (measured: 790 us per step at
+// 4 000 atoms); one warp per atom is 32x the parallelism and 1/32 of the serial chain.
+#define AZ_WARP_TPB 256
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+__global__ void __launch_bounds__(AZ_WARP_TPB)
+az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
+{
+    __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
+    __shared__ double s_red[96];
+    const AzGrid& g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (!SINGLE) {
+        for (int k = tid; k < P.nspec * P.nspec; k += AZ_WARP_TPB) s_tab[k] = A.table[k];
+        __syncthreads();
+    }
+    const int i = blockIdx.x * (AZ_WARP_TPB / 32) + (tid >> 5);
+    const bool act = i < az_n_owned(P);
+    float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
+    int hits = 0, ti = 0;
+    if (act) {
+        const float4 pi = A.pos[i];
+        ti = __float_as_int(pi.w);
+        float radi = 0.f;
+        if (RADII) radi = A.therm[i].y;
+        const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+        const int ci = A.cellOfSorted[i];
+        const int cxy = ci / onz;
+        const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+        const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+        const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+        constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
+        const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
+
+        auto sweep = [&](const int rb, const int re, const int code) {
+            const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
+            const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
+            const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
+            for (int j = rb + lane; j < re; j += 32) {
+                const float4 pj = __ldg(A.pos + j);
+                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                if (code) { dx -= shx; dy -= shy; dz -= shz; } // (x_i - x_j) - shift, exactly like the reference's secShifts
+                const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                const bool in = (r2 <= gate) & (j != i);
+                const int tj = __float_as_int(pj.w);
+                float radj = 0.f;
+                if (RADII) radj = A.therm[j].y;
+                float e1 = 0.f, e2 = 0.f, f;
+                if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+                else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+                f = in ? f : 0.f;
+                fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+                if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
+            }
+        };
+        int rb = 0, re = 0, rcode = 0; // pending range (cells adjacent in memory with the same image)
+        for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
+            int sx, shxi;
+            if (!az_neighbor(g, 0, gcx, ox, sx, shxi)) continue;
+            const int aox = ox < 0 ? -ox : ox;
+            const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+            for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
+                int sy, shyi;
+                if (!az_neighbor(g, 1, gcy, oy, sy, shyi)) continue;
+                const int aoy = oy < 0 ? -oy : oy;
+                const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+                const float mxy2 = mx * mx + my * my;
+                if (mxy2 > P.r2list) continue;
+                const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
+                for (int oz = -g.sten[2]; oz <= g.sten[2]; oz++) {
+                    int sz, shzi;
+                    if (!az_neighbor(g, 2, gcz, oz, sz, shzi)) continue;
+                    const int aoz = oz < 0 ? -oz : oz;
+                    const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+                    if (mxy2 + mz * mz > P.r2list) continue;
+                    const int cid = az_cell_id(g, colbase + sz);
+                    const int jb = A.first[cid], je = jb + A.count[cid];
+                    const int code = az_shift_code(shxi, shyi, shzi);
+                    if (jb == re && code == rcode) re = je;
+                    else {
+                        if (re > rb) sweep(rb, re, rcode);
+                        rb = jb; re = je; rcode = code;
+                    }
+                }
+            }
+        }
+        if (re > rb) sweep(rb, re, rcode);
+    }
+    // the 32 shares of atom i (all lanes of a warp belong to the same atom, so the whole warp is in or out)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fx += __shfl_down_sync(0xffffffffu, fx, o);
+        fy += __shfl_down_sync(0xffffffffu, fy, o);
+        fz += __shfl_down_sync(0xffffffffu, fz, o);
+    }
+    if (act && lane == 0) {
         const float q = P.charge[ti];
         A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
     }

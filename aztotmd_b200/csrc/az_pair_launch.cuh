@@ -2,10 +2,12 @@
 #pragma once
 #include "az_engine.h"
 
-// mode: 0 = cell-tile force sweep, 1 = cell-tile sweep that records the Verlet list + list force pass, 2 = list force pass
+// mode: 0 = cell-tile force sweep (shared-memory windows, one thread per atom), 1 = list build + list force pass,
+// 2 = list force pass, 3 = cell sweep with one warp per atom
 #define AZ_PAIR_MODE_TILE 0
 #define AZ_PAIR_MODE_TILE_LIST 1
 #define AZ_PAIR_MODE_LIST 2
+#define AZ_PAIR_MODE_WARP 3
 
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_go(az_engine* e, const AzPairArgs& A)
@@ -26,15 +28,22 @@ static int az_pair_go(az_engine* e, const AzPairArgs& A)
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 {
-    if (e->list_pipe == 4) AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 4>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
-    else if (e->list_pipe == 2) AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 2>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
-    else AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 0>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 0>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    return AZ_OK;
+}
+
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+static int az_pair_warp_go(az_engine* e, const AzPairArgs& A)
+{
+    AZ_LAUNCH((az_k_pair_warp<VK, CK, SINGLE, RADII, ENERGY>), e->warp_nblocks, AZ_WARP_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
 }
 
 template <int VK, int CK, bool SINGLE, bool RADII>
 static int az_pair_go_e(az_engine* e, const AzPairArgs& A, bool energy, int mode)
 {
+    if (mode == AZ_PAIR_MODE_WARP)
+        return energy ? az_pair_warp_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_warp_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_LIST)
         return energy ? az_pair_list_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_list_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_TILE_LIST) { // record the neighbours, then take this step's forces from the list like every other step

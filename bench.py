@@ -46,6 +46,9 @@ WORKLOADS = {
     "lj500k": (50, "synthetic fcc LJ argon, 500,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj4k": (10, "synthetic fcc LJ argon, 4,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj32k": (20, "synthetic fcc LJ argon, 32,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    # latency-bound decks of the reference (BASELINE configs 0 and 1), rebuilt synthetically (the shipped files cannot travel)
+    "cs1": (0, "case-study-1-like: 40,000 argon atoms, dilute gas in a 1141.5 A box, LJ rc 4.0 A, cell_list 85, radiative thermostat 298 K"),
+    "cs2": (0, "case-study-2-like: 4,000 abstract atoms, 35 A box, surk rc 6.0 A + radii, cell_list 2.7, radiative thermostat 500 K"),
 }
 AR_EPS, AR_SIGMA, AR_MASS = 0.01006, 3.3952, 39.9
 
@@ -60,6 +63,28 @@ def lj_system(ncell, rebuild, skin, seed=12345, cell_div=1):
                timestep=0.001, cell_size=(rc + (skin if rebuild > 1 else 0.0)) / cell_div, temperature=86.6, seed=seed)
     s.set_vdw(0, 0, "lnjs", rc, [AR_EPS, AR_SIGMA])
     s.vel = s.gauss_velocities(seed)
+    return s
+
+
+def case_study_system(name, seed=12345):
+    """Synthetic twins of the reference's two shipped decks (same sizes, box, potentials, thermostat, cell_list)."""
+    from aztotmd_b200 import abi
+    from aztotmd_b200.engine import Species, System
+    rng = np.random.default_rng(seed)
+    if name == "cs1":
+        m, L = 35, 1141.5  # 35^3 = 42 875 sites of a simple cubic lattice, the first 40 000 are used
+        g = (np.arange(m) + 0.5) * (L / m)
+        pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:40000] + rng.uniform(-10.0, 10.0, size=(40000, 3))
+        s = System(pos=pos % L, types=np.zeros(40000, dtype=np.int32), box=(L, L, L), species=[Species("Ar", AR_MASS, 0.0, 0, 2.73, 4.731, 0.2)],
+                   timestep=0.001, cell_size=85.0, temperature=298.0, seed=seed, tstat_kind=abi.TSTAT_RADI)
+        s.set_vdw(0, 0, "lnjs", 4.0, [AR_EPS, AR_SIGMA])
+        return s
+    g = np.arange(16) * 1.3
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:4000]
+    pos = pos + (35.0 - g[-1]) / 2 + rng.uniform(-0.2, 0.2, size=pos.shape)
+    s = System(pos=pos, types=np.zeros(4000, dtype=np.int32), box=(35.0, 35.0, 35.0), species=[Species("Ar", AR_MASS, 0.0, 0, 2.73, 4.731, 0.2)],
+               timestep=0.001, cell_size=2.7, temperature=500.0, seed=seed, tstat_kind=abi.TSTAT_RADI, n_equil=10000, eq_freq=2500)
+    s.set_vdw(0, 0, "surk", 6.0, [75.0, 8.0, 1.0, 1.0])
     return s
 
 
@@ -179,11 +204,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncell, desc = WORKLOADS[args.workload]
-    n_atoms = 4 * ncell ** 3
+    n_atoms = 4 * ncell ** 3 if ncell else (40000 if args.workload == "cs1" else 4000)
     config = {"workload": "%s; cell_list = rc%s; rebuild every %d steps; dt = 1 fs; NVE" % (
         desc, " + skin %.2f A" % args.skin if args.rebuild > 1 else "", args.rebuild),
         "n_atoms": n_atoms, "rebuild_every": args.rebuild, "skin": args.skin if args.rebuild > 1 else 0.0,
-        "l2": "inputs larger than L2 (%.0f MB of pos/vel/frc streams vs 126 MB)" % (n_atoms * 48 / 1e6)}
+        "l2": ("inputs larger than L2 (%.0f MB of pos/vel/frc streams vs 126 MB)" % (n_atoms * 48 / 1e6)) if n_atoms * 48 > 126e6 else
+              "latency-bound deck: the whole state (%.1f MB) fits L2 by construction of the reference's case study; no flush" % (n_atoms * 48 / 1e6)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -212,7 +238,7 @@ def main():
     assert lib.az_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)) == 0
     fp32_peak = tf.value
 
-    s = lj_system(ncell, args.rebuild, args.skin, cell_div=args.cell_div)
+    s = lj_system(ncell, args.rebuild, args.skin, cell_div=args.cell_div) if ncell else case_study_system(args.workload)
     e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0, pair_variant=args.pair_variant)
     if args.list_pipe >= 0:
         e.set_option("list_pipe", args.list_pipe)

@@ -55,7 +55,33 @@ struct EmuComm : AzComm {
         return AZ_OK;
     }
 };
+// Second transport of the emulator build: the exchange and the all-reduce are handed to callbacks, so that a
+// test can carry them over torch.distributed (gloo) between real processes (tests/test_gloo_bricks.py).
+typedef int (*az_emu_exchange_cb)(int n_ops, const int* peers, const void* const* send, const size_t* send_bytes,
+                                  void* const* recv, const size_t* recv_bytes);
+typedef int (*az_emu_allreduce_cb)(double* data, int n, int take_max);
+az_emu_exchange_cb g_exchange_cb = nullptr;
+az_emu_allreduce_cb g_allreduce_cb = nullptr;
+
+struct CallbackComm : AzComm {
+    int exchange(const std::vector<AzP2P>& ops, cudaStream_t) override
+    {
+        std::vector<int> peers; std::vector<const void*> sp; std::vector<size_t> sb, rb; std::vector<void*> rp;
+        for (const AzP2P& o : ops) { peers.push_back(o.peer); sp.push_back(o.send); sb.push_back(o.send_bytes); rp.push_back(o.recv); rb.push_back(o.recv_bytes); }
+        int rc = g_exchange_cb((int)ops.size(), peers.data(), sp.data(), sb.data(), rp.data(), rb.data());
+        if (rc) { err = "callback comm: exchange failed"; return AZ_ERR_COMM; }
+        return AZ_OK;
+    }
+    int allreduce(double* dev, int n, bool take_max, cudaStream_t) override
+    {
+        int rc = g_allreduce_cb(dev, n, take_max ? 1 : 0);
+        if (rc) { err = "callback comm: allreduce failed"; return AZ_ERR_COMM; }
+        return AZ_OK;
+    }
+};
 } // namespace
+
+extern "C" void az_emu_set_comm_callbacks(az_emu_exchange_cb ex, az_emu_allreduce_cb ar) { g_exchange_cb = ex; g_allreduce_cb = ar; }
 
 int az_comm_make_id(void* id128, std::string*)
 {
@@ -69,6 +95,12 @@ int az_comm_make_id(void* id128, std::string*)
 int az_comm_create(const void* id, int rank, int nranks, int, AzComm** out, std::string* err)
 {
     if (!id) { if (err) *err = "multi-rank create needs an id"; return AZ_ERR_INVALID; }
+    if (g_exchange_cb && g_allreduce_cb) {
+        CallbackComm* c = new CallbackComm();
+        c->rank = rank; c->nranks = nranks;
+        *out = c;
+        return AZ_OK;
+    }
     std::string key((const char*)id, strnlen((const char*)id, 128));
     std::lock_guard<std::mutex> lk(g_m);
     World*& w = g_worlds[key];

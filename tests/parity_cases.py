@@ -370,6 +370,21 @@ def case_fused_kick_drift_is_bitwise_the_separate_kernels(lib):
         a.close(); b.close(); c.close()
 
 
+def case_tile_kernel_variant(lib):
+    """pair_variant = 1: the shared-memory cell-tile sweep (one thread per atom) instead of the default
+    warp-per-atom sweep -- same parity bars."""
+    o, e = run_parity(lib, azt.lj_system(ncell=(6, 6, 6), seed=61), nsteps=2, pair_variant=1)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(5, 5, 5), seed=62, cell_size=2.9), nsteps=1, pair_variant=1)
+    e.close()
+    o, e = run_parity(lib, azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_FENNEL), nsteps=2, pair_variant=1)
+    e.close()
+    o, e = run_parity(lib, azt.surk_system(n_side=6, n_equil=4, eq_freq=2), nsteps=3, thermo=True, state_tol=1e-4, later_force_tol=1e-4, pair_variant=1)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(6, 6, 6), seed=9, cell_size=17.0), nsteps=1, pair_variant=1)  # several i-batches per CTA
+    e.close()
+
+
 def case_error_paths(lib):
     s = azt.lj_system(ncell=(3, 3, 3))
     s.cell_size = 0.0
@@ -420,6 +435,7 @@ ALL_CASES = [
     ("skin_violation", case_skin_violation_is_reported),
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
+    ("tile_kernel_variant", case_tile_kernel_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
     ("error_paths", case_error_paths),
 ]
