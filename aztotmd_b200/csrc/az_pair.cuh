@@ -629,38 +629,51 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
                 if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
             }
         };
-        int rb = 0, re = 0, rcode = 0; // pending range (cells adjacent in memory with the same image)
-        for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
-            int sx, shxi;
-            if (!az_neighbor(g, 0, gcx, ox, sx, shxi)) continue;
-            const int aox = ox < 0 ? -ox : ox;
-            const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
-            for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
-                int sy, shyi;
-                if (!az_neighbor(g, 1, gcy, oy, sy, shyi)) continue;
-                const int aoy = oy < 0 ? -oy : oy;
-                const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
-                const float mxy2 = mx * mx + my * my;
-                if (mxy2 > P.r2list) continue;
-                const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
-                for (int oz = -g.sten[2]; oz <= g.sten[2]; oz++) {
-                    int sz, shzi;
-                    if (!az_neighbor(g, 2, gcz, oz, sz, shzi)) continue;
-                    const int aoz = oz < 0 ? -oz : oz;
+        // The stencil cells are enumerated 32 at a time, one cell per lane (z offset fastest): validity, image and
+        // the two loads (first, count) of all cells of a chunk are in flight together instead of one after the other.
+        // Runs of lanes whose ranges are adjacent in memory with the same image (the z neighbours of one column)
+        // are merged, then the warp sweeps the merged ranges one by one.
+        const int wx = 2 * g.sten[0] + 1, wy = 2 * g.sten[1] + 1, wz = 2 * g.sten[2] + 1;
+        const int ncells = wx * wy * wz;
+        for (int c0 = 0; c0 < ncells; c0 += 32) {
+            const int c = c0 + lane;
+            int jb = -1, je = -1, code = 0;
+            if (c < ncells) {
+                const int oz = c % wz - g.sten[2], t = c / wz;
+                const int oy = t % wy - g.sten[1], ox = t / wy - g.sten[0];
+                int sx, sy, sz, shxi, shyi, shzi;
+                if (az_neighbor(g, 0, gcx, ox, sx, shxi) && az_neighbor(g, 1, gcy, oy, sy, shyi) && az_neighbor(g, 2, gcz, oz, sz, shzi)) {
+                    const int aox = ox < 0 ? -ox : ox, aoy = oy < 0 ? -oy : oy, aoz = oz < 0 ? -oz : oz;
+                    const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+                    const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
                     const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
-                    if (mxy2 + mz * mz > P.r2list) continue;
-                    const int cid = az_cell_id(g, colbase + sz);
-                    const int jb = A.first[cid], je = jb + A.count[cid];
-                    const int code = az_shift_code(shxi, shyi, shzi);
-                    if (jb == re && code == rcode) re = je;
-                    else {
-                        if (re > rb) sweep(rb, re, rcode);
-                        rb = jb; re = je; rcode = code;
+                    const float mxy2 = mx * mx + my * my;
+                    if (mxy2 <= P.r2list && mxy2 + mz * mz <= P.r2list) {
+                        const int cid = az_cell_id(g, (sx * g.nl[1] + sy) * g.nl[2] + sz);
+                        jb = A.first[cid];
+                        je = jb + A.count[cid];
+                        code = az_shift_code(shxi, shyi, shzi);
                     }
                 }
             }
+            const bool valid = je > jb;
+            // continuation: this lane's range starts where the previous lane's ends, same image
+            const int pje = __shfl_up_sync(0xffffffffu, je, 1), pcode = __shfl_up_sync(0xffffffffu, code, 1);
+            const int pvalid = __shfl_up_sync(0xffffffffu, (int)valid, 1);
+            const bool cont = valid && lane > 0 && pvalid && pje == jb && pcode == code;
+            const unsigned contmask = __ballot_sync(0xffffffffu, cont);
+            unsigned heads = __ballot_sync(0xffffffffu, valid && !cont);
+            // a head's run covers the consecutive continuation lanes behind it
+            const unsigned behind = lane < 31 ? (contmask >> (lane + 1)) : 0u;
+            const int runlen = __ffs((int)~behind) - 1; // consecutive ones from bit 0
+            const int je_run = __shfl_sync(0xffffffffu, je, min(31, lane + runlen));
+            while (heads) {
+                const int h = __ffs((int)heads) - 1;
+                heads &= heads - 1;
+                const int rb = __shfl_sync(0xffffffffu, jb, h), re = __shfl_sync(0xffffffffu, je_run, h), rcode = __shfl_sync(0xffffffffu, code, h);
+                sweep(rb, re, rcode);
+            }
         }
-        if (re > rb) sweep(rb, re, rcode);
     }
     // the 32 shares of atom i (all lanes of a warp belong to the same atom, so the whole warp is in or out)
 #pragma unroll

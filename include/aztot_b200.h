@@ -158,8 +158,9 @@ typedef struct az_cuda_opts {
     int rebuild_every;   /* 0/1 = reference behaviour (bin + sort every step)         */
     float skin;          /* extra cell width when rebuild_every > 1 (Angstrom)        */
     int use_graph;       /* 1 = capture the steady-state step in a CUDA graph         */
-    int pair_variant;    /* 0 = auto (Verlet list between rebuilds, warp-per-atom cell sweep on the every-step
-                            schedule), 1 = shared-memory cell tiles only */
+    int pair_variant;    /* 0 = auto (Verlet list between rebuilds and for large systems, warp-per-atom cell sweep
+                            for small systems on the every-step schedule), 1 = shared-memory cell tiles,
+                            2 = list (rebuilt every step if rebuild_every <= 1), 3 = warp-per-atom sweep */
     int cells_per_block; /* 0 = auto; z-run length a CTA owns in the pair kernel      */
     /* spatial domain decomposition (new functionality) */
     int rank, n_ranks;

@@ -385,6 +385,21 @@ def case_tile_kernel_variant(lib):
     e.close()
 
 
+def case_list_every_step_variant(lib):
+    """pair_variant = 2 on the every-step schedule (what large systems use automatically): the Verlet list is
+    rebuilt every step with radius rc, so the recorded set IS the in-range set -- same parity bars."""
+    o, e = run_parity(lib, azt.lj_system(ncell=(6, 6, 6), seed=63), nsteps=3, pair_variant=2)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(5, 5, 5), seed=64, cell_size=2.9), nsteps=2, pair_variant=2)
+    e.close()
+    o, e = run_parity(lib, azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_DIRECT), nsteps=2, pair_variant=2)
+    e.close()
+    o, e = run_parity(lib, azt.surk_system(n_side=6, n_equil=4, eq_freq=2), nsteps=3, thermo=True, state_tol=1e-4, later_force_tol=1e-4, pair_variant=2)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(4, 4, 4), seed=5), nsteps=2, pair_variant=2)  # 2 cells per axis: generic cell walk
+    e.close()
+
+
 def case_error_paths(lib):
     s = azt.lj_system(ncell=(3, 3, 3))
     s.cell_size = 0.0
@@ -436,6 +451,7 @@ ALL_CASES = [
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
     ("tile_kernel_variant", case_tile_kernel_variant),
+    ("list_every_step_variant", case_list_every_step_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
     ("error_paths", case_error_paths),
 ]
