@@ -105,7 +105,12 @@ static int dd_alloc(az_engine* e);
 static int dd_store_keep(az_engine* e, const az_system_desc* d);
 static void dd_free(az_engine* e);
 static int dd_rebuild(az_engine* e, int c);
-static int dd_refresh_ghosts(az_engine* e, int c);
+static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream);
+static int dd_wait_ghosts(az_engine* e);
+static int dd_mark_moved(az_engine* e);
+static bool dd_overlap(const az_engine* e);
+static int* dd_block_flags(const az_engine* e);
+static void dd_set_overlap(az_engine* e, bool on);
 static int dd_init_counts(az_engine* e, int n_keep);
 static int dd_reduce_stats(az_engine* e, az_stats* o, int* flags);
 static int dd_owned_count(az_engine* e, int* n);
@@ -523,8 +528,9 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         e->since_rebuild = 0;
     } else {
         e->since_rebuild++;
-        if (e->dd) { int rc = dd_refresh_ghosts(e, c); if (rc) return rc; }
+        if (e->dd) { int rc = dd_overlap(e) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
     }
+    const bool split = !rebuild && dd_overlap(e); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
     { // K4: pair forces
         const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
@@ -536,7 +542,20 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
         A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg;
-        int rc = az_launch_pair(e, A, want_energy, pair_mode);
+        A.blockFlag = dd_block_flags(e);
+        int rc;
+        if (split) { // blocks that list no ghost run while the halo is in flight, the others once it has landed
+            A.phase = 1;
+            rc = az_launch_pair(e, A, want_energy, pair_mode);
+            if (rc) return rc;
+            rc = dd_refresh_ghosts(e, c, true); // pack -> exchange -> overwrite the ghost slots, on the halo stream
+            if (rc) return rc;
+            rc = dd_wait_ghosts(e);
+            if (rc) return rc;
+            A.phase = 2;
+            AZ_COUNT(e, pair_timer, 1);
+        }
+        rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
     }
@@ -895,6 +914,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!e || !key) return AZ_ERR_INVALID;
     if (!strcmp(key, "energy_every_step")) { e->energy_every_step = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_pipe")) { e->list_pipe = (int)value; return AZ_OK; }
+    if (!strcmp(key, "halo_overlap")) { dd_set_overlap(e, value != 0.0); return AZ_OK; }
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)

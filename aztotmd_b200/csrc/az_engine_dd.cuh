@@ -24,6 +24,12 @@ struct AzDDHost {
     double* red = nullptr; // 128 doubles of all-reduce scratch
     bool replicated = true;
     std::vector<int> keep; // indices into the create-time arrays of the atoms this rank took
+    // halo / compute overlap on the steps between rebuilds: the ghost refresh runs on its own stream while the list
+    // blocks that see no ghost are already computing
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_moved = nullptr, ev_ghosts = nullptr;
+    int* blockFlag = nullptr;
+    bool overlap = true;
     int n_create = 0;      // length of the create-time arrays (az_engine_upload takes arrays of the same shape)
     int *keepSrc = nullptr, *keepGid = nullptr, *keepType = nullptr; // device copies for az_engine_upload
 };
@@ -45,6 +51,10 @@ static void dd_free(az_engine* e)
     if (!h) return;
     cudaFree(h->cellmap); cudaFree(h->stay); cudaFree(h->newIndex); cudaFree(h->sendList); cudaFree(h->ghostSlot); cudaFree(h->migList);
     cudaFree(h->gSendPos); cudaFree(h->gRecvPos); cudaFree(h->gSendAux); cudaFree(h->gRecvAux); cudaFree(h->mSend); cudaFree(h->mRecv);
+    cudaFree(h->blockFlag);
+    if (h->ev_moved) cudaEventDestroy(h->ev_moved);
+    if (h->ev_ghosts) cudaEventDestroy(h->ev_ghosts);
+    if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
     cudaFree(h->cnt); cudaFree(h->red); cudaFree(h->keepSrc); cudaFree(h->keepGid); cudaFree(h->keepType);
     delete h->comm;
     delete h;
@@ -368,6 +378,10 @@ static int dd_alloc(az_engine* e)
     AZ_ALLOC(e, h->gSendPos, D.gs[AZ_NDIR]); AZ_ALLOC(e, h->gRecvPos, D.gr[AZ_NDIR]);
     AZ_ALLOC(e, h->gSendAux, D.gs[AZ_NDIR]); AZ_ALLOC(e, h->gRecvAux, D.gr[AZ_NDIR]);
     AZ_ALLOC(e, h->mSend, D.ms[AZ_NDIR]); AZ_ALLOC(e, h->mRecv, D.mr[AZ_NDIR]);
+    AZ_ALLOC(e, h->blockFlag, e->list_nblocks > 0 ? e->list_nblocks : 1);
+    AZ_CUDA(e, cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
+    AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_ghosts, cudaEventDisableTiming));
     return AZ_OK;
 }
 
@@ -453,11 +467,12 @@ static int dd_rebuild(az_engine* e, int c)
 }
 
 // steps between rebuilds: the ghosts get the current positions (and radii) of their originals
-static int dd_refresh_ghosts(az_engine* e, int c)
+static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream)
 {
     AzDDHost* h = e->dd;
     const AzDD& D = h->D;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = on_halo_stream ? h->halo_stream : e->stream;
+    if (on_halo_stream) AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0)); // recorded by dd_mark_moved
     auto blocks = [](int n) { return (n + AZ_TPB - 1) / AZ_TPB; };
     float2* th = e->use_therm ? e->therm[c] : nullptr;
     Timer t(e, AZ_TIMER_HALO);
@@ -469,12 +484,29 @@ static int dd_refresh_ghosts(az_engine* e, int c)
         dd_add_ops(h, ops2, h->gSendAux, D.gs, h->gRecvAux, D.gr, sizeof(float2));
         ops.insert(ops.end(), ops2.begin(), ops2.end());
     }
-    int rc = dd_exchange(e, ops);
-    if (rc) return rc;
+    int rc = h->comm->exchange(ops, st);
+    if (rc) { e->err = h->comm->err; return rc; }
     AZ_LAUNCH(az_k_ghost_update, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->ghostSlot, h->gRecvPos, h->gRecvAux, e->pos[c], th);
+    if (on_halo_stream) AZ_CUDA(e, cudaEventRecord(h->ev_ghosts, h->halo_stream));
     AZ_COUNT(e, AZ_TIMER_HALO, 2);
     return AZ_OK;
 }
+
+// positions of this step are final (the kick + drift kernel is the last thing on the engine's stream so far)
+static int dd_mark_moved(az_engine* e)
+{
+    AZ_CUDA(e, cudaEventRecord(e->dd->ev_moved, e->stream));
+    return AZ_OK;
+}
+
+static int dd_wait_ghosts(az_engine* e)
+{
+    AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->dd->ev_ghosts, 0));
+    return AZ_OK;
+}
+static bool dd_overlap(const az_engine* e) { return e->dd && e->dd->overlap && e->use_list; }
+static int* dd_block_flags(const az_engine* e) { return e->dd ? e->dd->blockFlag : nullptr; }
+static void dd_set_overlap(az_engine* e, bool on) { if (e->dd) e->dd->overlap = on; }
 
 static int dd_read_counts(az_engine* e, AzDDCounts* out)
 {

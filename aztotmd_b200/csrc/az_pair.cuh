@@ -34,6 +34,9 @@ struct AzPairArgs {
     int* nbr;                // Verlet list, blocked by warp: row k of atom i at nbr[((i >> 5) * nbr_cap + k) * 32 + (i & 31)]
     int* nbrCount;           // LIST build: neighbours of atom i within the list radius
     int nbr_stride, nbr_cap;
+    int* blockFlag;          // bricks: 1 if any atom of this 128-atom block lists a ghost (written by az_k_build_list)
+    int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
+                             // in flight), 2 = blocks with ghosts (after the halo)
     int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
@@ -303,7 +306,11 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
 {
     const AzGrid& g = P.g;
     const int i = blockIdx.x * AZ_LIST_TPB + threadIdx.x;
-    if (i >= az_n_owned(P)) return;
+    const int n_owned = az_n_owned(P);
+    __shared__ int s_ghost; // bricks: does any atom of this block see a ghost?
+    if (A.blockFlag) { if (threadIdx.x == 0) s_ghost = 0; __syncthreads(); }
+    int jmax = -1; // end of the farthest range swept by this thread (ghosts sit behind the owned atoms)
+    if (i < n_owned) {
     const float4 pi = A.pos[i];
     // owned cells are numbered first, z fastest inside the owned block
     const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
@@ -322,6 +329,7 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
 
     // all j of one contiguous range against atom i
     auto sweep = [&](const int rb, const int re, const int code) {
+        jmax = max(jmax, re - 1);
         if (code == 0) {
             const int room = cap - nB;
 #pragma unroll 4
@@ -427,6 +435,12 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
     if (re > rb) sweep(rb, re, rcode);
     if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }
     A.nbrCount[i] = nA | (nB << AZ_NBR_CNT_BITS);
+    }
+    if (A.blockFlag) { // ghosts sit behind the owned atoms in the sorted streams
+        if (jmax >= n_owned) atomicOr(&s_ghost, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) A.blockFlag[blockIdx.x] = s_ghost;
+    }
 }
 
 // az_k_pair_list: the force pass of every step of the list path (the rebuild step's forces come from
@@ -444,6 +458,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         for (int k = tid; k < P.nspec * P.nspec; k += AZ_LIST_TPB) s_tab[k] = A.table[k];
         __syncthreads();
     }
+    if (A.phase && ((A.phase == 1) == (A.blockFlag[blockIdx.x] != 0))) return; // the other phase owns this block
     const int i = blockIdx.x * AZ_LIST_TPB + tid;
     const bool act = i < az_n_owned(P);
     float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;

@@ -90,6 +90,8 @@ def bench_main(args, config):
     n_global = s.n_atoms_global
     e = Engine(s, device=local, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0,
                rank=rank, n_ranks=world, pgrid=pgrid, comm_id=cid)
+    if getattr(args, "no_halo_overlap", False):
+        e.set_option("halo_overlap", 0)
     K, W = args.steps, args.warmup
     e.step(0, W)
     st = e.stats()  # collective; surfaces overflow flags early

@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--pair-variant", type=int, default=0, help="0 auto (Verlet list between rebuilds), 1 cell tiles only")
     ap.add_argument("--list-pipe", type=int, default=-1, help="software-pipeline depth of the list force pass (experiment)")
     ap.add_argument("--list-dbg", type=int, default=0, help="diagnostic variants of the list pass (results are NOT physical)")
+    ap.add_argument("--no-halo-overlap", action="store_true", help="multi-GPU: refresh the ghosts on the engine's stream (A/B of the overlap)")
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
