@@ -379,7 +379,12 @@ static int dd_alloc(az_engine* e)
     AZ_ALLOC(e, h->gSendAux, D.gs[AZ_NDIR]); AZ_ALLOC(e, h->gRecvAux, D.gr[AZ_NDIR]);
     AZ_ALLOC(e, h->mSend, D.ms[AZ_NDIR]); AZ_ALLOC(e, h->mRecv, D.mr[AZ_NDIR]);
     AZ_ALLOC(e, h->blockFlag, e->list_nblocks > 0 ? e->list_nblocks : 1);
-    AZ_CUDA(e, cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    { // highest priority: the halo's small kernels and NCCL's copy kernels take SM slots as soon as blocks of the
+      // (much larger) list kernel retire, instead of queueing behind all of them
+        int lo = 0, hi = 0;
+        AZ_CUDA(e, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        AZ_CUDA(e, cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, hi));
+    }
     AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
     AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_ghosts, cudaEventDisableTiming));
     return AZ_OK;
