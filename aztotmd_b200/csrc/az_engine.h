@@ -38,7 +38,6 @@ struct az_engine {
     bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
     bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
-    int list_pipe = 0; // software-pipeline depth of the list force pass (0, 2, 4 neighbours per stage)
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;
     // device state
@@ -55,7 +54,6 @@ struct az_engine {
     double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
     unsigned long long* partN = nullptr;
     int n_pair_partials = 0;
-    double* stage = nullptr; // unused alias kept for the emulator build
     // az_engine_upload staging: two buffers of 6*n doubles filled on a copy stream, so that the H2D copy of the
     // next upload overlaps the kernels of the current step (az_engine_upload_async)
     double* stage2[2] = { nullptr, nullptr };

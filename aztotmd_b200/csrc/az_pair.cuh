@@ -447,7 +447,7 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
 // it too).  One thread per atom, no atomics, same pair arithmetic and the same r2 <= r2Max gate on
 // current positions as the cell sweep, so the pair set per step is identical to the every-step-rebuild
 // schedule as long as no atom moved more than skin/2 (tracked by az_k_integrate_a / az_k_finalize).
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, int PIPE>
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 __global__ void __launch_bounds__(AZ_LIST_TPB)
 az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
@@ -489,69 +489,22 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         const int* __restrict__ const rows = A.nbr + az_nbr_base(i, A.nbr_cap);
         const int* __restrict__ row = rows;
         int k = 0;
-        if (PIPE == 0) {
-            // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
-            // gathers of chunk k (L1/L2) are consumed
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            const int dbg = A.dbg;
-            auto ldidx = [&](const int* p, int kk) { return dbg == 2 ? max(0, min(az_n_owned(P) - 1, i + kk - (cnt >> 1))) : *p; };
-            auto ldpos = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : __ldg(A.pos + c); };
-            if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
-            for (; k + 4 <= cnt; k += 4) {
-                row += 4 * stride;
-                const float4 p0 = ldpos(c0), p1 = ldpos(c1), p2 = ldpos(c2), p3 = ldpos(c3);
-                float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
-                if (RADII) { r0 = A.therm[c0].y; r1 = A.therm[c1].y; r2_ = A.therm[c2].y; r3 = A.therm[c3].y; }
-                int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-                if (k + 8 <= cnt) { n0 = ldidx(row, k + 4); n1 = ldidx(row + stride, k + 5); n2 = ldidx(row + 2 * stride, k + 6); n3 = ldidx(row + 3 * stride, k + 7); }
-                plain(p0, r0); plain(p1, r1); plain(p2, r2_); plain(p3, r3);
-                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-            }
-        } else {
-            // two-deep pipeline: indices run two chunks ahead of the arithmetic, gathered positions one chunk
-            constexpr int U = PIPE > 0 ? PIPE : 1;
-            const int nfull = cnt / U;
-            int ic[U], in_[U];
-            float4 pc[U];
-            float rc_[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) { ic[u] = 0; in_[u] = 0; pc[u] = make_float4(0.f, 0.f, 0.f, 0.f); rc_[u] = 0.f; }
-            if (nfull > 0) {
-#pragma unroll
-                for (int u = 0; u < U; u++) ic[u] = row[u * stride];
-                row += U * stride;
-            }
-            if (nfull > 1) {
-#pragma unroll
-                for (int u = 0; u < U; u++) in_[u] = row[u * stride];
-                row += U * stride;
-            }
-            if (nfull > 0) {
-#pragma unroll
-                for (int u = 0; u < U; u++) { pc[u] = __ldg(A.pos + ic[u]); if (RADII) rc_[u] = A.therm[ic[u]].y; }
-            }
-            for (int c = 0; c < nfull; c++) {
-                float4 pn[U];
-                float rn[U];
-                int i2[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) { pn[u] = pc[u]; rn[u] = 0.f; i2[u] = 0; }
-                if (c + 1 < nfull) {
-#pragma unroll
-                    for (int u = 0; u < U; u++) { pn[u] = __ldg(A.pos + in_[u]); if (RADII) rn[u] = A.therm[in_[u]].y; }
-                }
-                if (c + 2 < nfull) {
-#pragma unroll
-                    for (int u = 0; u < U; u++) i2[u] = row[u * stride];
-                    row += U * stride;
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) plain(pc[u], rc_[u]);
-#pragma unroll
-                for (int u = 0; u < U; u++) { pc[u] = pn[u]; rc_[u] = rn[u]; in_[u] = i2[u]; }
-            }
-            k = nfull * U;
-            row = rows + k * stride;
+        // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
+        // gathers of chunk k (L1/L2) are consumed
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        const int dbg = A.dbg;
+        auto ldidx = [&](const int* p, int kk) { return dbg == 2 ? max(0, min(az_n_owned(P) - 1, i + kk - (cnt >> 1))) : *p; };
+        auto ldpos = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : __ldg(A.pos + c); };
+        if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
+        for (; k + 4 <= cnt; k += 4) {
+            row += 4 * stride;
+            const float4 p0 = ldpos(c0), p1 = ldpos(c1), p2 = ldpos(c2), p3 = ldpos(c3);
+            float r0 = 0.f, r1 = 0.f, r2_ = 0.f, r3 = 0.f;
+            if (RADII) { r0 = A.therm[c0].y; r1 = A.therm[c1].y; r2_ = A.therm[c2].y; r3 = A.therm[c3].y; }
+            int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            if (k + 8 <= cnt) { n0 = ldidx(row, k + 4); n1 = ldidx(row + stride, k + 5); n2 = ldidx(row + 2 * stride, k + 6); n3 = ldidx(row + 3 * stride, k + 7); }
+            plain(p0, r0); plain(p1, r1); plain(p2, r2_); plain(p3, r3);
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         }
         for (; k < cnt; k++) {
             const int c = *row; row += stride;

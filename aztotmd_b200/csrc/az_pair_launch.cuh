@@ -28,7 +28,7 @@ static int az_pair_go(az_engine* e, const AzPairArgs& A)
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 {
-    AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, 0>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+    AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
 }
 

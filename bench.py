@@ -46,6 +46,8 @@ WORKLOADS = {
     "lj500k": (50, "synthetic fcc LJ argon, 500,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj4k": (10, "synthetic fcc LJ argon, 4,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj32k": (20, "synthetic fcc LJ argon, 32,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    # BASELINE config 3 of the ionic kind: rock-salt NaCl-like melt, Buckingham + real-space Coulomb (DSF), 1 000 000 ions
+    "nacl1m": (-50, "synthetic NaCl-like ionic melt, 1,000,000 ions (50^3 rock-salt cells, a = 5.9 A), Buckingham rc 9 A + DSF Coulomb rc 12 A alpha 0.2, 1200 K"),
     # latency-bound decks of the reference (BASELINE configs 0 and 1), rebuilt synthetically (the shipped files cannot travel)
     "cs1": (0, "case-study-1-like: 40,000 argon atoms, dilute gas in a 1141.5 A box, LJ rc 4.0 A, cell_list 85, radiative thermostat 298 K"),
     "cs2": (0, "case-study-2-like: 4,000 abstract atoms, 35 A box, surk rc 6.0 A + radii, cell_list 2.7, radiative thermostat 500 K"),
@@ -62,6 +64,21 @@ def lj_system(ncell, rebuild, skin, seed=12345, cell_div=1):
     s = System(pos=pos, types=np.zeros(len(pos), dtype=np.int32), box=box, species=[Species("Ar", AR_MASS)],
                timestep=0.001, cell_size=(rc + (skin if rebuild > 1 else 0.0)) / cell_div, temperature=86.6, seed=seed)
     s.set_vdw(0, 0, "lnjs", rc, [AR_EPS, AR_SIGMA])
+    s.vel = s.gauss_velocities(seed)
+    return s
+
+
+def ionic_system(ncell, rebuild, skin, seed=2):
+    from aztotmd_b200 import abi
+    from aztotmd_b200.decks import rocksalt_positions
+    from aztotmd_b200.engine import Species, System
+    pos, types, box = rocksalt_positions((ncell,) * 3, 5.9, jitter=0.05, seed=seed)
+    s = System(pos=pos, types=types.astype(np.int32), box=box, species=[Species("Na", 22.99, 1.0), Species("Cl", 35.45, -1.0)],
+               timestep=0.001, cell_size=12.0 + (skin if rebuild > 1 else 0.0), elec_kind=abi.ELEC_FENNEL, r_real=12.0, alpha=0.2,
+               temperature=1200.0, seed=seed)
+    s.set_vdw(0, 0, "buck", 9.0, [424.097, 0.317, 1.05])
+    s.set_vdw(0, 1, "buck", 9.0, [1256.31, 0.317, 7.00])
+    s.set_vdw(1, 1, "buck", 9.0, [3488.998, 0.317, 72.40])
     s.vel = s.gauss_velocities(seed)
     return s
 
@@ -134,6 +151,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of the same workload (profiles/r1/ncu_traffic.json); null for workloads that were not captured."""
+    p = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    key = "%s/rebuild%d/skin%.2f" % (args.workload, args.rebuild, args.skin if args.rebuild > 1 else 0.0)
+    ent = d.get(key, {}).get(kernel)
+    return ent["dram_bytes_per_launch"] if ent else None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -193,7 +223,6 @@ def main():
     ap.add_argument("--rebuild", type=int, default=10)
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--pair-variant", type=int, default=0, help="0 auto (Verlet list between rebuilds), 1 cell tiles only")
-    ap.add_argument("--list-pipe", type=int, default=-1, help="software-pipeline depth of the list force pass (experiment)")
     ap.add_argument("--list-dbg", type=int, default=0, help="diagnostic variants of the list pass (results are NOT physical)")
     ap.add_argument("--no-halo-overlap", action="store_true", help="multi-GPU: refresh the ghosts on the engine's stream (A/B of the overlap)")
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
@@ -205,7 +234,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncell, desc = WORKLOADS[args.workload]
-    n_atoms = 4 * ncell ** 3 if ncell else (40000 if args.workload == "cs1" else 4000)
+    n_atoms = 4 * ncell ** 3 if ncell > 0 else (8 * (-ncell) ** 3 if ncell < 0 else (40000 if args.workload == "cs1" else 4000))
     config = {"workload": "%s; cell_list = rc%s; rebuild every %d steps; dt = 1 fs; NVE" % (
         desc, " + skin %.2f A" % args.skin if args.rebuild > 1 else "", args.rebuild),
         "n_atoms": n_atoms, "rebuild_every": args.rebuild, "skin": args.skin if args.rebuild > 1 else 0.0,
@@ -239,10 +268,13 @@ def main():
     assert lib.az_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)) == 0
     fp32_peak = tf.value
 
-    s = lj_system(ncell, args.rebuild, args.skin, cell_div=args.cell_div) if ncell else case_study_system(args.workload)
+    if ncell > 0:
+        s = lj_system(ncell, args.rebuild, args.skin, cell_div=args.cell_div)
+    elif ncell < 0:
+        s = ionic_system(-ncell, args.rebuild, args.skin)
+    else:
+        s = case_study_system(args.workload)
     e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0, pair_variant=args.pair_variant)
-    if args.list_pipe >= 0:
-        e.set_option("list_pipe", args.list_pipe)
     if args.list_dbg:
         e.set_option("list_dbg", args.list_dbg)
     K, W = args.steps, args.warmup
@@ -267,7 +299,10 @@ def main():
     pair_ms = tm[dom]["ms"] / max(1, tm[dom]["launches"])
     pair_total_ms = tm["pair"]["ms"] + tm["pair_list"]["ms"]
     rest_ms = (tm["integrate_a"]["ms"] + tm["integrate_b"]["ms"] + tm["scan"]["ms"] + tm["sort"]["ms"]) / K
-    flops_per_launch = FLOP_PER_PAIR * st.n_pairs
+    # algorithmic flop per unique in-range pair: LJ 30; Buckingham + DSF 66 (each transcendental counted as 8);
+    # surk 44 (30 - 9 for LJ's polynomial + sqrt and 4 divisions at ~5 each + 3)
+    flop_per_pair = {"nacl1m": 66.0, "cs2": 44.0}.get(args.workload, FLOP_PER_PAIR)
+    flops_per_launch = flop_per_pair * st.n_pairs
     achieved_tf = flops_per_launch / (pair_ms * 1e-3) / 1e12
     nreb = max(1, math.ceil(K / args.rebuild))
     hbm_bytes_step = n_atoms * ((HBM_BYTES_PER_ATOM_STEP - 32.0) + HBM_BYTES_PER_ATOM_SORT * nreb / K)
@@ -310,9 +345,9 @@ def main():
                    "pipeline": "az_engine_upload_async: H2D of step k+1 overlaps the kernels of step k; every step re-bins (uploaded positions invalidate the cell list)"},
            "gpu_launches": int(launches),
            "roofline": {"bound": "fp32", "kernel": dom_kernel, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                        "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+                        "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(dom_kernel, args),
                         "peak_source": "az_measure_fp32_peak in this run (FFMA chains; effective %.0f MHz x 148 SM x 128 lanes)" % mhz.value,
-                        "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch" % (FLOP_PER_PAIR, st.n_pairs),
+                        "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch" % (flop_per_pair, st.n_pairs),
                         "avg_launch_ms": pair_ms, "launches": tm[dom]["launches"],
                         "share_of_step": tm[dom]["ms"] / ms, "all_pair_kernels_share_of_step": pair_total_ms / ms},
            "roofline_hbm": {"bound": "hbm", "kernels": "integrate_a + scan + sort + integrate_b", "achieved": achieved_gbs,

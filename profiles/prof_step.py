@@ -15,8 +15,6 @@ variant = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 ncell, _ = bench.WORKLOADS[wl]
 s = bench.lj_system(ncell, rebuild, skin)
 e = Engine(s, rebuild_every=rebuild, skin=skin if rebuild > 1 else 0.0, pair_variant=variant)
-if len(sys.argv) > 6:
-    e.set_option("list_pipe", int(sys.argv[6]))
 e.step(0, steps)
 st = e.stats()
 print("ok", wl, steps, st.engKin_d, st.engVdW_d, st.n_pairs, e.launch_count)

@@ -202,6 +202,10 @@ def nacl_system(ncell=(3, 3, 3), a=5.9, rc_vdw=9.0, r_real=9.0, alpha=0.2, elec=
         s.set_vdw(0, 0, "lnjs", rc_vdw, [0.005, 2.5])
         s.set_vdw(0, 1, "buck", rc_vdw, [1256.31, 0.317, 7.00])
         s.set_vdw(1, 1, "bmhs", rc_vdw, [0.25, 3.0, 3.2, 70.0, 140.0])
+    elif kind == "mixed2":  # the remaining analytic forms: elin, einv, bmhs
+        s.set_vdw(0, 0, "elin", rc_vdw, [900.0, 0.33, 0.02])
+        s.set_vdw(0, 1, "einv", rc_vdw, [900.0, 0.33, 1.5])
+        s.set_vdw(1, 1, "bmhs", rc_vdw, [0.25, 3.0, 3.2, 70.0, 140.0])
     if vel:
         s.vel = s.gauss_velocities(seed + 100)
     return s

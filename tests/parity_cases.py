@@ -198,7 +198,7 @@ def case_face_crossings_and_pressure(lib):
     e.close()
 
 
-def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e-5, pipe=0):
+def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e-5):
     """Extension (BASELINE config 3): binning every R steps with a skin gives the same forces and
     energies as binning every step.  variant 0 = Verlet list between rebuilds, 1 = stale cell tiles."""
     e1 = Engine(s, lib=lib)
@@ -206,8 +206,6 @@ def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e
     o = azt.Oracle(s)
     for eng in (e1, e2):
         eng.set_option("energy_every_step", 1)
-    if pipe:
-        e2.set_option("list_pipe", pipe)
     for step in range(nsteps):
         e1.step(step, 1); e2.step(step, 1); o.step(step, 1)
         s1, s2, so = e1.stats(), e2.stats(), o.stats()
@@ -230,12 +228,6 @@ def _rebuild_vs_every_step(lib, s, skin, variant, nsteps=8, thermo=False, tol=1e
 
 def case_rebuild_interval_list(lib):
     _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 0)
-
-
-def case_rebuild_interval_list_pipelined(lib):
-    # the software-pipelined variants of the list force pass (2 and 4 neighbours per stage)
-    _rebuild_vs_every_step(lib, azt.lj_system(ncell=(6, 6, 6), seed=14, cell_size=9.3), 0.8, 0, nsteps=6, pipe=4)
-    _rebuild_vs_every_step(lib, azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6), 0.6, 0, nsteps=6, pipe=2)
 
 
 def case_rebuild_interval_list_wide_stencils(lib):
@@ -435,13 +427,14 @@ ALL_CASES = [
     ("ionic_buck_ewald_real", lambda lib: case_ionic(lib, abi.ELEC_EWALD)),
     ("ionic_buck_nocoul", lambda lib: case_ionic(lib, abi.ELEC_NONE)),
     ("ionic_mixed_table_dsf", lambda lib: case_ionic(lib, abi.ELEC_FENNEL, kind="mixed")),
+    ("ionic_elin_einv_bmh_ewald_real", lambda lib: case_ionic(lib, abi.ELEC_EWALD, kind="mixed2")),
+    ("elin_einv_bmh_nocoul", lambda lib: case_ionic(lib, abi.ELEC_NONE, kind="mixed2")),
     ("ionic_efield_frozen", case_ionic_efield_frozen),
     ("surk_radiative_equil", case_surk_radiative),
     ("lj_radiative", case_lj_radiative),
     ("equilibration_scaling", case_equilibration_scaling),
     ("face_crossings_pressure", case_face_crossings_and_pressure),
     ("rebuild_interval_list", case_rebuild_interval_list),
-    ("rebuild_interval_list_pipelined", case_rebuild_interval_list_pipelined),
     ("rebuild_interval_list_wide_stencils", case_rebuild_interval_list_wide_stencils),
     ("rebuild_interval_stale_tiles", case_rebuild_interval_stale_tiles),
     ("rebuild_interval_list_ionic", case_rebuild_interval_list_ionic),

@@ -123,6 +123,23 @@ def test_buckingham_with_and_without_coulomb_agree():
     assert f0 == pytest.approx(p[0] * math.exp(-r / p[1]) / r / p[1] - 6 * p[2] / r ** 8, rel=1e-5)
 
 
+def test_bmh_elin_einv_known_answers():
+    """The three remaining analytic forms of the table (src/cuVdW.cu:115-136,162-179,200-217) against their formulas."""
+    r = 2.9
+    A, B, sg, Cc, D = 0.25, 3.0, 3.2, 70.0, 140.0  # bmhs: U = A exp[B(s - r)] - C/r^6 - D/r^8
+    f, e, _ = pair(abi.VDW_BMH, [A, B, sg, Cc, D], r, rc=9.0)
+    assert e == pytest.approx(A * math.exp(B * (sg - r)) - Cc / r ** 6 - D / r ** 8, rel=2e-5)
+    assert f == pytest.approx(A * B * math.exp(B * (sg - r)) / r - 6 * Cc / r ** 8 - 8 * D / r ** 10, rel=2e-5)
+    A, ro, Cc = 900.0, 0.33, 0.02                   # elin: U = A exp(-r/ro) + C r
+    f, e, _ = pair(abi.VDW_ELIN, [A, ro, Cc], r, rc=9.0)
+    assert e == pytest.approx(A * math.exp(-r / ro) + Cc * r, rel=2e-5)
+    assert f == pytest.approx(A * math.exp(-r / ro) / r / ro - Cc / r, rel=2e-5)
+    A, ro, Cc = 900.0, 0.33, 1.5                    # einv: U = A exp(-r/ro) - C/r
+    f, e, _ = pair(abi.VDW_EINV, [A, ro, Cc], r, rc=9.0)
+    assert e == pytest.approx(A * math.exp(-r / ro) - Cc / r, rel=2e-5)
+    assert f == pytest.approx(A * math.exp(-r / ro) / r / ro - Cc / r ** 3, rel=2e-5)
+
+
 def test_surk_at_initial_radii():
     # case study 2: surk 6.0 75.0 8.0 1.0 1.0 with a = b = 2.73/4.731 (radii at U = 0)
     a = 2.73 / 4.731
