@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "az_pair_launch.cuh"
@@ -311,7 +312,8 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     e->n_scan_tiles = (nc + AZ_SCAN_TILE - 1) / AZ_SCAN_TILE;
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
     e->n_atom_blocks = (capo + AZ_TPB - 1) / AZ_TPB;
-    AZ_ALLOC(e, e->partKE, e->n_atom_blocks); AZ_ALLOC(e, e->partU, e->n_atom_blocks);
+    e->n_ke_blocks = (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB; // >= n_atom_blocks: the list kernel may host the integrator
+    AZ_ALLOC(e, e->partKE, e->n_ke_blocks); AZ_ALLOC(e, e->partU, e->n_ke_blocks);
     // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
     // Pair path (pair_variant 0 = auto): between rebuilds always the Verlet list.  On the every-step schedule a large
     // system also goes through the list (build + force pass per step: 1.9 ms at 4 M atoms against 3.6 ms for the
@@ -355,6 +357,8 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     // cell tiles only, 2 = list, 3 = warp-per-atom sweep
     e->warp_nblocks = (capo + (AZ_WARP_TPB / 32) - 1) / (AZ_WARP_TPB / 32);
     e->use_warp = !e->use_list && pv != 1;
+    e->fuse_pair = e->use_list && !e->use_therm && !e->P.has_efield;
+    if (e->fuse_pair) { AZ_ALLOC(e, e->pos_alt, capt); AZ_ALLOC(e, e->vel_alt, capt); }
     { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve all pair kernels
       if (e->warp_nblocks > np) np = e->warp_nblocks;
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
@@ -418,7 +422,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     dd_free(e);
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
-    cudaFree(e->frc); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
+    cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
     cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
@@ -530,6 +534,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         e->since_rebuild++;
         if (e->dd) { int rc = dd_overlap(e) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
     }
+    // the integrator rides on the list kernel when the next step's kick may follow this step's forces directly
+    const bool ride = fuse_next && e->fuse_pair && !eq_step;
     const bool split = !rebuild && dd_overlap(e); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
     { // K4: pair forces
         const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
@@ -543,6 +549,14 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.single = e->h_table[0]; A.table = e->table;
         A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg;
         A.blockFlag = dd_block_flags(e);
+        if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
+            const bool rb_next = step_rebuilds(e);
+            A.fuse = 1 + (rb_next ? (e->dd ? AZ_IA_WRAP : AZ_IA_BIN) : AZ_IA_STALE);
+            A.slot_next = 1 - slot;
+            A.vel = e->vel[c]; A.pos_next = e->pos_alt; A.vel_next = e->vel_alt;
+            A.cellOf = e->cellOf; A.slotOf = e->slotOf; A.cellCount = e->cellCount; A.sc = e->sc; A.partKE = e->partKE;
+            e->clear_counts_bytes = (rb_next && !e->dd) ? sizeof(int) * (size_t)(nc + 1) : 0; // clear_clist for the next step's binning
+        }
         int rc;
         if (split) { // blocks that list no ghost run while the halo is in flight, the others once it has landed
             A.phase = 1;
@@ -558,7 +572,18 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
+        if (ride) { // the new positions / velocities are in the alternate buffers: swap roles
+            std::swap(e->pos[c], e->pos_alt);
+            std::swap(e->vel[c], e->vel_alt);
+            e->clear_counts_bytes = 0;
+        }
     }
+    if (ride) {
+        Timer t(e, AZ_TIMER_INTEGRATE_B);
+        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
+                  e->partU, 0, e->partN, e->pos[c], e->sc, e->revArea[0], e->revArea[1], e->revArea[2]);
+        AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1);
+    } else
     { // K5: half kick + KE (+ thermostat) + derived quantities
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         const int drift_mode = rebuild ? 32 : 64;

@@ -46,6 +46,10 @@ struct az_engine {
     cudaEvent_t ev_step[2] = {};
     int cur = 0;
     float4 *pos[2] = { nullptr, nullptr }, *vel[2] = { nullptr, nullptr }, *frc = nullptr;
+    float4 *pos_alt = nullptr, *vel_alt = nullptr; // targets of the integrator that rides on the list kernel (swapped with pos/vel[cur])
+    bool fuse_pair = false;     // the list kernel also integrates (no thermostat, no per-atom radii, no external field)
+    int n_ke_blocks = 0;        // capacity of partKE / partU
+    size_t clear_counts_bytes = 0; // != 0: the list force pass must be preceded by clear_clist (its rider bins the next step)
     int* id[2] = { nullptr, nullptr };
     float2* therm[2] = { nullptr, nullptr };
     int *cellOf = nullptr, *slotOf = nullptr, *cellSorted = nullptr, *keyTmp = nullptr;

@@ -76,6 +76,10 @@ struct AzScalars {
 #define AZ_IA_STALE 0
 #define AZ_IA_BIN 1
 #define AZ_IA_WRAP 2
+// m |v|^2 of verlet_2stage's kinetic-energy sum (src/cuMDfunc.cu:521-599) with the contraction written out, so that
+// every kernel that hosts the second half kick rounds it the same way
+__device__ __forceinline__ float az_ke_term(const float4 v, float m) { return fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x)) * m; }
+
 // per-atom body: returns |v|^2 after the kick; eF receives q * (x . E)
 template <int MODE>
 __device__ __forceinline__ float az_kick_drift(const AzParams& P, int i, int slot, float4& p, float4& v, const float4 f, int* __restrict__ cellOf,
@@ -357,7 +361,7 @@ az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __r
         int t = __float_as_int(pos[i].w);
         float h = P.rMasshdT[t];
         v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
-        ke = (double)((v.x * v.x + v.y * v.y + v.z * v.z) * P.mass[t]);
+        ke = (double)az_ke_term(v, P.mass[t]);
         if (TSTAT) {
             float2 th = therm[i];
             az_tstat_radi_atom(P, step, id[i], t, photons[i], uv, v.x, v.y, v.z, th.x, th.y);
@@ -392,7 +396,7 @@ az_k_integrate_ba(const __grid_constant__ AzParams P, int step, int slot_next, f
         int t = __float_as_int(p.w);
         float h = P.rMasshdT[t];
         v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z); // verlet_2stage of step n
-        ke = (double)((v.x * v.x + v.y * v.y + v.z * v.z) * P.mass[t]);
+        ke = (double)az_ke_term(v, P.mass[t]);
         if (TSTAT) {
             float2 th = therm[i];
             az_tstat_radi_atom(P, step, id[i], t, photons[i], uv, v.x, v.y, v.z, th.x, th.y);
@@ -446,10 +450,21 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 static __global__ void __launch_bounds__(1024)
 az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
-              const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, const float4* __restrict__ pos, AzScalars* __restrict__ sc,
+              const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, const float4* __restrict__ pos, AzScalars* __restrict__ gsc,
               float revAx, float revAy, float revAz)
 {
     __shared__ double sm[4 * 32];
+    // The scalar block is staged in shared memory: the bookkeeping below is ~60 dependent read-modify-writes by one
+    // thread, which cost a global-memory round trip each when done in place (16 us per step) and nothing here.
+    __shared__ AzScalars ssc;
+    AzScalars* sc = &ssc;
+    {
+        const int nw = (int)(sizeof(AzScalars) / sizeof(int));
+        const int* src = reinterpret_cast<const int*>(gsc);
+        int* dst = reinterpret_cast<int*>(&ssc);
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
     double v[4] = { 0, 0, 0, 0 };
     if (mode & 1) for (int k = threadIdx.x; k < nKE; k += blockDim.x) v[0] += partKE[k];
     if (mode & 2) for (int k = threadIdx.x; k < nPair; k += blockDim.x) { v[1] += partV[k]; v[2] += partC[k]; }
@@ -461,7 +476,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, 
         az_block_sum<1>(c, sm);
         if (threadIdx.x == 0) { sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25); sc->nVisits = (unsigned long long)(c[0] + 0.5); }
     }
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x == 0) {
     if (mode & (32 | 64)) { // this step's face crossings join the cumulative momenta (put_periodic, src/cuMDfunc.cu:72-104)
         for (int a = 0; a < 3; a++) {
             sc->posMom[a] += sc->posMomPend[slot][a]; sc->posMomPend[slot][a] = 0.0;
@@ -512,6 +527,14 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, 
         }
         sc->step = step;
         sc->x_first = pos[0].x;
+    }
+    }
+    __syncthreads();
+    {
+        const int nw = (int)(sizeof(AzScalars) / sizeof(int));
+        const int* src = reinterpret_cast<const int*>(&ssc);
+        int* dst = reinterpret_cast<int*>(gsc);
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
     }
 }
 

@@ -34,6 +34,15 @@ struct AzPairArgs {
     int* nbr;                // Verlet list, blocked by warp: row k of atom i at nbr[((i >> 5) * nbr_cap + k) * 32 + (i & 31)]
     int* nbrCount;           // LIST build: neighbours of atom i within the list radius
     int nbr_stride, nbr_cap;
+    // az_k_pair_list with the integrator riding on it (fuse != 0): second half kick of this step, kinetic energy, and the
+    // next step's kick + drift (+ wrap, + bin) applied to atom i right after its force is known; the new position and
+    // velocity go to the alternate buffers (neighbours still read the current ones), forces are never written
+    int fuse;                // 0 = off, else 1 + AZ_IA_* mode of the next step's drift
+    int slot_next;
+    const float4* vel; float4* pos_next; float4* vel_next;
+    int *cellOf, *slotOf, *cellCount;
+    AzScalars* sc;
+    double* partKE;
     int* blockFlag;          // bricks: 1 if any atom of this 128-atom block lists a ghost (written by az_k_build_list)
     int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
                              // in flight), 2 = blocks with ghosts (after the halo)
@@ -461,7 +470,8 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
     if (A.phase && ((A.phase == 1) == (A.blockFlag[blockIdx.x] != 0))) return; // the other phase owns this block
     const int i = blockIdx.x * AZ_LIST_TPB + tid;
     const bool act = i < az_n_owned(P);
-    float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f;
+    float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f, v2 = 0.f;
+    double ke = 0.0;
     int hits = 0, ti = 0;
     if (act) {
         const float4 pi = A.pos[i];
@@ -527,12 +537,34 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
         const float q = P.charge[ti];
-        A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+        const float4 f = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+        if (!A.fuse) A.frc[i] = f;
+        else { // verlet_2stage of this step and verlet_1stage of the next one (az_k_integrate_ba's body)
+            float4 p = pi, v = A.vel[i];
+            const float h = P.rMasshdT[ti];
+            v.x = fmaf(h, f.x, v.x); v.y = fmaf(h, f.y, v.y); v.z = fmaf(h, f.z, v.z);
+            ke = (double)az_ke_term(v, P.mass[ti]);
+            double eF = 0.0;
+            if (A.fuse == 1 + AZ_IA_STALE) v2 = az_kick_drift<AZ_IA_STALE>(P, i, A.slot_next, p, v, f, A.cellOf, A.slotOf, A.cellCount, A.sc, eF);
+            else if (A.fuse == 1 + AZ_IA_BIN) v2 = az_kick_drift<AZ_IA_BIN>(P, i, A.slot_next, p, v, f, A.cellOf, A.slotOf, A.cellCount, A.sc, eF);
+            else v2 = az_kick_drift<AZ_IA_WRAP>(P, i, A.slot_next, p, v, f, A.cellOf, A.slotOf, A.cellCount, A.sc, eF);
+            A.pos_next[i] = p; A.vel_next[i] = v;
+        }
     }
     if (ENERGY) {
         double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
         az_block_sum<3>(vv, s_red);
         if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+    }
+    if (A.fuse) {
+        double kk[1] = { ke };
+        az_block_sum<1>(kk, s_red);
+        if (tid == 0) A.partKE[blockIdx.x] = 0.5 * kk[0];
+        if (A.fuse == 1 + AZ_IA_STALE) { // the fastest atom bounds the drift since the last rebuild
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));
+            if ((tid & 31) == 0 && __float_as_uint(v2) > *(volatile unsigned*)&A.sc->vmax2_bits[A.slot_next]) atomicMax(&A.sc->vmax2_bits[A.slot_next], __float_as_uint(v2));
+        }
     }
 }
 

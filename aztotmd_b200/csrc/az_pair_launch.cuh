@@ -28,6 +28,12 @@ static int az_pair_go(az_engine* e, const AzPairArgs& A)
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 {
+    // the rider of the list kernel bins the next step: clear_clist comes after everything that still reads this
+    // step's counts (the list build just before) and before the kernel that counts again
+    if (e->clear_counts_bytes && A.phase != 2) {
+        cudaError_t err = cudaMemsetAsync(A.cellCount, 0, e->clear_counts_bytes, e->stream);
+        if (err != cudaSuccess) { e->err = std::string("cudaMemsetAsync: ") + cudaGetErrorString(err); return AZ_ERR_CUDA; }
+    }
     AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
 }

@@ -337,7 +337,9 @@ def case_fused_kick_drift_is_bitwise_the_separate_kernels(lib):
     """Inside one az_engine_step call the second half kick of step n and the kick + drift of step n+1 share
     a pass over the atoms; the trajectory must be bitwise the one of single-step calls (separate kernels)."""
     systems = [(azt.lj_system(ncell=(6, 6, 6), seed=31, temperature=800.0), {}),
-               (azt.lj_system(ncell=(6, 6, 6), seed=32, cell_size=9.3), dict(rebuild_every=4, skin=0.8)),
+               (azt.lj_system(ncell=(6, 6, 6), seed=32, cell_size=9.3), dict(rebuild_every=4, skin=0.8)),   # integrator rides on the list kernel
+               (azt.lj_system(ncell=(6, 6, 6), seed=34, temperature=600.0), dict(pair_variant=2)),            # ... and bins the next step
+               (azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6), dict(rebuild_every=3, skin=0.6)),
                (azt.surk_system(n_side=6, n_equil=4, eq_freq=2), {}),
                (azt.lj_system(ncell=(5, 5, 5), seed=33, vel=False, tstat=abi.TSTAT_RADI, temperature=298.0), dict(rebuild_every=3, skin=0.6, _rad=True))]
     for s, kw in systems:
