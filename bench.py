@@ -303,6 +303,9 @@ def main():
     # surk 44 (30 - 9 for LJ's polynomial + sqrt and 4 divisions at ~5 each + 3)
     flop_per_pair = {"nacl1m": 66.0, "cs2": 44.0}.get(args.workload, FLOP_PER_PAIR)
     flops_per_launch = flop_per_pair * st.n_pairs
+    rides = dom == "pair_list" and args.workload not in ("cs1", "cs2")  # thermostat-free: the integrator rides on the list kernel
+    if rides:
+        flops_per_launch += FLOP_PER_ATOM_INTEGRATE * n_atoms
     achieved_tf = flops_per_launch / (pair_ms * 1e-3) / 1e12
     nreb = max(1, math.ceil(K / args.rebuild))
     hbm_bytes_step = n_atoms * ((HBM_BYTES_PER_ATOM_STEP - 32.0) + HBM_BYTES_PER_ATOM_SORT * nreb / K)
@@ -347,7 +350,8 @@ def main():
            "roofline": {"bound": "fp32", "kernel": dom_kernel, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                         "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(dom_kernel, args),
                         "peak_source": "az_measure_fp32_peak in this run (FFMA chains; effective %.0f MHz x 148 SM x 128 lanes)" % mhz.value,
-                        "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch" % (flop_per_pair, st.n_pairs),
+                        "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch%s" % (
+                            flop_per_pair, st.n_pairs, " + %.0f flop per atom of the integrator that rides on the kernel" % FLOP_PER_ATOM_INTEGRATE if rides else ""),
                         "avg_launch_ms": pair_ms, "launches": tm[dom]["launches"],
                         "share_of_step": tm[dom]["ms"] / ms, "all_pair_kernels_share_of_step": pair_total_ms / ms},
            "roofline_hbm": {"bound": "hbm", "kernels": "integrate_a + scan + sort + integrate_b", "achieved": achieved_gbs,
