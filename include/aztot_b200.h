@@ -157,7 +157,7 @@ typedef struct az_cuda_opts {
     int device;          /* CUDA device ordinal                                       */
     int rebuild_every;   /* 0/1 = reference behaviour (bin + sort every step)         */
     float skin;          /* extra cell width when rebuild_every > 1 (Angstrom)        */
-    int use_graph;       /* 1 = capture the steady-state step in a CUDA graph         */
+    int use_graph;       /* reserved (a step is 2-3 launches on one stream; no graph capture yet) */
     int pair_variant;    /* 0 = auto (Verlet list between rebuilds and for large systems, warp-per-atom cell sweep
                             for small systems on the every-step schedule), 1 = shared-memory cell tiles,
                             2 = list (rebuilt every step if rebuild_every <= 1), 3 = warp-per-atom sweep */

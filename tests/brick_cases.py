@@ -172,6 +172,58 @@ def case_brick_layout_errors(lib, devices=None):
     assert ei.value.status == abi.AZ_ERR_INVALID
 
 
+def case_bricks_equilibration_rescale_uses_global_kinetic_energy(lib, devices=None):
+    # temp_scale on bricks: the scale factor comes from the kinetic energy of ALL bricks (one all-reduce of a double)
+    s = azt.lj_system(ncell=(8, 5, 5), seed=71, n_equil=10, eq_freq=2, temperature=150.0)
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=5, devices=devices)
+
+
+def case_bricks_ionic_list_with_rider(lib, devices=None):
+    # two species, DSF Coulomb, Verlet list between rebuilds, several steps per call are exercised by run_bricks' single steps;
+    # here one multi-step call per rank, so that the integrator rides on the list kernel across the halo refresh
+    s = azt.nacl_system(ncell=(8, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6)
+    n = len(s.pos)
+    cid = unique_comm_id(lib)
+    out = [None, None]
+    err = []
+    bar = threading.Barrier(2)
+
+    def work(r):
+        try:
+            e = Engine(s, lib=lib, rank=r, n_ranks=2, pgrid=(2, 1, 1), comm_id=cid, device=(devices[r] if devices else 0), rebuild_every=3, skin=0.6)
+            bar.wait()
+            e.step(0, 7)
+            st = e.stats()
+            out[r] = (e.dump(), e.download(abi.ORDER_SORTED), st)
+            bar.wait()
+            e.close()
+        except Exception as ex:  # noqa: BLE001
+            err.append(ex)
+            bar.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=600) for t in th]
+    real = [x for x in err if not isinstance(x, threading.BrokenBarrierError)]
+    if real:
+        raise real[0]
+    assert not err
+    e1 = Engine(s, lib=lib, rebuild_every=3, skin=0.6)
+    e1.step(0, 7)
+    s1 = e1.stats()
+    frc = np.zeros((n, 3), np.float32)
+    seen = np.zeros(n, np.int32)
+    for d, a, st in out:
+        frc[d["ids"]] = d["frc"]; seen[d["ids"]] += 1
+        sc = max(abs(s1.engVdW_d), abs(s1.engCoul1_d), abs(s1.engKin_d))
+        assert abs(st.engVdW_d - s1.engVdW_d) <= 1e-4 * sc and abs(st.engCoul1_d - s1.engCoul1_d) <= 1e-4 * sc and abs(st.engKin_d - s1.engKin_d) <= 1e-4 * sc
+        assert st.n_pairs == s1.n_pairs
+    assert (seen == 1).all()
+    d1 = azt.sort_by_id(e1.dump())
+    assert np.abs(frc - d1["frc"]).max() <= 2e-4 * np.abs(d1["frc"]).max()
+    e1.close()
+
+
 def slab_share(system, r, n_ranks, pgrid):
     """Distributed input: rank r passes the atoms whose coordinate along the first decomposed axis falls
     in its 1/P slab of the box (NOT the engine's cell-aligned brick: stragglers migrate in the first step)."""
