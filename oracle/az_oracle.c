@@ -596,12 +596,49 @@ void azo_angled_vector(const float *invec, float cos_phi, float theta, float *ou
     for (int a = 0; a < 3; a++) out[a] = v1[a] * cos_phi + sinPhi * (cosTh * v2[a] + sinTh * v3[a]);
 }
 
+/* One atom through the body of tstat_radi9 (src/cuTemp.cu:736-758): adsorb_rand_photon (:484-507) with the unit vector
+ * uv[3 * (rn1 % 3072)], then, if U > 1e-4, radiate_photon3 (:631-685) with the draws rn2, rn3.  Exported so that
+ * tests can feed the same draws to the reference's own source compiled on the CPU (oracle/ref_device_harness.cpp). */
+void azo_tstat_atom(float mass, float pe, uint32_t rn1, uint32_t rn2, uint32_t rn3, const float *uv, float *v, float *U_io)
+{
+    float U = *U_io;
+    { /* adsorb_rand_photon, src/cuTemp.cu:484-507 */
+        float v02 = f3sqr(v);
+        const float *u = &uv[3 * (rn1 % AZ_N_UVECT)];
+        float ermc = pe * REV_LIGHT / mass;
+        v[0] += ermc * u[0]; v[1] += ermc * u[1]; v[2] += ermc * u[2];
+        float v12 = f3sqr(v);
+        U += pe + 0.5f * mass * (v02 - v12);
+    }
+    if ((double)U > 1e-4) { /* radiate_photon3, src/cuTemp.cu:631-685 */
+        float u0 = U;
+        float v02 = f3sqr(v);
+        float v0 = sqrtf(v02);
+        float ph_eng = 0.9f * u0;
+        float ermc = ph_eng * REV_LIGHT / mass;
+        float ermcv0 = ermc / v0;
+        float rv[3];
+        if (!(ermcv0 < 1.f)) { /* fix of the uninitialised vector: anti-parallel to v */
+            if (v0 > 0.f) { rv[0] = -v[0] / v0; rv[1] = -v[1] / v0; rv[2] = -v[2] / v0; }
+            else { const float *u = &uv[3 * (rn1 % AZ_N_UVECT)]; rv[0] = u[0]; rv[1] = u[1]; rv[2] = u[2]; }
+        } else {
+            float cos_phi = (float)(rn2 % 2048u) / 1024.f * (1.f - ermcv0);
+            cos_phi -= 1.f;
+            float theta = (float)(rn3 % 2048u) / 1024.f * NUM_PI;
+            azo_angled_vector(v, cos_phi, theta, rv);
+        }
+        v[0] += ermc * rv[0]; v[1] += ermc * rv[1]; v[2] += ermc * rv[2];
+        float v12 = f3sqr(v);
+        U -= (ph_eng + 0.5f * mass * (v12 - v02));
+    }
+    *U_io = U;
+}
+
 static void tstat_radi(azo_state *s, int step)
 {
     double teng = 0;
     for (int i = 0; i < s->n; i++) {
         int tp = s->type[i];
-        float mass = s->mass[tp];
         float pe = s->photons[i]; /* sorted index, in-order case of src/cuTemp.cu:715-722 */
         uint32_t rn[4];
         philox4x32_10((uint32_t)s->id[i], (uint32_t)step, 0x52414449u /* "RADI" */, 0,
@@ -609,35 +646,7 @@ static void tstat_radi(azo_state *s, int step)
         /* rn[0] is the burnt draw of src/cuTemp.cu:738 */
         float v[3] = { s->vx[i], s->vy[i], s->vz[i] };
         float U = s->eng[i];
-        { /* adsorb_rand_photon, src/cuTemp.cu:484-507 */
-            float v02 = f3sqr(v);
-            const float *u = &s->uv[3 * (rn[1] % AZ_N_UVECT)];
-            float ermc = pe * REV_LIGHT / mass;
-            v[0] += ermc * u[0]; v[1] += ermc * u[1]; v[2] += ermc * u[2];
-            float v12 = f3sqr(v);
-            U += pe + 0.5f * mass * (v02 - v12);
-        }
-        if ((double)U > 1e-4) { /* radiate_photon3, src/cuTemp.cu:631-685 */
-            float u0 = U;
-            float v02 = f3sqr(v);
-            float v0 = sqrtf(v02);
-            float ph_eng = 0.9f * u0;
-            float ermc = ph_eng * REV_LIGHT / mass;
-            float ermcv0 = ermc / v0;
-            float rv[3];
-            if (!(ermcv0 < 1.f)) { /* fix of the uninitialised vector: anti-parallel to v */
-                if (v0 > 0.f) { rv[0] = -v[0] / v0; rv[1] = -v[1] / v0; rv[2] = -v[2] / v0; }
-                else { const float *u = &s->uv[3 * (rn[1] % AZ_N_UVECT)]; rv[0] = u[0]; rv[1] = u[1]; rv[2] = u[2]; }
-            } else {
-                float cos_phi = (float)(rn[2] % 2048u) / 1024.f * (1.f - ermcv0);
-                cos_phi -= 1.f;
-                float theta = (float)(rn[3] % 2048u) / 1024.f * NUM_PI;
-                azo_angled_vector(v, cos_phi, theta, rv);
-            }
-            v[0] += ermc * rv[0]; v[1] += ermc * rv[1]; v[2] += ermc * rv[2];
-            float v12 = f3sqr(v);
-            U -= (ph_eng + 0.5f * mass * (v12 - v02));
-        }
+        azo_tstat_atom(s->mass[tp], pe, rn[1], rn[2], rn[3], s->uv, v, &U);
         s->vx[i] = v[0]; s->vy[i] = v[1]; s->vz[i] = v[2];
         s->eng[i] = U;
         float restrE = U < s->mxEng[tp] ? U : s->mxEng[tp];

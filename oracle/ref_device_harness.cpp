@@ -1,0 +1,110 @@
+// ref_device_harness.cpp -- TEST INFRASTRUCTURE.  The reference's own __device__ functions of the hot path,
+// executed on the CPU: oracle/build_ref_device.sh extracts the function bodies VERBATIM from the reference's .cu
+// files (into a temporary include file, never into the repository) and compiles them here as host code.  This pins
+// the arithmetic that exists only in the reference's CUDA build -- the radius/temperature-dependent pair function and
+// the radiative thermostat -- against the reference's source lines, since the CUDA build itself does not compute on
+// the B200 box.  tests/golden/make_golden_device.py runs this library and commits the vectors.
+//
+//   cu_fe_* / cu_fer_* / surk_pot               src/cuVdW.cu:25-257
+//   direct_coul, real_ewald, fennel             src/cuElec.cu:27-37,94-134
+//   get_angled_vector, rand_uvect,
+//   adsorb_rand_photon, radiate_photon3         src/cuTemp.cu:230-234,395-453,484-507,631-685
+//   float3_sqr, float3_length, ...              src/cuUtils.cu:27-75
+//
+// The only substitution: rnd_xor128 (src/cuUtils.cu:89-105; racy, seeded from uninitialised memory) is replaced by a
+// queue of numbers the caller supplies, so that the same draws can be fed to the oracle.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <cuda_runtime.h> // float3, uint4, make_float3 (host-side vector types only)
+#undef __device__
+#undef __global__
+#undef __host__
+#undef __constant__
+#define __device__
+#define __global__
+#define __host__
+#define __constant__ static
+
+#include "cuStruct.h" // the reference's cudaMD / cudaVdW (oracle/build_ref_device.sh passes -I to its directory)
+
+static const float d_Fcoul_scale = 14.3996f; // src/main.cu:40
+static const float d_sqrtpi = 1.772453f;     // src/main.cu:41
+static const int dnUvect = 3072;             // src/cuTemp.h:6
+
+static unsigned int g_rnd[64];
+static int g_rnd_n = 0, g_rnd_pos = 0;
+unsigned int rnd_xor128(uint4&) { return g_rnd_pos < g_rnd_n ? g_rnd[g_rnd_pos++] : 0u; }
+
+// CUDA's float overloads of the math library used by the extracted bodies
+static inline void sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+
+#include "ref_device_funcs.inc" // verbatim function bodies, generated at build time
+
+extern "C" {
+
+// kind: the reference's vdW type ids (src/vdw.h:15-21); with_r != 0 selects the *_r variant (r known from Coulomb)
+int refdev_vdw(int kind, const float* p, float r2, float r_in, int with_r, float rad1, float rad2, float* f_over_r, float* eng)
+{
+    cudaVdW v;
+    memset(&v, 0, sizeof(v));
+    v.p0 = p[0]; v.p1 = p[1]; v.p2 = p[2]; v.p3 = p[3]; v.p4 = p[4];
+    float e = 0.f, r = r_in, f;
+    switch (kind) {
+    case 1: f = with_r ? cu_fer_lj(r2, r, &v, e) : cu_fe_lj(r2, &v, e); break;
+    case 2: f = with_r ? cu_fer_buck(r2, r, &v, e) : cu_fe_buck(r2, &v, e); break;
+    case 4: f = with_r ? cu_fer_bmh(r2, r, &v, e) : cu_fe_bmh(r2, &v, e); break;
+    case 5: f = with_r ? cu_fer_elin(r2, r, &v, e) : cu_fe_elin(r2, &v, e); break;
+    case 6: f = with_r ? cu_fer_einv(r2, r, &v, e) : cu_fe_einv(r2, &v, e); break;
+    case 7: f = surk_pot(r2, rad1, rad2, &v, e); break;
+    default: return -1;
+    }
+    *f_over_r = f; *eng = e;
+    return 0;
+}
+
+// kind: 1 direct, 2 Ewald real part, 3 Fennell (DSF); returns r through r_out like the reference
+int refdev_coul(int kind, float r2, float chprd, float alpha, float daipi2, float elC1, float elC2, float rElec,
+                float* f_over_r, float* eng, float* r_out)
+{
+    static cudaMD md;
+    md.alpha = alpha; md.daipi2 = daipi2; md.elC1 = elC1; md.elC2 = elC2; md.rElec = rElec;
+    float e = 0.f, r = 0.f, f;
+    switch (kind) {
+    case 1: f = direct_coul(r2, r, chprd, &md, e); break;
+    case 2: f = real_ewald(r2, r, chprd, &md, e); break;
+    case 3: f = fennel(r2, r, chprd, &md, e); break;
+    default: return -1;
+    }
+    *f_over_r = f; *eng = e; *r_out = r;
+    return 0;
+}
+
+void refdev_angled_vector(const float* in, float cos_phi, float theta, float* out)
+{
+    float3 r = get_angled_vector(make_float3(in[0], in[1], in[2]), cos_phi, theta);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+// One atom through the body of tstat_radi9 (src/cuTemp.cu:736-758): absorb a photon of energy pe from the direction
+// uvects[rnd[0] % 3072], then, if U > 1e-4, radiate_photon3 with the draws rnd[1], rnd[2]; radius = A / (B - min(U, mx)).
+void refdev_tstat_atom(float* vel, float* U, float mass, float pe, const unsigned* rnd, const float* uvects /*3072 x 3*/,
+                       float radA, float radB, float mxEng, float* radius)
+{
+    static cudaMD md;
+    static float3 uv[3072];
+    for (int k = 0; k < 3072; k++) uv[k] = make_float3(uvects[3 * k], uvects[3 * k + 1], uvects[3 * k + 2]);
+    md.uvects = uv;
+    g_rnd[0] = rnd[0]; g_rnd[1] = rnd[1]; g_rnd[2] = rnd[2]; g_rnd_n = 3; g_rnd_pos = 0;
+    uint4 st = make_uint4(0, 0, 0, 0);
+    float3 v = make_float3(vel[0], vel[1], vel[2]);
+    float u = *U;
+    adsorb_rand_photon(&v, &u, mass, pe, st, &md, 0);
+    if (u > 1e-4) radiate_photon3(&v, &u, mass, st, &md, 0);
+    vel[0] = v.x; vel[1] = v.y; vel[2] = v.z;
+    *U = u;
+    float restrE = u < mxEng ? u : mxEng;
+    *radius = radA / (radB - restrE);
+}
+
+} // extern "C"

@@ -1,0 +1,117 @@
+"""Generate tests/golden/ref_device_vectors.npz: outputs of the reference's OWN __device__ functions (pair functions of
+src/cuVdW.cu and src/cuElec.cu, get_angled_vector / adsorb_rand_photon / radiate_photon3 of src/cuTemp.cu) executed
+on the CPU by oracle/_ref/libref_device.so (oracle/build_ref_device.sh; needs /root/reference, i.e. this container).
+The vectors pin the arithmetic that exists only in the reference's CUDA build.  Run:  python tests/golden/make_golden_device.py"""
+import ctypes as C
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import azt  # noqa: E402
+from aztotmd_b200.engine import KB, M_SCALE  # noqa: E402
+
+_fp = C.POINTER(C.c_float)
+
+
+def main():
+    subprocess.run(["bash", os.path.join(ROOT, "oracle", "build_ref_device.sh")], check=True)
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_device.so"))
+    lib.refdev_vdw.argtypes = [C.c_int, _fp, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, _fp, _fp]
+    lib.refdev_coul.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp]
+    lib.refdev_angled_vector.argtypes = [_fp, C.c_float, C.c_float, _fp]
+    lib.refdev_tstat_atom.argtypes = [_fp, _fp, C.c_float, C.c_float, C.POINTER(C.c_uint), _fp, C.c_float, C.c_float, C.c_float, _fp]
+    rng = np.random.default_rng(20261018)
+    out = {}
+
+    # ---- van der Waals forms: kind, prepared parameters p0..p4, r^2, radii -> F/r, U (with and without a known r)
+    params = {1: [4 * 0.01006, 3.3952 ** 2, 24 * 0.01006, 0, 0], 2: [1256.31, 0.317, 7.0, 0, 0], 4: [0.25, 3.0, 3.2, 70.0, 140.0],
+              5: [900.0, 0.33, 0.02, 0, 0], 6: [900.0, 0.33, 1.5, 0, 0], 7: [75.0, 8.0, 1.0, 1.0, 0]}
+    rows = []
+    for kind, p in params.items():
+        pp = (C.c_float * 5)(*p)
+        for _ in range(48):
+            r = float(np.float32(rng.uniform(2.2, 9.0) if kind != 7 else rng.uniform(1.0, 6.0)))
+            r2 = float(np.float32(r * r))
+            rad = [float(np.float32(rng.uniform(0.577, 0.603))) for _ in range(2)]
+            for with_r in (0, 1):
+                f, e = C.c_float(), C.c_float()
+                rin = float(np.float32(math.sqrt(r2))) if with_r else 0.0
+                assert lib.refdev_vdw(kind, pp, r2, rin, with_r, rad[0], rad[1], C.byref(f), C.byref(e)) == 0
+                rows.append([kind, with_r, r2, rad[0], rad[1], f.value, e.value] + list(p))
+    out["vdw"] = np.array(rows, dtype=np.float64)
+
+    # ---- real-space Coulomb: kind, r^2, q_i q_j -> F/r, U, r
+    alpha, rc = 0.2, 12.0
+    daipi2 = 2 * alpha / math.sqrt(3.14159265359)
+    c1 = math.erfc(alpha * rc) / rc
+    c2 = math.erfc(alpha * rc) / rc ** 2 + daipi2 * math.exp(-(alpha * rc) ** 2) / rc
+    rows = []
+    for kind in (1, 2, 3):
+        for _ in range(48):
+            r = float(np.float32(rng.uniform(2.0, 12.0)))
+            r2 = float(np.float32(r * r))
+            q = float(rng.choice([-1.0, 1.0, 0.64, -2.0]))
+            f, e, ro = C.c_float(), C.c_float(), C.c_float()
+            assert lib.refdev_coul(kind, r2, q, alpha, daipi2, c1, c2, rc, C.byref(f), C.byref(e), C.byref(ro)) == 0
+            rows.append([kind, r2, q, f.value, e.value, ro.value])
+    out["coul"] = np.array(rows, dtype=np.float64)
+    out["coul_consts"] = np.array([alpha, daipi2, c1, c2, rc], dtype=np.float64)
+
+    # ---- get_angled_vector
+    rows = []
+    for _ in range(64):
+        v = rng.standard_normal(3).astype(np.float32)
+        if rng.random() < 0.15:
+            v[0] = 0.0  # the v1.x == 0 branches
+        cos_phi = float(np.float32(rng.uniform(-1.0, 1.0)))
+        theta = float(np.float32(rng.uniform(0.0, 6.28)))
+        o = (C.c_float * 3)()
+        lib.refdev_angled_vector(v.ctypes.data_as(_fp), cos_phi, theta, o)
+        rows.append(list(v) + [cos_phi, theta] + list(o))
+    out["angled"] = np.array(rows, dtype=np.float64)
+
+    # ---- one atom through the thermostat body
+    ux, uy, uz = (np.zeros(3072) for _ in range(3))
+    ol = azt.oracle_lib()
+    dp = C.POINTER(C.c_double)
+    ol.azo_default_uvects(ux.ctypes.data_as(dp), uy.ctypes.data_as(dp), uz.ctypes.data_as(dp))
+    uv = np.stack([ux, uy, uz], 1).astype(np.float32).copy()
+    mass = float(np.float32(39.9 * M_SCALE))
+    rows = []
+    while len(rows) < 96:
+        v = (rng.standard_normal(3) * 3.0).astype(np.float32)
+        U = float(np.float32(rng.choice([0.0, rng.uniform(0, 0.05), rng.uniform(0.05, 0.3)])))
+        pe = float(np.float32(rng.gamma(5.0, KB * 500.0)))
+        rnd = rng.integers(0, 2 ** 31, size=3).astype(np.uint32)
+        # the reference leaves the radiated direction uninitialised when e/(m c v0) >= 1 (src/cuTemp.cu:663-675): only
+        # vectors on the defined branch are kept
+        vv, UU = v.copy(), np.float32(U)
+        u = uv[int(rnd[0]) % 3072]
+        ermc = np.float32(pe) * np.float32(3.33567e-5) / np.float32(mass)
+        v1 = vv + ermc * u
+        U1 = UU + np.float32(pe) + np.float32(0.5) * np.float32(mass) * (np.float32((vv * vv).sum()) - np.float32((v1 * v1).sum()))
+        if U1 > 1e-4:
+            a = np.float32(0.9) * U1 * np.float32(3.33567e-5) / np.float32(mass)
+            if not a / np.sqrt((v1 * v1).sum()) < 0.98:
+                continue
+        vel = v.copy()
+        Uc = C.c_float(U)
+        rad = C.c_float()
+        lib.refdev_tstat_atom(vel.ctypes.data_as(_fp), C.byref(Uc), mass, pe, rnd.ctypes.data_as(C.POINTER(C.c_uint)),
+                              uv.ctypes.data_as(_fp), 2.73, 4.731, 0.2, C.byref(rad))
+        rows.append(list(v) + [U, pe, float(rnd[0]), float(rnd[1]), float(rnd[2])] + list(vel) + [Uc.value, rad.value])
+    out["tstat"] = np.array(rows, dtype=np.float64)
+    out["tstat_mass"] = np.array([mass])
+    np.savez_compressed(os.path.join(HERE, "ref_device_vectors.npz"), **out)
+    print("wrote ref_device_vectors.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

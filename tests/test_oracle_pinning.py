@@ -226,3 +226,71 @@ def test_case_study_1_has_no_pair_inside_cutoff():
     o = azt.Oracle(s)
     o.forces_only()
     assert o.pairs_in_range() == 0 and o.stats().engVdW_d == 0.0 and not o.dump()["frc"].any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own __device__ functions, executed on the CPU (oracle/ref_device_harness.cpp: bodies cut verbatim from
+# src/cuVdW.cu, src/cuElec.cu, src/cuTemp.cu at build time) -> tests/golden/ref_device_vectors.npz
+# (tests/golden/make_golden_device.py).  These pin the arithmetic that exists only in the CUDA build: surk and the
+# radiative thermostat, plus every other pair function including the *_r variants.
+DEV = os.path.join(GOLD, "ref_device_vectors.npz")
+
+
+def test_oracle_pair_functions_match_reference_device_source():
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    worst = 0.0
+    for row in z["vdw"]:
+        kind, with_r, r2, ra, rb, f_ref, e_ref = int(row[0]), int(row[1]), row[2], row[3], row[4], row[5], row[6]
+        p = (C.c_float * 5)(*row[7:12])
+        ev, ec = C.c_float(), C.c_float()
+        # with_r: the reference takes r from the Coulomb term that ran first (pair_1, src/cuPairs.cu:131-146); a direct
+        # Coulomb term with zero charge product supplies r without adding anything
+        elec = abi.ELEC_DIRECT if with_r else abi.ELEC_NONE
+        f = lib.azo_pair_eval(kind, p, 1e6, elec, 0.0, 0.0, 0.0, 0.0, 1e3, 0.0, r2, 1e6, ra, rb, C.byref(ev), C.byref(ec))
+        if abs(f_ref) <= abi.AZ_MX_FRC:  # force_autocap clamps the total, the device function does not
+            worst = max(worst, abs(f - f_ref) / max(abs(f_ref), 1e-12))
+            assert f == pytest.approx(f_ref, rel=3e-6, abs=1e-12), (kind, with_r, r2)
+        assert ev.value == pytest.approx(e_ref, rel=3e-6, abs=1e-10), (kind, with_r, r2)
+    alpha, daipi2, c1, c2, rc = z["coul_consts"]
+    for kind, r2, q, f_ref, e_ref, r_ref in z["coul"]:
+        ev, ec = C.c_float(), C.c_float()
+        p = (C.c_float * 5)()
+        f = lib.azo_pair_eval(abi.VDW_NONE, p, 0.0, int(kind), alpha, daipi2, c1, c2, rc, q, r2, 1e6, 0.0, 0.0, C.byref(ev), C.byref(ec))
+        assert f == pytest.approx(f_ref, rel=3e-6, abs=1e-9), (kind, r2)
+        assert ec.value == pytest.approx(e_ref, rel=3e-6, abs=2e-7), (kind, r2)
+    assert worst < 3e-6
+
+
+def test_oracle_angled_vector_matches_reference_device_source():
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    for row in z["angled"]:
+        v = (C.c_float * 3)(*row[0:3])
+        o = (C.c_float * 3)()
+        lib.azo_angled_vector(v, C.c_float(row[3]), C.c_float(row[4]), o)
+        assert np.allclose(np.array(o[:]), row[5:8], rtol=2e-5, atol=2e-6), row
+
+
+def test_oracle_thermostat_atom_matches_reference_device_source():
+    """adsorb_rand_photon + radiate_photon3 of the reference's source on the CPU, fed the same three draws."""
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    lib.azo_tstat_atom.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, _fp, _fp, _fp]
+    ux, uy, uz = (np.zeros(3072) for _ in range(3))
+    dp = C.POINTER(C.c_double)
+    lib.azo_default_uvects(ux.ctypes.data_as(dp), uy.ctypes.data_as(dp), uz.ctypes.data_as(dp))
+    uv = np.stack([ux, uy, uz], 1).astype(np.float32).copy()
+    mass = float(z["tstat_mass"][0])
+    radiated = 0
+    for row in z["tstat"]:
+        v = np.array(row[0:3], dtype=np.float32)
+        U = C.c_float(row[3])
+        lib.azo_tstat_atom(mass, row[4], int(row[5]), int(row[6]), int(row[7]), uv.ctypes.data_as(_fp), v.ctypes.data_as(_fp), C.byref(U))
+        vs = max(np.abs(row[8:11]).max(), 1e-6)
+        assert np.abs(v - row[8:11]).max() <= 2e-5 * vs, row
+        assert U.value == pytest.approx(row[11], rel=2e-4, abs=2e-6), row  # U is a difference of two kinetic energies
+        rad = 2.73 / (4.731 - min(U.value, 0.2))
+        assert rad == pytest.approx(row[12], rel=1e-5)
+        radiated += row[3] + row[4] > 1e-3
+    assert radiated > 30  # the radiate_photon3 branch is exercised
