@@ -413,6 +413,16 @@ void azo_default_uvects(double *ux, double *uy, double *uz)
 }
 
 /* ------------------------------------------------------------- stage 1 ---- */
+/* one axis of put_periodic (src/cuMDfunc.cu:35-60): returns the wrapped coordinate, *n = number of box lengths removed */
+float azo_wrap_coord(float x, float L, float revL, int *n)
+{
+    int nx = (int)floor((double)x * (double)revL);
+    x -= (float)((float)nx * L);
+    if (x >= L) x = 0.f;
+    *n = nx;
+    return x;
+}
+
 static void put_periodic(azo_state *s, int i)
 {
     float *c[3] = { &s->x[i], &s->y[i], &s->z[i] };
@@ -420,9 +430,8 @@ static void put_periodic(azo_state *s, int i)
     int t = s->type[i];
     float m = s->mass[t];
     for (int a = 0; a < 3; a++) {
-        int nx = (int)floor((double)*c[a] * (double)s->revL[a]);
-        *c[a] -= (float)((float)nx * s->L[a]);
-        if (*c[a] >= s->L[a]) *c[a] = 0.f;
+        int nx;
+        *c[a] = azo_wrap_coord(*c[a], s->L[a], s->revL[a], &nx);
         if (nx > 0) { s->acPos[t][a]++; s->posMom[a] += (double)(m * v[a]); }
         else if (nx < 0) { s->acNeg[t][a]++; s->negMom[a] += (double)(m * (-v[a])); }
     }

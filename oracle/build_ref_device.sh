@@ -20,6 +20,9 @@ want = {
                  "cu_fe_einv", "cu_fer_einv", "surk_pot"],
     "cuElec.cu": ["direct_coul", "real_ewald", "fennel"],
     "cuTemp.cu": ["rand_uvect", "get_angled_vector", "adsorb_rand_photon", "radiate_photon3"],
+    "cuMDfunc.cu": ["put_periodic"],
+    "cuSort.cu": ["count_cell"],
+    "cuCellList.cu": ["split_cells", "cell_dist_int"],   # host functions of the CUDA build
 }
 def strip_comments(s):  # only to find the braces; the emitted text is the original
     s = re.sub(r"/\*.*?\*/", lambda m: " " * len(m.group(0)), s, flags=re.S)
@@ -32,7 +35,7 @@ for fn, names in want.items():
         for m in re.finditer(r"^__constant__ const float (revLight|Light|revPlank|numPi)[^\n]*\n", src, flags=re.M):
             chunks.append(m.group(0))
     for name in names:
-        m = re.search(r"^__device__\s+[\w\s\*]+?\b%s\s*\(" % re.escape(name), bare, flags=re.M)
+        m = re.search(r"^(?:__device__\s+)?[\w\*]+[\w\s\*]*?\b%s\s*\(" % re.escape(name), bare, flags=re.M)
         if not m:
             raise SystemExit("function %s not found in %s" % (name, fn))
         i = bare.index("{", m.end())

@@ -10,6 +10,9 @@
 //   get_angled_vector, rand_uvect,
 //   adsorb_rand_photon, radiate_photon3         src/cuTemp.cu:230-234,395-453,484-507,631-685
 //   float3_sqr, float3_length, ...              src/cuUtils.cu:27-75
+//   put_periodic                                src/cuMDfunc.cu:35-106
+//   count_cell                                  src/cuSort.cu:114-128
+//   split_cells, cell_dist_int (host code)      src/cuCellList.cu:9-34,98-132
 //
 // The only substitution: rnd_xor128 (src/cuUtils.cu:89-105; racy, seeded from uninitialised memory) is replaced by a
 // queue of numbers the caller supplies, so that the same draws can be fed to the oracle.
@@ -35,6 +38,10 @@ static const int dnUvect = 3072;             // src/cuTemp.h:6
 static unsigned int g_rnd[64];
 static int g_rnd_n = 0, g_rnd_pos = 0;
 unsigned int rnd_xor128(uint4&) { return g_rnd_pos < g_rnd_n ? g_rnd[g_rnd_pos++] : 0u; }
+
+// the serial stand-ins of the device atomics used by put_periodic / count_cell
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
 
 // CUDA's float overloads of the math library used by the extracted bodies
 static inline void sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
@@ -105,6 +112,54 @@ void refdev_tstat_atom(float* vel, float* U, float mass, float pe, const unsigne
     *U = u;
     float restrE = u < mxEng ? u : mxEng;
     *radius = radA / (radB - restrE);
+}
+
+// split_cells with div_type 1 as init_cudaMD calls it (src/cuInit.cu:979)
+void refdev_split_cells(const float* L, float r, int nAt, int* cnum, float* csize, float* crev)
+{
+    static cudaMD md;
+    md.leng = make_float3(L[0], L[1], L[2]);
+    split_cells(1, r, 0, nAt, &md);
+    cnum[0] = md.cNumber.x; cnum[1] = md.cNumber.y; cnum[2] = md.cNumber.z;
+    csize[0] = md.cSize.x; csize[1] = md.cSize.y; csize[2] = md.cSize.z;
+    crev[0] = md.cRevSize.x; crev[1] = md.cRevSize.y; crev[2] = md.cRevSize.z;
+}
+
+int refdev_cell_dist(int xi, int xj, int mx, float csize, float rskip, float* rmin, float* rmax, int* shift)
+{
+    return cell_dist_int(xi, xj, mx, csize, rskip, *rmin, *rmax, *shift);
+}
+
+// put_periodic followed by count_cell for one atom of species 0: wrapped position, cell index, face-crossing counters
+// (pos x,y,z then neg x,y,z) and momenta
+void refdev_wrap_and_bin(float* xyz, const float* vel, float mass, const float* L, const int* cnum, const float* crev,
+                         int* cell, int* crossings, float* mom)
+{
+    static cudaMD md;
+    static int3 acPos[1], acNeg[1];
+    static int cellIdx[1], inside[1];
+    static int counts[1 << 20];
+    md.leng = make_float3(L[0], L[1], L[2]);
+    md.revLeng = make_float3(1.f / L[0], 1.f / L[1], 1.f / L[2]); // src/cuInit.cu:937
+    md.cNumber = make_int3(cnum[0], cnum[1], cnum[2]);
+    md.cRevSize = make_float3(crev[0], crev[1], crev[2]);
+    md.cnYZ = cnum[1] * cnum[2];
+    md.nCell = cnum[0] * cnum[1] * cnum[2];
+    acPos[0] = make_int3(0, 0, 0); acNeg[0] = make_int3(0, 0, 0);
+    md.specAcBoxPos = acPos; md.specAcBoxNeg = acNeg;
+    md.posMom = make_float3(0.f, 0.f, 0.f); md.negMom = make_float3(0.f, 0.f, 0.f);
+    md.cellIndexes = cellIdx; md.insideCellIndex = inside; md.nAtInCell = counts;
+    float3 p = make_float3(xyz[0], xyz[1], xyz[2]);
+    put_periodic(p, make_float3(vel[0], vel[1], vel[2]), mass, 0, &md);
+    xyz[0] = p.x; xyz[1] = p.y; xyz[2] = p.z;
+    cellIdx[0] = -1;
+    const float3 q = p;
+    int c = (int)(floor((double)q.x * (double)md.cRevSize.x) * md.cnYZ + floor((double)q.y * (double)md.cRevSize.y) * md.cNumber.z + floor((double)q.z * (double)md.cRevSize.z));
+    if (c >= 0 && c < md.nCell && md.nCell <= (1 << 20)) { counts[c] = 0; count_cell(0, p, &md); *cell = cellIdx[0]; }
+    else *cell = c; // out of the grid: the reference would write out of bounds; report the raw index
+    crossings[0] = acPos[0].x; crossings[1] = acPos[0].y; crossings[2] = acPos[0].z;
+    crossings[3] = acNeg[0].x; crossings[4] = acNeg[0].y; crossings[5] = acNeg[0].z;
+    mom[0] = md.posMom.x; mom[1] = md.posMom.y; mom[2] = md.posMom.z; mom[3] = md.negMom.x; mom[4] = md.negMom.y; mom[5] = md.negMom.z;
 }
 
 } // extern "C"

@@ -108,6 +108,57 @@ def main():
                               uv.ctypes.data_as(_fp), 2.73, 4.731, 0.2, C.byref(rad))
         rows.append(list(v) + [U, pe, float(rnd[0]), float(rnd[1]), float(rnd[2])] + list(vel) + [Uc.value, rad.value])
     out["tstat"] = np.array(rows, dtype=np.float64)
+
+    # ---- grid geometry (split_cells), cell-pair existence per axis (cell_dist_int), wrap + bin (put_periodic, count_cell)
+    _ip = C.POINTER(C.c_int)
+    lib.refdev_split_cells.argtypes = [_fp, C.c_float, C.c_int, _ip, _fp, _fp]
+    lib.refdev_cell_dist.restype = C.c_int
+    lib.refdev_cell_dist.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp, _fp, _ip]
+    lib.refdev_wrap_and_bin.argtypes = [_fp, _fp, C.c_float, _fp, _ip, _fp, _ip, _ip, _fp]
+    rows = []
+    boxes = [(1141.5, 1141.5, 1141.5, 85.0), (35.0, 35.0, 35.0, 2.7), (570.26, 570.26, 570.26, 8.488), (570.26, 570.26, 570.26, 8.738)]
+    for _ in range(60):
+        boxes.append((float(np.float32(rng.uniform(8, 300))), float(np.float32(rng.uniform(8, 300))), float(np.float32(rng.uniform(8, 300))),
+                      float(np.float32(rng.uniform(2.0, 14.0)))))
+    for lx, ly, lz, r in boxes:
+        if min(lx, ly, lz) < r:
+            continue
+        L = (C.c_float * 3)(lx, ly, lz)
+        cn, cs, cr = (C.c_int * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        lib.refdev_split_cells(L, r, 1000, cn, cs, cr)
+        rows.append([L[0], L[1], L[2], np.float32(r)] + list(cn) + list(cs) + list(cr))
+    out["grid"] = np.array(rows, dtype=np.float64)
+    rows = []
+    for mx in range(1, 10):
+        for csize, rskip in ((3.0, 2.9), (3.0, 3.1), (2.9, 6.0), (2.917, 8.0), (8.8, 8.488)):
+            for xi in range(mx):
+                for xj in range(mx):
+                    rmin, rmax, sh = C.c_float(), C.c_float(), C.c_int()
+                    skip = lib.refdev_cell_dist(xi, xj, mx, csize, rskip, C.byref(rmin), C.byref(rmax), C.byref(sh))
+                    rows.append([mx, csize, rskip, xi, xj, skip, sh.value, rmin.value])
+    out["celldist"] = np.array(rows, dtype=np.float64)
+    rows = []
+    for _ in range(400):
+        lx, ly, lz, r = boxes[int(rng.integers(0, len(boxes)))]
+        if min(lx, ly, lz) < r:
+            continue
+        L = (C.c_float * 3)(lx, ly, lz)
+        cn, cs, cr = (C.c_int * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        lib.refdev_split_cells(L, r, 1000, cn, cs, cr)
+        mode = rng.integers(0, 4)
+        x = np.array([rng.uniform(0, lx), rng.uniform(0, ly), rng.uniform(0, lz)], dtype=np.float32)
+        if mode == 1:   # just outside a face
+            a = int(rng.integers(0, 3)); x[a] = np.float32([lx, ly, lz][a] + rng.uniform(0, 0.5)) if rng.random() < 0.5 else np.float32(-rng.uniform(0, 0.5))
+        elif mode == 2:  # exactly on a cell or box boundary
+            a = int(rng.integers(0, 3)); x[a] = np.float32(cs[a] * int(rng.integers(0, cn[a] + 1)))
+        elif mode == 3:  # one ulp below the upper face
+            a = int(rng.integers(0, 3)); x[a] = np.nextafter(np.float32([lx, ly, lz][a]), np.float32(0))
+        v = rng.standard_normal(3).astype(np.float32)
+        xin = x.copy()
+        cell, cross, mom = C.c_int(), (C.c_int * 6)(), (C.c_float * 6)()
+        lib.refdev_wrap_and_bin(x.ctypes.data_as(_fp), v.ctypes.data_as(_fp), np.float32(0.004135), L, cn, cr, C.byref(cell), cross, mom)
+        rows.append(list(xin) + list(v) + [L[0], L[1], L[2]] + list(cn) + list(cr) + list(x) + [cell.value] + list(cross) + list(mom))
+    out["wrapbin"] = np.array(rows, dtype=np.float64)
     out["tstat_mass"] = np.array([mass])
     np.savez_compressed(os.path.join(HERE, "ref_device_vectors.npz"), **out)
     print("wrote ref_device_vectors.npz:", {k: v.shape for k, v in out.items()})

@@ -294,3 +294,73 @@ def test_oracle_thermostat_atom_matches_reference_device_source():
         assert rad == pytest.approx(row[12], rel=1e-5)
         radiated += row[3] + row[4] > 1e-3
     assert radiated > 30  # the radiate_photon3 branch is exercised
+
+
+def test_oracle_grid_matches_reference_split_cells_bit_exactly():
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    for row in z["grid"]:
+        cn, cs, cr = (C.c_int * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        lib.azo_split_cells(C.c_float(row[0]), C.c_float(row[1]), C.c_float(row[2]), C.c_float(row[3]), cn, cs, cr)
+        assert list(cn) == [int(v) for v in row[4:7]], row
+        assert [np.float32(v) for v in cs] == [np.float32(v) for v in row[7:10]], row      # cSize, bit-exact
+        assert [np.float32(v) for v in cr] == [np.float32(v) for v in row[10:13]], row     # cRevSize, bit-exact
+
+
+def test_oracle_cell_pairs_match_reference_cell_dist_int():
+    """Per axis: the set of (cell, neighbour, image shift) the oracle's stencil walk visits equals the set of ordered cell
+    pairs cell_dist_int (src/cuCellList.cu:98-132) keeps, with the same shift sign."""
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    lib.azo_stencil_half.restype = C.c_int
+    lib.azo_stencil_half.argtypes = [C.c_int, C.c_float, C.c_float]
+    lib.azo_neighbor.restype = C.c_int
+    lib.azo_neighbor.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    groups = {}
+    for mx, csize, rskip, xi, xj, skip, sh, rmin in z["celldist"]:
+        groups.setdefault((int(mx), float(csize), float(rskip)), {})[(int(xi), int(xj))] = (int(skip), int(sh))
+    for (mx, csize, rskip), ref in groups.items():
+        kept_ref = {(xi, xj): sh for (xi, xj), (skip, sh) in ref.items() if not skip}
+        sten = lib.azo_stencil_half(mx, csize, rskip)
+        kept = {}
+        for c in range(mx):
+            for o in range(-sten, sten + 1):
+                cn, sh = C.c_int(), C.c_int()
+                if lib.azo_neighbor(mx, c, o, C.byref(cn), C.byref(sh)):
+                    assert (c, cn.value) not in kept, "a cell pair must exist once"
+                    kept[(c, cn.value)] = sh.value
+        # the reference's shift is +1 when the FIRST cell has the larger coordinate and the pair is wrapped; the stencil
+        # walk reports the image of the neighbour: +1 when the neighbour was reached by stepping past the upper face
+        assert set(kept) == set(kept_ref), (mx, csize, rskip, sorted(set(kept) ^ set(kept_ref)))
+        for k, sh in kept.items():
+            assert sh == kept_ref[k], (mx, csize, rskip, k, sh, kept_ref[k])
+
+
+def test_oracle_wrap_and_bin_match_reference_put_periodic_and_count_cell():
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    lib.azo_wrap_coord.restype = C.c_float
+    lib.azo_wrap_coord.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int)]
+    checked = 0
+    for row in z["wrapbin"]:
+        xin, L, cn, cr = row[0:3], row[6:9], [int(v) for v in row[9:12]], row[12:15]
+        xref, cell_ref, cross = row[15:18], int(row[18]), [int(v) for v in row[19:25]]
+        x, pos_cross, neg_cross = [], [], []
+        for a in range(3):
+            n = C.c_int()
+            revL = np.float32(1.0) / np.float32(L[a])
+            x.append(lib.azo_wrap_coord(C.c_float(xin[a]), C.c_float(L[a]), C.c_float(revL), C.byref(n)))
+            pos_cross.append(1 if n.value > 0 else 0)
+            neg_cross.append(1 if n.value < 0 else 0)
+        assert [np.float32(v) for v in x] == [np.float32(v) for v in xref], row   # wrapped coordinates, bit-exact
+        assert pos_cross + neg_cross == cross
+        ncell = cn[0] * cn[1] * cn[2]
+        if 0 <= cell_ref < ncell:  # inside the grid the clamp of the oracle is inactive: indices must be equal
+            crev = (C.c_float * 3)(*cr)
+            cnum = (C.c_int * 3)(*cn)
+            c = lib.azo_cell_index(C.c_float(x[0]), C.c_float(x[1]), C.c_float(x[2]), crev, cnum)
+            per_axis_ok = all(0 <= int(np.floor(np.float64(np.float32(x[a])) * np.float64(np.float32(cr[a])))) < cn[a] for a in range(3))
+            if per_axis_ok:
+                assert c == cell_ref, row
+                checked += 1
+    assert checked > 300
