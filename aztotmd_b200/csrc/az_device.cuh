@@ -77,7 +77,7 @@ __device__ __forceinline__ int az_n_owned(const AzParams& P) { return P.n_dyn ? 
 #define AZ_NUM_PI 3.14159f       // numPi, src/cuTemp.cu:228
 
 // ---------------------------------------------------------------------------------------
-// Philox4x32-10, identical to oracle/az_oracle.c
+// Philox4x32-10 (Salmon et al. 2011); the CPU checker restates the same rounds
 __device__ __forceinline__ void az_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                           uint32_t k0, uint32_t k1, uint32_t out[4])
 {
