@@ -62,6 +62,7 @@ class az_system_desc(C.Structure):
         ("timestep", C.c_double), ("n_equil", C.c_int), ("eq_freq", C.c_int),
         ("r2_max", C.c_double), ("cell_size", C.c_double), ("efield", C.c_double * 3),
         ("global_ids", _ip), ("n_atoms_global", C.c_longlong),
+        ("tstat_tau", C.c_double), ("reset_vels", C.c_int), ("reserved3", C.c_int),
     ]
 
 

@@ -14,7 +14,7 @@
 // The scan semantics are the reference's: every directive is looked up by rewinding the file and
 // trying fscanf(template) at each whitespace-separated token, first match wins, unknown words are
 // comments.  Directives outside the hot path (bonds, angles, linkage, eJump, red-ox chemistry,
-// Nose-Hoover, reciprocal Ewald) are rejected with AZ_ERR_UNSUPPORTED instead of being silently
+// reciprocal Ewald) are rejected with AZ_ERR_UNSUPPORTED instead of being silently
 // dropped.  Random draws (photon energies, Gaussian velocities) come from a seeded counter-based
 // generator, not from the time-seeded rand() of src/main.cu:242 -- extra keys: `seed N` in
 // control.txt; `rebuild N`, `skin X`, `device N` in cuda.txt (the reference ignores unknown words).
@@ -237,14 +237,17 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     Rng rng(deck_seed);
 
     // thermostat (read_tstat)
-    double temp = 0.0;
+    double temp = 0.0, tstat_tau = 0.0;
     int tstat_kind = AZ_TSTAT_NONE;
     if (!scan_first(f, " temperature %lf ", &temp)) DECK_FAIL(AZ_ERR_IO, "ERROR[404]: temperature is not defined in control.txt file!");
     {
         char ts[64] = "";
         if (fscanf(f, "%63s", ts) != 1) DECK_FAIL(AZ_ERR_IO, "ERROR[405]: unknown thermostat type!");
         if (!strcmp(ts, "none")) tstat_kind = AZ_TSTAT_NONE;
-        else if (!strcmp(ts, "nose")) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'temperature ... nose': the Nose-Hoover thermostat is outside the hot path (SURVEY 8f)");
+        else if (!strcmp(ts, "nose")) { // read_tstat, src/temperature.cpp:104-110
+            if (fscanf(f, " %lf ", &tstat_tau) != 1 || !(tstat_tau > 0.0)) DECK_FAIL(AZ_ERR_IO, "'temperature ... nose': the relaxation time tau is missing");
+            tstat_kind = AZ_TSTAT_NOSE;
+        }
         else if (!strcmp(ts, "radi")) {
             if (fscanf(f, "%d", &d->tstat_step) != 1) DECK_FAIL(AZ_ERR_IO, "ERROR[a002]: there is no step parameter for radiative thermostat!");
             tstat_kind = AZ_TSTAT_RADI;
@@ -302,7 +305,8 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     double U[3] = { 0, 0, 0 };
     if (scan_first(f, " elecfield %lf ", &U[0])) { if (fscanf(f, " %lf %lf ", &U[1], &U[2]) != 2) { U[1] = U[2] = 0.0; } }
     else U[0] = 0.0;
-    if (scan_number(f, " reset_vels %d ") != 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'reset_vels' is outside the hot path (SURVEY 8f)");
+    const int reset_vels = scan_number(f, " reset_vels %d "); // src/sys_init.cpp:857
+    if (reset_vels < 0) DECK_FAIL(AZ_ERR_IO, "'reset_vels' must not be negative");
     { int mn; if (scan_first(f, " max_neigh %d ", &mn) && mn > 0) d->opts.max_neigh = mn; } // rows of the Verlet list per atom
     double cell_size = 0.0;
     if (!scan_first(f, " cell_list %lf ", &cell_size)) DECK_FAIL(AZ_ERR_IO, "'cell_list' is required by the CUDA path (desired_cell_size, src/cuInit.cu:979)");
@@ -389,6 +393,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
         s.el_c2 = erfc(aRc) / (rReal * rReal) + s.daipi2 * exp(-aRc * aRc) / rReal;
     }
     s.tstat_kind = tstat_kind; s.temperature = temp; s.t_kin = tKin;
+    s.tstat_tau = tstat_tau; s.reset_vels = reset_vels;
     s.photons = d->photons.empty() ? nullptr : d->photons.data();
     s.seed = deck_seed;
     s.timestep = tSt; s.n_equil = nEq; s.eq_freq = freqEq;

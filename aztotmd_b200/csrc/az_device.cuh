@@ -65,6 +65,7 @@ struct AzParams {
     // thermostat
     int tstat;
     float teKin;
+    float rQmass, qMassTau2; // Nose-Hoover: 1 / (2 tKin tau^2), 2 tKin (src/sys_init.cpp:1107-1111)
     uint32_t seed_lo, seed_hi;
     AzGrid g;
 };

@@ -167,6 +167,11 @@ static int build_params(az_engine* e, const az_system_desc* d, const az_cuda_opt
     }
     P.tstat = d->tstat_kind;
     P.teKin = (float)d->t_kin;
+    if (P.tstat == AZ_TSTAT_NOSE) { // src/sys_init.cpp:1107-1111, narrowed like init_cuda_tstat (src/cuTemp.cu:20-23)
+        P.rQmass = (float)(0.5 / d->t_kin / d->tstat_tau / d->tstat_tau);
+        P.qMassTau2 = (float)(2.0 * d->t_kin);
+    }
+    e->reset_vels = d->reset_vels;
     P.seed_lo = (uint32_t)d->seed; P.seed_hi = (uint32_t)(d->seed >> 32);
 
     // cell grid (split_cells) and stencil
@@ -249,8 +254,10 @@ extern "C" int az_engine_create(const az_system_desc* d, const az_cuda_opts* o, 
     if (d->abi_version != AZ_ABI_VERSION) { AZ_SET_ERR((az_engine*)0, "abi_version %d != %d", d->abi_version, AZ_ABI_VERSION); return AZ_ERR_INVALID; }
     if (d->n_atoms <= 0 || d->n_species <= 0 || d->n_species > AZ_MAX_SPECIES) { AZ_SET_ERR((az_engine*)0, "bad n_atoms/n_species"); return AZ_ERR_INVALID; }
     if (!d->xs || !d->ys || !d->zs || !d->types || !d->species || !d->vdw) { AZ_SET_ERR((az_engine*)0, "missing atom/species/vdw arrays"); return AZ_ERR_INVALID; }
-    if (d->tstat_kind == AZ_TSTAT_NOSE) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat is outside the hot path (SURVEY 8f)"); return AZ_ERR_UNSUPPORTED; }
-    if (d->tstat_kind != AZ_TSTAT_NONE && d->tstat_kind != AZ_TSTAT_RADI) { AZ_SET_ERR((az_engine*)0, "unknown thermostat kind"); return AZ_ERR_INVALID; }
+    if (d->tstat_kind == AZ_TSTAT_NOSE && !(d->tstat_tau > 0.0 && d->t_kin > 0.0)) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat needs tstat_tau > 0 and t_kin > 0"); return AZ_ERR_INVALID; }
+    if (d->tstat_kind == AZ_TSTAT_NOSE && o && o->n_ranks > 1) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat on bricks is not implemented (its friction needs the global kinetic energy twice per step)"); return AZ_ERR_UNSUPPORTED; }
+    if (d->reset_vels < 0) { AZ_SET_ERR((az_engine*)0, "reset_vels < 0"); return AZ_ERR_INVALID; }
+    if (d->tstat_kind < AZ_TSTAT_NONE || d->tstat_kind > AZ_TSTAT_RADI) { AZ_SET_ERR((az_engine*)0, "unknown thermostat kind"); return AZ_ERR_INVALID; }
     if (d->tstat_kind == AZ_TSTAT_RADI && !d->photons) { AZ_SET_ERR((az_engine*)0, "radiative thermostat needs photon energies"); return AZ_ERR_INVALID; }
     for (int i = 0; i < d->n_atoms; i++)
         if (d->types[i] < 0 || d->types[i] >= d->n_species) { AZ_SET_ERR((az_engine*)0, "atom %d has type %d", i, d->types[i]); return AZ_ERR_INVALID; }
@@ -490,6 +497,13 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const int n_pp = e->use_list ? e->list_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks); // live pair partials this step
     const int slot = (int)(e->steps_done & 1);
 
+    const bool nose = (P.tstat == AZ_TSTAT_NOSE);
+    if (nose) { // first application of the step, before verlet_1stage (src/main.cu:291-299)
+        Timer t(e, AZ_TIMER_INTEGRATE_A);
+        AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+        AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
+        AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 2);
+    }
     if (!skip_a) { // K1: half kick + drift (+ wrap + bin)
         Timer t(e, AZ_TIMER_INTEGRATE_A);
         if (P.has_efield) { AZ_LAUNCH(az_k_reset_step, 1, 1, 0, st, e->sc); AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 1); }
@@ -588,6 +602,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         const int drift_mode = rebuild ? 32 : 64;
         const int emode = want_energy ? 2 : 0;
+        const bool reset_now = e->reset_vels > 0 && step % e->reset_vels == 0;
         float2* th = radi ? e->therm[c] : nullptr;
         const float* ph = radi ? e->photons : nullptr;
         const float* uv = radi ? e->uv : nullptr;
@@ -604,22 +619,41 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
                     if (radi) AZ_BA(true, AZ_IA_BIN); else AZ_BA(false, AZ_IA_BIN);
                 } else { if (radi) AZ_BA(true, AZ_IA_STALE); else AZ_BA(false, AZ_IA_STALE); }
 #undef AZ_BA
+            } else if (reset_now) { // zero_vel instead of verlet_2stage (src/main.cu:372-374); apply_tstat still runs the thermostat
+                AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
+                if (radi) { AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 0); AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1); }
             } else if (radi) {
                 AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
             } else {
                 AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
             }
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | (radi ? 4 : 0) | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            const int radi_mode = radi ? 4 : 0;
+            if (nose) { // second application of the step (apply_tstat): needs this step's kinetic energy, then the quantities
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                          e->revArea[0], e->revArea[1], e->revArea[2]);
+                AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+                AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                          e->revArea[0], e->revArea[1], e->revArea[2]);
+                AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 3);
+            } else
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | radi_mode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
-            AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+            if (reset_now) AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
+            else AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
             AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (e->dd) { int rc = dd_global_tscale(e); if (rc) return rc; }
-            if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU);
-            else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU);
+            if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 1);
+            else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU, 1);
+            if (nose) { // apply_tstat: the rescale comes first, then the thermostat (src/cuTemp.cu:777-794)
+                AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+                AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
+                AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
+            }
             AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
@@ -643,7 +677,7 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         // kick and drift of step n+1) unless something must happen in between: an equilibration rescale, or the
         // external field's per-step energy reset.  The last step of the call ends on a plain second half kick,
         // so downloads and statistics always see the state "after step n".
-        const bool fuse = e->fuse_integrate && k + 1 < nsteps && !is_eq_step(e, step) && !e->P.has_efield;
+        const bool fuse = e->fuse_integrate && k + 1 < nsteps && !is_eq_step(e, step) && !e->P.has_efield && e->P.tstat != AZ_TSTAT_NOSE && e->reset_vels == 0;
         // potential energies are reduced on the last step of the call (the one az_engine_stats reports)
         int rc = one_step(e, step, e->energy_every_step || k == nsteps - 1, a_done, fuse);
         if (rc) return rc;

@@ -17,7 +17,7 @@ struct az_engine {
     int rank = 0, n_ranks = 1;
     AzParams P;
     float revArea[3] = { 0, 0, 0 };
-    int n_eq = 0, eq_freq = 0;
+    int n_eq = 0, eq_freq = 0, reset_vels = 0;
     int rebuild_every = 1, since_rebuild = 0;
     bool binned = false, use_therm = false, energy_every_step = false, energy_valid = false;
     int profile = 0; // 0 off, 1 synchronous sections, 2 recorded events resolved later

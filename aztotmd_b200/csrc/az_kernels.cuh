@@ -56,6 +56,7 @@ struct AzScalars {
     int overflow, dbg_count, dbg_atom; // sticky error flags (+ worst list row count and the atom it belongs to)
     // flags:: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots, 16 neighbour-list rows
     float tscale_k;
+    float chit, consInt, nose_scale; // Nose-Hoover friction, conserved-quantity integral, velocity factor of the block in flight
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
     unsigned long long nVisits; // the same, counted from both sides (a brick sees cross-brick pairs from one side only)
@@ -419,11 +420,11 @@ __global__ void __launch_bounds__(AZ_TPB)
 az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restrict__ pos,
             float4* __restrict__ vel, const int* __restrict__ id, float2* __restrict__ therm,
             const float* __restrict__ photons, const float* __restrict__ uv,
-            const AzScalars* __restrict__ sc, double* __restrict__ partU)
+            const AzScalars* __restrict__ sc, double* __restrict__ partU, int use_k)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ut = 0.0;
-    float k = sc->tscale_k;
+    float k = use_k ? sc->tscale_k : 1.f; // use_k == 0: thermostat only (a 'reset_vels' step: zero_vel, then apply_tstat)
     if (i < az_n_owned(P)) {
         float4 v = vel[i];
         v.x *= k; v.y *= k; v.z *= k;
@@ -554,6 +555,36 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, 
         int* dst = reinterpret_cast<int*>(gsc);
         for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
     }
+}
+
+// Nose-Hoover (src/cuTemp.cu:115-163): before_nose and after_nose(1) are pure scalar recurrences, so both run in one
+// thread BEFORE the velocities are touched; az_k_vscale then applies md->tscale like tstat_nose.
+static __global__ void az_k_nose_scalars(const __grid_constant__ AzParams P, AzScalars* __restrict__ sc)
+{
+    float chit = sc->chit, ke = sc->engKin_f;
+    chit += P.tSt * (ke - P.teKin) * P.rQmass;             // before_nose
+    const float ts = 1.f - P.tSt * chit;
+    ke = ke * ts * ts;                                     // after_nose(refresh_kin = 1)
+    sc->consInt += P.tSt * chit * P.qMassTau2;
+    chit += P.tSt * (ke - P.teKin) * P.rQmass;
+    sc->chit = chit; sc->nose_scale = ts; sc->engKin_f = ke; sc->engKin = (double)ke;
+}
+
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_vscale(const __grid_constant__ AzParams P, float4* __restrict__ vel, const AzScalars* __restrict__ sc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float k = sc->nose_scale;
+    if (i < az_n_owned(P)) { float4 v = vel[i]; v.x *= k; v.y *= k; v.z *= k; vel[i] = v; }
+}
+
+// zero_vel (src/cuMDfunc.cu:602-622): 'reset_vels' steps replace the second half kick; the kinetic energy becomes 0
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_zero_vel(const __grid_constant__ AzParams P, float4* __restrict__ vel, double* __restrict__ partKE)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < az_n_owned(P)) vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) partKE[blockIdx.x] = 0.0;
 }
 
 static __global__ void az_k_reset_step(AzScalars* sc) { sc->engElecField = 0.0; } // reset_quantities

@@ -80,6 +80,8 @@ class System:
     # domain decomposition, distributed input: this rank's share of the system with its persistent ids
     global_ids: Optional[np.ndarray] = None
     n_atoms_global: int = 0
+    tstat_tau: float = 0.0   # Nose-Hoover relaxation time, ps ('temperature T nose tau')
+    reset_vels: int = 0      # every n-th step: zero the velocities instead of the second half kick
 
     def set_vdw(self, i: int, j: int, kind: str, rcut: float, params: Sequence[float]):
         e = prepare_vdw(kind, rcut, params)
@@ -227,6 +229,8 @@ class DescHolder:
             self.keep.append(gi)
             d.global_ids = gi.ctypes.data_as(C.POINTER(C.c_int))
         d.n_atoms_global = int(s.n_atoms_global)
+        d.tstat_tau = float(s.tstat_tau)
+        d.reset_vels = int(s.reset_vels)
         self.desc = d
 
 

@@ -77,7 +77,7 @@ typedef enum az_elec_kind {
 /* thermostat kinds: values are tpTerm* of src/dataStruct.h */
 typedef enum az_tstat_kind {
     AZ_TSTAT_NONE = 0,
-    AZ_TSTAT_NOSE = 1, /* not on the hot path yet -> AZ_ERR_UNSUPPORTED */
+    AZ_TSTAT_NOSE = 1, /* before_nose / tstat_nose / after_nose  src/cuTemp.cu:115-163 (applied twice per step, src/main.cu:291-299 and apply_tstat) */
     AZ_TSTAT_RADI = 2  /* tstat_radi9  src/cuTemp.cu:689-773 */
 } az_tstat_kind;
 
@@ -150,6 +150,10 @@ typedef struct az_system_desc {
      * atoms within one brick of its own) with these persistent ids; t_kin is the global value. */
     const int *global_ids;
     long long n_atoms_global;  /* 0 = n_atoms */
+    /* Nose-Hoover thermostat (src/cuTemp.cu:115-163, host prep src/sys_init.cpp:1107-1111) and 'reset_vels' */
+    double tstat_tau;          /* TStat::tau ('temperature T nose tau'); rQmass = 0.5 / tKin / tau^2, qMassTau2 = 2 tKin */
+    int reset_vels;            /* Sim::reset_vels: every n-th step velocities are zeroed instead of the 2nd half kick (src/main.cu:372-377) */
+    int reserved3;
 } az_system_desc;
 
 /* cuda.txt-level options plus the multi-GPU layout.  Zero-initialise for defaults. */

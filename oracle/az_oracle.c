@@ -273,6 +273,8 @@ typedef struct azo_state {
     float r2max;
     int nEq, freqEq;
     int tstat; float teKin;
+    float rQmass, qMassTau2, chit, consInt; /* Nose-Hoover (init_cuda_tstat, src/cuTemp.cu:17-24) */
+    int reset_vels;
     uint64_t seed;
     /* species */
     float mass[AZ_MAX_SPECIES], charge[AZ_MAX_SPECIES], rMasshdT[AZ_MAX_SPECIES];
@@ -322,6 +324,12 @@ azo_state *azo_create(const az_system_desc *d)
     s->r2max = (float)d->r2_max;
     s->nEq = d->n_equil; s->freqEq = d->eq_freq;
     s->tstat = d->tstat_kind; s->teKin = (float)d->t_kin;
+    if (s->tstat == AZ_TSTAT_NOSE) { /* src/sys_init.cpp:1107-1111, narrowed like src/cuTemp.cu:20-23 */
+        s->rQmass = (float)(0.5 / d->t_kin / d->tstat_tau / d->tstat_tau);
+        s->qMassTau2 = (float)(2.0 * d->t_kin);
+        s->chit = 0.f; s->consInt = 0.f;
+    }
+    s->reset_vels = d->reset_vels;
     s->seed = d->seed;
     for (int i = 0; i < s->nspec; i++) {
         s->mass[i] = (float)d->species[i].mass;
@@ -665,6 +673,27 @@ static void tstat_radi(azo_state *s, int step)
     s->engTemp += teng;
 }
 
+/* before_nose + tstat_nose + after_nose(1) (src/cuTemp.cu:115-163): the Nose-Hoover friction is advanced with the
+ * current kinetic energy, velocities are scaled, the kinetic energy follows the scaling and the friction is advanced
+ * again with the new kinetic energy.  The reference's main applies this block twice per step: before verlet_1stage
+ * (src/main.cu:291-299) and inside apply_tstat (src/cuTemp.cu:787-794). */
+void azo_nose_scalars(float tSt, float teKin, float rQmass, float qMassTau2, float *engKin, float *chit, float *consInt, float *tscale)
+{
+    *chit += tSt * (*engKin - teKin) * rQmass;          /* before_nose */
+    *tscale = 1.f - tSt * *chit;
+    *engKin = *engKin * *tscale * *tscale;              /* after_nose(refresh_kin = 1) */
+    *consInt += tSt * *chit * qMassTau2;
+    *chit += tSt * (*engKin - teKin) * rQmass;
+}
+
+static void nose(azo_state *s)
+{
+    float ts;
+    azo_nose_scalars(s->tSt, s->teKin, s->rQmass, s->qMassTau2, &s->engKin_f, &s->chit, &s->consInt, &ts);
+    for (int i = 0; i < s->n; i++) { s->vx[i] *= ts; s->vy[i] *= ts; s->vz[i] *= ts; }
+    s->engKin = (double)s->engKin_f;
+}
+
 static void apply_tstat(azo_state *s, int step)
 {
     if (s->nEq && step <= s->nEq && s->freqEq > 0 && (step % s->freqEq) == 0) {
@@ -677,6 +706,7 @@ static void apply_tstat(azo_state *s, int step)
         s->engKin = (double)s->teKin;
     }
     if (s->tstat == AZ_TSTAT_RADI) tstat_radi(s, step);
+    if (s->tstat == AZ_TSTAT_NOSE) nose(s);
 }
 
 /* calc_quantities, src/main.cu:121-162 */
@@ -710,9 +740,14 @@ int azo_step(azo_state *s, int first_step, int nsteps)
     for (int k = 0; k < nsteps; k++) {
         int step = first_step + k;
         s->engCoul1 = 0; s->engVdW = 0; s->engTemp = 0; s->engElecField = 0; /* reset_quantities */
+        if (s->tstat == AZ_TSTAT_NOSE) nose(s);           /* src/main.cu:291-299 */
         stage1(s);
         sort_atoms(s);
         forces(s);
+        if (s->reset_vels && step % s->reset_vels == 0) { /* zero_vel, src/main.cu:372-374, src/cuMDfunc.cu:602-622 */
+            for (int i = 0; i < s->n; i++) { s->vx[i] = 0.f; s->vy[i] = 0.f; s->vz[i] = 0.f; }
+            s->engKin = 0.0; s->engKin_f = 0.f;
+        } else
         stage2(s);
         apply_tstat(s, step);
         calc_quantities(s, step);

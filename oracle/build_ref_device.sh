@@ -19,7 +19,7 @@ want = {
     "cuVdW.cu": ["cu_fe_lj", "cu_fer_lj", "cu_fe_buck", "cu_fer_buck", "cu_fe_bmh", "cu_fer_bmh", "cu_fe_elin", "cu_fer_elin",
                  "cu_fe_einv", "cu_fer_einv", "surk_pot"],
     "cuElec.cu": ["direct_coul", "real_ewald", "fennel"],
-    "cuTemp.cu": ["rand_uvect", "get_angled_vector", "adsorb_rand_photon", "radiate_photon3"],
+    "cuTemp.cu": ["rand_uvect", "get_angled_vector", "adsorb_rand_photon", "radiate_photon3", "before_nose", "after_nose"],
     "cuMDfunc.cu": ["put_periodic"],
     "cuSort.cu": ["count_cell"],
     "cuCellList.cu": ["split_cells", "cell_dist_int"],   # host functions of the CUDA build
@@ -35,7 +35,7 @@ for fn, names in want.items():
         for m in re.finditer(r"^__constant__ const float (revLight|Light|revPlank|numPi)[^\n]*\n", src, flags=re.M):
             chunks.append(m.group(0))
     for name in names:
-        m = re.search(r"^(?:__device__\s+)?[\w\*]+[\w\s\*]*?\b%s\s*\(" % re.escape(name), bare, flags=re.M)
+        m = re.search(r"^(?:__device__\s+|__global__\s+)?[\w\*]+[\w\s\*]*?\b%s\s*\(" % re.escape(name), bare, flags=re.M)
         if not m:
             raise SystemExit("function %s not found in %s" % (name, fn))
         i = bare.index("{", m.end())

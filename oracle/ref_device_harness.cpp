@@ -9,6 +9,7 @@
 //   direct_coul, real_ewald, fennel             src/cuElec.cu:27-37,94-134
 //   get_angled_vector, rand_uvect,
 //   adsorb_rand_photon, radiate_photon3         src/cuTemp.cu:230-234,395-453,484-507,631-685
+//   before_nose, after_nose (1-thread kernels)  src/cuTemp.cu:115-123,156-163
 //   float3_sqr, float3_length, ...              src/cuUtils.cu:27-75
 //   put_periodic                                src/cuMDfunc.cu:35-106
 //   count_cell                                  src/cuSort.cu:114-128
@@ -160,6 +161,18 @@ void refdev_wrap_and_bin(float* xyz, const float* vel, float mass, const float* 
     crossings[0] = acPos[0].x; crossings[1] = acPos[0].y; crossings[2] = acPos[0].z;
     crossings[3] = acNeg[0].x; crossings[4] = acNeg[0].y; crossings[5] = acNeg[0].z;
     mom[0] = md.posMom.x; mom[1] = md.posMom.y; mom[2] = md.posMom.z; mom[3] = md.negMom.x; mom[4] = md.negMom.y; mom[5] = md.negMom.z;
+}
+
+// one Nose-Hoover block as apply_tstat launches it: before_nose, [tstat_nose scales the velocities by md->tscale], after_nose(1)
+void refdev_nose(float tSt, float teKin, float rQmass, float qMassTau2, float* engKin, float* chit, float* consInt, float* tscale)
+{
+    static cudaMD md;
+    md.tSt = tSt; md.teKin = teKin; md.rQmass = rQmass; md.qMassTau2 = qMassTau2;
+    md.engKin = *engKin; md.chit = *chit; md.consInt = *consInt;
+    before_nose(&md);
+    *tscale = md.tscale;
+    after_nose(1, &md);
+    *engKin = md.engKin; *chit = md.chit; *consInt = md.consInt;
 }
 
 } // extern "C"

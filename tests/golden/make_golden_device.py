@@ -159,6 +159,19 @@ def main():
         lib.refdev_wrap_and_bin(x.ctypes.data_as(_fp), v.ctypes.data_as(_fp), np.float32(0.004135), L, cn, cr, C.byref(cell), cross, mom)
         rows.append(list(xin) + list(v) + [L[0], L[1], L[2]] + list(cn) + list(cr) + list(x) + [cell.value] + list(cross) + list(mom))
     out["wrapbin"] = np.array(rows, dtype=np.float64)
+
+    # ---- Nose-Hoover scalar recurrence: 40 consecutive blocks from three starting points
+    lib.refdev_nose.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp, _fp]
+    rows = []
+    for teKin, tau, ke0 in ((19.4, 0.02, 48.0), (5.0, 0.1, 1.0), (120.0, 0.5, 119.0)):
+        rq, qt = np.float32(0.5 / teKin / tau / tau), np.float32(2.0 * teKin)
+        ke, chit, ci, ts = C.c_float(ke0), C.c_float(0.0), C.c_float(0.0), C.c_float(0.0)
+        for k in range(40):
+            kin = ke.value
+            lib.refdev_nose(np.float32(0.001), np.float32(teKin), rq, qt, C.byref(ke), C.byref(chit), C.byref(ci), C.byref(ts))
+            rows.append([0.001, teKin, float(rq), float(qt), kin, ke.value, chit.value, ci.value, ts.value])
+            ke = C.c_float(ke.value * (1.0 + 0.01 * math.sin(k)))  # the integrator changes the kinetic energy between blocks
+    out["nose"] = np.array(rows, dtype=np.float64)
     out["tstat_mass"] = np.array([mass])
     np.savez_compressed(os.path.join(HERE, "ref_device_vectors.npz"), **out)
     print("wrote ref_device_vectors.npz:", {k: v.shape for k, v in out.items()})

@@ -394,11 +394,45 @@ def case_list_every_step_variant(lib):
     e.close()
 
 
+def case_nose_hoover(lib):
+    """'temperature T nose tau' (SURVEY 8f-2): the friction is advanced twice per step (before verlet_1stage and in
+    apply_tstat, src/main.cu:291-299, src/cuTemp.cu:787-794); hot start well above the target so that it acts visibly."""
+    s = azt.lj_system(ncell=(5, 5, 5), seed=81, temperature=300.0, tstat=abi.TSTAT_NOSE)
+    s.temperature = 120.0   # target below the initial kinetic temperature
+    s.tstat_tau = 0.02
+    o, e = run_parity(lib, s, nsteps=6, state_tol=5e-5)
+    so, se = o.stats(), e.stats()
+    ke0 = 1.5 * len(s.pos) * 300.0 * 8.617e-5
+    assert se.engKin_d < 0.9 * ke0            # the thermostat removed kinetic energy
+    e.close()
+    # ... together with the equilibration rescale and a multi-step call
+    s = azt.lj_system(ncell=(5, 5, 5), seed=82, temperature=150.0, tstat=abi.TSTAT_NOSE, n_equil=4, eq_freq=2)
+    s.tstat_tau = 0.05
+    o = azt.Oracle(s)
+    e = Engine(s, lib=lib, rebuild_every=3, skin=0.6)
+    o.step(0, 7); e.step(0, 7)
+    so, se = o.stats(), e.stats()
+    assert abs(so.engKin_d - se.engKin_d) <= 2e-5 * so.engKin_d and abs(so.engVdW_d - se.engVdW_d) <= 2e-5 * abs(so.engVdW_d)
+    e.close()
+
+
+def case_reset_vels(lib):
+    """'reset_vels n': every n-th step the velocities are zeroed instead of the second half kick (quenching)."""
+    s = azt.lj_system(ncell=(5, 5, 5), seed=83, temperature=200.0)
+    s.reset_vels = 3
+    o, e = run_parity(lib, s, nsteps=7)
+    e.close()
+    s = azt.surk_system(n_side=6)   # the radiative thermostat still acts on the zeroed velocities (apply_tstat follows zero_vel)
+    s.reset_vels = 2
+    o, e = run_parity(lib, s, nsteps=4, thermo=True, state_tol=1e-4, later_force_tol=1e-4)
+    e.close()
+
+
 def case_error_paths(lib):
     s = azt.lj_system(ncell=(3, 3, 3))
     s.cell_size = 0.0
     for mutate, status in ((lambda x: setattr(x, "cell_size", 0.0), abi.AZ_ERR_INVALID),
-                           (lambda x: setattr(x, "tstat_kind", abi.TSTAT_NOSE), abi.AZ_ERR_UNSUPPORTED),
+                           (lambda x: setattr(x, "tstat_kind", abi.TSTAT_NOSE), abi.AZ_ERR_INVALID),   # Nose-Hoover without a relaxation time
                            (lambda x: setattr(x, "box", (0.0, 10.0, 10.0)), abi.AZ_ERR_INVALID)):
         t = azt.lj_system(ncell=(3, 3, 3))
         mutate(t)
@@ -445,6 +479,8 @@ ALL_CASES = [
     ("skin_violation", case_skin_violation_is_reported),
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
+    ("nose_hoover", case_nose_hoover),
+    ("reset_vels", case_reset_vels),
     ("tile_kernel_variant", case_tile_kernel_variant),
     ("list_every_step_variant", case_list_every_step_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),

@@ -142,9 +142,22 @@ def test_photon_energies_follow_e4_exp_distribution(lib, tmp_path):
     lib.az_deck_free(h)
 
 
+def test_nose_hoover_and_reset_vels_directives(lib, tmp_path):
+    write_cs2_like(tmp_path)
+    p = os.path.join(str(tmp_path), "control.txt")
+    text = open(p).read().replace("radi\t0.2", "nose 0.35", 1) + "\nreset_vels 40\n"
+    open(p, "w").write(text)
+    rc, h = load(lib, tmp_path)
+    assert rc == 0, lib.az_deck_error(h)
+    d = lib.az_deck_desc(h).contents
+    assert d.tstat_kind == abi.TSTAT_NOSE and d.tstat_tau == pytest.approx(0.35) and d.reset_vels == 40
+    assert not d.photons  # no photon table without the radiative thermostat
+    lib.az_deck_free(h)
+
+
 @pytest.mark.parametrize("edit,status,needle", [
     (("control.txt", "timestep 0.001 ps", ""), abi.AZ_ERR_IO, b"ERROR[411]"),
-    (("control.txt", "radi\t0.2", "nose 0.2"), abi.AZ_ERR_UNSUPPORTED, b"Nose"),
+    (("control.txt", "radi\t0.2", "nose zzz"), abi.AZ_ERR_IO, b"tau"),
     (("control.txt", "elec\tfenn", "elec\tzzz"), abi.AZ_ERR_IO, b"ERROR[404]"),
     (("control.txt", "init_vel\tzero", "no_vel zero"), abi.AZ_ERR_IO, b"ERROR[406]"),
     (("control.txt", "cell_list\t2.7", ""), abi.AZ_ERR_IO, b"cell_list"),

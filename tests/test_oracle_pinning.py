@@ -364,3 +364,19 @@ def test_oracle_wrap_and_bin_match_reference_put_periodic_and_count_cell():
                 assert c == cell_ref, row
                 checked += 1
     assert checked > 300
+
+
+def test_oracle_nose_hoover_recurrence_matches_reference_source():
+    """before_nose + after_nose(1) of src/cuTemp.cu executed on the CPU: friction, velocity factor, kinetic energy, integral."""
+    z = np.load(DEV)
+    lib = azt.oracle_lib()
+    lib.azo_nose_scalars.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp, _fp]
+    chit, ci = C.c_float(0.0), C.c_float(0.0)
+    prev_te = None
+    for tSt, teKin, rq, qt, ke_in, ke_out, chit_ref, ci_ref, ts_ref in z["nose"]:
+        if prev_te != teKin:
+            chit, ci, prev_te = C.c_float(0.0), C.c_float(0.0), teKin
+        ke, ts = C.c_float(ke_in), C.c_float()
+        lib.azo_nose_scalars(tSt, teKin, rq, qt, C.byref(ke), C.byref(chit), C.byref(ci), C.byref(ts))
+        assert np.float32(ts.value) == np.float32(ts_ref) and np.float32(ke.value) == np.float32(ke_out)   # bit-exact
+        assert np.float32(chit.value) == np.float32(chit_ref) and np.float32(ci.value) == np.float32(ci_ref)
