@@ -299,6 +299,9 @@ az_k_pair(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs
 // merged into one j-range.  delta and r2 are formed exactly like the force pass forms them, so with
 // skin == 0 the recorded set is the in-range set.
 #define AZ_LIST_TPB 128
+// az_k_pair_list asks for 16 resident blocks (32 registers, 64 warps per SM) in its plain Lennard-Jones form: the kernel
+// is bound by gather latency and more warps hide it (ncu: 0.357 ms at 32 registers, 0.366 ms at 48); the forms with
+// exp/erfc, a species table or per-atom radii would spill at 32 registers and ask for 10 blocks (48 registers)
 #define AZ_NBR_CNT_BITS 16
 
 __device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)(i >> 5) * (size_t)cap) * 32 + (size_t)(i & 31); }
@@ -457,7 +460,7 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
 // current positions as the cell sweep, so the pair set per step is identical to the every-step-rebuild
 // schedule as long as no atom moved more than skin/2 (tracked by az_k_integrate_a / az_k_finalize).
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
-__global__ void __launch_bounds__(AZ_LIST_TPB)
+__global__ void __launch_bounds__(AZ_LIST_TPB, (VK == AZ_VDW_LJ && CK == AZ_ELEC_NONE && SINGLE && !RADII && !ENERGY) ? 16 : 10)
 az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
@@ -502,9 +505,14 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
         // gathers of chunk k (L1/L2) are consumed
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#ifdef AZ_LIST_DBG // diagnostic build only (bench.py --list-dbg): 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
         const int dbg = A.dbg;
         auto ldidx = [&](const int* p, int kk) { return dbg == 2 ? max(0, min(az_n_owned(P) - 1, i + kk - (cnt >> 1))) : *p; };
         auto ldpos = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : __ldg(A.pos + c); };
+#else
+        auto ldidx = [&](const int* p, int) { return *p; };
+        auto ldpos = [&](int c) { return __ldg(A.pos + c); };
+#endif
         if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
         for (; k + 4 <= cnt; k += 4) {
             row += 4 * stride;
