@@ -128,6 +128,9 @@ ENGINE_SYMBOLS = {
     "az_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "az_engine_info": (C.c_int, [C.c_void_p, C.POINTER(az_engine_info_t)]),
     "az_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "az_engine_rdf_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "az_engine_rdf_sample": (C.c_int, [C.c_void_p]),
+    "az_engine_rdf_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int, _ip, _ip, _ip]),
 }
 DECK_SYMBOLS = {
     "az_deck_load": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -139,6 +142,7 @@ DECK_SYMBOLS = {
     "az_deck_warnings": (C.c_char_p, [C.c_void_p]),
     "az_deck_nstep_stat": (C.c_int, [C.c_void_p]),
     "az_deck_species_count": (C.c_int, [C.c_void_p, C.c_int]),
+    "az_deck_rdf": (C.c_int, [C.c_void_p, _dp, _dp, _ip, _ip]),
     "az_deck_free": (None, [C.c_void_p]),
 }
 

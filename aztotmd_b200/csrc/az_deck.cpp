@@ -84,6 +84,8 @@ struct az_deck {
     az_cuda_opts opts;
     int nsteps = 0, stat_period = 1000, nstep_stat = 10, nstep_msd = 10;
     int tstat_step = 0;
+    double rdf_rmax = 0.0, rdf_dr = 0.0;   // read_rdf, src/rdf.cpp:14-37
+    int rdf_freq = 0, rdf_outfreq = 0, rdf_nuclei = 0;
     std::vector<double> xs, ys, zs, vxs, vys, vzs, photons;
     std::vector<int> types;
     std::vector<az_species> species;
@@ -310,7 +312,20 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     { int mn; if (scan_first(f, " max_neigh %d ", &mn) && mn > 0) d->opts.max_neigh = mn; } // rows of the Verlet list per atom
     double cell_size = 0.0;
     if (!scan_first(f, " cell_list %lf ", &cell_size)) DECK_FAIL(AZ_ERR_IO, "'cell_list' is required by the CUDA path (desired_cell_size, src/cuInit.cu:979)");
-    { double r; if (!scan_first(f, " rdf %lf ", &r)) DECK_WARN("note: no 'rdf' directive (the reference demands one, ERROR[408]); RDF sampling is outside the hot path anyway"); }
+    { // read_rdf (src/rdf.cpp:14-37): rdf rmax dr freq outfreq [nucl]
+        double r;
+        if (!scan_first(f, " rdf %lf ", &r)) DECK_WARN("note: no 'rdf' directive (the reference demands one, ERROR[408]): no RDF is sampled");
+        else {
+            char word[64] = "";
+            if (fscanf(f, " %lf %d %d", &d->rdf_dr, &d->rdf_freq, &d->rdf_outfreq) != 3 || !(d->rdf_dr > 0.0) || d->rdf_freq <= 0)
+                DECK_FAIL(AZ_ERR_IO, "rdf directive: expected 'rdf rmax dr freq outfreq [nucl]'");
+            d->rdf_rmax = r;
+            if (fscanf(f, " %63s", word) == 1 && !strcmp(word, "nucl")) {
+                d->rdf_nuclei = 1;
+                DECK_WARN("note: 'rdf ... nucl': the by-nuclei table rdf_n.dat is not produced (no red-ox species on this path); rdf.dat by species is");
+            }
+        }
+    }
     d->stat_period = 1000;
     if (!scan_first(f, " stat %d ", &d->stat_period)) { d->stat_period = 1000; DECK_WARN("WARNING[133]: stat directive is not specified, default value of 1000 is used"); }
     if (d->stat_period <= 0) d->stat_period = 1000;
@@ -413,4 +428,13 @@ extern "C" const char* az_deck_error(const az_deck* d) { return d ? d->err.c_str
 extern "C" const char* az_deck_warnings(const az_deck* d) { return d ? d->warnings.c_str() : ""; }
 extern "C" int az_deck_nstep_stat(const az_deck* d) { return d ? d->nstep_stat : 0; }
 extern "C" int az_deck_species_count(const az_deck* d, int t) { return (d && t >= 0 && t < (int)d->spec_count.size()) ? d->spec_count[t] : 0; }
+extern "C" int az_deck_rdf(const az_deck* d, double* r_max, double* dr, int* freq, int* outfreq)
+{
+    if (!d || d->rdf_freq <= 0) return 0;
+    if (r_max) *r_max = d->rdf_rmax;
+    if (dr) *dr = d->rdf_dr;
+    if (freq) *freq = d->rdf_freq;
+    if (outfreq) *outfreq = d->rdf_outfreq;
+    return 1;
+}
 extern "C" void az_deck_free(az_deck* d) { delete d; }

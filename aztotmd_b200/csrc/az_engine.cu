@@ -432,7 +432,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
-    cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
+    cudaFree(e->rdf_hist); cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
     for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -936,6 +936,75 @@ extern "C" int az_measure_fp32_peak(int device, double* tflops, double* sm_mhz_e
     *tflops = best;
     if (sm_mhz_effective) *sm_mhz_effective = best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;
     cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st); cudaFree(out);
+    return AZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------- RDF
+extern "C" int az_engine_rdf_begin(az_engine* e, double r_max, double dr)
+{
+    if (!e) return AZ_ERR_INVALID;
+    if (!(r_max > 0.0) || !(dr > 0.0)) { AZ_SET_ERR(e, "rdf: r_max and dr must be positive"); return AZ_ERR_INVALID; }
+    if (e->dd) { AZ_SET_ERR(e, "rdf sampling on bricks is not implemented"); return AZ_ERR_UNSUPPORTED; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    const AzGrid& g = e->P.g;
+    const double idrdf = 1.0 / dr;                                   // Sim::idRDF, src/rdf.cpp:22
+    double minR = r_max;
+    if (minR > (double)e->P.L[0]) minR = (double)e->P.L[0];          // init_rdf, src/rdf.cpp:38-45
+    const int nb = (int)(minR * idrdf);
+    const int np = e->P.nspec * (e->P.nspec + 1) / 2;
+    if (nb <= 0) { AZ_SET_ERR(e, "rdf: dr is larger than the radius"); return AZ_ERR_INVALID; }
+    if ((size_t)nb * np * sizeof(unsigned) > 200 * 1024) { AZ_SET_ERR(e, "rdf: %d bins x %d pairs do not fit the shared-memory histogram", nb, np); return AZ_ERR_UNSUPPORTED; }
+    const float reach = (float)r_max + e->P.skin; // cells may be stale by up to skin / 2 per atom
+    for (int a = 0; a < 3; a++) {
+        int s1 = 1;
+        while ((float)s1 * g.csize[a] <= reach && s1 < g.n[a]) s1++;
+        if (g.n[a] < 2 * s1 + 1) { AZ_SET_ERR(e, "rdf: radius %g needs %d cell layers on axis %d, the grid has %d cells (every pair must be seen through one image only)", r_max, s1, a, g.n[a]); return AZ_ERR_UNSUPPORTED; }
+        e->rdf_sten[a] = s1;
+    }
+    cudaFree(e->rdf_hist); e->rdf_hist = nullptr;
+    AZ_ALLOC(e, e->rdf_hist, (size_t)nb * np);
+    e->rdf_nbins = nb; e->rdf_npair = np; e->rdf_samples = 0;
+    e->rdf_r2max = (float)(r_max * r_max); e->rdf_idrdf = (float)idrdf; e->rdf_r2stencil = reach * reach;
+#ifndef AZ_EMU
+    if ((size_t)nb * np * sizeof(unsigned) > 48 * 1024)
+        AZ_CUDA(e, cudaFuncSetAttribute(az_k_rdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)nb * np * sizeof(unsigned))));
+#endif
+    return AZ_OK;
+}
+
+extern "C" int az_engine_rdf_sample(az_engine* e)
+{
+    if (!e) return AZ_ERR_INVALID;
+    if (!e->rdf_hist) { AZ_SET_ERR(e, "rdf: call az_engine_rdf_begin first"); return AZ_ERR_INVALID; }
+    if (!e->binned) { AZ_SET_ERR(e, "rdf: the atoms are not binned yet (sample after a step)"); return AZ_ERR_INVALID; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    AzRdfArgs A;
+    memset(&A, 0, sizeof(A));
+    const int c = e->cur;
+    A.pos = e->pos[c]; A.cellOfSorted = e->cellSorted; A.first = e->first; A.count = e->cellCount; A.hist = e->rdf_hist;
+    for (int a = 0; a < 3; a++) A.sten[a] = e->rdf_sten[a];
+    A.nbins = e->rdf_nbins; A.npair = e->rdf_npair; A.r2max = e->rdf_r2max; A.idrdf = e->rdf_idrdf; A.r2stencil = e->rdf_r2stencil;
+    const int blocks = (e->n + (AZ_RDF_TPB / 32) - 1) / (AZ_RDF_TPB / 32);
+    AZ_LAUNCH(az_k_rdf, blocks, AZ_RDF_TPB, (size_t)e->rdf_nbins * e->rdf_npair * sizeof(unsigned), e->stream, e->P, A);
+    e->launches++;
+    e->rdf_samples++;
+    AZ_CUDA(e, cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_engine_rdf_read(az_engine* e, unsigned long long* counts, int capacity, int* n_bins, int* n_pairs, int* n_samples)
+{
+    if (!e) return AZ_ERR_INVALID;
+    if (!e->rdf_hist) { AZ_SET_ERR(e, "rdf: call az_engine_rdf_begin first"); return AZ_ERR_INVALID; }
+    if (n_bins) *n_bins = e->rdf_nbins;
+    if (n_pairs) *n_pairs = e->rdf_npair;
+    if (n_samples) *n_samples = e->rdf_samples;
+    if (counts) {
+        if (capacity < e->rdf_nbins * e->rdf_npair) { AZ_SET_ERR(e, "rdf: capacity %d < %d", capacity, e->rdf_nbins * e->rdf_npair); return AZ_ERR_INVALID; }
+        AZ_CUDA(e, cudaSetDevice(e->device));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        AZ_CUDA(e, cudaMemcpy(counts, e->rdf_hist, sizeof(unsigned long long) * e->rdf_nbins * e->rdf_npair, cudaMemcpyDeviceToHost));
+    }
     return AZ_OK;
 }
 

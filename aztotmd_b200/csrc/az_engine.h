@@ -67,6 +67,10 @@ struct az_engine {
     AzScalars* sc = nullptr;
     AzVdw* table = nullptr;
     float *photons = nullptr, *uv = nullptr;
+    // radial distribution function (az_engine_rdf_*)
+    unsigned long long* rdf_hist = nullptr;
+    int rdf_nbins = 0, rdf_npair = 0, rdf_samples = 0, rdf_sten[3] = { 0, 0, 0 };
+    float rdf_r2max = 0.f, rdf_idrdf = 0.f, rdf_r2stencil = 0.f;
     size_t dev_bytes = 0;
     // accounting
     long long launches = 0;

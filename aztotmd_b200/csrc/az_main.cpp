@@ -8,6 +8,7 @@
 //   revcon.xyz           out_atoms, save_box        src/out_md.cpp:65-86, src/box.cpp:169-176
 //   velocities.dat       out_velocities             src/out_md.cpp:126-194
 //   tchars.dat           out_thermalchar            src/main.cu:51-118
+//   rdf.dat, rdf<N>.dat  rdf_iter, copy_rdf         src/cuStat.cu:514-594 (sampled from the cell grid, not by brute force)
 // Statistics rows are produced for iStep % stat == 0 like stat_iter (src/cuStat.cu:387-404).
 #include <math.h>
 #include <stdio.h>
@@ -21,6 +22,40 @@
 #include "../../include/aztot_b200.h"
 
 extern "C" const char* az_deck_warnings(const az_deck*);
+
+// copy_rdf (src/cuStat.cu:514-561): normalisation and layout of rdf.dat
+static void write_rdf(const char* fname, az_engine* eng, const az_deck* deck, const az_system_desc* d, double dr)
+{
+    int nb = 0, np = 0, ns = 0;
+    if (az_engine_rdf_read(eng, nullptr, 0, &nb, &np, &ns) != AZ_OK || ns <= 0) return;
+    std::vector<unsigned long long> cnt((size_t)nb * np);
+    if (az_engine_rdf_read(eng, cnt.data(), (int)cnt.size(), nullptr, nullptr, nullptr) != AZ_OK) return;
+    FILE* f = fopen(fname, "w");
+    if (!f) return;
+    const int nspec = d->n_species;
+    fprintf(f, "r");
+    for (int i = 0; i < nspec; i++)
+        for (int j = i; j < nspec; j++) fprintf(f, "\t%s-%s", d->species[i].name, d->species[j].name);
+    fprintf(f, "\n");
+    const double sphera = 4.0 * 3.14159265359 / 3.0; // src/const.h:11,15
+    const double C1 = 2 / (sphera * dr * dr * dr * ns);
+    const float volume = (float)(d->la * d->lb * d->lc);
+    for (int i = 0; i < nb; i++) {
+        fprintf(f, "%f", (i + 0.5) * dr);
+        const float C2 = 1.f / (3.f * i * (i + 1.f) + 1.f);
+        int k = 0, l = 0;
+        for (int j = 0; j < np; j++) {
+            const float C3 = (k == l) ? 1.f : 0.5f;
+            // what brute_rdf accumulated per pair: volume / N_k / N_l (src/cuStat.cu:497)
+            const float acc = (float)cnt[(size_t)i * np + j] * (volume / (float)az_deck_species_count(deck, k) / (float)az_deck_species_count(deck, l));
+            fprintf(f, "\t%f", acc * C1 * C2 * C3);
+            l++;
+            if (l == nspec) { k++; l = k; }
+        }
+        fprintf(f, "\n");
+    }
+    fclose(f);
+}
 
 static void print_stat(int iStep, const az_stats& s, const az_system_desc* d)
 {
@@ -76,17 +111,37 @@ int main(int argc, char** argv)
     for (int i = 0; i < nspec; i++) fprintf(fm, "\t%s_px\tnx\tpy\tny\tpz\tnz", d->species[i].name);
     fprintf(fm, "\n");
 
+    double rdf_rmax = 0.0, rdf_dr = 0.0;
+    int rdf_freq = 0, rdf_outfreq = 0;
+    bool rdf_on = az_deck_rdf(deck, &rdf_rmax, &rdf_dr, &rdf_freq, &rdf_outfreq) != 0;
+    if (rdf_on && az_engine_rdf_begin(eng, rdf_rmax, rdf_dr) != AZ_OK) {
+        printf("WARNING: no RDF will be written: %s\n", az_last_error(eng));
+        rdf_on = false;
+    }
+
     az_stats st;
     memset(&st, 0, sizeof(st));
     int iStep = 0;
     while (iStep < nSt) {
-        // advance to the next statistics step (iStep % stat == 0) or to the end
+        // advance to the next statistics step (iStep % stat == 0), the next RDF sample, or the end
         int target = (iStep % stat == 0) ? iStep : ((iStep / stat + 1) * stat);
+        if (rdf_on) {
+            const int tr = (iStep % rdf_freq == 0) ? iStep : ((iStep / rdf_freq + 1) * rdf_freq);
+            if (tr < target) target = tr;
+        }
         if (target > nSt - 1) target = nSt - 1;
         rc = az_engine_step(eng, iStep, target - iStep + 1);
         if (rc == AZ_OK) rc = az_engine_stats(eng, &st);
         if (rc != AZ_OK) { printf("ERROR: %s\n", az_last_error(eng)); break; }
         iStep = target;
+        if (rdf_on && iStep % rdf_freq == 0) { // rdf_iter, src/cuStat.cu:563-594
+            if (az_engine_rdf_sample(eng) != AZ_OK) { printf("ERROR: %s\n", az_last_error(eng)); rc = AZ_ERR_CUDA; break; }
+            if (rdf_outfreq && iStep % rdf_outfreq == 0) {
+                char name[64];
+                snprintf(name, sizeof(name), "rdf%d.dat", iStep);
+                write_rdf(name, eng, deck, d, rdf_dr);
+            }
+        }
         if (iStep % stat == 0) {
             print_stat(iStep, st, d);
             double t = iStep * d->timestep;
@@ -103,6 +158,7 @@ int main(int argc, char** argv)
     }
     if (rc == AZ_OK) print_stat(iStep, st, d); // final output to screen
     fclose(fs); fclose(fm);
+    if (rdf_on) write_rdf("rdf.dat", eng, deck, d, rdf_dr);
 
     // md_to_host: atoms come back in cell-sorted order, like the reference
     const int n = d->n_atoms;

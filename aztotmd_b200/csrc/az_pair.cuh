@@ -577,6 +577,58 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 }
 
 
+// The stencil cells of one atom, enumerated by a whole warp 32 at a time, one cell per lane (z offset fastest): validity,
+// image and the two loads (first, count) of all cells of a chunk are in flight together instead of one after the
+// other.  Runs of lanes whose ranges are adjacent in memory with the same image (the z neighbours of one column) are
+// merged, then `sweep(first_atom, end_atom, image_code)` is called by all lanes for every merged range.
+template <class F>
+__device__ __forceinline__ void az_warp_stencil_ranges(const AzGrid& g, const int* sten, float r2lim, int gcx, int gcy, int gcz,
+                                                       const int* __restrict__ first, const int* __restrict__ count, int lane, F&& sweep)
+{
+    const int wy = 2 * sten[1] + 1, wz = 2 * sten[2] + 1;
+    const int ncells = (2 * sten[0] + 1) * wy * wz;
+    for (int c0 = 0; c0 < ncells; c0 += 32) {
+        const int c = c0 + lane;
+        int jb = -1, je = -1, code = 0;
+        if (c < ncells) {
+            const int oz = c % wz - sten[2], t = c / wz;
+            const int oy = t % wy - sten[1], ox = t / wy - sten[0];
+            int sx, sy, sz, shxi, shyi, shzi;
+            if (az_neighbor(g, 0, gcx, ox, sx, shxi) && az_neighbor(g, 1, gcy, oy, sy, shyi) && az_neighbor(g, 2, gcz, oz, sz, shzi)) {
+                const int aox = ox < 0 ? -ox : ox, aoy = oy < 0 ? -oy : oy, aoz = oz < 0 ? -oz : oz;
+                const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+                const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+                const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+                const float mxy2 = mx * mx + my * my;
+                if (mxy2 <= r2lim && mxy2 + mz * mz <= r2lim) {
+                    const int cid = az_cell_id(g, (sx * g.nl[1] + sy) * g.nl[2] + sz);
+                    jb = first[cid];
+                    je = jb + count[cid];
+                    code = az_shift_code(shxi, shyi, shzi);
+                }
+            }
+        }
+        const bool valid = je > jb;
+        // continuation: this lane's range starts where the previous lane's ends, same image
+        const int pje = __shfl_up_sync(0xffffffffu, je, 1), pcode = __shfl_up_sync(0xffffffffu, code, 1);
+        const int pvalid = __shfl_up_sync(0xffffffffu, (int)valid, 1);
+        const bool cont = valid && lane > 0 && pvalid && pje == jb && pcode == code;
+        const unsigned contmask = __ballot_sync(0xffffffffu, cont);
+        unsigned heads = __ballot_sync(0xffffffffu, valid && !cont);
+        // a head's run covers the consecutive continuation lanes behind it
+        const unsigned behind = lane < 31 ? (contmask >> (lane + 1)) : 0u;
+        const int runlen = __ffs((int)~behind) - 1; // consecutive ones from bit 0
+        const int je_run = __shfl_sync(0xffffffffu, je, min(31, lane + runlen));
+        while (heads) {
+            const int h = __ffs((int)heads) - 1;
+            heads &= heads - 1;
+            const int rb = __shfl_sync(0xffffffffu, jb, h), re = __shfl_sync(0xffffffffu, je_run, h), rcode = __shfl_sync(0xffffffffu, code, h);
+            sweep(rb, re, rcode);
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------------------------------
 // az_k_pair_warp: the reference schedule (bin + sort every step, no list) with one WARP per atom.  The lanes
 // stride over the atoms of the stencil cells straight from the sorted stream (coalesced float4 loads; z-adjacent
@@ -637,51 +689,7 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
                 if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
             }
         };
-        // The stencil cells are enumerated 32 at a time, one cell per lane (z offset fastest): validity, image and
-        // the two loads (first, count) of all cells of a chunk are in flight together instead of one after the other.
-        // Runs of lanes whose ranges are adjacent in memory with the same image (the z neighbours of one column)
-        // are merged, then the warp sweeps the merged ranges one by one.
-        const int wx = 2 * g.sten[0] + 1, wy = 2 * g.sten[1] + 1, wz = 2 * g.sten[2] + 1;
-        const int ncells = wx * wy * wz;
-        for (int c0 = 0; c0 < ncells; c0 += 32) {
-            const int c = c0 + lane;
-            int jb = -1, je = -1, code = 0;
-            if (c < ncells) {
-                const int oz = c % wz - g.sten[2], t = c / wz;
-                const int oy = t % wy - g.sten[1], ox = t / wy - g.sten[0];
-                int sx, sy, sz, shxi, shyi, shzi;
-                if (az_neighbor(g, 0, gcx, ox, sx, shxi) && az_neighbor(g, 1, gcy, oy, sy, shyi) && az_neighbor(g, 2, gcz, oz, sz, shzi)) {
-                    const int aox = ox < 0 ? -ox : ox, aoy = oy < 0 ? -oy : oy, aoz = oz < 0 ? -oz : oz;
-                    const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
-                    const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
-                    const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
-                    const float mxy2 = mx * mx + my * my;
-                    if (mxy2 <= P.r2list && mxy2 + mz * mz <= P.r2list) {
-                        const int cid = az_cell_id(g, (sx * g.nl[1] + sy) * g.nl[2] + sz);
-                        jb = A.first[cid];
-                        je = jb + A.count[cid];
-                        code = az_shift_code(shxi, shyi, shzi);
-                    }
-                }
-            }
-            const bool valid = je > jb;
-            // continuation: this lane's range starts where the previous lane's ends, same image
-            const int pje = __shfl_up_sync(0xffffffffu, je, 1), pcode = __shfl_up_sync(0xffffffffu, code, 1);
-            const int pvalid = __shfl_up_sync(0xffffffffu, (int)valid, 1);
-            const bool cont = valid && lane > 0 && pvalid && pje == jb && pcode == code;
-            const unsigned contmask = __ballot_sync(0xffffffffu, cont);
-            unsigned heads = __ballot_sync(0xffffffffu, valid && !cont);
-            // a head's run covers the consecutive continuation lanes behind it
-            const unsigned behind = lane < 31 ? (contmask >> (lane + 1)) : 0u;
-            const int runlen = __ffs((int)~behind) - 1; // consecutive ones from bit 0
-            const int je_run = __shfl_sync(0xffffffffu, je, min(31, lane + runlen));
-            while (heads) {
-                const int h = __ffs((int)heads) - 1;
-                heads &= heads - 1;
-                const int rb = __shfl_sync(0xffffffffu, jb, h), re = __shfl_sync(0xffffffffu, je_run, h), rcode = __shfl_sync(0xffffffffu, code, h);
-                sweep(rb, re, rcode);
-            }
-        }
+        az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep);
     }
     // the 32 shares of atom i (all lanes of a warp belong to the same atom, so the whole warp is in or out)
 #pragma unroll
@@ -698,5 +706,69 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
         az_block_sum<3>(vv, s_red);
         if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// az_k_rdf: radial distribution histogram from the cell grid (replaces the O(N^2) brute_rdf,
+// src/cuStat.cu:436-512).  One warp per atom, lanes stride over the atoms of the stencil cells of the RDF radius; every
+// unordered pair inside the radius is counted once (j > i) in a per-CTA shared histogram of integers, flushed with
+// integer atomics: the result is exact and independent of the execution order (the reference accumulates
+// volume / (N_a N_b) per pair with float atomics).  Bin and species-pair index are the reference's:
+// iR = (int)(sqrt((double)r2) * idRDF), iPair = mn * (nSpec - 1) + mn * (1 - mn) / 2 + mx.
+struct AzRdfArgs {
+    const float4* pos; const int* cellOfSorted; const int* first; const int* count;
+    unsigned long long* hist; // [nbins * npair], bin-major like md->rdf
+    int sten[3];
+    int nbins, npair;
+    float r2max, idrdf, r2stencil;
+};
+
+#define AZ_RDF_TPB 256
+static __global__ void __launch_bounds__(AZ_RDF_TPB)
+az_k_rdf(const __grid_constant__ AzParams P, const __grid_constant__ AzRdfArgs A)
+{
+    AZ_DYN_SMEM(unsigned, s_hist); // nbins * npair counters
+    const AzGrid& g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nh = A.nbins * A.npair;
+    for (int k = tid; k < nh; k += AZ_RDF_TPB) s_hist[k] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * (AZ_RDF_TPB / 32) + (tid >> 5);
+    if (i < az_n_owned(P)) {
+        const float4 pi = A.pos[i];
+        const int ti = __float_as_int(pi.w);
+        const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+        const int ci = A.cellOfSorted[i];
+        const int cxy = ci / onz;
+        const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+        const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+        const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+        const int m = P.nspec - 1;
+        auto sweep = [&](const int rb, const int re, const int code) {
+            const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
+            const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
+            const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
+            for (int j = max(rb, i + 1) + lane; j < re; j += 32) { // j > i: every unordered pair once
+                const float4 pj = __ldg(A.pos + j);
+                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                if (code) { dx -= shx; dy -= shy; dz -= shz; }
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 < A.r2max) {
+                    const int iR = (int)(sqrt((double)r2) * (double)A.idrdf);
+                    const int tj = __float_as_int(pj.w);
+                    const int mn = min(ti, tj), mx = max(ti, tj);
+                    const int iPair = mn * m + mn * (1 - mn) / 2 + mx;
+                    if (iR < A.nbins) atomicAdd(&s_hist[iR * A.npair + iPair], 1u);
+                }
+            }
+        };
+        az_warp_stencil_ranges(g, A.sten, A.r2stencil, gcx, gcy, gcz, A.first, A.count, lane, sweep);
+    }
+    __syncthreads();
+    for (int k = tid; k < nh; k += AZ_RDF_TPB) {
+        const unsigned v = s_hist[k];
+        if (v) atomicAdd(&A.hist[k], (unsigned long long)v);
     }
 }

@@ -77,7 +77,7 @@ def write_deck(dirname, *, names, pos, box, field_txt, control_txt, cuda_txt=Non
 
 def lj_argon_deck(dirname, ncell, *, rho_star=0.8442, rc_sigma=2.5, temperature=86.6,
                   nstep=100, init_vel="gaus", tstat="none", cell_list=None, jitter=0.05, seed=1,
-                  rebuild_every=1, skin=0.0, stat=1000):
+                  rebuild_every=1, skin=0.0, stat=1000, rdf_freq=10 ** 9, rdf_rmax=8.0, rdf_dr=0.02):
     """fcc LJ argon (config 3/5 of BASELINE.json): a = (4/rho)^(1/3) sigma, rc = 2.5 sigma."""
     if isinstance(ncell, int):
         ncell = (ncell, ncell, ncell)
@@ -89,9 +89,9 @@ def lj_argon_deck(dirname, ncell, *, rho_star=0.8442, rc_sigma=2.5, temperature=
     ctl = (
         "timestep 0.001 ps\nnstep %d\nnequil 0\neqfreq 100\ntemperature %g\t%s\n"
         "init_vel\t%s\npermittivity 1.0\ncell_list\t%.6f\nmax_neigh\t185\nelec\tnone\n"
-        "rdf\t8.0 0.02\t%d\t%d\nhist %d\nstat\t%d\nseed %d\n"
+        "rdf\t%g %g\t%d\t%d\nhist %d\nstat\t%d\nseed %d\n"
         % (nstep, temperature, tstat, init_vel, cell_list if cell_list else rc,
-           10 ** 9, 10 ** 9, 10 ** 9, stat, seed))
+           rdf_rmax, rdf_dr, rdf_freq, 10 ** 9, 10 ** 9, stat, seed))
     cuda = "nstep stat 50\nnstep msdstat 50\nnthread a 16\nnthread b 32\nrebuild %d\nskin %g\n" % (
         rebuild_every, skin)
     write_deck(dirname, names="Ar", pos=pos, box=box, field_txt=field, control_txt=ctl, cuda_txt=cuda)

@@ -384,6 +384,20 @@ class Engine:
             self._pending_upload = (cols, vcols)  # the arrays must outlive the copy
         self._check(fn(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
 
+    def rdf_begin(self, r_max: float, dr: float):
+        self._check(self.lib.az_engine_rdf_begin(self._h, float(r_max), float(dr)))
+
+    def rdf_sample(self):
+        self._check(self.lib.az_engine_rdf_sample(self._h))
+
+    def rdf_counts(self):
+        """(counts[n_bins, n_pairs] of unordered pairs per bin and species pair, n_samples)."""
+        nb, npair, ns = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.az_engine_rdf_read(self._h, None, 0, C.byref(nb), C.byref(npair), C.byref(ns)))
+        buf = np.zeros(nb.value * npair.value, dtype=np.uint64)
+        self._check(self.lib.az_engine_rdf_read(self._h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.size, None, None, None))
+        return buf.reshape(nb.value, npair.value), ns.value
+
     def profile(self, mode: int = 1):
         """0 off, 1 synchronous per-section timing, 2 recorded events (no host sync in the loop)."""
         self._check(self.lib.az_engine_profile(self._h, int(mode)))

@@ -258,6 +258,17 @@ int az_engine_upload(az_engine *e, const double *xs, const double *ys, const dou
 int az_engine_upload_async(az_engine *e, const double *xs, const double *ys, const double *zs,
                            const double *vxs, const double *vys, const double *vzs);
 
+/* Radial distribution function from the cell grid: replaces init_cuda_rdf / brute_rdf / rdf_iter / copy_rdf
+ * (src/cuStat.cu:418-594; the reference's brute force is O(N^2) per sample).  az_engine_rdf_begin allocates and clears
+ * the histogram: n_bins = (int)(min(r_max, la) / dr) like init_rdf (src/rdf.cpp:38-45), one column per unordered species
+ * pair in the reference's order (i <= j, row-major).  az_engine_rdf_sample adds the pairs of the current configuration
+ * (call it after a step, every 'rdf' frequency steps).  az_engine_rdf_read returns the raw integer pair counts, bin-major
+ * (counts[bin * n_pairs + pair]), and the number of samples; the normalisation of copy_rdf (src/cuStat.cu:514-561) is
+ * host arithmetic on them: g = count * V / (N_a N_b) * 2 / (4/3 pi dr^3 n_samples) / (3 i (i + 1) + 1) * (a == b ? 1 : 1/2). */
+int az_engine_rdf_begin(az_engine *e, double r_max, double dr);
+int az_engine_rdf_sample(az_engine *e);
+int az_engine_rdf_read(az_engine *e, unsigned long long *counts, int capacity, int *n_bins, int *n_pairs, int *n_samples);
+
 /* Per-kernel device timers (CUDA events on the engine stream).  az_engine_profile(e, 1) times each
  * section synchronously; (e, 2) only records events inside the step loop (no host sync) and
  * az_engine_timers resolves them once the stream has drained; (e, 0) switches timing off. */
@@ -318,6 +329,8 @@ const char *az_deck_error(const az_deck *d);      /* d may be NULL: error of the
 const char *az_deck_warnings(const az_deck *d);   /* the WARNING[...] lines the reference would print */
 int az_deck_nstep_stat(const az_deck *d);         /* cuda.txt 'nstep stat' (flush granularity)       */
 int az_deck_species_count(const az_deck *d, int species);
+/* the 'rdf rmax dr freq outfreq' directive (src/rdf.cpp:14-37); returns 0 if the deck has none */
+int az_deck_rdf(const az_deck *d, double *r_max, double *dr, int *freq, int *outfreq);
 void az_deck_free(az_deck *d);
 
 #ifdef __cplusplus

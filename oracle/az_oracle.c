@@ -853,3 +853,33 @@ int azo_forces_allpairs(azo_state *s, float *fx, float *fy, float *fz, double *e
     *evdw_out = evdw; *ecoul_out = ecoul;
     return 0;
 }
+
+
+/* brute_rdf (src/cuStat.cu:436-512) restated: every unordered pair, minimum image by delta_periodic
+ * (src/cuMDfunc.cu:178-203), r2 < r2max, bin = (int)(sqrt((double)r2) * idRDF), pair index
+ * mn * (nSpec - 1) + mn * (1 - mn) / 2 + mx.  Integer counts (the reference adds volume / (N_a N_b) per pair in float;
+ * the normalisation of copy_rdf is applied by the caller).  counts[bin * npair + pair] += 1. */
+int azo_rdf_counts(azo_state *s, float r_max, float dr, unsigned long long *counts, int nbins)
+{
+    const float idrdf = (float)(1.0 / (double)dr);
+    const float r2max = (float)((double)r_max * (double)r_max);
+    const int m = s->nspec - 1, npair = s->nspec * (s->nspec + 1) / 2;
+    const float half[3] = { 0.5f * s->L[0], 0.5f * s->L[1], 0.5f * s->L[2] };
+    for (int i = 0; i < s->n - 1; i++)
+        for (int j = i + 1; j < s->n; j++) {
+            float d[3] = { s->x[i] - s->x[j], s->y[i] - s->y[j], s->z[i] - s->z[j] };
+            for (int a = 0; a < 3; a++) {
+                if (d[a] > half[a]) d[a] -= s->L[a];
+                else if (d[a] < -half[a]) d[a] += s->L[a];
+            }
+            float r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (r2 < r2max) {
+                int iR = (int)(sqrt((double)r2) * (double)idrdf);
+                int mn = s->type[i], mx = s->type[j];
+                if (mn > mx) { int t = mn; mn = mx; mx = t; }
+                int iPair = mn * m + mn * (1 - mn) / 2 + mx;
+                if (iR < nbins) counts[(size_t)iR * npair + iPair]++;
+            }
+        }
+    return 0;
+}

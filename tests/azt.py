@@ -47,6 +47,7 @@ def oracle_lib():
         lib.azo_pair_eval.restype = C.c_float
         lib.azo_pair_eval.argtypes = [C.c_int, _fp, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp]
+        lib.azo_rdf_counts.argtypes = [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_ulonglong), C.c_int]
         lib.azo_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         lib.azo_default_uvects.argtypes = [_dp, _dp, _dp]
         lib.azo_angled_vector.argtypes = [_fp, C.c_float, C.c_float, _fp]
@@ -65,6 +66,11 @@ def emu_lib():
 
 class Oracle:
     """CPU restatement of the reference's step (oracle/az_oracle.c)."""
+
+    def rdf_counts(self, r_max, dr, nbins, npair):
+        buf = np.zeros(nbins * npair, dtype=np.uint64)
+        self.lib.azo_rdf_counts(self._h, r_max, dr, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), nbins)
+        return buf.reshape(nbins, npair)
 
     def __init__(self, system):
         self.lib = oracle_lib()

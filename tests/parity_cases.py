@@ -428,6 +428,44 @@ def case_reset_vels(lib):
     e.close()
 
 
+def case_rdf_from_cells_equals_brute_force(lib):
+    """the cell-based RDF histogram holds exactly the pair counts of the reference's O(N^2) brute_rdf
+    (integers, so equality is exact), for one and two species, radii below and above the force cut-off, stale cells."""
+    cases = [(azt.lj_system(ncell=(9, 9, 9), seed=91), {}, 11.0, 0.05),                       # rRDF > rc: two cell layers
+             (azt.lj_system(ncell=(6, 6, 6), seed=92, cell_size=9.3), dict(rebuild_every=4, skin=0.8), 7.0, 0.1),  # stale cells
+             (azt.nacl_system(ncell=(5, 5, 5)), {}, 8.0, 0.02),                               # three species pairs
+             (azt.surk_system(n_side=6, spacing=1.3, box=35.0), {}, 8.0, 0.02)]               # case-study-2 geometry, 7 cells wide stencil
+    for s, kw, r_max, dr in cases:
+        o = azt.Oracle(s)
+        e = Engine(s, lib=lib, **kw)
+        e.rdf_begin(r_max, dr)
+        total = None
+        for k in range(3):
+            o.step(k, 1); e.step(k, 1)
+            e.rdf_sample()
+            counts, ns = e.rdf_counts()
+            ref = o.rdf_counts(r_max, dr, counts.shape[0], counts.shape[1])
+            total = ref if total is None else total + ref
+            assert ns == k + 1
+            if k == 0:
+                assert np.array_equal(counts, ref), (int(np.abs(counts.astype(np.int64) - ref.astype(np.int64)).sum()), int(ref.sum()))
+        # later steps: positions agree to rounding, a pair exactly on a bin edge may move by one bin
+        diff = np.abs(counts.astype(np.int64) - total.astype(np.int64))
+        assert diff.sum() <= 1e-4 * total.sum() + 4 and counts.sum() > 1000
+        assert abs(int(counts.sum()) - int(total.sum())) <= 2
+        e.close()
+    # a radius that would need more than one image of a cell is refused, not silently wrong
+    s = azt.lj_system(ncell=(4, 4, 4), seed=93)
+    e = Engine(s, lib=lib)
+    try:
+        e.rdf_begin(10.0, 0.1)
+    except AzError as err:
+        assert err.status == abi.AZ_ERR_UNSUPPORTED
+    else:
+        raise AssertionError("expected AZ_ERR_UNSUPPORTED")
+    e.close()
+
+
 def case_error_paths(lib):
     s = azt.lj_system(ncell=(3, 3, 3))
     s.cell_size = 0.0
@@ -479,6 +517,7 @@ ALL_CASES = [
     ("skin_violation", case_skin_violation_is_reported),
     ("download_upload", case_download_upload_roundtrip),
     ("determinism", case_determinism),
+    ("rdf_from_cells", case_rdf_from_cells_equals_brute_force),
     ("nose_hoover", case_nose_hoover),
     ("reset_vels", case_reset_vels),
     ("tile_kernel_variant", case_tile_kernel_variant),

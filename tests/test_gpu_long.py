@@ -151,6 +151,23 @@ def test_host_driver_lj_deck_outputs(lib, tmp_path):
     lib.az_deck_free(h)
 
 
+def test_host_driver_writes_rdf_dat(lib, tmp_path):
+    """'rdf rmax dr freq outfreq': rdf.dat in copy_rdf's layout; liquid-like argon: first peak near 1.1 sigma, g -> 1."""
+    d = str(tmp_path)
+    decks.lj_argon_deck(d, 12, nstep=300, stat=100, temperature=120.0, rdf_freq=10, rdf_rmax=12.0, rdf_dr=0.05, seed=9)
+    r = run_driver(d, "--seed", "9")
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = read_table(os.path.join(d, "rdf.dat"))
+    assert rows[0] == ["r", "Ar-Ar"] and len(rows) == 1 + int(12.0 / 0.05)
+    rr = np.array([float(x[0]) for x in rows[1:]])
+    g = np.array([float(x[1]) for x in rows[1:]])
+    assert rr[0] == pytest.approx(0.025) and rr[1] - rr[0] == pytest.approx(0.05)
+    assert g[rr < 3.0].max() == 0.0                       # excluded core
+    peak = rr[np.argmax(g)]
+    assert 3.5 < peak < 4.1 and g.max() > 2.0             # first shell of the (thermalising) fcc solid at 2^(1/6) sigma .. a/sqrt(2)
+    assert g[(rr > 10.5)].mean() == pytest.approx(1.0, abs=0.15)
+
+
 def test_host_driver_radiative_deck_outputs(lib, tmp_path):
     """A case-study-2-like deck (surk + radiative thermostat): tchars.dat and the engTerm column appear."""
     import test_deck
