@@ -754,7 +754,7 @@ az_k_rdf(const __grid_constant__ AzParams P, const __grid_constant__ AzRdfArgs A
                 const float4 pj = __ldg(A.pos + j);
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 if (code) { dx -= shx; dy -= shy; dz -= shz; }
-                const float r2 = dx * dx + dy * dy + dz * dz;
+                const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); // nvcc's contraction of dx*dx + dy*dy + dz*dz, as in the force kernels
                 if (r2 < A.r2max) {
                     const int iR = (int)(sqrt((double)r2) * (double)A.idrdf);
                     const int tj = __float_as_int(pj.w);

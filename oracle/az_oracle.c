@@ -872,7 +872,7 @@ int azo_rdf_counts(azo_state *s, float r_max, float dr, unsigned long long *coun
                 if (d[a] > half[a]) d[a] -= s->L[a];
                 else if (d[a] < -half[a]) d[a] += s->L[a];
             }
-            float r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            float r2 = fmaf(d[2], d[2], fmaf(d[0], d[0], d[1] * d[1])); /* nvcc contracts dx*dx + dy*dy + dz*dz like this (see the force path) */
             if (r2 < r2max) {
                 int iR = (int)(sqrt((double)r2) * (double)idrdf);
                 int mn = s->type[i], mx = s->type[j];
