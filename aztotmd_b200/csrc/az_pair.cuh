@@ -465,9 +465,12 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
     __shared__ double s_red[96];
+    __shared__ double s_kw[AZ_LIST_TPB / 32];
+    __shared__ int s_done;
     const int tid = threadIdx.x;
-    if (!SINGLE) {
-        for (int k = tid; k < P.nspec * P.nspec; k += AZ_LIST_TPB) s_tab[k] = A.table[k];
+    if (!SINGLE || A.fuse) { // all warps are here at the same time: this barrier costs nothing
+        for (int k = tid; k < P.nspec * P.nspec && !SINGLE; k += AZ_LIST_TPB) s_tab[k] = A.table[k];
+        if (tid == 0) s_done = 0;
         __syncthreads();
     }
     if (A.phase && ((A.phase == 1) == (A.blockFlag[blockIdx.x] != 0))) return; // the other phase owns this block
@@ -565,9 +568,20 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
     }
     if (A.fuse) {
-        double kk[1] = { ke };
-        az_block_sum<1>(kk, s_red);
-        if (tid == 0) A.partKE[blockIdx.x] = 0.5 * kk[0];
+        // no block barrier (ncu: 10 % of the stall samples sat on it): every warp leaves its sum in shared memory and
+        // retires; the LAST warp to arrive adds the four in a fixed order, so the block's partial is reproducible
+        const double kw = az_warp_sum(ke);
+        if ((tid & 31) == 0) {
+            s_kw[tid >> 5] = kw;
+            __threadfence_block();
+            if (atomicAdd(&s_done, 1) == AZ_LIST_TPB / 32 - 1) {
+                __threadfence_block();
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < AZ_LIST_TPB / 32; w++) t += ((volatile double*)s_kw)[w];
+                A.partKE[blockIdx.x] = 0.5 * t;
+            }
+        }
         if (A.fuse == 1 + AZ_IA_STALE) { // the fastest atom bounds the drift since the last rebuild
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, o));

@@ -210,6 +210,7 @@ static inline double atomicAdd(double* p, double v)
     memcpy(&f, &o, 8); return f;
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ----------------------------------------------------------------------------- math / bit casts
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
