@@ -14,7 +14,7 @@ AZ_MAX_SPECIES = 15
 AZ_N_UVECT = 3072
 AZ_N_MOM = 20
 AZ_MX_FRC = 1.0e4
-AZ_N_TIMERS = 7
+AZ_N_TIMERS = 8
 
 AZ_OK = 0
 AZ_ERR_INVALID, AZ_ERR_NO_DEVICE, AZ_ERR_CUDA, AZ_ERR_UNSUPPORTED = -1, -2, -3, -4
@@ -28,7 +28,7 @@ VDW_BY_NAME = {"lnjs": VDW_LJ, "buck": VDW_BUCK, "p746": VDW_P746, "bmhs": VDW_B
 ELEC_NONE, ELEC_DIRECT, ELEC_EWALD, ELEC_FENNEL = range(4)
 TSTAT_NONE, TSTAT_NOSE, TSTAT_RADI = range(3)
 ORDER_SORTED, ORDER_ORIGINAL = 0, 1
-TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo", "pair_list"]
+TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo", "pair_list", "ewald"]
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -63,6 +63,7 @@ class az_system_desc(C.Structure):
         ("r2_max", C.c_double), ("cell_size", C.c_double), ("efield", C.c_double * 3),
         ("global_ids", _ip), ("n_atoms_global", C.c_longlong),
         ("tstat_tau", C.c_double), ("reset_vels", C.c_int), ("reserved3", C.c_int),
+        ("ewald_k", C.c_int * 3), ("reserved4", C.c_int),
     ]
 
 
@@ -80,7 +81,7 @@ class az_stats(C.Structure):
                 ("posMom", C.c_float * 3), ("negMom", C.c_float * 3), ("pressure", C.c_float), ("x_first", C.c_float),
                 ("specAcBoxPos", (C.c_int * 3) * AZ_MAX_SPECIES), ("specAcBoxNeg", (C.c_int * 3) * AZ_MAX_SPECIES),
                 ("engKin_d", C.c_double), ("engVdW_d", C.c_double), ("engCoul1_d", C.c_double), ("engTemp_d", C.c_double),
-                ("n_pairs", C.c_longlong)]
+                ("n_pairs", C.c_longlong), ("engCoul3", C.c_float), ("reserved", C.c_float), ("engCoul2_d", C.c_double)]
 
 
 class az_atoms_out(C.Structure):

@@ -258,6 +258,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     // electrostatics (read_elec)
     int elec_kind = AZ_ELEC_NONE;
     double rReal = 0.0, alpha = 0.0;
+    int ewald_k[3] = { 0, 0, 0 };
     {
         char es[64] = "";
         if (!scan_first(f, " elec %63s", es)) DECK_FAIL(AZ_ERR_IO, "ERROR[401]: electrostatic calculations are not specified in control.txt. Use 'elec' directive!");
@@ -268,14 +269,13 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
             int kx, ky, kz;
             elec_kind = AZ_ELEC_EWALD;
             if (fscanf(f, " %lf %lf %d %d %d", &rReal, &alpha, &kx, &ky, &kz) != 5) DECK_FAIL(AZ_ERR_IO, "elec pme: missing parameters");
+            ewald_k[0] = kx; ewald_k[1] = ky; ewald_k[2] = kz;
         } else if (!strcmp(es, "fenn")) { elec_kind = AZ_ELEC_FENNEL; if (fscanf(f, " %lf %lf", &rReal, &alpha) != 2) DECK_FAIL(AZ_ERR_IO, "elec fenn: missing parameters"); }
         else DECK_FAIL(AZ_ERR_IO, "ERROR[404]: Unknown type of electrostatic calculations: %s.", es);
         if (!charged && elec_kind) {
             DECK_WARN("WARNING[b004] The species do not have charges, but electrostatic directive is %s. The electrostatic type is switched to none!", es);
             elec_kind = AZ_ELEC_NONE; // rReal stays set, like the reference (src/elec.cpp:52-57)
         }
-        if (elec_kind == AZ_ELEC_EWALD)
-            DECK_FAIL(AZ_ERR_UNSUPPORTED, "'elec pme': the reciprocal-space Ewald sum is outside the hot path and disabled in the reference's shipped build (USE_EWALD off, src/defines.h:18)");
     }
     double eps = 1.0;
     if (!scan_first(f, " permittivity %lf ", &eps)) { eps = 1.0; DECK_WARN("WARNING[131]: permittivity was not defined in control.txt file. used value of 1.0!"); }
@@ -401,6 +401,10 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     s.la = la; s.lb = lb; s.lc = lc;
     s.species = d->species.data(); s.vdw = d->vdw.data(); s.max_r_vdw = max_r_vdw;
     s.elec_kind = elec_kind; s.r_real = rReal; s.alpha = alpha; s.eps = eps;
+    if (elec_kind == AZ_ELEC_EWALD) { // prepare_elec, src/elec.cpp:376-397: the engine derives the k-space constants itself
+        s.daipi2 = 2 * alpha / kSqrtPi;
+        for (int a = 0; a < 3; a++) s.ewald_k[a] = ewald_k[a];
+    }
     if (elec_kind == AZ_ELEC_FENNEL) { // prepare_elec, src/elec.cpp:399-405
         double aRc = alpha * rReal;
         s.daipi2 = 2 * alpha / kSqrtPi;

@@ -4,6 +4,7 @@
 // src/cuPairs.cu:2519-2568, apply_tstat src/cuTemp.cu:775-803, md_to_host src/cuInit.cu:1212-1261,
 // free_device_md src/cuInit.cu:1263-1373).  There is no CPU fallback: without a CUDA device
 // az_engine_create fails with AZ_ERR_NO_DEVICE.
+#define AZ_EWALD_KERNELS
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -102,6 +103,7 @@ template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
 #define AZ_ALLOC(e, p, n) do { int rc_ = dev_alloc(e, &(p), (size_t)(n)); if (rc_) return rc_; } while (0)
 
 static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
+static int ewald_setup(az_engine* e, const az_system_desc* d, double qs[2]);
 static int dd_alloc(az_engine* e);
 static int dd_store_keep(az_engine* e, const az_system_desc* d);
 static void dd_free(az_engine* e);
@@ -319,7 +321,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     e->n_scan_tiles = (nc + AZ_SCAN_TILE - 1) / AZ_SCAN_TILE;
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
     e->n_atom_blocks = (capo + AZ_TPB - 1) / AZ_TPB;
-    e->n_ke_blocks = (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB; // >= n_atom_blocks: the list kernel may host the integrator
+    e->n_ke_blocks = std::max(e->n_atom_blocks, (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB); // the list kernel may host the integrator
     AZ_ALLOC(e, e->partKE, e->n_ke_blocks); AZ_ALLOC(e, e->partU, e->n_ke_blocks);
     // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
     // Pair path (pair_variant 0 = auto): between rebuilds always the Verlet list.  On the every-step schedule a large
@@ -364,7 +366,8 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     // cell tiles only, 2 = list, 3 = warp-per-atom sweep
     e->warp_nblocks = (capo + (AZ_WARP_TPB / 32) - 1) / (AZ_WARP_TPB / 32);
     e->use_warp = !e->use_list && pv != 1;
-    e->fuse_pair = e->use_list && !e->use_therm && !e->P.has_efield;
+    const bool ewald_rec = d->elec_kind == AZ_ELEC_EWALD && (d->ewald_k[0] > 0 || d->ewald_k[1] > 0 || d->ewald_k[2] > 0);
+    e->fuse_pair = e->use_list && !e->use_therm && !e->P.has_efield && !ewald_rec; // the k-space forces come after the pair pass
     if (e->fuse_pair) { AZ_ALLOC(e, e->pos_alt, capt); AZ_ALLOC(e, e->vel_alt, capt); }
     { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve all pair kernels
       if (e->warp_nblocks > np) np = e->warp_nblocks;
@@ -415,6 +418,12 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
         if (e->use_therm) AZ_CUDA(e, cudaMemcpy(e->therm[0], hth.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
     }
     if (e->dd) { rc = dd_init_counts(e, n); if (rc) return rc; }
+    if (ewald_rec) {
+        double qs[2] = { 0.0, 0.0 }; // sum q, sum q^2 over the atoms this rank keeps
+        for (int k = 0; k < n; k++) { const double q = d->species[d->types[src(k)]].charge; qs[0] += q; qs[1] += q * q; }
+        rc = ewald_setup(e, d, qs);
+        if (rc) return rc;
+    }
     e->cur = 0;
     e->binned = false;
     e->since_rebuild = 0;
@@ -429,6 +438,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     dd_free(e);
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
+    cudaFree(e->ew_kv); cudaFree(e->ew_kr); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
@@ -478,6 +488,94 @@ static bool step_rebuilds(const az_engine* e) { return !e->binned || e->rebuild_
 static bool is_eq_step(const az_engine* e, int step)
 {
     return e->n_eq && step <= e->n_eq && e->eq_freq > 0 && (step % e->eq_freq) == 0; // src/cuTemp.cu:777-779
+}
+
+// ---- reciprocal-space Ewald: host preparation (prepare_elec, src/elec.cpp:376-397) and the per-step launches
+static int ewald_setup(az_engine* e, const az_system_desc* d, double qs[2])
+{
+    const double kPiD = 3.14159265359, twopi = 2.0 * kPiD; // src/const.h:11-12
+    const double eps = d->eps != 0.0 ? d->eps : 1.0;
+    const double L[3] = { d->la, d->lb, d->lc };
+    const int kx = d->ewald_k[0], ky = d->ewald_k[1], kz = d->ewald_k[2];
+    if (kx < 1 || ky < 1 || kz < 1 || !(d->alpha > 0.0)) { AZ_SET_ERR(e, "elec pme: kx, ky, kz must be >= 1 and alpha > 0"); return AZ_ERR_INVALID; }
+    if (kx > 255 || ky > 255 || kz > 255) { AZ_SET_ERR(e, "elec pme: at most 255 k-vectors per axis"); return AZ_ERR_UNSUPPORTED; }
+    // the cut-off in k space: 1.05 * 2 pi * min(kx / a, ky / b, kz / c) (src/elec.cpp:383-393)
+    double rkcut = kx / L[0];
+    if (rkcut > ky / L[1]) rkcut = ky / L[1];
+    if (rkcut > kz / L[2]) rkcut = kz / L[2];
+    rkcut *= twopi * 1.05;
+    const double rkcut2 = rkcut * rkcut, mr4a2 = -0.25 / d->alpha / d->alpha;
+    std::vector<int4> kv; std::vector<float4> kr;
+    int mmin = 0, nmin = 1, pl = -1, pm = 0; // the reference's enumeration, src/elec.cpp:234-324
+    for (int l = 0; l < kx; l++) {
+        const double rkx = l * twopi / L[0];
+        for (int m = mmin; m < ky; m++) {
+            const double rky = m * twopi / L[1];
+            for (int n = nmin; n < kz; n++) {
+                const double rkz = n * twopi / L[2];
+                const double rk2 = rkx * rkx + rky * rky + rkz * rkz;
+                if (rk2 < rkcut2) {
+                    const int am = m < 0 ? -m : m, an = n < 0 ? -n : n;
+                    kv.push_back(make_int4(l, am | (m < 0 ? 256 : 0), an | (n < 0 ? 256 : 0), (l != pl || m != pm || kv.empty()) ? 1 : 0));
+                    kr.push_back(make_float4((float)rkx, (float)rky, (float)rkz, (float)(exp(rk2 * mr4a2) / rk2)));
+                    pl = l; pm = m;
+                }
+            }
+            nmin = 1 - kz;
+        }
+        mmin = 1 - ky;
+    }
+    const int nk = (int)kv.size();
+    if (nk == 0) { AZ_SET_ERR(e, "elec pme: no k-vector inside the cut-off"); return AZ_ERR_INVALID; }
+    if (nk > AZ_EW_MAX_K) { AZ_SET_ERR(e, "elec pme: %d k-vectors, at most %d are supported", nk, AZ_EW_MAX_K); return AZ_ERR_UNSUPPORTED; }
+    AzEwald& E = e->ew;
+    E.nk = nk; E.kx = kx > 1 ? kx : 2; E.ky = ky > 1 ? ky : 2; E.kz = kz > 1 ? kz : 2;
+    for (int a = 0; a < 3; a++) E.tpl[a] = (float)(twopi / L[a]);
+    const double scale = 2.0 * twopi / (L[0] * L[1] * L[2]) * (double)AZ_FCOUL_SCALE / eps; // Elec::scale, src/elec.cpp:380
+    E.escale = scale; E.fscale = (float)(2.0 * scale);                                  // Elec::scale2
+    AZ_ALLOC(e, e->ew_kv, nk); AZ_ALLOC(e, e->ew_kr, nk); AZ_ALLOC(e, e->ew_T, nk); AZ_ALLOC(e, e->ew_Sd, nk);
+    AZ_CUDA(e, cudaMemcpy(e->ew_kv, kv.data(), sizeof(int4) * nk, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->ew_kr, kr.data(), sizeof(float4) * nk, cudaMemcpyHostToDevice));
+    E.kv = e->ew_kv; E.kr = e->ew_kr;
+    const int ntiles = (e->cap + AZ_EW_TILE - 1) / AZ_EW_TILE;
+    e->ew_blocks = std::max(1, std::min(ntiles, 2 * (e->n_sm > 0 ? e->n_sm : 148)));
+    AZ_ALLOC(e, e->ew_part, (size_t)e->ew_blocks * nk);
+    e->ew_smem_s = sizeof(float2) * AZ_EW_TILE * (size_t)(E.kx + E.ky + E.kz);
+    e->ew_smem_f = sizeof(float2) * AZ_EW_FTPB * (size_t)(E.kx + E.ky + E.kz);
+    if (e->ew_smem_s > 200 * 1024) { AZ_SET_ERR(e, "elec pme: kx + ky + kz = %d does not fit the shared-memory tables (at most 200)", E.kx + E.ky + E.kz); return AZ_ERR_UNSUPPORTED; }
+#ifndef AZ_EMU
+    if (e->ew_smem_s > 48 * 1024) {
+        AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_s));
+        AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_f));
+    }
+#endif
+    // ewald_const (src/elec.cpp:144-165) from the global charge sums
+    if (e->dd) { int rc = dd_allreduce_host(e, qs, 2, false); if (rc) return rc; }
+    const double vol = L[0] * L[1] * L[2];
+    const double c3 = (double)AZ_FCOUL_SCALE * (-d->alpha / sqrt(kPiD) * qs[1] - 0.5 * kPiD * (qs[0] * qs[0] / d->alpha / d->alpha) / vol) / eps;
+    AZ_CUDA(e, cudaMemcpy(&e->sc->engCoul3, &c3, sizeof(double), cudaMemcpyHostToDevice));
+    return AZ_OK;
+}
+
+// add_elec of the step (src/main.cpp:99; src/main.cu:330-336 in the CUDA twin): k-space forces onto frc, engCoul2
+static int ewald_step(az_engine* e, int c)
+{
+    Timer t(e, AZ_TIMER_EWALD);
+    cudaStream_t st = e->stream;
+    const AzEwald& E = e->ew;
+    AZ_LAUNCH(az_k_ewald_sfac, e->ew_blocks, AZ_EW_TPB, e->ew_smem_s, st, e->P, E, e->pos[c], e->ew_part);
+    if (e->dd) { // the structure factor is a sum over all atoms of all bricks
+        AZ_LAUNCH(az_k_ewald_reduce, 1, 1024, 0, st, E, e->ew_part, e->ew_blocks, e->ew_Sd, e->ew_T, &e->sc->engCoul2, 0);
+        int rc = dd_allreduce_dev(e, (double*)e->ew_Sd, 2 * E.nk, st);
+        if (rc) return rc;
+        AZ_LAUNCH(az_k_ewald_reduce, 1, 1024, 0, st, E, e->ew_part, e->ew_blocks, e->ew_Sd, e->ew_T, &e->sc->engCoul2, 2);
+        AZ_COUNT(e, AZ_TIMER_EWALD, 1);
+    } else
+        AZ_LAUNCH(az_k_ewald_reduce, 1, 1024, 0, st, E, e->ew_part, e->ew_blocks, e->ew_Sd, e->ew_T, &e->sc->engCoul2, 1);
+    const int nb = (e->cap + AZ_EW_FTPB - 1) / AZ_EW_FTPB;
+    AZ_LAUNCH(az_k_ewald_force, nb, AZ_EW_FTPB, e->ew_smem_f, st, e->P, E, e->pos[c], e->ew_T, e->frc);
+    AZ_COUNT(e, AZ_TIMER_EWALD, 3);
+    return AZ_OK;
 }
 
 // One MD step.  skip_a: this step's first half kick + drift was already done by the fused kernel of the
@@ -592,6 +690,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             e->clear_counts_bytes = 0;
         }
     }
+    if (e->ew.nk) { int rc = ewald_step(e, c); if (rc) return rc; }
     if (ride) {
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
@@ -727,7 +826,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     o->step = e->last_step;
     o->n_atoms_total = e->n_global;
     o->engTot = h.engTot; o->engKin = h.engKin_f; o->engVdW = (float)h.engVdW; o->engCoul1 = (float)h.engCoul1;
-    o->engCoul2 = 0.f; o->engTemp = (float)h.engTemp; o->engElecField = (float)h.engElecField; o->engPot = h.engPot;
+    o->engCoul2 = (float)h.engCoul2; o->engCoul3 = (float)h.engCoul3; o->engCoul2_d = h.engCoul2; o->engTemp = (float)h.engTemp; o->engElecField = (float)h.engElecField; o->engPot = h.engPot;
     for (int a = 0; a < 3; a++) { o->posMom[a] = (float)h.posMom[a]; o->negMom[a] = (float)h.negMom[a]; }
     o->pressure = h.pressure;
     o->x_first = h.x_first;

@@ -4,6 +4,7 @@
 #include <vector>
 #include <string.h>
 #include "az_pair.cuh"
+#include "az_ewald.cuh"
 
 static inline float __int_as_float_host(int i) { float f; memcpy(&f, &i, 4); return f; }
 
@@ -58,6 +59,11 @@ struct az_engine {
     double *partKE = nullptr, *partU = nullptr, *partV = nullptr, *partC = nullptr;
     unsigned long long* partN = nullptr;
     int n_pair_partials = 0;
+    // reciprocal-space Ewald (az_ewald.cuh); ew.nk == 0: off
+    AzEwald ew = {};
+    int4* ew_kv = nullptr; float4* ew_kr = nullptr; float2 *ew_part = nullptr, *ew_T = nullptr; double2* ew_Sd = nullptr;
+    int ew_blocks = 0;
+    size_t ew_smem_s = 0, ew_smem_f = 0;
     // az_engine_upload staging: two buffers of 6*n doubles filled on a copy stream, so that the H2D copy of the
     // next upload overlaps the kernels of the current step (az_engine_upload_async)
     double* stage2[2] = { nullptr, nullptr };

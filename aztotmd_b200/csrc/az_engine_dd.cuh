@@ -73,6 +73,14 @@ static int dd_allreduce_host(az_engine* e, double* v, int n, bool take_max)
     return AZ_OK;
 }
 
+// in place, device memory, asynchronous on `st`: sum over the ranks
+static int dd_allreduce_dev(az_engine* e, double* dev, int n, cudaStream_t st)
+{
+    int rc = e->dd->comm->allreduce(dev, n, false, st);
+    if (rc) e->err = e->dd->comm->err;
+    return rc;
+}
+
 // the brick grid with the smallest halo surface among the factorisations of n_ranks that fit
 static bool dd_pick_grid(const AzGrid& g, int nr, int pg[3])
 {
@@ -364,7 +372,7 @@ static int dd_reduce_stats(az_engine* e, az_stats* o, int* flags)
     for (int b = 0; b < 5; b++) if (v[k++] > 0.5) f |= 1 << b;
     *flags = f;
     o->engKin = (float)o->engKin_d; o->engVdW = (float)o->engVdW_d; o->engCoul1 = (float)o->engCoul1_d; o->engTemp = (float)o->engTemp_d;
-    o->engPot = o->engCoul1 + o->engVdW; // calc_quantities, src/main.cu:121-162
+    o->engPot = o->engCoul1 + o->engCoul2 + o->engCoul3 + o->engVdW; // calc_quantities, src/main.cu:121-162 (the k-space terms are global on every rank)
     o->engTot = o->engPot + o->engKin;
     return AZ_OK;
 }

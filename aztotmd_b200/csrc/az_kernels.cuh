@@ -48,6 +48,7 @@ struct AzScalars {
     int acPos[AZ_MAX_SPECIES][3], acNeg[AZ_MAX_SPECIES][3];
     double engElecField;                      // per step
     double engKin, engVdW, engCoul1, engTemp; // per step, reduced
+    double engCoul2, engCoul3;                // Ewald: reciprocal-space energy (az_k_ewald_reduce, every step), constant term (set once)
     float engKin_f;                           // after after_tscale
     float posMomBuf[AZ_N_MOM][3], negMomBuf[AZ_N_MOM][3];
     int iMom;
@@ -522,7 +523,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, 
         sc->engKin_f = P.teKin; sc->engKin = (double)P.teKin; // after_tscale, src/cuTemp.cu:109-113
     }
     if (mode & 16) {
-        float engCoulTot = (float)sc->engCoul1;
+        float engCoulTot = (float)sc->engCoul1 + (float)sc->engCoul2 + (float)sc->engCoul3; // src/main.cu:127
         sc->engPot = engCoulTot + (float)sc->engVdW;
         sc->engTot = sc->engPot + sc->engKin_f;
         float pm[3] = { (float)sc->posMom[0], (float)sc->posMom[1], (float)sc->posMom[2] };

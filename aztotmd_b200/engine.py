@@ -82,6 +82,7 @@ class System:
     n_atoms_global: int = 0
     tstat_tau: float = 0.0   # Nose-Hoover relaxation time, ps ('temperature T nose tau')
     reset_vels: int = 0      # every n-th step: zero the velocities instead of the second half kick
+    ewald_k: Sequence[int] = (0, 0, 0)  # 'elec pme rc alpha kx ky kz': reciprocal-space Ewald when any is > 0
 
     def set_vdw(self, i: int, j: int, kind: str, rcut: float, params: Sequence[float]):
         e = prepare_vdw(kind, rcut, params)
@@ -231,6 +232,8 @@ class DescHolder:
         d.n_atoms_global = int(s.n_atoms_global)
         d.tstat_tau = float(s.tstat_tau)
         d.reset_vels = int(s.reset_vels)
+        for a in range(3):
+            d.ewald_k[a] = int(s.ewald_k[a]) if ek == abi.ELEC_EWALD else 0
         self.desc = d
 
 

@@ -48,6 +48,9 @@ WORKLOADS = {
     "lj32k": (20, "synthetic fcc LJ argon, 32,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     # BASELINE config 3 of the ionic kind: rock-salt NaCl-like melt, Buckingham + real-space Coulomb (DSF), 1 000 000 ions
     "nacl1m": (-50, "synthetic NaCl-like ionic melt, 1,000,000 ions (50^3 rock-salt cells, a = 5.9 A), Buckingham rc 9 A + DSF Coulomb rc 12 A alpha 0.2, 1200 K"),
+    # the full Ewald sum ('elec pme 12 0.2 8 8 8': real space + 8x15x15 half space of k-vectors inside the cut-off + constant)
+    "nacl64k_pme": (-20.5, "synthetic NaCl-like ionic melt, 64,000 ions (20^3 rock-salt cells), Buckingham rc 9 A + Ewald sum: real space rc 12 A alpha 0.2, reciprocal space kx=ky=kz=8"),
+    "nacl1m_pme": (-50.5, "synthetic NaCl-like ionic melt, 1,000,000 ions, Buckingham rc 9 A + Ewald sum: real space rc 12 A alpha 0.2, reciprocal space kx=ky=kz=8 (the reference's k-vector budget, not a converged sum at this box size)"),
     # latency-bound decks of the reference (BASELINE configs 0 and 1), rebuilt synthetically (the shipped files cannot travel)
     "cs1": (0, "case-study-1-like: 40,000 argon atoms, dilute gas in a 1141.5 A box, LJ rc 4.0 A, cell_list 85, radiative thermostat 298 K"),
     "cs2": (0, "case-study-2-like: 4,000 abstract atoms, 35 A box, surk rc 6.0 A + radii, cell_list 2.7, radiative thermostat 500 K"),
@@ -70,12 +73,14 @@ def lj_system(ncell, rebuild, skin, seed=12345, cell_div=1):
 
 def ionic_system(ncell, rebuild, skin, seed=2):
     from aztotmd_b200 import abi
+    pme = ncell != int(ncell)  # x.5: the same box with the full Ewald sum
+    ncell = int(ncell)
     from aztotmd_b200.decks import rocksalt_positions
     from aztotmd_b200.engine import Species, System
     pos, types, box = rocksalt_positions((ncell,) * 3, 5.9, jitter=0.05, seed=seed)
     s = System(pos=pos, types=types.astype(np.int32), box=box, species=[Species("Na", 22.99, 1.0), Species("Cl", 35.45, -1.0)],
-               timestep=0.001, cell_size=12.0 + (skin if rebuild > 1 else 0.0), elec_kind=abi.ELEC_FENNEL, r_real=12.0, alpha=0.2,
-               temperature=1200.0, seed=seed)
+               timestep=0.001, cell_size=12.0 + (skin if rebuild > 1 else 0.0), elec_kind=abi.ELEC_EWALD if pme else abi.ELEC_FENNEL, r_real=12.0, alpha=0.2,
+               temperature=1200.0, seed=seed, ewald_k=(8, 8, 8) if pme else (0, 0, 0))
     s.set_vdw(0, 0, "buck", 9.0, [424.097, 0.317, 1.05])
     s.set_vdw(0, 1, "buck", 9.0, [1256.31, 0.317, 7.00])
     s.set_vdw(1, 1, "buck", 9.0, [3488.998, 0.317, 72.40])
@@ -223,6 +228,7 @@ def main():
     ap.add_argument("--rebuild", type=int, default=10)
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--pair-variant", type=int, default=0, help="0 auto (Verlet list between rebuilds), 1 cell tiles only")
+    ap.add_argument("--option", action="append", default=[], help="engine option key=value (az_engine_set_option), for A/B runs")
     ap.add_argument("--list-dbg", type=int, default=0, help="diagnostic variants of the list pass (results are NOT physical)")
     ap.add_argument("--no-halo-overlap", action="store_true", help="multi-GPU: refresh the ghosts on the engine's stream (A/B of the overlap)")
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
@@ -234,7 +240,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncell, desc = WORKLOADS[args.workload]
-    n_atoms = 4 * ncell ** 3 if ncell > 0 else (8 * (-ncell) ** 3 if ncell < 0 else (40000 if args.workload == "cs1" else 4000))
+    n_atoms = 4 * ncell ** 3 if ncell > 0 else (8 * int(-ncell) ** 3 if ncell < 0 else (40000 if args.workload == "cs1" else 4000))
     config = {"workload": "%s; cell_list = rc%s; rebuild every %d steps; dt = 1 fs; NVE" % (
         desc, " + skin %.2f A" % args.skin if args.rebuild > 1 else "", args.rebuild),
         "n_atoms": n_atoms, "rebuild_every": args.rebuild, "skin": args.skin if args.rebuild > 1 else 0.0,
@@ -277,6 +283,9 @@ def main():
     e = Engine(s, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0, pair_variant=args.pair_variant)
     if args.list_dbg:
         e.set_option("list_dbg", args.list_dbg)
+    for kv in args.option:
+        k, v = kv.split("=")
+        e.set_option(k, float(v))
     K, W = args.steps, args.warmup
     e.step(0, W)
     st = e.stats()  # also surfaces skin/overflow errors early
@@ -301,7 +310,7 @@ def main():
     rest_ms = (tm["integrate_a"]["ms"] + tm["integrate_b"]["ms"] + tm["scan"]["ms"] + tm["sort"]["ms"]) / K
     # algorithmic flop per unique in-range pair: LJ 30; Buckingham + DSF 66 (each transcendental counted as 8);
     # surk 44 (30 - 9 for LJ's polynomial + sqrt and 4 divisions at ~5 each + 3)
-    flop_per_pair = {"nacl1m": 66.0, "cs2": 44.0}.get(args.workload, FLOP_PER_PAIR)
+    flop_per_pair = {"nacl1m": 66.0, "nacl1m_pme": 66.0, "nacl64k_pme": 66.0, "cs2": 44.0}.get(args.workload, FLOP_PER_PAIR)
     flops_per_launch = flop_per_pair * st.n_pairs
     rides = dom == "pair_list" and args.workload not in ("cs1", "cs2")  # thermostat-free: the integrator rides on the list kernel
     if rides:

@@ -70,7 +70,7 @@ typedef enum az_vdw_kind {
 typedef enum az_elec_kind {
     AZ_ELEC_NONE = 0,   /* no_coul      src/cuElec.cu:20     */
     AZ_ELEC_DIRECT = 1, /* direct_coul  src/cuElec.cu:27-37  */
-    AZ_ELEC_EWALD = 2,  /* real_ewald   src/cuElec.cu:94-113 (real-space part only) */
+    AZ_ELEC_EWALD = 2,  /* real_ewald   src/cuElec.cu:94-113; + reciprocal space if az_system_desc.ewald_k is set */
     AZ_ELEC_FENNEL = 3  /* fennel (DSF) src/cuElec.cu:115-134 */
 } az_elec_kind;
 
@@ -154,6 +154,13 @@ typedef struct az_system_desc {
     double tstat_tau;          /* TStat::tau ('temperature T nose tau'); rQmass = 0.5 / tKin / tau^2, qMassTau2 = 2 tKin */
     int reset_vels;            /* Sim::reset_vels: every n-th step velocities are zeroed instead of the 2nd half kick (src/main.cu:372-377) */
     int reserved3;
+    /* reciprocal-space part of the Ewald sum ('elec pme rc alpha kx ky kz', src/elec.cpp:47-51).  With
+     * elec_kind == AZ_ELEC_EWALD and any ewald_k > 0 the engine adds the k-space forces and energies of ewald_rec
+     * (src/elec.cpp:167-336; the CUDA twin recip_ewald / ewald_force, src/cuElec.cu:151-381, is compiled out of the
+     * reference by defines.h:18) and the constant term of ewald_const (src/elec.cpp:144-165).  All zero: real-space
+     * part only, as the reference's CUDA build does. */
+    int ewald_k[3];            /* Elec::kx, ky, kz: l in [0,kx), m in (-ky,ky), n in (-kz,kz) */
+    int reserved4;
 } az_system_desc;
 
 /* cuda.txt-level options plus the multi-GPU layout.  Zero-initialise for defaults. */
@@ -188,6 +195,9 @@ typedef struct az_stats {
     int specAcBoxNeg[AZ_MAX_SPECIES][3];
     double engKin_d, engVdW_d, engCoul1_d, engTemp_d; /* unrounded accumulators */
     long long n_pairs;   /* unique pairs inside r2Max seen by the last energy-reducing force pass */
+    float engCoul3;      /* Ewald: constant term (ewald_const, src/elec.cpp:144-165); engCoul2 = reciprocal-space energy */
+    float reserved;
+    double engCoul2_d;
 } az_stats;
 
 #define AZ_ORDER_SORTED 0   /* cell-sorted order, what md_to_host hands back */
@@ -279,7 +289,8 @@ int az_engine_rdf_read(az_engine *e, unsigned long long *counts, int capacity, i
 #define AZ_TIMER_INTEGRATE_B 4 /* verlet_2stage + thermostat + quantities  */
 #define AZ_TIMER_HALO 5        /* multi-GPU halo / migration               */
 #define AZ_TIMER_PAIR_LIST 6   /* Verlet-list force pass between rebuilds  */
-#define AZ_N_TIMERS 7
+#define AZ_TIMER_EWALD 7       /* reciprocal-space Ewald (ewald_rec)       */
+#define AZ_N_TIMERS 8
 int az_engine_profile(az_engine *e, int enable);
 int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
 long long az_engine_launch_count(az_engine *e); /* kernels launched since create */

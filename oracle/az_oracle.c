@@ -26,6 +26,8 @@
  *   host narrowing       init_cudaMD            src/cuInit.cu:768-791,934-961
  *                        init_cuda_tstat        src/cuTemp.cu:11-62
  *   unit vectors         read_tstat             src/temperature.cpp:164-223
+ *   k-space Ewald        ewald_rec, ewald_const, prepare_elec   src/elec.cpp:144-165,167-336,376-397 (the serial
+ *                        twin, double precision: the CUDA twin src/cuElec.cu:151-381 is compiled out, defines.h:18)
  *
  * Deliberate, documented divergences from reference behaviour:
  *   - within-cell order is canonical (ascending persistent id) instead of atomicAdd
@@ -302,11 +304,18 @@ typedef struct azo_state {
     float pressure, engTot, engPot;
     int last_step;
     long long n_pairs_in_range; /* unique in-cutoff pairs of the last force evaluation */
+    /* reciprocal-space Ewald: Elec::kx,ky,kz, alpha, eps and the double box, as the serial twin keeps them */
+    int ew_k[3];
+    double ew_alpha, ew_eps, boxd[3];
+    double engCoul2, engCoul3;
+    float *frx, *fry, *frz; /* the k-space force of the last evaluation alone (sorted order), for the parity tests */
 } azo_state;
 
 static void *xmalloc(size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) { fprintf(stderr, "azo: oom\n"); abort(); } return p; }
 
 void azo_default_uvects(double *ux, double *uy, double *uz);
+
+double azo_ewald_const(int n, const int *types, const az_species *sp, double alpha, double eps, double vol);
 
 azo_state *azo_create(const az_system_desc *d)
 {
@@ -382,6 +391,13 @@ azo_state *azo_create(const az_system_desc *d)
         for (int k = 0; k < AZ_N_UVECT; k++) { s->uv[3 * k] = (float)ux[k]; s->uv[3 * k + 1] = (float)uy[k]; s->uv[3 * k + 2] = (float)uz[k]; }
         free(ux);
     }
+    for (int a = 0; a < 3; a++) s->ew_k[a] = (d->elec_kind == AZ_ELEC_EWALD) ? d->ewald_k[a] : 0;
+    s->ew_alpha = d->alpha; s->ew_eps = d->eps != 0.0 ? d->eps : 1.0;
+    s->boxd[0] = d->la; s->boxd[1] = d->lb; s->boxd[2] = d->lc;
+    if (s->ew_k[0] > 0 || s->ew_k[1] > 0 || s->ew_k[2] > 0) {
+        s->frx = (float *)xmalloc(sizeof(float) * n); s->fry = (float *)xmalloc(sizeof(float) * n); s->frz = (float *)xmalloc(sizeof(float) * n);
+        s->engCoul3 = azo_ewald_const(n, d->types, d->species, d->alpha, s->ew_eps, d->la * d->lb * d->lc);
+    }
     s->last_step = -1;
     return s;
 }
@@ -394,6 +410,7 @@ void azo_destroy(azo_state *s)
     for (int k = 0; k < 11; k++) free(s->t_f[k]);
     free(s->type); free(s->id); free(s->cell); free(s->order); free(s->t_i[0]); free(s->t_i[1]);
     free(s->first); free(s->count);
+    free(s->frx); free(s->fry); free(s->frz);
     free(s);
 }
 
@@ -574,6 +591,125 @@ static void forces(azo_state *s)
     s->n_pairs_in_range = npairs / 2;
 }
 
+/* ------------------------------------------------- reciprocal-space Ewald ---- */
+#define FCOUL_SCALE_D 14.3996 /* the engine's Coulomb constant (d_Fcoul_scale, src/main.cu:40); the serial twin's
+                               * Fcoul_scale (src/const.h:44) is the same number to 6 digits */
+#define PI_D 3.14159265359    /* src/const.h:11 */
+
+/* ewald_const (src/elec.cpp:144-165): the self-energy and the charged-system term, computed once */
+double azo_ewald_const(int n, const int *types, const az_species *sp, double alpha, double eps, double vol)
+{
+    double sq = 0.0, eng = 0.0;
+    for (int i = 0; i < n; i++) { double q = sp[types[i]].charge; sq += q; eng += q * q; }
+    eng *= -alpha / sqrt(PI_D);
+    double q = -0.5 * PI_D * (sq * sq / alpha / alpha) / vol;
+    return FCOUL_SCALE_D * (eng + q) / eps;
+}
+
+/* The k-vectors of ewald_rec in its own enumeration order (src/elec.cpp:234-324): l in [0,kx), m from 0 (l = 0) or
+ * 1-ky, n from 1 (l = m = 0 ... the reference's nmin/mmin switches) or 1-kz, kept if |k|^2 < rkcut2 with
+ * rkcut = 1.05 * 2 pi * min(kx/a, ky/b, kz/c) (prepare_elec, src/elec.cpp:383-393).  Returns the count;
+ * lmn[3*k..], rk[3*k..] and ak[k] = exp(-|k|^2/(4 alpha^2))/|k|^2 are filled up to cap entries. */
+int azo_ewald_kvecs(double la, double lb, double lc, double alpha, int kx, int ky, int kz, int cap, int *lmn, double *rk, double *ak)
+{
+    const double twopi = 2.0 * PI_D;
+    const double ra = 1.0 / la, rb = 1.0 / lb, rc = 1.0 / lc;
+    double rkcut = kx * ra;
+    if (rkcut > ky * rb) rkcut = ky * rb;
+    if (rkcut > kz * rc) rkcut = kz * rc;
+    rkcut *= twopi * 1.05;
+    const double rkcut2 = rkcut * rkcut, mr4a2 = -0.25 / alpha / alpha;
+    int mmin = 0, nmin = 1, ik = 0;
+    for (int l = 0; l < kx; l++) {
+        double rkx = l * twopi * ra;
+        for (int m = mmin; m < ky; m++) {
+            double rky = m * twopi * rb;
+            for (int n = nmin; n < kz; n++) {
+                double rkz = n * twopi * rc;
+                double rk2 = rkx * rkx + rky * rky + rkz * rkz;
+                if (rk2 < rkcut2) {
+                    if (ik < cap) {
+                        if (lmn) { lmn[3 * ik] = l; lmn[3 * ik + 1] = m; lmn[3 * ik + 2] = n; }
+                        if (rk) { rk[3 * ik] = rkx; rk[3 * ik + 1] = rky; rk[3 * ik + 2] = rkz; }
+                        if (ak) ak[ik] = exp(rk2 * mr4a2) / rk2;
+                    }
+                    ik++;
+                }
+            }
+            nmin = 1 - kz;
+        }
+        mmin = 1 - ky;
+    }
+    return ik;
+}
+
+/* ewald_rec (src/elec.cpp:167-336) on the current (float) positions, in double like the serial twin: structure factor
+ * S(k) = sum_i q_i exp(i k r_i), energy scale * sum_k ak |S|^2 with scale = 4 pi Fcoul / (V eps), force on atom i
+ * 2 scale * sum_k ak (Im c_ik Re S - Re c_ik Im S) k, c_ik = q_i exp(i k r_i).  exp(i k r) is built from
+ * exp(i 2 pi x/a) by repeated complex multiplication exactly as the reference fills its elc/emc/enc tables. */
+static void ewald_rec(azo_state *s)
+{
+    const int kx = s->ew_k[0], ky = s->ew_k[1], kz = s->ew_k[2], n = s->n;
+    if (kx <= 0 && ky <= 0 && kz <= 0) return;
+    const double twopi = 2.0 * PI_D;
+    int nk = azo_ewald_kvecs(s->boxd[0], s->boxd[1], s->boxd[2], s->ew_alpha, kx, ky, kz, 0, NULL, NULL, NULL);
+    int *lmn = (int *)xmalloc(sizeof(int) * 3 * nk);
+    double *rk = (double *)xmalloc(sizeof(double) * 3 * nk), *ak = (double *)xmalloc(sizeof(double) * nk);
+    azo_ewald_kvecs(s->boxd[0], s->boxd[1], s->boxd[2], s->ew_alpha, kx, ky, kz, nk, lmn, rk, ak);
+    const int K[3] = { kx > 1 ? kx : 2, ky > 1 ? ky : 2, kz > 1 ? kz : 2 };
+    double *tc[3], *ts[3];
+    for (int a = 0; a < 3; a++) { tc[a] = (double *)xmalloc(sizeof(double) * n * K[a]); ts[a] = (double *)xmalloc(sizeof(double) * n * K[a]); }
+    const float *pos[3] = { s->x, s->y, s->z };
+    for (int a = 0; a < 3; a++)
+        for (int i = 0; i < n; i++) {
+            double *c = tc[a] + (size_t)i * K[a], *sn = ts[a] + (size_t)i * K[a];
+            c[0] = 1.0; sn[0] = 0.0;
+            double ang = twopi * (double)pos[a][i] / s->boxd[a];
+            c[1] = cos(ang); sn[1] = sin(ang);
+            for (int l = 2; l < K[a]; l++) { c[l] = c[l - 1] * c[1] - sn[l - 1] * sn[1]; sn[l] = sn[l - 1] * c[1] + c[l - 1] * sn[1]; }
+        }
+    const double scale = 2.0 * twopi / (s->boxd[0] * s->boxd[1] * s->boxd[2]) * FCOUL_SCALE_D / s->ew_eps, scale2 = 2.0 * scale;
+    double *ckc = (double *)xmalloc(sizeof(double) * n), *cks = (double *)xmalloc(sizeof(double) * n);
+    double *fx = (double *)xmalloc(sizeof(double) * n), *fy = (double *)xmalloc(sizeof(double) * n), *fz = (double *)xmalloc(sizeof(double) * n);
+    double eng = 0.0;
+    for (int k = 0; k < nk; k++) {
+        const int l = lmn[3 * k], m = lmn[3 * k + 1], nn = lmn[3 * k + 2];
+        const int am = m < 0 ? -m : m, an = nn < 0 ? -nn : nn;
+        const double sm = m < 0 ? -1.0 : 1.0, sn_ = nn < 0 ? -1.0 : 1.0; /* negative index: complex conjugate */
+        double sumC = 0.0, sumS = 0.0;
+        for (int i = 0; i < n; i++) {
+            const double ch = (double)s->charge[s->type[i]];
+            const double elc = tc[0][(size_t)i * K[0] + l], els = ts[0][(size_t)i * K[0] + l];
+            const double emc = tc[1][(size_t)i * K[1] + am], ems = sm * ts[1][(size_t)i * K[1] + am];
+            const double enc = tc[2][(size_t)i * K[2] + an], ens = sn_ * ts[2][(size_t)i * K[2] + an];
+            const double lmc = elc * emc - els * ems, lms = els * emc + ems * elc;
+            ckc[i] = ch * (lmc * enc - lms * ens);
+            cks[i] = ch * (lms * enc + lmc * ens);
+            sumC += ckc[i]; sumS += cks[i];
+        }
+        eng += ak[k] * (sumC * sumC + sumS * sumS);
+        for (int i = 0; i < n; i++) {
+            const double x = ak[k] * (cks[i] * sumC - ckc[i] * sumS) * scale2;
+            fx[i] += rk[3 * k] * x; fy[i] += rk[3 * k + 1] * x; fz[i] += rk[3 * k + 2] * x;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        s->frx[i] = (float)fx[i]; s->fry[i] = (float)fy[i]; s->frz[i] = (float)fz[i];
+        s->fx[i] += s->frx[i]; s->fy[i] += s->fry[i]; s->fz[i] += s->frz[i];
+    }
+    s->engCoul2 = scale * eng;
+    for (int a = 0; a < 3; a++) { free(tc[a]); free(ts[a]); }
+    free(lmn); free(rk); free(ak); free(ckc); free(cks); free(fx); free(fy); free(fz);
+}
+
+/* the k-space force of the last force evaluation alone, sorted order */
+int azo_ewald_forces(azo_state *s, float *fx, float *fy, float *fz)
+{
+    if (!s->frx) return AZ_ERR_INVALID;
+    memcpy(fx, s->frx, sizeof(float) * s->n); memcpy(fy, s->fry, sizeof(float) * s->n); memcpy(fz, s->frz, sizeof(float) * s->n);
+    return 0;
+}
+
 /* -------------------------------------------------------------- stage 2 ---- */
 static void stage2(azo_state *s)
 {
@@ -712,7 +848,7 @@ static void apply_tstat(azo_state *s, int step)
 /* calc_quantities, src/main.cu:121-162 */
 static void calc_quantities(azo_state *s, int step)
 {
-    float engCoulTot = (float)s->engCoul1;
+    float engCoulTot = (float)s->engCoul1 + (float)s->engCoul2 + (float)s->engCoul3; /* src/main.cu:127 */
     s->engPot = engCoulTot + (float)s->engVdW;
     s->engTot = s->engPot + s->engKin_f;
     float pm[3] = { (float)s->posMom[0], (float)s->posMom[1], (float)s->posMom[2] };
@@ -744,6 +880,7 @@ int azo_step(azo_state *s, int first_step, int nsteps)
         stage1(s);
         sort_atoms(s);
         forces(s);
+        ewald_rec(s);                                     /* add_elec, src/main.cpp:99 (src/main.cu:330-336) */
         if (s->reset_vels && step % s->reset_vels == 0) { /* zero_vel, src/main.cu:372-374, src/cuMDfunc.cu:602-622 */
             for (int i = 0; i < s->n; i++) { s->vx[i] = 0.f; s->vy[i] = 0.f; s->vz[i] = 0.f; }
             s->engKin = 0.0; s->engKin_f = 0.f;
@@ -768,6 +905,7 @@ int azo_forces_only(azo_state *s)
     }
     sort_atoms(s);
     forces(s);
+    ewald_rec(s);
     return 0;
 }
 
@@ -776,7 +914,7 @@ int azo_stats(azo_state *s, az_stats *o)
     memset(o, 0, sizeof(*o));
     o->step = s->last_step; o->n_atoms_total = s->n;
     o->engTot = s->engTot; o->engKin = s->engKin_f; o->engVdW = (float)s->engVdW;
-    o->engCoul1 = (float)s->engCoul1; o->engCoul2 = 0.f; o->engTemp = (float)s->engTemp;
+    o->engCoul1 = (float)s->engCoul1; o->engCoul2 = (float)s->engCoul2; o->engCoul3 = (float)s->engCoul3; o->engCoul2_d = s->engCoul2; o->engTemp = (float)s->engTemp;
     o->engElecField = (float)s->engElecField; o->engPot = s->engPot;
     for (int a = 0; a < 3; a++) { o->posMom[a] = (float)s->posMom[a]; o->negMom[a] = (float)s->negMom[a]; }
     o->pressure = s->pressure;

@@ -102,8 +102,9 @@ int main(int argc, char** argv)
     double t3 = now();
     if (df) { dump(df, "final", atoms, sim); fclose(df); }
     printf("{\"n_atoms\": %d, \"nsteps\": %d, \"init_s\": %.6f, \"loop_s\": %.6f, \"s_per_step\": %.9f, "
-           "\"atom_steps_per_s\": %.6e, \"engVdW\": %.10e, \"engCoul\": %.10e, \"engKin\": %.10e, \"n_cells\": %d}\n",
+           "\"atom_steps_per_s\": %.6e, \"engVdW\": %.10e, \"engCoul\": %.10e, \"engKin\": %.10e, \"n_cells\": %d, "
+           "\"engElec1\": %.10e, \"engElec2\": %.10e}\n",
            atoms->nAt, nsteps, t1 - t0, t3 - t2, nsteps ? (t3 - t2) / nsteps : 0.0,
-           nsteps ? (double)atoms->nAt * nsteps / (t3 - t2) : 0.0, sim->engVdW, sim->engElec3, sim->engKin, sim->nHead);
+           nsteps ? (double)atoms->nAt * nsteps / (t3 - t2) : 0.0, sim->engVdW, sim->engElec3, sim->engKin, sim->nHead, sim->engElec1, sim->engElec2);
     return 0;
 }

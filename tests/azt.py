@@ -193,13 +193,13 @@ def lj_system(ncell=(4, 4, 4), rho_star=0.8442, rc_sigma=2.5, temperature=86.6, 
 
 
 def nacl_system(ncell=(3, 3, 3), a=5.9, rc_vdw=9.0, r_real=9.0, alpha=0.2, elec=abi.ELEC_FENNEL, temperature=1200.0,
-                seed=2, cell_size=None, vel=True, kind="buck"):
+                seed=2, cell_size=None, vel=True, kind="buck", jitter=0.05, ewald_k=(0, 0, 0)):
     from aztotmd_b200.decks import rocksalt_positions
-    pos, types, box = rocksalt_positions(ncell, a, jitter=0.05, seed=seed)
+    pos, types, box = rocksalt_positions(ncell, a, jitter=jitter, seed=seed)
     s = System(pos=pos, types=types.astype(np.int32), box=box,
                species=[Species("Na", 22.99, 1.0), Species("Cl", 35.45, -1.0)], timestep=0.001,
                cell_size=cell_size if cell_size else max(r_real, rc_vdw), elec_kind=elec, r_real=r_real, alpha=alpha,
-               temperature=temperature, seed=seed)
+               temperature=temperature, seed=seed, ewald_k=ewald_k)
     if kind == "buck":
         s.set_vdw(0, 0, "buck", rc_vdw, [424.097, 0.317, 1.05])
         s.set_vdw(0, 1, "buck", rc_vdw, [1256.31, 0.317, 7.00])

@@ -92,6 +92,8 @@ def check_against_single(lib, system, n_ranks, pgrid, nsteps=3, tol=2e-5, distri
             assert abs(sr.engVdW_d - s1.engVdW_d) <= tol * sc, (k, sr.engVdW_d, s1.engVdW_d)
             assert abs(sr.engCoul1_d - s1.engCoul1_d) <= tol * sc
             assert abs(sr.engKin_d - s1.engKin_d) <= tol * sc
+            assert abs(sr.engCoul2_d - s1.engCoul2_d) <= tol * sc and abs(sr.engCoul3 - s1.engCoul3) <= tol * max(sc, abs(s1.engCoul3))
+            assert abs(sr.engTot - s1.engTot) <= 4 * tol * max(sc, abs(s1.engTot))
             assert sr.n_pairs == s1.n_pairs == o.pairs_in_range(), (sr.n_pairs, s1.n_pairs)
     frc, pos, vel, seen = gather_by_id(res, n)
     assert (seen == 1).all(), "every atom is owned by exactly one brick (%d missing, %d duplicated)" % ((seen == 0).sum(), (seen > 1).sum())
@@ -133,6 +135,15 @@ def case_four_bricks_2x2(lib, devices=None):
 def case_eight_bricks_2x2x2_ionic(lib, devices=None):
     s = azt.nacl_system(ncell=(7, 7, 7), elec=abi.ELEC_FENNEL, r_real=9.0, rc_vdw=9.0, cell_size=9.0)
     check_against_single(lib, s, 8, (2, 2, 2), nsteps=2, devices=devices)
+
+
+def case_bricks_ewald_reciprocal(lib, devices=None):
+    """'elec pme' on bricks: every rank sums q exp(ikr) over the atoms it owns, the structure factor is all-reduced,
+    the k-space energy and the constant term are global on every rank."""
+    s = azt.nacl_system(ncell=(7, 5, 5), elec=abi.ELEC_EWALD, alpha=0.3, jitter=0.4, ewald_k=(7, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.0)
+    res = check_against_single(lib, s, 2, (2, 1, 1), nsteps=2, devices=devices)
+    assert res[0]["stats"][0].engCoul2 > 1.0
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=2, distributed=True, devices=devices)
 
 
 def case_bricks_verlet_list_between_rebuilds(lib, devices=None):

@@ -43,6 +43,8 @@ static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
 static inline int2 make_int2(int x, int y) { return int2{ x, y }; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z, w }; }
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{ x, y }; }
 
 // ----------------------------------------------------------------------------- qualifiers
 #define __global__
@@ -229,6 +231,7 @@ static inline float __ldg(const float* p) { return *p; }
 static inline int __ldg(const int* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
 static inline float2 __ldg(const float2* p) { return *p; }
+static inline int4 __ldg(const int4* p) { return *p; }
 using std::min; using std::max;
 
 // ----------------------------------------------------------------------------- host runtime

@@ -65,7 +65,15 @@ def main():
             info = decks.nacl_deck(d, 5, rc_vdw=9.0, r_real=9.0, alpha=0.2, elec=elec, init_vel="zero", nstep=2)
             cases.append(("nacl5_buck_" + elec, d, "full", dict(kind="nacl", ncell=5, elec=elec, rc_vdw=9.0, r_real=9.0,
                                                                 alpha=0.2, box=[float(x) for x in info["box"]])))
+        # rock salt, Buckingham + full Ewald sum (real space + reciprocal space + constant term): 'elec pme'
+        d = os.path.join(tmp, "nacl_pme")
+        info = decks.nacl_deck(d, 5, rc_vdw=9.0, r_real=9.0, alpha=0.3, elec="pme", init_vel="zero", nstep=2, jitter=0.4)
+        cases.append(("nacl5_buck_pme", d, "full", dict(kind="nacl", ncell=5, elec="pme", rc_vdw=9.0, r_real=9.0, alpha=0.3,
+                                                        ewald_k=[6, 6, 6], jitter=0.4, box=[float(x) for x in info["box"]])))
+        only = sys.argv[1:]
         for name, d, mode, meta in cases:
+            if only and name not in only:
+                continue
             dumps, line = run(d, 0, mode)
             init = dumps["init"]
             names = [l.split()[0] for l in open(os.path.join(d, "atoms.xyz")).read().splitlines()[2:] if l.strip()]
@@ -75,8 +83,13 @@ def main():
                     uniq.append(nm)
             types = np.array([uniq.index(nm) for nm in names], dtype=np.int32)
             out = os.path.join(HERE, "ref_serial_%s.npz" % name)
+            extra = {}
+            if meta.get("elec") == "pme":
+                import json
+                j = json.loads(line)
+                extra = dict(engElec1=j["engElec1"], engElec2=j["engElec2"])
             np.savez_compressed(out, pos=init["pos"], frc=init["frc"], types=types, engVdW=init["engVdW"],
-                                engCoul=init["engCoul"], meta=np.array(repr(meta)), harness=np.array(line))
+                                engCoul=init["engCoul"], meta=np.array(repr(meta)), harness=np.array(line), **extra)
             print(name, line)
             print("  ->", out, os.path.getsize(out), "bytes")
 

@@ -46,6 +46,9 @@ def assert_stats_close(so, se, tol=ENERGY_TOL, thermo=False, escale=None):
     for k in ("engKin_d", "engVdW_d", "engCoul1_d") + (("engTemp_d",) if thermo else ()):
         a, b = getattr(so, k), getattr(se, k)
         assert abs(a - b) <= tol * max(abs(a), floor), "%s: oracle %r engine %r" % (k, a, b)
+    # reciprocal-space Ewald: k-space energy (fp32 phases against the oracle's double ones) and the constant term
+    assert abs(so.engCoul2_d - se.engCoul2_d) <= 10 * tol * max(abs(so.engCoul2_d), floor), "engCoul2: oracle %r engine %r" % (so.engCoul2_d, se.engCoul2_d)
+    assert abs(so.engCoul3 - se.engCoul3) <= tol * max(abs(so.engCoul3), floor)
     assert abs(so.engTot - se.engTot) <= 4 * tol * max(abs(so.engTot), floor)
 
 
@@ -135,6 +138,21 @@ def case_ionic(lib, elec, kind="buck"):
     s = azt.nacl_system(ncell=(5, 5, 5), elec=elec, kind=kind)
     o, e = run_parity(lib, s, nsteps=2)
     e.close()
+
+
+def case_ewald_reciprocal(lib):
+    """'elec pme': real-space + reciprocal-space + constant term on a disordered rock-salt box."""
+    s = azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_EWALD, alpha=0.3, jitter=0.4, ewald_k=(6, 6, 6))
+    o, e = run_parity(lib, s, nsteps=2)
+    st = e.stats()
+    assert st.engCoul2 > 1.0 and st.engCoul3 < -1000.0  # both terms are live
+    e.close()
+    s2 = azt.nacl_system(ncell=(5, 4, 6), elec=abi.ELEC_EWALD, alpha=0.3, jitter=0.4, ewald_k=(5, 4, 7))  # anisotropic box and k ranges
+    o, e = run_parity(lib, s2, nsteps=2)
+    e.close()
+    # the list path with a rebuild interval runs the same k-space passes after the list force pass
+    s3 = azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_EWALD, alpha=0.3, ewald_k=(6, 6, 6))
+    _rebuild_vs_every_step(lib, s3, 1.0, 0, nsteps=6)
 
 
 def case_ionic_efield_frozen(lib):
@@ -503,6 +521,7 @@ ALL_CASES = [
     ("ionic_mixed_table_dsf", lambda lib: case_ionic(lib, abi.ELEC_FENNEL, kind="mixed")),
     ("ionic_elin_einv_bmh_ewald_real", lambda lib: case_ionic(lib, abi.ELEC_EWALD, kind="mixed2")),
     ("elin_einv_bmh_nocoul", lambda lib: case_ionic(lib, abi.ELEC_NONE, kind="mixed2")),
+    ("ewald_reciprocal", case_ewald_reciprocal),
     ("ionic_efield_frozen", case_ionic_efield_frozen),
     ("surk_radiative_equil", case_surk_radiative),
     ("lj_radiative", case_lj_radiative),

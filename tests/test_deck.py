@@ -200,6 +200,29 @@ def test_ionic_deck_dsf_constants(lib, tmp_path):
     lib.az_deck_free(h)
 
 
+def test_ionic_deck_pme_carries_the_k_ranges(lib, tmp_path):
+    """'elec pme rc alpha kx ky kz' (src/elec.cpp:47-51): the k ranges reach the engine, which derives the k-space
+    constants itself; the deck-built description steps through the kernels (emulator) like the oracle."""
+    import parity_cases
+    decks.nacl_deck(str(tmp_path), 5, rc_vdw=9.0, r_real=9.0, alpha=0.3, elec="pme", jitter=0.4, nstep=2)
+    rc, h = load(lib, tmp_path, seed=3)
+    assert rc == 0, lib.az_deck_error(h)
+    d = lib.az_deck_desc(h).contents
+    assert d.elec_kind == abi.ELEC_EWALD and list(d.ewald_k) == [6, 6, 6] and d.alpha == 0.3
+    assert d.daipi2 == pytest.approx(2 * 0.3 / math.sqrt(3.14159265359), rel=1e-12)
+    o = azt.Oracle(d)
+    e = Engine(d, lib=azt.emu_lib())
+    e.set_option("energy_every_step", 1)
+    o.step(0, 1); e.step(0, 1)
+    do, de = o.dump(), e.dump()
+    parity_cases.assert_cells_equal(do, de)
+    parity_cases.assert_forces_close(o, do, de)
+    parity_cases.assert_stats_close(o.stats(), e.stats())
+    assert e.stats().engCoul2 > 1.0
+    e.close()
+    lib.az_deck_free(h)
+
+
 def test_deck_drives_the_kernels_like_the_python_system(lib, tmp_path):
     """A deck-built description goes through the same kernels (emulator build) and matches the oracle."""
     import parity_cases

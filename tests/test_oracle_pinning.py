@@ -31,9 +31,10 @@ def system_from_fixture(path):
         s = System(pos=pos, types=types, box=meta["box"], species=[Species("Ar", azt.AR_MASS)], cell_size=meta["rc"])
         s.set_vdw(0, 0, "lnjs", meta["rc"], [azt.AR_EPS, azt.AR_SIGMA])
     else:
-        ek = {"fenn": abi.ELEC_FENNEL, "dir": abi.ELEC_DIRECT}[meta["elec"]]
+        ek = {"fenn": abi.ELEC_FENNEL, "dir": abi.ELEC_DIRECT, "pme": abi.ELEC_EWALD}[meta["elec"]]
         s = System(pos=pos, types=types, box=meta["box"], species=[Species("Na", 22.99, 1.0), Species("Cl", 35.45, -1.0)],
-                   cell_size=max(meta["r_real"], meta["rc_vdw"]), elec_kind=ek, r_real=meta["r_real"], alpha=meta["alpha"])
+                   cell_size=max(meta["r_real"], meta["rc_vdw"]), elec_kind=ek, r_real=meta["r_real"], alpha=meta["alpha"],
+                   ewald_k=meta.get("ewald_k", (0, 0, 0)))
         s.set_vdw(0, 0, "buck", meta["rc_vdw"], [424.097, 0.317, 1.05])
         s.set_vdw(0, 1, "buck", meta["rc_vdw"], [1256.31, 0.317, 7.00])
         s.set_vdw(1, 1, "buck", meta["rc_vdw"], [3488.998, 0.317, 72.40])
@@ -64,6 +65,9 @@ def test_oracle_matches_reference_serial_build(path):
     # the serial twin's direct/DSF real-space energy (Sim::engElec3)
     if float(z["engCoul"]) != 0.0:
         assert st.engCoul1_d == pytest.approx(float(z["engCoul"]), rel=5e-6)
+    if "engElec2" in z.files:  # 'elec pme': reciprocal-space energy (Sim::engElec2) and the constant term (Sim::engElec1)
+        assert st.engCoul2_d == pytest.approx(float(z["engElec2"]), rel=5e-6)
+        assert st.engCoul3 == pytest.approx(float(z["engElec1"]), rel=5e-6)
 
 
 def pair(kind, p, r, rc=100.0, elec=0, alpha=0.0, q=0.0, rad=(0.0, 0.0), r_real=0.0):
