@@ -438,7 +438,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     dd_free(e);
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
-    cudaFree(e->ew_kv); cudaFree(e->ew_kr); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
+    cudaFree(e->ew_ak); cudaFree(e->ew_pairs); cudaFree(e->ew_runs); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
@@ -505,49 +505,58 @@ static int ewald_setup(az_engine* e, const az_system_desc* d, double qs[2])
     if (rkcut > kz / L[2]) rkcut = kz / L[2];
     rkcut *= twopi * 1.05;
     const double rkcut2 = rkcut * rkcut, mr4a2 = -0.25 / d->alpha / d->alpha;
-    std::vector<int4> kv; std::vector<float4> kr;
-    int mmin = 0, nmin = 1, pl = -1, pm = 0; // the reference's enumeration, src/elec.cpp:234-324
+    // the reference's enumeration (src/elec.cpp:234-324); for one (l, m) the kept n form one interval, contiguous in the list
+    std::vector<float> ak; std::vector<int4> runs, pairs;
+    int mmin = 0, nmin = 1;
     for (int l = 0; l < kx; l++) {
         const double rkx = l * twopi / L[0];
         for (int m = mmin; m < ky; m++) {
             const double rky = m * twopi / L[1];
+            const int am = m < 0 ? -m : m, lmcode = l | (am << 8) | (m < 0 ? 1 << 16 : 0);
+            int n_lo = 0, n_hi = 0, k_lo = -1;
             for (int n = nmin; n < kz; n++) {
                 const double rkz = n * twopi / L[2];
                 const double rk2 = rkx * rkx + rky * rky + rkz * rkz;
                 if (rk2 < rkcut2) {
-                    const int am = m < 0 ? -m : m, an = n < 0 ? -n : n;
-                    kv.push_back(make_int4(l, am | (m < 0 ? 256 : 0), an | (n < 0 ? 256 : 0), (l != pl || m != pm || kv.empty()) ? 1 : 0));
-                    kr.push_back(make_float4((float)rkx, (float)rky, (float)rkz, (float)(exp(rk2 * mr4a2) / rk2)));
-                    pl = l; pm = m;
+                    if (k_lo < 0) { k_lo = (int)ak.size(); n_lo = n; }
+                    else if (n != n_hi + 1) { AZ_SET_ERR(e, "elec pme: k-vectors of one (l, m) are not contiguous"); return AZ_ERR_INVALID; }
+                    n_hi = n;
+                    ak.push_back((float)(exp(rk2 * mr4a2) / rk2));
                 }
+            }
+            if (k_lo >= 0) {
+                if (n_lo < 0 && n_lo != -n_hi) { AZ_SET_ERR(e, "elec pme: asymmetric n range"); return AZ_ERR_INVALID; }
+                runs.push_back(make_int4(lmcode, n_lo, n_hi, k_lo));
+                for (int n = (n_lo > 0 ? n_lo : 0); n <= n_hi; n++) // (l, m, n) and, if kept, (l, m, -n)
+                    pairs.push_back(make_int4(lmcode | (n << 20), k_lo + (n - n_lo), (n > 0 && -n >= n_lo) ? k_lo + (-n - n_lo) : -1, 0));
             }
             nmin = 1 - kz;
         }
         mmin = 1 - ky;
     }
-    const int nk = (int)kv.size();
+    const int nk = (int)ak.size();
     if (nk == 0) { AZ_SET_ERR(e, "elec pme: no k-vector inside the cut-off"); return AZ_ERR_INVALID; }
-    if (nk > AZ_EW_MAX_K) { AZ_SET_ERR(e, "elec pme: %d k-vectors, at most %d are supported", nk, AZ_EW_MAX_K); return AZ_ERR_UNSUPPORTED; }
+    if (nk > AZ_EW_MAX_K || (int)pairs.size() > AZ_EW_MAX_PAIRS) { AZ_SET_ERR(e, "elec pme: %d k-vectors, at most %d are supported", nk, AZ_EW_MAX_K); return AZ_ERR_UNSUPPORTED; }
     AzEwald& E = e->ew;
     E.nk = nk; E.kx = kx > 1 ? kx : 2; E.ky = ky > 1 ? ky : 2; E.kz = kz > 1 ? kz : 2;
     for (int a = 0; a < 3; a++) E.tpl[a] = (float)(twopi / L[a]);
     const double scale = 2.0 * twopi / (L[0] * L[1] * L[2]) * (double)AZ_FCOUL_SCALE / eps; // Elec::scale, src/elec.cpp:380
     E.escale = scale; E.fscale = (float)(2.0 * scale);                                  // Elec::scale2
-    AZ_ALLOC(e, e->ew_kv, nk); AZ_ALLOC(e, e->ew_kr, nk); AZ_ALLOC(e, e->ew_T, nk); AZ_ALLOC(e, e->ew_Sd, nk);
-    AZ_CUDA(e, cudaMemcpy(e->ew_kv, kv.data(), sizeof(int4) * nk, cudaMemcpyHostToDevice));
-    AZ_CUDA(e, cudaMemcpy(e->ew_kr, kr.data(), sizeof(float4) * nk, cudaMemcpyHostToDevice));
-    E.kv = e->ew_kv; E.kr = e->ew_kr;
+    E.npairs = (int)pairs.size(); E.nruns = (int)runs.size();
+    AZ_ALLOC(e, e->ew_ak, nk); AZ_ALLOC(e, e->ew_pairs, pairs.size()); AZ_ALLOC(e, e->ew_runs, runs.size()); AZ_ALLOC(e, e->ew_T, nk); AZ_ALLOC(e, e->ew_Sd, nk);
+    AZ_CUDA(e, cudaMemcpy(e->ew_ak, ak.data(), sizeof(float) * nk, cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->ew_pairs, pairs.data(), sizeof(int4) * pairs.size(), cudaMemcpyHostToDevice));
+    AZ_CUDA(e, cudaMemcpy(e->ew_runs, runs.data(), sizeof(int4) * runs.size(), cudaMemcpyHostToDevice));
+    E.ak = e->ew_ak; E.pairs = e->ew_pairs; E.runs = e->ew_runs;
     const int ntiles = (e->cap + AZ_EW_TILE - 1) / AZ_EW_TILE;
     e->ew_blocks = std::max(1, std::min(ntiles, 2 * (e->n_sm > 0 ? e->n_sm : 148)));
     AZ_ALLOC(e, e->ew_part, (size_t)e->ew_blocks * nk);
     e->ew_smem_s = sizeof(float2) * AZ_EW_TILE * (size_t)(E.kx + E.ky + E.kz);
-    e->ew_smem_f = sizeof(float2) * AZ_EW_FTPB * (size_t)(E.kx + E.ky + E.kz);
-    if (e->ew_smem_s > 200 * 1024) { AZ_SET_ERR(e, "elec pme: kx + ky + kz = %d does not fit the shared-memory tables (at most 200)", E.kx + E.ky + E.kz); return AZ_ERR_UNSUPPORTED; }
+    e->ew_smem_f = sizeof(float2) * (AZ_EW_FTPB * (size_t)(E.kx + E.ky + E.kz) + ((nk + 1) & ~1)) + sizeof(int4) * runs.size();
+    if (e->ew_smem_s > 200 * 1024 || e->ew_smem_f > 200 * 1024) { AZ_SET_ERR(e, "elec pme: kx + ky + kz = %d does not fit the shared-memory tables (at most 200)", E.kx + E.ky + E.kz); return AZ_ERR_UNSUPPORTED; }
 #ifndef AZ_EMU
-    if (e->ew_smem_s > 48 * 1024) {
-        AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_s));
-        AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_f));
-    }
+    if (e->ew_smem_s > 48 * 1024) AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_s));
+    if (e->ew_smem_f > 48 * 1024) AZ_CUDA(e, cudaFuncSetAttribute(az_k_ewald_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->ew_smem_f));
 #endif
     // ewald_const (src/elec.cpp:144-165) from the global charge sums
     if (e->dd) { int rc = dd_allreduce_host(e, qs, 2, false); if (rc) return rc; }

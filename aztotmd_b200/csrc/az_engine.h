@@ -61,7 +61,7 @@ struct az_engine {
     int n_pair_partials = 0;
     // reciprocal-space Ewald (az_ewald.cuh); ew.nk == 0: off
     AzEwald ew = {};
-    int4* ew_kv = nullptr; float4* ew_kr = nullptr; float2 *ew_part = nullptr, *ew_T = nullptr; double2* ew_Sd = nullptr;
+    float* ew_ak = nullptr; int4 *ew_pairs = nullptr, *ew_runs = nullptr; float2 *ew_part = nullptr, *ew_T = nullptr; double2* ew_Sd = nullptr;
     int ew_blocks = 0;
     size_t ew_smem_s = 0, ew_smem_f = 0;
     // az_engine_upload staging: two buffers of 6*n doubles filled on a copy stream, so that the H2D copy of the

@@ -10,21 +10,26 @@
 // (ewald_setup, az_engine.cu), so the set of vectors is the reference's exactly.
 //
 // B200 design: nothing of size N x nK is ever stored.
-//   az_k_ewald_sfac   one thread per k-vector, the atoms of a 128-atom tile staged in shared memory as the three tables
-//                     exp(i 2 pi l x / a), l < kx (likewise y, z) built with the reference's recurrence; every thread
-//                     walks the tile with its own (l, m, n) and keeps its partial S(k) in registers over all the
-//                     tiles of its block: no reduction inside the tile loop, no atomics.  One partial per block and k.
+//   az_k_ewald_sfac   one thread per pair of k-vectors (l, m, +n) / (l, m, -n); the atoms of a 128-atom tile staged in
+//                     shared memory as the three tables exp(i 2 pi l x / a), l < kx (likewise y, z) built with the
+//                     reference's recurrence; every thread walks the tile with its own (l, m, n) -- three shared loads
+//                     and 12 FMAs give both members of the pair, since exp(-i n z) is the conjugate of exp(i n z) --
+//                     and keeps its partial S(k) in registers over all the tiles of its block: no reduction inside
+//                     the tile loop, no atomics.  One partial per block and k.
 //   az_k_ewald_reduce one block: partials summed in double in block order (reproducible), a_k S(k) stored for the force
 //                     pass, E_rec reduced in a fixed order.
-//   az_k_ewald_force  one thread per atom, its tables in shared memory (one column per thread), the k list read as
-//                     warp-uniform loads; exp(i (l x + m y)) is reused while (l, m) stays the same.
+//   az_k_ewald_force  one thread per atom, its tables in shared memory (one column per thread), a_k S(k) and the list
+//                     of (l, m) runs staged in shared memory; within a run (n = -nmax .. nmax, contiguous in the
+//                     reference's order) exp(i (l x + m y)) is formed once, +n and -n share the four products with
+//                     exp(i n z), and the x / y components of the force are applied once per run.
 #pragma once
 #include "az_device.cuh"
 
 #define AZ_EW_TILE 128      // atoms per shared-memory tile of the structure-factor pass
 #define AZ_EW_TPB 256       // threads of the structure-factor pass
-#define AZ_EW_KPT 8         // k-vectors per thread: nK <= AZ_EW_TPB * AZ_EW_KPT
-#define AZ_EW_MAX_K (AZ_EW_TPB * AZ_EW_KPT)
+#define AZ_EW_KPT 5         // k-vector pairs per thread of the structure-factor pass
+#define AZ_EW_MAX_PAIRS (AZ_EW_TPB * AZ_EW_KPT)
+#define AZ_EW_MAX_K 2048    // k-vectors (the reference's NTOTKVEC is 1200, src/defines.h:32)
 #define AZ_EW_FTPB 128      // threads (atoms) per block of the force pass
 
 struct AzEwald {
@@ -33,8 +38,10 @@ struct AzEwald {
     float tpl[3];        // 2 pi / box length
     float fscale;        // 2 * scale
     double escale;       // scale
-    const int4* kv;      // l, |m| | sign bit 8, |n| | sign bit 8, 1 if (l, m) differs from the entry before
-    const float4* kr;    // k vector (x, y, z), a_k
+    int npairs, nruns;
+    const float* ak;     // [nk] a_k, the reference's enumeration order (src/elec.cpp:234-324)
+    const int4* pairs;   // [npairs] x = l | |m| << 8 | (m < 0) << 16 | n << 20 (n >= 0), y = index of (l, m, n), z = index of (l, m, -n) or -1
+    const int4* runs;    // [nruns] x = l | |m| << 8 | (m < 0) << 16, y = lowest n, z = highest n, w = index of (l, m, lowest n)
 };
 
 #ifdef AZ_EWALD_KERNELS // az_engine.cu only: the other units need the argument struct, not the kernels
@@ -65,15 +72,14 @@ az_k_ewald_sfac(const __grid_constant__ AzParams P, const __grid_constant__ AzEw
     const int tid = threadIdx.x;
     const int n = az_n_owned(P);
     const int ntiles = (n + AZ_EW_TILE - 1) / AZ_EW_TILE;
-    // this thread's k-vectors: table offsets and conjugation signs, packed
+    // this thread's k-vector pairs: table offsets and the conjugation sign of m, packed
     int koff[AZ_EW_KPT];
-    float2 acc[AZ_EW_KPT];
+    float2 accp[AZ_EW_KPT], accm[AZ_EW_KPT];
 #pragma unroll
     for (int j = 0; j < AZ_EW_KPT; j++) {
         const int k = tid + j * AZ_EW_TPB;
-        acc[j] = make_float2(0.f, 0.f);
-        koff[j] = -1;
-        if (k < E.nk) { const int4 v = E.kv[k]; koff[j] = v.x | (v.y << 8) | (v.z << 18); }
+        accp[j] = accm[j] = make_float2(0.f, 0.f);
+        koff[j] = k < E.npairs ? E.pairs[k].x : -1;
     }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int a0 = tile * AZ_EW_TILE;
@@ -101,27 +107,35 @@ az_k_ewald_sfac(const __grid_constant__ AzParams P, const __grid_constant__ AzEw
         for (int j = 0; j < AZ_EW_KPT; j++) {
             const int ko = koff[j];
             if (ko < 0) continue;
-            const int l = ko & 255, m = (ko >> 8) & 255, nn = (ko >> 18) & 255;
-            const float sm = (ko & (1 << 16)) ? -1.f : 1.f, sn = (ko & (1 << 26)) ? -1.f : 1.f; // negative index: conjugate
-            const float2* px = tx + l;
-            const float2* py = ty + m;
-            const float2* pz = tz + nn;
-            float2 s = acc[j];
+            const float sm = (ko & (1 << 16)) ? -1.f : 1.f; // negative m: conjugate
+            const float2* px = tx + (ko & 255);
+            const float2* py = ty + ((ko >> 8) & 255);
+            const float2* pz = tz + (ko >> 20);
+            float2 sp = accp[j], sn = accm[j];
 #pragma unroll 4
             for (int a = 0; a < na; a++) {
                 const float2 ex = px[a * E.kx];
-                float2 ey = py[a * E.ky], ez = pz[a * E.kz];
-                ey.y *= sm; ez.y *= sn;
-                const float2 c = az_cmul(az_cmul(ex, ey), ez);
-                s.x += c.x; s.y += c.y;
+                float2 ey = py[a * E.ky];
+                const float2 ez = pz[a * E.kz];
+                ey.y *= sm;
+                const float2 lm = az_cmul(ex, ey);
+                // lm * ez and lm * conj(ez) share their four products
+                sp.x = fmaf(lm.x, ez.x, sp.x); sp.x = fmaf(-lm.y, ez.y, sp.x);
+                sp.y = fmaf(lm.y, ez.x, sp.y); sp.y = fmaf(lm.x, ez.y, sp.y);
+                sn.x = fmaf(lm.x, ez.x, sn.x); sn.x = fmaf(lm.y, ez.y, sn.x);
+                sn.y = fmaf(lm.y, ez.x, sn.y); sn.y = fmaf(-lm.x, ez.y, sn.y);
             }
-            acc[j] = s;
+            accp[j] = sp; accm[j] = sn;
         }
     }
 #pragma unroll
     for (int j = 0; j < AZ_EW_KPT; j++) {
         const int k = tid + j * AZ_EW_TPB;
-        if (k < E.nk) part[(size_t)blockIdx.x * E.nk + k] = acc[j];
+        if (k < E.npairs) {
+            const int4 v = E.pairs[k];
+            part[(size_t)blockIdx.x * E.nk + v.y] = accp[j];
+            if (v.z >= 0) part[(size_t)blockIdx.x * E.nk + v.z] = accm[j];
+        }
     }
 }
 
@@ -136,11 +150,23 @@ az_k_ewald_reduce(const __grid_constant__ AzEwald E, const float2* __restrict__ 
     for (int k = threadIdx.x; k < E.nk; k += 1024) {
         double sx = 0.0, sy = 0.0;
         if (finish != 2) {
-            for (int b = 0; b < nparts; b++) { const float2 p = part[(size_t)b * E.nk + k]; sx += (double)p.x; sy += (double)p.y; }
+            // eight independent partial sums (eight loads in flight per thread), combined in a fixed order
+            double ax[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ay[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+            int b = 0;
+            for (; b + 8 <= nparts; b += 8) {
+                float2 p[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) p[u] = part[(size_t)(b + u) * E.nk + k];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { ax[u] += (double)p[u].x; ay[u] += (double)p[u].y; }
+            }
+            for (; b < nparts; b++) { const float2 p = part[(size_t)b * E.nk + k]; ax[0] += (double)p.x; ay[0] += (double)p.y; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { sx += ax[u]; sy += ay[u]; }
             Sd[k] = make_double2(sx, sy);
         } else { const double2 v = Sd[k]; sx = v.x; sy = v.y; }
         if (finish) {
-            const float ak = E.kr[k].w;
+            const float ak = E.ak[k];
             T[k] = make_float2(ak * (float)sx, ak * (float)sy);
             e += (double)ak * (sx * sx + sy * sy);
         }
@@ -157,7 +183,7 @@ az_k_ewald_reduce(const __grid_constant__ AzEwald E, const float2* __restrict__ 
     }
 }
 
-// frc[i] += q_i * fscale * sum_k (Im e_ik T_k.x - Re e_ik T_k.y) k,   e_ik = exp(i k r_i)
+// frc[i] += q_i * fscale * sum_k (Im e_ik T_k.x - Re e_ik T_k.y) k,   e_ik = exp(i k r_i),  T_k = a_k S(k)
 __global__ void __launch_bounds__(AZ_EW_FTPB)
 az_k_ewald_force(const __grid_constant__ AzParams P, const __grid_constant__ AzEwald E, const float4* __restrict__ pos, const float2* __restrict__ T,
                  float4* __restrict__ frc)
@@ -165,30 +191,48 @@ az_k_ewald_force(const __grid_constant__ AzParams P, const __grid_constant__ AzE
     AZ_DYN_SMEM(float2, s_ew);
     const int tid = threadIdx.x;
     const int i = blockIdx.x * AZ_EW_FTPB + tid;
-    if (i >= az_n_owned(P)) return; // no barrier below: every thread works on its own column
     float2* tx = s_ew + tid;                         // [l][thread]
     float2* ty = tx + AZ_EW_FTPB * E.kx;
     float2* tz = ty + AZ_EW_FTPB * E.ky;
-    const float4 p = pos[i];
-    AZ_EW_FILL(tx, AZ_EW_FTPB, E.kx, E.tpl[0] * p.x);
-    AZ_EW_FILL(ty, AZ_EW_FTPB, E.ky, E.tpl[1] * p.y);
-    AZ_EW_FILL(tz, AZ_EW_FTPB, E.kz, E.tpl[2] * p.z);
+    float2* sT = s_ew + AZ_EW_FTPB * (E.kx + E.ky + E.kz);   // [nk]
+    int4* sR = (int4*)(sT + ((E.nk + 1) & ~1));               // [nruns], 16-byte aligned
+    for (int k = tid; k < E.nk; k += AZ_EW_FTPB) sT[k] = T[k];
+    for (int r = tid; r < E.nruns; r += AZ_EW_FTPB) sR[r] = E.runs[r];
+    const bool act = i < az_n_owned(P);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+        p = pos[i];
+        AZ_EW_FILL(tx, AZ_EW_FTPB, E.kx, E.tpl[0] * p.x);
+        AZ_EW_FILL(ty, AZ_EW_FTPB, E.ky, E.tpl[1] * p.y);
+        AZ_EW_FILL(tz, AZ_EW_FTPB, E.kz, E.tpl[2] * p.z);
+    }
+    __syncthreads();
+    if (!act) return;
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    float2 lm = make_float2(1.f, 0.f);
-    for (int k = 0; k < E.nk; k++) {
-        const int4 v = __ldg(E.kv + k);
-        const float4 kr = __ldg(E.kr + k);
-        const float2 t = __ldg(T + k);
-        if (v.w) {
-            float2 ey = ty[(v.y & 255) * AZ_EW_FTPB];
-            if (v.y & 256) ey.y = -ey.y;
-            lm = az_cmul(tx[v.x * AZ_EW_FTPB], ey);
+    for (int r = 0; r < E.nruns; r++) {
+        const int4 run = sR[r];
+        const int l = run.x & 255, m = (run.x >> 8) & 255;
+        float2 ey = ty[m * AZ_EW_FTPB];
+        const float sgn = (run.x & (1 << 16)) ? -1.f : 1.f;
+        ey.y *= sgn;
+        const float2 lm = az_cmul(tx[l * AZ_EW_FTPB], ey);
+        const float2* t0 = sT + (run.w - run.y); // t0[n] = T of (l, m, n)
+        float wsum = 0.f, wz = 0.f;
+        if (run.y <= 0) { const float2 t = t0[0]; wsum = lm.y * t.x - lm.x * t.y; } // n = 0
+        const bool both = run.y < 0; // the run is symmetric: n = -nmax .. nmax (only l = m = 0 starts at n = 1)
+        for (int n = 1; n <= run.z; n++) {
+            const float2 ez = tz[n * AZ_EW_FTPB];
+            const float a = lm.x * ez.x, b = lm.y * ez.y, c = lm.y * ez.x, d = lm.x * ez.y;
+            const float2 tp = t0[n];
+            const float wp = (c + d) * tp.x - (a - b) * tp.y;
+            float wm = 0.f;
+            if (both) { const float2 tm = t0[-n]; wm = (c - d) * tm.x - (a + b) * tm.y; }
+            wsum += wp + wm;
+            wz = fmaf((float)n, wp - wm, wz);
         }
-        float2 ez = tz[(v.z & 255) * AZ_EW_FTPB];
-        if (v.z & 256) ez.y = -ez.y;
-        const float2 c = az_cmul(lm, ez);
-        const float w = c.y * t.x - c.x * t.y;
-        fx = fmaf(w, kr.x, fx); fy = fmaf(w, kr.y, fy); fz = fmaf(w, kr.z, fz);
+        fx = fmaf((float)l * E.tpl[0], wsum, fx);
+        fy = fmaf(sgn * (float)m * E.tpl[1], wsum, fy);
+        fz = fmaf(E.tpl[2], wz, fz);
     }
     const float q = P.charge[__float_as_int(p.w)] * E.fscale;
     float4 f = frc[i];
