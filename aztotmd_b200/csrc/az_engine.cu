@@ -633,9 +633,14 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     } else if (rebuild) {
         {
             Timer t(e, AZ_TIMER_SCAN);
-            AZ_LAUNCH(az_k_scan_tiles, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum);
-            AZ_LAUNCH(az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum, e->first);
-            AZ_COUNT(e, AZ_TIMER_SCAN, 2);
+            if (e->n_scan_tiles <= AZ_SCAN_ONE_LAUNCH) {
+                AZ_LAUNCH(az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, (const int*)nullptr, e->first);
+                AZ_COUNT(e, AZ_TIMER_SCAN, 1);
+            } else {
+                AZ_LAUNCH(az_k_scan_tiles, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum);
+                AZ_LAUNCH(az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum, e->first);
+                AZ_COUNT(e, AZ_TIMER_SCAN, 2);
+            }
         }
         {
             Timer t(e, AZ_TIMER_SORT);

@@ -161,7 +161,10 @@ az_k_integrate_a(const __grid_constant__ AzParams P, int slot, float4* __restric
 // ---------------------------------------------------------------------------------------
 // K2: exclusive scan of nAtInCell -> firstAtomInCell (calc_firstAtomInCell, src/cuSort.cu:130-143,
 // a single-thread loop in the reference).  Two launches: tile sums, then each tile adds the
-// sums of the tiles before it and scans its own items.
+// sums of the tiles before it and scans its own items.  Up to AZ_SCAN_ONE_LAUNCH tiles (the 40 000- and 4 000-atom
+// decks: 2 197 and 1 728 cells) the second kernel alone sums the counts before its tile itself: one launch less
+// on a latency-bound step.
+#define AZ_SCAN_ONE_LAUNCH 8
 #define AZ_SCAN_TPB 256
 #define AZ_SCAN_IPT 8
 #define AZ_SCAN_TILE (AZ_SCAN_TPB * AZ_SCAN_IPT)
@@ -197,7 +200,8 @@ az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ ti
     __shared__ int s_off;
     // offset of this tile = sum of the tile sums before it
     int off = 0;
-    for (int k = threadIdx.x; k < (int)blockIdx.x; k += AZ_SCAN_TPB) off += tileSum[k];
+    if (tileSum) { for (int k = threadIdx.x; k < (int)blockIdx.x; k += AZ_SCAN_TPB) off += tileSum[k]; }
+    else { for (int k = threadIdx.x; k < (int)blockIdx.x * AZ_SCAN_TILE; k += AZ_SCAN_TPB) off += count[k]; } // few tiles: one launch, no tile sums
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) off += __shfl_down_sync(0xffffffffu, off, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = off;

@@ -702,21 +702,33 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
             const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
             const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
-            for (int j = rb + lane; j < re; j += 32) {
-                const float4 pj = __ldg(A.pos + j);
+            // one candidate per lane: delta, gate, and -- only if some lane has a partner in range -- the pair term
+            auto cand = [&](const float4 pj, const int j, const bool valid) {
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 if (code) { dx -= shx; dy -= shy; dz -= shz; } // (x_i - x_j) - shift, exactly like the reference's secShifts
                 const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
-                const bool in = (r2 <= gate) & (j != i);
+                const bool in = valid & (r2 <= gate) & (j != i);
+                // dilute systems (case study 1: 490 candidates per atom, almost no pair inside 4 A): skip the pair term
+                // when no lane has a partner in range
+                if (!__any_sync(0xffffffffu, in)) return;
                 const int tj = __float_as_int(pj.w);
                 float radj = 0.f;
-                if (RADII) radj = A.therm[j].y;
+                if (RADII) radj = A.therm[valid ? j : rb].y;
                 float e1 = 0.f, e2 = 0.f, f;
                 if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
                 else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
                 f = in ? f : 0.f;
                 fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
                 if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
+            };
+            // uniform trip count (the vote needs the whole warp), two loads in flight per lane: the step of the small
+            // decks is bound by the latency of these loads, not by arithmetic
+            for (int j0 = rb; j0 < re; j0 += 64) {
+                const int ja = j0 + lane, jb = ja + 32;
+                const bool va = ja < re, vb = jb < re;
+                const float4 pa = __ldg(A.pos + (va ? ja : rb)), pb = __ldg(A.pos + (vb ? jb : rb));
+                cand(pa, ja, va);
+                if (j0 + 32 < re) cand(pb, jb, vb);
             }
         };
         az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep);
