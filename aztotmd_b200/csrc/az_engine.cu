@@ -257,7 +257,6 @@ extern "C" int az_engine_create(const az_system_desc* d, const az_cuda_opts* o, 
     if (d->n_atoms <= 0 || d->n_species <= 0 || d->n_species > AZ_MAX_SPECIES) { AZ_SET_ERR((az_engine*)0, "bad n_atoms/n_species"); return AZ_ERR_INVALID; }
     if (!d->xs || !d->ys || !d->zs || !d->types || !d->species || !d->vdw) { AZ_SET_ERR((az_engine*)0, "missing atom/species/vdw arrays"); return AZ_ERR_INVALID; }
     if (d->tstat_kind == AZ_TSTAT_NOSE && !(d->tstat_tau > 0.0 && d->t_kin > 0.0)) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat needs tstat_tau > 0 and t_kin > 0"); return AZ_ERR_INVALID; }
-    if (d->tstat_kind == AZ_TSTAT_NOSE && o && o->n_ranks > 1) { AZ_SET_ERR((az_engine*)0, "Nose-Hoover thermostat on bricks is not implemented (its friction needs the global kinetic energy twice per step)"); return AZ_ERR_UNSUPPORTED; }
     if (d->reset_vels < 0) { AZ_SET_ERR((az_engine*)0, "reset_vels < 0"); return AZ_ERR_INVALID; }
     if (d->tstat_kind < AZ_TSTAT_NONE || d->tstat_kind > AZ_TSTAT_RADI) { AZ_SET_ERR((az_engine*)0, "unknown thermostat kind"); return AZ_ERR_INVALID; }
     if (d->tstat_kind == AZ_TSTAT_RADI && !d->photons) { AZ_SET_ERR((az_engine*)0, "radiative thermostat needs photon energies"); return AZ_ERR_INVALID; }
@@ -607,7 +606,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const bool nose = (P.tstat == AZ_TSTAT_NOSE);
     if (nose) { // first application of the step, before verlet_1stage (src/main.cu:291-299)
         Timer t(e, AZ_TIMER_INTEGRATE_A);
-        AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+        AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, e->dd ? 1 : 0);
         AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_A, 2);
     }
@@ -744,7 +743,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             if (nose) { // second application of the step (apply_tstat): needs this step's kinetic energy, then the quantities
                 AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
-                AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+                if (e->dd) { int rc = dd_global_nose(e); if (rc) return rc; }
+                else AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, 0);
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
                 AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
@@ -763,7 +763,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 1);
             else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU, 1);
             if (nose) { // apply_tstat: the rescale comes first, then the thermostat (src/cuTemp.cu:777-794)
-                AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc);
+                AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, e->dd ? 1 : 0); // bricks: keGlob = teKin after the rescale
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
             }
@@ -1057,7 +1057,6 @@ extern "C" int az_engine_rdf_begin(az_engine* e, double r_max, double dr)
 {
     if (!e) return AZ_ERR_INVALID;
     if (!(r_max > 0.0) || !(dr > 0.0)) { AZ_SET_ERR(e, "rdf: r_max and dr must be positive"); return AZ_ERR_INVALID; }
-    if (e->dd) { AZ_SET_ERR(e, "rdf sampling on bricks is not implemented"); return AZ_ERR_UNSUPPORTED; }
     AZ_CUDA(e, cudaSetDevice(e->device));
     const AzGrid& g = e->P.g;
     const double idrdf = 1.0 / dr;                                   // Sim::idRDF, src/rdf.cpp:22
@@ -1072,6 +1071,7 @@ extern "C" int az_engine_rdf_begin(az_engine* e, double r_max, double dr)
         int s1 = 1;
         while ((float)s1 * g.csize[a] <= reach && s1 < g.n[a]) s1++;
         if (g.n[a] < 2 * s1 + 1) { AZ_SET_ERR(e, "rdf: radius %g needs %d cell layers on axis %d, the grid has %d cells (every pair must be seen through one image only)", r_max, s1, a, g.n[a]); return AZ_ERR_UNSUPPORTED; }
+        if (e->dd && g.dec[a] && s1 > g.sten[a]) { AZ_SET_ERR(e, "rdf: radius %g reaches %d cell layers on axis %d, the ghost shell of a brick has %d", r_max, s1, a, g.sten[a]); return AZ_ERR_UNSUPPORTED; }
         e->rdf_sten[a] = s1;
     }
     cudaFree(e->rdf_hist); e->rdf_hist = nullptr;
@@ -1097,7 +1097,9 @@ extern "C" int az_engine_rdf_sample(az_engine* e)
     A.pos = e->pos[c]; A.cellOfSorted = e->cellSorted; A.first = e->first; A.count = e->cellCount; A.hist = e->rdf_hist;
     for (int a = 0; a < 3; a++) A.sten[a] = e->rdf_sten[a];
     A.nbins = e->rdf_nbins; A.npair = e->rdf_npair; A.r2max = e->rdf_r2max; A.idrdf = e->rdf_idrdf; A.r2stencil = e->rdf_r2stencil;
-    const int blocks = (e->n + (AZ_RDF_TPB / 32) - 1) / (AZ_RDF_TPB / 32);
+    A.id = e->dd ? e->id[c] : nullptr;
+    const int n_slots = e->dd ? e->n_atom_blocks * AZ_TPB : e->n; // bricks: the owned count lives on the device (az_n_owned)
+    const int blocks = (n_slots + (AZ_RDF_TPB / 32) - 1) / (AZ_RDF_TPB / 32);
     AZ_LAUNCH(az_k_rdf, blocks, AZ_RDF_TPB, (size_t)e->rdf_nbins * e->rdf_npair * sizeof(unsigned), e->stream, e->P, A);
     e->launches++;
     e->rdf_samples++;
@@ -1117,6 +1119,17 @@ extern "C" int az_engine_rdf_read(az_engine* e, unsigned long long* counts, int 
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));
         AZ_CUDA(e, cudaMemcpy(counts, e->rdf_hist, sizeof(unsigned long long) * e->rdf_nbins * e->rdf_npair, cudaMemcpyDeviceToHost));
+        if (e->dd) { // collective: every rank gets the histogram of the whole box (integers below 2^53 are exact in the double all-reduce)
+            const int nh = e->rdf_nbins * e->rdf_npair;
+            std::vector<double> v(128);
+            for (int k0 = 0; k0 < nh; k0 += 128) {
+                const int m = std::min(128, nh - k0);
+                for (int k = 0; k < m; k++) v[k] = (double)counts[k0 + k];
+                int rc = dd_allreduce_host(e, v.data(), m, false);
+                if (rc) return rc;
+                for (int k = 0; k < m; k++) counts[k0 + k] = (unsigned long long)(v[k] + 0.5);
+            }
+        }
     }
     return AZ_OK;
 }

@@ -542,6 +542,19 @@ static __global__ void az_k_dd_tscale_k(const __grid_constant__ AzParams P, AzSc
     // after_tscale (src/cuTemp.cu:109-113) sets engKin := teKin; each brick keeps its share so that the sum is teKin
     const double share = red[0] != 0.0 ? red[1] / red[0] : 0.0;
     sc->engKin = (double)P.teKin * share; sc->engKin_f = (float)sc->engKin;
+    sc->keGlob = P.teKin;
+}
+
+// Nose-Hoover on bricks, second application of the step: all-reduce this step's kinetic energy, then the scalar recurrence
+static int dd_global_nose(az_engine* e)
+{
+    AzDDHost* h = e->dd;
+    AZ_LAUNCH(az_k_dd_ke_out, 1, 1, 0, e->stream, e->sc, h->red);
+    int rc = h->comm->allreduce(h->red, 1, false, e->stream); // red[1] keeps the local value
+    if (rc) { e->err = h->comm->err; return rc; }
+    AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, e->stream, e->P, e->sc, (const double*)h->red, 2);
+    e->launches += 2;
+    return AZ_OK;
 }
 
 static int dd_global_tscale(az_engine* e)

@@ -57,6 +57,7 @@ struct AzScalars {
     int overflow, dbg_count, dbg_atom; // sticky error flags (+ worst list row count and the atom it belongs to)
     // flags:: 1 skin exceeded, 2 cell larger than the pair tile, 4 NaN energy, 8 halo slots, 16 neighbour-list rows
     float tscale_k;
+    float keGlob;                    // bricks + Nose-Hoover: kinetic energy of the whole system after the last application
     float chit, consInt, nose_scale; // Nose-Hoover friction, conserved-quantity integral, velocity factor of the block in flight
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
@@ -564,15 +565,22 @@ az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, 
 
 // Nose-Hoover (src/cuTemp.cu:115-163): before_nose and after_nose(1) are pure scalar recurrences, so both run in one
 // thread BEFORE the velocities are touched; az_k_vscale then applies md->tscale like tstat_nose.
-static __global__ void az_k_nose_scalars(const __grid_constant__ AzParams P, AzScalars* __restrict__ sc)
+// Bricks: the friction follows the kinetic energy of the WHOLE system.  glob = 1: take it from sc->keGlob (the value the
+// previous application left behind); glob = 2: red[0] is this step's all-reduced kinetic energy, red[1] this brick's
+// share.  Every rank runs the same recurrence on the same number, so chit and the scale factor agree bit for bit; the
+// brick's own engKin stays its share (the statistics sum the shares).
+static __global__ void az_k_nose_scalars(const __grid_constant__ AzParams P, AzScalars* __restrict__ sc, const double* __restrict__ red, int glob)
 {
-    float chit = sc->chit, ke = sc->engKin_f;
+    float chit = sc->chit;
+    float ke = glob == 2 ? (float)red[0] : (glob == 1 ? sc->keGlob : sc->engKin_f);
+    float ke_own = glob == 2 ? (float)red[1] : sc->engKin_f;
     chit += P.tSt * (ke - P.teKin) * P.rQmass;             // before_nose
     const float ts = 1.f - P.tSt * chit;
     ke = ke * ts * ts;                                     // after_nose(refresh_kin = 1)
+    ke_own = glob ? ke_own * ts * ts : ke;
     sc->consInt += P.tSt * chit * P.qMassTau2;
     chit += P.tSt * (ke - P.teKin) * P.rQmass;
-    sc->chit = chit; sc->nose_scale = ts; sc->engKin_f = ke; sc->engKin = (double)ke;
+    sc->chit = chit; sc->nose_scale = ts; sc->keGlob = ke; sc->engKin_f = ke_own; sc->engKin = (double)ke_own;
 }
 
 static __global__ void __launch_bounds__(AZ_TPB)

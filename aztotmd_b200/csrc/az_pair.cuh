@@ -761,6 +761,7 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 // iR = (int)(sqrt((double)r2) * idRDF), iPair = mn * (nSpec - 1) + mn * (1 - mn) / 2 + mx.
 struct AzRdfArgs {
     const float4* pos; const int* cellOfSorted; const int* first; const int* count;
+    const int* id;            // bricks: persistent ids of the sorted atoms, ghosts included (NULL on one GPU)
     unsigned long long* hist; // [nbins * npair], bin-major like md->rdf
     int sten[3];
     int nbins, npair;
@@ -788,11 +789,15 @@ az_k_rdf(const __grid_constant__ AzParams P, const __grid_constant__ AzRdfArgs A
         const int gcy = g.olo[1] + cxy % ony + g.goff[1];
         const int gcx = g.olo[0] + cxy / ony + g.goff[0];
         const int m = P.nspec - 1;
+        const int idi = A.id ? A.id[i] : 0;
         auto sweep = [&](const int rb, const int re, const int code) {
             const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
             const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
             const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
-            for (int j = max(rb, i + 1) + lane; j < re; j += 32) { // j > i: every unordered pair once
+            // every unordered pair once: j > i on one GPU; on bricks the pair belongs to the brick that owns the atom with
+            // the lower persistent id (the other brick sees the same pair with the roles of owner and ghost exchanged)
+            for (int j = (A.id ? rb : max(rb, i + 1)) + lane; j < re; j += 32) {
+                if (A.id && A.id[j] <= idi) continue;
                 const float4 pj = __ldg(A.pos + j);
                 float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                 if (code) { dx -= shx; dy -= shy; dz -= shz; }

@@ -13,7 +13,7 @@ from aztotmd_b200 import abi
 from aztotmd_b200.engine import AzError, Engine, unique_comm_id
 
 
-def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=None, **kw):
+def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=None, rdf=None, **kw):
     """Advance `system` on n_ranks bricks; returns per-rank results gathered after the last step."""
     cid = unique_comm_id(lib)
     out = [None] * n_ranks
@@ -32,13 +32,19 @@ def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=N
             # multi-thread caveat); with one process per GPU (bench.py, production) this cannot happen
             barrier.wait()
             e.set_option("energy_every_step", 1)
+            if rdf:
+                e.rdf_begin(*rdf)
             stats = []
             for k in range(nsteps):
                 e.step(k, 1)
                 stats.append(e.stats())
+                if rdf:
+                    e.rdf_sample()
             d = e.dump()
             a = e.download(abi.ORDER_SORTED)
             out[r] = dict(stats=stats, dump=d, atoms=a, info=e.info)
+            if rdf:
+                out[r]["rdf"] = e.rdf_counts()  # collective: the histogram of the whole box on every rank
             barrier.wait()
             e.close()
         except Exception as ex:  # noqa: BLE001
@@ -144,6 +150,36 @@ def case_bricks_ewald_reciprocal(lib, devices=None):
     res = check_against_single(lib, s, 2, (2, 1, 1), nsteps=2, devices=devices)
     assert res[0]["stats"][0].engCoul2 > 1.0
     check_against_single(lib, s, 2, (2, 1, 1), nsteps=2, distributed=True, devices=devices)
+
+
+def case_bricks_rdf_histogram_is_global_and_exact(lib, devices=None):
+    """SURVEY 8f-1 on bricks: every unordered pair is counted by the brick that owns the atom with the lower id; the
+    all-reduced integer histogram equals the reference's O(N^2) brute_rdf counts (oracle) exactly."""
+    for s, pg, r_max, dr in ((azt.lj_system(ncell=(8, 5, 5), seed=31), (2, 1, 1), 7.0, 0.1),
+                             (azt.nacl_system(ncell=(7, 7, 5), elec=abi.ELEC_FENNEL, r_real=9.0, rc_vdw=9.0, cell_size=9.0), (2, 2, 1), 8.0, 0.05)):
+        nr = pg[0] * pg[1] * pg[2]
+        res = run_bricks(lib, s, nr, pg, 1, devices=devices, rdf=(r_max, dr))
+        o = azt.Oracle(s)
+        o.step(0, 1)
+        counts, ns = res[0]["rdf"]
+        ref = o.rdf_counts(r_max, dr, counts.shape[0], counts.shape[1])
+        assert ns == 1 and counts.sum() > 1000
+        for r in res:
+            assert np.array_equal(r["rdf"][0], ref), (int(np.abs(r["rdf"][0].astype(np.int64) - ref.astype(np.int64)).sum()), int(ref.sum()))
+
+
+def case_bricks_nose_hoover_uses_global_kinetic_energy(lib, devices=None):
+    """SURVEY 8f-2 on bricks: the friction recurrence runs on the all-reduced kinetic energy, identically on every rank;
+    energies, forces and velocities follow the single-GPU engine, with and without the equilibration rescale."""
+    s = azt.lj_system(ncell=(8, 5, 5), seed=33, temperature=300.0, tstat=abi.TSTAT_NOSE)
+    s.temperature = 120.0
+    s.tstat_tau = 0.02
+    res = check_against_single(lib, s, 2, (2, 1, 1), nsteps=5, devices=devices)
+    ke0 = 1.5 * len(s.pos) * 300.0 * 8.617e-5
+    assert res[0]["stats"][-1].engKin_d < 0.95 * ke0  # the thermostat acted
+    s = azt.lj_system(ncell=(8, 5, 5), seed=34, temperature=150.0, tstat=abi.TSTAT_NOSE, n_equil=4, eq_freq=2)
+    s.tstat_tau = 0.05
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=5, devices=devices)
 
 
 def case_bricks_verlet_list_between_rebuilds(lib, devices=None):
