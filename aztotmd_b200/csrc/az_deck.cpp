@@ -17,7 +17,7 @@
 // reciprocal Ewald) are rejected with AZ_ERR_UNSUPPORTED instead of being silently
 // dropped.  Random draws (photon energies, Gaussian velocities) come from a seeded counter-based
 // generator, not from the time-seeded rand() of src/main.cu:242 -- extra keys: `seed N` in
-// control.txt; `rebuild N`, `skin X`, `device N` in cuda.txt (the reference ignores unknown words).
+// control.txt; `rebuild N`, `skin X`, `device N`, `graph 0|1` in cuda.txt (the reference ignores unknown words).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -339,6 +339,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     { int v; float s; // extensions; 'nthread a/b' of the reference are accepted and ignored
         if (scan_first(f, " rebuild %d", &v)) d->opts.rebuild_every = v;
         if (scan_first(f, " skin %f", &s)) d->opts.skin = s;
+        if (scan_first(f, " graph %d", &v)) d->opts.use_graph = v; // replay the step loop between two 'stat' samples as one CUDA graph
         if (scan_first(f, " device %d", &v)) d->opts.device = v;
     }
     fclose(f); f = nullptr;

@@ -45,9 +45,12 @@ struct AzGrid {
 // linear local coordinate (including ghost layers) -> storage cell id
 __device__ __forceinline__ int az_cell_id(const AzGrid& g, int lin) { return g.cellmap ? g.cellmap[lin] : lin; }
 
+// the step a kernel works on: its launch argument, plus the device-resident base when the launch is part of a replayed graph
+#define AZ_STEP(P, k) ((k) + ((P).step_base ? *(P).step_base : 0))
 struct AzParams {
     int n_local;        // atoms resident on this GPU that take part as i-atoms (owned); launch bound when n_dyn is set
     const int* n_dyn;   // domain decomposition: device-resident owned-atom count (AzDDCounts::n_owned), else NULL
+    const int* step_base; // CUDA-graph replay: kernels receive the step RELATIVE to the first step of the call and add *step_base; else NULL
     int nspec;
     float L[3], revL[3];
     float tSt;

@@ -289,6 +289,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     e->n = d->n_atoms;
     e->n_global = d->n_atoms_global > 0 ? (int)d->n_atoms_global : d->n_atoms;
     e->rebuild_every = (o && o->rebuild_every > 1) ? o->rebuild_every : 1;
+    e->use_graph = o && o->use_graph != 0 && !(o->n_ranks > 1); // bricks: NCCL calls sit between the kernels of a step
     e->n_ranks = (o && o->n_ranks > 1) ? o->n_ranks : 1;
     e->rank = o ? o->rank : 0;
     AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -372,6 +373,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
       if (e->warp_nblocks > np) np = e->warp_nblocks;
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
+    if (e->use_graph) { AZ_ALLOC(e, e->step0_dev, 1); e->P.step_base = e->step0_dev; }
     AZ_ALLOC(e, e->table, e->h_table.size());
     AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
     if (e->dd) { rc = dd_alloc(e); if (rc) return rc; rc = dd_store_keep(e, d); if (rc) return rc; }
@@ -437,6 +439,11 @@ extern "C" void az_engine_destroy(az_engine* e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     dd_free(e);
     for (int k = 0; k < 2; k++) { cudaFree(e->pos[k]); cudaFree(e->vel[k]); cudaFree(e->id[k]); cudaFree(e->therm[k]); }
+#ifndef AZ_EMU
+    for (auto& g : e->graphs) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+#endif
+    e->graphs.clear();
+    cudaFree(e->step0_dev);
     cudaFree(e->ew_ak); cudaFree(e->ew_pairs); cudaFree(e->ew_runs); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
@@ -602,6 +609,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     int c = e->cur;
     const int n_pp = e->use_list ? e->list_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks); // live pair partials this step
     const int slot = (int)(e->steps_done & 1);
+    const int ks = P.step_base ? step - e->call_first : step; // what the kernels get: relative when *step_base supplies the rest
 
     const bool nose = (P.tstat == AZ_TSTAT_NOSE);
     if (nose) { // first application of the step, before verlet_1stage (src/main.cu:291-299)
@@ -706,7 +714,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     if (e->ew.nk) { int rc = ewald_step(e, c); if (rc) return rc; }
     if (ride) {
         Timer t(e, AZ_TIMER_INTEGRATE_B);
-        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
+        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
                   e->partU, 0, e->partN, e->pos[c], e->sc, e->revArea[0], e->revArea[1], e->revArea[2]);
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1);
     } else
@@ -723,7 +731,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
                 // the next step's kick + drift rides on this pass; its mode follows the next step's schedule
                 const bool rb_next = step_rebuilds(e);
                 const int ns = 1 - slot;
-#define AZ_BA(TS, MODE) AZ_LAUNCH((az_k_integrate_ba<TS, MODE>), nb, AZ_TPB, 0, st, P, step, ns, e->pos[c], e->vel[c], e->frc, e->id[c], th, ph, uv, \
+#define AZ_BA(TS, MODE) AZ_LAUNCH((az_k_integrate_ba<TS, MODE>), nb, AZ_TPB, 0, st, P, ks, ns, e->pos[c], e->vel[c], e->frc, e->id[c], th, ph, uv, \
                                   e->partKE, e->partU, e->cellOf, e->slotOf, e->cellCount, e->sc)
                 if (rb_next && e->dd) { if (radi) AZ_BA(true, AZ_IA_WRAP); else AZ_BA(false, AZ_IA_WRAP); }
                 else if (rb_next) {
@@ -733,41 +741,41 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
 #undef AZ_BA
             } else if (reset_now) { // zero_vel instead of verlet_2stage (src/main.cu:372-374); apply_tstat still runs the thermostat
                 AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
-                if (radi) { AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 0); AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1); }
+                if (radi) { AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 0); AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1); }
             } else if (radi) {
-                AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
             } else {
-                AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
             }
             const int radi_mode = radi ? 4 : 0;
             if (nose) { // second application of the step (apply_tstat): needs this step's kinetic energy, then the quantities
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
                 if (e->dd) { int rc = dd_global_nose(e); if (rc) return rc; }
                 else AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, 0);
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 3);
             } else
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | emode | radi_mode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | radi_mode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
             if (reset_now) AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
-            else AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            else AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (e->dd) { int rc = dd_global_tscale(e); if (rc) return rc; }
-            if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 1);
-            else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, step, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU, 1);
+            if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 1);
+            else AZ_LAUNCH(az_k_tscale<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->sc, e->partU, 1);
             if (nose) { // apply_tstat: the rescale comes first, then the thermostat (src/cuTemp.cu:777-794)
                 AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, e->dd ? 1 : 0); // bricks: keGlob = teKin after the rescale
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
             }
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, step, slot, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
         }
@@ -778,11 +786,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     return AZ_OK;
 }
 
-extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
+static int run_steps(az_engine* e, int first_step, int nsteps)
 {
-    if (!e) return AZ_ERR_INVALID;
-    if (nsteps < 0) { AZ_SET_ERR(e, "nsteps < 0"); return AZ_ERR_INVALID; }
-    AZ_CUDA(e, cudaSetDevice(e->device));
     bool a_done = false; // the fused kernel of the previous step already did this step's kick + drift
     for (int k = 0; k < nsteps; k++) {
         const int step = first_step + k;
@@ -796,6 +801,102 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         if (rc) return rc;
         a_done = fuse;
     }
+    return AZ_OK;
+}
+
+static __global__ void az_k_set_int(int* p, int v) { *p = v; }
+
+#ifndef AZ_EMU
+// What decides the launch sequence of a call, apart from the step numbers the kernels read from the device: the number
+// of steps, where the engine stands in its rebuild / buffer ping-pong cycle, and which steps rescale or zero velocities.
+static unsigned long long graph_key(const az_engine* e, int first_step, int nsteps)
+{
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
+    mix((unsigned long long)nsteps); mix((unsigned long long)e->since_rebuild); mix(e->binned ? 1 : 0); mix((unsigned long long)(e->steps_done & 1));
+    mix((unsigned long long)e->cur); mix(e->energy_every_step ? 1 : 0); mix(e->fuse_integrate ? 1 : 0);
+    mix((unsigned long long)(uintptr_t)e->pos[0]); mix((unsigned long long)(uintptr_t)e->pos[1]); mix((unsigned long long)(uintptr_t)e->pos_alt);
+    mix((unsigned long long)(uintptr_t)e->vel[0]); mix((unsigned long long)(uintptr_t)e->vel[1]); mix((unsigned long long)(uintptr_t)e->vel_alt);
+    for (int k = 0; k < nsteps; k++) {
+        const int step = first_step + k;
+        const int bits = (is_eq_step(e, step) ? 1 : 0) | ((e->reset_vels > 0 && step % e->reset_vels == 0) ? 2 : 0);
+        if (bits) { mix((unsigned long long)k); mix((unsigned long long)bits); }
+    }
+    // the pressure ring switches behaviour at step AZ_N_MOM - 1 inside the kernel: no host decision depends on it
+    return h;
+}
+
+static az_engine::GraphEnd graph_end_state(const az_engine* e)
+{
+    az_engine::GraphEnd g;
+    g.cur = e->cur; g.since_rebuild = e->since_rebuild; g.binned = e->binned;
+    for (int k = 0; k < 2; k++) { g.pos[k] = e->pos[k]; g.vel[k] = e->vel[k]; }
+    g.pos_alt = e->pos_alt; g.vel_alt = e->vel_alt; g.clear_counts_bytes = e->clear_counts_bytes;
+    g.launches = e->launches;
+    for (int k = 0; k < AZ_N_TIMERS; k++) g.t_launch[k] = e->t_launch[k];
+    return g;
+}
+#endif
+
+extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
+{
+    if (!e) return AZ_ERR_INVALID;
+    if (nsteps < 0) { AZ_SET_ERR(e, "nsteps < 0"); return AZ_ERR_INVALID; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    if (!e->use_graph || nsteps == 0) {
+        int rc = run_steps(e, first_step, nsteps);
+        if (rc) return rc;
+        AZ_CUDA(e, cudaGetLastError());
+        return AZ_OK;
+    }
+    // graph mode: the kernels take their step from the device (*step0_dev + index inside the call)
+    e->call_first = first_step;
+    AZ_LAUNCH(az_k_set_int, 1, 1, 0, e->stream, e->step0_dev, first_step);
+    e->launches++;
+#ifdef AZ_EMU
+    int rc = run_steps(e, first_step, nsteps); // no graph API in the host emulator: same kernels, same relative steps
+    if (rc) return rc;
+#else
+    if (e->profile != 0) { // per-section timers need the plain launches
+        int rc = run_steps(e, first_step, nsteps);
+        if (rc) return rc;
+        AZ_CUDA(e, cudaGetLastError());
+        return AZ_OK;
+    }
+    const unsigned long long key = graph_key(e, first_step, nsteps);
+    for (auto& g : e->graphs)
+        if (g.key == key) { // replay: one launch for the whole call, then put the host-side cycle where the call leaves it
+            AZ_CUDA(e, cudaGraphLaunch((cudaGraphExec_t)g.exec, e->stream));
+            const long long l0 = g.end.launches;
+            e->cur = g.end.cur; e->since_rebuild = g.end.since_rebuild; e->binned = g.end.binned;
+            for (int k = 0; k < 2; k++) { e->pos[k] = g.end.pos[k]; e->vel[k] = g.end.vel[k]; }
+            e->pos_alt = g.end.pos_alt; e->vel_alt = g.end.vel_alt; e->clear_counts_bytes = g.end.clear_counts_bytes;
+            e->launches += l0; // the kernels the graph holds
+            for (int k = 0; k < AZ_N_TIMERS; k++) e->t_launch[k] += g.end.t_launch[k];
+            e->steps_done += nsteps; e->last_step = first_step + nsteps - 1; e->energy_valid = true;
+            e->graph_replays++;
+            return AZ_OK;
+        }
+    // first call of this shape: record the launches instead of running them, then run the recording
+    const az_engine::GraphEnd before = graph_end_state(e);
+    AZ_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+    int rc = run_steps(e, first_step, nsteps);
+    cudaGraph_t graph = nullptr;
+    cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (cerr != cudaSuccess) { AZ_SET_ERR(e, "cudaStreamEndCapture: %s", cudaGetErrorString(cerr)); return AZ_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    cerr = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (cerr != cudaSuccess) { AZ_SET_ERR(e, "cudaGraphInstantiate: %s", cudaGetErrorString(cerr)); return AZ_ERR_CUDA; }
+    az_engine::GraphEntry ent;
+    ent.key = key; ent.exec = (void*)exec; ent.end = graph_end_state(e);
+    ent.end.launches -= before.launches; // deltas
+    for (int k = 0; k < AZ_N_TIMERS; k++) ent.end.t_launch[k] -= before.t_launch[k];
+    if (e->graphs.size() >= 16) { cudaGraphExecDestroy((cudaGraphExec_t)e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+    e->graphs.push_back(ent);
+    AZ_CUDA(e, cudaGraphLaunch(exec, e->stream));
+#endif
     AZ_CUDA(e, cudaGetLastError());
     return AZ_OK;
 }
@@ -1187,6 +1288,7 @@ extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
     o->n_sm = e->n_sm; o->device_bytes = (long long)e->dev_bytes;
     o->list_rows = e->nbr_cap;
     o->capacity = e->dd ? e->P.n_local : e->n; o->n_ranks = e->n_ranks;
+    o->graph_replays = e->graph_replays; o->graphs_cached = (int)e->graphs.size();
     if (e->sc) {
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -27,6 +27,15 @@ struct az_engine {
     int last_step = -1;
     long long steps_done = 0;
     bool fuse_integrate = true; // second half kick of step n and kick + drift of step n+1 in one pass
+    // az_cuda_opts.use_graph: az_engine_step(first, n) is captured once per call shape as a CUDA graph and replayed (the
+    // latency-bound decks are launch-gap bound); kernels then read the step from *step0_dev + their relative index
+    bool use_graph = false;
+    int* step0_dev = nullptr;
+    int call_first = 0;
+    struct GraphEnd { int cur, since_rebuild; bool binned; float4 *pos[2], *vel[2], *pos_alt, *vel_alt; size_t clear_counts_bytes; long long launches, t_launch[AZ_N_TIMERS]; };
+    struct GraphEntry { unsigned long long key; void* exec; GraphEnd end; };
+    std::vector<GraphEntry> graphs;
+    long long graph_replays = 0;
     // pair kernel configuration
     int pair_vk = 0, pair_ck = 0;
     bool pair_single = false, pair_radii = false;

@@ -356,11 +356,12 @@ void az_tstat_radi_atom(const AzParams& P, int step, int pid, int tp, float pe,
 // Partial sums go to per-block slots; az_k_finalize reduces them in a fixed order.
 template <bool TSTAT>
 __global__ void __launch_bounds__(AZ_TPB)
-az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __restrict__ pos,
+az_k_integrate_b(const __grid_constant__ AzParams P, int step_k, const float4* __restrict__ pos,
                  float4* __restrict__ vel, const float4* __restrict__ frc, const int* __restrict__ id,
                  float2* __restrict__ therm, const float* __restrict__ photons,
                  const float* __restrict__ uv, double* __restrict__ partKE, double* __restrict__ partU)
 {
+    const int step = AZ_STEP(P, step_k);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0, ut = 0.0;
     if (i < az_n_owned(P)) {
@@ -388,12 +389,13 @@ az_k_integrate_b(const __grid_constant__ AzParams P, int step, const float4* __r
 // of 64 B + 80 B for the two passes.  Used inside az_engine_step for consecutive steps of one call.
 template <bool TSTAT, int MODE>
 __global__ void __launch_bounds__(AZ_TPB)
-az_k_integrate_ba(const __grid_constant__ AzParams P, int step, int slot_next, float4* __restrict__ pos, float4* __restrict__ vel,
+az_k_integrate_ba(const __grid_constant__ AzParams P, int step_k, int slot_next, float4* __restrict__ pos, float4* __restrict__ vel,
                   const float4* __restrict__ frc, const int* __restrict__ id, float2* __restrict__ therm,
                   const float* __restrict__ photons, const float* __restrict__ uv, double* __restrict__ partKE,
                   double* __restrict__ partU, int* __restrict__ cellOf, int* __restrict__ slotOf, int* __restrict__ cellCount,
                   AzScalars* __restrict__ sc)
 {
+    const int step = AZ_STEP(P, step_k);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0, ut = 0.0, eF = 0.0;
     float v2 = 0.f;
@@ -423,11 +425,12 @@ az_k_integrate_ba(const __grid_constant__ AzParams P, int step, int slot_next, f
 // temp_scale (src/cuTemp.cu:77-107) [+ tstat_radi9] on an equilibration step.
 template <bool TSTAT>
 __global__ void __launch_bounds__(AZ_TPB)
-az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restrict__ pos,
+az_k_tscale(const __grid_constant__ AzParams P, int step_k, const float4* __restrict__ pos,
             float4* __restrict__ vel, const int* __restrict__ id, float2* __restrict__ therm,
             const float* __restrict__ photons, const float* __restrict__ uv,
             const AzScalars* __restrict__ sc, double* __restrict__ partU, int use_k)
 {
+    const int step = AZ_STEP(P, step_k);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ut = 0.0;
     float k = use_k ? sc->tscale_k : 1.f; // use_k == 0: thermostat only (a 'reset_vels' step: zero_vel, then apply_tstat)
@@ -455,11 +458,12 @@ az_k_tscale(const __grid_constant__ AzParams P, int step, const float4* __restri
 // 4 = thermal energy, 8 = this is an equilibration T-scale step (computes tscale_k, after_tscale),
 // 16 = calc_quantities (src/main.cu:121-162) and publish, 32 = rebuild step, 64 = stale-cell step.
 static __global__ void __launch_bounds__(1024)
-az_k_finalize(const __grid_constant__ AzParams P, int step, int slot, int mode, const double* __restrict__ partKE, int nKE,
+az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode, const double* __restrict__ partKE, int nKE,
               const double* __restrict__ partV, const double* __restrict__ partC, int nPair,
               const double* __restrict__ partU, int nU, const unsigned long long* __restrict__ partN, const float4* __restrict__ pos, AzScalars* __restrict__ gsc,
               float revAx, float revAy, float revAz)
 {
+    const int step = AZ_STEP(P, step_k);
     __shared__ double sm[4 * 32];
     // The scalar block is staged in shared memory: the bookkeeping below is ~60 dependent read-modify-writes by one
     // thread, which cost a global-memory round trip each when done in place (16 us per step) and nothing here.

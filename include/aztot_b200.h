@@ -168,7 +168,9 @@ typedef struct az_cuda_opts {
     int device;          /* CUDA device ordinal                                       */
     int rebuild_every;   /* 0/1 = reference behaviour (bin + sort every step)         */
     float skin;          /* extra cell width when rebuild_every > 1 (Angstrom)        */
-    int use_graph;       /* reserved (a step is 2-3 launches on one stream; no graph capture yet) */
+    int use_graph;       /* 1: az_engine_step(first, n) is captured as a CUDA graph the first time a call shape (n, position in
+                            the rebuild cycle) occurs and replayed afterwards -- for the latency-bound decks whose step is
+                            6-7 short kernels; single GPU only; per-section timers (az_engine_profile) switch it off */
     int pair_variant;    /* 0 = auto (Verlet list between rebuilds and for large systems, warp-per-atom cell sweep
                             for small systems on the every-step schedule), 1 = shared-memory cell tiles,
                             2 = list (rebuilt every step if rebuild_every <= 1), 3 = warp-per-atom sweep */
@@ -324,6 +326,8 @@ typedef struct az_engine_info_t {
     int list_rows, flags;  /* list capacity per atom; raw sticky device flags */
     int capacity;          /* most atoms az_engine_download / az_engine_debug_dump can hand back (a brick's owned capacity) */
     int n_ranks;
+    long long graph_replays; /* az_engine_step calls served by replaying a captured CUDA graph (az_cuda_opts.use_graph) */
+    int graphs_cached, reserved;
 } az_engine_info_t;
 int az_engine_info(az_engine *e, az_engine_info_t *out);
 

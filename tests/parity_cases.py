@@ -382,6 +382,31 @@ def case_fused_kick_drift_is_bitwise_the_separate_kernels(lib):
         a.close(); b.close(); c.close()
 
 
+def case_graph_replay_is_bitwise_the_plain_launches(lib):
+    """az_cuda_opts.use_graph: a call is captured once per shape and replayed; the kernels read the step from the device
+    (thermostat RNG counter, pressure ring).  Trajectories, thermostat state and statistics must be BITWISE those of the
+    plain launches, over repeated calls of the same and of different lengths, on the every-step schedule with the
+    radiative thermostat and on the list path with a rebuild interval and the riding integrator.  (On the host emulator
+    there is no graph API: the same relative-step kernels run as plain launches.)"""
+    systems = [(azt.surk_system(n_side=5, spacing=1.3, box=30.0), {}),
+               (azt.lj_system(ncell=(6, 6, 6), seed=95, cell_size=9.3, n_equil=6, eq_freq=3), dict(rebuild_every=4, skin=0.8)),
+               (azt.lj_system(ncell=(5, 5, 5), seed=96, tstat=abi.TSTAT_RADI), {})]
+    for s, kw in systems:
+        a, b = Engine(s, lib=lib, **kw), Engine(s, lib=lib, use_graph=True, **kw)
+        step = 0
+        for n in (3, 4, 4, 4, 1, 4, 7, 7):   # repeated shapes are replays
+            a.step(step, n); b.step(step, n)
+            step += n
+            da, db = a.dump(), b.dump()
+            assert np.array_equal(da["pos"], db["pos"]) and np.array_equal(da["vel"], db["vel"]) and np.array_equal(da["frc"], db["frc"]), step
+            sa, sb = a.stats(), b.stats()
+            for k in ("engKin_d", "engVdW_d", "engTemp_d", "engTot", "pressure", "n_pairs", "step"):
+                assert getattr(sa, k) == getattr(sb, k), (k, step, getattr(sa, k), getattr(sb, k))
+        ta, tb = a.download(abi.ORDER_ORIGINAL), b.download(abi.ORDER_ORIGINAL)
+        assert np.array_equal(ta["engs"], tb["engs"], equal_nan=True) and np.array_equal(ta["radii"], tb["radii"], equal_nan=True)
+        a.close(); b.close()
+
+
 def case_tile_kernel_variant(lib):
     """pair_variant = 1: the shared-memory cell-tile sweep (one thread per atom) instead of the default
     warp-per-atom sweep -- same parity bars."""
@@ -542,5 +567,6 @@ ALL_CASES = [
     ("tile_kernel_variant", case_tile_kernel_variant),
     ("list_every_step_variant", case_list_every_step_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
+    ("graph_replay", case_graph_replay_is_bitwise_the_plain_launches),
     ("error_paths", case_error_paths),
 ]
