@@ -68,13 +68,26 @@ def main():
     cases = [("lj 2x1x1 every step", azt.lj_system(ncell=(8, 5, 5), seed=51), (2, 1, 1), {}, 3),
              ("lj 1x1x2 list", azt.lj_system(ncell=(5, 5, 8), seed=52, cell_size=9.3), (1, 1, 2), dict(rebuild_every=4, skin=0.8), 6),
              ("ionic 2x1x1", azt.nacl_system(ncell=(7, 5, 5), elec=abi.ELEC_FENNEL, r_real=9.0, rc_vdw=9.0, cell_size=9.0), (2, 1, 1), {}, 2)]
+    # SURVEY 8f rows on bricks: the all-reduced structure factor of the Ewald sum, the Nose-Hoover friction on the
+    # all-reduced kinetic energy, the RDF histogram all-reduced at read time
+    pme = azt.nacl_system(ncell=(7, 5, 5), elec=abi.ELEC_EWALD, alpha=0.3, jitter=0.4, ewald_k=(7, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.0)
+    nose = azt.lj_system(ncell=(8, 5, 5), seed=53, temperature=300.0, tstat=abi.TSTAT_NOSE)
+    nose.temperature = 120.0
+    nose.tstat_tau = 0.02
+    cases += [("ionic pme 2x1x1", pme, (2, 1, 1), {}, 2), ("lj nose-hoover + rdf 2x1x1", nose, (2, 1, 1), {}, 3)]
     for name, s, pgrid, kw, nsteps in cases:
+        rdf = (7.0, 0.1) if "rdf" in name else None
         e = Engine(s, lib=lib, rank=rank, n_ranks=world, pgrid=pgrid, comm_id=b"\0" * 128, **kw)
         e.set_option("energy_every_step", 1)
+        if rdf:
+            e.rdf_begin(*rdf)
         stats = []
         for k in range(nsteps):
             e.step(k, 1)
             stats.append(e.stats())
+            if rdf and k == 0:
+                e.rdf_sample()
+        rdf_counts = e.rdf_counts()[0] if rdf else None  # collective
         d = e.dump()
         a = e.download(abi.ORDER_SORTED)
         mine = dict(ids=d["ids"], frc=d["frc"], pos=a["pos"], vel=a["vel"], aid=a["ids"])
@@ -85,10 +98,16 @@ def main():
             lib.az_emu_set_comm_callbacks(EX_CB(), AR_CB())  # single engine below: no transport
             e1 = Engine(s, lib=lib, **kw)
             e1.set_option("energy_every_step", 1)
+            if rdf:
+                e1.rdf_begin(*rdf)
             n = len(s.pos)
             for k in range(nsteps):
                 e1.step(k, 1)
                 s1 = e1.stats()
+                if rdf and k == 0:
+                    e1.rdf_sample()
+                    assert np.array_equal(rdf_counts, e1.rdf_counts()[0]) and rdf_counts.sum() > 1000, name
+                assert abs(stats[k].engCoul2_d - s1.engCoul2_d) <= 1e-4 * max(abs(s1.engCoul2_d), 1e-9) and abs(stats[k].engCoul3 - s1.engCoul3) <= 1e-4 * max(abs(s1.engCoul3), 1e-9), name
                 sc = max(abs(s1.engVdW_d), abs(s1.engCoul1_d), abs(s1.engKin_d), 1e-9)
                 assert abs(stats[k].engVdW_d - s1.engVdW_d) <= 1e-4 * sc and abs(stats[k].engKin_d - s1.engKin_d) <= 1e-4 * sc, name
                 assert stats[k].n_pairs == s1.n_pairs, (name, k, stats[k].n_pairs, s1.n_pairs)

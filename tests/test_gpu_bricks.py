@@ -8,7 +8,8 @@ from aztotmd_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
-NEED = {"eight_bricks_2x2x2_ionic": 8, "four_bricks_2x2": 4, "distributed_input_with_ids": 4}
+NEED = {"eight_bricks_2x2x2_ionic": 8, "four_bricks_2x2": 4, "distributed_input_with_ids": 4,
+        "bricks_rdf_histogram_is_global_and_exact": 4}
 
 
 @pytest.fixture(scope="module")
@@ -24,4 +25,6 @@ def test_bricks_over_nccl(lib, name, case):
         need = 1
     if have < need:
         pytest.skip("needs %d GPUs, this box has %d" % (need, have))
-    case(lib, devices=list(range(8)))
+    # run_bricks skips (instead of waiting for ranks that can never join the communicator) if a case asks for more ranks
+    # than devices are listed here
+    case(lib, devices=list(range(have)))
