@@ -1219,7 +1219,8 @@ extern "C" int az_engine_rdf_read(az_engine* e, unsigned long long* counts, int 
         if (capacity < e->rdf_nbins * e->rdf_npair) { AZ_SET_ERR(e, "rdf: capacity %d < %d", capacity, e->rdf_nbins * e->rdf_npair); return AZ_ERR_INVALID; }
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));
-        AZ_CUDA(e, cudaMemcpy(counts, e->rdf_hist, sizeof(unsigned long long) * e->rdf_nbins * e->rdf_npair, cudaMemcpyDeviceToHost));
+        AZ_CUDA(e, cudaMemcpyAsync(counts, e->rdf_hist, sizeof(unsigned long long) * e->rdf_nbins * e->rdf_npair, cudaMemcpyDeviceToHost, e->stream));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream)); // like fetch_scalars: no legacy-stream copy while a peer may sit in a collective
         if (e->dd) { // collective: every rank gets the histogram of the whole box (integers below 2^53 are exact in the double all-reduce)
             const int nh = e->rdf_nbins * e->rdf_npair;
             std::vector<double> v(128);

@@ -1,6 +1,6 @@
 """Domain decomposition LOGIC on the CPU: the brick cases of tests/brick_cases.py on the emulator build
 (kernels compiled by g++ against tests/emu/cuda_emu.h, ranks talk through an in-process mailbox).  The
-NCCL build of the same code runs the same cases in tests/test_gpu_bricks.py on the GPU box."""
+NCCL build of the same code runs the same cases in tests/test_gpu_z_bricks.py on the GPU box."""
 import pytest
 
 import azt

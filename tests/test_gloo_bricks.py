@@ -1,6 +1,6 @@
 """world_size-2 test of the N > 1 path on the CPU with torch.distributed's gloo backend: two real processes
 (torchrun), one emulator-build engine each, halo exchange / migration / all-reduce carried by gloo
-send/recv/all_reduce (tests/gloo_brick_worker.py).  The production transport is NCCL (tests/test_gpu_bricks.py)."""
+send/recv/all_reduce (tests/gloo_brick_worker.py).  The production transport is NCCL (tests/test_gpu_z_bricks.py)."""
 import os
 import subprocess
 import sys

@@ -1,6 +1,7 @@
 """Domain decomposition on real GPUs: the brick cases of tests/brick_cases.py with NCCL between the
 devices of one box.  Needs >= 2 GPUs (gpurun --gpus 2/4/8); cases that need more devices than the box
-has are skipped -- loudly, with the count in the reason."""
+has are skipped -- loudly, with the count in the reason.  (The file name sorts behind test_gpu_parity.py on purpose:
+the single-GPU parity tests run first.)"""
 import pytest
 
 import brick_cases
