@@ -26,4 +26,9 @@ if [ ! -f "$OUT/cuda_emu.o" ] || [ "$HERE/cuda_emu.cpp" -nt "$OUT/cuda_emu.o" ] 
 fi
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 $CXX -shared -o "$OUT/libaztot_emu.so" "$OUT"/*.o -lpthread -lm
+# the host driver (az_main.cpp + the deck parser) linked against the emulator engine: the process surface of the
+# reference (decks in, stat.dat / msd.dat / rdf.dat / revcon.xyz out) can then be tested without a GPU
+if [ ! -f "$OUT/aztotmd_emu" ] || [ "$SRC/az_main.cpp" -nt "$OUT/aztotmd_emu" ] || [ "$SRC/az_deck.cpp" -nt "$OUT/aztotmd_emu" ] || [ "$OUT/libaztot_emu.so" -nt "$OUT/aztotmd_emu" ]; then
+  $CXX -O2 -std=c++17 -I"$ROOT/include" "$SRC/az_main.cpp" "$SRC/az_deck.cpp" -o "$OUT/aztotmd_emu" -L"$OUT" -laztot_emu -Wl,-rpath,'$ORIGIN' -lpthread -lm
+fi
 echo "built $OUT/libaztot_emu.so"
