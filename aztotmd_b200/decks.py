@@ -99,7 +99,7 @@ def lj_argon_deck(dirname, ncell, *, rho_star=0.8442, rc_sigma=2.5, temperature=
 
 
 def nacl_deck(dirname, ncell, *, a=5.9, rc_vdw=9.0, r_real=12.0, alpha=0.2, temperature=1200.0,
-              nstep=100, elec="fenn", init_vel="gaus", jitter=0.05, seed=2, cell_list=None, stat=1000):
+              nstep=100, elec="fenn", init_vel="gaus", jitter=0.05, seed=2, cell_list=None, stat=1000, ewald_k=(6, 6, 6)):
     """Rock-salt NaCl-like melt (config 4): Buckingham (Tosi-Fumi-like) + real-space Coulomb."""
     if isinstance(ncell, int):
         ncell = (ncell, ncell, ncell)
@@ -115,7 +115,7 @@ def nacl_deck(dirname, ncell, *, a=5.9, rc_vdw=9.0, r_real=12.0, alpha=0.2, temp
     elif elec == "dir":
         el = "elec\tdir\t%g\n" % r_real
     elif elec == "pme":
-        el = "elec\tpme\t%g\t%g\t6\t6\t6\n" % (r_real, alpha)
+        el = "elec\tpme\t%g\t%g\t%d\t%d\t%d\n" % (r_real, alpha, ewald_k[0], ewald_k[1], ewald_k[2])
     else:
         el = "elec\tnone\n"
     ctl = (

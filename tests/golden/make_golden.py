@@ -70,6 +70,11 @@ def main():
         info = decks.nacl_deck(d, 5, rc_vdw=9.0, r_real=9.0, alpha=0.3, elec="pme", init_vel="zero", nstep=2, jitter=0.4)
         cases.append(("nacl5_buck_pme", d, "full", dict(kind="nacl", ncell=5, elec="pme", rc_vdw=9.0, r_real=9.0, alpha=0.3,
                                                         ewald_k=[6, 6, 6], jitter=0.4, box=[float(x) for x in info["box"]])))
+        # ... and an anisotropic box with different k ranges per axis: the k-space cut-off is the smallest of k_a / L_a
+        d = os.path.join(tmp, "nacl_pme_aniso")
+        info = decks.nacl_deck(d, (6, 5, 7), rc_vdw=9.0, r_real=9.0, alpha=0.3, elec="pme", init_vel="zero", nstep=2, jitter=0.4, ewald_k=(7, 5, 9))
+        cases.append(("nacl657_buck_pme", d, "full", dict(kind="nacl", ncell=(6, 5, 7), elec="pme", rc_vdw=9.0, r_real=9.0, alpha=0.3,
+                                                          ewald_k=[7, 5, 9], jitter=0.4, box=[float(x) for x in info["box"]])))
         only = sys.argv[1:]
         for name, d, mode, meta in cases:
             if only and name not in only:
