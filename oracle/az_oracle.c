@@ -26,6 +26,8 @@
  *   host narrowing       init_cudaMD            src/cuInit.cu:768-791,934-961
  *                        init_cuda_tstat        src/cuTemp.cu:11-62
  *   unit vectors         read_tstat             src/temperature.cpp:164-223
+ *   bonds / angles       bond_harm..bond_e6812, angle_hcos, delta_periodic   src/cuBonds.cu:1123-1224, src/cuAngles.cu:230-283,
+ *                        src/cuMDfunc.cu:178-203  (SURVEY 8f-4 GROUNDWORK: pinned arithmetic, no kernel yet)
  *   k-space Ewald        ewald_rec, ewald_const, prepare_elec   src/elec.cpp:144-165,167-336,376-397 (the serial
  *                        twin, double precision: the CUDA twin src/cuElec.cu:151-381 is compiled out, defines.h:18)
  *
@@ -589,6 +591,68 @@ static void forces(azo_state *s)
     }
     s->engVdW += evdw; s->engCoul1 += ecoul;
     s->n_pairs_in_range = npairs / 2;
+}
+
+/* ------------------------------------------------ bonds and angles (8f-4) ---- */
+/* GROUNDWORK for SURVEY 8f-4 (no kernel exists yet): the arithmetic of the reference's constant bonds and valence angles,
+ * pinned on the reference's own device source (tests/golden/ref_device_bonds_angles.npz).
+ * Bond potentials, src/cuBonds.cu:1123-1224; kind = the reference's type id (define_bond_potential, :1236-1270):
+ * 1 harmonic, 2 Morse, 3 Pedone (Morse + E/r^12), 4 Buckingham, 5 exp-6-8-12.  Returns -dU/dr / r, adds U to *eng.
+ * Double-precision literals of the reference (2.0, 12.0, 1.0 / r2) promote their sub-expressions exactly as there. */
+float azo_bond_eval(int kind, const float *p, float r2, float r, float *eng)
+{
+    const float p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4];
+    switch (kind) {
+    case 1: { float x = r - p1; *eng += 0.5f * p0 * x * x; return -p0 / r * x; }
+    case 2: {
+        float x = r - p2; x = expf(-p1 * x); float y = 1 - x;
+        *eng += p0 * y * y - p3;
+        return (float)(-2.0 * p0 * p1 * x * y / r);
+    }
+    case 3: {
+        float x = r - p2; x = expf(-p1 * x); float y = 1 - x;
+        float ir2 = 1.f / r2, irn = ir2 * ir2; irn = irn * irn * irn;
+        *eng += p0 * y * y - p3 - p4 * irn;
+        return (float)(-2.0 * p0 * p1 * x * y / r - 12.0 * p4 * irn * ir2);
+    }
+    case 4: {
+        float ir2 = (float)(1.0 / r2), irn = ir2 * ir2;
+        *eng += p0 * expf(-r / p1) - p2 * irn * ir2;
+        return p0 * expf(-r / p1) / r / p1 - 6.f * p2 * irn * irn;
+    }
+    case 5: {
+        float ir2 = (float)(1.0 / r2), irn = ir2 * ir2;
+        *eng += p0 * expf(-r / p1) - p2 * irn * ir2 - p3 * irn * irn - p4 * irn * irn * irn;
+        return (float)(p0 * expf(-r / p1) / r / p1 - 6.f * p2 * irn * irn - 8.f * p3 * irn * irn * ir2 - 12.0 * p4 * irn * irn * irn * ir2);
+    }
+    }
+    return 0.f;
+}
+
+/* delta_periodic, src/cuMDfunc.cu:178-203: minimum image of one coordinate difference in a rectangular box */
+static float delta_periodic1(float d, float L, float halfL) { if (d > halfL) d -= L; else if (d < -halfL) d += L; return d; }
+
+/* angle_hcos, src/cuAngles.cu:230-283: U = k/2 (cos th - cos th0)^2 on (centre, ligand 1, ligand 2) = xyz[0..2];
+ * frc[0..2] receive the three forces (the reference adds them with atomicAdd), *eng the energy */
+void azo_angle_hcos(float k, float cos0, const float *xyz, const float *L, float *frc, float *eng)
+{
+    float ij[3], ik[3];
+    for (int a = 0; a < 3; a++) {
+        ij[a] = delta_periodic1(xyz[3 + a] - xyz[a], L[a], 0.5f * L[a]);
+        ik[a] = delta_periodic1(xyz[6 + a] - xyz[a], L[a], 0.5f * L[a]);
+    }
+    float r2ij = ij[0] * ij[0] + ij[1] * ij[1] + ij[2] * ij[2], rij = sqrtf(r2ij);
+    float r2ik = ik[0] * ik[0] + ik[1] * ik[1] + ik[2] * ik[2], rik = sqrtf(r2ik);
+    float cos_th = (ij[0] * ik[0] + ij[1] * ik[1] + ij[2] * ik[2]) / rij / rik;
+    float dCos = cos_th - cos0;
+    float c1 = -k * dCos;
+    float c2 = (float)(1.0 / rij / rik);
+    for (int a = 0; a < 3; a++) {
+        frc[a] = -c1 * (ik[a] * c2 + ij[a] * c2 - cos_th * (ij[a] / r2ij + ik[a] / r2ik));
+        frc[3 + a] = c1 * (ik[a] * c2 - cos_th * ij[a] / r2ij);
+        frc[6 + a] = c1 * (ij[a] * c2 - cos_th * ik[a] / r2ik);
+    }
+    *eng += 0.5f * k * dCos * dCos;
 }
 
 /* ------------------------------------------------- reciprocal-space Ewald ---- */

@@ -20,7 +20,9 @@ want = {
                  "cu_fe_einv", "cu_fer_einv", "surk_pot"],
     "cuElec.cu": ["direct_coul", "real_ewald", "fennel"],
     "cuTemp.cu": ["rand_uvect", "get_angled_vector", "adsorb_rand_photon", "radiate_photon3", "before_nose", "after_nose"],
-    "cuMDfunc.cu": ["put_periodic"],
+    "cuMDfunc.cu": ["put_periodic", "delta_periodic"],
+    "cuBonds.cu": ["bond_harm", "bond_morse", "bond_pedone", "bond_buck", "bond_e6812"],   # SURVEY 8f-4 groundwork
+    "cuAngles.cu": ["angle_hcos"],
     "cuSort.cu": ["count_cell"],
     "cuCellList.cu": ["split_cells", "cell_dist_int"],   # host functions of the CUDA build
 }
@@ -35,7 +37,12 @@ for fn, names in want.items():
         for m in re.finditer(r"^__constant__ const float (revLight|Light|revPlank|numPi)[^\n]*\n", src, flags=re.M):
             chunks.append(m.group(0))
     for name in names:
-        m = re.search(r"^(?:__device__\s+|__global__\s+)?[\w\*]+[\w\s\*]*?\b%s\s*\(" % re.escape(name), bare, flags=re.M)
+        m = None
+        for cand in re.finditer(r"^(?:__device__\s+|__global__\s+)?[\w\*]+[\w\s\*]*?\b%s\s*\(" % re.escape(name), bare, flags=re.M):
+            semi = bare.find(";", cand.end())
+            if semi < 0 or bare.index("{", cand.end()) < semi:  # a definition, not a forward declaration
+                m = cand
+                break
         if not m:
             raise SystemExit("function %s not found in %s" % (name, fn))
         i = bare.index("{", m.end())

@@ -14,6 +14,8 @@
 //   put_periodic                                src/cuMDfunc.cu:35-106
 //   count_cell                                  src/cuSort.cu:114-128
 //   split_cells, cell_dist_int (host code)      src/cuCellList.cu:9-34,98-132
+//   bond_harm/_morse/_pedone/_buck/_e6812       src/cuBonds.cu:1123-1224     (SURVEY 8f-4 groundwork: oracle pinned
+//   angle_hcos, delta_periodic                  src/cuAngles.cu:230-283, src/cuMDfunc.cu:178-203   before kernels exist)
 //
 // The only substitution: rnd_xor128 (src/cuUtils.cu:89-105; racy, seeded from uninitialised memory) is replaced by a
 // queue of numbers the caller supplies, so that the same draws can be fed to the oracle.
@@ -175,4 +177,42 @@ void refdev_nose(float tSt, float teKin, float rQmass, float qMassTau2, float* e
     *engKin = md.engKin; *chit = md.chit; *consInt = md.consInt;
 }
 
+
+// bond potentials by the reference's type ids (src/cuBonds.cu:1248-1270: 1 harm, 2 morse, 3 pedone, 4 buck, 5 e6812)
+int refdev_bond(int kind, const float* p, float r2, float r, float* f_over_r, float* eng)
+{
+    cudaBond b;
+    memset(&b, 0, sizeof(b));
+    b.p0 = p[0]; b.p1 = p[1]; b.p2 = p[2]; b.p3 = p[3]; b.p4 = p[4];
+    float e = 0.f, f;
+    switch (kind) {
+    case 1: f = bond_harm(r2, r, e, &b); break;
+    case 2: f = bond_morse(r2, r, e, &b); break;
+    case 3: f = bond_pedone(r2, r, e, &b); break;
+    case 4: f = bond_buck(r2, r, e, &b); break;
+    case 5: f = bond_e6812(r2, r, e, &b); break;
+    default: return -1;
+    }
+    *f_over_r = f; *eng = e;
+    return 0;
+}
+
+// angle_hcos on three atoms (centre, ligand 1, ligand 2) in a rectangular periodic box: forces (added to zero) and energy
+void refdev_angle_hcos(float k, float cos0, const float* xyz /*3 x 3*/, const float* L, float* frc /*3 x 3*/, float* eng)
+{
+    static cudaMD md;
+    float3 pos[3], f[3];
+    for (int a = 0; a < 3; a++) { pos[a] = make_float3(xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2]); f[a] = make_float3(0.f, 0.f, 0.f); }
+    md.xyz = pos; md.frs = f;
+    md.leng = make_float3(L[0], L[1], L[2]);
+    md.halfLeng = make_float3(0.5f * L[0], 0.5f * L[1], 0.5f * L[2]);   // src/cuInit.cu:937
+    cudaAngle t;
+    memset(&t, 0, sizeof(t));
+    t.p0 = k; t.p1 = cos0;
+    int4 ang = make_int4(0, 1, 2, 1);
+    float e = 0.f;
+    angle_hcos(&ang, &t, &md, e);
+    for (int a = 0; a < 3; a++) { frc[3 * a] = f[a].x; frc[3 * a + 1] = f[a].y; frc[3 * a + 2] = f[a].z; }
+    *eng = e;
+}
 } // extern "C"

@@ -173,7 +173,46 @@ def main():
             ke = C.c_float(ke.value * (1.0 + 0.01 * math.sin(k)))  # the integrator changes the kinetic energy between blocks
     out["nose"] = np.array(rows, dtype=np.float64)
     out["tstat_mass"] = np.array([mass])
-    np.savez_compressed(os.path.join(HERE, "ref_device_vectors.npz"), **out)
+    if "bonds" not in sys.argv[1:]:  # the committed file is only rewritten on request: `make_golden_device.py all`
+        if "all" in sys.argv[1:] or not os.path.exists(os.path.join(HERE, "ref_device_vectors.npz")):
+            np.savez_compressed(os.path.join(HERE, "ref_device_vectors.npz"), **out)
+    bonds_and_angles(lib)
+
+
+def bonds_and_angles(lib):
+    """SURVEY 8f-4 groundwork: the reference's bond potentials (src/cuBonds.cu:1123-1224) and the harmonic-cosine valence
+    angle (src/cuAngles.cu:230-283, with delta_periodic) -> tests/golden/ref_device_bonds_angles.npz"""
+    lib.refdev_bond.argtypes = [C.c_int, _fp, C.c_float, C.c_float, _fp, _fp]
+    lib.refdev_angle_hcos.argtypes = [C.c_float, C.c_float, _fp, _fp, _fp, _fp]
+    rng = np.random.default_rng(8642)
+    params = {1: [25.0, 1.1, 0, 0, 0], 2: [4.5, 2.0, 0.96, 4.5, 0], 3: [0.3, 2.0, 2.1, 0.3, 1.0], 4: [1256.31, 0.317, 7.0, 0, 0],
+              5: [900.0, 0.33, 1.5, 3.0, 5.0]}
+    rows = []
+    for kind, p in params.items():
+        pp = (C.c_float * 5)(*p)
+        for _ in range(40):
+            r = float(np.float32(rng.uniform(0.8, 3.0)))
+            r2 = float(np.float32(r * r))
+            f, e = C.c_float(), C.c_float()
+            assert lib.refdev_bond(kind, pp, r2, r, C.byref(f), C.byref(e)) == 0
+            rows.append([kind, r2, r, f.value, e.value] + list(p))
+    out = {"bond": np.array(rows, dtype=np.float64)}
+    rows = []
+    L = np.array([20.0, 24.0, 28.0], dtype=np.float32)
+    for _ in range(120):
+        k, cos0 = float(np.float32(rng.uniform(1.0, 8.0))), float(np.float32(math.cos(rng.uniform(1.6, 2.2))))
+        c = rng.uniform(0.0, 1.0, 3) * L
+        l1 = c + rng.normal(0.0, 1.0, 3)
+        l2 = c + rng.normal(0.0, 1.0, 3)
+        xyz = (np.stack([c, l1, l2]) % L).astype(np.float32)  # ligands may sit across a periodic face
+        frc = np.zeros(9, dtype=np.float32)
+        e = C.c_float()
+        lib.refdev_angle_hcos(k, cos0, xyz.ravel().ctypes.data_as(_fp), L.ctypes.data_as(_fp), frc.ctypes.data_as(_fp), C.byref(e))
+        rows.append([k, cos0] + [float(v) for v in xyz.ravel()] + [float(v) for v in frc] + [e.value])
+    out["angle"] = np.array(rows, dtype=np.float64)
+    out["angle_box"] = L.astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_device_bonds_angles.npz"), **out)
+    print("bonds/angles:", len(out["bond"]), "bond vectors,", len(out["angle"]), "angle vectors")
     print("wrote ref_device_vectors.npz:", {k: v.shape for k, v in out.items()})
 
 

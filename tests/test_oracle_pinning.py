@@ -384,3 +384,52 @@ def test_oracle_nose_hoover_recurrence_matches_reference_source():
         lib.azo_nose_scalars(tSt, teKin, rq, qt, C.byref(ke), C.byref(chit), C.byref(ci), C.byref(ts))
         assert np.float32(ts.value) == np.float32(ts_ref) and np.float32(ke.value) == np.float32(ke_out)   # bit-exact
         assert np.float32(chit.value) == np.float32(chit_ref) and np.float32(ci.value) == np.float32(ci_ref)
+
+
+# SURVEY 8f-4 groundwork (oracle first, no kernel yet): the reference's bond potentials and valence-angle term, cut out of
+# src/cuBonds.cu / src/cuAngles.cu and executed on the CPU -> tests/golden/ref_device_bonds_angles.npz
+DEV_BA = os.path.join(GOLD, "ref_device_bonds_angles.npz")
+
+
+def test_oracle_bond_potentials_match_reference_device_source():
+    z = np.load(DEV_BA)
+    lib = azt.oracle_lib()
+    lib.azo_bond_eval.restype = C.c_float
+    lib.azo_bond_eval.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.POINTER(C.c_float)]
+    assert sorted(set(int(k) for k in z["bond"][:, 0])) == [1, 2, 3, 4, 5]
+    for row in z["bond"]:
+        kind, r2, r, f_ref, e_ref = int(row[0]), row[1], row[2], row[3], row[4]
+        p = (C.c_float * 5)(*row[5:10])
+        e = C.c_float(0.0)
+        f = lib.azo_bond_eval(kind, p, r2, r, C.byref(e))
+        assert f == pytest.approx(f_ref, rel=3e-6, abs=1e-9), (kind, r)
+        assert e.value == pytest.approx(e_ref, rel=3e-6, abs=2e-6), (kind, r)
+    # known answers: harmonic at r0 (no force, no energy), Morse at r0 (U = -C, no force)
+    e = C.c_float(0.0)
+    assert lib.azo_bond_eval(1, (C.c_float * 5)(25.0, 1.1, 0, 0, 0), 1.1 * 1.1, 1.1, C.byref(e)) == 0.0 and e.value == 0.0
+    e = C.c_float(0.0)
+    assert lib.azo_bond_eval(2, (C.c_float * 5)(4.5, 2.0, 0.96, 4.5, 0), 0.96 ** 2, 0.96, C.byref(e)) == 0.0 and e.value == pytest.approx(-4.5)
+
+
+def test_oracle_valence_angle_matches_reference_device_source():
+    z = np.load(DEV_BA)
+    lib = azt.oracle_lib()
+    fp = C.POINTER(C.c_float)
+    lib.azo_angle_hcos.restype = None
+    lib.azo_angle_hcos.argtypes = [C.c_float, C.c_float, fp, fp, fp, fp]
+    L = z["angle_box"].astype(np.float32)
+    crossed = 0
+    for row in z["angle"]:
+        k, cos0 = row[0], row[1]
+        xyz = np.ascontiguousarray(row[2:11], dtype=np.float32)
+        f_ref, e_ref = row[11:20], row[20]
+        frc = np.zeros(9, dtype=np.float32)
+        e = C.c_float(0.0)
+        lib.azo_angle_hcos(k, cos0, xyz.ctypes.data_as(fp), L.ctypes.data_as(fp), frc.ctypes.data_as(fp), C.byref(e))
+        scale = max(float(np.abs(f_ref).max()), 1e-6)
+        assert np.abs(frc - f_ref).max() <= 5e-6 * scale, (k, cos0)
+        assert e.value == pytest.approx(e_ref, rel=5e-6, abs=1e-9)
+        assert np.abs(frc.reshape(3, 3).sum(0)).max() <= 2e-5 * scale   # the three forces cancel
+        d = np.abs(xyz.reshape(3, 3)[1:] - xyz.reshape(3, 3)[0])
+        crossed += int((d > 0.5 * L).any())
+    assert crossed >= 5  # minimum-image branches of delta_periodic were exercised
