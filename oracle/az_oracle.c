@@ -655,6 +655,30 @@ void azo_angle_hcos(float k, float cos0, const float *xyz, const float *L, float
     *eng += 0.5f * k * dCos * dCos;
 }
 
+/* apply_const_bonds, src/cuBonds.cu:709-797 (serial twin: exec_bondlist, src/bonds.cpp:1069-1218, constant bonds): for every
+ * bond (id1, id2, type) delta = x1 - x2 through delta_periodic, f = force_eng(r2, r), frc[id1] += f delta, frc[id2] -= f delta.
+ * Plain arrays (the boundary for bonds does not exist yet); forces are accumulated in double per atom like forces() does;
+ * returns the bond energy. */
+double azo_apply_const_bonds(int n_bonds, const int *at1, const int *at2, const int *btype, const int *type_kind, const float *type_par /*5 per type*/,
+                             int n, const float *x, const float *y, const float *z, const float *L, double *fx, double *fy, double *fz)
+{
+    double eng = 0.0;
+    (void)n;
+    for (int b = 0; b < n_bonds; b++) {
+        const int i = at1[b], j = at2[b], t = btype[b];
+        if (t == 0) continue; /* empty bond, src/cuBonds.cu:731 */
+        float dx = delta_periodic1(x[i] - x[j], L[0], 0.5f * L[0]);
+        float dy = delta_periodic1(y[i] - y[j], L[1], 0.5f * L[1]);
+        float dz = delta_periodic1(z[i] - z[j], L[2], 0.5f * L[2]);
+        float r2 = dx * dx + dy * dy + dz * dz, r = sqrtf(r2), e = 0.f;
+        float f = azo_bond_eval(type_kind[t], type_par + 5 * t, r2, r, &e);
+        eng += (double)e;
+        fx[i] += (double)(f * dx); fy[i] += (double)(f * dy); fz[i] += (double)(f * dz);
+        fx[j] -= (double)(f * dx); fy[j] -= (double)(f * dy); fz[j] -= (double)(f * dz);
+    }
+    return eng;
+}
+
 /* ------------------------------------------------- reciprocal-space Ewald ---- */
 #define FCOUL_SCALE_D 14.3996 /* the engine's Coulomb constant (d_Fcoul_scale, src/main.cu:40); the serial twin's
                                * Fcoul_scale (src/const.h:44) is the same number to 6 digits */

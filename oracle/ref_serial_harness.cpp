@@ -83,6 +83,12 @@ int main(int argc, char** argv)
         sim->add_elec(atoms, field, elec, box, sim);
         sim->forcefield(atoms, field, elec, box, sim);
     }
+    // SURVEY 8f-4 groundwork: the loop of main.cpp adds the bonded terms after the force field (src/main.cpp:101-104);
+    // the initial force evaluation of init_serial does not.  With argv[5] == "bonds" the initial dump carries them too.
+    if (argc > 5 && strcmp(argv[5], "bonds") == 0) {
+        if (field->nBonds) exec_bondlist(atoms, field, sim, box);
+        if (field->nAngles) exec_anglelist(atoms, field, sim, box);
+    }
     double t1 = now();
     FILE* df = strcmp(dumpname, "-") ? fopen(dumpname, "wb") : NULL;
     if (df) dump(df, "init", atoms, sim);
@@ -95,6 +101,8 @@ int main(int argc, char** argv)
         clear_force(atoms, field->species, sim, box);
         sim->add_elec(atoms, field, elec, box, sim);
         sim->forcefield(atoms, field, elec, box, sim);
+        if (field->nBonds) exec_bondlist(atoms, field, sim, box);     // src/main.cpp:101-104
+        if (field->nAngles) exec_anglelist(atoms, field, sim, box);
         if (iSt > sim->nEq) integrate2(atoms, field->species, sim, 0, tstat);
         else integrate2(atoms, field->species, sim, (sim->freqEq && (iSt % sim->freqEq) == 0) ? 1 : 0, tstat);
         calc_chars(sim, tSim);
@@ -103,8 +111,8 @@ int main(int argc, char** argv)
     if (df) { dump(df, "final", atoms, sim); fclose(df); }
     printf("{\"n_atoms\": %d, \"nsteps\": %d, \"init_s\": %.6f, \"loop_s\": %.6f, \"s_per_step\": %.9f, "
            "\"atom_steps_per_s\": %.6e, \"engVdW\": %.10e, \"engCoul\": %.10e, \"engKin\": %.10e, \"n_cells\": %d, "
-           "\"engElec1\": %.10e, \"engElec2\": %.10e}\n",
+           "\"engElec1\": %.10e, \"engElec2\": %.10e, \"engBond\": %.10e, \"engAngle\": %.10e, \"n_bonds\": %d}\n",
            atoms->nAt, nsteps, t1 - t0, t3 - t2, nsteps ? (t3 - t2) / nsteps : 0.0,
-           nsteps ? (double)atoms->nAt * nsteps / (t3 - t2) : 0.0, sim->engVdW, sim->engElec3, sim->engKin, sim->nHead, sim->engElec1, sim->engElec2);
+           nsteps ? (double)atoms->nAt * nsteps / (t3 - t2) : 0.0, sim->engVdW, sim->engElec3, sim->engKin, sim->nHead, sim->engElec1, sim->engElec2, sim->engBond, sim->engAngle, field->nBonds);
     return 0;
 }

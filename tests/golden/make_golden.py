@@ -38,9 +38,9 @@ def read_dump(path):
     return out
 
 
-def run(deckdir, nsteps, mode):
+def run(deckdir, nsteps, mode, extra=None):
     dump = os.path.join(deckdir, "dump.bin")
-    r = subprocess.run([HARNESS, str(nsteps), mode, dump, "1"], cwd=deckdir, stdin=subprocess.DEVNULL,
+    r = subprocess.run([HARNESS, str(nsteps), mode, dump, "1"] + ([extra] if extra else []), cwd=deckdir, stdin=subprocess.DEVNULL,
                        capture_output=True, text=True, check=True)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     return read_dump(dump), line
@@ -75,11 +75,22 @@ def main():
         info = decks.nacl_deck(d, (6, 5, 7), rc_vdw=9.0, r_real=9.0, alpha=0.3, elec="pme", init_vel="zero", nstep=2, jitter=0.4, ewald_k=(7, 5, 9))
         cases.append(("nacl657_buck_pme", d, "full", dict(kind="nacl", ncell=(6, 5, 7), elec="pme", rc_vdw=9.0, r_real=9.0, alpha=0.3,
                                                           ewald_k=[7, 5, 9], jitter=0.4, box=[float(x) for x in info["box"]])))
+        # SURVEY 8f-4 groundwork: LJ argon with a list of constant bonds (harmonic and Morse), bonded terms added to the initial forces
+        d = os.path.join(tmp, "lj5_bonds")
+        info = decks.lj_argon_deck(d, 5, nstep=2, init_vel="zero")
+        btypes = [(1, [5.0, 3.8, 0, 0, 0], "harm\t5.0\t3.8"), (2, [0.4, 1.5, 4.0, 0.4, 0], "mors\t0.4\t1.5\t4.0\t0.4")]
+        with open(os.path.join(d, "field.txt"), "a") as ff:
+            ff.write("bonds %d\n" % len(btypes) + "".join("%d\tAr\tAr\t%s\tcon\tcon\n" % (k + 1, t[2]) for k, t in enumerate(btypes)) + "bond_list 1\n")
+        blist = [(4 * k, 4 * k + 1, 1 + (k % 2)) for k in range(0, info["n_atoms"] // 4, 3)] + [(2, 4 * 5 * 5 * 4 + 2, 1)]  # the last one spans a periodic face
+        with open(os.path.join(d, "bonds.txt"), "w") as ff:
+            ff.write("%d\n" % len(blist) + "".join("%d %d %d\n" % b for b in blist))
+        cases.append(("lj5_bonds", d, "full", dict(kind="lj", ncell=5, rc=info["rc"], box=[float(x) for x in info["box"]], bonds=blist,
+                                                   bond_types=[(t[0], t[1]) for t in btypes])))
         only = sys.argv[1:]
         for name, d, mode, meta in cases:
             if only and name not in only:
                 continue
-            dumps, line = run(d, 0, mode)
+            dumps, line = run(d, 0, mode, "bonds" if "bonds" in meta else None)
             init = dumps["init"]
             names = [l.split()[0] for l in open(os.path.join(d, "atoms.xyz")).read().splitlines()[2:] if l.strip()]
             uniq = []
@@ -89,10 +100,14 @@ def main():
             types = np.array([uniq.index(nm) for nm in names], dtype=np.int32)
             out = os.path.join(HERE, "ref_serial_%s.npz" % name)
             extra = {}
+            import json
             if meta.get("elec") == "pme":
-                import json
                 j = json.loads(line)
                 extra = dict(engElec1=j["engElec1"], engElec2=j["engElec2"])
+            if "bonds" in meta:
+                j = json.loads(line)
+                assert j["n_bonds"] == len(meta["bonds"])
+                extra = dict(engBond=j["engBond"])
             np.savez_compressed(out, pos=init["pos"], frc=init["frc"], types=types, engVdW=init["engVdW"],
                                 engCoul=init["engCoul"], meta=np.array(repr(meta)), harness=np.array(line), **extra)
             print(name, line)

@@ -41,6 +41,30 @@ def system_from_fixture(path):
     return s, z
 
 
+def bonded_forces(meta, pos):
+    """oracle/az_oracle.c: azo_apply_const_bonds on the fixture's bond list; returns (forces[n, 3], bond energy)"""
+    lib = azt.oracle_lib()
+    ip, fp, dp = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    lib.azo_apply_const_bonds.restype = C.c_double
+    lib.azo_apply_const_bonds.argtypes = [C.c_int, ip, ip, ip, ip, fp, C.c_int, fp, fp, fp, fp, dp, dp, dp]
+    b = np.array(meta["bonds"], dtype=np.int32)
+    at1, at2, bt = (np.ascontiguousarray(b[:, k]) for k in range(3))
+    nt = max(t[0] for t in meta["bond_types"]) + 1
+    kinds = np.zeros(nt, dtype=np.int32)
+    par = np.zeros((nt, 5), dtype=np.float32)
+    for k, (kind, p) in enumerate(meta["bond_types"]):  # type ids of the list start at 1 ([0] = empty bond)
+        kinds[k + 1] = kind
+        par[k + 1] = p
+    n = len(pos)
+    xyz = [np.ascontiguousarray(pos[:, a], dtype=np.float32) for a in range(3)]
+    L = np.array(meta["box"], dtype=np.float32)
+    f = [np.zeros(n) for _ in range(3)]
+    eng = lib.azo_apply_const_bonds(len(b), at1.ctypes.data_as(ip), at2.ctypes.data_as(ip), bt.ctypes.data_as(ip), kinds.ctypes.data_as(ip),
+                                    par.ctypes.data_as(fp), n, *(a.ctypes.data_as(fp) for a in xyz), L.ctypes.data_as(fp),
+                                    *(a.ctypes.data_as(dp) for a in f))
+    return np.stack(f, 1), eng
+
+
 FIXTURES = sorted(glob.glob(os.path.join(GOLD, "ref_serial_*.npz")))
 
 
@@ -58,7 +82,15 @@ def test_oracle_matches_reference_serial_build(path):
     d = azt.sort_by_id(o.dump())
     scale = np.zeros(o.n, dtype=np.float32)
     scale[o.dump()["ids"]] = o.force_scale()
-    err = np.abs(d["frc"].astype(np.float64) - z["frc"]).max(1)
+    frc = d["frc"].astype(np.float64)
+    meta = ast.literal_eval(str(z["meta"]))
+    if "bonds" in meta:  # SURVEY 8f-4 groundwork: constant bonds on top of the pair forces (apply_const_bonds / exec_bondlist)
+        fb, eb = bonded_forces(meta, z["pos"])
+        assert np.abs(fb).max(1).astype(bool).sum() == len({a for b in meta["bonds"] for a in b[:2]})
+        frc = frc + fb
+        scale = scale + np.abs(fb).sum(1).astype(np.float32)
+        assert eb == pytest.approx(float(z["engBond"]), rel=5e-6)
+    err = np.abs(frc - z["frc"]).max(1)
     assert (err <= 1e-5 * np.maximum(scale, 1e-12)).all(), float((err / np.maximum(scale, 1e-12)).max())
     st = o.stats()
     assert st.engVdW_d == pytest.approx(float(z["engVdW"]), rel=2e-6)
