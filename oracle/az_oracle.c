@@ -679,6 +679,26 @@ double azo_apply_const_bonds(int n_bonds, const int *at1, const int *at2, const 
     return eng;
 }
 
+/* apply_angles, src/cuAngles.cu:169-228 (serial twin: exec_anglelist, src/angles.cpp:229-242): for every valence angle
+ * (centre, ligand 1, ligand 2, type) the harmonic-cosine term; type_par = (k, cos0) per type, type 0 = empty.  Returns
+ * the angle energy. */
+double azo_apply_angles(int n_angles, const int *centre, const int *lig1, const int *lig2, const int *atype, const float *type_par /*2 per type*/,
+                        const float *x, const float *y, const float *z, const float *L, double *fx, double *fy, double *fz)
+{
+    double eng = 0.0;
+    for (int a = 0; a < n_angles; a++) {
+        const int t = atype[a];
+        if (t == 0) continue;
+        const int id[3] = { centre[a], lig1[a], lig2[a] };
+        float xyz[9], f[9], e = 0.f;
+        for (int k = 0; k < 3; k++) { xyz[3 * k] = x[id[k]]; xyz[3 * k + 1] = y[id[k]]; xyz[3 * k + 2] = z[id[k]]; }
+        azo_angle_hcos(type_par[2 * t], type_par[2 * t + 1], xyz, L, f, &e);
+        eng += (double)e;
+        for (int k = 0; k < 3; k++) { fx[id[k]] += (double)f[3 * k]; fy[id[k]] += (double)f[3 * k + 1]; fz[id[k]] += (double)f[3 * k + 2]; }
+    }
+    return eng;
+}
+
 /* ------------------------------------------------- reciprocal-space Ewald ---- */
 #define FCOUL_SCALE_D 14.3996 /* the engine's Coulomb constant (d_Fcoul_scale, src/main.cu:40); the serial twin's
                                * Fcoul_scale (src/const.h:44) is the same number to 6 digits */

@@ -86,6 +86,20 @@ def main():
             ff.write("%d\n" % len(blist) + "".join("%d %d %d\n" % b for b in blist))
         cases.append(("lj5_bonds", d, "full", dict(kind="lj", ncell=5, rc=info["rc"], box=[float(x) for x in info["box"]], bonds=blist,
                                                    bond_types=[(t[0], t[1]) for t in btypes])))
+        # ... and the same with valence angles (harmonic cosine) on top
+        d = os.path.join(tmp, "lj5_bonds_angles")
+        info = decks.lj_argon_deck(d, 5, nstep=2, init_vel="zero")
+        atypes = [(6.0, -0.3), (2.5, 0.45)]
+        with open(os.path.join(d, "field.txt"), "a") as ff:
+            ff.write("bonds %d\n" % len(btypes) + "".join("%d\tAr\tAr\t%s\tcon\tcon\n" % (k + 1, t[2]) for k, t in enumerate(btypes)) + "bond_list 1\n")
+            ff.write("angles %d\n" % len(atypes) + "".join("%d\tAr\thcos\t%g\t%g\n" % (k + 1, t[0], t[1]) for k, t in enumerate(atypes)) + "angle_list 1\n")
+        with open(os.path.join(d, "bonds.txt"), "w") as ff:
+            ff.write("%d\n" % len(blist) + "".join("%d %d %d\n" % b for b in blist))
+        alist = [(4 * k, 4 * k + 1, 4 * k + 2, 1 + (k % 2)) for k in range(1, info["n_atoms"] // 4, 4)] + [(1, 3, 4 * 5 * 4 + 1, 2)]  # the last one reaches through a face
+        with open(os.path.join(d, "angles.txt"), "w") as ff:
+            ff.write("%d\n" % len(alist) + "".join("%d %d %d %d\n" % a for a in alist))
+        cases.append(("lj5_bonds_angles", d, "full", dict(kind="lj", ncell=5, rc=info["rc"], box=[float(x) for x in info["box"]], bonds=blist,
+                                                          bond_types=[(t[0], t[1]) for t in btypes], angles=alist, angle_types=atypes)))
         only = sys.argv[1:]
         for name, d, mode, meta in cases:
             if only and name not in only:
@@ -107,7 +121,7 @@ def main():
             if "bonds" in meta:
                 j = json.loads(line)
                 assert j["n_bonds"] == len(meta["bonds"])
-                extra = dict(engBond=j["engBond"])
+                extra = dict(engBond=j["engBond"], engAngle=j["engAngle"])
             np.savez_compressed(out, pos=init["pos"], frc=init["frc"], types=types, engVdW=init["engVdW"],
                                 engCoul=init["engCoul"], meta=np.array(repr(meta)), harness=np.array(line), **extra)
             print(name, line)

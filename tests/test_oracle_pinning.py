@@ -65,6 +65,26 @@ def bonded_forces(meta, pos):
     return np.stack(f, 1), eng
 
 
+def angle_forces(meta, pos):
+    """oracle/az_oracle.c: azo_apply_angles on the fixture's angle list; returns (forces[n, 3], angle energy)"""
+    lib = azt.oracle_lib()
+    ip, fp, dp = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    lib.azo_apply_angles.restype = C.c_double
+    lib.azo_apply_angles.argtypes = [C.c_int, ip, ip, ip, ip, fp, fp, fp, fp, fp, dp, dp, dp]
+    a = np.array(meta["angles"], dtype=np.int32)
+    cols = [np.ascontiguousarray(a[:, k]) for k in range(4)]
+    par = np.zeros((len(meta["angle_types"]) + 1, 2), dtype=np.float32)
+    for k, t in enumerate(meta["angle_types"]):
+        par[k + 1] = t
+    n = len(pos)
+    xyz = [np.ascontiguousarray(pos[:, k], dtype=np.float32) for k in range(3)]
+    L = np.array(meta["box"], dtype=np.float32)
+    f = [np.zeros(n) for _ in range(3)]
+    eng = lib.azo_apply_angles(len(a), *(c.ctypes.data_as(ip) for c in cols), par.ctypes.data_as(fp), *(v.ctypes.data_as(fp) for v in xyz),
+                               L.ctypes.data_as(fp), *(v.ctypes.data_as(dp) for v in f))
+    return np.stack(f, 1), eng
+
+
 FIXTURES = sorted(glob.glob(os.path.join(GOLD, "ref_serial_*.npz")))
 
 
@@ -90,6 +110,11 @@ def test_oracle_matches_reference_serial_build(path):
         frc = frc + fb
         scale = scale + np.abs(fb).sum(1).astype(np.float32)
         assert eb == pytest.approx(float(z["engBond"]), rel=5e-6)
+        if "angles" in meta:  # valence angles (apply_angles / exec_anglelist)
+            fa, ea = angle_forces(meta, z["pos"])
+            frc = frc + fa
+            scale = scale + np.abs(fa).sum(1).astype(np.float32)
+            assert abs(ea) > 1e-3 and ea == pytest.approx(float(z["engAngle"]), rel=5e-6)
     err = np.abs(frc - z["frc"]).max(1)
     assert (err <= 1e-5 * np.maximum(scale, 1e-12)).all(), float((err / np.maximum(scale, 1e-12)).max())
     st = o.stats()
