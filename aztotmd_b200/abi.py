@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-AZ_ABI_VERSION = 1
+AZ_ABI_VERSION = 2
 AZ_MAX_SPECIES = 15
 AZ_N_UVECT = 3072
 AZ_N_MOM = 20
@@ -45,6 +45,20 @@ class az_vdw_entry(C.Structure):
                 ("p2", C.c_double), ("p3", C.c_double), ("p4", C.c_double), ("r2cut", C.c_double)]
 
 
+BOND_NONE, BOND_HARM, BOND_MORSE, BOND_PEDONE, BOND_BUCK, BOND_E612 = range(6)
+BOND_BY_NAME = {"harm": BOND_HARM, "mors": BOND_MORSE, "pdn": BOND_PEDONE, "buck": BOND_BUCK, "e612": BOND_E612}
+ANGLE_HCOS = 1
+
+
+class az_bond_type(C.Structure):
+    _fields_ = [("kind", C.c_int), ("spec1", C.c_int), ("spec2", C.c_int), ("reserved", C.c_int),
+                ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double), ("p3", C.c_double), ("p4", C.c_double)]
+
+
+class az_angle_type(C.Structure):
+    _fields_ = [("kind", C.c_int), ("central", C.c_int), ("p0", C.c_double), ("p1", C.c_double)]
+
+
 class az_system_desc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int), ("n_atoms", C.c_int), ("n_species", C.c_int), ("reserved0", C.c_int),
@@ -64,6 +78,10 @@ class az_system_desc(C.Structure):
         ("global_ids", _ip), ("n_atoms_global", C.c_longlong),
         ("tstat_tau", C.c_double), ("reset_vels", C.c_int), ("reserved3", C.c_int),
         ("ewald_k", C.c_int * 3), ("reserved4", C.c_int),
+        ("n_bond_types", C.c_int), ("n_bonds", C.c_int), ("bond_types", C.POINTER(az_bond_type)),
+        ("bond_at1", _ip), ("bond_at2", _ip), ("bond_type", _ip),
+        ("n_angle_types", C.c_int), ("n_angles", C.c_int), ("angle_types", C.POINTER(az_angle_type)),
+        ("angle_centre", _ip), ("angle_lig1", _ip), ("angle_lig2", _ip), ("angle_type", _ip),
     ]
 
 
@@ -81,7 +99,8 @@ class az_stats(C.Structure):
                 ("posMom", C.c_float * 3), ("negMom", C.c_float * 3), ("pressure", C.c_float), ("x_first", C.c_float),
                 ("specAcBoxPos", (C.c_int * 3) * AZ_MAX_SPECIES), ("specAcBoxNeg", (C.c_int * 3) * AZ_MAX_SPECIES),
                 ("engKin_d", C.c_double), ("engVdW_d", C.c_double), ("engCoul1_d", C.c_double), ("engTemp_d", C.c_double),
-                ("n_pairs", C.c_longlong), ("engCoul3", C.c_float), ("reserved", C.c_float), ("engCoul2_d", C.c_double)]
+                ("n_pairs", C.c_longlong), ("engCoul3", C.c_float), ("reserved", C.c_float), ("engCoul2_d", C.c_double),
+                ("engBond", C.c_float), ("engAngle", C.c_float), ("engBond_d", C.c_double), ("engAngle_d", C.c_double)]
 
 
 class az_atoms_out(C.Structure):
@@ -145,6 +164,10 @@ DECK_SYMBOLS = {
     "az_deck_nstep_stat": (C.c_int, [C.c_void_p]),
     "az_deck_species_count": (C.c_int, [C.c_void_p, C.c_int]),
     "az_deck_rdf": (C.c_int, [C.c_void_p, _dp, _dp, _ip, _ip]),
+    "az_deck_nuclei": (C.c_int, [C.c_void_p, _ip]),
+    "az_deck_nucleus_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "az_deck_nucleus_count": (C.c_int, [C.c_void_p, C.c_int]),
+    "az_deck_rdf_nuclei": (C.c_int, [C.c_void_p]),
     "az_deck_free": (None, [C.c_void_p]),
 }
 
@@ -165,7 +188,8 @@ def bind(lib: C.CDLL, symbols=None, strict: bool = True) -> C.CDLL:
 
 
 STRICT_DECK = True
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libaztot_b200.so")
+# AZTOT_B200_LIB: an A/B build of the same engine (profiles/build_variant.sh) for measurement jobs; never a different backend
+LIB_PATH = os.environ.get("AZTOT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libaztot_b200.so")
 _lib = None
 
 

@@ -24,6 +24,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/aztot_b200.h"
@@ -91,6 +92,13 @@ struct az_deck {
     std::vector<az_species> species;
     std::vector<az_vdw_entry> vdw;
     std::vector<int> spec_count;
+    // nuclei (second word of a 'spec' line, read_spec src/sys_init.cpp:78-104): Field::nNucl, nnames, nnumbers, Spec::nuclei
+    std::vector<std::string> nucl_names;
+    std::vector<int> nucl_of_spec, nucl_count;
+    // 'bonds' / 'bond_list' + bonds.txt, 'angles' / 'angle_list' + angles.txt
+    std::vector<az_bond_type> bond_types;
+    std::vector<az_angle_type> angle_types;
+    std::vector<int> b_at1, b_at2, b_type, a_c, a_l1, a_l2, a_type;
 };
 
 static thread_local std::string g_deck_error;
@@ -138,15 +146,59 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
         s.mass = mass * kMScale;
         s.charge = q;
         if (q != 0.0) charged = true;
+        int k = -1; // define nucleus (or add new), src/sys_init.cpp:88-103
+        for (size_t j = 0; j < d->nucl_names.size(); j++) if (d->nucl_names[j] == nucl) k = (int)j;
+        if (k < 0) { k = (int)d->nucl_names.size(); d->nucl_names.push_back(nucl); }
+        d->nucl_of_spec.push_back(k);
     }
     { // directives whose physics is outside the hot path must not be dropped silently
         int n;
         if ((n = scan_number(f, " red-ox %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'red-ox %d': electron transfer chemistry is outside the hot path", n);
-        if ((n = scan_number(f, " bonds %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'bonds %d': bonded terms are outside the hot path", n);
-        if ((n = scan_number(f, " angles %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'angles %d': angle terms are outside the hot path", n);
         if ((n = scan_number(f, " linkage %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'linkage %d': reactive bonding is outside the hot path", n);
-        if ((n = scan_number(f, " bond_list %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'bond_list %d': bonded terms are outside the hot path", n);
+        if ((n = scan_number(f, " evol_bonds %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'evol_bonds %d': reactive bonding is outside the hot path", n);
+        if ((n = scan_number(f, " h-bonds %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'h-bonds %d': hydrogen bonds are outside the hot path", n);
+        if ((n = scan_number(f, " angle_forming %d")) > 0) DECK_FAIL(AZ_ERR_UNSUPPORTED, "'angle_forming %d': reactive angles are outside the hot path", n);
     }
+    { // bond types (read_bond, src/bonds.cpp:125-300): "n spec1 spec2 key params... low high"; constant bonds only ('con con')
+        const int nb = scan_number(f, " bonds %d");
+        if (nb > 0) {
+            d->bond_types.assign(nb + 1, az_bond_type()); // [0] is reserved as 'empty bond' (src/sys_init.cpp:294)
+            for (auto& b : d->bond_types) memset(&b, 0, sizeof(b));
+            static const struct { const char* key; int kind, np; } kB[] = { { "harm", AZ_BOND_HARM, 2 }, { "mors", AZ_BOND_MORSE, 4 }, { "pdn", AZ_BOND_PEDONE, 5 },
+                                                                            { "buck", AZ_BOND_BUCK, 3 }, { "e612", AZ_BOND_E612, 5 } };
+            for (int i = 1; i <= nb; i++) {
+                int num; char s1[64], s2[64], key[64];
+                if (fscanf(f, "%d %63s %63s %63s", &num, s1, s2, key) != 4) DECK_FAIL(AZ_ERR_IO, "bad bond type line %d in field.txt", i);
+                const int t1 = spec_by_name(d, s1), t2 = spec_by_name(d, s2);
+                if (t1 < 0 || t2 < 0) DECK_FAIL(AZ_ERR_IO, "ERROR[124]: Unknown species in bonds declaration: %d %s %s", num, s1, s2);
+                az_bond_type& b = d->bond_types[i];
+                b.spec1 = t1; b.spec2 = t2;
+                double p[5] = { 0, 0, 0, 0, 0 };
+                int np = -1;
+                for (const auto& k : kB) if (!strcmp(k.key, key)) { b.kind = k.kind; np = k.np; }
+                if (np < 0) DECK_FAIL(AZ_ERR_IO, "ERROR[126]: Unknown potential type in bonds declaration: %d %s", num, key);
+                for (int k = 0; k < np; k++) if (fscanf(f, " %lf", &p[k]) != 1) DECK_FAIL(AZ_ERR_IO, "bond type %d: too few parameters", i);
+                b.p0 = p[0]; b.p1 = p[1]; b.p2 = p[2]; b.p3 = p[3]; b.p4 = p[4]; // E_scale = r_scale = 1 (src/const.h:39-41)
+                for (int lim = 0; lim < 2; lim++) { // lower / upper limit of the bond: only constant bonds are on this path
+                    if (fscanf(f, " %63s", key) != 1 || strcmp(key, "con")) DECK_FAIL(AZ_ERR_UNSUPPORTED, "bond type %d: '%s' limit: mutable / breakable bonds are reactive chemistry, outside the hot path", i, key);
+                }
+            }
+        }
+        const int na = scan_number(f, " angles %d ");
+        if (na > 0) { // read_angle, src/angles.cpp:78-130: "n central key k cos0"
+            d->angle_types.assign(na + 1, az_angle_type());
+            for (auto& a : d->angle_types) memset(&a, 0, sizeof(a));
+            for (int i = 1; i <= na; i++) {
+                int num; char s1[64], key[64]; double p0, p1;
+                if (fscanf(f, "%d %63s %63s %lf %lf", &num, s1, key, &p0, &p1) != 5) DECK_FAIL(AZ_ERR_IO, "bad angle type line %d in field.txt", i);
+                const int t = spec_by_name(d, s1);
+                if (t < 0) DECK_FAIL(AZ_ERR_IO, "ERROR[011]: Unknown species in angle declaration: %d %s %s", num, s1, key);
+                if (strcmp(key, "hcos")) DECK_FAIL(AZ_ERR_IO, "ERROR[012]: Unknown potential type in angle declaration: %d %s", num, key);
+                d->angle_types[i].kind = AZ_ANGLE_HCOS; d->angle_types[i].central = t; d->angle_types[i].p0 = p0; d->angle_types[i].p1 = p1;
+            }
+        }
+    }
+    const bool use_bond_list = scan_number(f, " bond_list %d") > 0, use_angle_list = scan_number(f, " angle_list %d") > 0;
     int nfrozen = scan_number(f, " frozensp %d");
     for (int i = 0; i < nfrozen; i++) {
         char nm[64];
@@ -218,6 +270,49 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
         d->spec_count[t]++;
     }
     fclose(f); f = nullptr;
+    d->nucl_count.assign(d->nucl_names.size(), 0); // Field::nnumbers, src/sys_init.cpp:539
+    for (int i = 0; i < n; i++) d->nucl_count[d->nucl_of_spec[d->types[i]]]++;
+
+    // ------------------------------------------------------------------ bonds.txt / angles.txt (read_bondlist, read_anglelist)
+    if (use_bond_list && !d->bond_types.empty()) {
+        f = fopen((base + "bonds.txt").c_str(), "r");
+        if (!f) DECK_WARN("WARNING[a001] bond list is used, but there is no such file. No bonds are downloaded");
+        else {
+            int nb = 0;
+            if (fscanf(f, "%d", &nb) != 1 || nb < 0) DECK_FAIL(AZ_ERR_IO, "bonds.txt: bad bond count");
+            for (int i = 0; i < nb; i++) {
+                int a1, a2, k;
+                if (fscanf(f, "%d %d %d", &a1, &a2, &k) != 3) DECK_FAIL(AZ_ERR_IO, "bonds.txt: bad line %d", i + 1);
+                if (a1 < 0 || a1 >= n || a2 < 0 || a2 >= n || k <= 0 || k >= (int)d->bond_types.size()) DECK_FAIL(AZ_ERR_IO, "bonds.txt: line %d: atom or type out of range", i + 1);
+                const az_bond_type& b = d->bond_types[k]; // turn the bond if necessary and verify its type, src/bonds.cpp:50-77
+                if (b.spec1 == d->types[a1]) { if (b.spec2 != d->types[a2]) DECK_FAIL(AZ_ERR_IO, "ERROR [121] incorrect type of 2th atom in bond (type: %d, line: %d)", k, i); }
+                else if (b.spec1 == d->types[a2] && b.spec2 == d->types[a1]) std::swap(a1, a2);
+                else DECK_FAIL(AZ_ERR_IO, "ERROR [123] incorrect type of atoms for bond type(%d) in bond list, line: %d", k, i);
+                d->b_at1.push_back(a1); d->b_at2.push_back(a2); d->b_type.push_back(k);
+            }
+            fclose(f); f = nullptr;
+        }
+    }
+    if (use_angle_list) {
+        if (d->angle_types.empty()) DECK_WARN("WARNING[b006] 'anlge_list' directive is ignored, because there are no angle type defintions");
+        else {
+            f = fopen((base + "angles.txt").c_str(), "r");
+            if (!f) DECK_WARN("WARNING[a002] angle list is used, but there is no such file. No anlges are downloaded");
+            else {
+                int na = 0;
+                if (fscanf(f, "%d", &na) != 1 || na < 0) DECK_FAIL(AZ_ERR_IO, "angles.txt: bad angle count");
+                for (int i = 0; i < na; i++) {
+                    int c, l1, l2, x;
+                    if (fscanf(f, "%d %d %d %d", &c, &l1, &l2, &x) != 4) DECK_FAIL(AZ_ERR_IO, "angles.txt: bad line %d", i + 1);
+                    if (c < 0 || c >= n || l1 < 0 || l1 >= n || l2 < 0 || l2 >= n) DECK_FAIL(AZ_ERR_IO, "angles.txt: line %d: atom out of range", i + 1);
+                    if (x <= 0 || x >= (int)d->angle_types.size()) DECK_FAIL(AZ_ERR_IO, "ERROR[013] wrong atom type number in angles.txt");
+                    if (d->types[c] != d->angle_types[x].central) DECK_FAIL(AZ_ERR_IO, "ERROR[014] wrong central atom type in angle list (%d postion)", i);
+                    d->a_c.push_back(c); d->a_l1.push_back(l1); d->a_l2.push_back(l2); d->a_type.push_back(x);
+                }
+                fclose(f); f = nullptr;
+            }
+        }
+    }
 
     // ------------------------------------------------------------------ control.txt (read_sim)
     f = fopen((base + "control.txt").c_str(), "r");
@@ -321,8 +416,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
                 DECK_FAIL(AZ_ERR_IO, "rdf directive: expected 'rdf rmax dr freq outfreq [nucl]'");
             d->rdf_rmax = r;
             if (fscanf(f, " %63s", word) == 1 && !strcmp(word, "nucl")) {
-                d->rdf_nuclei = 1;
-                DECK_WARN("note: 'rdf ... nucl': the by-nuclei table rdf_n.dat is not produced (no red-ox species on this path); rdf.dat by species is");
+                d->rdf_nuclei = 1; // nrdf_iter / copy_nrdf instead of rdf_iter / copy_rdf (src/main.cu:392-395): rdf.dat and rdf_n.dat
             }
         }
     }
@@ -347,7 +441,7 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     // ------------------------------------------------------------------ derived values (init_md)
     const bool use_elec = elec_kind != AZ_ELEC_NONE;
     double rMax = use_elec ? rReal : (nvdw > 0 ? max_r_vdw : 0.0); // src/sys_init.cpp:1059-1072
-    long long degFree = 3LL * n - (tstat_kind ? 1 : 0);             // :1099-1102 (no bonds on this path)
+    long long degFree = 3LL * n - (long long)d->b_at1.size() - (tstat_kind ? 1 : 0); // :1099-1102 (Field::nBonds)
     double tKin = 0.5 * temp * kKB * (double)degFree;               // :1106
     if (tstat_kind == AZ_TSTAT_RADI) { // photon_engs: inverse CDF of P ~ e^4 exp(-e/kT) on 0..1 eV by bisection
         d->photons.assign(n, 0.0);
@@ -420,6 +514,14 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     s.r2_max = rMax * rMax;
     s.cell_size = cell_size;
     for (int a = 0; a < 3; a++) s.efield[a] = U[a];
+    if (!d->b_at1.empty()) {
+        s.n_bond_types = (int)d->bond_types.size(); s.bond_types = d->bond_types.data();
+        s.n_bonds = (int)d->b_at1.size(); s.bond_at1 = d->b_at1.data(); s.bond_at2 = d->b_at2.data(); s.bond_type = d->b_type.data();
+    }
+    if (!d->a_c.empty()) {
+        s.n_angle_types = (int)d->angle_types.size(); s.angle_types = d->angle_types.data();
+        s.n_angles = (int)d->a_c.size(); s.angle_centre = d->a_c.data(); s.angle_lig1 = d->a_l1.data(); s.angle_lig2 = d->a_l2.data(); s.angle_type = d->a_type.data();
+    }
     d->nsteps = nSt;
     *out = d;
     return AZ_OK;
@@ -442,4 +544,13 @@ extern "C" int az_deck_rdf(const az_deck* d, double* r_max, double* dr, int* fre
     if (outfreq) *outfreq = d->rdf_outfreq;
     return 1;
 }
+extern "C" int az_deck_nuclei(const az_deck* d, int* nucleus_of_species)
+{
+    if (!d) return 0;
+    if (nucleus_of_species) for (size_t i = 0; i < d->nucl_of_spec.size(); i++) nucleus_of_species[i] = d->nucl_of_spec[i];
+    return (int)d->nucl_names.size();
+}
+extern "C" const char* az_deck_nucleus_name(const az_deck* d, int k) { return (d && k >= 0 && k < (int)d->nucl_names.size()) ? d->nucl_names[k].c_str() : ""; }
+extern "C" int az_deck_nucleus_count(const az_deck* d, int k) { return (d && k >= 0 && k < (int)d->nucl_count.size()) ? d->nucl_count[k] : 0; }
+extern "C" int az_deck_rdf_nuclei(const az_deck* d) { return d ? d->rdf_nuclei : 0; }
 extern "C" void az_deck_free(az_deck* d) { delete d; }

@@ -110,6 +110,29 @@ __device__ __forceinline__ float az_fast_exp(float x) { return __expf(x); }
 __device__ __forceinline__ float az_fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
+// ---------------------------------------------------------------------------------------
+// Packed FP32 pairs (sm_100a: add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, two IEEE-rn results per issue slot).
+// Each half is rounded exactly like the scalar instruction, so a packed evaluation of two list rows gives bitwise the
+// terms of two scalar evaluations.  The emulator build carries the two halves in a struct and uses the scalar ops.
+#ifdef AZ_EMU
+struct az_f2 { float lo, hi; };
+__device__ __forceinline__ az_f2 az_pk(float a, float b) { az_f2 r; r.lo = a; r.hi = b; return r; }
+__device__ __forceinline__ float az_lo(az_f2 v) { return v.lo; }
+__device__ __forceinline__ float az_hi(az_f2 v) { return v.hi; }
+__device__ __forceinline__ az_f2 az_fma2(az_f2 a, az_f2 b, az_f2 c) { return az_pk(fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)); }
+__device__ __forceinline__ az_f2 az_mul2(az_f2 a, az_f2 b) { return az_pk(__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)); }
+__device__ __forceinline__ az_f2 az_add2(az_f2 a, az_f2 b) { return az_pk(__fadd_rn(a.lo, b.lo), __fadd_rn(a.hi, b.hi)); }
+#else
+typedef unsigned long long az_f2;
+__device__ __forceinline__ az_f2 az_pk(float a, float b) { az_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float az_lo(az_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float az_hi(az_f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ az_f2 az_fma2(az_f2 a, az_f2 b, az_f2 c) { az_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ az_f2 az_mul2(az_f2 a, az_f2 b) { az_f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ az_f2 az_add2(az_f2 a, az_f2 b) { az_f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#endif
+__device__ __forceinline__ az_f2 az_pk1(float a) { return az_pk(a, a); }
+
 template <int VK>
 __device__ __forceinline__ float az_vdw_feng(const AzVdw& v, float r2, float& r, bool have_r,
                                              float rad1, float rad2, float& eng)

@@ -104,6 +104,7 @@ template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
 
 static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
 static int ewald_setup(az_engine* e, const az_system_desc* d, double qs[2]);
+static int bonded_setup(az_engine* e, const az_system_desc* d);
 static int dd_alloc(az_engine* e);
 static int dd_store_keep(az_engine* e, const az_system_desc* d);
 static void dd_free(az_engine* e);
@@ -225,6 +226,24 @@ static int pick_pair_config(az_engine* e, const az_system_desc* d, const az_cuda
     else if (all_same && kind0 == AZ_VDW_BUCK) { e->pair_vk = AZ_VDW_BUCK; e->pair_single = false; }
     else if (all_same && kind0 == AZ_VDW_SURK && e->pair_ck == AZ_ELEC_NONE) e->pair_vk = AZ_VDW_SURK;
     else { e->pair_vk = AZ_VK_MIXED; e->pair_single = false; }
+
+    // Packed list pass (one Lennard-Jones entry, no Coulomb): the r2 above which force_autocap (src/cuPairs.cu:94-115) is
+    // the identity.  F/r = p2/r2 * s (2 s - 1), s = (p1/r2)^3, falls monotonically through the repulsive range; find where
+    // it reaches 0.9 MX_FRC and check the attractive side on a grid.  No such r2 (absurd parameters): the kernel always
+    // takes the clamped scalar form.
+    e->r2_safe = 3.4e38f;
+    if (e->pair_vk == AZ_VDW_LJ && e->pair_single && e->pair_ck == AZ_ELEC_NONE && !e->pair_radii) {
+        const AzVdw& t = e->h_table[0];
+        auto fr = [&](double r2) { const double s = pow((double)t.p1 / r2, 3.0); return (double)t.p2 / r2 * s * (2.0 * s - 1.0); };
+        const double lim = 0.9 * (double)AZ_MX_FRC, gate = std::min((double)e->P.r2max, (double)t.r2cut);
+        double lo = 1e-12 * (double)t.p1, hi = (double)t.p1; // r = 1e-6 sigma ... sigma
+        if (t.p1 > 0.f && t.p2 > 0.f && fr(hi) < lim && fr(lo) > lim) {
+            for (int it = 0; it < 200; it++) { const double mid = sqrt(lo * hi); if (fr(mid) > lim) lo = mid; else hi = mid; }
+            bool ok = true;
+            for (int k = 0; k <= 4096 && ok; k++) { const double r2 = hi * pow(std::max(gate, hi) / hi, k / 4096.0); if (fabs(fr(r2)) > lim) ok = false; }
+            if (ok) e->r2_safe = (float)(hi * 1.0001);
+        }
+    }
 
     // CTA shape: a z-run of cells holding about one thread block of atoms
     const double owned_cells = (double)(g.ohi[0] - g.olo[0]) * (g.ohi[1] - g.olo[1]) * (g.ohi[2] - g.olo[2]);
@@ -425,10 +444,88 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
         rc = ewald_setup(e, d, qs);
         if (rc) return rc;
     }
+    if (d->n_bonds > 0 || d->n_angles > 0) { rc = bonded_setup(e, d); if (rc) return rc; }
     e->cur = 0;
     e->binned = false;
     e->since_rebuild = 0;
     e->last_step = -1;
+    return AZ_OK;
+}
+
+// SURVEY 8f-4.  The bond / angle lists of the description (atoms.xyz indices = persistent ids) become one CSR per kind,
+// keyed by persistent id: the entries of atom i are the bonds / angles that touch it, in list order, so that the thread
+// owning atom i sums its bonded forces in a fixed order (az_k_bonded).  Replaces the device copies init_cudaMD makes of
+// Field::at1/at2/bTypes and centrs/lig1/lig2/angTypes and the index rewriting of sort_bonds / sort_angles.
+static int bonded_setup(az_engine* e, const az_system_desc* d)
+{
+    const int n = e->n;
+    if (e->dd) { AZ_SET_ERR(e, "bonds / angles are single-GPU only (a bond may span two bricks)"); return AZ_ERR_UNSUPPORTED; }
+    auto bad_atom = [&](int a) { return a < 0 || a >= n; };
+    std::vector<int> start(n + 1, 0);
+    if (d->n_bonds > 0) {
+        if (!d->bond_types || !d->bond_at1 || !d->bond_at2 || !d->bond_type || d->n_bond_types < 2 || d->n_bond_types > 65535) { AZ_SET_ERR(e, "bonds: missing arrays or no bond types"); return AZ_ERR_INVALID; }
+        std::vector<AzBondType> bt(d->n_bond_types);
+        for (int t = 0; t < d->n_bond_types; t++) {
+            const az_bond_type& b = d->bond_types[t];
+            if (b.kind < AZ_BOND_NONE || b.kind > AZ_BOND_E612) { AZ_SET_ERR(e, "bond type %d: unknown kind %d", t, b.kind); return AZ_ERR_INVALID; }
+            bt[t] = { (float)b.p0, (float)b.p1, (float)b.p2, (float)b.p3, (float)b.p4, b.kind };
+        }
+        for (int b = 0; b < d->n_bonds; b++) {
+            const int a1 = d->bond_at1[b], a2 = d->bond_at2[b], t = d->bond_type[b];
+            if (bad_atom(a1) || bad_atom(a2) || a1 == a2 || t < 0 || t >= d->n_bond_types) { AZ_SET_ERR(e, "bond %d: atoms %d %d type %d out of range", b, a1, a2, t); return AZ_ERR_INVALID; }
+            if (t == 0 || bt[t].kind == AZ_BOND_NONE) continue; // empty bond, src/cuBonds.cu:731
+            start[a1 + 1]++; start[a2 + 1]++;
+        }
+        for (int i = 0; i < n; i++) start[i + 1] += start[i];
+        std::vector<int2> ent(start[n] ? start[n] : 1);
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int b = 0; b < d->n_bonds; b++) {
+            const int a1 = d->bond_at1[b], a2 = d->bond_at2[b], t = d->bond_type[b];
+            if (t == 0 || bt[t].kind == AZ_BOND_NONE) continue;
+            ent[fill[a1]++] = make_int2(a2, t | (1 << 16));
+            ent[fill[a2]++] = make_int2(a1, t);
+        }
+        AZ_ALLOC(e, e->bStart, n + 1); AZ_ALLOC(e, e->bEnt, ent.size()); AZ_ALLOC(e, e->bTypes, bt.size());
+        AZ_CUDA(e, cudaMemcpy(e->bStart, start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->bEnt, ent.data(), sizeof(int2) * ent.size(), cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->bTypes, bt.data(), sizeof(AzBondType) * bt.size(), cudaMemcpyHostToDevice));
+    }
+    if (d->n_angles > 0) {
+        if (!d->angle_types || !d->angle_centre || !d->angle_lig1 || !d->angle_lig2 || !d->angle_type || d->n_angle_types < 2 || d->n_angle_types > 65535) { AZ_SET_ERR(e, "angles: missing arrays or no angle types"); return AZ_ERR_INVALID; }
+        std::vector<AzAngleType> at(d->n_angle_types);
+        for (int t = 0; t < d->n_angle_types; t++) {
+            if (d->angle_types[t].kind != 0 && d->angle_types[t].kind != AZ_ANGLE_HCOS) { AZ_SET_ERR(e, "angle type %d: unknown kind %d", t, d->angle_types[t].kind); return AZ_ERR_INVALID; }
+            at[t] = { (float)d->angle_types[t].p0, (float)d->angle_types[t].p1 };
+        }
+        std::fill(start.begin(), start.end(), 0);
+        auto live = [&](int a) { const int t = d->angle_type[a]; return t != 0 && d->angle_types[t].kind != 0; };
+        for (int a = 0; a < d->n_angles; a++) {
+            const int c = d->angle_centre[a], l1 = d->angle_lig1[a], l2 = d->angle_lig2[a], t = d->angle_type[a];
+            if (bad_atom(c) || bad_atom(l1) || bad_atom(l2) || c == l1 || c == l2 || l1 == l2 || t < 0 || t >= d->n_angle_types) { AZ_SET_ERR(e, "angle %d: atoms %d %d %d type %d out of range", a, c, l1, l2, t); return AZ_ERR_INVALID; }
+            if (!live(a)) continue;
+            start[c + 1]++; start[l1 + 1]++; start[l2 + 1]++;
+        }
+        for (int i = 0; i < n; i++) start[i + 1] += start[i];
+        std::vector<int4> ent(start[n] ? start[n] : 1);
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int a = 0; a < d->n_angles; a++) {
+            if (!live(a)) continue;
+            const int c = d->angle_centre[a], l1 = d->angle_lig1[a], l2 = d->angle_lig2[a], t = d->angle_type[a];
+            ent[fill[c]++] = make_int4(l1, l2, t, 0);
+            ent[fill[l1]++] = make_int4(c, l2, t | (1 << 16), 0);
+            ent[fill[l2]++] = make_int4(c, l1, t | (2 << 16), 0);
+        }
+        AZ_ALLOC(e, e->aStart, n + 1); AZ_ALLOC(e, e->aEnt, ent.size()); AZ_ALLOC(e, e->aTypes, at.size());
+        AZ_CUDA(e, cudaMemcpy(e->aStart, start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->aEnt, ent.data(), sizeof(int4) * ent.size(), cudaMemcpyHostToDevice));
+        AZ_CUDA(e, cudaMemcpy(e->aTypes, at.data(), sizeof(AzAngleType) * at.size(), cudaMemcpyHostToDevice));
+    }
+    AZ_ALLOC(e, e->whereId, n);
+    { std::vector<int> ident(n); for (int i = 0; i < n; i++) ident[i] = i;
+      AZ_CUDA(e, cudaMemcpy(e->whereId, ident.data(), sizeof(int) * n, cudaMemcpyHostToDevice)); }
+    AZ_ALLOC(e, e->partBond, e->n_atom_blocks); AZ_ALLOC(e, e->partAngle, e->n_atom_blocks);
+    e->bonded = true;
+    e->fuse_pair = false; // the integrator cannot ride on the pair pass: the bonded forces follow it
     return AZ_OK;
 }
 
@@ -449,6 +546,8 @@ extern "C" void az_engine_destroy(az_engine* e)
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
     cudaFree(e->rdf_hist); cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
+    cudaFree(e->whereId); cudaFree(e->bStart); cudaFree(e->aStart); cudaFree(e->bEnt); cudaFree(e->aEnt); cudaFree(e->bTypes); cudaFree(e->aTypes);
+    cudaFree(e->partBond); cudaFree(e->partAngle);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
     for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -654,10 +753,10 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             AZ_LAUNCH(az_k_sort_keys, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
             if (e->use_therm)
                 AZ_LAUNCH(az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, (int*)nullptr);
+                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, (int*)nullptr, e->whereId);
             else
                 AZ_LAUNCH(az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, (int*)nullptr);
+                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, (int*)nullptr, e->whereId);
             AZ_COUNT(e, AZ_TIMER_SORT, 2);
         }
         c = e->cur = 1 - c; // refresh_arrays (src/cuSort.cu:74-100): host-side ping-pong
@@ -680,7 +779,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.frc = e->frc; A.partV = e->partV; A.partC = e->partC; A.partN = e->partN; A.flags = &e->sc->overflow;
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
-        A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg;
+        A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg; A.r2_safe = e->r2_safe;
         A.blockFlag = dd_block_flags(e);
         if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
             const bool rb_next = step_rebuilds(e);
@@ -712,6 +811,17 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         }
     }
     if (e->ew.nk) { int rc = ewald_step(e, c); if (rc) return rc; }
+    if (e->bonded) { // apply_const_bonds / apply_angles (src/main.cu:307-311,352-362) onto the pair forces
+        Timer t(e, AZ_TIMER_PAIR);
+        AzBondedArgs B;
+        memset(&B, 0, sizeof(B));
+        B.pos = e->pos[c]; B.id = e->id[c]; B.whereId = e->whereId; B.frc = e->frc;
+        B.bStart = e->bStart; B.bEnt = e->bEnt; B.bTypes = e->bTypes; B.aStart = e->aStart; B.aEnt = e->aEnt; B.aTypes = e->aTypes;
+        B.partB = e->partBond; B.partA = e->partAngle;
+        AZ_LAUNCH(az_k_bonded, nb, AZ_TPB, 0, st, P, B);
+        AZ_LAUNCH(az_k_bonded_reduce, 1, 256, 0, st, e->partBond, e->partAngle, nb, e->sc);
+        AZ_COUNT(e, AZ_TIMER_PAIR, 2);
+    }
     if (ride) {
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
@@ -948,6 +1058,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     for (int t = 0; t < e->P.nspec; t++)
         for (int a = 0; a < 3; a++) { o->specAcBoxPos[t][a] = h.acPos[t][a]; o->specAcBoxNeg[t][a] = h.acNeg[t][a]; }
     o->engKin_d = h.engKin; o->engVdW_d = h.engVdW; o->engCoul1_d = h.engCoul1; o->engTemp_d = h.engTemp;
+    o->engBond = (float)h.engBond; o->engAngle = (float)h.engAngle; o->engBond_d = h.engBond; o->engAngle_d = h.engAngle;
     o->n_pairs = e->dd ? (long long)h.nVisits : (long long)h.nPairs;
     if (e->dd) { // collective: every rank reduces, then every rank sees the OR of the flags
         int flags = h.overflow;

@@ -47,6 +47,7 @@ struct az_engine {
     int warp_nblocks = 0;     // az_k_pair_warp: one warp per owned atom
     bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
+    float r2_safe = 3.4e38f; // packed Lennard-Jones list pass: below this r2 the reference's force_autocap clamp can act
     bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;
@@ -86,6 +87,13 @@ struct az_engine {
     unsigned long long* rdf_hist = nullptr;
     int rdf_nbins = 0, rdf_npair = 0, rdf_samples = 0, rdf_sten[3] = { 0, 0, 0 };
     float rdf_r2max = 0.f, rdf_idrdf = 0.f, rdf_r2stencil = 0.f;
+    // constant bonds and valence angles (az_k_bonded); bonded == false: nothing of this is allocated
+    bool bonded = false;
+    int* whereId = nullptr;          // persistent id -> current place in the sorted streams (written by az_k_sort_scatter)
+    int *bStart = nullptr, *aStart = nullptr;
+    int2* bEnt = nullptr; int4* aEnt = nullptr;
+    AzBondType* bTypes = nullptr; AzAngleType* aTypes = nullptr;
+    double *partBond = nullptr, *partAngle = nullptr;
     size_t dev_bytes = 0;
     // accounting
     long long launches = 0;

@@ -49,6 +49,7 @@ struct AzScalars {
     double engElecField;                      // per step
     double engKin, engVdW, engCoul1, engTemp; // per step, reduced
     double engCoul2, engCoul3;                // Ewald: reciprocal-space energy (az_k_ewald_reduce, every step), constant term (set once)
+    double engBond, engAngle;                 // constant bonds / valence angles (az_k_bonded_reduce, every step)
     float engKin_f;                           // after after_tscale
     float posMomBuf[AZ_N_MOM][3], negMomBuf[AZ_N_MOM][3];
     int iMom;
@@ -253,7 +254,7 @@ az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ 
                   const float4* __restrict__ pos, const float4* __restrict__ vel,
                   const int* __restrict__ id, const float2* __restrict__ therm,
                   float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o,
-                  float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex)
+                  float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex, int* __restrict__ whereId)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dyn) n = *n_dyn;
@@ -271,6 +272,7 @@ az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ 
     cell_o[d] = c;
     if (THERM) therm_o[d] = therm[i];
     if (newIndex) newIndex[i] = d; // domain decomposition: send lists and ghost slots follow the atoms
+    if (whereId) whereId[my] = d;  // bonds / angles name persistent ids (sort_bonds / sort_angles, src/cuSort.cu:199-235)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -533,7 +535,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode
     }
     if (mode & 16) {
         float engCoulTot = (float)sc->engCoul1 + (float)sc->engCoul2 + (float)sc->engCoul3; // src/main.cu:127
-        sc->engPot = engCoulTot + (float)sc->engVdW;
+        sc->engPot = engCoulTot + (float)sc->engVdW + (float)sc->engBond + (float)sc->engAngle; // src/main.cu:128
         sc->engTot = sc->engPot + sc->engKin_f;
         float pm[3] = { (float)sc->posMom[0], (float)sc->posMom[1], (float)sc->posMom[2] };
         float nm[3] = { (float)sc->negMom[0], (float)sc->negMom[1], (float)sc->negMom[2] };
@@ -565,6 +567,134 @@ az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode
         int* dst = reinterpret_cast<int*>(gsc);
         for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// constant bonds (apply_const_bonds, src/cuBonds.cu:709-797; potentials :1123-1224) and valence angles
+// (apply_angles + angle_hcos, src/cuAngles.cu:169-283).  The reference walks the bond list and scatters both forces of a
+// bond with float atomics; here one thread owns one atom and walks the bonds / angles that touch it (a CSR by persistent
+// id built at create time), so every force component is summed in a fixed order by the thread that owns it: no atomics,
+// bitwise reproducible.  A bond is evaluated by both of its atoms from the same delta = x(at1) - x(at2), an angle by all
+// three of its atoms; the energy is counted by the first atom / the centre.  `whereId` takes a persistent id to the
+// atom's current place in the sorted streams (the reference rewrites the lists after every sort instead).
+struct AzBondType { float p0, p1, p2, p3, p4; int kind; };
+struct AzAngleType { float k, cos0; };
+struct AzBondedArgs {
+    const float4* pos; const int* id; const int* whereId; float4* frc;
+    const int* bStart; const int2* bEnt;    // per persistent id: [bStart[id], bStart[id+1]) entries (partner id, type | first << 16)
+    const AzBondType* bTypes;
+    const int* aStart; const int4* aEnt;    // entries (id A, id B, type | role << 16, 0): role 0 = I am the centre (A, B = ligands 1, 2),
+    const AzAngleType* aTypes;              // 1 = I am ligand 1 (A = centre, B = ligand 2), 2 = I am ligand 2 (A = centre, B = ligand 1)
+    double *partB, *partA;
+};
+
+__device__ __forceinline__ float az_delta_periodic(float d, float L) // delta_periodic, src/cuMDfunc.cu:178-203
+{
+    const float h = 0.5f * L;
+    if (d > h) d -= L; else if (d < -h) d += L;
+    return d;
+}
+
+// force_eng of the five bond kinds: returns -dU/dr / r, adds U
+__device__ __forceinline__ float az_bond_feng(const AzBondType& b, float r2, float r, float& eng)
+{
+    switch (b.kind) {
+    case AZ_BOND_HARM: { const float x = r - b.p1; eng += 0.5f * b.p0 * x * x; return -b.p0 / r * x; }
+    case AZ_BOND_MORSE: {
+        float x = r - b.p2; x = expf(-b.p1 * x); const float y = 1.f - x;
+        eng += b.p0 * y * y - b.p3;
+        return (float)(-2.0 * b.p0 * b.p1 * x * y / r);
+    }
+    case AZ_BOND_PEDONE: {
+        float x = r - b.p2; x = expf(-b.p1 * x); const float y = 1.f - x;
+        const float ir2 = 1.f / r2; float irn = ir2 * ir2; irn = irn * irn * irn;
+        eng += b.p0 * y * y - b.p3 - b.p4 * irn;
+        return (float)(-2.0 * b.p0 * b.p1 * x * y / r - 12.0 * b.p4 * irn * ir2);
+    }
+    case AZ_BOND_BUCK: {
+        const float ir2 = (float)(1.0 / r2), irn = ir2 * ir2, ex = expf(-r / b.p1);
+        eng += b.p0 * ex - b.p2 * irn * ir2;
+        return b.p0 * ex / r / b.p1 - 6.f * b.p2 * irn * irn;
+    }
+    case AZ_BOND_E612: {
+        const float ir2 = (float)(1.0 / r2), irn = ir2 * ir2, ex = expf(-r / b.p1);
+        eng += b.p0 * ex - b.p2 * irn * ir2 - b.p3 * irn * irn - b.p4 * irn * irn * irn;
+        return (float)(b.p0 * ex / r / b.p1 - 6.f * b.p2 * irn * irn - 8.f * b.p3 * irn * irn * ir2 - 12.0 * b.p4 * irn * irn * irn * ir2);
+    }
+    }
+    return 0.f;
+}
+
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_bonded(const __grid_constant__ AzParams P, const __grid_constant__ AzBondedArgs A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double eb = 0.0, ea = 0.0;
+    if (i < az_n_owned(P)) {
+        const float4 p = A.pos[i];
+        const int me = A.id[i];
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (A.bStart)
+            for (int k = A.bStart[me]; k < A.bStart[me + 1]; k++) {
+                const int2 en = A.bEnt[k];
+                const float4 q = A.pos[A.whereId[en.x]];
+                const bool first = (en.y >> 16) != 0;
+                // delta = x(at1) - x(at2), whichever of the two I am: both ends then see the same F/r
+                const float dx = az_delta_periodic(first ? p.x - q.x : q.x - p.x, P.L[0]);
+                const float dy = az_delta_periodic(first ? p.y - q.y : q.y - p.y, P.L[1]);
+                const float dz = az_delta_periodic(first ? p.z - q.z : q.z - p.z, P.L[2]);
+                const float r2 = dx * dx + dy * dy + dz * dz, r = sqrtf(r2);
+                float e = 0.f;
+                const float f = az_bond_feng(A.bTypes[en.y & 0xffff], r2, r, e);
+                if (first) { fx += f * dx; fy += f * dy; fz += f * dz; eb += (double)e; }
+                else { fx -= f * dx; fy -= f * dy; fz -= f * dz; }
+            }
+        if (A.aStart)
+            for (int k = A.aStart[me]; k < A.aStart[me + 1]; k++) {
+                const int4 en = A.aEnt[k];
+                const int role = en.z >> 16;
+                const float4 qa = A.pos[A.whereId[en.x]], qb = A.pos[A.whereId[en.y]];
+                // (centre, ligand 1, ligand 2)
+                const float4 c = role == 0 ? p : qa, l1 = role == 0 ? qa : (role == 1 ? p : qb), l2 = role == 0 ? qb : (role == 1 ? qb : p);
+                const float ijx = az_delta_periodic(l1.x - c.x, P.L[0]), ijy = az_delta_periodic(l1.y - c.y, P.L[1]), ijz = az_delta_periodic(l1.z - c.z, P.L[2]);
+                const float ikx = az_delta_periodic(l2.x - c.x, P.L[0]), iky = az_delta_periodic(l2.y - c.y, P.L[1]), ikz = az_delta_periodic(l2.z - c.z, P.L[2]);
+                const float r2ij = ijx * ijx + ijy * ijy + ijz * ijz, rij = sqrtf(r2ij);
+                const float r2ik = ikx * ikx + iky * iky + ikz * ikz, rik = sqrtf(r2ik);
+                const float cos_th = (ijx * ikx + ijy * iky + ijz * ikz) / rij / rik;
+                const AzAngleType t = A.aTypes[en.z & 0xffff];
+                const float dCos = cos_th - t.cos0;
+                const float c1 = -t.k * dCos;
+                const float c2 = (float)(1.0 / rij / rik);
+                if (role == 0) {
+                    fx += -c1 * (ikx * c2 + ijx * c2 - cos_th * (ijx / r2ij + ikx / r2ik));
+                    fy += -c1 * (iky * c2 + ijy * c2 - cos_th * (ijy / r2ij + iky / r2ik));
+                    fz += -c1 * (ikz * c2 + ijz * c2 - cos_th * (ijz / r2ij + ikz / r2ik));
+                    ea += (double)(0.5f * t.k * dCos * dCos);
+                } else if (role == 1) {
+                    fx += c1 * (ikx * c2 - cos_th * ijx / r2ij); fy += c1 * (iky * c2 - cos_th * ijy / r2ij); fz += c1 * (ikz * c2 - cos_th * ijz / r2ij);
+                } else {
+                    fx += c1 * (ijx * c2 - cos_th * ikx / r2ik); fy += c1 * (ijy * c2 - cos_th * iky / r2ik); fz += c1 * (ijz * c2 - cos_th * ikz / r2ik);
+                }
+            }
+        float4 f = A.frc[i];
+        f.x += fx; f.y += fy; f.z += fz;
+        A.frc[i] = f;
+    }
+    __shared__ double sm[64];
+    double vv[2] = { eb, ea };
+    az_block_sum<2>(vv, sm);
+    if (threadIdx.x == 0) { A.partB[blockIdx.x] = vv[0]; A.partA[blockIdx.x] = vv[1]; }
+}
+
+// fixed-order sum of the per-block bonded energies (one block)
+static __global__ void __launch_bounds__(256)
+az_k_bonded_reduce(const double* __restrict__ partB, const double* __restrict__ partA, int n, AzScalars* __restrict__ sc)
+{
+    __shared__ double sm[64];
+    double v[2] = { 0.0, 0.0 };
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { v[0] += partB[k]; v[1] += partA[k]; }
+    az_block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { sc->engBond = v[0]; sc->engAngle = v[1]; }
 }
 
 // Nose-Hoover (src/cuTemp.cu:115-163): before_nose and after_nose(1) are pure scalar recurrences, so both run in one

@@ -17,6 +17,8 @@
 #include <time.h>
 #include <unistd.h>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/aztot_b200.h"
@@ -51,6 +53,54 @@ static void write_rdf(const char* fname, az_engine* eng, const az_deck* deck, co
             fprintf(f, "\t%f", acc * C1 * C2 * C3);
             l++;
             if (l == nspec) { k++; l = k; }
+        }
+        fprintf(f, "\n");
+    }
+    fclose(f);
+}
+
+// copy_nrdf (src/cuStat.cu:696-777): the same histogram by nuclei.  brute_nrdf adds 2 V / (NN_a NN_b) per pair to the bin of the
+// nucleus pair of the two species (src/cuStat.cu:675-676); the integer counts per species pair carry the same information.
+static void write_nrdf(const char* fname, az_engine* eng, const az_deck* deck, const az_system_desc* d, double dr)
+{
+    int nb = 0, np = 0, ns = 0;
+    if (az_engine_rdf_read(eng, nullptr, 0, &nb, &np, &ns) != AZ_OK || ns <= 0) return;
+    std::vector<unsigned long long> cnt((size_t)nb * np);
+    if (az_engine_rdf_read(eng, cnt.data(), (int)cnt.size(), nullptr, nullptr, nullptr) != AZ_OK) return;
+    const int nspec = d->n_species;
+    std::vector<int> nof(nspec);
+    const int nn = az_deck_nuclei(deck, nof.data());
+    if (nn <= 0) return;
+    FILE* f = fopen(fname, "w");
+    if (!f) return;
+    fprintf(f, "r");
+    for (int i = 0; i < nn; i++)
+        for (int j = i; j < nn; j++) fprintf(f, "\t%s-%s", az_deck_nucleus_name(deck, i), az_deck_nucleus_name(deck, j));
+    fprintf(f, "\n");
+    const double sphera = 4.0 * 3.14159265359 / 3.0;
+    const double C1 = 2 / (sphera * dr * dr * dr * ns);
+    const float volume = (float)(d->la * d->lb * d->lc);
+    const int nnp = nn * (nn + 1) / 2, m = nn - 1;
+    std::vector<double> acc(nnp);
+    for (int i = 0; i < nb; i++) {
+        fprintf(f, "%f", (i + 0.5) * dr);
+        const float C2 = 1.f / (3.f * i * (i + 1.f) + 1.f);
+        std::fill(acc.begin(), acc.end(), 0.0);
+        int k = 0, l = 0;
+        for (int j = 0; j < np; j++) { // species pair (k, l), k <= l -> nucleus pair
+            int a = nof[k], b = nof[l];
+            if (a > b) std::swap(a, b);
+            const int ip = a * m + a * (1 - a) / 2 + b; // n_iPair, src/cuStat.cu:668
+            acc[ip] += (double)((float)cnt[(size_t)i * np + j] * (volume / (float)az_deck_nucleus_count(deck, a) / (float)az_deck_nucleus_count(deck, b)));
+            l++;
+            if (l == nspec) { k++; l = k; }
+        }
+        k = 0; l = 0;
+        for (int j = 0; j < nnp; j++) {
+            const float C3 = (k == l) ? 1.f : 0.5f;
+            fprintf(f, "\t%f", (float)acc[j] * C1 * C2 * C3);
+            l++;
+            if (l == nn) { k++; l = k; }
         }
         fprintf(f, "\n");
     }
@@ -101,11 +151,16 @@ int main(int argc, char** argv)
     FILE* fm = fopen("msd.dat", "w");
     if (!fs || !fm) { printf("ERROR: cannot open stat.dat / msd.dat for writing\n"); return 1; }
     const bool radi = d->tstat_kind == AZ_TSTAT_RADI;
+    const bool has_bnd = d->n_bond_types > 0, has_ang = d->n_angle_types > 0; // fld->nBdata, fld->nAdata (src/cuStat.cu:311-314)
     fprintf(fs, "time\tstep\tengTot\tengKin\tengVdW\tengCoul1\tengCoul2");
     if (radi) fprintf(fs, "\tengTerm");
+    if (has_bnd) fprintf(fs, "\tengBnd");
+    if (has_ang) fprintf(fs, "\tengAngle");
     fprintf(fs, "\tmomPx\tmomNx\tmomPy\tmomNy\tmomPz\tmomNz\tpress");
     fprintf(fs, "\ntime, ps\tstep, n\tengTot, eV\tengKin, eV\tengVdW, eV\tengCoul1, eV\tengCoul2, eV");
     if (radi) fprintf(fs, "\tengTerm, eV");
+    if (has_bnd) fprintf(fs, "\tengBnd, eV");
+    if (has_ang) fprintf(fs, "\tengAngle, eV");
     fprintf(fs, "\tmomPx, eVps/A\tmomNx, eVps/A\tmomPy, eVps/A\tmomNy, eVps/A\tmomPz, eVps/A\tmomNz, eVps/A\tpress, atm\n");
     fprintf(fm, "time\tstep");
     for (int i = 0; i < nspec; i++) fprintf(fm, "\t%s_px\tnx\tpy\tny\tpz\tnz", d->species[i].name);
@@ -114,6 +169,7 @@ int main(int argc, char** argv)
     double rdf_rmax = 0.0, rdf_dr = 0.0;
     int rdf_freq = 0, rdf_outfreq = 0;
     bool rdf_on = az_deck_rdf(deck, &rdf_rmax, &rdf_dr, &rdf_freq, &rdf_outfreq) != 0;
+    const bool rdf_nucl = az_deck_rdf_nuclei(deck) != 0;
     if (rdf_on && az_engine_rdf_begin(eng, rdf_rmax, rdf_dr) != AZ_OK) {
         printf("WARNING: no RDF will be written: %s\n", az_last_error(eng));
         rdf_on = false;
@@ -140,6 +196,7 @@ int main(int argc, char** argv)
                 char name[64];
                 snprintf(name, sizeof(name), "rdf%d.dat", iStep);
                 write_rdf(name, eng, deck, d, rdf_dr);
+                if (rdf_nucl) { snprintf(name, sizeof(name), "rdf_n%d.dat", iStep); write_nrdf(name, eng, deck, d, rdf_dr); } // nrdf_iter, src/cuStat.cu:779-797
             }
         }
         if (iStep % stat == 0) {
@@ -147,6 +204,8 @@ int main(int argc, char** argv)
             double t = iStep * d->timestep;
             fprintf(fs, "%f\t%d\t%f\t%f\t%f\t%f\t%f", t, iStep, st.engTot, st.engKin, st.engVdW, st.engCoul1, st.engCoul2);
             if (radi) fprintf(fs, "\t%f", st.engTemp);
+            if (has_bnd) fprintf(fs, "\t%f", st.engBond);
+            if (has_ang) fprintf(fs, "\t%f", st.engAngle);
             fprintf(fs, "\t%f\t%f\t%f\t%f\t%f\t%f\t%f\n", st.posMom[0], st.negMom[0], st.posMom[1], st.negMom[1], st.posMom[2], st.negMom[2], st.pressure);
             fprintf(fm, "%f\t%d", t, iStep);
             for (int i = 0; i < nspec; i++)
@@ -159,6 +218,7 @@ int main(int argc, char** argv)
     if (rc == AZ_OK) print_stat(iStep, st, d); // final output to screen
     fclose(fs); fclose(fm);
     if (rdf_on) write_rdf("rdf.dat", eng, deck, d, rdf_dr);
+    if (rdf_on && rdf_nucl) write_nrdf("rdf_n.dat", eng, deck, d, rdf_dr); // copy_nrdf at the end of the run (src/main.cu:420-424)
 
     // md_to_host: atoms come back in cell-sorted order, like the reference
     const int n = d->n_atoms;

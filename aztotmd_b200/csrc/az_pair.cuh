@@ -47,6 +47,7 @@ struct AzPairArgs {
     int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
                              // in flight), 2 = blocks with ghosts (after the halo)
     int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
+    float r2_safe;           // packed LJ list pass: |F/r| < MX_FRC for every r2 in [r2_safe, gate] (+inf: always take the clamped form)
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
     int tile_cap;            // atoms the dynamic shared tile holds
@@ -346,6 +347,27 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
         jmax = max(jmax, re - 1);
         if (code == 0) {
             const int room = cap - nB;
+            if ((i < rb || i >= re) && nA + (re - rb) <= room) {
+                // the common case (8 of the 9 columns of an atom): atom i is not in the range and the rows cannot run out, so
+                // the loop body is the distance test and a predicated store + pointer bump.  Two candidates per FADD2 / FFMA2;
+                // each half is rounded like the scalar fmaf chain of the force pass, so the recorded set is the same.
+                int j = rb, o = nA * 32; // o: offset of the next free row, in ints (one IMAD.WIDE + ST + IADD per hit)
+#pragma unroll 2
+                for (; j + 2 <= re; j += 2) {
+                    const float4 pa = __ldg(A.pos + j), pb = __ldg(A.pos + j + 1);
+                    const az_f2 dx = az_pk(pi.x - pa.x, pi.x - pb.x), dy = az_pk(pi.y - pa.y, pi.y - pb.y), dz = az_pk(pi.z - pa.z, pi.z - pb.z);
+                    const az_f2 r2 = az_fma2(dz, dz, az_fma2(dx, dx, az_mul2(dy, dy)));
+                    if (az_lo(r2) <= lim) { rows[o] = j; o += 32; }
+                    if (az_hi(r2) <= lim) { rows[o] = j + 1; o += 32; }
+                }
+                if (j < re) {
+                    const float4 pj = __ldg(A.pos + j);
+                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                    if (fmaf(dz, dz, fmaf(dx, dx, dy * dy)) <= lim) { rows[o] = j; o += 32; }
+                }
+                nA = o >> 5;
+                return;
+            }
 #pragma unroll 4
             for (int j = rb; j < re; j++) {
                 const float4 pj = __ldg(A.pos + j);
@@ -474,7 +496,22 @@ __device__ __forceinline__ int az_ld_stream(const int* p)
 // current positions as the cell sweep, so the pair set per step is identical to the every-step-rebuild
 // schedule as long as no atom moved more than skin/2 (tracked by az_k_integrate_a / az_k_finalize).
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
-__global__ void __launch_bounds__(AZ_LIST_TPB, (VK == AZ_VDW_LJ && CK == AZ_ELEC_NONE && SINGLE && !RADII && !ENERGY) ? 2048 / AZ_LIST_TPB : 1280 / AZ_LIST_TPB)
+// AZ_LIST_PACKED = 1 selects the f32x2 form of the Lennard-Jones row loop (FADD2 / FMUL2 / FFMA2: 17 issue slots per
+// row instead of 26).  Measured on B200 (profiles/r2/): it is SLOWER -- 0.427 ms per pass at 40 registers / 48 warps per SM,
+// 0.438 ms at 48 / 40, 0.73 ms at 32 / 64 with spills, against 0.385 ms for the scalar loop at 32 registers / 64 warps --
+// because the pass is bound by the L1 data pipe, not by issue slots: every gather LDG.128 touches ~6 distinct 128-byte
+// lines (ncu: l1tex__data_pipe_lsu_wavefronts 80 % of peak, issue 42 %), and with fewer resident warps less of that
+// latency is hidden.  The scalar loop stays the default; the packed loop is kept for the measurement.
+#ifndef AZ_LIST_PACKED
+#define AZ_LIST_PACKED 0
+#endif
+#ifndef AZ_LIST_CHUNK
+#define AZ_LIST_CHUNK 4
+#endif
+#ifndef AZ_LIST_LJ_WARPS
+#define AZ_LIST_LJ_WARPS (AZ_LIST_PACKED ? 48 : 64) // resident warps per SM the plain Lennard-Jones form asks for (40 / 32 registers)
+#endif
+__global__ void __launch_bounds__(AZ_LIST_TPB, (VK == AZ_VDW_LJ && CK == AZ_ELEC_NONE && SINGLE && !RADII && !ENERGY) ? AZ_LIST_LJ_WARPS * 32 / AZ_LIST_TPB : 1280 / AZ_LIST_TPB)
 az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
@@ -502,7 +539,15 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         const int cnt = cnt2 & ((1 << AZ_NBR_CNT_BITS) - 1), cntB = cnt2 >> AZ_NBR_CNT_BITS;
         constexpr int stride = 32; // ints between consecutive rows of one atom (one 128-byte line per warp and row)
         constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
+#if defined(AZ_LIST_DBG) || (!AZ_LIST_PACKED && !defined(AZ_EMU))
+        constexpr bool PACKED = false;
+#else
+        constexpr bool PACKED = FOLD && VK == AZ_VDW_LJ && !RADII; // the emulator build always exercises the packed form's logic
+#endif
         const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
+        const int* __restrict__ const rows = A.nbr + az_nbr_base(i, A.nbr_cap);
+        // ---- scalar form: every (vdW, Coulomb) combination; the reference's force_autocap clamp on every pair
+        auto scalar_rows = [&]() {
         // one neighbour: pair term from the finished delta, masked accumulate
         auto one = [&](const float dx, const float dy, const float dz, const float4 pj, const float radj) {
             const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
@@ -516,7 +561,6 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
         };
         auto plain = [&](const float4 pj, const float radj) { one(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z, pj, radj); };
-        const int* __restrict__ const rows = A.nbr + az_nbr_base(i, A.nbr_cap);
         const int* __restrict__ row = rows;
         int k = 0;
         // software pipeline by hand: the index loads of chunk k+1 (HBM stream) are in flight while the
@@ -563,6 +607,81 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             const float sz = ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
             one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
+        };
+        if (PACKED) {
+            // ---- packed form (one Lennard-Jones entry, no Coulomb): two list rows per FADD2 / FMUL2 / FFMA2.  Each half is
+            // the scalar arithmetic of az_vdw_feng<LJ> rounded the same way; the clamp of force_autocap is left out of the
+            // loop and the smallest r2 is tracked instead: F/r of this entry stays inside +-MX_FRC for every r2 >= r2_safe
+            // (worked out by the host from the table entry), so the clamp is the identity unless min r2 < r2_safe -- a hot
+            // collision -- and then the atom is redone in the scalar, clamped form below.
+            const az_f2 kp1 = az_pk1(A.single.p1), kp2 = az_pk1(A.single.p2), kp0 = az_pk1(A.single.p0);
+            const az_f2 ktwo = az_pk1(2.f), kmone = az_pk1(-1.f);
+            az_f2 fx2 = az_pk1(0.f), fy2 = fx2, fz2 = fx2, ev2 = fx2;
+            bool hot = false; // some r2 below r2_safe (kept in a predicate register)
+            const float safe = A.r2_safe;
+            auto two = [&](const az_f2 dx, const az_f2 dy, const az_f2 dz) {
+                const az_f2 r2 = az_fma2(dz, dz, az_fma2(dx, dx, az_mul2(dy, dy)));
+                const float ra = az_lo(r2), rb = az_hi(r2);
+                hot |= (ra < safe) | (rb < safe);
+                // the gate acts on 1/r2: a row outside it carries sr6 = 0, hence F/r = -0 and U = -0, which leave the sums as they are
+                const bool ina = ra <= gate, inb = rb <= gate;
+                const az_f2 r2i = az_pk(ina ? az_fast_rcp(ra) : 0.f, inb ? az_fast_rcp(rb) : 0.f);
+                const az_f2 sr2 = az_mul2(kp1, r2i);
+                const az_f2 sr6 = az_mul2(az_mul2(sr2, sr2), sr2);
+                const az_f2 f = az_mul2(az_mul2(az_mul2(kp2, r2i), sr6), az_fma2(ktwo, sr6, kmone));
+                fx2 = az_fma2(f, dx, fx2); fy2 = az_fma2(f, dy, fy2); fz2 = az_fma2(f, dz, fz2);
+                if (ENERGY) {
+                    ev2 = az_fma2(az_mul2(kp0, sr6), az_add2(sr6, kmone), ev2);
+                    hits += (ina ? 1 : 0) + (inb ? 1 : 0);
+                }
+            };
+            auto pair2 = [&](const float4 pa, const float4 pb) { two(az_pk(pi.x - pa.x, pi.x - pb.x), az_pk(pi.y - pa.y, pi.y - pb.y), az_pk(pi.z - pa.z, pi.z - pb.z)); };
+            constexpr float FAR = 1.0e15f; // second half of an odd row: r2 = 3e30, outside every gate
+            const int* __restrict__ row = rows;
+            int k = 0;
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#if AZ_LIST_CHUNK == 2
+            if (cnt >= 2) { c0 = az_ld_stream(row); c1 = az_ld_stream(row + stride); }
+#pragma unroll 1
+            for (; k + 2 <= cnt; k += 2) {
+                row += 2 * stride;
+                const float4 p0 = __ldg(A.pos + c0), p1 = __ldg(A.pos + c1);
+                if (k + 4 <= cnt) { c0 = az_ld_stream(row); c1 = az_ld_stream(row + stride); }
+                pair2(p0, p1);
+            }
+            (void)c2; (void)c3;
+#else
+            if (cnt >= 4) { c0 = az_ld_stream(row); c1 = az_ld_stream(row + stride); c2 = az_ld_stream(row + 2 * stride); c3 = az_ld_stream(row + 3 * stride); }
+#pragma unroll 1
+            for (; k + 4 <= cnt; k += 4) {
+                row += 4 * stride;
+                const float4 p0 = __ldg(A.pos + c0), p1 = __ldg(A.pos + c1), p2 = __ldg(A.pos + c2), p3 = __ldg(A.pos + c3);
+                int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                if (k + 8 <= cnt) { n0 = az_ld_stream(row); n1 = az_ld_stream(row + stride); n2 = az_ld_stream(row + 2 * stride); n3 = az_ld_stream(row + 3 * stride); }
+                pair2(p0, p1); pair2(p2, p3);
+                c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            }
+#endif
+            for (; k < cnt; k++) {
+                const int c = az_ld_stream(row); row += stride;
+                const float4 pj = __ldg(A.pos + c);
+                two(az_pk(pi.x - pj.x, FAR), az_pk(pi.y - pj.y, FAR), az_pk(pi.z - pj.z, FAR));
+            }
+            const int* __restrict__ rowB = rows + (A.nbr_cap - 1) * stride;
+            for (int kb = 0; kb < cntB; kb++) {
+                const int c = *rowB; rowB -= stride;
+                const int j = c & AZ_NBR_MASK, sc = (int)((unsigned)c >> AZ_NBR_BITS);
+                const float4 pj = __ldg(A.pos + j);
+                const float sx = ((float)((sc >> 1) & 1) - (float)(sc & 1)) * P.L[0];
+                const float sy = ((float)((sc >> 3) & 1) - (float)((sc >> 2) & 1)) * P.L[1];
+                const float sz = ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
+                two(az_pk((pi.x - pj.x) - sx, FAR), az_pk((pi.y - pj.y) - sy, FAR), az_pk((pi.z - pj.z) - sz, FAR));
+            }
+            if (!hot) {
+                fx = az_lo(fx2) + az_hi(fx2); fy = az_lo(fy2) + az_hi(fy2); fz = az_lo(fz2) + az_hi(fz2);
+                if (ENERGY) ev = az_lo(ev2) + az_hi(ev2);
+            } else { hits = 0; scalar_rows(); } // a pair close enough for the clamp (or coincident atoms): the clamped form decides
+        } else scalar_rows();
         const float q = P.charge[ti];
         const float4 f = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
         if (!A.fuse) A.frc[i] = f;

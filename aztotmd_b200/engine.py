@@ -76,7 +76,12 @@ class System:
     init_radii: Optional[np.ndarray] = None
     init_engs: Optional[np.ndarray] = None
     seed: int = 12345
-    n_bonds: int = 0
+    # constant bonds / valence angles.  bond_types[k] = (kind name, params), k = 1.. (type 0 is the empty entry);
+    # bonds = rows (atom 1, atom 2, type); angle_types[k] = (k, cos theta0); angles = rows (centre, ligand 1, ligand 2, type)
+    bond_types: Sequence = ()
+    bonds: Optional[np.ndarray] = None
+    angle_types: Sequence = ()
+    angles: Optional[np.ndarray] = None
     # domain decomposition, distributed input: this rank's share of the system with its persistent ids
     global_ids: Optional[np.ndarray] = None
     n_atoms_global: int = 0
@@ -113,6 +118,10 @@ class System:
     @property
     def r_max(self) -> float:  # src/sys_init.cpp:1059-1072
         return self.r_real if self.effective_elec_kind else self.max_r_vdw
+
+    @property
+    def n_bonds(self) -> int:
+        return 0 if self.bonds is None else len(self.bonds)
 
     @property
     def deg_free(self) -> int:  # src/sys_init.cpp:1099-1102
@@ -234,6 +243,31 @@ class DescHolder:
         d.reset_vels = int(s.reset_vels)
         for a in range(3):
             d.ewald_k[a] = int(s.ewald_k[a]) if ek == abi.ELEC_EWALD else 0
+
+        def ints(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            self.keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int))
+
+        if s.bonds is not None and len(s.bonds):
+            bt = (abi.az_bond_type * (len(s.bond_types) + 1))()
+            for k, (name, par) in enumerate(s.bond_types):
+                t = bt[k + 1]
+                t.kind = abi.BOND_BY_NAME[name]
+                p = list(par) + [0.0] * (5 - len(par))
+                t.p0, t.p1, t.p2, t.p3, t.p4 = p
+            self.keep.append(bt)
+            b = np.asarray(s.bonds, dtype=np.int32)
+            d.n_bond_types, d.n_bonds, d.bond_types = len(bt), len(b), bt
+            d.bond_at1, d.bond_at2, d.bond_type = ints(b[:, 0]), ints(b[:, 1]), ints(b[:, 2])
+        if s.angles is not None and len(s.angles):
+            at = (abi.az_angle_type * (len(s.angle_types) + 1))()
+            for k, (kk, c0) in enumerate(s.angle_types):
+                at[k + 1].kind, at[k + 1].p0, at[k + 1].p1 = abi.ANGLE_HCOS, kk, c0
+            self.keep.append(at)
+            a = np.asarray(s.angles, dtype=np.int32)
+            d.n_angle_types, d.n_angles, d.angle_types = len(at), len(a), at
+            d.angle_centre, d.angle_lig1, d.angle_lig2, d.angle_type = ints(a[:, 0]), ints(a[:, 1]), ints(a[:, 2]), ints(a[:, 3])
         self.desc = d
 
 

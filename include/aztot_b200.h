@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define AZ_ABI_VERSION 1
+#define AZ_ABI_VERSION 2
 #define AZ_MAX_SPECIES 15   /* MX_SPEC, src/defines.h:15 */
 #define AZ_N_UVECT 3072     /* nUvect, src/cuTemp.h:4-6 = 3 * 32 * 16 * 2 */
 #define AZ_N_MOM 20         /* nMom, src/cuInit.cu:921 (pressure ring length) */
@@ -80,6 +80,32 @@ typedef enum az_tstat_kind {
     AZ_TSTAT_NOSE = 1, /* before_nose / tstat_nose / after_nose  src/cuTemp.cu:115-163 (applied twice per step, src/main.cu:291-299 and apply_tstat) */
     AZ_TSTAT_RADI = 2  /* tstat_radi9  src/cuTemp.cu:689-773 */
 } az_tstat_kind;
+
+/* constant bonds (apply_const_bonds, src/cuBonds.cu:709-797) and valence angles (apply_angles,
+ * src/cuAngles.cu:169-228).  Bond kinds are the reference's type ids (define_bond_potential, src/cuBonds.cu:1236-1270;
+ * parameters as read_bond leaves them, src/bonds.cpp:125-250). */
+typedef enum az_bond_kind {
+    AZ_BOND_NONE = 0,   /* empty entry: type 0 is reserved for "no bond" (src/cuBonds.cu:731)                    */
+    AZ_BOND_HARM = 1,   /* harm  U = 1/2 k (r-r0)^2                       p0 = k, p1 = r0                        */
+    AZ_BOND_MORSE = 2,  /* mors  U = D[1-exp(-a(r-r0))]^2 - C             p0 = D, p1 = a, p2 = r0, p3 = C        */
+    AZ_BOND_PEDONE = 3, /* pdn   U = Morse - E/r^12                       ... p4 = E                             */
+    AZ_BOND_BUCK = 4,   /* buck  U = A exp(-r/ro) - C/r^6                 p0 = A, p1 = ro, p2 = C                */
+    AZ_BOND_E612 = 5    /* e612  U = A exp(-r/ro) - C/r^6 - D/r^8 - F/r^12   p0..p4 = A, ro, C, D, F             */
+} az_bond_kind;
+
+typedef struct az_bond_type {
+    int kind;           /* az_bond_kind */
+    int spec1, spec2;   /* species of the first / second atom (read_bond; informational) */
+    int reserved;
+    double p0, p1, p2, p3, p4;
+} az_bond_type;
+
+#define AZ_ANGLE_HCOS 1 /* hcos  U = 1/2 k (cos th - cos th0)^2, src/cuAngles.cu:230-283: p0 = k, p1 = cos th0 */
+typedef struct az_angle_type {
+    int kind;           /* 0 = empty, AZ_ANGLE_HCOS */
+    int central;        /* species of the central atom (informational) */
+    double p0, p1;
+} az_angle_type;
 
 /* One species; mirror of the fields of Spec that init_cudaMD reads
  * (src/cuInit.cu:843-866).  Internal units (mass already * m_scale). */
@@ -161,6 +187,16 @@ typedef struct az_system_desc {
      * part only, as the reference's CUDA build does. */
     int ewald_k[3];            /* Elec::kx, ky, kz: l in [0,kx), m in (-ky,ky), n in (-kz,kz) */
     int reserved4;
+    /* constant bonds and valence angles ('bonds' / 'bond_list' + bonds.txt, 'angles' / 'angle_list' +
+     * angles.txt; src/bonds.cpp:25-110, src/angles.cpp:20-130).  Atom indices are positions in the arrays above
+     * (atoms.xyz order); the engine follows the atoms through every sort itself (what sort_bonds / sort_angles,
+     * src/cuSort.cu:199-235, do in the reference).  Type 0 of either table is the empty entry.  Single GPU only. */
+    int n_bond_types, n_bonds;
+    const az_bond_type *bond_types;                 /* [n_bond_types]                         */
+    const int *bond_at1, *bond_at2, *bond_type;     /* [n_bonds]                              */
+    int n_angle_types, n_angles;
+    const az_angle_type *angle_types;               /* [n_angle_types]                        */
+    const int *angle_centre, *angle_lig1, *angle_lig2, *angle_type; /* [n_angles]             */
 } az_system_desc;
 
 /* cuda.txt-level options plus the multi-GPU layout.  Zero-initialise for defaults. */
@@ -200,6 +236,8 @@ typedef struct az_stats {
     float engCoul3;      /* Ewald: constant term (ewald_const, src/elec.cpp:144-165); engCoul2 = reciprocal-space energy */
     float reserved;
     double engCoul2_d;
+    float engBond, engAngle;   /* md->engBond, md->engAngl (part of engPot, src/main.cu:128) */
+    double engBond_d, engAngle_d;
 } az_stats;
 
 #define AZ_ORDER_SORTED 0   /* cell-sorted order, what md_to_host hands back */
@@ -346,6 +384,13 @@ int az_deck_nstep_stat(const az_deck *d);         /* cuda.txt 'nstep stat' (flus
 int az_deck_species_count(const az_deck *d, int species);
 /* the 'rdf rmax dr freq outfreq' directive (src/rdf.cpp:14-37); returns 0 if the deck has none */
 int az_deck_rdf(const az_deck *d, double *r_max, double *dr, int *freq, int *outfreq);
+/* 'rdf ... nucl': the by-nuclei table of brute_nrdf / copy_nrdf (src/cuStat.cu:614-777).  Every species names its nucleus
+ * (second word of a 'spec' line, read_spec src/sys_init.cpp:78-104).  az_deck_nuclei returns the number of distinct nuclei
+ * and, if asked, the nucleus index of every species; az_deck_rdf_nuclei says whether the deck asked for rdf_n.dat. */
+int az_deck_nuclei(const az_deck *d, int *nucleus_of_species /* [n_species] or NULL */);
+const char *az_deck_nucleus_name(const az_deck *d, int nucleus);
+int az_deck_nucleus_count(const az_deck *d, int nucleus);   /* atoms carrying that nucleus (Field::nnumbers) */
+int az_deck_rdf_nuclei(const az_deck *d);
 void az_deck_free(az_deck *d);
 
 #ifdef __cplusplus

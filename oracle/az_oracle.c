@@ -311,6 +311,12 @@ typedef struct azo_state {
     double ew_alpha, ew_eps, boxd[3];
     double engCoul2, engCoul3;
     float *frx, *fry, *frz; /* the k-space force of the last evaluation alone (sorted order), for the parity tests */
+    /* constant bonds and valence angles, by persistent id (the reference remaps the indices through every
+     * sort instead: sort_bonds / sort_angles, src/cuSort.cu:199-235) */
+    int n_bonds, n_btypes, *b_at1, *b_at2, *b_type, *bt_kind; float *bt_par;
+    int n_angles, n_atypes, *a_c, *a_l1, *a_l2, *a_type; float *at_par;
+    int *where; /* current (sorted) index of persistent id */
+    double engBond, engAngle;
 } azo_state;
 
 static void *xmalloc(size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) { fprintf(stderr, "azo: oom\n"); abort(); } return p; }
@@ -400,6 +406,26 @@ azo_state *azo_create(const az_system_desc *d)
         s->frx = (float *)xmalloc(sizeof(float) * n); s->fry = (float *)xmalloc(sizeof(float) * n); s->frz = (float *)xmalloc(sizeof(float) * n);
         s->engCoul3 = azo_ewald_const(n, d->types, d->species, d->alpha, s->ew_eps, d->la * d->lb * d->lc);
     }
+    if (d->n_bonds > 0 || d->n_angles > 0) s->where = (int *)xmalloc(sizeof(int) * n);
+    if (d->n_bonds > 0) {
+        s->n_bonds = d->n_bonds; s->n_btypes = d->n_bond_types;
+        s->b_at1 = (int *)xmalloc(sizeof(int) * d->n_bonds); s->b_at2 = (int *)xmalloc(sizeof(int) * d->n_bonds); s->b_type = (int *)xmalloc(sizeof(int) * d->n_bonds);
+        memcpy(s->b_at1, d->bond_at1, sizeof(int) * d->n_bonds); memcpy(s->b_at2, d->bond_at2, sizeof(int) * d->n_bonds); memcpy(s->b_type, d->bond_type, sizeof(int) * d->n_bonds);
+        s->bt_kind = (int *)xmalloc(sizeof(int) * d->n_bond_types); s->bt_par = (float *)xmalloc(sizeof(float) * 5 * d->n_bond_types);
+        for (int t = 0; t < d->n_bond_types; t++) { /* narrowed like init_cudaMD narrows cudaBond (src/cuInit.cu) */
+            const az_bond_type *b = &d->bond_types[t];
+            s->bt_kind[t] = b->kind;
+            s->bt_par[5 * t] = (float)b->p0; s->bt_par[5 * t + 1] = (float)b->p1; s->bt_par[5 * t + 2] = (float)b->p2; s->bt_par[5 * t + 3] = (float)b->p3; s->bt_par[5 * t + 4] = (float)b->p4;
+        }
+    }
+    if (d->n_angles > 0) {
+        s->n_angles = d->n_angles; s->n_atypes = d->n_angle_types;
+        s->a_c = (int *)xmalloc(sizeof(int) * d->n_angles); s->a_l1 = (int *)xmalloc(sizeof(int) * d->n_angles); s->a_l2 = (int *)xmalloc(sizeof(int) * d->n_angles); s->a_type = (int *)xmalloc(sizeof(int) * d->n_angles);
+        memcpy(s->a_c, d->angle_centre, sizeof(int) * d->n_angles); memcpy(s->a_l1, d->angle_lig1, sizeof(int) * d->n_angles);
+        memcpy(s->a_l2, d->angle_lig2, sizeof(int) * d->n_angles); memcpy(s->a_type, d->angle_type, sizeof(int) * d->n_angles);
+        s->at_par = (float *)xmalloc(sizeof(float) * 2 * d->n_angle_types);
+        for (int t = 0; t < d->n_angle_types; t++) { s->at_par[2 * t] = (float)d->angle_types[t].p0; s->at_par[2 * t + 1] = (float)d->angle_types[t].p1; }
+    }
     s->last_step = -1;
     return s;
 }
@@ -413,6 +439,8 @@ void azo_destroy(azo_state *s)
     free(s->type); free(s->id); free(s->cell); free(s->order); free(s->t_i[0]); free(s->t_i[1]);
     free(s->first); free(s->count);
     free(s->frx); free(s->fry); free(s->frz);
+    free(s->b_at1); free(s->b_at2); free(s->b_type); free(s->bt_kind); free(s->bt_par);
+    free(s->a_c); free(s->a_l1); free(s->a_l2); free(s->a_type); free(s->at_par); free(s->where);
     free(s);
 }
 
@@ -699,6 +727,35 @@ double azo_apply_angles(int n_angles, const int *centre, const int *lig1, const 
     return eng;
 }
 
+/* The bonded terms of one step on the sorted arrays (src/main.cu:307-311 apply_const_bonds, :352-362 apply_angles): the
+ * lists name persistent ids, `where` takes them to the current order.  The reference adds them with float atomics; here
+ * per-atom sums are formed in double and narrowed once, like forces() does. */
+static void bonded(azo_state *s)
+{
+    s->engBond = 0.0; s->engAngle = 0.0;
+    if (!s->n_bonds && !s->n_angles) return;
+    const int n = s->n;
+    for (int i = 0; i < n; i++) s->where[s->id[i]] = i;
+    double *f = (double *)xmalloc(sizeof(double) * 3 * n), *fx = f, *fy = f + n, *fz = f + 2 * n;
+    if (s->n_bonds) {
+        int *c1 = (int *)xmalloc(sizeof(int) * s->n_bonds), *c2 = (int *)xmalloc(sizeof(int) * s->n_bonds);
+        for (int b = 0; b < s->n_bonds; b++) { c1[b] = s->where[s->b_at1[b]]; c2[b] = s->where[s->b_at2[b]]; }
+        s->engBond = azo_apply_const_bonds(s->n_bonds, c1, c2, s->b_type, s->bt_kind, s->bt_par, n, s->x, s->y, s->z, s->L, fx, fy, fz);
+        free(c1); free(c2);
+    }
+    if (s->n_angles) {
+        int *c0 = (int *)xmalloc(sizeof(int) * s->n_angles), *c1 = (int *)xmalloc(sizeof(int) * s->n_angles), *c2 = (int *)xmalloc(sizeof(int) * s->n_angles);
+        for (int a = 0; a < s->n_angles; a++) { c0[a] = s->where[s->a_c[a]]; c1[a] = s->where[s->a_l1[a]]; c2[a] = s->where[s->a_l2[a]]; }
+        s->engAngle = azo_apply_angles(s->n_angles, c0, c1, c2, s->a_type, s->at_par, s->x, s->y, s->z, s->L, fx, fy, fz);
+        free(c0); free(c1); free(c2);
+    }
+    for (int i = 0; i < n; i++) {
+        s->fx[i] += (float)fx[i]; s->fy[i] += (float)fy[i]; s->fz[i] += (float)fz[i];
+        s->fscale[i] += (float)(fabs(fx[i]) + fabs(fy[i]) + fabs(fz[i])); /* the bonded terms join the scale the force tolerance is relative to */
+    }
+    free(f);
+}
+
 /* ------------------------------------------------- reciprocal-space Ewald ---- */
 #define FCOUL_SCALE_D 14.3996 /* the engine's Coulomb constant (d_Fcoul_scale, src/main.cu:40); the serial twin's
                                * Fcoul_scale (src/const.h:44) is the same number to 6 digits */
@@ -957,7 +1014,7 @@ static void apply_tstat(azo_state *s, int step)
 static void calc_quantities(azo_state *s, int step)
 {
     float engCoulTot = (float)s->engCoul1 + (float)s->engCoul2 + (float)s->engCoul3; /* src/main.cu:127 */
-    s->engPot = engCoulTot + (float)s->engVdW;
+    s->engPot = engCoulTot + (float)s->engVdW + (float)s->engBond + (float)s->engAngle; /* src/main.cu:128 */
     s->engTot = s->engPot + s->engKin_f;
     float pm[3] = { (float)s->posMom[0], (float)s->posMom[1], (float)s->posMom[2] };
     float nm[3] = { (float)s->negMom[0], (float)s->negMom[1], (float)s->negMom[2] };
@@ -989,6 +1046,7 @@ int azo_step(azo_state *s, int first_step, int nsteps)
         sort_atoms(s);
         forces(s);
         ewald_rec(s);                                     /* add_elec, src/main.cpp:99 (src/main.cu:330-336) */
+        bonded(s);                                        /* apply_const_bonds / apply_angles, src/main.cu:307-311,352-362 */
         if (s->reset_vels && step % s->reset_vels == 0) { /* zero_vel, src/main.cu:372-374, src/cuMDfunc.cu:602-622 */
             for (int i = 0; i < s->n; i++) { s->vx[i] = 0.f; s->vy[i] = 0.f; s->vz[i] = 0.f; }
             s->engKin = 0.0; s->engKin_f = 0.f;
@@ -1014,6 +1072,7 @@ int azo_forces_only(azo_state *s)
     sort_atoms(s);
     forces(s);
     ewald_rec(s);
+    bonded(s);
     return 0;
 }
 
@@ -1031,6 +1090,7 @@ int azo_stats(azo_state *s, az_stats *o)
         o->specAcBoxPos[t][a] = s->acPos[t][a]; o->specAcBoxNeg[t][a] = s->acNeg[t][a];
     }
     o->engKin_d = s->engKin; o->engVdW_d = s->engVdW; o->engCoul1_d = s->engCoul1; o->engTemp_d = s->engTemp;
+    o->engBond = (float)s->engBond; o->engAngle = (float)s->engAngle; o->engBond_d = s->engBond; o->engAngle_d = s->engAngle;
     return 0;
 }
 

@@ -45,7 +45,7 @@ rw("main.cu", lambda s: s.replace("texture<float, 2, cudaReadModeElementType> qP
 PY
 cd "$TMP"
 pids=()
-for f in *.cu; do "$NVCC" -O2 -arch=sm_100a -rdc=true -w -Xcompiler -fpermissive -I. -c "$f" -o "${f%.cu}.o" & pids+=($!); done
+for f in *.cu; do "$NVCC" -O2 -lineinfo -arch=sm_100a -rdc=true -w -Xcompiler -fpermissive -I. -c "$f" -o "${f%.cu}.o" & pids+=($!); done
 for f in angles bonds box cell_list ejump elec integrators md_utils out_md rdf sys_init temperature utils vdw; do
   g++ -O2 -std=c++17 -fpermissive -w -I. -c "$f.cpp" -o "$f.o" & pids+=($!)
 done

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 out=aztotmd_b200/lib/variants/$name
 mkdir -p $out/obj
-C=aztotmd_b200/csrc
+C=${AZ_VARIANT_SRC:-aztotmd_b200/csrc}
 pids=()
 for f in az_engine az_pair_inst_lj az_pair_inst_buck az_pair_inst_surk az_pair_inst_mixed; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -I include -I $C "$@" -c $C/$f.cu -o $out/obj/$f.o &

@@ -49,6 +49,9 @@ def assert_stats_close(so, se, tol=ENERGY_TOL, thermo=False, escale=None):
     # reciprocal-space Ewald: k-space energy (fp32 phases against the oracle's double ones) and the constant term
     assert abs(so.engCoul2_d - se.engCoul2_d) <= 10 * tol * max(abs(so.engCoul2_d), floor), "engCoul2: oracle %r engine %r" % (so.engCoul2_d, se.engCoul2_d)
     assert abs(so.engCoul3 - se.engCoul3) <= tol * max(abs(so.engCoul3), floor)
+    for k in ("engBond_d", "engAngle_d"):  # bonded energies (exp / acos-free forms in fp32: 5e-6 like the reference pinning)
+        a, b = getattr(so, k), getattr(se, k)
+        assert abs(a - b) <= max(tol, 5e-6) * max(abs(a), floor), "%s: oracle %r engine %r" % (k, a, b)
     assert abs(so.engTot - se.engTot) <= 4 * tol * max(abs(so.engTot), floor)
 
 
@@ -437,6 +440,90 @@ def case_list_every_step_variant(lib):
     e.close()
 
 
+def case_force_autocap_fires(lib):
+    """force_autocap (src/cuPairs.cu:94-115): two pairs are put 0.5 A and 0.9 A apart, where the Lennard-Jones F/r is
+    1.8e10 and 1.6e7 -- far beyond MX_FRC = 1e4 -- so the clamp decides the force on those four atoms.  Every pair pass
+    is driven through it: the warp sweep (default for small systems), the shared-memory tiles, the Verlet list rebuilt
+    every step (whose packed f32x2 loop leaves the clamp to a scalar redo of the atoms that need it) and the list
+    reused between rebuilds."""
+    s = azt.lj_system(ncell=(5, 5, 5), seed=71, vel=False)
+    pos = s.pos.copy()
+    pos[1] = pos[0] + np.array([0.3, -0.4, 0.0])          # r = 0.5 A
+    pos[101] = pos[100] + np.array([0.0, 0.54, 0.72])     # r = 0.9 A
+    s.pos = pos
+    for kw in ({}, {"pair_variant": 1}, {"pair_variant": 2}, {"rebuild_every": 4, "skin": 0.6}):
+        if "rebuild_every" in kw:
+            s.cell_size = 2.5 * azt.AR_SIGMA + 0.6
+        o, e = run_parity(lib, s, nsteps=1, **kw) # zero velocities, zero initial forces: step 0 evaluates the initial positions
+        f = azt.sort_by_id(e.dump())["frc"].astype(np.float64)
+        # the clamped pair term is exactly MX_FRC * delta; the other ~55 neighbours add forces of order 0.1
+        assert abs(np.linalg.norm(f[0]) - 1e4 * 0.5) < 5.0 and abs(np.linalg.norm(f[1]) - 1e4 * 0.5) < 5.0, (kw, f[0], f[1])
+        assert abs(np.linalg.norm(f[100]) - 1e4 * 0.9) < 5.0 and abs(np.linalg.norm(f[101]) - 1e4 * 0.9) < 5.0, (kw, f[100], f[101])
+        e.close()
+
+
+def bonded_lj_system(seed=81, angles=True, **kw):
+    """500 argon atoms with a list of constant bonds (harmonic and Morse alternating; the last one reaches through a
+    periodic face) and harmonic-cosine valence angles -- the layout of tests/golden/make_golden.py's bonded decks."""
+    s = azt.lj_system(ncell=(5, 5, 5), seed=seed, **kw)
+    n = len(s.pos)
+    s.bond_types = [("harm", [5.0, 3.8]), ("mors", [0.4, 1.5, 4.0, 0.4]), ("pdn", [0.3, 1.2, 4.1, 0.3, 50.0]), ("buck", [900.0, 0.35, 60.0]),
+                    ("e612", [800.0, 0.36, 50.0, 20.0, 10.0])]
+    b = [(4 * k, 4 * k + 1, 1 + (k % 5)) for k in range(0, n // 4, 3)] + [(2, 4 * 5 * 5 * 4 + 2, 1)]
+    s.bonds = np.array(b, dtype=np.int32)
+    if angles:
+        s.angle_types = [(6.0, -0.3), (2.5, 0.45)]
+        a = [(4 * k, 4 * k + 1, 4 * k + 2, 1 + (k % 2)) for k in range(1, n // 4, 4)] + [(1, 3, 4 * 5 * 4 + 1, 2)]
+        s.angles = np.array(a, dtype=np.int32)
+    return s
+
+
+def case_bonds_and_angles(lib):
+    """constant bonds (all five potentials) and valence angles on top of the LJ pair forces, followed through
+    the sort of every step: forces 1e-5, engBond / engAngle 5e-6, on the warp sweep, the tile sweep, the list rebuilt
+    every step, and the list reused between rebuilds (where the integrator may not ride on the pair pass)."""
+    for kw in ({}, {"pair_variant": 1}, {"pair_variant": 2}):
+        o, e = run_parity(lib, bonded_lj_system(), nsteps=4, **kw)
+        st = e.stats()
+        assert abs(st.engBond_d) > 1e-2 and abs(st.engAngle_d) > 1e-3 and abs(st.engTot - (st.engKin + st.engVdW + st.engBond + st.engAngle)) < 1e-3
+        e.close()
+    o, e = run_parity(lib, bonded_lj_system(angles=False, cell_size=2.5 * azt.AR_SIGMA + 0.6), nsteps=6, rebuild_every=3, skin=0.6)
+    e.close()
+    # degrees of freedom: every bond removes one (src/sys_init.cpp:1099-1102)
+    s = bonded_lj_system()
+    assert s.deg_free == 3 * len(s.pos) - len(s.bonds)
+
+
+def case_bonds_match_the_reference_serial_build(lib):
+    """The engine on the reference-generated decks with bonds / bonds + angles (tests/golden/ref_serial_lj5_bonds*.npz: forces and
+    bonded energies of the reference's own serial build, exec_bondlist / exec_anglelist): first force evaluation from the
+    fixture's positions, 1e-5 of the per-atom term scale, energies 5e-6."""
+    import ast
+    import os
+    names = {v: k for k, v in abi.BOND_BY_NAME.items()}
+    for fx in ("ref_serial_lj5_bonds.npz", "ref_serial_lj5_bonds_angles.npz"):
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fx))
+        meta = ast.literal_eval(str(z["meta"]))
+        s = System(pos=z["pos"], types=z["types"].astype(np.int32), box=tuple(meta["box"]), species=[Species("Ar", azt.AR_MASS)],
+                   timestep=0.001, cell_size=meta["rc"], temperature=86.6)
+        s.set_vdw(0, 0, "lnjs", meta["rc"], [azt.AR_EPS, azt.AR_SIGMA])
+        s.bond_types = [(names[kind], list(p)) for kind, p in meta["bond_types"]]
+        s.bonds = np.array(meta["bonds"], dtype=np.int32)
+        if "angles" in meta:
+            s.angle_types = [tuple(t) for t in meta["angle_types"]]
+            s.angles = np.array(meta["angles"], dtype=np.int32)
+        o, e = run_parity(lib, s, nsteps=1)  # zero velocities and zero initial forces: step 0 evaluates the fixture's positions
+        d = azt.sort_by_id(e.dump())
+        scale = np.zeros(o.n, dtype=np.float32); scale[o.dump()["ids"]] = o.force_scale()
+        err = np.abs(d["frc"].astype(np.float64) - z["frc"]).max(1)
+        assert (err <= 1e-5 * np.maximum(scale, 1e-12)).all(), float((err / np.maximum(scale, 1e-12)).max())
+        st = e.stats()
+        assert abs(st.engBond_d - float(z["engBond"])) <= 5e-6 * abs(float(z["engBond"]))
+        if "angles" in meta:
+            assert abs(st.engAngle_d - float(z["engAngle"])) <= 5e-6 * abs(float(z["engAngle"]))
+        e.close()
+
+
 def case_nose_hoover(lib):
     """'temperature T nose tau' (SURVEY 8f-2): the friction is advanced twice per step (before verlet_1stage and in
     apply_tstat, src/main.cu:291-299, src/cuTemp.cu:787-794); hot start well above the target so that it acts visibly."""
@@ -563,6 +650,9 @@ ALL_CASES = [
     ("determinism", case_determinism),
     ("rdf_from_cells", case_rdf_from_cells_equals_brute_force),
     ("nose_hoover", case_nose_hoover),
+    ("force_autocap", case_force_autocap_fires),
+    ("bonds_angles", case_bonds_and_angles),
+    ("bonds_reference_serial", case_bonds_match_the_reference_serial_build),
     ("reset_vels", case_reset_vels),
     ("tile_kernel_variant", case_tile_kernel_variant),
     ("list_every_step_variant", case_list_every_step_variant),

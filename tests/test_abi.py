@@ -33,10 +33,10 @@ def test_every_declared_function_is_bound_and_exported():
 
 
 def test_struct_layouts_match_the_c_compiler(tmp_path):
-    structs = ["az_species", "az_vdw_entry", "az_system_desc", "az_cuda_opts", "az_stats", "az_atoms_out", "az_dump", "az_engine_info_t"]
-    probes = {"az_system_desc": ["n_atoms", "xs", "types", "la", "species", "elec_kind", "photons", "seed", "timestep", "efield", "global_ids", "n_atoms_global"],
+    structs = ["az_species", "az_vdw_entry", "az_bond_type", "az_angle_type", "az_system_desc", "az_cuda_opts", "az_stats", "az_atoms_out", "az_dump", "az_engine_info_t"]
+    probes = {"az_system_desc": ["n_atoms", "xs", "types", "la", "species", "elec_kind", "photons", "seed", "timestep", "efield", "global_ids", "n_atoms_global", "ewald_k", "n_bonds", "bond_types", "bond_type", "n_angles", "angle_types", "angle_type"],
               "az_cuda_opts": ["rebuild_every", "skin", "rank", "pgrid", "nccl_id", "max_neigh"],
-              "az_stats": ["engTot", "posMom", "pressure", "specAcBoxPos", "engKin_d", "n_pairs"],
+              "az_stats": ["engTot", "posMom", "pressure", "specAcBoxPos", "engKin_d", "n_pairs", "engCoul2_d", "engBond", "engAngle_d"],
               "az_engine_info_t": ["cnum", "csize", "pair_blocks", "device_bytes", "list_rows", "capacity"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aztot_b200.h"', 'int main(void) {']
     for s in structs:

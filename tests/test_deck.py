@@ -241,12 +241,56 @@ def test_deck_drives_the_kernels_like_the_python_system(lib, tmp_path):
     lib.az_deck_free(h)
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/case study 1"), reason="reference tree not present")
-@pytest.mark.parametrize("case,n,cells", [("case study 1", 40000, 13), ("case study 2", 4000, 12)])
+DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decks")
+
+
+@pytest.mark.parametrize("case,n,cells", [("cs1", 40000, 13), ("cs2", 4000, 12)])
 def test_shipped_case_studies_parse(lib, case, n, cells):
-    rc, h = load(lib, "/root/reference/" + case, seed=1)
+    """tests/golden/decks/cs1, cs2: the reference's two shipped decks (input fixtures, byte copies)."""
+    rc, h = load(lib, os.path.join(DECKS, case), seed=1)
     assert rc == 0, lib.az_deck_error(h)
     d = lib.az_deck_desc(h).contents
     assert d.n_atoms == n and d.tstat_kind == abi.TSTAT_RADI
     assert int(math.floor(np.float32(d.la) / np.float32(d.cell_size))) == cells
+    lib.az_deck_free(h)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/case study 1"), reason="reference tree not present")
+@pytest.mark.parametrize("case,ref", [("cs1", "case study 1"), ("cs2", "case study 2")])
+def test_committed_decks_are_the_shipped_files(case, ref):
+    for f in ("atoms.xyz", "control.txt", "field.txt", "cuda.txt"):
+        assert open(os.path.join(DECKS, case, f), "rb").read() == open(os.path.join("/root/reference", ref, f), "rb").read(), f
+
+
+def test_oracle_reproduces_the_reference_serial_build_on_case_study_1(lib, tmp_path):
+    """Pins oracle/az_oracle.c on the shipped 40 000-atom deck: same velocities as the reference's serial build drew
+    (tests/golden/deck_cs1_ref_serial.npz), 20 steps, its kinetic energy, the one pair that comes inside rc, positions."""
+    import shutil
+    g = np.load(os.path.join(os.path.dirname(DECKS), "deck_cs1_ref_serial.npz"))
+    d = os.path.join(str(tmp_path), "cs1")
+    shutil.copytree(os.path.join(DECKS, "cs1"), d)
+    ctl = open(os.path.join(d, "control.txt"), encoding="latin-1").read().replace("temperature 298.0\tradi\t0.2", "temperature 298.0\tnone")
+    open(os.path.join(d, "control.txt"), "w", encoding="latin-1").write(ctl)
+    rc, h = load(lib, d, seed=1)
+    assert rc == 0
+    desc = lib.az_deck_desc(h).contents
+    n, L = desc.n_atoms, float(desc.la)
+    pos = np.stack([np.ctypeslib.as_array(p, shape=(n,)) for p in (desc.xs, desc.ys, desc.zs)], 1).copy()
+    pos0 = (pos + g["shift"]) % L
+    keep = [np.ascontiguousarray(pos0[:, a]) for a in range(3)] + [np.ascontiguousarray(g["vel0"][:, a]) for a in range(3)]
+    ptr = [a.ctypes.data_as(C.POINTER(C.c_double)) for a in keep]
+    desc.xs, desc.ys, desc.zs, desc.vxs, desc.vys, desc.vzs = ptr
+    o = azt.Oracle(desc)
+    o.step(0, int(g["nstep"]))
+    st = o.stats()
+    assert abs(st.engKin_d - float(g["engKin"])) <= 2e-6 * float(g["engKin"])
+    a = o.download(abi.ORDER_ORIGINAL)
+    dp = a["pos"][::16] - g["pos_sub"]
+    dp -= L * np.round(dp / L)
+    assert np.abs(dp).max() <= 1.3e-3   # 20 steps x half an ulp of an fp32 coordinate in [1024, 1141.5) A (ulp = 1.2e-4 A): the reference's CUDA build holds positions in fp32 too
+    dmp = o.dump()
+    f = np.zeros((n, 3)); f[dmp["ids"]] = dmp["frc"]
+    nz = np.nonzero(np.abs(f).max(1) > 0)[0]
+    assert np.array_equal(nz, g["frc_idx"])
+    assert np.abs(f[nz] - g["frc"]).max() <= 2e-3 * np.abs(g["frc"]).max()
     lib.az_deck_free(h)

@@ -79,3 +79,77 @@ def test_driver_reports_deck_errors_like_the_reference(tmp_path):
     open(ctl, "w").write(open(ctl).read().replace("timestep 0.001 ps\n", ""))
     r = run_driver(str(tmp_path))
     assert r.returncode != 0 and "ERROR[411]" in r.stdout
+
+
+def test_driver_bonds_angles_deck_and_nuclei_rdf(tmp_path):
+    """SURVEY 8f-4 + 8f-1 through the process surface: 'bonds' / 'bond_list' + bonds.txt and 'angles' / 'angle_list' + angles.txt
+    add the engBnd / engAngle columns of start_stat (src/cuStat.cu:311-314); 'rdf ... nucl' adds rdf_n.dat in copy_nrdf's
+    layout (src/cuStat.cu:696-777).  The deck is written like tests/golden/make_golden.py writes the decks the reference's
+    serial build ran, and the first row equals the engine driven through the ABI on the same deck."""
+    d = str(tmp_path)
+    info = decks.lj_argon_deck(d, 5, nstep=12, stat=4, init_vel="zero", rdf_freq=4, rdf_rmax=8.0, rdf_dr=0.1)
+    ctl = open(os.path.join(d, "control.txt")).read().splitlines()
+    ctl = [(l + "\tnucl") if l.startswith("rdf") else l for l in ctl]
+    open(os.path.join(d, "control.txt"), "w").write("\n".join(ctl) + "\n")
+    with open(os.path.join(d, "field.txt"), "a") as f:
+        f.write("bonds 2\n1\tAr\tAr\tharm\t5.0\t3.8\tcon\tcon\n2\tAr\tAr\tmors\t0.4\t1.5\t4.0\t0.4\tcon\tcon\nbond_list 1\n")
+        f.write("angles 2\n1\tAr\thcos\t6\t-0.3\n2\tAr\thcos\t2.5\t0.45\nangle_list 1\n")
+    n = info["n_atoms"]
+    blist = [(4 * k, 4 * k + 1, 1 + (k % 2)) for k in range(0, n // 4, 3)] + [(2, 4 * 5 * 5 * 4 + 2, 1)]
+    open(os.path.join(d, "bonds.txt"), "w").write("%d\n" % len(blist) + "".join("%d %d %d\n" % b for b in blist))
+    alist = [(4 * k, 4 * k + 1, 4 * k + 2, 1 + (k % 2)) for k in range(1, n // 4, 4)]
+    open(os.path.join(d, "angles.txt"), "w").write("%d\n" % len(alist) + "".join("%d %d %d %d\n" % a for a in alist))
+    r = run_driver(d, "--seed", "7")
+    assert r.returncode == 0, r.stdout + r.stderr
+    stat = read_table(os.path.join(d, "stat.dat"))
+    assert stat[0][7:9] == ["engBnd", "engAngle"] and stat[1][7:9] == ["engBnd, eV", "engAngle, eV"]
+    ebnd = [float(x[7]) for x in stat[2:]]
+    eang = [float(x[8]) for x in stat[2:]]
+    assert len(ebnd) == 3 and all(v > 0.01 for v in ebnd) and all(v > 0.001 for v in eang)
+    # rdf_n.dat: one nucleus ("Ar" names itself as its nucleus): the table equals rdf.dat column for column
+    rdf = read_table(os.path.join(d, "rdf.dat"))
+    nrdf = read_table(os.path.join(d, "rdf_n.dat"))
+    assert nrdf[0] == ["r", "Ar-Ar"] and nrdf[1:] == rdf[1:]
+    lib = abi.load_library()
+    h = C.c_void_p()
+    assert lib.az_deck_load(d.encode(), 7, C.byref(h)) == 0
+    desc = lib.az_deck_desc(h).contents
+    assert desc.n_bonds == len(blist) and desc.n_angles == len(alist) and desc.n_bond_types == 3
+    e = Engine(desc, lib=azt.emu_lib(), opts=lib.az_deck_opts(h).contents)
+    e.step(0, 1)
+    st = e.stats()
+    assert abs(st.engBond - ebnd[0]) <= 1e-5 * abs(ebnd[0]) and abs(st.engAngle - eang[0]) <= 1e-5 * abs(eang[0])
+    o = azt.Oracle(desc)
+    o.step(0, 1)
+    assert abs(o.stats().engBond_d - st.engBond_d) <= 5e-6 * abs(st.engBond_d)
+    e.close()
+    lib.az_deck_free(h)
+    # mutable bonds are reactive chemistry: refused, not ignored
+    with open(os.path.join(d, "field.txt")) as f:
+        txt = f.read().replace("3.8\tcon\tcon", "3.8\tcon\tmut\t4.5\t2")
+    open(os.path.join(d, "field.txt"), "w").write(txt)
+    r = run_driver(d)
+    assert r.returncode != 0 and "reactive" in r.stdout
+
+
+def test_nuclei_rdf_of_a_two_species_deck(tmp_path):
+    """Two species, each its own nucleus (second word of the 'spec' lines): rdf_n.dat carries the Na-Na, Na-Cl, Cl-Cl columns of the
+    nuclei, normalised by the per-nucleus atom counts (Field::nnumbers), and the deck surface reports the nucleus table."""
+    d = str(tmp_path)
+    decks.nacl_deck(d, 4, rc_vdw=7.0, r_real=7.0, alpha=0.35, elec="fenn", nstep=4, stat=2, cell_list=7.0)
+    ctl = open(os.path.join(d, "control.txt")).read().splitlines()
+    ctl = [("rdf\t7.0 0.1\t2\t1000000\tnucl") if l.startswith("rdf") else l for l in ctl]
+    open(os.path.join(d, "control.txt"), "w").write("\n".join(ctl) + "\n")
+    r = run_driver(d, "--seed", "5")
+    assert r.returncode == 0, r.stdout + r.stderr
+    nrdf = read_table(os.path.join(d, "rdf_n.dat"))
+    rdf = read_table(os.path.join(d, "rdf.dat"))
+    assert nrdf[0] == ["r", "Na-Na", "Na-Cl", "Cl-Cl"] and rdf[0] == nrdf[0]
+    assert nrdf[1:] == rdf[1:]  # every species is its own nucleus here
+    lib = abi.load_library()
+    h = C.c_void_p()
+    assert lib.az_deck_load(d.encode(), 5, C.byref(h)) == 0
+    nof = (C.c_int * 2)()
+    assert lib.az_deck_nuclei(h, nof) == 2 and list(nof) == [0, 1] and lib.az_deck_rdf_nuclei(h) == 1
+    assert lib.az_deck_nucleus_name(h, 1) == b"Cl" and lib.az_deck_nucleus_count(h, 0) == 256
+    lib.az_deck_free(h)

@@ -38,6 +38,13 @@ def system_from_fixture(path):
         s.set_vdw(0, 0, "buck", meta["rc_vdw"], [424.097, 0.317, 1.05])
         s.set_vdw(0, 1, "buck", meta["rc_vdw"], [1256.31, 0.317, 7.00])
         s.set_vdw(1, 1, "buck", meta["rc_vdw"], [3488.998, 0.317, 72.40])
+    if "bonds" in meta:  # the fixture's constant bonds / valence angles travel in the system description
+        names = {v: k for k, v in abi.BOND_BY_NAME.items()}
+        s.bond_types = [(names[kind], list(p)) for kind, p in meta["bond_types"]]
+        s.bonds = np.array(meta["bonds"], dtype=np.int32)
+        if "angles" in meta:
+            s.angle_types = [tuple(t) for t in meta["angle_types"]]
+            s.angles = np.array(meta["angles"], dtype=np.int32)
     return s, z
 
 
@@ -104,20 +111,18 @@ def test_oracle_matches_reference_serial_build(path):
     scale[o.dump()["ids"]] = o.force_scale()
     frc = d["frc"].astype(np.float64)
     meta = ast.literal_eval(str(z["meta"]))
-    if "bonds" in meta:  # SURVEY 8f-4 groundwork: constant bonds on top of the pair forces (apply_const_bonds / exec_bondlist)
-        fb, eb = bonded_forces(meta, z["pos"])
+    st = o.stats()
+    if "bonds" in meta:  # constant bonds on top of the pair forces (apply_const_bonds / exec_bondlist), inside the oracle's step
+        fb, eb = bonded_forces(meta, z["pos"])  # ... and the executor on its own
         assert np.abs(fb).max(1).astype(bool).sum() == len({a for b in meta["bonds"] for a in b[:2]})
-        frc = frc + fb
-        scale = scale + np.abs(fb).sum(1).astype(np.float32)
         assert eb == pytest.approx(float(z["engBond"]), rel=5e-6)
+        assert st.engBond_d == pytest.approx(float(z["engBond"]), rel=5e-6)
         if "angles" in meta:  # valence angles (apply_angles / exec_anglelist)
             fa, ea = angle_forces(meta, z["pos"])
-            frc = frc + fa
-            scale = scale + np.abs(fa).sum(1).astype(np.float32)
             assert abs(ea) > 1e-3 and ea == pytest.approx(float(z["engAngle"]), rel=5e-6)
+            assert st.engAngle_d == pytest.approx(float(z["engAngle"]), rel=5e-6)
     err = np.abs(frc - z["frc"]).max(1)
     assert (err <= 1e-5 * np.maximum(scale, 1e-12)).all(), float((err / np.maximum(scale, 1e-12)).max())
-    st = o.stats()
     assert st.engVdW_d == pytest.approx(float(z["engVdW"]), rel=2e-6)
     # the serial twin's direct/DSF real-space energy (Sim::engElec3)
     if float(z["engCoul"]) != 0.0:
