@@ -139,6 +139,8 @@ ENGINE_SYMBOLS = {
     "az_engine_debug_dump": (C.c_int, [C.c_void_p, C.POINTER(az_dump)]),
     "az_engine_upload": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
     "az_engine_upload_async": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "az_engine_upload_f32_async": (C.c_int, [C.c_void_p, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "az_engine_download_f32": (C.c_int, [C.c_void_p, _fp, _fp, _fp, _fp, _fp, _fp]),
     "az_engine_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "az_engine_timers": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     "az_engine_launch_count": (C.c_longlong, [C.c_void_p]),
@@ -151,6 +153,7 @@ ENGINE_SYMBOLS = {
     "az_comm_unique_id": (C.c_int, [C.c_void_p]),
     "az_engine_rdf_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "az_engine_rdf_sample": (C.c_int, [C.c_void_p]),
+    "az_default_uvects": (C.c_int, [_dp, _dp, _dp]),
     "az_engine_rdf_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int, _ip, _ip, _ip]),
 }
 DECK_SYMBOLS = {
@@ -168,6 +171,7 @@ DECK_SYMBOLS = {
     "az_deck_nucleus_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "az_deck_nucleus_count": (C.c_int, [C.c_void_p, C.c_int]),
     "az_deck_rdf_nuclei": (C.c_int, [C.c_void_p]),
+    "az_photon_energy": (C.c_int, [C.c_double, C.c_double, C.c_double, _dp]),
     "az_deck_free": (None, [C.c_void_p]),
 }
 

@@ -4,7 +4,16 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
-#include <nccl.h>
+// No <nccl.h>: the library is loaded with dlopen, and a CUDA-only box (no NCCL headers) must still build the engine for
+// single-GPU use.  The handful of NCCL types this file needs are declared here with the values of nccl.h (stable since
+// NCCL 2.0: ncclSuccess = 0, ncclChar = 0, ncclDouble = 8, ncclSum = 0, ncclMax = 2, a 128-byte unique id).
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclChar = 0, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclMax = 2 } ncclRedOp_t;
+}
 
 #include "az_comm.h"
 #include "../../include/aztot_b200.h"

@@ -17,7 +17,7 @@
 // reciprocal Ewald) are rejected with AZ_ERR_UNSUPPORTED instead of being silently
 // dropped.  Random draws (photon energies, Gaussian velocities) come from a seeded counter-based
 // generator, not from the time-seeded rand() of src/main.cu:242 -- extra keys: `seed N` in
-// control.txt; `rebuild N`, `skin X`, `device N`, `graph 0|1` in cuda.txt (the reference ignores unknown words).
+// control.txt; `rebuild N`, `skin X`, `device N`, `graph 0|1` in cuda.txt (the reference ignores unknown words; graph replay defaults to on below 100 000 atoms).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -118,6 +118,32 @@ static int spec_by_name(const az_deck* d, const char* name)
     for (size_t i = 0; i < d->species.size(); i++)
         if (strcmp(d->species[i].name, name) == 0) return (int)i;
     return -1;
+}
+
+// photon_engs (src/temperature.cpp:28-89) for ONE uniform draw x: the photon energy y in 0..1 eV with
+// (1 - x) exp(y / kT) = sum_{k<=4} (y / kT)^k / k!  (the CDF of P ~ e^4 exp(-e / kT)), by the reference's bisection: start at
+// y = 0.5, tolerance 1e-3 on the residual, at most 20 halvings, then the previous atom's value.  Returns 0 when the
+// reference would draw x again (no sign change on [0, 1]).  The reference feeds it rand01() of the time-seeded rand();
+// the deck loader feeds it a seeded counter-based stream.
+extern "C" int az_photon_energy(double x, double temperature, double prev, double* e_out)
+{
+    const double r24 = 1.0 / 24.0, r6 = 1.0 / 6.0; // src/temperature.cpp:18-19
+    const double theta = 1.0 / (kKB * temperature), eps = 1e-3;
+    auto prob4 = [&](double xx, double y) {
+        const double ty = theta * y, ty2 = ty * ty;
+        return (1 - xx) * exp(y * theta) - (r24 * ty2 * ty2 + r6 * ty2 * ty + 0.5 * ty * ty + ty + 1);
+    };
+    const double ra = prob4(x, 0.0), rb = prob4(x, 1.0);
+    if (ra * rb > 0) return 0;
+    double a = 0.0, b = 1.0, y = 0.5, r = prob4(x, y);
+    int k = 0;
+    while (r > eps || r < -eps) {
+        if (r * ra < 0) { b = y; y = 0.5 * (a + y); } else { a = y; y = 0.5 * (y + b); }
+        r = prob4(x, y);
+        if (++k >= 20) { y = prev; break; }
+    }
+    if (e_out) *e_out = (y == y) ? y : prev;
+    return 1;
 }
 
 extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
@@ -433,7 +459,12 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     { int v; float s; // extensions; 'nthread a/b' of the reference are accepted and ignored
         if (scan_first(f, " rebuild %d", &v)) d->opts.rebuild_every = v;
         if (scan_first(f, " skin %f", &s)) d->opts.skin = s;
-        if (scan_first(f, " graph %d", &v)) d->opts.use_graph = v; // replay the step loop between two 'stat' samples as one CUDA graph
+        // replay the step loop between two 'stat' samples as one CUDA graph.  Default: on for the latency-bound decks (fewer than
+        // 100 000 atoms: the case studies' steps are 6-7 kernels of a few microseconds each, so the gaps between launches are a
+        // fifth of the step), off for large systems where a step is milliseconds; 'graph 0|1' overrides.  Results are bitwise
+        // those of the plain launches (case_graph_replay).
+        if (scan_first(f, " graph %d", &v)) d->opts.use_graph = v;
+        else d->opts.use_graph = (n < 100000) ? 1 : 0;
         if (scan_first(f, " device %d", &v)) d->opts.device = v;
     }
     fclose(f); f = nullptr;
@@ -445,23 +476,11 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
     double tKin = 0.5 * temp * kKB * (double)degFree;               // :1106
     if (tstat_kind == AZ_TSTAT_RADI) { // photon_engs: inverse CDF of P ~ e^4 exp(-e/kT) on 0..1 eV by bisection
         d->photons.assign(n, 0.0);
-        const double theta = 1.0 / (kKB * temp), tol = 1e-3;
-        auto prob4 = [&](double x, double y) {
-            double ty = theta * y, ty2 = ty * ty;
-            return (1 - x) * exp(y * theta) - (ty2 * ty2 / 24.0 + ty2 * ty / 6.0 + 0.5 * ty * ty + ty + 1);
-        };
         for (int i = 0; i < n; i++) {
-            double a = 0.0, b = 1.0, x, ra, rb;
+            double y = 0.0;
             int guard = 0;
-            do { x = rng.rand01(); ra = prob4(x, 0.0); rb = prob4(x, 1.0); } while (ra * rb > 0 && ++guard < 1000);
-            double y = 0.5, r = prob4(x, y);
-            int k = 0;
-            while (r > tol || r < -tol) {
-                if (r * ra < 0) { b = y; y = 0.5 * (a + y); } else { a = y; y = 0.5 * (y + b); }
-                r = prob4(x, y);
-                if (++k >= 20) { y = i > 0 ? d->photons[i - 1] : y; break; }
-            }
-            d->photons[i] = (y == y) ? y : (i > 0 ? d->photons[i - 1] : 0.0);
+            while (!az_photon_energy(rng.rand01(), temp, i > 0 ? d->photons[i - 1] : 0.5, &y) && ++guard < 1000) {}
+            d->photons[i] = y;
         }
     }
     if (init_vel == 1) { // gauss_temp

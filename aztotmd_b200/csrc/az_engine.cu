@@ -46,9 +46,11 @@ static void host_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 
 // The 3072 preset photon directions of read_tstat (src/temperature.cpp:164-223): three axis
-// permutations x 32 azimuths x 16 polar angles, each followed by its opposite.
-static void default_uvects(float* uv)
+// permutations x 32 azimuths x 16 polar angles, each followed by its opposite; doubles, exactly the host arithmetic of
+// the reference (tests/test_oracle_pinning.py compares the table bit for bit with what read_tstat builds).
+extern "C" int az_default_uvects(double* ux, double* uy, double* uz)
 {
+    if (!ux || !uy || !uz) return AZ_ERR_INVALID;
     const double pi = 3.14159265359, twopi = 2.0 * pi; // src/const.h:11-12
     int k = 0;
     for (int perm = 0; perm < 3; perm++)
@@ -61,11 +63,19 @@ static void default_uvects(float* uv)
                 if (perm == 0) { c = st; b = sp * ct; a = cp * ct; }
                 else if (perm == 1) { b = st; c = sp * ct; a = cp * ct; }
                 else { a = st; b = sp * ct; c = cp * ct; }
-                uv[3 * k] = (float)a; uv[3 * k + 1] = (float)b; uv[3 * k + 2] = (float)c;
-                uv[3 * k + 3] = (float)-a; uv[3 * k + 4] = (float)-b; uv[3 * k + 5] = (float)-c;
+                ux[k] = a; uy[k] = b; uz[k] = c;
+                ux[k + 1] = -a; uy[k + 1] = -b; uz[k + 1] = -c;
                 k += 2;
             }
         }
+    return AZ_OK;
+}
+
+static void default_uvects(float* uv)
+{
+    std::vector<double> t(3 * AZ_N_UVECT);
+    az_default_uvects(t.data(), t.data() + AZ_N_UVECT, t.data() + 2 * AZ_N_UVECT);
+    for (int k = 0; k < AZ_N_UVECT; k++) { uv[3 * k] = (float)t[k]; uv[3 * k + 1] = (float)t[AZ_N_UVECT + k]; uv[3 * k + 2] = (float)t[2 * AZ_N_UVECT + k]; }
 }
 
 // split_cells, div_type 1 (src/cuCellList.cu:9-34 as called from src/cuInit.cu:979)
@@ -120,7 +130,7 @@ static int dd_reduce_stats(az_engine* e, az_stats* o, int* flags);
 static int dd_owned_count(az_engine* e, int* n);
 static const std::vector<int>* dd_keep(az_engine* e);
 static int dd_global_tscale(az_engine* e);
-static int stage_upload(az_engine* e, const double* const src[6], int len, double* dst[6], int* slot_out);
+static int stage_upload(az_engine* e, const void* const src[6], int len, size_t esize, void* dst[6], int* slot_out);
 static int dd_upload(az_engine* e, const double* const src[6], double* dst[6], int* slot);
 
 // ---------------------------------------------------------------------------------------- ABI
@@ -153,6 +163,11 @@ static int build_params(az_engine* e, const az_system_desc* d, const az_cuda_opt
     P.r2max = (float)d->r2_max;
     P.skin = (o && o->rebuild_every > 1) ? o->skin : 0.f;
     if (P.skin < 0.f) { AZ_SET_ERR(e, "negative skin"); return AZ_ERR_INVALID; }
+    if (o && o->rebuild_every > 1 && !(o->skin > 0.f)) { // a list reused for R steps with no margin is invalid after the first move
+        AZ_SET_ERR(e, "rebuild %d needs a positive 'skin' (cuda.txt): cells and neighbour lists are reused for %d steps, so every atom needs room to move skin/2",
+                   o->rebuild_every, o->rebuild_every);
+        return AZ_ERR_INVALID;
+    }
     float rc = sqrtf(P.r2max);
     P.r2list = P.skin > 0.f ? (rc + P.skin) * (rc + P.skin) : P.r2max;
     for (int a = 0; a < 3; a++) P.efield[a] = (float)d->efield[a];
@@ -547,7 +562,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
     cudaFree(e->rdf_hist); cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     cudaFree(e->whereId); cudaFree(e->bStart); cudaFree(e->aStart); cudaFree(e->bEnt); cudaFree(e->aEnt); cudaFree(e->bTypes); cudaFree(e->aTypes);
-    cudaFree(e->partBond); cudaFree(e->partAngle);
+    cudaFree(e->partBond); cudaFree(e->partAngle); cudaFree(e->dl_buf);
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     for (int k = 0; k < 2; k++) if (e->ev_step[k]) cudaEventDestroy(e->ev_step[k]);
     for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -558,26 +573,43 @@ extern "C" void az_engine_destroy(az_engine* e)
 }
 
 // ---------------------------------------------------------------------------------------- step
+// NVTX ranges around the sections of a step (tracing).  nvtx3 is header-only and resolves the injection
+// library at run time: without a profiler attached a range is a no-op.  AZ_NO_NVTX (and the emulator build) compile them out.
+#if !defined(AZ_EMU) && !defined(AZ_NO_NVTX) && __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+struct az_nvtx_range {
+    explicit az_nvtx_range(int k)
+    {
+        static const char* names[AZ_N_TIMERS] = { "az:integrate_a", "az:scan", "az:sort", "az:pair", "az:integrate_b", "az:halo", "az:pair_list", "az:ewald" };
+        nvtxRangePushA(k >= 0 && k < AZ_N_TIMERS ? names[k] : "az:section");
+    }
+    ~az_nvtx_range() { nvtxRangePop(); }
+};
+#else
+struct az_nvtx_range { explicit az_nvtx_range(int) {} };
+#endif
 namespace {
 // profile 1: synchronous per-section timing; profile 2: events are only recorded (no host sync
 // inside the step loop) and resolved by az_engine_timers after the stream has drained.
 struct Timer {
-    az_engine* e; int k; cudaEvent_t a = nullptr, b = nullptr;
-    Timer(az_engine* e_, int k_) : e(e_), k(k_)
+    az_engine* e; int k; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+    az_nvtx_range nvtx; // one NVTX range per section (nsys / ncu timelines)
+    // `on`: the stream the section's kernels run on (the halo refresh of a brick runs on its own stream)
+    Timer(az_engine* e_, int k_, cudaStream_t on = nullptr) : e(e_), k(k_), s(on ? on : e_->stream), nvtx(k_)
     {
-        if (e->profile == 1) cudaEventRecord(e->ev[2 * k], e->stream);
-        else if (e->profile == 2) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e->stream); }
+        if (e->profile == 1) cudaEventRecord(e->ev[2 * k], s);
+        else if (e->profile == 2) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
     }
     ~Timer()
     {
         if (e->profile == 1) {
-            cudaEventRecord(e->ev[2 * k + 1], e->stream);
+            cudaEventRecord(e->ev[2 * k + 1], s);
             cudaEventSynchronize(e->ev[2 * k + 1]);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]);
             e->t_ms[k] += ms;
         } else if (e->profile == 2) {
-            cudaEventRecord(b, e->stream);
+            cudaEventRecord(b, s);
             e->pending.push_back({ a, b, k });
         }
     }
@@ -989,16 +1021,35 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         }
     // first call of this shape: record the launches instead of running them, then run the recording
     const az_engine::GraphEnd before = graph_end_state(e);
+    const long long steps_before = e->steps_done;
+    const int last_before = e->last_step;
+    const bool evalid_before = e->energy_valid;
+    // nothing ran while the launches were being recorded: if the recording cannot be turned into a graph the host-side
+    // cycle (buffer roles, rebuild phase, step counters) goes back to where it stood and the steps run as plain launches
+    auto restore = [&]() {
+        e->cur = before.cur; e->since_rebuild = before.since_rebuild; e->binned = before.binned;
+        for (int k = 0; k < 2; k++) { e->pos[k] = before.pos[k]; e->vel[k] = before.vel[k]; }
+        e->pos_alt = before.pos_alt; e->vel_alt = before.vel_alt; e->clear_counts_bytes = before.clear_counts_bytes;
+        e->launches = before.launches;
+        for (int k = 0; k < AZ_N_TIMERS; k++) e->t_launch[k] = before.t_launch[k];
+        e->steps_done = steps_before; e->last_step = last_before; e->energy_valid = evalid_before;
+    };
     AZ_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
     int rc = run_steps(e, first_step, nsteps);
     cudaGraph_t graph = nullptr;
     cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (cerr != cudaSuccess) { AZ_SET_ERR(e, "cudaStreamEndCapture: %s", cudaGetErrorString(cerr)); return AZ_ERR_CUDA; }
     cudaGraphExec_t exec = nullptr;
-    cerr = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (cerr != cudaSuccess) { AZ_SET_ERR(e, "cudaGraphInstantiate: %s", cudaGetErrorString(cerr)); return AZ_ERR_CUDA; }
+    if (!rc && cerr == cudaSuccess) cerr = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc || cerr != cudaSuccess) {
+        cudaGetLastError(); // clear the capture error
+        restore();
+        if (rc) return rc;  // a launch-sequence error would repeat
+        rc = run_steps(e, first_step, nsteps);
+        if (rc) return rc;
+        AZ_CUDA(e, cudaGetLastError());
+        return AZ_OK;
+    }
     az_engine::GraphEntry ent;
     ent.key = key; ent.exec = (void*)exec; ent.end = graph_end_state(e);
     ent.end.launches -= before.launches; // deltas
@@ -1143,7 +1194,7 @@ extern "C" int az_engine_debug_dump(az_engine* e, az_dump* o)
 // H2D staging shared by the single-GPU and the brick upload: the six arrays (each `len` doubles) are copied
 // on a copy stream into one of two staging buffers; the engine's stream waits for the copy.  With
 // async == false the call returns after the data has left the caller's arrays (borrowed for the call only).
-static int stage_upload(az_engine* e, const double* const src[6], int len, double* dst[6], int* slot_out)
+static int stage_upload(az_engine* e, const void* const src[6], int len, size_t esize, void* dst[6], int* slot_out)
 {
     if (!e->copy_stream) {
         AZ_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -1157,9 +1208,9 @@ static int stage_upload(az_engine* e, const double* const src[6], int len, doubl
     const int b = e->up_slot;
     e->up_slot ^= 1;
     AZ_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->ev_unpacked[b], 0)); // the kernel that last read this buffer is done
-    for (int k = 0; k < 6; k++) {
-        dst[k] = src[k] ? e->stage2[b] + (size_t)k * len : nullptr;
-        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], sizeof(double) * len, cudaMemcpyHostToDevice, e->copy_stream));
+    for (int k = 0; k < 6; k++) { // the staging buffers are sized for doubles; floats use the front of each slice
+        dst[k] = src[k] ? (void*)((char*)e->stage2[b] + (size_t)k * len * sizeof(double)) : nullptr;
+        if (src[k]) AZ_CUDA(e, cudaMemcpyAsync(dst[k], src[k], esize * len, cudaMemcpyHostToDevice, e->copy_stream));
     }
     AZ_CUDA(e, cudaEventRecord(e->ev_copied[b], e->copy_stream));
     AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_copied[b], 0));
@@ -1167,23 +1218,24 @@ static int stage_upload(az_engine* e, const double* const src[6], int len, doubl
     return AZ_OK;
 }
 
-static int upload_impl(az_engine* e, const double* xs, const double* ys, const double* zs,
-                       const double* vxs, const double* vys, const double* vzs, bool async)
+template <class T>
+static int upload_impl(az_engine* e, const T* xs, const T* ys, const T* zs, const T* vxs, const T* vys, const T* vzs, bool async)
 {
     if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
     AZ_CUDA(e, cudaSetDevice(e->device));
-    const double* src[6] = { xs, ys, zs, vxs, vys, vzs };
-    double* dst[6];
+    const void* src[6] = { xs, ys, zs, vxs, vys, vzs };
+    void* dst[6];
     int b = 0;
     if (e->dd) {
-        int rc = dd_upload(e, src, dst, &b);
+        if (sizeof(T) != sizeof(double)) { AZ_SET_ERR(e, "az_engine_upload_f32_async is single-GPU only"); return AZ_ERR_UNSUPPORTED; }
+        int rc = dd_upload(e, (const double* const*)src, (double**)dst, &b);
         if (rc) return rc;
     } else {
         const int n = e->n, c = e->cur;
-        int rc = stage_upload(e, src, n, dst, &b);
+        int rc = stage_upload(e, src, n, sizeof(T), dst, &b);
         if (rc) return rc;
-        AZ_LAUNCH(az_k_upload, e->n_atom_blocks, AZ_TPB, 0, e->stream, n, e->id[c], dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
-                  e->pos[c], e->vel[c], e->frc);
+        AZ_LAUNCH(az_k_upload<T>, e->n_atom_blocks, AZ_TPB, 0, e->stream, n, e->id[c], (const T*)dst[0], (const T*)dst[1], (const T*)dst[2], (const T*)dst[3],
+                  (const T*)dst[4], (const T*)dst[5], e->pos[c], e->vel[c], e->frc);
         e->launches++;
     }
     AZ_CUDA(e, cudaEventRecord(e->ev_unpacked[b], e->stream));
@@ -1205,6 +1257,34 @@ extern "C" int az_engine_upload_async(az_engine* e, const double* xs, const doub
                                       const double* vxs, const double* vys, const double* vzs)
 {
     return upload_impl(e, xs, ys, zs, vxs, vys, vzs, true);
+}
+
+// float inputs: half the PCIe traffic of the reference's double arrays (the engine computes in fp32 anyway: src/cuInit.cu:775-779
+// narrows every coordinate on upload)
+extern "C" int az_engine_upload_f32_async(az_engine* e, const float* xs, const float* ys, const float* zs,
+                                          const float* vxs, const float* vys, const float* vzs)
+{
+    return upload_impl(e, xs, ys, zs, vxs, vys, vzs, true);
+}
+
+// positions (and velocities) of all atoms back to the host in atoms.xyz order, float, one device-side gather + one D2H copy per
+// array; the host arrays should be pinned (az_host_alloc).  Synchronous at return.  Single GPU.
+extern "C" int az_engine_download_f32(az_engine* e, float* xs, float* ys, float* zs, float* vxs, float* vys, float* vzs)
+{
+    if (!e || !xs || !ys || !zs) return AZ_ERR_INVALID;
+    if (e->dd) { AZ_SET_ERR(e, "az_engine_download_f32 is single-GPU only (a brick hands its atoms back through az_engine_download)"); return AZ_ERR_UNSUPPORTED; }
+    AZ_CUDA(e, cudaSetDevice(e->device));
+    const int n = e->n, c = e->cur;
+    const int with_vel = (vxs && vys && vzs) ? 1 : 0;
+    if (!e->dl_buf) AZ_ALLOC(e, e->dl_buf, (size_t)6 * n);
+    AZ_LAUNCH(az_k_download_f32, e->n_atom_blocks, AZ_TPB, 0, e->stream, e->P, n, e->rebuild_every > 1 ? 1 : 0, e->id[c], e->pos[c], e->vel[c], e->dl_buf, with_vel);
+    e->launches++;
+    float* host[6] = { xs, ys, zs, vxs, vys, vzs };
+    for (int k = 0; k < (with_vel ? 6 : 3); k++)
+        AZ_CUDA(e, cudaMemcpyAsync(host[k], e->dl_buf + (size_t)k * n, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaGetLastError());
+    return AZ_OK;
 }
 
 extern "C" int az_engine_step_timed(az_engine* e, int first_step, int nsteps, float* ms)

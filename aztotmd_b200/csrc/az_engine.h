@@ -80,6 +80,7 @@ struct az_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {}, ev_unpacked[2] = {};
     int up_slot = 0;
+    float* dl_buf = nullptr; // az_engine_download_f32: 6 * n floats in atoms.xyz order
     AzScalars* sc = nullptr;
     AzVdw* table = nullptr;
     float *photons = nullptr, *uv = nullptr;

@@ -322,7 +322,7 @@ static int dd_upload(az_engine* e, const double* const src[6], double* dst[6], i
     AzDDHost* h = e->dd;
     if (e->use_therm) { AZ_SET_ERR(e, "az_engine_upload on bricks does not carry the thermostat state"); return AZ_ERR_UNSUPPORTED; }
     const int nc = h->n_create, n = (int)h->keep.size(), c = e->cur;
-    int rc = stage_upload(e, src, nc, dst, slot);
+    int rc = stage_upload(e, (const void* const*)src, nc, sizeof(double), (void**)dst, slot);
     if (rc) return rc;
     AZ_LAUNCH(az_k_upload_dd, (n + AZ_TPB - 1) / AZ_TPB, AZ_TPB, 0, e->stream, n, h->keepSrc, h->keepGid, h->keepType, dst[0], dst[1], dst[2], dst[3], dst[4], dst[5],
               e->pos[c], e->vel[c], e->id[c], e->frc);
@@ -488,7 +488,7 @@ static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream)
     if (on_halo_stream) AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0)); // recorded by dd_mark_moved
     auto blocks = [](int n) { return (n + AZ_TPB - 1) / AZ_TPB; };
     float2* th = e->use_therm ? e->therm[c] : nullptr;
-    Timer t(e, AZ_TIMER_HALO);
+    Timer t(e, AZ_TIMER_HALO, st); // events on the stream the halo kernels run on
     AZ_LAUNCH(az_k_ghost_pack<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, D, h->sendList, e->pos[c], e->id[c], th, h->gSendPos, h->gSendAux);
     std::vector<AzP2P> ops;
     dd_add_ops(h, ops, h->gSendPos, D.gs, h->gRecvPos, D.gr, sizeof(float4));

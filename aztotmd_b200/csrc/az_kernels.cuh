@@ -748,10 +748,11 @@ az_k_gather_by_id(int n, const int* __restrict__ id, const float4* __restrict__ 
 // az_engine_upload on the device: host SoA doubles (struct Atoms layout) staged in HBM are
 // narrowed to float exactly like src/cuInit.cu:775-777 and gathered into the slot that
 // currently holds each persistent id; forces are zeroed like a fresh init_cudaMD.
-static __global__ void __launch_bounds__(AZ_TPB)
-az_k_upload(int n, const int* __restrict__ id, const double* __restrict__ xs, const double* __restrict__ ys,
-            const double* __restrict__ zs, const double* __restrict__ vxs, const double* __restrict__ vys,
-            const double* __restrict__ vzs, float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ frc)
+template <class T>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_upload(int n, const int* __restrict__ id, const T* __restrict__ xs, const T* __restrict__ ys,
+            const T* __restrict__ zs, const T* __restrict__ vxs, const T* __restrict__ vys,
+            const T* __restrict__ vzs, float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ frc)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -761,6 +762,29 @@ az_k_upload(int n, const int* __restrict__ id, const double* __restrict__ xs, co
     pos[i] = p;
     vel[i] = make_float4(vxs ? (float)vxs[k] : 0.f, vys ? (float)vys[k] : 0.f, vzs ? (float)vzs[k] : 0.f, 0.f);
     frc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// az_engine_download_f32: positions (wrapped like put_periodic) and velocities back in atoms.xyz order, as float SoA
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_download_f32(const __grid_constant__ AzParams P, int n, int wrap, const int* __restrict__ id, const float4* __restrict__ pos,
+                  const float4* __restrict__ vel, float* __restrict__ out /* 6 arrays of n */, int with_vel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = id[i];
+    float4 p = pos[i];
+    if (wrap) {
+        float* c[3] = { &p.x, &p.y, &p.z };
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int nx = (int)floor((double)*c[a] * (double)P.revL[a]);
+            float x = *c[a] - (float)nx * P.L[a];
+            if (x >= P.L[a]) x = 0.f;
+            *c[a] = x;
+        }
+    }
+    out[k] = p.x; out[(size_t)n + k] = p.y; out[2 * (size_t)n + k] = p.z;
+    if (with_vel) { const float4 v = vel[i]; out[3 * (size_t)n + k] = v.x; out[4 * (size_t)n + k] = v.y; out[5 * (size_t)n + k] = v.z; }
 }
 
 // FP32 FMA throughput probe: 8 independent FMA chains per thread, no memory traffic.

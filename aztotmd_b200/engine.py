@@ -423,6 +423,25 @@ class Engine:
             self._pending_upload = (cols, vcols)  # the arrays must outlive the copy
         self._check(fn(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
 
+    def upload_f32(self, pos: np.ndarray, vel: Optional[np.ndarray] = None):
+        """az_engine_upload_f32_async: float arrays, half the host->device bytes; asynchronous (the arrays are kept alive)."""
+        cols = [np.ascontiguousarray(pos[:, a], dtype=np.float32) for a in range(3)]
+        vcols = [np.ascontiguousarray(vel[:, a], dtype=np.float32) for a in range(3)] if vel is not None else [None] * 3
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+        self._pending_upload = (cols, vcols)
+        self._check(self.lib.az_engine_upload_f32_async(self._h, *[ptr(a) for a in cols], *[ptr(a) for a in vcols]))
+
+    def download_f32(self, with_vel: bool = True) -> dict:
+        """az_engine_download_f32: positions (wrapped) and velocities in atoms.xyz order as float32."""
+        n = self.n
+        a = [np.zeros(n, dtype=np.float32) for _ in range(6 if with_vel else 3)]
+        ptr = [x.ctypes.data_as(C.POINTER(C.c_float)) for x in a] + [None] * (0 if with_vel else 3)
+        self._check(self.lib.az_engine_download_f32(self._h, *ptr))
+        out = dict(pos=np.stack(a[0:3], 1))
+        if with_vel:
+            out["vel"] = np.stack(a[3:6], 1)
+        return out
+
     def rdf_begin(self, r_max: float, dr: float):
         self._check(self.lib.az_engine_rdf_begin(self._h, float(r_max), float(dr)))
 

@@ -93,7 +93,43 @@ def bench_main(args, config):
     if getattr(args, "no_halo_overlap", False):
         e.set_option("halo_overlap", 0)
     K, W = args.steps, args.warmup
-    e.step(0, W)
+    # ---- halo_check: the bricks against ONE engine holding the same global lattice.  Two steps from the common start: step 0
+    # bins, migrates and selects ghosts, step 1 runs on refreshed ghost positions (the per-step halo path); energies and the
+    # pair count of step 1 must agree with the single-GPU run.
+    HC_STEPS = 2
+    e.set_option("energy_every_step", 1)
+    e.step(0, HC_STEPS)
+    st_b = e.stats()
+    e.set_option("energy_every_step", 0)
+    halo_check = None
+    if rank == 0 and not getattr(args, "no_halo_check", False):
+        try:
+            parts = [s] + [brick_system(ncell, pgrid, r, args.rebuild, args.skin) for r in range(1, world)]
+            order = np.argsort(np.concatenate([p.global_ids for p in parts]), kind="stable")
+            g = parts[0]
+            from .engine import System
+            whole = System(pos=np.concatenate([p.pos for p in parts])[order], types=np.zeros(n_global, dtype=np.int32), box=g.box, species=g.species,
+                           timestep=g.timestep, cell_size=g.cell_size, temperature=g.temperature, seed=g.seed)
+            whole.vdw = g.vdw
+            whole.vel = np.concatenate([p.vel for p in parts])[order]
+            del parts
+            one = Engine(whole, device=local, rebuild_every=args.rebuild, skin=args.skin if args.rebuild > 1 else 0.0)
+            one.set_option("energy_every_step", 1)
+            one.step(0, HC_STEPS)
+            st_1 = one.stats()
+            one.close()
+            del whole
+            rel = lambda a, b: abs(a - b) / max(abs(a), abs(b), 1e-30)  # noqa: E731
+            d_v, d_k = rel(st_b.engVdW_d, st_1.engVdW_d), rel(st_b.engKin_d, st_1.engKin_d)
+            pairs_ok = st_b.n_pairs == st_1.n_pairs  # unique in-range pairs: the all-reduced visits of the bricks / 2
+            ok = d_v <= 2e-6 and d_k <= 2e-6 and pairs_ok
+            halo_check = {"status": "ok" if ok else "MISMATCH", "steps": HC_STEPS, "engVdW_rel": d_v, "engKin_rel": d_k, "tolerance": 2e-6,
+                          "pairs_bricks": int(st_b.n_pairs), "pairs_single_gpu": int(st_1.n_pairs),
+                          "what": "%d bricks vs one engine holding the same %d-atom lattice on GPU 0" % (world, n_global)}
+        except Exception as ex:  # noqa: BLE001 -- the check must not take the benchmark line down
+            halo_check = {"status": "error", "why": repr(ex)[:300]}
+    dist.barrier()
+    e.step(HC_STEPS, W)
     st = e.stats()  # collective; surfaces overflow flags early
     launches0 = e.launch_count
     clocks = bench.ClockSampler(device=local) if rank == 0 else None
@@ -102,7 +138,7 @@ def bench_main(args, config):
     e.profile(2)
     dist.barrier()
     e.sync()
-    ms = e.step_timed(W, K)  # CUDA events on the engine's stream, this rank
+    ms = e.step_timed(HC_STEPS + W, K)  # CUDA events on the engine's stream, this rank
     e.sync()
     dist.barrier()
     tm = e.timers()
@@ -125,7 +161,7 @@ def bench_main(args, config):
     dp = C.POINTER(C.c_double)
     ptr = [C.cast(hp + 8 * n * k, dp) for k in range(6)]
     ne = max(1, args.e2e_steps)
-    first = W + K
+    first = HC_STEPS + W + K
     up = lib.az_engine_upload_async
     for _ in range(2):
         assert up(e._h, *ptr) == 0, lib.az_last_error(e._h)
@@ -176,6 +212,8 @@ def bench_main(args, config):
                             "share_of_step": tm[dom]["ms"] / ms},
                "kernel_ms_per_step": {k: v["ms"] / K for k, v in tm.items()},
                "energy": {"engKin": st.engKin_d, "engVdW": st.engVdW_d, "pairs_in_cutoff": st.n_pairs},
+               "halo_check": halo_check["status"] if halo_check else "skipped", "halo_check_detail": halo_check,
+               "ns_per_day": 86400.0 / (ms_max / K * 1e-3) * 1e-6,
                "hbm_peak": {"value": hbm_peak, "source": hbm_src}}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

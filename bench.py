@@ -156,16 +156,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_entry(kernel, args):
+    """The committed `ncu --set full` capture of the dominant kernel on the same workload (profiles/r2/ncu_traffic.json, else
+    profiles/r1/): dram__bytes_read.sum + dram__bytes_write.sum per launch and the pipe that limits it; None if not captured."""
+    for rnd in ("r2", "r1"):
+        p = os.path.join(ROOT, "profiles", rnd, "ncu_traffic.json")
+        if not os.path.exists(p):
+            continue
+        with open(p) as f:
+            d = json.load(f)
+        key = "%s/rebuild%d/skin%.2f" % (args.workload, args.rebuild, args.skin if args.rebuild > 1 else 0.0)
+        ent = d.get(key, {}).get(kernel)
+        if ent:
+            return dict(ent, source="profiles/%s/ncu_traffic.json" % rnd)
+    return None
+
+
 def ncu_traffic(kernel, args):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of the same workload (profiles/r1/ncu_traffic.json); null for workloads that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        d = json.load(f)
-    key = "%s/rebuild%d/skin%.2f" % (args.workload, args.rebuild, args.skin if args.rebuild > 1 else 0.0)
-    ent = d.get(key, {}).get(kernel)
+    ent = ncu_entry(kernel, args)
     return ent["dram_bytes_per_launch"] if ent else None
 
 
@@ -176,6 +184,54 @@ def load_peaks():
             d = json.load(f)
         return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def small_deck_line(lib, name="cs1", steps=2000, warmup=200):
+    """The other half of BASELINE.json's metric ("LJ Argon at 40k and 4M atoms"): the reference's SHIPPED case study 1
+    (tests/golden/decks/cs1: 40 000 argon atoms, dilute gas, LJ rc 4 A, radiative thermostat, cell_list 85) on its own
+    schedule (bin + sort every step), as plain launches and as a CUDA-graph replay.  Latency-bound: one wave of CTAs."""
+    from aztotmd_b200 import abi
+    from aztotmd_b200.engine import Engine
+    d = os.path.join(ROOT, "tests", "golden", "decks", name)
+    if not os.path.isdir(d):
+        return {"unavailable": "tests/golden/decks/%s missing" % name}
+    h = C.c_void_p()
+    if lib.az_deck_load(d.encode(), 12345, C.byref(h)) != 0:
+        return {"unavailable": "deck does not parse"}
+    desc = lib.az_deck_desc(h).contents
+    out = {"workload": "shipped case study 1 (tests/golden/decks/cs1): 40,000 Ar, LJ rc 4 A, radiative thermostat 298 K, rebuild every step",
+           "n_atoms": int(desc.n_atoms), "steps": steps}
+    for tag, graph in (("plain", 0), ("graph", 1)):
+        opts = abi.az_cuda_opts.from_buffer_copy(bytes(lib.az_deck_opts(h).contents))
+        opts.use_graph = graph
+        e = Engine(desc, lib=lib, opts=opts)
+        e.step(0, warmup)
+        e.stats()
+        first = warmup
+        ms = e.step_timed(first, steps); first += steps
+        if graph:  # the first call of a shape records the graph; time a replay
+            ms = min(e.step_timed(first + k * steps, steps) for k in range(2))
+        out[tag] = {"us_per_step": ms / steps * 1e3, "atom_steps_per_s": desc.n_atoms * steps / (ms * 1e-3)}
+        e.close()
+    lib.az_deck_free(h)
+    return out
+
+
+def ref_cuda_baseline():
+    """north_star's first target is a ratio to the reference's own CUDA build.  That build (oracle/_ref/aztotmd_ref, the
+    reference sources compiled for sm_100a) was run on a B200 by profiles/ref_cuda_probe.py; the committed record
+    says what it did there -- see profiles/r2/reference_cuda.json and DESIGN.md section 6."""
+    p = os.path.join(ROOT, "profiles", "r2", "reference_cuda.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        j = json.load(f)
+    t = j.get("timing", {})
+    a = t.get("reference_cuda", {})
+    return {"value": a.get("atom_steps_per_s"), "unit": "atom-steps/s", "n_atoms": t.get("n_atoms"),
+            "stat_dat_valid": bool(a.get("stat", {}).get("valid")), "loop_completed": a.get("loop_completed"),
+            "new_engine_same_deck": t.get("new_engine", {}).get("atom_steps_per_s"),
+            "source": "profiles/r2/reference_cuda.json (gpurun job on a B200 of this pool, not this run)", "note": j.get("note")}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -235,6 +291,8 @@ def main():
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-halo-check", action="store_true", help="multi-GPU: skip the comparison with a single-GPU run of the same lattice")
+    ap.add_argument("--no-small-deck", action="store_true", help="skip the 40 000-atom case-study-1 leg of the default run")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -252,10 +310,14 @@ def main():
         if rank != 0:
             return
         r = run_reference_sample(args.steps, args.warmup)
+        # the serial twin's start-up is O(N^2) (all_pairs, src/sys_init.cpp:1184): it is timed on a bounded cut of the workload
+        # (same lattice, density, potential, cut-off) and the line says so -- n_atoms is the cut's, not the 4 M of the GPU arm
+        config = dict(config, n_atoms=int(r["n_atoms"]), n_atoms_gpu_arm=n_atoms,
+                      workload=config["workload"] + "; CPU arm: %d-atom cut of this lattice" % r["n_atoms"])
         print(json.dumps({"impl": "reference", "metric": "atom-steps/s", "value": r["value"], "unit": "atom-steps/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic", "config": config,
+                          "data": "synthetic", "config": config, "ns_per_day": 86400.0 / (r["ms_per_step"] * 1e-3) * 1e-6,
                           "cpu_baseline": {"value": r["value"], "unit": "atom-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                           "e2e": {"value": r["value"], "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -349,44 +411,76 @@ def main():
     if rides:
         flops_per_launch += FLOP_PER_ATOM_INTEGRATE * n_atoms
     achieved_tf = flops_per_launch / (pair_ms * 1e-3) / 1e12
-    nreb = max(1, math.ceil(K / args.rebuild))
-    hbm_bytes_step = n_atoms * ((HBM_BYTES_PER_ATOM_STEP - 32.0) + HBM_BYTES_PER_ATOM_SORT * nreb / K)
-    achieved_gbs = hbm_bytes_step / (rest_ms * 1e-3) / 1e9 if rest_ms > 0 else 0.0
+    # HBM-bound remainder, graded on the bytes its kernels really move.  With the rider the integrate passes are gone (the
+    # list kernel reads / writes pos and vel itself) except az_k_integrate_a at the head and az_k_integrate_b at the tail of
+    # a call, so what is left per step is the reorder at a rebuild: az_k_sort_keys + az_k_sort_scatter, 72 B per atom
+    # ((16 + 16 + 4) B read and written).  Without the rider az_k_integrate_ba adds 80 B per atom and step.
+    n_sorts = tm["sort"]["launches"] // 2
+    sort_ms = tm["sort"]["ms"] / max(1, n_sorts)
+    sort_gbs = HBM_BYTES_PER_ATOM_SORT * n_atoms / (sort_ms * 1e-3) / 1e9 if n_sorts else 0.0
+    hbm_kernels = "az_k_sort_keys + az_k_sort_scatter (per rebuild)"
+    achieved_gbs, hbm_ms, hbm_bytes = sort_gbs, sort_ms, HBM_BYTES_PER_ATOM_SORT * n_atoms
+    if not rides and tm["integrate_b"]["launches"] > 0:  # the fused second-kick + first-kick pass of every step (incl. az_k_finalize)
+        ib_ms = tm["integrate_b"]["ms"] / K
+        hbm_kernels = "az_k_integrate_ba (+ az_k_finalize) per step"
+        achieved_gbs, hbm_ms, hbm_bytes = 80.0 * n_atoms / (ib_ms * 1e-3) / 1e9, ib_ms, 80.0 * n_atoms
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with HOST buffers (pinned): every step uploads this step's positions and velocities,
+    # advances one step and reads the step's result back.  Three variants of the same loop:
+    #   f64      the reference's own host layout (struct Atoms: six double arrays, 48 B per atom) in, az_stats out
+    #   f32      float arrays in (az_engine_upload_f32_async, 24 B per atom), az_stats out            <- the `e2e` headline
+    #   f32+pos  float arrays in, az_stats AND all positions out (az_engine_download_f32, 12 B per atom)
     n = n_atoms
-    hp = lib.az_host_alloc(6 * 8 * n)
-    assert hp, "pinned allocation failed"
-    host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(6, n))
     a = e.download()
-    host[0:3] = a["pos"].T
-    host[3:6] = a["vel"].T
-    dp = C.POINTER(C.c_double)
-    ptr = [C.cast(hp + 8 * n * k, dp) for k in range(6)]
+    dpt, fpt = C.POINTER(C.c_double), C.POINTER(C.c_float)
     ne = max(1, args.e2e_steps)
-    up = lib.az_engine_upload_async  # double-buffered staging: the H2D copy of step k+1 overlaps the kernels of step k
-    for _ in range(2):  # warm the path
-        assert up(e._h, *ptr) == 0
-        e.step(first, 1); e.stats(); first += 1
-    e.sync()
-    t0 = time.perf_counter()
-    assert up(e._h, *ptr) == 0
-    for k in range(ne):
-        e.step(first, 1)                  # waits (on the device) for the staged inputs of this step
-        if k + 1 < ne:
-            assert up(e._h, *ptr) == 0    # next step's inputs: pinned host memory -> staging buffer, copy stream
-        e.stats()                         # D2H read of this step's statistics (synchronises)
-        first += 1
-    t1 = time.perf_counter()
-    e2e_value = n * ne / (t1 - t0)
-    lib.az_host_free(hp)
+
+    def e2e_loop(kind):
+        nonlocal first
+        esz = 8 if kind == "f64" else 4
+        hp = lib.az_host_alloc(6 * esz * n)
+        assert hp, "pinned allocation failed"
+        ctype, ptype, up = (C.c_double, dpt, lib.az_engine_upload_async) if kind == "f64" else (C.c_float, fpt, lib.az_engine_upload_f32_async)
+        host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(ctype)), shape=(6, n))
+        host[0:3] = a["pos"].T
+        host[3:6] = a["vel"].T
+        ptr = [C.cast(hp + esz * n * k, ptype) for k in range(6)]
+        back = None
+        if kind == "f32+pos":
+            bp = lib.az_host_alloc(3 * 4 * n)
+            back = [C.cast(bp + 4 * n * k, fpt) for k in range(3)] + [None, None, None]
+        for _ in range(2):  # warm the path
+            assert up(e._h, *ptr) == 0
+            e.step(first, 1); e.stats(); first += 1
+        e.sync()
+        t0 = time.perf_counter()
+        assert up(e._h, *ptr) == 0            # pinned host memory -> staging buffer on the copy stream
+        for k in range(ne):
+            e.step(first, 1)                  # waits (on the device) for the staged inputs of this step
+            if k + 1 < ne:
+                assert up(e._h, *ptr) == 0    # next step's inputs: the copy overlaps the kernels of this step
+            if back:
+                assert lib.az_engine_download_f32(e._h, *back) == 0
+            e.stats()                         # D2H read of this step's statistics (synchronises)
+            first += 1
+        t1 = time.perf_counter()
+        lib.az_host_free(hp)
+        if back:
+            lib.az_host_free(bp)
+        return {"value": n * ne / (t1 - t0), "h2d_bytes_per_step": 6 * esz * n,
+                "d2h_bytes_per_step": C.sizeof(abi.az_stats) + (3 * 4 * n if back else 0)}
+
+    e2e_f64, e2e_f32, e2e_pos = e2e_loop("f64"), e2e_loop("f32"), e2e_loop("f32+pos")
+    e2e_value = e2e_f32["value"]
 
     out = {"metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": config, "clocks": clk,
-           "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": 6 * 8 * n,
-                   "d2h_bytes_per_step": C.sizeof(abi.az_stats), "steps": ne, "timer": "host wall clock",
-                   "pipeline": "az_engine_upload_async: H2D of step k+1 overlaps the kernels of step k; every step re-bins (uploaded positions invalidate the cell list)"},
+           "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": e2e_f32["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": e2e_f32["d2h_bytes_per_step"], "steps": ne, "timer": "host wall clock",
+                   "pipeline": "az_engine_upload_f32_async (float arrays, pinned): H2D of step k+1 overlaps the kernels of step k; every step re-bins and "
+                               "rebuilds the list (uploaded positions invalidate it); az_stats read back every step",
+                   "variants": {"f64_in_stats_out": e2e_f64, "f32_in_stats_out": e2e_f32, "f32_in_stats_and_positions_out": e2e_pos}},
            "gpu_launches": int(launches),
            "roofline": {"bound": "fp32", "kernel": dom_kernel, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                         "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(dom_kernel, args),
@@ -394,21 +488,29 @@ def main():
                         "algorithmic": "%.0f flop per unique in-cutoff pair x %d pairs per launch%s" % (
                             flop_per_pair, st.n_pairs, " + %.0f flop per atom of the integrator that rides on the kernel" % FLOP_PER_ATOM_INTEGRATE if rides else ""),
                         "avg_launch_ms": pair_ms, "launches": tm[dom]["launches"],
-                        "share_of_step": tm[dom]["ms"] / ms_prof, "all_pair_kernels_share_of_step": pair_total_ms / ms_prof},
-           "roofline_hbm": {"bound": "hbm", "kernels": "integrate_a + scan + sort + integrate_b", "achieved": achieved_gbs,
+                        "share_of_step": tm[dom]["ms"] / ms_prof, "all_pair_kernels_share_of_step": pair_total_ms / ms_prof,
+                        "limiter": (ncu_entry(dom_kernel, args) or {}).get("limiter")},
+           "roofline_hbm": {"bound": "hbm", "kernels": hbm_kernels, "achieved": achieved_gbs,
                             "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
-                            "avg_ms_per_step": rest_ms, "algorithmic_bytes_per_step": hbm_bytes_step},
+                            "avg_ms": hbm_ms, "algorithmic_bytes": hbm_bytes,
+                            "other_non_pair_ms_per_step": rest_ms},
            "kernel_ms_per_step": {k: v["ms"] / K for k, v in tm.items()},
+           "ns_per_day": 86400.0 / (ms / K * 1e-3) * (s.timestep * 1e3) * 1e-6,
            "section_events": {"where": "inside the timed region" if sections_inside else "separate pass of K steps after the timed region (the events add launch gaps on latency-bound decks)",
                               "ms_per_step": ms_prof / K},
            "energy": {"engKin": st.engKin_d, "engVdW": st.engVdW_d, "pairs_in_cutoff": st.n_pairs}}
     if graph:
         out["cuda_graph"] = graph
         out["config"]["cuda_graph"] = "az_engine_step replayed as one CUDA graph (value, ms_per_step)"
+    e.close()
+    if args.workload == "lj4m" and not args.no_small_deck:
+        out["cs1"] = small_deck_line(lib)
+    rc = ref_cuda_baseline()
+    if rc:
+        out["ref_cuda_baseline"] = rc
     if not args.no_cpu_baseline:
         r = run_reference_sample(steps=10, warmup=2, budget_s=15.0)
         out["cpu_baseline"] = {"value": r["value"], "unit": "atom-steps/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-    e.close()
     print(json.dumps(out))
 
 

@@ -307,6 +307,14 @@ int az_engine_upload(az_engine *e, const double *xs, const double *ys, const dou
  * next az_engine_sync / az_engine_stats / az_engine_download. */
 int az_engine_upload_async(az_engine *e, const double *xs, const double *ys, const double *zs,
                            const double *vxs, const double *vys, const double *vzs);
+/* The same from float arrays: half the host->device bytes (the engine narrows every coordinate to float on upload anyway,
+ * src/cuInit.cu:775-779).  Single GPU. */
+int az_engine_upload_f32_async(az_engine *e, const float *xs, const float *ys, const float *zs,
+                               const float *vxs, const float *vys, const float *vzs);
+/* Positions (wrapped into the box) and, if the last three pointers are set, velocities of all atoms in atoms.xyz order as
+ * float: one gather kernel and one D2H copy per array; pinned host arrays (az_host_alloc) make the copies run at PCIe
+ * speed.  Synchronous at return.  Single GPU. */
+int az_engine_download_f32(az_engine *e, float *xs, float *ys, float *zs, float *vxs, float *vys, float *vzs);
 
 /* Radial distribution function from the cell grid: replaces init_cuda_rdf / brute_rdf / rdf_iter / copy_rdf
  * (src/cuStat.cu:418-594; the reference's brute force is O(N^2) per sample).  az_engine_rdf_begin allocates and clears
@@ -391,6 +399,11 @@ int az_deck_nuclei(const az_deck *d, int *nucleus_of_species /* [n_species] or N
 const char *az_deck_nucleus_name(const az_deck *d, int nucleus);
 int az_deck_nucleus_count(const az_deck *d, int nucleus);   /* atoms carrying that nucleus (Field::nnumbers) */
 int az_deck_rdf_nuclei(const az_deck *d);
+/* Host-side thermostat tables of read_tstat (src/temperature.cpp:91-259), exposed so that they can be pinned on the reference:
+ * the 3 x 32 x 16 x 2 = AZ_N_UVECT preset unit vectors (:164-223; what the engine uses when az_system_desc.uvect_* are NULL),
+ * and photon_engs' inverse CDF for one uniform draw (:28-89; returns 0 when the reference would draw again). */
+int az_default_uvects(double *ux, double *uy, double *uz);
+int az_photon_energy(double x, double temperature, double prev, double *e_out);
 void az_deck_free(az_deck *d);
 
 #ifdef __cplusplus

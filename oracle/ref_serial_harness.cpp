@@ -89,6 +89,18 @@ int main(int argc, char** argv)
         if (field->nBonds) exec_bondlist(atoms, field, sim, box);
         if (field->nAngles) exec_anglelist(atoms, field, sim, box);
     }
+    // a32 pinning: argv[5] == "tstat" writes what read_tstat (src/temperature.cpp:91-259) built for `temperature T radi n` under
+    // srand(seed) -- the photon energies of photon_engs and the 3072 preset unit vectors -- to tstat.bin and stops
+    if (argc > 5 && strcmp(argv[5], "tstat") == 0) {
+        FILE* tf = fopen("tstat.bin", "wb");
+        int n = atoms->nAt, nv = 16 * 32 * 2 * 3;
+        fwrite(&n, sizeof(int), 1, tf); fwrite(&nv, sizeof(int), 1, tf);
+        fwrite(tstat->photons, sizeof(double), n, tf);
+        fwrite(tstat->uvectX, sizeof(double), nv, tf); fwrite(tstat->uvectY, sizeof(double), nv, tf); fwrite(tstat->uvectZ, sizeof(double), nv, tf);
+        fclose(tf);
+        printf("{\"tstat\": %d, \"temperature\": %.6f}\n", n, tstat->Temp);
+        return 0;
+    }
     double t1 = now();
     FILE* df = strcmp(dumpname, "-") ? fopen(dumpname, "wb") : NULL;
     if (df) dump(df, "init", atoms, sim);

@@ -92,8 +92,29 @@ def make_cs2():
     print("  ->", out)
 
 
+def make_tstat():
+    """a32: what the reference's read_tstat (src/temperature.cpp:91-259) builds for `temperature 298 radi 1` under srand(1):
+    the photon energies of photon_engs and the 3072 preset unit vectors -> tests/golden/ref_tstat_tables.npz"""
+    from aztotmd_b200 import decks
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "t")
+        decks.lj_argon_deck(d, 6, nstep=1, init_vel="zero", tstat="radi\t1", temperature=298.0)
+        r = subprocess.run([HARNESS, "0", "fast", "-", "1", "tstat"], cwd=d, stdin=subprocess.DEVNULL, capture_output=True, text=True, check=True)
+        raw = open(os.path.join(d, "tstat.bin"), "rb").read()
+    n, nv = np.frombuffer(raw[:8], dtype=np.int32)
+    a = np.frombuffer(raw[8:], dtype=np.float64)
+    photons, uv = a[:n], a[n:].reshape(3, nv)
+    assert nv == 3072 and len(a) == n + 3 * nv
+    out = os.path.join(HERE, "ref_tstat_tables.npz")
+    np.savez_compressed(out, photons=photons, uvect=uv, temperature=298.0, srand=1,
+                        source=np.array("oracle/_ref/ref_serial_harness 0 fast - 1 tstat (read_tstat of /root/reference/src/temperature.cpp)"))
+    print("tstat: %d photon energies (mean %.5f eV), %d unit vectors -> %s (%d bytes)" % (n, photons.mean(), nv, out, os.path.getsize(out)))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["cs1", "cs2"]
+    what = sys.argv[1:] or ["cs1", "cs2", "tstat"]
+    if "tstat" in what:
+        make_tstat()
     if "cs1" in what:
         make_cs1()
     if "cs2" in what:

@@ -337,6 +337,14 @@ def case_download_upload_roundtrip(lib):
     g.step(0, 1)
     d3 = azt.sort_by_id(g.dump())
     assert np.array_equal(d3["pos"], d2["pos"]) and np.array_equal(d3["frc"], d2["frc"])
+    # float entry points: az_engine_upload_f32_async narrows nothing the double path would not (bitwise the same step), and
+    # az_engine_download_f32 hands back what az_engine_download does, in atoms.xyz order
+    g.upload_f32(pos0, vel0)
+    g.step(0, 1)
+    d4 = azt.sort_by_id(g.dump())
+    assert np.array_equal(d4["pos"], d2["pos"]) and np.array_equal(d4["frc"], d2["frc"])
+    a64, a32 = g.download(abi.ORDER_ORIGINAL), g.download_f32()
+    assert np.array_equal(a32["pos"], a64["pos"].astype(np.float32)) and np.array_equal(a32["vel"], a64["vel"].astype(np.float32))
     e.close(); f.close(); g.close()
 
 

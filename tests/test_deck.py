@@ -161,7 +161,8 @@ def test_nose_hoover_and_reset_vels_directives(lib, tmp_path):
     (("control.txt", "elec\tfenn", "elec\tzzz"), abi.AZ_ERR_IO, b"ERROR[404]"),
     (("control.txt", "init_vel\tzero", "no_vel zero"), abi.AZ_ERR_IO, b"ERROR[406]"),
     (("control.txt", "cell_list\t2.7", ""), abi.AZ_ERR_IO, b"cell_list"),
-    (("field.txt", "red-ox 0", "bonds 2"), abi.AZ_ERR_UNSUPPORTED, b"bonds"),
+    (("field.txt", "red-ox 0", "bonds 1\n1 Ar Ar harm 5.0 3.8 con mut 4.5 2"), abi.AZ_ERR_UNSUPPORTED, b"reactive"),  # mutable bonds: reactive chemistry
+    (("field.txt", "red-ox 0", "linkage 2"), abi.AZ_ERR_UNSUPPORTED, b"linkage"),
     (("field.txt", "surk\t6.0\t75.0\t8.0\t1.0\t1.0", "quux\t6.0\t75.0\t8.0"), abi.AZ_ERR_IO, b"ERROR[006]"),
     (("atoms.xyz", "Ar\t10.000000\t10.000000\t10.000000", "Xe\t10.000000\t10.000000\t10.000000"), abi.AZ_ERR_IO, b"ERROR[009]"),
 ])
