@@ -28,6 +28,10 @@ struct AzComm {
     // ranks the k-th send matches the k-th receive.  Asynchronous on `st`.
     virtual int exchange(const std::vector<AzP2P>& ops, cudaStream_t st) = 0;
     virtual int allreduce(double* dev, int n, bool take_max, cudaStream_t st) = 0; // in place: sum or max
+    // Peer memory (NVLink / NVSwitch inside one box): every rank offers `nbuf` device buffers; on return
+    // remote[r * nbuf + b] is a pointer THIS rank's kernels can store through to reach buffer b of rank r (its own buffers
+    // for r == rank).  Collective.  AZ_ERR_UNSUPPORTED: the transport has no peer memory (the caller keeps send/recv).
+    virtual int share(void* const* local, int nbuf, std::vector<void*>* remote) { (void)local; (void)nbuf; (void)remote; return -4; }
 };
 
 // id: 128 bytes shared by all ranks (ncclUniqueId for the NCCL implementation).

@@ -29,6 +29,7 @@ struct NcclApi {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_api;
@@ -43,7 +44,7 @@ bool load_api(std::string* err)
 #define AZ_SYM(field, name) *(void**)(&g_api.field) = dlsym(h, name); if (!g_api.field) { if (err) *err = std::string("libnccl lacks ") + name; return false; }
     AZ_SYM(GetUniqueId, "ncclGetUniqueId") AZ_SYM(CommInitRank, "ncclCommInitRank") AZ_SYM(CommDestroy, "ncclCommDestroy")
     AZ_SYM(Send, "ncclSend") AZ_SYM(Recv, "ncclRecv") AZ_SYM(GroupStart, "ncclGroupStart") AZ_SYM(GroupEnd, "ncclGroupEnd")
-    AZ_SYM(AllReduce, "ncclAllReduce") AZ_SYM(GetErrorString, "ncclGetErrorString")
+    AZ_SYM(AllReduce, "ncclAllReduce") AZ_SYM(AllGather, "ncclAllGather") AZ_SYM(GetErrorString, "ncclGetErrorString")
 #undef AZ_SYM
     g_api.h = h;
     return true;
@@ -51,7 +52,69 @@ bool load_api(std::string* err)
 
 struct NcclComm : AzComm {
     ncclComm_t comm = nullptr;
-    ~NcclComm() override { if (comm) g_api.CommDestroy(comm); }
+    std::vector<void*> opened; // cudaIpcOpenMemHandle mappings of the peers' buffers
+    ~NcclComm() override
+    {
+        for (void* p : opened) cudaIpcCloseMemHandle(p);
+        if (comm) g_api.CommDestroy(comm);
+    }
+    // Peer memory through CUDA IPC: every rank publishes (handle of the allocation, offset of the buffer inside it) for each
+    // buffer, the records travel in one ncclAllGather, and every rank maps the allocations of the others (peer access is
+    // enabled lazily by cudaIpcOpenMemHandle).  One box only: all ranks must be able to reach each other over NVLink / PCIe.
+    int share(void* const* local, int nbuf, std::vector<void*>* remote) override
+    {
+        struct Rec { cudaIpcMemHandle_t h; unsigned long long off; };
+        typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+        GetRange get_range = nullptr;
+        {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { err = "cuMemGetAddressRange is not available"; return AZ_ERR_UNSUPPORTED; }
+            get_range = (GetRange)fn;
+        }
+        std::vector<Rec> mine(nbuf), all((size_t)nbuf * nranks);
+        for (int b = 0; b < nbuf; b++) {
+            unsigned long long base = 0; size_t size = 0;
+            if (get_range(&base, &size, (unsigned long long)local[b]) != 0) { err = "cuMemGetAddressRange failed"; return AZ_ERR_UNSUPPORTED; }
+            if (cudaIpcGetMemHandle(&mine[b].h, (void*)base) != cudaSuccess) { cudaGetLastError(); err = "cudaIpcGetMemHandle failed (peer memory needs cudaMalloc'ed buffers)"; return AZ_ERR_UNSUPPORTED; }
+            mine[b].off = (unsigned long long)local[b] - base;
+        }
+        Rec *d_mine = nullptr, *d_all = nullptr;
+        if (cudaMalloc(&d_mine, sizeof(Rec) * nbuf) != cudaSuccess || cudaMalloc(&d_all, sizeof(Rec) * nbuf * nranks) != cudaSuccess) { err = "cudaMalloc failed"; return AZ_ERR_CUDA; }
+        cudaMemcpy(d_mine, mine.data(), sizeof(Rec) * nbuf, cudaMemcpyHostToDevice);
+        ncclResult_t r = g_api.AllGather(d_mine, d_all, sizeof(Rec) * nbuf, ncclChar, comm, 0);
+        if (r != ncclSuccess) { cudaFree(d_mine); cudaFree(d_all); return fail("ncclAllGather", r); }
+        cudaStreamSynchronize(0);
+        cudaMemcpy(all.data(), d_all, sizeof(Rec) * nbuf * nranks, cudaMemcpyDeviceToHost);
+        cudaFree(d_mine); cudaFree(d_all);
+        remote->assign((size_t)nbuf * nranks, nullptr);
+        int ok = 1;
+        for (int rk = 0; rk < nranks && ok; rk++)
+            for (int b = 0; b < nbuf; b++) {
+                if (rk == rank) { (*remote)[(size_t)rk * nbuf + b] = local[b]; continue; }
+                void* p = nullptr;
+                // buffers of one rank may share an allocation: map every distinct handle once
+                for (int q = 0; q < b; q++)
+                    if (!memcmp(&all[(size_t)rk * nbuf + q].h, &all[(size_t)rk * nbuf + b].h, sizeof(cudaIpcMemHandle_t)))
+                        p = (char*)(*remote)[(size_t)rk * nbuf + q] - all[(size_t)rk * nbuf + q].off;
+                if (!p) {
+                    if (cudaIpcOpenMemHandle(&p, all[(size_t)rk * nbuf + b].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+                    opened.push_back(p);
+                }
+                (*remote)[(size_t)rk * nbuf + b] = (char*)p + all[(size_t)rk * nbuf + b].off;
+            }
+        // collective verdict: peer memory is used by all ranks or by none
+        double v = ok ? 0.0 : 1.0, *d_v = nullptr;
+        cudaMalloc(&d_v, sizeof(double));
+        cudaMemcpy(d_v, &v, sizeof(double), cudaMemcpyHostToDevice);
+        r = g_api.AllReduce(d_v, d_v, 1, ncclDouble, ncclMax, comm, 0);
+        cudaStreamSynchronize(0);
+        cudaMemcpy(&v, d_v, sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(d_v);
+        if (r != ncclSuccess) return fail("ncclAllReduce", r);
+        if (v != 0.0) { err = "cudaIpcOpenMemHandle failed on some rank (no peer access between the GPUs?)"; return AZ_ERR_UNSUPPORTED; }
+        return AZ_OK;
+    }
     int fail(const char* what, ncclResult_t r)
     {
         err = std::string(what) + ": " + g_api.GetErrorString(r);

@@ -1464,6 +1464,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
+    if (!strcmp(key, "list_staged")) { e->list_staged = value != 0.0; return AZ_OK; }       // A/B of the two FAST list builds
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;
 }

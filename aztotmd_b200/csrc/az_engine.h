@@ -48,6 +48,7 @@ struct az_engine {
     bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
     float r2_safe = 3.4e38f; // packed Lennard-Jones list pass: below this r2 the reference's force_autocap clamp can act
+    bool list_staged = false; // az_k_build_list_staged (rows staged in shared memory, lockstep flush): measured slower, kept for the A/B (az_pair.cuh)
     bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
     int *nbr = nullptr, *nbrCount = nullptr;
     std::vector<AzVdw> h_table;

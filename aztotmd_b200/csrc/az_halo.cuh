@@ -251,6 +251,92 @@ az_k_ghost_update(const __grid_constant__ AzDD D, const int* __restrict__ ghostS
     if (therm) therm[s].y = in_aux[t].y;
 }
 
+// ---------------------------------------------------------------------------------------
+// Ghost refresh over PEER MEMORY (NVLink 5 / NVSwitch): the steps between rebuilds without a NCCL call.  At create time every
+// rank maps the receive staging and the arrival flags of its neighbours (AzComm::share -> CUDA IPC).  az_k_ghost_put is
+// the pack kernel with the stores pointed at the neighbour: entry k of my message for direction d lands in entry
+// gr[26-d] + k of the neighbour's staging buffer, exactly where ncclRecv would have put it; when the last block of the
+// grid has finished, it raises the neighbour's arrival flag for that direction to `seq` (a counter all ranks advance together).
+// az_k_ghost_update_wait is az_k_ghost_update behind a wait for the flags of the directions in use.  Two staging
+// buffers alternate (seq & 1): a neighbour that is one step ahead writes the other one.  [Why that is enough: a rank posts
+// put(n) only after its force pass n-1, which consumed the neighbour's put(n-1), which the neighbour posted after ITS update(n-2)
+// -- so nobody still reads buffer (n & 1) when put(n) arrives.]
+struct AzPeer {
+    float4* pos[AZ_NDIR];  // neighbour's staging (both halves, 2 * gr[AZ_NDIR] entries), NULL = direction unused
+    float2* aux[AZ_NDIR];
+    int* flags[AZ_NDIR];   // neighbour's arrival flags [AZ_NDIR]
+};
+
+__device__ __forceinline__ int az_ld_volatile(const int* p) { return *(const volatile int*)p; }
+
+template <bool AUX>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_ghost_put(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R, const int* __restrict__ sendList, const float4* __restrict__ pos,
+               const float2* __restrict__ therm, int seq, int* __restrict__ done)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < D.gs[AZ_NDIR]) {
+        const int d = az_dir_of(D.gs, t), k = t - D.gs[d];
+        const int capacity = D.gs[d + 1] - D.gs[d] - 1;
+        if (k >= 1 && k - 1 < min(D.cnt->sendCount[d], capacity) && R.pos[d]) {
+            const int i = sendList[t];
+            const size_t dst = (size_t)(seq & 1) * D.gr[AZ_NDIR] + D.gr[AZ_NDIR - 1 - d] + k; // the neighbour's entry for "from direction 26-d"
+            R.pos[d][dst] = pos[i];
+            if (AUX) R.aux[d][dst] = make_float2(0.f, therm[i].y);
+        }
+    }
+    // completion: the last block to finish raises the flags (all stores of all blocks are visible system-wide before that)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(done, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            for (int d = 0; d < AZ_NDIR; d++)
+                if (R.flags[d]) *(volatile int*)(R.flags[d] + (AZ_NDIR - 1 - d)) = seq;
+            __threadfence_system();
+        }
+    }
+}
+
+#ifdef AZ_EMU
+__device__ __forceinline__ float4 az_ld_cg4(const float4* p) { return *(const volatile float4*)p; }
+__device__ __forceinline__ float2 az_ld_cg2(const float2* p) { return *(const volatile float2*)p; }
+#else
+__device__ __forceinline__ float4 az_ld_cg4(const float4* p) { return __ldcg(p); } // L2 only: the line may sit stale in L1 from two steps ago
+__device__ __forceinline__ float2 az_ld_cg2(const float2* p) { return __ldcg(p); }
+#endif
+
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_ghost_update_wait(const __grid_constant__ AzDD D, const int* __restrict__ ghostSlot, const float4* __restrict__ stage_pos,
+                       const float2* __restrict__ stage_aux, float4* __restrict__ pos, float2* __restrict__ therm, const int* __restrict__ flags,
+                       int seq, int* __restrict__ err_flags)
+{
+    // every block waits for the messages of all directions in use (a direction is in use iff its capacity is not empty)
+    if (threadIdx.x < AZ_NDIR) {
+        const int d = threadIdx.x;
+        if (D.gr[d + 1] - D.gr[d] - 1 > 0) {
+            long long spins = 0;
+            while (az_ld_volatile(flags + d) - seq < 0) { // flags only grow; a neighbour may already be one step ahead
+                if (++spins > (1ll << 31)) { atomicOr(err_flags, AZ_FLAG_HALO); break; } // a neighbour died: report instead of hanging the GPU
+#ifdef AZ_EMU
+                az_emu_yield();
+#endif
+            }
+        }
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.gr[AZ_NDIR]) return;
+    const int d = az_dir_of(D.gr, t), k = t - D.gr[d];
+    if (k == 0 || k - 1 >= D.cnt->recvCount[d]) return;
+    const int s = ghostSlot[t];
+    const size_t src = (size_t)(seq & 1) * D.gr[AZ_NDIR] + t;
+    pos[s] = az_ld_cg4(stage_pos + src);
+    if (therm) therm[s].y = az_ld_cg2(stage_aux + src).y;
+}
+
 // count_cell for the owned and ghost atoms of a brick: global cell from the (wrapped) position, then the
 // periodic image that falls inside the local grid.  Leavers (stay == 0) are dead: cell -1, skipped by the sort.
 static __global__ void __launch_bounds__(AZ_TPB)

@@ -479,6 +479,181 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
     }
 }
 
+// warp-wide integer max / min, the same value in every lane (REDUX on the device)
+__device__ __forceinline__ int az_warp_max_int(int v)
+{
+#ifdef AZ_EMU
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+    return __shfl_sync(0xffffffffu, v, 0);
+#else
+    return __reduce_max_sync(0xffffffffu, v);
+#endif
+}
+__device__ __forceinline__ int az_warp_min_int(int v) { return -az_warp_max_int(-v); }
+
+// az_k_build_list_staged: the rebuild step on grids where every stencil offset is a distinct cell (the FAST case of
+// az_k_build_list; large systems).  Same thread-per-atom walk, same candidate ranges, same distance test -- what changes is
+// where the hits go.  ncu on B200 (profiles/r2/): az_k_build_list is bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts
+// 73 % of peak), and three quarters of those wavefronts are its predicated row stores: the lanes of a warp sit at different
+// row counts, so one `rows[nA * 32] = j` touches ~7 different 128-byte lines.  Here a hit goes to a shared-memory ring
+// (s_rows[row & 63][thread]: conflict-free, one wavefront) and the warp flushes the ring in lockstep over the ROW index, so
+// every global store instruction writes one line.  For that the lanes of a warp must stay together: the walk over
+// columns / z pieces has the same trip counts in every lane, every range is swept in chunks of AZ_BL_CHUNK candidates up
+// to the longest range of the warp (shorter ones idle), and the flush decision is a warp vote.  Neighbours through a
+// periodic face (rare) and ranges that are not contiguous in memory (ghost cells of a brick) keep the direct stores.
+// MEASURED AND REJECTED (B200, 4 M atoms, profiles/r2/ncu_full_lj4m_staged_build_summary.txt): the L1 data pipe falls from 73 % to
+// 43 % and the store sectors from 203 M to 48 M as intended, but the kernel takes 2.60 ms against 1.49 ms: the lockstep
+// bookkeeping (ring index, self test on every candidate, chunk votes, idle lanes of shorter ranges) raises the instruction
+// count from 1.01e9 to 1.70e9 warp instructions and the 32 KB ring cuts the resident warps from 31 to 21 per SM (L1 hit
+// rate 87 % -> 56 %).  Off by default (az_engine_set_option "list_staged" 1 switches it on for the A/B); results are identical.
+#define AZ_BL_RING 64
+#define AZ_BL_CHUNK 16
+static __global__ void __launch_bounds__(AZ_LIST_TPB)
+az_k_build_list_staged(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
+{
+    __shared__ int s_rows[AZ_BL_RING * AZ_LIST_TPB];
+    __shared__ int s_ghost;
+    const AzGrid& g = P.g;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * AZ_LIST_TPB + tid;
+    const int n_owned = az_n_owned(P);
+    if (A.blockFlag) { if (tid == 0) s_ghost = 0; __syncthreads(); }
+    const bool act = i < n_owned;
+    const int ia = act ? i : max(0, n_owned - 1); // idle lanes walk along with the last atom's cell and record nothing
+    const float4 pi = A.pos[ia];
+    const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+    const int ci = A.cellOfSorted[ia];
+    const int cxy = ci / onz;
+    const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+    const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+    const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+    const int cap = A.nbr_cap;
+    int* __restrict__ rows = A.nbr + az_nbr_base(ia, cap);
+    int nA = 0, fA = 0, nB = 0, jmax = -1; // rows recorded / already flushed (plain), imaged rows, farthest j swept
+    const float lim = P.r2list;
+    int* __restrict__ ring = s_rows + tid;
+
+    auto flush = [&]() { // lockstep over the row index: one 128-byte line per store instruction
+        const int kmin = az_warp_min_int(fA), kmax = az_warp_max_int(nA);
+        for (int k = kmin; k < kmax; k++)
+            if (act && k >= fA && k < nA && k < cap - nB) rows[k * 32] = ring[(k & (AZ_BL_RING - 1)) * AZ_LIST_TPB];
+        fA = nA;
+    };
+    // one contiguous range per lane, swept by the whole warp in lockstep (lanes with a shorter or empty range idle)
+    auto sweep_lock = [&](const int rb, const int re) {
+        const int len = act ? max(0, re - rb) : 0;
+        if (len > 0) jmax = max(jmax, re - 1);
+        const int maxlen = az_warp_max_int(len);
+        const bool self = act && i >= rb && i < re; // the own column holds atom i itself
+        for (int p0 = 0; p0 < maxlen; p0 += AZ_BL_CHUNK) {
+            const int a = rb + p0, b = min(rb + len, a + AZ_BL_CHUNK);
+            int j = a;
+            for (; j + 2 <= b; j += 2) {
+                const float4 pa = __ldg(A.pos + j), pb = __ldg(A.pos + j + 1);
+                const az_f2 dx = az_pk(pi.x - pa.x, pi.x - pb.x), dy = az_pk(pi.y - pa.y, pi.y - pb.y), dz = az_pk(pi.z - pa.z, pi.z - pb.z);
+                const az_f2 r2 = az_fma2(dz, dz, az_fma2(dx, dx, az_mul2(dy, dy))); // each half rounds like the force pass's fmaf chain
+                if ((az_lo(r2) <= lim) & !(self & (j == i))) { ring[(nA & (AZ_BL_RING - 1)) * AZ_LIST_TPB] = j; nA++; }
+                if ((az_hi(r2) <= lim) & !(self & (j + 1 == i))) { ring[(nA & (AZ_BL_RING - 1)) * AZ_LIST_TPB] = j + 1; nA++; }
+            }
+            if (j < b) {
+                const float4 pj = __ldg(A.pos + j);
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                if ((fmaf(dz, dz, fmaf(dx, dx, dy * dy)) <= lim) & !(self & (j == i))) { ring[(nA & (AZ_BL_RING - 1)) * AZ_LIST_TPB] = j; nA++; }
+            }
+            if (__any_sync(0xffffffffu, nA - fA > AZ_BL_RING - AZ_BL_CHUNK)) flush();
+        }
+    };
+    // direct stores (no staging): imaged neighbours and the few non-contiguous ranges; the caller has flushed the ring
+    auto sweep_direct = [&](const int rb, const int re, const int code) {
+        if (!act || re <= rb) return;
+        jmax = max(jmax, re - 1);
+        if (code == 0) {
+            const int room = cap - nB;
+            for (int j = rb; j < re; j++) {
+                const float4 pj = __ldg(A.pos + j);
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const bool hit = (fmaf(dz, dz, fmaf(dx, dx, dy * dy)) <= lim) & (j != i);
+                if (hit & (nA < room)) rows[nA * 32] = j;
+                nA += hit ? 1 : 0;
+            }
+            fA = nA;
+        } else {
+            const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
+            const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
+            const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
+            for (int j = rb; j < re; j++) {
+                const float4 pj = __ldg(A.pos + j);
+                const float dx = (pi.x - pj.x) - shx, dy = (pi.y - pj.y) - shy, dz = (pi.z - pj.z) - shz;
+                const bool hit = (fmaf(dz, dz, fmaf(dx, dx, dy * dy)) <= lim) & (j != i);
+                if (hit & (nB < cap - nA)) rows[(cap - 1 - nB) * 32] = j | (code << AZ_NBR_BITS);
+                nB += hit ? 1 : 0;
+            }
+        }
+    };
+
+    const int nz = g.n[2];
+    for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
+        const int ux = gcx + ox;
+        const int shxi = (ux < 0) ? -1 : ((ux >= g.n[0]) ? 1 : 0);
+        const int sx = g.dec[0] ? (ux - g.goff[0]) : (ux - shxi * g.n[0]);
+        const int aox = ox < 0 ? -ox : ox;
+        const float ddx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+        for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
+            const int uy = gcy + oy;
+            const int shyi = (uy < 0) ? -1 : ((uy >= g.n[1]) ? 1 : 0);
+            const int sy = g.dec[1] ? (uy - g.goff[1]) : (uy - shyi * g.n[1]);
+            const int aoy = oy < 0 ? -oy : oy;
+            const float ddy = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+            const float dxy2 = ddx * ddx + ddy * ddy;
+            if (dxy2 > lim) continue; // the same in every lane: depends on the offsets only
+            // |oz| = k is kept iff dxy2 + ((k-1)*csize)^2 <= lim  (cell_dist_int; checked exactly: sqrt and floor round)
+            int kz = min(g.sten[2], 1 + (int)floorf(sqrtf(lim - dxy2) * g.crev[2]));
+            while (kz < g.sten[2] && dxy2 + ((float)kz * g.csize[2]) * ((float)kz * g.csize[2]) <= lim) kz++;
+            while (kz > 0 && dxy2 + ((float)(kz - 1) * g.csize[2]) * ((float)(kz - 1) * g.csize[2]) > lim) kz--;
+            const int ua = gcz - kz, ub = gcz + kz;
+            const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
+#pragma unroll 1
+            for (int shzi = -1; shzi <= 1; shzi++) { // the interval, split where it crosses a periodic face
+                const int a = max(ua, shzi * nz), b = min(ub, shzi * nz + nz - 1);
+                const bool some = a <= b;
+                const int off = g.dec[2] ? g.goff[2] : shzi * nz;
+                int rb = 0, re = 0;
+                bool contig = true;
+                if (some) {
+                    const int cid_a = az_cell_id(g, colbase + a - off), cid_b = az_cell_id(g, colbase + b - off);
+                    contig = (cid_b - cid_a == b - a);
+                    if (contig) { rb = A.first[cid_a]; re = A.first[cid_b + 1]; }
+                }
+                const int code = az_shift_code(shxi, shyi, shzi);
+                const bool lock = contig && code == 0;
+                if (__all_sync(0xffffffffu, lock || !some || !act)) sweep_lock(lock && some ? rb : 0, lock && some ? re : 0);
+                else { // some lane of the warp needs the direct stores for this piece: everybody takes them
+                    flush();
+                    if (some) {
+                        if (contig) sweep_direct(rb, re, code);
+                        else
+                            for (int u = a; u <= b; u++) { // ghost cells of a brick are not numbered along z
+                                const int cid = az_cell_id(g, colbase + u - off);
+                                const int jb = A.first[cid];
+                                sweep_direct(jb, jb + A.count[cid], code);
+                            }
+                    }
+                }
+            }
+        }
+    }
+    flush();
+    if (act) {
+        if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }
+        A.nbrCount[i] = nA | (nB << AZ_NBR_CNT_BITS);
+    }
+    if (A.blockFlag) { // ghosts sit behind the owned atoms in the sorted streams
+        if (act && jmax >= n_owned) atomicOr(&s_ghost, 1);
+        __syncthreads();
+        if (tid == 0) A.blockFlag[blockIdx.x] = s_ghost;
+    }
+}
+
 // read-once global load: no L1 allocation
 __device__ __forceinline__ int az_ld_stream(const int* p)
 {

@@ -53,7 +53,8 @@ static int az_pair_go_e(az_engine* e, const AzPairArgs& A, bool energy, int mode
     if (mode == AZ_PAIR_MODE_LIST)
         return energy ? az_pair_list_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_list_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_TILE_LIST) { // record the neighbours, then take this step's forces from the list like every other step
-        if (e->list_fast) AZ_LAUNCH(az_k_build_list<true>, e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+        if (e->list_fast && e->list_staged) AZ_LAUNCH(az_k_build_list_staged, e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
+        else if (e->list_fast) AZ_LAUNCH(az_k_build_list<true>, e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
         else AZ_LAUNCH(az_k_build_list<false>, e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
         return energy ? az_pair_list_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_list_go<VK, CK, SINGLE, RADII, false>(e, A);
     }

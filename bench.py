@@ -46,6 +46,7 @@ WORKLOADS = {
     "lj500k": (50, "synthetic fcc LJ argon, 500,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj4k": (10, "synthetic fcc LJ argon, 4,000 atoms, rho*=0.8442, rc=2.5 sigma"),
     "lj32k": (20, "synthetic fcc LJ argon, 32,000 atoms, rho*=0.8442, rc=2.5 sigma"),
+    "lj131k": (32, "synthetic fcc LJ argon, 131,072 atoms, rho*=0.8442, rc=2.5 sigma (the deck of profiles/ref_cuda_probe.py)"),
     # BASELINE config 3 of the ionic kind: rock-salt NaCl-like melt, Buckingham + real-space Coulomb (DSF), 1 000 000 ions
     "nacl1m": (-50, "synthetic NaCl-like ionic melt, 1,000,000 ions (50^3 rock-salt cells, a = 5.9 A), Buckingham rc 9 A + DSF Coulomb rc 12 A alpha 0.2, 1200 K"),
     # the full Ewald sum ('elec pme 12 0.2 8 8 8': real space + 8x15x15 half space of k-vectors inside the cut-off + constant)

@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2_06_pytest_parity.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_06_pytest_parity.log
+timeout 600 python bench.py --steps 100 --warmup 20 > gpurun_out/r2_06_bench_staged.json 2> gpurun_out/r2_06_bench_staged.err; echo "rc=$?" >> gpurun_out/r2_06_bench_staged.err
+timeout 600 python bench.py --steps 100 --warmup 20 --option list_staged=0 --no-cpu-baseline --no-small-deck --e2e-steps 2 > gpurun_out/r2_06_bench_unstaged.json 2> gpurun_out/r2_06_bench_unstaged.err; echo "rc=$?" >> gpurun_out/r2_06_bench_unstaged.err
+timeout 600 python bench.py --workload lj131k --rebuild 1 --steps 1000 --warmup 50 --no-cpu-baseline --e2e-steps 2 > gpurun_out/r2_06_bench_lj131k_r1.json 2> gpurun_out/r2_06_bench_lj131k_r1.err; echo "rc=$?" >> gpurun_out/r2_06_bench_lj131k_r1.err
+timeout 300 python profiles/prof_step.py lj4m 12 10 0.25 0 > gpurun_out/r2_06_prof_plain.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_06_launches.csv python profiles/prof_step.py lj4m 12 10 0.25 0 > gpurun_out/r2_06_ncu_launches.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"az_k_pair_list|az_k_build_list" -s 0 -c 3 -o gpurun_out/r2_06_full python profiles/prof_step.py lj4m 12 10 0.25 0 > gpurun_out/r2_06_ncu_full.log 2>&1
+echo done

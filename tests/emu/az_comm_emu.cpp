@@ -6,6 +6,7 @@
 #include <deque>
 #include <map>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include "az_comm.h"
 #include "../../include/aztot_b200.h"
@@ -43,6 +44,20 @@ struct EmuComm : AzComm {
             }
         return AZ_OK;
     }
+    int share(void* const* local, int nbuf, std::vector<void*>* remote) override
+    {
+        if (getenv("AZ_EMU_NO_PEER")) return AZ_ERR_UNSUPPORTED; // tests: the send/recv halo path
+        std::vector<AzP2P> ops;
+        std::vector<std::vector<void*>> in(nranks, std::vector<void*>(nbuf));
+        for (int r = 0; r < nranks; r++) if (r != rank) ops.push_back({ r, local, sizeof(void*) * nbuf, nullptr, 0 });
+        for (int r = 0; r < nranks; r++) if (r != rank) ops.push_back({ r, nullptr, 0, in[r].data(), sizeof(void*) * nbuf });
+        int rc = exchange(ops, nullptr);
+        if (rc) return rc;
+        remote->assign((size_t)nbuf * nranks, nullptr);
+        for (int r = 0; r < nranks; r++)
+            for (int b = 0; b < nbuf; b++) (*remote)[(size_t)r * nbuf + b] = r == rank ? local[b] : in[r][b];
+        return AZ_OK;
+    }
     int allreduce(double* dev, int n, bool take_max, cudaStream_t) override
     {
         std::unique_lock<std::mutex> lk(w->m);
@@ -55,6 +70,7 @@ struct EmuComm : AzComm {
         return AZ_OK;
     }
 };
+// (EmuComm::share is defined below the struct: the ranks are threads of one process, a "peer mapping" is the pointer itself)
 // Second transport of the emulator build: the exchange and the all-reduce are handed to callbacks, so that a
 // test can carry them over torch.distributed (gloo) between real processes (tests/test_gloo_bricks.py).
 typedef int (*az_emu_exchange_cb)(int n_ops, const int* peers, const void* const* send, const size_t* send_bytes,
