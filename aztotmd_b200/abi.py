@@ -121,7 +121,7 @@ class az_engine_info_t(C.Structure):
                 ("pair_smem_bytes", C.c_int), ("pair_zc", C.c_int), ("pair_vk", C.c_int), ("pair_ck", C.c_int),
                 ("n_sm", C.c_int), ("max_neigh_seen", C.c_int), ("device_bytes", C.c_longlong),
                 ("list_rows", C.c_int), ("flags", C.c_int), ("capacity", C.c_int), ("n_ranks", C.c_int),
-                ("graph_replays", C.c_longlong), ("graphs_cached", C.c_int), ("reserved", C.c_int)]
+                ("graph_replays", C.c_longlong), ("graphs_cached", C.c_int), ("peer_halo", C.c_int)]
 
 
 # every symbol include/aztot_b200.h declares: name -> (restype, argtypes)

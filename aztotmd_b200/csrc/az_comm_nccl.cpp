@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 // No <nccl.h>: the library is loaded with dlopen, and a CUDA-only box (no NCCL headers) must still build the engine for
 // single-GPU use.  The handful of NCCL types this file needs are declared here with the values of nccl.h (stable since
 // NCCL 2.0: ncclSuccess = 0, ncclChar = 0, ncclDouble = 8, ncclSum = 0, ncclMax = 2, a 128-byte unique id).
@@ -63,7 +64,9 @@ struct NcclComm : AzComm {
     // enabled lazily by cudaIpcOpenMemHandle).  One box only: all ranks must be able to reach each other over NVLink / PCIe.
     int share(void* const* local, int nbuf, std::vector<void*>* remote) override
     {
-        struct Rec { cudaIpcMemHandle_t h; unsigned long long off; };
+        // pid / dev / ptr: ranks that live in ONE process (threads, as in the tests) cannot open each other's IPC handles; they
+        // enable direct peer access between their devices and use the pointer itself (unified virtual addressing)
+        struct Rec { cudaIpcMemHandle_t h; unsigned long long off; long long pid; int dev; int pad; unsigned long long ptr; };
         typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
         GetRange get_range = nullptr;
         {
@@ -78,6 +81,8 @@ struct NcclComm : AzComm {
             if (get_range(&base, &size, (unsigned long long)local[b]) != 0) { err = "cuMemGetAddressRange failed"; return AZ_ERR_UNSUPPORTED; }
             if (cudaIpcGetMemHandle(&mine[b].h, (void*)base) != cudaSuccess) { cudaGetLastError(); err = "cudaIpcGetMemHandle failed (peer memory needs cudaMalloc'ed buffers)"; return AZ_ERR_UNSUPPORTED; }
             mine[b].off = (unsigned long long)local[b] - base;
+            mine[b].pid = (long long)getpid(); mine[b].ptr = (unsigned long long)local[b]; mine[b].pad = 0;
+            cudaGetDevice(&mine[b].dev);
         }
         Rec *d_mine = nullptr, *d_all = nullptr;
         if (cudaMalloc(&d_mine, sizeof(Rec) * nbuf) != cudaSuccess || cudaMalloc(&d_all, sizeof(Rec) * nbuf * nranks) != cudaSuccess) { err = "cudaMalloc failed"; return AZ_ERR_CUDA; }
@@ -92,6 +97,20 @@ struct NcclComm : AzComm {
         for (int rk = 0; rk < nranks && ok; rk++)
             for (int b = 0; b < nbuf; b++) {
                 if (rk == rank) { (*remote)[(size_t)rk * nbuf + b] = local[b]; continue; }
+                const Rec& rr = all[(size_t)rk * nbuf + b];
+                if (rr.pid == (long long)getpid()) { // same process: peer access instead of IPC
+                    int mydev = 0, can = 0;
+                    cudaGetDevice(&mydev);
+                    if (rr.dev != mydev) {
+                        cudaDeviceCanAccessPeer(&can, mydev, rr.dev);
+                        if (!can) { ok = 0; break; }
+                        cudaError_t pe = cudaDeviceEnablePeerAccess(rr.dev, 0);
+                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+                        cudaGetLastError();
+                    }
+                    (*remote)[(size_t)rk * nbuf + b] = (void*)rr.ptr;
+                    continue;
+                }
                 void* p = nullptr;
                 // buffers of one rank may share an allocation: map every distinct handle once
                 for (int q = 0; q < b; q++)

@@ -81,6 +81,32 @@ __device__ __forceinline__ int az_n_owned(const AzParams& P) { return P.n_dyn ? 
 #define AZ_NUM_PI 3.14159f       // numPi, src/cuTemp.cu:228
 
 // ---------------------------------------------------------------------------------------
+// Wait until an arrival flag written by a neighbour GPU over peer memory (az_k_ghost_put) has reached `seq`.  Flags only grow;
+// a neighbour may already be one step ahead.  Bounded: if the neighbour died the sticky halo flag is raised (bit 8 =
+// AZ_FLAG_HALO) and the kernel goes on with stale ghosts instead of hanging the GPU.  In the emulator build the ranks are
+// host threads: yield the core while waiting and give them a minute.
+#ifdef AZ_EMU
+#include <chrono>
+#include <thread>
+static inline void az_wait_flag(const int* flag, int seq, int* err_flags)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) - seq < 0) {
+        std::this_thread::yield();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) { __atomic_fetch_or(err_flags, 8, __ATOMIC_RELAXED); break; }
+    }
+}
+#else
+__device__ __forceinline__ void az_wait_flag(const int* flag, int seq, int* err_flags)
+{
+    long long spins = 0;
+    while (*(const volatile int*)flag - seq < 0)
+        if (++spins > (1ll << 24)) { atomicOr(err_flags, 8); break; } // ~10 s
+    __threadfence();
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011); the CPU checker restates the same rounds
 __device__ __forceinline__ void az_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                           uint32_t k0, uint32_t k1, uint32_t out[4])

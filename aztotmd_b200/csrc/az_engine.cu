@@ -123,6 +123,13 @@ static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream);
 static int dd_wait_ghosts(az_engine* e);
 static int dd_mark_moved(az_engine* e);
 static bool dd_overlap(const az_engine* e);
+static bool dd_peer_halo(const az_engine* e);
+static bool dd_fused(const az_engine* e);
+static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage_out);
+static int dd_wait_put(az_engine* e);
+static int dd_sync_ghosts(az_engine* e);
+static int dd_fused_args(az_engine* e, AzPairArgs& A);
+static int dd_block_order(az_engine* e);
 static int* dd_block_flags(const az_engine* e);
 static void dd_set_overlap(az_engine* e, bool on);
 static int dd_init_counts(az_engine* e, int n_keep);
@@ -796,11 +803,12 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         e->since_rebuild = 0;
     } else {
         e->since_rebuild++;
-        if (e->dd) { int rc = dd_overlap(e) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
+        if (e->dd) { int rc = (dd_overlap(e) || dd_fused(e)) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
     }
     // the integrator rides on the list kernel when the next step's kick may follow this step's forces directly
     const bool ride = fuse_next && e->fuse_pair && !eq_step;
-    const bool split = !rebuild && dd_overlap(e); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
+    const bool fusedh = !rebuild && dd_fused(e);  // peer-memory halo: one list launch, ghost-touching blocks last, waiting on arrival flags
+    const bool split = !rebuild && !fusedh && dd_overlap(e); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
     { // K4: pair forces
         const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
@@ -822,6 +830,13 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             e->clear_counts_bytes = (rb_next && !e->dd) ? sizeof(int) * (size_t)(nc + 1) : 0; // clear_clist for the next step's binning
         }
         int rc;
+        if (fusedh) { // put on the halo stream; the list pass reads the ghosts from the staging once the flags are up
+            rc = dd_put_ghosts(e, c, &A.haloSeq, &A.ghostStage);
+            if (rc) return rc;
+            rc = dd_fused_args(e, A);
+            if (rc) return rc;
+            A.phase = 3;
+        }
         if (split) { // blocks that list no ghost run while the halo is in flight, the others once it has landed
             A.phase = 1;
             rc = az_launch_pair(e, A, want_energy, pair_mode);
@@ -835,6 +850,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         }
         rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
+        if (fusedh) { rc = dd_wait_put(e); if (rc) return rc; } // whatever moves the atoms next comes after the put has read them
+        if (rebuild && dd_fused(e)) { rc = dd_block_order(e); if (rc) return rc; } // the list (and its per-block ghost flags) is new
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
         if (ride) { // the new positions / velocities are in the alternate buffers: swap roles
             std::swap(e->pos[c], e->pos_alt);
@@ -1383,6 +1400,7 @@ extern "C" int az_engine_rdf_sample(az_engine* e)
     if (!e->rdf_hist) { AZ_SET_ERR(e, "rdf: call az_engine_rdf_begin first"); return AZ_ERR_INVALID; }
     if (!e->binned) { AZ_SET_ERR(e, "rdf: the atoms are not binned yet (sample after a step)"); return AZ_ERR_INVALID; }
     AZ_CUDA(e, cudaSetDevice(e->device));
+    { int rc = dd_sync_ghosts(e); if (rc) return rc; } // fused halo: the last ghosts sit in the receive staging only
     AzRdfArgs A;
     memset(&A, 0, sizeof(A));
     const int c = e->cur;
@@ -1482,6 +1500,7 @@ extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
     o->list_rows = e->nbr_cap;
     o->capacity = e->dd ? e->P.n_local : e->n; o->n_ranks = e->n_ranks;
     o->graph_replays = e->graph_replays; o->graphs_cached = (int)e->graphs.size();
+    o->peer_halo = dd_peer_halo(e) ? (e->dd->fused ? 2 : 1) : 0;
     if (e->sc) {
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -30,6 +30,20 @@ struct AzDDHost {
     cudaEvent_t ev_moved = nullptr, ev_ghosts = nullptr;
     int* blockFlag = nullptr;
     bool overlap = true;
+    // ghost refresh over peer memory (AzComm::share): no NCCL call on the steps between rebuilds
+    bool p2p = false;
+    AzPeer peerPtr;                       // the neighbours' staging buffers and arrival flags, per direction
+    float4* stagePos = nullptr;           // my receive staging: two halves of gr[AZ_NDIR] entries (alternating with halo_seq & 1)
+    float2* stageAux = nullptr;
+    int *haloFlags = nullptr, *putDone = nullptr;
+    int halo_seq = 0;                     // advanced by every refresh; the same on all ranks
+    // fused halo (peer memory + Verlet list): ONE list-pass launch per step; ghost-touching blocks come last in blockOrder, wait
+    // for the arrival flags and read the ghosts from the staging; nothing scatters them into pos[] unless somebody asks
+    bool fused = false;
+    int *blockOrder = nullptr, *ghostEntry = nullptr;
+    cudaEvent_t ev_put = nullptr;
+    bool pos_ghosts_stale = false;        // pos[] still holds the ghost positions of the last scatter (rebuild or dd_sync_ghosts)
+    int halo_dirs = 0;
     int n_create = 0;      // length of the create-time arrays (az_engine_upload takes arrays of the same shape)
     int *keepSrc = nullptr, *keepGid = nullptr, *keepType = nullptr; // device copies for az_engine_upload
 };
@@ -52,6 +66,9 @@ static void dd_free(az_engine* e)
     cudaFree(h->cellmap); cudaFree(h->stay); cudaFree(h->newIndex); cudaFree(h->sendList); cudaFree(h->ghostSlot); cudaFree(h->migList);
     cudaFree(h->gSendPos); cudaFree(h->gRecvPos); cudaFree(h->gSendAux); cudaFree(h->gRecvAux); cudaFree(h->mSend); cudaFree(h->mRecv);
     cudaFree(h->blockFlag);
+    cudaFree(h->stagePos); cudaFree(h->stageAux); cudaFree(h->haloFlags); cudaFree(h->putDone);
+    cudaFree(h->blockOrder); cudaFree(h->ghostEntry);
+    if (h->ev_put) cudaEventDestroy(h->ev_put);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_ghosts) cudaEventDestroy(h->ev_ghosts);
     if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
@@ -395,6 +412,36 @@ static int dd_alloc(az_engine* e)
     }
     AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
     AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_ghosts, cudaEventDisableTiming));
+    // Peer memory for the per-step ghost refresh.  Every rank offers its receive staging (two halves) and its arrival flags;
+    // if the transport cannot map them (no NVLink / IPC, or the callback transport of the tests) the NCCL send/recv path stays.
+    memset(&h->peerPtr, 0, sizeof(h->peerPtr));
+    const char* no_p2p = getenv("AZTOT_NO_PEER_HALO");
+    if (!(no_p2p && no_p2p[0] == '1')) {
+        AZ_ALLOC(e, h->stagePos, (size_t)2 * D.gr[AZ_NDIR]); AZ_ALLOC(e, h->stageAux, (size_t)2 * D.gr[AZ_NDIR]);
+        AZ_ALLOC(e, h->haloFlags, AZ_NDIR); AZ_ALLOC(e, h->putDone, 1);
+        void* local[3] = { h->stagePos, h->stageAux, h->haloFlags };
+        std::vector<void*> remote;
+        const int rc = h->comm->share(local, 3, &remote);
+        if (rc == AZ_OK) {
+            for (int dir = 0; dir < AZ_NDIR; dir++) {
+                const int pr = h->peer[dir];
+                if (pr < 0) continue;
+                h->peerPtr.pos[dir] = (float4*)remote[(size_t)pr * 3 + 0];
+                h->peerPtr.aux[dir] = (float2*)remote[(size_t)pr * 3 + 1];
+                h->peerPtr.flags[dir] = (int*)remote[(size_t)pr * 3 + 2];
+            }
+            h->p2p = true;
+            for (int dir = 0; dir < AZ_NDIR; dir++) if (h->peer[dir] >= 0) h->halo_dirs |= 1 << dir;
+            // the fused single-launch list pass: needs the list (per-block ghost flags) and positions only (radii travel in the aux stream)
+            const char* no_fuse = getenv("AZTOT_NO_FUSED_HALO");
+            if (e->use_list && !e->use_therm && !(no_fuse && no_fuse[0] == '1')) {
+                AZ_ALLOC(e, h->blockOrder, e->list_nblocks > 0 ? e->list_nblocks : 1);
+                AZ_ALLOC(e, h->ghostEntry, D.gr[AZ_NDIR] > 0 ? D.gr[AZ_NDIR] : 1);
+                AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_put, cudaEventDisableTiming));
+                h->fused = true;
+            }
+        } else if (rc != AZ_ERR_UNSUPPORTED) { e->err = h->comm->err; return rc; }
+    }
     return AZ_OK;
 }
 
@@ -474,6 +521,8 @@ static int dd_rebuild(az_engine* e, int c)
         const int nmax = D.gs[AZ_NDIR] > D.gr[AZ_NDIR] ? D.gs[AZ_NDIR] : D.gr[AZ_NDIR];
         AZ_LAUNCH(az_k_dd_remap, blocks(nmax), AZ_TPB, 0, st, D, h->newIndex, h->sendList, h->ghostSlot);
         AZ_LAUNCH(az_k_dd_publish, 1, 1, 0, st, D, e->first, h->n_owned_cells, nc);
+        if (h->fused) { AZ_LAUNCH(az_k_ghost_entry, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->ghostSlot, h->ghostEntry); AZ_COUNT(e, AZ_TIMER_SORT, 1); }
+        h->pos_ghosts_stale = false; // the ghosts were appended to pos[] just now
         AZ_COUNT(e, AZ_TIMER_SORT, 4);
     }
     return AZ_OK;
@@ -489,6 +538,15 @@ static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream)
     auto blocks = [](int n) { return (n + AZ_TPB - 1) / AZ_TPB; };
     float2* th = e->use_therm ? e->therm[c] : nullptr;
     Timer t(e, AZ_TIMER_HALO, st); // events on the stream the halo kernels run on
+    if (h->p2p) { // stores straight into the neighbours' staging over NVLink + arrival flags; no NCCL call, no host-side group
+        const int seq = ++h->halo_seq;
+        if (th) AZ_LAUNCH(az_k_ghost_put<true>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, D, h->peerPtr, h->sendList, e->pos[c], th, seq, h->putDone);
+        else AZ_LAUNCH(az_k_ghost_put<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, D, h->peerPtr, h->sendList, e->pos[c], th, seq, h->putDone);
+        AZ_LAUNCH(az_k_ghost_update_wait, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->ghostSlot, h->stagePos, h->stageAux, e->pos[c], th, h->haloFlags, seq, &e->sc->overflow);
+        if (on_halo_stream) AZ_CUDA(e, cudaEventRecord(h->ev_ghosts, h->halo_stream));
+        AZ_COUNT(e, AZ_TIMER_HALO, 2);
+        return AZ_OK;
+    }
     AZ_LAUNCH(az_k_ghost_pack<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, D, h->sendList, e->pos[c], e->id[c], th, h->gSendPos, h->gSendAux);
     std::vector<AzP2P> ops;
     dd_add_ops(h, ops, h->gSendPos, D.gs, h->gRecvPos, D.gr, sizeof(float4));
@@ -505,6 +563,41 @@ static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream)
     return AZ_OK;
 }
 
+// Fused halo, steps between rebuilds: only the put (on the halo stream, behind ev_moved).  The list pass that follows on the
+// engine's stream takes the ghosts from the staging; *seq_out / *stage_out tell it which flags value and which half.
+static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage_out)
+{
+    AzDDHost* h = e->dd;
+    const AzDD& D = h->D;
+    auto blocks = [](int n) { return (n + AZ_TPB - 1) / AZ_TPB; };
+    AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0));
+    Timer t(e, AZ_TIMER_HALO, h->halo_stream);
+    const int seq = ++h->halo_seq;
+    AZ_LAUNCH(az_k_ghost_put<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, h->halo_stream, D, h->peerPtr, h->sendList, e->pos[c], (const float2*)nullptr, seq, h->putDone);
+    AZ_CUDA(e, cudaEventRecord(h->ev_put, h->halo_stream));
+    AZ_COUNT(e, AZ_TIMER_HALO, 1);
+    h->pos_ghosts_stale = true;
+    *seq_out = seq;
+    *stage_out = h->stagePos + (size_t)(seq & 1) * D.gr[AZ_NDIR];
+    return AZ_OK;
+}
+// ... and whatever on the engine's stream changes positions next must come after the put has read them
+static int dd_wait_put(az_engine* e) { AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->dd->ev_put, 0)); return AZ_OK; }
+
+// Readers of ghost positions other than the list pass (RDF sampling): scatter the last received ghosts into pos[].  The flags
+// of that refresh have been seen by the list pass that ran on this stream, so no wait is needed.
+static int dd_sync_ghosts(az_engine* e)
+{
+    AzDDHost* h = e->dd;
+    if (!h || !h->fused || !h->pos_ghosts_stale) return AZ_OK;
+    const AzDD& D = h->D;
+    AZ_LAUNCH(az_k_ghost_update_wait, (D.gr[AZ_NDIR] + AZ_TPB - 1) / AZ_TPB, AZ_TPB, 0, e->stream, D, h->ghostSlot, h->stagePos, h->stageAux, e->pos[e->cur],
+              (float2*)nullptr, h->haloFlags, h->halo_seq, &e->sc->overflow);
+    e->launches++;
+    h->pos_ghosts_stale = false;
+    return AZ_OK;
+}
+
 // positions of this step are final (the kick + drift kernel is the last thing on the engine's stream so far)
 static int dd_mark_moved(az_engine* e)
 {
@@ -518,6 +611,20 @@ static int dd_wait_ghosts(az_engine* e)
     return AZ_OK;
 }
 static bool dd_overlap(const az_engine* e) { return e->dd && e->dd->overlap && e->use_list; }
+static bool dd_peer_halo(const az_engine* e) { return e->dd && e->dd->p2p; }
+static bool dd_fused(const az_engine* e) { return e->dd && e->dd->fused && e->dd->overlap; }
+static int dd_fused_args(az_engine* e, AzPairArgs& A)
+{
+    AzDDHost* h = e->dd;
+    A.blockOrder = h->blockOrder; A.ghostEntry = h->ghostEntry; A.haloFlags = h->haloFlags; A.haloDirs = h->halo_dirs;
+    return AZ_OK;
+}
+static int dd_block_order(az_engine* e)
+{
+    AZ_LAUNCH(az_k_block_order, 1, 1024, 0, e->stream, e->dd->blockFlag, e->list_nblocks, e->dd->blockOrder);
+    e->launches++;
+    return AZ_OK;
+}
 static int* dd_block_flags(const az_engine* e) { return e->dd ? e->dd->blockFlag : nullptr; }
 static void dd_set_overlap(az_engine* e, bool on) { if (e->dd) e->dd->overlap = on; }
 

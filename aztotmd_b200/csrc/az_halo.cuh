@@ -301,8 +301,8 @@ az_k_ghost_put(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R,
 }
 
 #ifdef AZ_EMU
-__device__ __forceinline__ float4 az_ld_cg4(const float4* p) { return *(const volatile float4*)p; }
-__device__ __forceinline__ float2 az_ld_cg2(const float2* p) { return *(const volatile float2*)p; }
+__device__ __forceinline__ float4 az_ld_cg4(const float4* p) { __sync_synchronize(); return *p; }
+__device__ __forceinline__ float2 az_ld_cg2(const float2* p) { __sync_synchronize(); return *p; }
 #else
 __device__ __forceinline__ float4 az_ld_cg4(const float4* p) { return __ldcg(p); } // L2 only: the line may sit stale in L1 from two steps ago
 __device__ __forceinline__ float2 az_ld_cg2(const float2* p) { return __ldcg(p); }
@@ -316,15 +316,7 @@ az_k_ghost_update_wait(const __grid_constant__ AzDD D, const int* __restrict__ g
     // every block waits for the messages of all directions in use (a direction is in use iff its capacity is not empty)
     if (threadIdx.x < AZ_NDIR) {
         const int d = threadIdx.x;
-        if (D.gr[d + 1] - D.gr[d] - 1 > 0) {
-            long long spins = 0;
-            while (az_ld_volatile(flags + d) - seq < 0) { // flags only grow; a neighbour may already be one step ahead
-                if (++spins > (1ll << 31)) { atomicOr(err_flags, AZ_FLAG_HALO); break; } // a neighbour died: report instead of hanging the GPU
-#ifdef AZ_EMU
-                az_emu_yield();
-#endif
-            }
-        }
+        if (D.gr[d + 1] - D.gr[d] - 1 > 0) az_wait_flag(flags + d, seq, err_flags);
     }
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,6 +327,18 @@ az_k_ghost_update_wait(const __grid_constant__ AzDD D, const int* __restrict__ g
     const size_t src = (size_t)(seq & 1) * D.gr[AZ_NDIR] + t;
     pos[s] = az_ld_cg4(stage_pos + src);
     if (therm) therm[s].y = az_ld_cg2(stage_aux + src).y;
+}
+
+// fused halo: sorted ghost index - n_owned -> entry of the receive staging (the inverse of ghostSlot), rebuilt with the list
+static __global__ void __launch_bounds__(AZ_TPB)
+az_k_ghost_entry(const __grid_constant__ AzDD D, const int* __restrict__ ghostSlot, int* __restrict__ ghostEntry)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= D.gr[AZ_NDIR]) return;
+    const int d = az_dir_of(D.gr, t), k = t - D.gr[d];
+    if (k == 0 || k - 1 >= D.cnt->recvCount[d]) return;
+    const int s = ghostSlot[t] - D.cnt->n_owned;
+    if (s >= 0 && s < D.gr[AZ_NDIR]) ghostEntry[s] = t;
 }
 
 // count_cell for the owned and ghost atoms of a brick: global cell from the (wrapped) position, then the

@@ -45,7 +45,14 @@ struct AzPairArgs {
     double* partKE;
     int* blockFlag;          // bricks: 1 if any atom of this 128-atom block lists a ghost (written by az_k_build_list)
     int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
-                             // in flight), 2 = blocks with ghosts (after the halo)
+                             // in flight), 2 = blocks with ghosts (after the halo), 3 = FUSED: one launch, blocks taken in
+                             // blockOrder (ghost-free first); a block that lists ghosts waits for the arrival flags of the
+                             // peer-memory halo and reads ghost positions straight from the receive staging
+    const int* blockOrder;   // phase 3: permutation of the blocks, ghost-free ones first (az_k_block_order)
+    const float4* ghostStage;// phase 3: this step's half of the receive staging (az_halo.cuh)
+    const int* ghostEntry;   // phase 3: sorted ghost index - n_owned -> entry of the staging
+    const int* haloFlags;    // phase 3: arrival flags [27]
+    int haloSeq, haloDirs;   // phase 3: the value the flags must reach; bit d set = direction d is in use
     int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
     float r2_safe;           // packed LJ list pass: |F/r| < MX_FRC for every r2 in [r2_safe, gate] (+inf: always take the clamped form)
     int zc;                  // z-run length per CTA
@@ -654,6 +661,37 @@ az_k_build_list_staged(const __grid_constant__ AzParams P, const __grid_constant
     }
 }
 
+// ghost positions written by a neighbour GPU: read them from L2 (a line of the same staging half may sit stale in L1)
+__device__ __forceinline__ float4 az_ld_cg4g(const float4* p)
+{
+#ifdef AZ_EMU
+    __sync_synchronize();
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+
+// Fused halo: the order in which az_k_pair_list takes its blocks -- those that list no ghost first, so that the blocks which must
+// wait for the neighbours' stores come last and the wait hides behind the rest of the grid.  One block, stable partition.
+static __global__ void __launch_bounds__(1024)
+az_k_block_order(const int* __restrict__ blockFlag, int n, int* __restrict__ order)
+{
+    __shared__ int s_cnt[1024];
+    __shared__ int s_tot;
+    const int t = threadIdx.x, per = (n + 1023) / 1024, b0 = t * per, b1 = min(n, b0 + per);
+    int c = 0;
+    for (int b = b0; b < b1; b++) c += blockFlag[b] ? 0 : 1; // ghost-free blocks in my slice
+    s_cnt[t] = c;
+    __syncthreads();
+    if (t == 0) { int run = 0; for (int k = 0; k < 1024; k++) { const int v = s_cnt[k]; s_cnt[k] = run; run += v; } s_tot = run; }
+    __syncthreads();
+    int free_at = s_cnt[t], ghost_at = s_tot + (b0 < n ? b0 : n) - s_cnt[t]; // ghost blocks before my slice = blocks before - free before
+    for (int b = b0; b < b1; b++) {
+        if (blockFlag[b]) order[ghost_at++] = b; else order[free_at++] = b;
+    }
+}
+
 // read-once global load: no L1 allocation
 __device__ __forceinline__ int az_ld_stream(const int* p)
 {
@@ -699,9 +737,16 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         if (tid == 0) s_done = 0;
         __syncthreads();
     }
-    if (A.phase && ((A.phase == 1) == (A.blockFlag[blockIdx.x] != 0))) return; // the other phase owns this block
-    const int i = blockIdx.x * AZ_LIST_TPB + tid;
-    const bool act = i < az_n_owned(P);
+    const int blk = A.phase == 3 ? A.blockOrder[blockIdx.x] : (int)blockIdx.x;
+    if ((A.phase == 1 || A.phase == 2) && ((A.phase == 1) == (A.blockFlag[blk] != 0))) return; // the other phase owns this block
+    const bool ghost_blk = A.phase == 3 && A.blockFlag[blk] != 0;
+    if (ghost_blk) { // the neighbours' stores for this step must have landed (az_k_ghost_put raises the flags over NVLink)
+        if (tid < 27 && ((A.haloDirs >> tid) & 1)) az_wait_flag(A.haloFlags + tid, A.haloSeq, A.flags);
+        __syncthreads();
+    }
+    const int n_own = az_n_owned(P);
+    const int i = blk * AZ_LIST_TPB + tid;
+    const bool act = i < n_own;
     float fx = 0.f, fy = 0.f, fz = 0.f, ev = 0.f, ec = 0.f, v2 = 0.f;
     double ke = 0.0;
     int hits = 0, ti = 0;
@@ -749,7 +794,8 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         // the list is a pure stream (every row is read once per step): keep it out of L1 so that the gathered
         // positions stay there (B200: 0.3624 -> 0.3575 ms per pass; __ldcs alone 0.3616)
         auto ldidx = [&](const int* p, int) { return az_ld_stream(p); };
-        auto ldpos = [&](int c) { return __ldg(A.pos + c); };
+        // a block that lists ghosts (fused halo) takes them from the receive staging: L2 loads, the neighbour wrote them over NVLink
+        auto ldpos = [&](int c) { return (ghost_blk && c >= n_own) ? az_ld_cg4g(A.ghostStage + A.ghostEntry[c - n_own]) : __ldg(A.pos + c); };
 #endif
         if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
         for (; k + 4 <= cnt; k += 4) {
@@ -764,7 +810,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         }
         for (; k < cnt; k++) {
             const int c = ldidx(row, k); row += stride;
-            const float4 pj = __ldg(A.pos + c);
+            const float4 pj = ldpos(c);
             float radj = 0.f;
             if (RADII) radj = A.therm[c].y;
             plain(pj, radj);
@@ -774,7 +820,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         for (int kb = 0; kb < cntB; kb++) {
             const int c = *rowB; rowB -= stride;
             const int j = c & AZ_NBR_MASK, sc = (int)((unsigned)c >> AZ_NBR_BITS);
-            const float4 pj = __ldg(A.pos + j);
+            const float4 pj = ldpos(j);
             float radj = 0.f;
             if (RADII) radj = A.therm[j].y;
             const float sx = ((float)((sc >> 1) & 1) - (float)(sc & 1)) * P.L[0];
@@ -783,7 +829,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
         };
-        if (PACKED) {
+        if (PACKED && !ghost_blk) { // (a block that reads ghosts from the halo staging takes the scalar form)
             // ---- packed form (one Lennard-Jones entry, no Coulomb): two list rows per FADD2 / FMUL2 / FFMA2.  Each half is
             // the scalar arithmetic of az_vdw_feng<LJ> rounded the same way; the clamp of force_autocap is left out of the
             // loop and the smallest r2 is tracked instead: F/r of this entry stays inside +-MX_FRC for every r2 >= r2_safe
@@ -875,7 +921,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
     if (ENERGY) {
         double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
         az_block_sum<3>(vv, s_red);
-        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+        if (tid == 0) { A.partV[blk] = vv[0]; A.partC[blk] = vv[1]; A.partN[blk] = (unsigned long long)(vv[2] + 0.5); }
     }
     if (A.fuse) {
         // no block barrier (ncu: 10 % of the stall samples sat on it): every warp leaves its sum in shared memory and
@@ -889,7 +935,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
                 double t = 0.0;
 #pragma unroll
                 for (int w = 0; w < AZ_LIST_TPB / 32; w++) t += ((volatile double*)s_kw)[w];
-                A.partKE[blockIdx.x] = 0.5 * t;
+                A.partKE[blk] = 0.5 * t;
             }
         }
         if (A.fuse == 1 + AZ_IA_STALE) { // the fastest atom bounds the drift since the last rebuild

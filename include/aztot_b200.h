@@ -373,7 +373,9 @@ typedef struct az_engine_info_t {
     int capacity;          /* most atoms az_engine_download / az_engine_debug_dump can hand back (a brick's owned capacity) */
     int n_ranks;
     long long graph_replays; /* az_engine_step calls served by replaying a captured CUDA graph (az_cuda_opts.use_graph) */
-    int graphs_cached, reserved;
+    int graphs_cached;
+    int peer_halo;       /* bricks: 0 = the per-step ghost refresh is ncclSend/ncclRecv; 1 = peer memory (NVLink stores + arrival flags);
+                            2 = peer memory fused with the list pass (one launch per step, ghost-touching blocks wait on the flags) */
 } az_engine_info_t;
 int az_engine_info(az_engine *e, az_engine_info_t *out);
 

@@ -190,6 +190,32 @@ def case_bricks_verlet_list_between_rebuilds(lib, devices=None):
     check_against_single(lib, s, 2, (2, 1, 1), nsteps=7, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
 
 
+def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
+    """The per-step ghost refresh has two transports: stores into the neighbour's staging buffer over peer memory with arrival
+    flags (NVLink / NVSwitch; az_k_ghost_put, consumed either by az_k_ghost_update_wait or -- fused -- by the ghost-touching
+    blocks of the list pass themselves, straight from the staging) and ncclSend / ncclRecv.  Same ghosts either way: the
+    three runs agree bit for bit, and each agrees with the single engine.  (Several non-rebuild steps in a row exercise the
+    alternation of the two staging halves; the Verlet-list schedule overlaps the refresh with the ghost-free blocks.)"""
+    import os
+    s = azt.lj_system(ncell=(8, 5, 5), seed=29, cell_size=2.5 * azt.AR_SIGMA + 0.8)
+    runs = {}
+    for tag, env in (("fused", {}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
+        os.environ.update(env)
+        try:
+            runs[tag] = check_against_single(lib, s, 2, (2, 1, 1), nsteps=9, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    assert all(r["info"].peer_halo == 0 for r in runs["sendrecv"])
+    if devices is None:  # emulator: the ranks are threads of one process, peer memory always exists
+        assert all(r["info"].peer_halo == 1 for r in runs["peer"]) and all(r["info"].peer_halo == 2 for r in runs["fused"])
+    for tag in ("fused", "peer"):
+        for a, b in zip(runs[tag], runs["sendrecv"]):
+            assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["dump"]["frc"], b["dump"]["frc"]), tag
+            assert np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
+    print("peer_halo:", [r["info"].peer_halo for r in runs["fused"]], [r["info"].peer_halo for r in runs["peer"]])
+
+
 def case_bricks_migration_hot_atoms(lib, devices=None):
     # hot and fast: atoms cross brick faces every few steps
     s = azt.lj_system(ncell=(8, 5, 5), seed=26, temperature=3000.0)

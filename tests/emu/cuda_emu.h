@@ -213,6 +213,7 @@ static inline double atomicAdd(double* p, double v)
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __sync_synchronize(); } // ranks are host threads: a full barrier
 
 // ----------------------------------------------------------------------------- math / bit casts
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
