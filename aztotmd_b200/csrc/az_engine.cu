@@ -129,7 +129,7 @@ static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage
 static int dd_wait_put(az_engine* e);
 static int dd_sync_ghosts(az_engine* e);
 static int dd_fused_args(az_engine* e, AzPairArgs& A);
-static int dd_block_order(az_engine* e);
+static int dd_join_halo_stream(az_engine* e);
 static int* dd_block_flags(const az_engine* e);
 static void dd_set_overlap(az_engine* e, bool on);
 static int dd_init_counts(az_engine* e, int n_keep);
@@ -820,6 +820,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
         A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg; A.r2_safe = e->r2_safe;
+        A.prune = (e->warp_prune && rebuild) ? 1 : 0; // the atom-to-cell distance test needs cells that are exact for this step's positions
         A.blockFlag = dd_block_flags(e);
         if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
             const bool rb_next = step_rebuilds(e);
@@ -830,12 +831,25 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             e->clear_counts_bytes = (rb_next && !e->dd) ? sizeof(int) * (size_t)(nc + 1) : 0; // clear_clist for the next step's binning
         }
         int rc;
-        if (fusedh) { // put on the halo stream; the list pass reads the ghosts from the staging once the flags are up
+        if (fusedh) {
+            // Fused halo.  Halo stream: put my boundary atoms into the neighbours' staging, then the GHOSTS instantiation of the list
+            // pass for the blocks that list ghosts (it waits for the neighbours' flags itself).  Engine stream: the ghost-free
+            // blocks (phase 1).  The two launches run side by side; the engine's stream joins the halo stream afterwards.
+            if (e->clear_counts_bytes) { // the riders of BOTH launches bin the next step: clear_clist before either starts
+                AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, e->clear_counts_bytes, st));
+                e->clear_counts_bytes = 0;
+            }
+            rc = dd_mark_moved(e);
+            if (rc) return rc;
             rc = dd_put_ghosts(e, c, &A.haloSeq, &A.ghostStage);
             if (rc) return rc;
             rc = dd_fused_args(e, A);
             if (rc) return rc;
             A.phase = 3;
+            rc = az_launch_pair(e, A, want_energy, pair_mode);
+            if (rc) return rc;
+            AZ_COUNT(e, pair_timer, 1);
+            A.phase = 1;
         }
         if (split) { // blocks that list no ghost run while the halo is in flight, the others once it has landed
             A.phase = 1;
@@ -850,8 +864,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         }
         rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
-        if (fusedh) { rc = dd_wait_put(e); if (rc) return rc; } // whatever moves the atoms next comes after the put has read them
-        if (rebuild && dd_fused(e)) { rc = dd_block_order(e); if (rc) return rc; } // the list (and its per-block ghost flags) is new
+        if (fusedh) { rc = dd_join_halo_stream(e); if (rc) return rc; } // finalize, and whatever moves the atoms next, come after both launches
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
         if (ride) { // the new positions / velocities are in the alternate buffers: swap roles
             std::swap(e->pos[c], e->pos_alt);
@@ -1482,6 +1495,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
+    if (!strcmp(key, "warp_prune")) { e->warp_prune = value != 0.0; return AZ_OK; }         // A/B of the per-atom cell pruning in the warp sweep
     if (!strcmp(key, "list_staged")) { e->list_staged = value != 0.0; return AZ_OK; }       // A/B of the two FAST list builds
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;

@@ -45,6 +45,7 @@ struct az_engine {
     bool use_list = false;
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
     int warp_nblocks = 0;     // az_k_pair_warp: one warp per owned atom
+    bool warp_prune = true;   // az_k_pair_warp: drop the stencil cells an atom cannot reach from where it stands
     bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
     float r2_safe = 3.4e38f; // packed Lennard-Jones list pass: below this r2 the reference's force_autocap clamp can act
@@ -54,6 +55,7 @@ struct az_engine {
     std::vector<AzVdw> h_table;
     // device state
     cudaStream_t stream = nullptr;
+    cudaStream_t pair_stream = nullptr; // fused halo: where the ghost-touching blocks of the list pass are launched (the halo stream)
     cudaEvent_t ev[2 * AZ_N_TIMERS] = {};
     cudaEvent_t ev_step[2] = {};
     int cur = 0;

@@ -40,7 +40,7 @@ struct AzDDHost {
     // fused halo (peer memory + Verlet list): ONE list-pass launch per step; ghost-touching blocks come last in blockOrder, wait
     // for the arrival flags and read the ghosts from the staging; nothing scatters them into pos[] unless somebody asks
     bool fused = false;
-    int *blockOrder = nullptr, *ghostEntry = nullptr;
+    int* ghostEntry = nullptr;
     cudaEvent_t ev_put = nullptr;
     bool pos_ghosts_stale = false;        // pos[] still holds the ghost positions of the last scatter (rebuild or dd_sync_ghosts)
     int halo_dirs = 0;
@@ -67,7 +67,7 @@ static void dd_free(az_engine* e)
     cudaFree(h->gSendPos); cudaFree(h->gRecvPos); cudaFree(h->gSendAux); cudaFree(h->gRecvAux); cudaFree(h->mSend); cudaFree(h->mRecv);
     cudaFree(h->blockFlag);
     cudaFree(h->stagePos); cudaFree(h->stageAux); cudaFree(h->haloFlags); cudaFree(h->putDone);
-    cudaFree(h->blockOrder); cudaFree(h->ghostEntry);
+    cudaFree(h->ghostEntry);
     if (h->ev_put) cudaEventDestroy(h->ev_put);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_ghosts) cudaEventDestroy(h->ev_ghosts);
@@ -435,7 +435,6 @@ static int dd_alloc(az_engine* e)
             // the fused single-launch list pass: needs the list (per-block ghost flags) and positions only (radii travel in the aux stream)
             const char* no_fuse = getenv("AZTOT_NO_FUSED_HALO");
             if (e->use_list && !e->use_therm && !(no_fuse && no_fuse[0] == '1')) {
-                AZ_ALLOC(e, h->blockOrder, e->list_nblocks > 0 ? e->list_nblocks : 1);
                 AZ_ALLOC(e, h->ghostEntry, D.gr[AZ_NDIR] > 0 ? D.gr[AZ_NDIR] : 1);
                 AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_put, cudaEventDisableTiming));
                 h->fused = true;
@@ -616,13 +615,16 @@ static bool dd_fused(const az_engine* e) { return e->dd && e->dd->fused && e->dd
 static int dd_fused_args(az_engine* e, AzPairArgs& A)
 {
     AzDDHost* h = e->dd;
-    A.blockOrder = h->blockOrder; A.ghostEntry = h->ghostEntry; A.haloFlags = h->haloFlags; A.haloDirs = h->halo_dirs;
+    A.ghostEntry = h->ghostEntry; A.haloFlags = h->haloFlags; A.haloDirs = h->halo_dirs;
+    e->pair_stream = h->halo_stream;
     return AZ_OK;
 }
-static int dd_block_order(az_engine* e)
+// the GHOSTS launch is the last thing on the halo stream: the engine's stream goes on behind it
+static int dd_join_halo_stream(az_engine* e)
 {
-    AZ_LAUNCH(az_k_block_order, 1, 1024, 0, e->stream, e->dd->blockFlag, e->list_nblocks, e->dd->blockOrder);
-    e->launches++;
+    AzDDHost* h = e->dd;
+    AZ_CUDA(e, cudaEventRecord(h->ev_ghosts, h->halo_stream));
+    AZ_CUDA(e, cudaStreamWaitEvent(e->stream, h->ev_ghosts, 0));
     return AZ_OK;
 }
 static int* dd_block_flags(const az_engine* e) { return e->dd ? e->dd->blockFlag : nullptr; }

@@ -45,15 +45,15 @@ struct AzPairArgs {
     double* partKE;
     int* blockFlag;          // bricks: 1 if any atom of this 128-atom block lists a ghost (written by az_k_build_list)
     int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
-                             // in flight), 2 = blocks with ghosts (after the halo), 3 = FUSED: one launch, blocks taken in
-                             // blockOrder (ghost-free first); a block that lists ghosts waits for the arrival flags of the
-                             // peer-memory halo and reads ghost positions straight from the receive staging
-    const int* blockOrder;   // phase 3: permutation of the blocks, ghost-free ones first (az_k_block_order)
+                             // in flight), 2 = blocks with ghosts (after the halo), 3 = blocks with ghosts in the FUSED halo: the
+                             // GHOSTS instantiation, on the halo stream beside phase 1; it waits for the arrival flags of the
+                             // peer-memory halo itself and reads ghost positions straight from the receive staging
     const float4* ghostStage;// phase 3: this step's half of the receive staging (az_halo.cuh)
     const int* ghostEntry;   // phase 3: sorted ghost index - n_owned -> entry of the staging
     const int* haloFlags;    // phase 3: arrival flags [27]
     int haloSeq, haloDirs;   // phase 3: the value the flags must reach; bit d set = direction d is in use
     int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
+    int prune;               // warp sweep: drop stencil cells the atom itself cannot reach (cells binned this step)
     float r2_safe;           // packed LJ list pass: |F/r| < MX_FRC for every r2 in [r2_safe, gate] (+inf: always take the clamped form)
     int zc;                  // z-run length per CTA
     int nruns;               // ceil(owned nz / zc)
@@ -672,26 +672,6 @@ __device__ __forceinline__ float4 az_ld_cg4g(const float4* p)
 #endif
 }
 
-// Fused halo: the order in which az_k_pair_list takes its blocks -- those that list no ghost first, so that the blocks which must
-// wait for the neighbours' stores come last and the wait hides behind the rest of the grid.  One block, stable partition.
-static __global__ void __launch_bounds__(1024)
-az_k_block_order(const int* __restrict__ blockFlag, int n, int* __restrict__ order)
-{
-    __shared__ int s_cnt[1024];
-    __shared__ int s_tot;
-    const int t = threadIdx.x, per = (n + 1023) / 1024, b0 = t * per, b1 = min(n, b0 + per);
-    int c = 0;
-    for (int b = b0; b < b1; b++) c += blockFlag[b] ? 0 : 1; // ghost-free blocks in my slice
-    s_cnt[t] = c;
-    __syncthreads();
-    if (t == 0) { int run = 0; for (int k = 0; k < 1024; k++) { const int v = s_cnt[k]; s_cnt[k] = run; run += v; } s_tot = run; }
-    __syncthreads();
-    int free_at = s_cnt[t], ghost_at = s_tot + (b0 < n ? b0 : n) - s_cnt[t]; // ghost blocks before my slice = blocks before - free before
-    for (int b = b0; b < b1; b++) {
-        if (blockFlag[b]) order[ghost_at++] = b; else order[free_at++] = b;
-    }
-}
-
 // read-once global load: no L1 allocation
 __device__ __forceinline__ int az_ld_stream(const int* p)
 {
@@ -708,7 +688,12 @@ __device__ __forceinline__ int az_ld_stream(const int* p)
 // it too).  One thread per atom, no atomics, same pair arithmetic and the same r2 <= r2Max gate on
 // current positions as the cell sweep, so the pair set per step is identical to the every-step-rebuild
 // schedule as long as no atom moved more than skin/2 (tracked by az_k_integrate_a / az_k_finalize).
-template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+// GHOSTS = true is the instantiation for the fused halo of a brick (A.phase == 3): it works on the blocks that list ghosts only,
+// waits for the arrival flags of the peer-memory halo and takes ghost positions from the receive staging.  It runs on the halo
+// stream beside the GHOSTS = false launch (phase 1: the ghost-free blocks) of the same step.  Two instantiations rather than one
+// kernel with a block-level branch: the extra live values of the ghost path spilled 108 bytes into the 32-register row loop of
+// EVERY block and made the whole pass 1.8x slower (B200, profiles/r2/bench_n2_fused_spill_v1.json).
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY, bool GHOSTS = false>
 // AZ_LIST_PACKED = 1 selects the f32x2 form of the Lennard-Jones row loop (FADD2 / FMUL2 / FFMA2: 17 issue slots per
 // row instead of 26).  Measured on B200 (profiles/r2/): it is SLOWER -- 0.427 ms per pass at 40 registers / 48 warps per SM,
 // 0.438 ms at 48 / 40, 0.73 ms at 32 / 64 with spills, against 0.385 ms for the scalar loop at 32 registers / 64 warps --
@@ -724,7 +709,7 @@ template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 #ifndef AZ_LIST_LJ_WARPS
 #define AZ_LIST_LJ_WARPS (AZ_LIST_PACKED ? 48 : 64) // resident warps per SM the plain Lennard-Jones form asks for (40 / 32 registers)
 #endif
-__global__ void __launch_bounds__(AZ_LIST_TPB, (VK == AZ_VDW_LJ && CK == AZ_ELEC_NONE && SINGLE && !RADII && !ENERGY) ? AZ_LIST_LJ_WARPS * 32 / AZ_LIST_TPB : 1280 / AZ_LIST_TPB)
+__global__ void __launch_bounds__(AZ_LIST_TPB, (VK == AZ_VDW_LJ && CK == AZ_ELEC_NONE && SINGLE && !RADII && !ENERGY && !GHOSTS) ? AZ_LIST_LJ_WARPS * 32 / AZ_LIST_TPB : 1280 / AZ_LIST_TPB)
 az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
@@ -737,13 +722,13 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         if (tid == 0) s_done = 0;
         __syncthreads();
     }
-    const int blk = A.phase == 3 ? A.blockOrder[blockIdx.x] : (int)blockIdx.x;
-    if ((A.phase == 1 || A.phase == 2) && ((A.phase == 1) == (A.blockFlag[blk] != 0))) return; // the other phase owns this block
-    const bool ghost_blk = A.phase == 3 && A.blockFlag[blk] != 0;
-    if (ghost_blk) { // the neighbours' stores for this step must have landed (az_k_ghost_put raises the flags over NVLink)
+    const int blk = (int)blockIdx.x;
+    if (GHOSTS) {
+        if (A.blockFlag[blk] == 0) return; // phase 1 (the other launch) owns the blocks that list no ghost
+        // the neighbours' stores for this step must have landed (az_k_ghost_put raises the flags over NVLink)
         if (tid < 27 && ((A.haloDirs >> tid) & 1)) az_wait_flag(A.haloFlags + tid, A.haloSeq, A.flags);
         __syncthreads();
-    }
+    } else if (A.phase && ((A.phase == 1) == (A.blockFlag[blk] != 0))) return; // the other phase owns this block
     const int n_own = az_n_owned(P);
     const int i = blk * AZ_LIST_TPB + tid;
     const bool act = i < n_own;
@@ -767,7 +752,7 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
         const int* __restrict__ const rows = A.nbr + az_nbr_base(i, A.nbr_cap);
         // ---- scalar form: every (vdW, Coulomb) combination; the reference's force_autocap clamp on every pair
-        auto scalar_rows = [&]() {
+        auto scalar_rows = [&](auto ldpos) { // ldpos(c): position of neighbour c (plain gather, or ghost-aware in a fused-halo block)
         // one neighbour: pair term from the finished delta, masked accumulate
         auto one = [&](const float dx, const float dy, const float dz, const float4 pj, const float radj) {
             const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
@@ -789,13 +774,13 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 #ifdef AZ_LIST_DBG // diagnostic build only (bench.py --list-dbg): 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
         const int dbg = A.dbg;
         auto ldidx = [&](const int* p, int kk) { return dbg == 2 ? max(0, min(az_n_owned(P) - 1, i + kk - (cnt >> 1))) : *p; };
-        auto ldpos = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : __ldg(A.pos + c); };
+        auto ldpos_dbg = ldpos;
+        auto ldpos2 = [&](int c) { return dbg == 1 ? make_float4(pi.x + 3.f + (float)c * 1e-12f, pi.y + 2.f, pi.z + 1.f, pi.w) : ldpos_dbg(c); };
+#define ldpos ldpos2
 #else
         // the list is a pure stream (every row is read once per step): keep it out of L1 so that the gathered
         // positions stay there (B200: 0.3624 -> 0.3575 ms per pass; __ldcs alone 0.3616)
         auto ldidx = [&](const int* p, int) { return az_ld_stream(p); };
-        // a block that lists ghosts (fused halo) takes them from the receive staging: L2 loads, the neighbour wrote them over NVLink
-        auto ldpos = [&](int c) { return (ghost_blk && c >= n_own) ? az_ld_cg4g(A.ghostStage + A.ghostEntry[c - n_own]) : __ldg(A.pos + c); };
 #endif
         if (cnt >= 4) { c0 = ldidx(row, 0); c1 = ldidx(row + stride, 1); c2 = ldidx(row + 2 * stride, 2); c3 = ldidx(row + 3 * stride, 3); }
         for (; k + 4 <= cnt; k += 4) {
@@ -828,8 +813,15 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             const float sz = ((float)((sc >> 5) & 1) - (float)((sc >> 4) & 1)) * P.L[2];
             one((pi.x - pj.x) - sx, (pi.y - pj.y) - sy, (pi.z - pj.z) - sz, pj, radj);
         }
+#ifdef AZ_LIST_DBG
+#undef ldpos
+#endif
         };
-        if (PACKED && !ghost_blk) { // (a block that reads ghosts from the halo staging takes the scalar form)
+        // the plain gather, or -- GHOSTS -- ghost positions from the receive staging (L2 loads: a neighbour GPU wrote them over NVLink)
+        auto ld_plain = [&](int c) { return __ldg(A.pos + c); };
+        auto ld_ghost = [&](int c) { return c >= n_own ? az_ld_cg4g(A.ghostStage + A.ghostEntry[c - n_own]) : __ldg(A.pos + c); };
+        if (GHOSTS) scalar_rows(ld_ghost);
+        else if (PACKED) { // (a block that reads ghosts from the halo staging takes the scalar form)
             // ---- packed form (one Lennard-Jones entry, no Coulomb): two list rows per FADD2 / FMUL2 / FFMA2.  Each half is
             // the scalar arithmetic of az_vdw_feng<LJ> rounded the same way; the clamp of force_autocap is left out of the
             // loop and the smallest r2 is tracked instead: F/r of this entry stays inside +-MX_FRC for every r2 >= r2_safe
@@ -901,8 +893,8 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
             if (!hot) {
                 fx = az_lo(fx2) + az_hi(fx2); fy = az_lo(fy2) + az_hi(fy2); fz = az_lo(fz2) + az_hi(fz2);
                 if (ENERGY) ev = az_lo(ev2) + az_hi(ev2);
-            } else { hits = 0; scalar_rows(); } // a pair close enough for the clamp (or coincident atoms): the clamped form decides
-        } else scalar_rows();
+            } else { hits = 0; scalar_rows(ld_plain); } // a pair close enough for the clamp (or coincident atoms): the clamped form decides
+        } else scalar_rows(ld_plain);
         const float q = P.charge[ti];
         const float4 f = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
         if (!A.fuse) A.frc[i] = f;
@@ -951,9 +943,14 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 // image and the two loads (first, count) of all cells of a chunk are in flight together instead of one after the
 // other.  Runs of lanes whose ranges are adjacent in memory with the same image (the z neighbours of one column) are
 // merged, then `sweep(first_atom, end_atom, image_code)` is called by all lanes for every merged range.
+// `prune` (cells binned this step only): a stencil cell is also dropped when the ATOM itself is farther than the cut-off from
+// that cell's box -- exact (every atom of the cell is at least that far away; 1e-4 of a cell edge of margin for the rounding
+// of the bin formula), free of divergence here because all lanes of the warp serve the same atom.  The reference's case
+// study 1 bins a 4 A cut-off into 87.8 A cells: 26 of the 27 cells of an atom drop out unless it sits within 4 A of a face.
 template <class F>
 __device__ __forceinline__ void az_warp_stencil_ranges(const AzGrid& g, const int* sten, float r2lim, int gcx, int gcy, int gcz,
-                                                       const int* __restrict__ first, const int* __restrict__ count, int lane, F&& sweep)
+                                                       const int* __restrict__ first, const int* __restrict__ count, int lane, F&& sweep,
+                                                       bool prune = false, float px = 0.f, float py = 0.f, float pz = 0.f)
 {
     const int wy = 2 * sten[1] + 1, wz = 2 * sten[2] + 1;
     const int ncells = (2 * sten[0] + 1) * wy * wz;
@@ -970,7 +967,16 @@ __device__ __forceinline__ void az_warp_stencil_ranges(const AzGrid& g, const in
                 const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
                 const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
                 const float mxy2 = mx * mx + my * my;
-                if (mxy2 <= r2lim && mxy2 + mz * mz <= r2lim) {
+                bool keep = mxy2 <= r2lim && mxy2 + mz * mz <= r2lim;
+                if (keep && prune) { // distance from the atom to the box of the (unwrapped) neighbour cell, per axis
+                    auto gap = [&](int o, int gc, float x, float cs) {
+                        const float d = o > 0 ? (float)(gc + o) * cs - x : (o < 0 ? x - (float)(gc + o + 1) * cs : 0.f);
+                        return fmaxf(0.f, d - 1e-4f * cs);
+                    };
+                    const float gx = gap(ox, gcx, px, g.csize[0]), gy = gap(oy, gcy, py, g.csize[1]), gz = gap(oz, gcz, pz, g.csize[2]);
+                    keep = gx * gx + gy * gy + gz * gz <= r2lim;
+                }
+                if (keep) {
                     const int cid = az_cell_id(g, (sx * g.nl[1] + sy) * g.nl[2] + sz);
                     jb = first[cid];
                     je = jb + count[cid];
@@ -1071,7 +1077,7 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
                 if (j0 + 32 < re) cand(pb, jb, vb);
             }
         };
-        az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep);
+        az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep, A.prune != 0, pi.x, pi.y, pi.z);
     }
     // the 32 shares of atom i (all lanes of a warp belong to the same atom, so the whole warp is in or out)
 #pragma unroll

@@ -30,9 +30,13 @@ static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 {
     // the rider of the list kernel bins the next step: clear_clist comes after everything that still reads this
     // step's counts (the list build just before) and before the kernel that counts again
-    if (e->clear_counts_bytes && A.phase != 2) {
+    if (e->clear_counts_bytes && A.phase != 2 && A.phase != 3) {
         cudaError_t err = cudaMemsetAsync(A.cellCount, 0, e->clear_counts_bytes, e->stream);
         if (err != cudaSuccess) { e->err = std::string("cudaMemsetAsync: ") + cudaGetErrorString(err); return AZ_ERR_CUDA; }
+    }
+    if (A.phase == 3) { // fused halo: the ghost-touching blocks, on the halo stream (no per-atom radii on this path)
+        if constexpr (!RADII) AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY, true>), e->list_nblocks, AZ_LIST_TPB, 0, e->pair_stream ? e->pair_stream : e->stream, e->P, A);
+        return AZ_OK;
     }
     AZ_LAUNCH((az_k_pair_list<VK, CK, SINGLE, RADII, ENERGY>), e->list_nblocks, AZ_LIST_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
