@@ -126,7 +126,7 @@ static bool dd_overlap(const az_engine* e);
 static bool dd_peer_halo(const az_engine* e);
 static bool dd_fused(const az_engine* e);
 static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage_out);
-static int dd_wait_put(az_engine* e);
+static int dd_fork_halo_stream(az_engine* e);
 static int dd_sync_ghosts(az_engine* e);
 static int dd_fused_args(az_engine* e, AzPairArgs& A);
 static int dd_join_halo_stream(az_engine* e);
@@ -832,16 +832,17 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         }
         int rc;
         if (fusedh) {
-            // Fused halo.  Halo stream: put my boundary atoms into the neighbours' staging, then the GHOSTS instantiation of the list
-            // pass for the blocks that list ghosts (it waits for the neighbours' flags itself).  Engine stream: the ghost-free
-            // blocks (phase 1).  The two launches run side by side; the engine's stream joins the halo stream afterwards.
+            // Fused halo.  Engine stream: put my boundary atoms into the neighbours' staging (the GPU is empty: a few microseconds),
+            // then the ghost-free blocks of the list pass (phase 1).  Halo stream, forked behind the put: the GHOSTS instantiation for
+            // the blocks that list ghosts (it waits for the neighbours' flags itself).  The two list launches run side by side;
+            // the engine's stream joins the halo stream afterwards.
             if (e->clear_counts_bytes) { // the riders of BOTH launches bin the next step: clear_clist before either starts
                 AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, e->clear_counts_bytes, st));
                 e->clear_counts_bytes = 0;
             }
-            rc = dd_mark_moved(e);
-            if (rc) return rc;
             rc = dd_put_ghosts(e, c, &A.haloSeq, &A.ghostStage);
+            if (rc) return rc;
+            rc = dd_fork_halo_stream(e);
             if (rc) return rc;
             rc = dd_fused_args(e, A);
             if (rc) return rc;

@@ -562,26 +562,27 @@ static int dd_refresh_ghosts(az_engine* e, int c, bool on_halo_stream)
     return AZ_OK;
 }
 
-// Fused halo, steps between rebuilds: only the put (on the halo stream, behind ev_moved).  The list pass that follows on the
-// engine's stream takes the ghosts from the staging; *seq_out / *stage_out tell it which flags value and which half.
+// Fused halo, steps between rebuilds: only the put, on the ENGINE's stream right behind the kick + drift -- while the GPU is
+// still empty, so that the neighbours see their flags a few microseconds later.  (On the halo stream beside the running list
+// pass the put took 60 us: its blocks had to wait for list blocks to retire, and every neighbour's ghost blocks waited with them.)
+// The list pass that follows takes the ghosts from the staging; *seq_out / *stage_out tell it which flags value and which half.
 static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage_out)
 {
     AzDDHost* h = e->dd;
     const AzDD& D = h->D;
     auto blocks = [](int n) { return (n + AZ_TPB - 1) / AZ_TPB; };
-    AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0));
-    Timer t(e, AZ_TIMER_HALO, h->halo_stream);
+    Timer t(e, AZ_TIMER_HALO);
     const int seq = ++h->halo_seq;
-    AZ_LAUNCH(az_k_ghost_put<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, h->halo_stream, D, h->peerPtr, h->sendList, e->pos[c], (const float2*)nullptr, seq, h->putDone);
-    AZ_CUDA(e, cudaEventRecord(h->ev_put, h->halo_stream));
+    static const int put_dbg = getenv("AZTOT_PUT_DBG") ? atoi(getenv("AZTOT_PUT_DBG")) : 0; // diagnostics of the put kernel's cost
+    AzPeer R = h->peerPtr;
+    if (put_dbg & 2) for (int d = 0; d < AZ_NDIR; d++) if (R.pos[d]) R.pos[d] = h->stagePos; // stores stay on this GPU (results are NOT valid)
+    AZ_LAUNCH(az_k_ghost_put<false>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, e->stream, D, R, h->sendList, e->pos[c], (const float2*)nullptr, seq, h->putDone, put_dbg);
     AZ_COUNT(e, AZ_TIMER_HALO, 1);
     h->pos_ghosts_stale = true;
     *seq_out = seq;
     *stage_out = h->stagePos + (size_t)(seq & 1) * D.gr[AZ_NDIR];
     return AZ_OK;
 }
-// ... and whatever on the engine's stream changes positions next must come after the put has read them
-static int dd_wait_put(az_engine* e) { AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->dd->ev_put, 0)); return AZ_OK; }
 
 // Readers of ghost positions other than the list pass (RDF sampling): scatter the last received ghosts into pos[].  The flags
 // of that refresh have been seen by the list pass that ran on this stream, so no wait is needed.
@@ -617,6 +618,14 @@ static int dd_fused_args(az_engine* e, AzPairArgs& A)
     AzDDHost* h = e->dd;
     A.ghostEntry = h->ghostEntry; A.haloFlags = h->haloFlags; A.haloDirs = h->halo_dirs;
     e->pair_stream = h->halo_stream;
+    return AZ_OK;
+}
+// the halo stream starts its GHOSTS launch behind the put (and the clear_clist memset) of the engine's stream
+static int dd_fork_halo_stream(az_engine* e)
+{
+    AzDDHost* h = e->dd;
+    AZ_CUDA(e, cudaEventRecord(h->ev_moved, e->stream));
+    AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0));
     return AZ_OK;
 }
 // the GHOSTS launch is the last thing on the halo stream: the engine's stream goes on behind it

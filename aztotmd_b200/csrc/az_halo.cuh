@@ -272,7 +272,7 @@ __device__ __forceinline__ int az_ld_volatile(const int* p) { return *(const vol
 template <bool AUX>
 __global__ void __launch_bounds__(AZ_TPB)
 az_k_ghost_put(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R, const int* __restrict__ sendList, const float4* __restrict__ pos,
-               const float2* __restrict__ therm, int seq, int* __restrict__ done)
+               const float2* __restrict__ therm, int seq, int* __restrict__ done, int dbg = 0)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < D.gs[AZ_NDIR]) {
@@ -285,10 +285,12 @@ az_k_ghost_put(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R,
             if (AUX) R.aux[d][dst] = make_float2(0.f, therm[i].y);
         }
     }
-    // completion: the last block to finish raises the flags (all stores of all blocks are visible system-wide before that)
-    __threadfence_system();
+    // completion: the last block to finish raises the flags.  One system-scope fence per BLOCK, by thread 0 behind the block
+    // barrier (fences are cumulative: the stores of the other threads, ordered before the barrier, are covered -- the pattern
+    // of a cooperative grid barrier); a fence in every thread made this kernel take 37 us for 2 MB of stores.
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (!(dbg & 1)) __threadfence_system(); else __threadfence(); // dbg (diagnostics only): device-scope fence per block
         const int ticket = atomicAdd(done, 1);
         if (ticket == (int)gridDim.x - 1) {
             *done = 0;

@@ -1014,8 +1014,11 @@ __device__ __forceinline__ void az_warp_stencil_ranges(const AzGrid& g, const in
 // 125 / 1 250 warps on 148 SMs and each thread walks 500-800 candidates serially (measured: 790 us per step at
 // 4 000 atoms); one warp per atom is 32x the parallelism and 1/32 of the serial chain.
 #define AZ_WARP_TPB 256
+#ifndef AZ_WARP_MINB
+#define AZ_WARP_MINB 1
+#endif
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
-__global__ void __launch_bounds__(AZ_WARP_TPB)
+__global__ void __launch_bounds__(AZ_WARP_TPB, AZ_WARP_MINB)
 az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];

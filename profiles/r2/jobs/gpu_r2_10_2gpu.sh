@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+run() { tag=$1; shift; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 100 --warmup 20 "$@" > gpurun_out/r2_10_bench_n2_$tag.json 2> gpurun_out/r2_10_bench_n2_$tag.err; echo "rc=$?" >> gpurun_out/r2_10_bench_n2_$tag.err; }
+run fused
+AZTOT_NO_FUSED_HALO=1 run peer_nooverlap --no-halo-overlap --no-halo-check
+run fused_b --no-halo-check
+timeout 300 python bench.py --steps 100 --warmup 20 --no-cpu-baseline --no-small-deck --e2e-steps 2 > gpurun_out/r2_10_bench_n1.json 2> gpurun_out/r2_10_bench_n1.err
+timeout 300 python bench.py --workload cs1 --rebuild 1 --steps 2000 --warmup 100 --no-cpu-baseline --e2e-steps 2 --graph > gpurun_out/r2_10_bench_cs1_graph.json 2> gpurun_out/r2_10_bench_cs1_graph.err
+echo done
