@@ -14,7 +14,7 @@ AZ_MAX_SPECIES = 15
 AZ_N_UVECT = 3072
 AZ_N_MOM = 20
 AZ_MX_FRC = 1.0e4
-AZ_N_TIMERS = 8
+AZ_N_TIMERS = 9
 
 AZ_OK = 0
 AZ_ERR_INVALID, AZ_ERR_NO_DEVICE, AZ_ERR_CUDA, AZ_ERR_UNSUPPORTED = -1, -2, -3, -4
@@ -28,7 +28,7 @@ VDW_BY_NAME = {"lnjs": VDW_LJ, "buck": VDW_BUCK, "p746": VDW_P746, "bmhs": VDW_B
 ELEC_NONE, ELEC_DIRECT, ELEC_EWALD, ELEC_FENNEL = range(4)
 TSTAT_NONE, TSTAT_NOSE, TSTAT_RADI = range(3)
 ORDER_SORTED, ORDER_ORIGINAL = 0, 1
-TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo", "pair_list", "ewald"]
+TIMER_NAMES = ["integrate_a", "scan", "sort", "pair", "integrate_b", "halo", "pair_list", "ewald", "migrate"]
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -89,7 +89,7 @@ class az_cuda_opts(C.Structure):
     _fields_ = [("device", C.c_int), ("rebuild_every", C.c_int), ("skin", C.c_float), ("use_graph", C.c_int),
                 ("pair_variant", C.c_int), ("cells_per_block", C.c_int), ("rank", C.c_int), ("n_ranks", C.c_int),
                 ("pgrid", C.c_int * 3), ("ghost_slots", C.c_int), ("nccl_id", C.c_void_p),
-                ("max_neigh", C.c_int), ("reserved", C.c_int * 7)]
+                ("max_neigh", C.c_int), ("list_format", C.c_int), ("tile_atoms", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class az_stats(C.Structure):
@@ -121,7 +121,9 @@ class az_engine_info_t(C.Structure):
                 ("pair_smem_bytes", C.c_int), ("pair_zc", C.c_int), ("pair_vk", C.c_int), ("pair_ck", C.c_int),
                 ("n_sm", C.c_int), ("max_neigh_seen", C.c_int), ("device_bytes", C.c_longlong),
                 ("list_rows", C.c_int), ("flags", C.c_int), ("capacity", C.c_int), ("n_ranks", C.c_int),
-                ("graph_replays", C.c_longlong), ("graphs_cached", C.c_int), ("peer_halo", C.c_int)]
+                ("graph_replays", C.c_longlong), ("graphs_cached", C.c_int), ("peer_halo", C.c_int),
+                ("tile_list", C.c_int), ("tile_atoms", C.c_int), ("tile_rows_smem", C.c_int),
+                ("tile_atoms_seen", C.c_int), ("tile_runs_seen", C.c_int), ("reserved", C.c_int)]
 
 
 # every symbol include/aztot_b200.h declares: name -> (restype, argtypes)

@@ -466,6 +466,8 @@ extern "C" int az_deck_load(const char* dir, uint64_t seed, az_deck** out)
         if (scan_first(f, " graph %d", &v)) d->opts.use_graph = v;
         else d->opts.use_graph = (n < 100000) ? 1 : 0;
         if (scan_first(f, " device %d", &v)) d->opts.device = v;
+        if (scan_first(f, " list_format %d", &v) && v >= 0 && v <= 2) d->opts.list_format = v; // 1 = global rows, 2 = tile lists (include/aztot_b200.h)
+        if (scan_first(f, " tile_atoms %d", &v) && v > 0) d->opts.tile_atoms = v;
     }
     fclose(f); f = nullptr;
 

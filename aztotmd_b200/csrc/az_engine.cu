@@ -125,6 +125,12 @@ static int dd_mark_moved(az_engine* e);
 static bool dd_overlap(const az_engine* e);
 static bool dd_peer_halo(const az_engine* e);
 static bool dd_fused(const az_engine* e);
+static bool dd_direct(const az_engine* e);
+static int dd_put_direct(az_engine* e, int c, AzPairArgs* A);
+static int dd_order_blocks(az_engine* e);
+static int dd_join_put(az_engine* e);
+static bool dd_direct_ok(az_engine* e, int c);
+static void dd_note_step_buffer(az_engine* e, int c);
 static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage_out);
 static int dd_fork_halo_stream(az_engine* e);
 static int dd_sync_ghosts(az_engine* e);
@@ -379,8 +385,10 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
         const double rl = sqrt((double)e->P.r2list);
         const double vol = (double)e->P.L[0] * e->P.L[1] * e->P.L[2];
         int cap = (o && o->max_neigh > 0) ? o->max_neigh : 0;
-        if (cap <= 0) {
-            // rows from the densest region of the initial configuration: bins of edge >= r_list
+        double rho = 0.0;
+        const double rho_avg = (double)e->n_global / vol;
+        {
+            // the densest region of the initial configuration: bins of edge >= r_list
             int nb3[3]; double inv[3];
             for (int a = 0; a < 3; a++) { nb3[a] = (int)floor((double)e->P.L[a] / rl); if (nb3[a] < 1) nb3[a] = 1; if (nb3[a] > 256) nb3[a] = 256; inv[a] = nb3[a] / (double)e->P.L[a]; }
             std::vector<int> bins((size_t)nb3[0] * nb3[1] * nb3[2], 0);
@@ -392,16 +400,55 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
                 int v = ++bins[((size_t)c[0] * nb3[1] + c[1]) * nb3[2] + c[2]];
                 if (v > mx) mx = v;
             }
-            double rho = mx * inv[0] * inv[1] * inv[2];
-            double rho_avg = (double)e->n_global / vol;
+            rho = mx * inv[0] * inv[1] * inv[2];
             if (rho < rho_avg) rho = rho_avg;
-            cap = (int)(1.5 * rho * 4.18879 * rl * rl * rl) + 32;
         }
+        if (cap <= 0) cap = (int)(1.5 * rho * 4.18879 * rl * rl * rl) + 32; // rows from that density
+        cap = (cap + 1) & ~1; // tile lists pack two rows per word
         if (cap >= (1 << AZ_NBR_CNT_BITS) / 2) { AZ_SET_ERR(e, "max_neigh %d is beyond the list format (%d rows)", cap, (1 << AZ_NBR_CNT_BITS) / 2 - 1); return AZ_ERR_INVALID; }
         e->nbr_cap = cap;
         e->nbr_stride = (capo + 31) / 32 * 32;
         AZ_ALLOC(e, e->nbr, (size_t)e->nbr_cap * e->nbr_stride);
         AZ_ALLOC(e, e->nbrCount, capo);
+        // Tile lists (az_tlist.cuh; list_format: 0 = auto = 1, 1 = global 32-bit rows, 2 = tile lists).  The footprint of a tile in
+        // a region with `a` atoms per cell is (2sx+1)(2sy+1) columns x (128 / a + 1 + 2sz cells [+ 2sz ghost cells when z is
+        // decomposed]) x a atoms; it grows with a, so the densest region sizes it.  10 % + 32 atoms of margin; a system that
+        // is smaller than that is simply held whole.
+        {
+            const AzGrid& g = e->P.g;
+            const double a_max = rho * (double)g.csize[0] * g.csize[1] * g.csize[2];
+            const double zcells = 1.0 + 2.0 * g.sten[2] * (g.dec[2] ? 2.0 : 1.0);
+            double foot = (2.0 * g.sten[0] + 1.0) * (2.0 * g.sten[1] + 1.0) * ((double)AZ_LIST_TPB + zcells * a_max);
+            int fc = (o && o->tile_atoms > 0) ? o->tile_atoms : (int)(1.10 * foot) + 32;
+            e->tl_user_cap = o && o->tile_atoms > 0;
+            if (fc > capt || capt <= 4096) fc = capt;
+            fc = (fc + 31) & ~31;
+            e->tl_foot_alloc = (capt + 31) & ~31;
+            e->tl_stride = (e->pair_single && !e->pair_radii) ? 3 : 5; // words per atom of the shared-memory footprint (az_k_pair_tlist)
+            const int bytes_per_atom = 4 * e->tl_stride;
+            const int lf = o ? o->list_format : 0;
+            e->tl_foot_cap = fc;
+            e->tl_smem_pass = (size_t)fc * bytes_per_atom;
+            int rs = (int)(1.25 * rho * 4.18879 * rl * rl * rl) + 8;
+            if (rs < 32) rs = 32;
+            if (rs > cap) rs = cap;
+            rs = (rs + 1) & ~1;
+            e->tl_rows_smem = rs;
+            e->tl_smem_build = (size_t)rs * AZ_LIST_TPB * sizeof(unsigned short);
+            const size_t smem_max = 200 * 1024;
+            const bool fits = (long long)(fc - 1) * e->tl_stride <= 65535 && e->tl_smem_pass <= smem_max && e->tl_smem_build <= smem_max;
+            if (lf == 2 && !fits) { AZ_SET_ERR(e, "list_format 2 (tile lists): a footprint of %d atoms does not fit shared memory", fc); return AZ_ERR_UNSUPPORTED; }
+            e->use_tlist = lf == 2 && fits; // auto = global rows: measured faster on B200 (az_tlist.cuh)
+            const int cap2 = (e->nbr_cap + 1) / 2;
+            if (lf == 2) { // (the A/B switch "tile_list" works on engines created with list_format 2)
+            AZ_ALLOC(e, e->nbr16, (size_t)cap2 * e->nbr_stride + 512); // (+ slack: the row loop requests eight rows ahead)
+            AZ_ALLOC(e, e->tileHdr, e->list_nblocks);
+            AZ_ALLOC(e, e->tileRuns, (size_t)e->list_nblocks * AZ_TL_RUNS);
+            AZ_ALLOC(e, e->tlStat, 4);
+            AZ_CUDA(e, cudaMemset(e->tlStat, 0, 4 * sizeof(int)));
+            AZ_CUDA(e, cudaMemset(e->tileHdr, 0, sizeof(int) * e->list_nblocks));
+            }
+        }
     }
     // pair_variant: 0 auto (list between rebuilds; warp-per-atom sweep on the every-step schedule), 1 = shared-memory
     // cell tiles only, 2 = list, 3 = warp-per-atom sweep
@@ -566,7 +613,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     cudaFree(e->ew_ak); cudaFree(e->ew_pairs); cudaFree(e->ew_runs); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
-    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount); cudaFree(e->nbr16); cudaFree(e->tileHdr); cudaFree(e->tileRuns); cudaFree(e->tlStat);
     cudaFree(e->rdf_hist); cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     cudaFree(e->whereId); cudaFree(e->bStart); cudaFree(e->aStart); cudaFree(e->bEnt); cudaFree(e->aEnt); cudaFree(e->bTypes); cudaFree(e->aTypes);
     cudaFree(e->partBond); cudaFree(e->partAngle); cudaFree(e->dl_buf);
@@ -587,7 +634,7 @@ extern "C" void az_engine_destroy(az_engine* e)
 struct az_nvtx_range {
     explicit az_nvtx_range(int k)
     {
-        static const char* names[AZ_N_TIMERS] = { "az:integrate_a", "az:scan", "az:sort", "az:pair", "az:integrate_b", "az:halo", "az:pair_list", "az:ewald" };
+        static const char* names[AZ_N_TIMERS] = { "az:integrate_a", "az:scan", "az:sort", "az:pair", "az:integrate_b", "az:halo", "az:pair_list", "az:ewald", "az:migrate" };
         nvtxRangePushA(k >= 0 && k < AZ_N_TIMERS ? names[k] : "az:section");
     }
     ~az_nvtx_range() { nvtxRangePop(); }
@@ -803,12 +850,19 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         e->since_rebuild = 0;
     } else {
         e->since_rebuild++;
-        if (e->dd) { int rc = (dd_overlap(e) || dd_fused(e)) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
+        if (e->dd && dd_direct(e)) {
+            // direct halo needs a position stream that was NOT the current one of the previous step (a neighbour that is one step
+            // behind still reads its ghost slots there): true whenever the integrator rode on the previous list pass; the first
+            // step of a call drifts in place, and then the ghosts take the staged route (peer put + scatter) for that step
+            if (!dd_direct_ok(e, c)) { int rc = dd_refresh_ghosts(e, c, false); if (rc) return rc; }
+        } else if (e->dd) { int rc = (dd_overlap(e) || dd_fused(e)) ? dd_mark_moved(e) : dd_refresh_ghosts(e, c, false); if (rc) return rc; }
     }
     // the integrator rides on the list kernel when the next step's kick may follow this step's forces directly
     const bool ride = fuse_next && e->fuse_pair && !eq_step;
+    const bool directh = !rebuild && dd_direct(e) && dd_direct_ok(e, c); // direct halo: boundary atoms stored into the neighbours' position streams, ONE plain list launch
     const bool fusedh = !rebuild && dd_fused(e);  // peer-memory halo: one list launch, ghost-touching blocks last, waiting on arrival flags
-    const bool split = !rebuild && !fusedh && dd_overlap(e); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
+    const bool split = !rebuild && !fusedh && !directh && dd_overlap(e);
+    dd_note_step_buffer(e, c); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
     { // K4: pair forces
         const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
@@ -820,6 +874,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.zc = e->pair_zc; A.nruns = e->pair_nruns; A.tile_cap = e->pair_tile_cap;
         A.single = e->h_table[0]; A.table = e->table;
         A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg; A.r2_safe = e->r2_safe;
+        A.nbr16 = e->nbr16; A.tileHdr = e->tileHdr; A.tileRuns = e->tileRuns; A.tlStat = e->tlStat; A.tl_rows_smem = e->tl_rows_smem; A.tl_foot_cap = e->tl_foot_cap; A.tl_stride = e->tl_stride;
+        A.n_total = e->dd ? e->cap_total_dd : e->n;
         A.prune = (e->warp_prune && rebuild) ? 1 : 0; // the atom-to-cell distance test needs cells that are exact for this step's positions
         A.blockFlag = dd_block_flags(e);
         if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
@@ -831,6 +887,11 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             e->clear_counts_bytes = (rb_next && !e->dd) ? sizeof(int) * (size_t)(nc + 1) : 0; // clear_clist for the next step's binning
         }
         int rc;
+        if (directh) { // (the put could not come earlier: it needs the drift of this step, which may have been the previous pass's rider)
+            rc = dd_put_direct(e, c, &A);
+            if (rc) return rc;
+            A.phase = 4;
+        }
         if (fusedh) {
             // Fused halo.  Engine stream: put my boundary atoms into the neighbours' staging (the GPU is empty: a few microseconds),
             // then the ghost-free blocks of the list pass (phase 1).  Halo stream, forked behind the put: the GHOSTS instantiation for
@@ -866,6 +927,8 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         rc = az_launch_pair(e, A, want_energy, pair_mode);
         if (rc) return rc;
         if (fusedh) { rc = dd_join_halo_stream(e); if (rc) return rc; } // finalize, and whatever moves the atoms next, come after both launches
+        if (directh) { rc = dd_join_put(e); if (rc) return rc; }
+        if (rebuild && e->use_list && dd_direct(e)) { rc = dd_order_blocks(e); if (rc) return rc; }
         AZ_COUNT(e, pair_timer, pair_mode == AZ_PAIR_MODE_TILE_LIST ? 2 : 1);
         if (ride) { // the new positions / velocities are in the alternate buffers: swap roles
             std::swap(e->pos[c], e->pos_alt);
@@ -1011,6 +1074,34 @@ static az_engine::GraphEnd graph_end_state(const az_engine* e)
 }
 #endif
 
+// Tile lists: fit the shared-memory allotments (footprint of the force pass, row columns of the build) to what the rebuilds
+// have actually seen.  They are launch parameters, not allocations: the create-time values come from a density estimate
+// that has to be generous (a lattice start makes the densest bin twice the average), and shared memory per CTA is what
+// bounds the resident warps of both kernels.  Called once behind the first rebuild (one stream synchronisation, never
+// again on the step path) and -- grow only -- from az_engine_stats, which synchronises anyway.  12 % + 32 atoms of
+// margin over the largest footprint seen; a rebuild that outgrows it raises AZ_FLAG_FOOT.
+static int tl_autotune(az_engine* e, bool shrink)
+{
+    if (!e->use_list || !e->use_tlist || !e->tlStat || e->tl_user_cap) return AZ_OK;
+    int st[4] = { 0, 0, 0, 0 };
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    AZ_CUDA(e, cudaMemcpy(st, e->tlStat, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[0] <= 0) return AZ_OK;
+    const int bytes_per_atom = 4 * e->tl_stride;
+    int fc = ((int)(1.12 * st[0]) + 32 + 31) & ~31;
+    const int fc_max = std::min(65535 / e->tl_stride + 1, (200 * 1024) / bytes_per_atom) & ~31;
+    if (fc > fc_max) fc = fc_max;
+    if (fc > e->tl_foot_alloc) fc = e->tl_foot_alloc; // (never more than the whole system)
+    int rs = (st[3] + 8 + 1) & ~1;
+    if (rs < 32) rs = 32;
+    if (rs > e->nbr_cap) rs = e->nbr_cap;
+    if (!shrink) { fc = std::max(fc, e->tl_foot_cap); rs = std::max(rs, e->tl_rows_smem); }
+    e->tl_foot_cap = fc; e->tl_smem_pass = (size_t)fc * bytes_per_atom;
+    e->tl_rows_smem = rs; e->tl_smem_build = (size_t)rs * AZ_LIST_TPB * sizeof(unsigned short);
+    e->tl_tuned = true;
+    return AZ_OK;
+}
+
 extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
 {
     if (!e) return AZ_ERR_INVALID;
@@ -1020,6 +1111,7 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         int rc = run_steps(e, first_step, nsteps);
         if (rc) return rc;
         AZ_CUDA(e, cudaGetLastError());
+        if (!e->tl_tuned && e->binned && nsteps > 0) { rc = tl_autotune(e, true); if (rc) return rc; }
         return AZ_OK;
     }
     // graph mode: the kernels take their step from the device (*step0_dev + index inside the call)
@@ -1118,6 +1210,13 @@ static int check_flags(az_engine* e, int flags, int worst_row)
     if (flags & AZ_FLAG_SKIN) { AZ_SET_ERR(e, "atoms drifted more than skin/2 between cell-list rebuilds (skin %g): raise 'skin' or lower 'rebuild'", e->P.skin); return AZ_ERR_OVERFLOW; }
     if (flags & AZ_FLAG_TILE) { AZ_SET_ERR(e, "a cell holds more atoms than the pair kernel's shared tile (%d)", e->pair_tile_cap); return AZ_ERR_OVERFLOW; }
     if (flags & AZ_FLAG_NBR) { AZ_SET_ERR(e, "an atom has more than %d neighbours inside the list radius (worst row: %d): raise 'max_neigh'", e->nbr_cap, worst_row); return AZ_ERR_OVERFLOW; }
+    if (flags & AZ_FLAG_FOOT) {
+        int st[4] = { 0, 0, 0, 0 };
+        if (e->tlStat) cudaMemcpy(st, e->tlStat, sizeof(st), cudaMemcpyDeviceToHost);
+        AZ_SET_ERR(e, "tile lists: the neighbourhood of a 128-atom tile outgrew its shared-memory allotment (%d atoms in %d runs seen, room for %d atoms / %d runs): raise 'tile_atoms' or set 'list_format 1'",
+                   st[0], st[1], e->tl_foot_cap, AZ_TL_RUNS);
+        return AZ_ERR_OVERFLOW;
+    }
     if (flags & AZ_FLAG_HALO) { AZ_SET_ERR(e, "a halo / migration message or the brick's atom capacity overflowed, or an atom crossed more than one ghost shell in a step"); return AZ_ERR_OVERFLOW; }
     return AZ_OK;
 }
@@ -1129,6 +1228,7 @@ extern "C" int az_engine_stats(az_engine* e, az_stats* o)
     int rc = fetch_scalars(e, &h);
     if (rc) return rc;
     if (!e->dd) { rc = check_flags(e, h.overflow, h.dbg_count); if (rc) return rc; }
+    if (e->tl_tuned && !e->use_graph) { rc = tl_autotune(e, false); if (rc) return rc; } // a system that densifies: grow the allotments in time
     memset(o, 0, sizeof(*o));
     o->step = e->last_step;
     o->n_atoms_total = e->n_global;
@@ -1497,6 +1597,10 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
     if (!strcmp(key, "warp_prune")) { e->warp_prune = value != 0.0; return AZ_OK; }         // A/B of the per-atom cell pruning in the warp sweep
+    if (!strcmp(key, "tile_list")) { // A/B of the two list formats; before the first step (the next rebuild writes the chosen format)
+        if (value != 0.0 && (!e->nbr16 || (long long)(e->tl_foot_cap - 1) * e->tl_stride > 65535 || e->tl_smem_pass > 200 * 1024)) { AZ_SET_ERR(e, "tile lists are not available for this engine"); return AZ_ERR_UNSUPPORTED; }
+        e->use_tlist = value != 0.0; e->binned = false; return AZ_OK;
+    }
     if (!strcmp(key, "list_staged")) { e->list_staged = value != 0.0; return AZ_OK; }       // A/B of the two FAST list builds
     AZ_SET_ERR(e, "unknown option '%s'", key);
     return AZ_ERR_INVALID;
@@ -1513,9 +1617,17 @@ extern "C" int az_engine_info(az_engine* e, az_engine_info_t* o)
     o->pair_zc = e->pair_zc; o->pair_vk = e->pair_vk; o->pair_ck = e->pair_ck;
     o->n_sm = e->n_sm; o->device_bytes = (long long)e->dev_bytes;
     o->list_rows = e->nbr_cap;
+    o->tile_list = (e->use_list && e->use_tlist) ? 1 : 0; o->tile_atoms = e->tl_foot_cap; o->tile_rows_smem = e->tl_rows_smem;
+    if (e->tlStat) {
+        int st[4] = { 0, 0, 0, 0 };
+        AZ_CUDA(e, cudaSetDevice(e->device));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        AZ_CUDA(e, cudaMemcpy(st, e->tlStat, sizeof(st), cudaMemcpyDeviceToHost));
+        o->tile_atoms_seen = st[0]; o->tile_runs_seen = st[1];
+    }
     o->capacity = e->dd ? e->P.n_local : e->n; o->n_ranks = e->n_ranks;
     o->graph_replays = e->graph_replays; o->graphs_cached = (int)e->graphs.size();
-    o->peer_halo = dd_peer_halo(e) ? (e->dd->fused ? 2 : 1) : 0;
+    o->peer_halo = dd_peer_halo(e) ? (e->dd->direct ? 3 : (e->dd->fused ? 2 : 1)) : 0;
     if (e->sc) {
         AZ_CUDA(e, cudaSetDevice(e->device));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -52,6 +52,16 @@ struct az_engine {
     bool list_staged = false; // az_k_build_list_staged (rows staged in shared memory, lockstep flush): measured slower, kept for the A/B (az_pair.cuh)
     bool list_fast = false; // every axis has more than 2*sten cells: az_k_build_list prunes by atom position and walks z-intervals
     int *nbr = nullptr, *nbrCount = nullptr;
+    // tile lists (az_tlist.cuh): the list format of the Verlet-list path unless list_format 1 asks for the global rows
+    bool use_tlist = false;
+    unsigned* nbr16 = nullptr;
+    int *tileHdr = nullptr, *tlStat = nullptr;
+    int4* tileRuns = nullptr;
+    bool tl_user_cap = false; // az_cuda_opts.tile_atoms was given: no fitting
+    int tl_foot_alloc = 0;    // the whole system, rounded up: no footprint is larger
+    bool tl_tuned = false; // the shared-memory allotments have been fitted to what the first rebuild saw
+    int tl_foot_cap = 0, tl_rows_smem = 0, tl_stride = 3;
+    size_t tl_smem_pass = 0, tl_smem_build = 0;
     std::vector<AzVdw> h_table;
     // device state
     cudaStream_t stream = nullptr;

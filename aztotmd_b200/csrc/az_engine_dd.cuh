@@ -42,6 +42,13 @@ struct AzDDHost {
     bool fused = false;
     int* ghostEntry = nullptr;
     cudaEvent_t ev_put = nullptr;
+    // direct halo (az_halo.cuh): boundary atoms are stored straight into the neighbours' sorted position streams
+    bool direct = false;
+    int* remoteSlot = nullptr;            // [gs total] where my k-th atom for direction d sits in that neighbour's streams
+    int* blockOrder = nullptr;            // launch order of the list blocks: ghost-free ones first
+    int slot_epoch = 0;                   // rebuilds so far; the same on all ranks
+    int prev_step_buf = -1;               // number of the position stream the previous step's force pass read
+    float4* pos_bufs[3] = { nullptr, nullptr, nullptr }; // my three position streams by number
     bool pos_ghosts_stale = false;        // pos[] still holds the ghost positions of the last scatter (rebuild or dd_sync_ghosts)
     int halo_dirs = 0;
     int n_create = 0;      // length of the create-time arrays (az_engine_upload takes arrays of the same shape)
@@ -65,7 +72,7 @@ static void dd_free(az_engine* e)
     if (!h) return;
     cudaFree(h->cellmap); cudaFree(h->stay); cudaFree(h->newIndex); cudaFree(h->sendList); cudaFree(h->ghostSlot); cudaFree(h->migList);
     cudaFree(h->gSendPos); cudaFree(h->gRecvPos); cudaFree(h->gSendAux); cudaFree(h->gRecvAux); cudaFree(h->mSend); cudaFree(h->mRecv);
-    cudaFree(h->blockFlag);
+    cudaFree(h->blockFlag); cudaFree(h->remoteSlot); cudaFree(h->blockOrder);
     cudaFree(h->stagePos); cudaFree(h->stageAux); cudaFree(h->haloFlags); cudaFree(h->putDone);
     cudaFree(h->ghostEntry);
     if (h->ev_put) cudaEventDestroy(h->ev_put);
@@ -418,17 +425,22 @@ static int dd_alloc(az_engine* e)
     const char* no_p2p = getenv("AZTOT_NO_PEER_HALO");
     if (!(no_p2p && no_p2p[0] == '1')) {
         AZ_ALLOC(e, h->stagePos, (size_t)2 * D.gr[AZ_NDIR]); AZ_ALLOC(e, h->stageAux, (size_t)2 * D.gr[AZ_NDIR]);
-        AZ_ALLOC(e, h->haloFlags, AZ_NDIR); AZ_ALLOC(e, h->putDone, 1);
-        void* local[3] = { h->stagePos, h->stageAux, h->haloFlags };
+        AZ_ALLOC(e, h->haloFlags, 2 * AZ_NDIR); AZ_ALLOC(e, h->putDone, 2);
+        AZ_ALLOC(e, h->remoteSlot, D.gs[AZ_NDIR] > 0 ? D.gs[AZ_NDIR] : 1);
+        AZ_ALLOC(e, h->blockOrder, e->list_nblocks > 0 ? e->list_nblocks : 1);
+        h->pos_bufs[0] = e->pos[0]; h->pos_bufs[1] = e->pos[1]; h->pos_bufs[2] = e->pos_alt ? e->pos_alt : e->pos[0];
+        void* local[7] = { h->stagePos, h->stageAux, h->haloFlags, h->remoteSlot, h->pos_bufs[0], h->pos_bufs[1], h->pos_bufs[2] };
         std::vector<void*> remote;
-        const int rc = h->comm->share(local, 3, &remote);
+        const int rc = h->comm->share(local, 7, &remote);
         if (rc == AZ_OK) {
             for (int dir = 0; dir < AZ_NDIR; dir++) {
                 const int pr = h->peer[dir];
                 if (pr < 0) continue;
-                h->peerPtr.pos[dir] = (float4*)remote[(size_t)pr * 3 + 0];
-                h->peerPtr.aux[dir] = (float2*)remote[(size_t)pr * 3 + 1];
-                h->peerPtr.flags[dir] = (int*)remote[(size_t)pr * 3 + 2];
+                h->peerPtr.pos[dir] = (float4*)remote[(size_t)pr * 7 + 0];
+                h->peerPtr.aux[dir] = (float2*)remote[(size_t)pr * 7 + 1];
+                h->peerPtr.flags[dir] = (int*)remote[(size_t)pr * 7 + 2];
+                h->peerPtr.slot[dir] = (int*)remote[(size_t)pr * 7 + 3];
+                for (int b = 0; b < 3; b++) h->peerPtr.pbuf[dir][b] = (float4*)remote[(size_t)pr * 7 + 4 + b];
             }
             h->p2p = true;
             for (int dir = 0; dir < AZ_NDIR; dir++) if (h->peer[dir] >= 0) h->halo_dirs |= 1 << dir;
@@ -438,6 +450,10 @@ static int dd_alloc(az_engine* e)
                 AZ_ALLOC(e, h->ghostEntry, D.gr[AZ_NDIR] > 0 ? D.gr[AZ_NDIR] : 1);
                 AZ_CUDA(e, cudaEventCreateWithFlags(&h->ev_put, cudaEventDisableTiming));
                 h->fused = true;
+                // ... or, better, no staging at all: the direct halo (positions only, the integrator riding on the list kernel
+                // or not -- the buffer rotation is the same on all ranks either way)
+                const char* no_direct = getenv("AZTOT_NO_DIRECT_HALO");
+                if (!(no_direct && no_direct[0] == '1')) h->direct = true;
             }
         } else if (rc != AZ_ERR_UNSUPPORTED) { e->err = h->comm->err; return rc; }
     }
@@ -477,7 +493,7 @@ static int dd_rebuild(az_engine* e, int c)
     int* flags = &e->sc->overflow;
     float2* th = e->use_therm ? e->therm[c] : nullptr;
     {
-        Timer t(e, AZ_TIMER_HALO);
+        Timer t(e, AZ_TIMER_MIGRATE);
         AZ_LAUNCH(az_k_dd_begin_rebuild, 1, 32, 0, st, D);
         AZ_LAUNCH(az_k_mig_classify, nbo, AZ_TPB, 0, st, P, D, e->pos[c], h->migList, h->stay, flags);
         AZ_LAUNCH(az_k_mig_pack, blocks(D.ms[AZ_NDIR]), AZ_TPB, 0, st, D, h->migList, e->pos[c], e->vel[c], e->id[c], th, h->mSend);
@@ -496,7 +512,7 @@ static int dd_rebuild(az_engine* e, int c)
         rc = dd_exchange(e, ops);
         if (rc) return rc;
         AZ_LAUNCH(az_k_ghost_append, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->gRecvPos, h->gRecvAux, e->pos[c], e->vel[c], e->id[c], th, h->stay, flags);
-        AZ_COUNT(e, AZ_TIMER_HALO, 7);
+        AZ_COUNT(e, AZ_TIMER_MIGRATE, 7);
     }
     const int nc = P.g.ncell_local;
     {
@@ -518,7 +534,8 @@ static int dd_rebuild(az_engine* e, int c)
             AZ_LAUNCH(az_k_sort_scatter<false>, nbt, AZ_TPB, 0, st, D.cap_total, ntot, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
                       e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, h->newIndex, (int*)nullptr);
         const int nmax = D.gs[AZ_NDIR] > D.gr[AZ_NDIR] ? D.gs[AZ_NDIR] : D.gr[AZ_NDIR];
-        AZ_LAUNCH(az_k_dd_remap, blocks(nmax), AZ_TPB, 0, st, D, h->newIndex, h->sendList, h->ghostSlot);
+        h->slot_epoch++;
+        AZ_LAUNCH(az_k_dd_remap, blocks(nmax), AZ_TPB, 0, st, D, h->newIndex, h->sendList, h->ghostSlot, h->peerPtr, h->direct ? 1 : 0, h->slot_epoch, h->putDone + 1);
         AZ_LAUNCH(az_k_dd_publish, 1, 1, 0, st, D, e->first, h->n_owned_cells, nc);
         if (h->fused) { AZ_LAUNCH(az_k_ghost_entry, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->ghostSlot, h->ghostEntry); AZ_COUNT(e, AZ_TIMER_SORT, 1); }
         h->pos_ghosts_stale = false; // the ghosts were appended to pos[] just now
@@ -584,6 +601,51 @@ static int dd_put_ghosts(az_engine* e, int c, int* seq_out, const float4** stage
     return AZ_OK;
 }
 
+// Direct halo, steps between rebuilds: my boundary atoms go straight into the ghost slots of the neighbours' current position
+// stream (the one with the same number as mine), then the arrival flags.  On the engine's stream behind the kick + drift.
+static int dd_put_direct(az_engine* e, int c, AzPairArgs* A)
+{
+    AzDDHost* h = e->dd;
+    const AzDD& D = h->D;
+    int buf = -1;
+    for (int b = 0; b < 3; b++) if (h->pos_bufs[b] == e->pos[c]) buf = b;
+    if (buf < 0) { AZ_SET_ERR(e, "direct halo: unknown position stream"); return AZ_ERR_INVALID; }
+    // On the halo stream, beside the list pass that starts right away on the engine's stream: the put reads this step's
+    // (final) positions, which nobody writes during this step; the ghost-touching blocks of the neighbours' list passes come
+    // last in their launches, so a put that has to wait a few microseconds for SM slots delays nobody.  (On the engine's
+    // stream the put cost 20 us of every step: launch, NVLink round trips of the fences, flags.)
+    AZ_CUDA(e, cudaEventRecord(h->ev_moved, e->stream));
+    AZ_CUDA(e, cudaStreamWaitEvent(h->halo_stream, h->ev_moved, 0));
+    {
+        Timer t(e, AZ_TIMER_HALO, h->halo_stream);
+        const int seq = ++h->halo_seq;
+        AZ_LAUNCH(az_k_ghost_put_direct<0>, (D.gs[AZ_NDIR] + AZ_TPB - 1) / AZ_TPB, AZ_TPB, 0, h->halo_stream, D, h->peerPtr, h->sendList, h->remoteSlot, e->pos[c], buf, seq,
+                  h->slot_epoch, h->haloFlags, h->putDone, &e->sc->overflow);
+        AZ_COUNT(e, AZ_TIMER_HALO, 1);
+        A->haloSeq = seq;
+    }
+    AZ_CUDA(e, cudaEventRecord(h->ev_put, h->halo_stream));
+    A->haloFlags = h->haloFlags; A->haloDirs = h->halo_dirs; A->blockOrder = h->blockOrder;
+    return AZ_OK;
+}
+// ... and whatever overwrites this step's positions next (the riding integrator of the NEXT step's list pass) comes behind the put
+static int dd_join_put(az_engine* e) { AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->dd->ev_put, 0)); return AZ_OK; }
+// the position stream this step's force pass reads, by number; direct puts are allowed when it differs from the previous step's
+static int dd_buf_number(const az_engine* e, int c)
+{
+    for (int b = 0; b < 3; b++) if (e->dd->pos_bufs[b] == e->pos[c]) return b;
+    return -1;
+}
+static bool dd_direct_ok(az_engine* e, int c) { const int b = dd_buf_number(e, c); return b >= 0 && b != e->dd->prev_step_buf; }
+static void dd_note_step_buffer(az_engine* e, int c) { if (e->dd) e->dd->prev_step_buf = dd_buf_number(e, c); }
+static int dd_order_blocks(az_engine* e) // behind every list build
+{
+    AzDDHost* h = e->dd;
+    AZ_LAUNCH(az_k_block_order, 1, 1024, 0, e->stream, h->blockFlag, e->list_nblocks, h->blockOrder);
+    e->launches++;
+    return AZ_OK;
+}
+
 // Readers of ghost positions other than the list pass (RDF sampling): scatter the last received ghosts into pos[].  The flags
 // of that refresh have been seen by the list pass that ran on this stream, so no wait is needed.
 static int dd_sync_ghosts(az_engine* e)
@@ -612,7 +674,8 @@ static int dd_wait_ghosts(az_engine* e)
 }
 static bool dd_overlap(const az_engine* e) { return e->dd && e->dd->overlap && e->use_list; }
 static bool dd_peer_halo(const az_engine* e) { return e->dd && e->dd->p2p; }
-static bool dd_fused(const az_engine* e) { return e->dd && e->dd->fused && e->dd->overlap; }
+static bool dd_direct(const az_engine* e) { return e->dd && e->dd->direct && e->dd->overlap; }
+static bool dd_fused(const az_engine* e) { return e->dd && e->dd->fused && e->dd->overlap && !e->dd->direct; }
 static int dd_fused_args(az_engine* e, AzPairArgs& A)
 {
     AzDDHost* h = e->dd;

@@ -264,7 +264,11 @@ az_k_ghost_update(const __grid_constant__ AzDD D, const int* __restrict__ ghostS
 struct AzPeer {
     float4* pos[AZ_NDIR];  // neighbour's staging (both halves, 2 * gr[AZ_NDIR] entries), NULL = direction unused
     float2* aux[AZ_NDIR];
-    int* flags[AZ_NDIR];   // neighbour's arrival flags [AZ_NDIR]
+    int* flags[AZ_NDIR];   // neighbour's arrival flags [2 * AZ_NDIR]: ghost positions of a step, then slot tables of a rebuild
+    // direct halo: the neighbour's three position streams (they rotate like mine: the same buffer number is "current" on
+    // every rank at every step) and its table of where my atoms sit in them
+    float4* pbuf[AZ_NDIR][3];
+    int* slot[AZ_NDIR];
 };
 
 __device__ __forceinline__ int az_ld_volatile(const int* p) { return *(const volatile int*)p; }
@@ -299,6 +303,86 @@ az_k_ghost_put(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R,
                 if (R.flags[d]) *(volatile int*)(R.flags[d] + (AZ_NDIR - 1 - d)) = seq;
             __threadfence_system();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// DIRECT halo (peer memory + Verlet list, positions only): my boundary atoms are stored straight into the ghost slots of the
+// neighbour's sorted position stream -- no staging, no scatter kernel, no ghost-aware loads in the force pass.  The list pass
+// is the plain kernel in ONE launch; the blocks that list ghosts (blockFlag, ordered last by az_k_block_order) wait in
+// their prologue for the arrival flags of this step.
+// * Where: at a rebuild every receiver knows the slot each received atom was sorted into (ghostSlot); az_k_dd_remap stores
+//   that number into the SENDER's remoteSlot table over NVLink and raises the sender's slot flag of that direction to the
+//   rebuild epoch.  The first put after a rebuild waits for those flags.
+// * Which buffer: the position streams rotate (sort: pos[c] -> pos[1-c]; the riding integrator: pos[c] <-> pos_alt) in the
+//   same way on every rank, so "the buffer that is current at step n" has the same number everywhere.  put(n) reads my
+//   current buffer and writes the neighbour's buffer of the same number.  A neighbour that is still at step n-1 has that
+//   buffer as the TARGET of its riding integrator, which writes owned slots only; it cannot be at n-2 or n+1 (it needs my
+//   put(n-1) to finish n-1, and I need its put(n) before I finish n).
+// * L1: peer stores land in L2.  A block reads ghost slots only behind its wait, but a 128-byte line that holds the last
+//   owned atoms AND the first ghosts could have been pulled into L1 by a block that does not wait; the list build therefore
+//   flags every block that touches that line (az_k_build_list: index >= n_owned & ~7).
+template <int DUMMY>
+__global__ void __launch_bounds__(AZ_TPB)
+az_k_ghost_put_direct(const __grid_constant__ AzDD D, const __grid_constant__ AzPeer R, const int* __restrict__ sendList,
+                      const int* __restrict__ remoteSlot, const float4* __restrict__ pos, int buf, int seq, int epoch,
+                      const int* __restrict__ myFlags, int* __restrict__ done, int* __restrict__ err_flags)
+{
+    if (threadIdx.x < AZ_NDIR && R.slot[threadIdx.x]) az_wait_flag(myFlags + AZ_NDIR + threadIdx.x, epoch, err_flags);
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < D.gs[AZ_NDIR]) {
+        const int d = az_dir_of(D.gs, t), k = t - D.gs[d];
+        const int capacity = D.gs[d + 1] - D.gs[d] - 1;
+        if (k >= 1 && k - 1 < min(D.cnt->sendCount[d], capacity) && R.pbuf[d][buf]) {
+            const int s = ((const volatile int*)remoteSlot)[t]; // written by the neighbour (L2)
+            if (s >= 0 && s < D.cap_total) R.pbuf[d][buf][s] = pos[sendList[t]];
+            else atomicOr(err_flags, AZ_FLAG_HALO);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int ticket = atomicAdd(done, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            for (int d = 0; d < AZ_NDIR; d++)
+                if (R.flags[d]) *(volatile int*)(R.flags[d] + (AZ_NDIR - 1 - d)) = seq;
+            __threadfence_system();
+        }
+    }
+}
+
+#define AZ_ORDER_GHOSTS 0x40000000
+// blocks of the list pass in launch order: the ones that list no ghost first (they can start at once), the others behind them
+static __global__ void __launch_bounds__(1024)
+az_k_block_order(const int* __restrict__ flag, int n, int* __restrict__ order)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int b0 = min(n, tid * per), b1 = min(n, b0 + per);
+    int nu = 0;
+    for (int b = b0; b < b1; b++) nu += flag[b] ? 0 : 1;
+    int incl = nu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = s_w[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+        s_w[lane] = iv - v;
+        if (lane == 31) s_total = iv;
+    }
+    __syncthreads();
+    int ku = s_w[w] + incl - nu;          // unflagged blocks before mine
+    int kf = s_total + (b0 - ku);         // flagged blocks before mine, behind all unflagged ones
+    for (int b = b0; b < b1; b++) {
+        if (flag[b]) order[kf++] = b | AZ_ORDER_GHOSTS; else order[ku++] = b; // (the flag travels with the entry: one load per block)
     }
 }
 
@@ -370,8 +454,11 @@ az_k_bin(const __grid_constant__ AzParams P, const __grid_constant__ AzDD D, con
 
 
 // send lists and ghost slots follow the atoms through the sort; then publish the new counts
+// Direct halo (R != NULL): the slot of every ghost also goes into the remoteSlot table of the rank that sent it (entry k of my
+// direction d is entry k of its direction 26-d), and the last block raises that rank's slot flags to `epoch`.
 static __global__ void __launch_bounds__(AZ_TPB)
-az_k_dd_remap(const __grid_constant__ AzDD D, const int* __restrict__ newIndex, int* __restrict__ sendList, int* __restrict__ ghostSlot)
+az_k_dd_remap(const __grid_constant__ AzDD D, const int* __restrict__ newIndex, int* __restrict__ sendList, int* __restrict__ ghostSlot,
+              const __grid_constant__ AzPeer R, int direct, int epoch, int* __restrict__ done)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < D.gs[AZ_NDIR]) {
@@ -384,7 +471,23 @@ az_k_dd_remap(const __grid_constant__ AzDD D, const int* __restrict__ newIndex, 
         if (k >= 1 && k - 1 < D.cnt->recvCount[d]) {
             int before = 0;
             for (int q = 0; q < d; q++) before += D.cnt->recvCount[q];
-            ghostSlot[t] = newIndex[D.cnt->ghost_base + before + (k - 1)];
+            const int slot = newIndex[D.cnt->ghost_base + before + (k - 1)];
+            ghostSlot[t] = slot;
+            if (direct && R.slot[d]) R.slot[d][D.gs[AZ_NDIR - 1 - d] + k] = slot;
+        }
+    }
+    if (direct) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const int ticket = atomicAdd(done, 1);
+            if (ticket == (int)gridDim.x - 1) {
+                *done = 0;
+                __threadfence_system();
+                for (int d = 0; d < AZ_NDIR; d++)
+                    if (R.flags[d]) *(volatile int*)(R.flags[d] + AZ_NDIR + (AZ_NDIR - 1 - d)) = epoch;
+                __threadfence_system();
+            }
         }
     }
 }

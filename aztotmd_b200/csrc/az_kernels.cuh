@@ -72,6 +72,7 @@ struct AzScalars {
 #define AZ_FLAG_NAN 4
 #define AZ_FLAG_HALO 8
 #define AZ_FLAG_NBR 16
+#define AZ_FLAG_FOOT 32 // tile lists: a footprint larger than the shared-memory allotment (or too many runs)
 
 // ---------------------------------------------------------------------------------------
 // K1: verlet_1stage (src/cuMDfunc.cu:333-518) + put_periodic (:35-106) + count_cell

@@ -34,6 +34,16 @@ struct AzPairArgs {
     int* nbr;                // Verlet list, blocked by warp: row k of atom i at nbr[((i >> 5) * nbr_cap + k) * 32 + (i & 31)]
     int* nbrCount;           // LIST build: neighbours of atom i within the list radius
     int nbr_stride, nbr_cap;
+    // tile lists (az_tlist.cuh): 16-bit rows that index the tile's footprint, two per word; per tile the number of runs and
+    // the runs (first atom in the sorted stream, offset in the footprint), closed by the entry (0, footprint size)
+    unsigned* nbr16;
+    int* tileHdr;
+    int4* tileRuns;          // [tile][AZ_TL_RUNS]: (first atom in the sorted stream, place in the footprint, length, 0)
+    int* tlStat;             // [0] largest footprint, [1] most runs, [2] most candidate ranges, [3] longest row column seen by a rebuild
+    int tl_rows_smem;        // az_k_build_tlist: rows per thread held in shared memory (even)
+    int tl_foot_cap;         // az_k_pair_tlist: atoms the shared-memory footprint holds
+    int tl_stride;           // words per atom of that footprint (3: x y z; 5: + type, radius); a row holds stride * place
+    int n_total;             // atoms in the sorted stream (owned + ghosts: capacity on bricks)
     // az_k_pair_list with the integrator riding on it (fuse != 0): second half kick of this step, kinetic energy, and the
     // next step's kick + drift (+ wrap, + bin) applied to atom i right after its force is known; the new position and
     // velocity go to the alternate buffers (neighbours still read the current ones), forces are never written
@@ -44,7 +54,9 @@ struct AzPairArgs {
     AzScalars* sc;
     double* partKE;
     int* blockFlag;          // bricks: 1 if any atom of this 128-atom block lists a ghost (written by az_k_build_list)
-    int phase;               // list pass on bricks: 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
+    const int* blockOrder;   // direct halo (phase 4): block of the launch -> block of atoms (ghost-free blocks first), or NULL
+    int phase;               // list pass on bricks: 4 = direct halo: all blocks in one launch, the ones that list ghosts wait for the
+                             // arrival flags first (the neighbours store into this rank's position stream, az_halo.cuh); 0 = all blocks, 1 = blocks without ghosts (runs while the halo is
                              // in flight), 2 = blocks with ghosts (after the halo), 3 = blocks with ghosts in the FUSED halo: the
                              // GHOSTS instantiation, on the halo stream beside phase 1; it waits for the arrival flags of the
                              // peer-memory halo itself and reads ghost positions straight from the receive staging
@@ -479,8 +491,10 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
     if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }
     A.nbrCount[i] = nA | (nB << AZ_NBR_CNT_BITS);
     }
-    if (A.blockFlag) { // ghosts sit behind the owned atoms in the sorted streams
-        if (jmax >= n_owned) atomicOr(&s_ghost, 1);
+    if (A.blockFlag) { // ghosts sit behind the owned atoms in the sorted streams; the 128-byte line they share with the last
+        // owned atoms counts as ghost territory (direct halo: no block that does not wait may pull it into L1)
+        const int gl = n_owned & ~7;
+        if (jmax >= gl || (i >= gl && i < n_owned)) atomicOr(&s_ghost, 1);
         __syncthreads();
         if (threadIdx.x == 0) A.blockFlag[blockIdx.x] = s_ghost;
     }
@@ -654,8 +668,9 @@ az_k_build_list_staged(const __grid_constant__ AzParams P, const __grid_constant
         if (nA + nB > cap) { atomicOr(A.flags, AZ_FLAG_NBR); atomicMax(A.flags + 1, nA + nB); nB = min(nB, cap); nA = min(nA, cap - nB); }
         A.nbrCount[i] = nA | (nB << AZ_NBR_CNT_BITS);
     }
-    if (A.blockFlag) { // ghosts sit behind the owned atoms in the sorted streams
-        if (act && jmax >= n_owned) atomicOr(&s_ghost, 1);
+    if (A.blockFlag) { // ghosts (and the line they share with the last owned atoms) sit behind the owned atoms in the sorted streams
+        const int gl = n_owned & ~7;
+        if (act && (jmax >= gl || i >= gl)) atomicOr(&s_ghost, 1);
         __syncthreads();
         if (tid == 0) A.blockFlag[blockIdx.x] = s_ghost;
     }
@@ -722,7 +737,14 @@ az_k_pair_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         if (tid == 0) s_done = 0;
         __syncthreads();
     }
-    const int blk = (int)blockIdx.x;
+    const int ob = (A.phase == 4) ? A.blockOrder[blockIdx.x] : (int)blockIdx.x; // direct halo: launch order, bit 30 = lists ghosts
+    const int blk = ob & 0x3fffffff;
+    if (!GHOSTS && A.phase == 4) { // direct halo: the neighbours' stores into my ghost slots for this step must have landed
+        if (ob >> 30) {
+            if (tid < 27 && ((A.haloDirs >> tid) & 1)) az_wait_flag(A.haloFlags + tid, A.haloSeq, A.flags);
+            __syncthreads();
+        }
+    } else
     if (GHOSTS) {
         if (A.blockFlag[blk] == 0) return; // phase 1 (the other launch) owns the blocks that list no ghost
         // the neighbours' stores for this step must have landed (az_k_ghost_put raises the flags over NVLink)
@@ -1168,3 +1190,5 @@ az_k_rdf(const __grid_constant__ AzParams P, const __grid_constant__ AzRdfArgs A
         if (v) atomicAdd(&A.hist[k], (unsigned long long)v);
     }
 }
+
+#include "az_tlist.cuh"

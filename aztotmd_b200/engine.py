@@ -288,6 +288,7 @@ class Engine:
 
     def __init__(self, system, *, device: int = 0, rebuild_every: int = 1, skin: float = 0.0,
                  cells_per_block: int = 0, pair_variant: int = 0, max_neigh: int = 0, use_graph: bool = False, lib=None,
+                 list_format: int = 0, tile_atoms: int = 0,
                  opts: Optional[abi.az_cuda_opts] = None,
                  rank: int = 0, n_ranks: int = 1, pgrid: Sequence[int] = (0, 0, 0), comm_id: Optional[bytes] = None):
         self.lib = lib if lib is not None else abi.load_library()
@@ -307,6 +308,7 @@ class Engine:
             opts.cells_per_block = cells_per_block
             opts.pair_variant = pair_variant
             opts.max_neigh = max_neigh
+            opts.list_format, opts.tile_atoms = list_format, tile_atoms
             opts.use_graph = 1 if use_graph else 0
             opts.rank, opts.n_ranks = rank, n_ranks
             for a in range(3):

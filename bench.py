@@ -400,7 +400,9 @@ def main():
 
     # dominant kernel: the Verlet-list pass when it runs (9 of 10 steps), else the cell-tile sweep
     dom = "pair_list" if tm["pair_list"]["launches"] > 0 else "pair"
-    dom_kernel = "az_k_pair_list" if dom == "pair_list" else "az_k_pair"
+    info = e.refresh_info()
+    tile_list = bool(getattr(info, "tile_list", 0))
+    dom_kernel = ("az_k_pair_tlist" if tile_list else "az_k_pair_list") if dom == "pair_list" else "az_k_pair"
     pair_ms = tm[dom]["ms"] / max(1, tm[dom]["launches"])
     pair_total_ms = tm["pair"]["ms"] + tm["pair_list"]["ms"]
     rest_ms = (tm["integrate_a"]["ms"] + tm["integrate_b"]["ms"] + tm["scan"]["ms"] + tm["sort"]["ms"]) / K
@@ -496,6 +498,9 @@ def main():
                             "avg_ms": hbm_ms, "algorithmic_bytes": hbm_bytes,
                             "other_non_pair_ms_per_step": rest_ms},
            "kernel_ms_per_step": {k: v["ms"] / K for k, v in tm.items()},
+           "list": {"format": "tile lists (16-bit rows into a shared-memory copy of each tile's neighbourhood)" if tile_list else "global 32-bit rows",
+                    "rows_capacity": int(info.list_rows), "tile_atoms": int(info.tile_atoms), "tile_atoms_seen": int(info.tile_atoms_seen),
+                    "tile_runs_seen": int(info.tile_runs_seen), "tile_rows_smem": int(info.tile_rows_smem)},
            "ns_per_day": 86400.0 / (ms / K * 1e-3) * (s.timestep * 1e3) * 1e-6,
            "section_events": {"where": "inside the timed region" if sections_inside else "separate pass of K steps after the timed region (the events add launch gaps on latency-bound decks)",
                               "ms_per_step": ms_prof / K},

@@ -217,7 +217,11 @@ typedef struct az_cuda_opts {
     int ghost_slots;     /* reserved                                                   */
     const void *nccl_id; /* 128 bytes from az_comm_unique_id, the same on all ranks   */
     int max_neigh;       /* rows of the Verlet list per atom ('max_neigh' of control.txt); 0 = from density */
-    int reserved[7];
+    int list_format;     /* Verlet-list path: 0 = auto (= 1), 1 = global 32-bit rows gathered through L1, 2 = tile lists: 16-bit
+                            rows that index a shared-memory copy of the neighbourhood of each 128-atom tile (bitwise the same
+                            forces, half the list bytes; measured slower on B200, kept for the A/B -- 'list_format' of cuda.txt) */
+    int tile_atoms;      /* tile lists: atoms the shared-memory neighbourhood of a tile holds; 0 = from density ('tile_atoms') */
+    int reserved[5];
 } az_cuda_opts;
 
 /* Scalars of stat.dat / msd.dat for the last completed step
@@ -335,10 +339,11 @@ int az_engine_rdf_read(az_engine *e, unsigned long long *counts, int capacity, i
 #define AZ_TIMER_SORT 2        /* sort_atoms                               */
 #define AZ_TIMER_PAIR 3        /* cell_list5a + cell_list4b_noshared       */
 #define AZ_TIMER_INTEGRATE_B 4 /* verlet_2stage + thermostat + quantities  */
-#define AZ_TIMER_HALO 5        /* multi-GPU halo / migration               */
+#define AZ_TIMER_HALO 5        /* multi-GPU: per-step ghost refresh        */
 #define AZ_TIMER_PAIR_LIST 6   /* Verlet-list force pass between rebuilds  */
 #define AZ_TIMER_EWALD 7       /* reciprocal-space Ewald (ewald_rec)       */
-#define AZ_N_TIMERS 8
+#define AZ_TIMER_MIGRATE 8     /* multi-GPU: migration + ghost selection at a rebuild */
+#define AZ_N_TIMERS 9
 int az_engine_profile(az_engine *e, int enable);
 int az_engine_timers(az_engine *e, double ms_sum[AZ_N_TIMERS], long long launches[AZ_N_TIMERS]);
 long long az_engine_launch_count(az_engine *e); /* kernels launched since create */
@@ -375,7 +380,13 @@ typedef struct az_engine_info_t {
     long long graph_replays; /* az_engine_step calls served by replaying a captured CUDA graph (az_cuda_opts.use_graph) */
     int graphs_cached;
     int peer_halo;       /* bricks: 0 = the per-step ghost refresh is ncclSend/ncclRecv; 1 = peer memory (NVLink stores + arrival flags);
-                            2 = peer memory fused with the list pass (one launch per step, ghost-touching blocks wait on the flags) */
+                            2 = peer memory fused with the list pass (ghost-touching blocks wait on the flags and read the staging);
+                            3 = direct: neighbours store their boundary atoms straight into this rank's sorted position stream,
+                            one plain list launch per step whose ghost-touching blocks wait on the flags */
+    int tile_list;       /* 1 = the Verlet-list path runs on tile lists (az_cuda_opts.list_format) */
+    int tile_atoms, tile_rows_smem;       /* shared-memory allotment: atoms of a tile's neighbourhood, rows per atom of the build */
+    int tile_atoms_seen, tile_runs_seen;  /* largest neighbourhood (atoms, runs of the sorted stream) any rebuild has seen */
+    int reserved;
 } az_engine_info_t;
 int az_engine_info(az_engine *e, az_engine_info_t *out);
 

@@ -193,13 +193,14 @@ def case_bricks_verlet_list_between_rebuilds(lib, devices=None):
 def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
     """The per-step ghost refresh has two transports: stores into the neighbour's staging buffer over peer memory with arrival
     flags (NVLink / NVSwitch; az_k_ghost_put, consumed either by az_k_ghost_update_wait or -- fused -- by the ghost-touching
-    blocks of the list pass themselves, straight from the staging) and ncclSend / ncclRecv.  Same ghosts either way: the
-    three runs agree bit for bit, and each agrees with the single engine.  (Several non-rebuild steps in a row exercise the
+    blocks of the list pass themselves, straight from the staging; or -- direct -- stores straight into the ghost slots of the
+    neighbour's sorted position stream, az_k_ghost_put_direct) and ncclSend / ncclRecv.  Same ghosts either way: the
+    four runs agree bit for bit, and each agrees with the single engine.  (Several non-rebuild steps in a row exercise the
     alternation of the two staging halves; the Verlet-list schedule overlaps the refresh with the ghost-free blocks.)"""
     import os
     s = azt.lj_system(ncell=(8, 5, 5), seed=29, cell_size=2.5 * azt.AR_SIGMA + 0.8)
     runs = {}
-    for tag, env in (("fused", {}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
+    for tag, env in (("direct", {}), ("fused", {"AZTOT_NO_DIRECT_HALO": "1"}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
         os.environ.update(env)
         try:
             runs[tag] = check_against_single(lib, s, 2, (2, 1, 1), nsteps=9, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
@@ -209,11 +210,12 @@ def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
     assert all(r["info"].peer_halo == 0 for r in runs["sendrecv"])
     if devices is None:  # emulator: the ranks are threads of one process, peer memory always exists
         assert all(r["info"].peer_halo == 1 for r in runs["peer"]) and all(r["info"].peer_halo == 2 for r in runs["fused"])
-    for tag in ("fused", "peer"):
+        assert all(r["info"].peer_halo == 3 for r in runs["direct"])
+    for tag in ("direct", "fused", "peer"):
         for a, b in zip(runs[tag], runs["sendrecv"]):
             assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["dump"]["frc"], b["dump"]["frc"]), tag
             assert np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
-    print("peer_halo:", [r["info"].peer_halo for r in runs["fused"]], [r["info"].peer_halo for r in runs["peer"]])
+    print("peer_halo:", [r["info"].peer_halo for r in runs["direct"]], [r["info"].peer_halo for r in runs["fused"]], [r["info"].peer_halo for r in runs["peer"]])
 
 
 def case_bricks_migration_hot_atoms(lib, devices=None):

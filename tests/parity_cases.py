@@ -10,6 +10,8 @@ engine behind the C ABI by the same steps and compares:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 import azt
@@ -418,6 +420,68 @@ def case_graph_replay_is_bitwise_the_plain_launches(lib):
         a.close(); b.close()
 
 
+def case_tile_list_is_bitwise_the_global_rows(lib):
+    """list_format 2 (tile lists: 16-bit rows into a shared-memory copy of each tile's neighbourhood, az_tlist.cuh) against
+    list_format 1 (32-bit rows gathered from global memory): same candidate ranges, same order, same pair arithmetic -- the
+    trajectories must agree bit for bit, on every pair-kernel instantiation, with rows through periodic faces, with rows
+    that outgrow the build's shared columns, and when the footprint is the whole (small) system."""
+    systems = [(azt.lj_system(ncell=(6, 6, 6), seed=32, cell_size=9.3), dict(rebuild_every=4, skin=0.8)),     # integrator rides on the list kernel
+               (azt.lj_system(ncell=(8, 6, 7), seed=35, temperature=500.0), dict(rebuild_every=5, skin=1.0)),  # anisotropic grid
+               (azt.lj_system(ncell=(6, 6, 6), seed=34, temperature=600.0), dict(pair_variant=2)),              # rebuilt every step
+               (azt.lj_system(ncell=(5, 5, 5), seed=36, cell_size=4.5), dict(rebuild_every=3, skin=0.5)),       # wide stencil
+               (azt.nacl_system(ncell=(5, 5, 5), r_real=9.0, rc_vdw=9.0, cell_size=9.6), dict(rebuild_every=3, skin=0.6)),
+               (azt.surk_system(n_side=6, n_equil=4, eq_freq=2), dict(rebuild_every=3, skin=0.5)),
+               (azt.lj_system(ncell=(5, 5, 5), seed=33, vel=False, tstat=abi.TSTAT_RADI, temperature=298.0), dict(rebuild_every=3, skin=0.6, _rad=True))]
+    # (the emulator build runs the plain Lennard-Jones rows of list_format 1 through the packed f32x2 form, which keeps two
+    # partial sums per component: there the comparison is to rounding, everywhere else -- and always on the GPU -- bitwise)
+    emu = "emu" in os.path.basename(getattr(lib, "_name", ""))
+    for s, kw in systems:
+        kw = dict(kw)
+        rad = kw.pop("_rad", False)
+        if rad:
+            s.species[0].radA, s.species[0].radB, s.species[0].mxEng = 2.73, 4.731, 0.2
+        exact = not (emu and len(s.species) == 1 and s.elec_kind == abi.ELEC_NONE and all(v["kind"] == abi.VDW_LJ for v in s.vdw.values()))
+        a, b = Engine(s, lib=lib, list_format=1, **kw), Engine(s, lib=lib, list_format=2, **kw)
+        assert a.info.tile_list == 0 and b.info.tile_list == 1
+        a.step(0, 9); b.step(0, 9)
+        da, db = a.dump(), b.dump()
+        for key in ("pos", "vel", "frc", "ids", "cell"):
+            if exact or key in ("ids", "cell"):
+                assert np.array_equal(da[key], db[key]), key
+            else:
+                assert np.abs(da[key] - db[key]).max() <= 1e-5 * np.abs(da[key]).max(), key
+        sa, sb = a.stats(), b.stats()
+        for key in ("engKin_d", "engVdW_d", "engCoul1_d", "engTemp_d", "n_pairs", "pressure"):
+            if exact or key == "n_pairs":
+                assert getattr(sa, key) == getattr(sb, key), key
+            else:
+                assert abs(getattr(sa, key) - getattr(sb, key)) <= 2e-6 * max(1e-30, abs(getattr(sa, key))), key
+        b.refresh_info()
+        assert 0 < b.info.tile_atoms_seen <= b.info.tile_atoms and 0 < b.info.tile_runs_seen <= 64
+        # single-step calls; the switch by name takes an engine created for tile lists back to the global rows
+        c = Engine(s, lib=lib, list_format=2, **kw)
+        for k in range(9):
+            c.step(k, 1)
+        assert np.array_equal(c.dump()["pos"], db["pos"]) and np.array_equal(c.dump()["frc"], db["frc"])
+        c.close()
+        c = Engine(s, lib=lib, list_format=2, **kw)
+        c.set_option("tile_list", 0)
+        c.step(0, 9)
+        assert np.array_equal(c.dump()["pos"], da["pos"]) and np.array_equal(c.dump()["frc"], da["frc"])
+        a.close(); b.close(); c.close()
+    # a footprint allotment that is too small is reported, not silently wrong
+    s = azt.lj_system(ncell=(12, 12, 12), seed=37)
+    e = Engine(s, lib=lib, rebuild_every=4, skin=0.8, list_format=2, tile_atoms=300)
+    e.step(0, 2)
+    try:
+        e.stats()
+    except AzError as err:
+        assert err.status == abi.AZ_ERR_OVERFLOW and "tile_atoms" in str(err)
+    else:
+        raise AssertionError("footprint overflow not reported")
+    e.close()
+
+
 def case_tile_kernel_variant(lib):
     """pair_variant = 1: the shared-memory cell-tile sweep (one thread per atom) instead of the default
     warp-per-atom sweep -- same parity bars."""
@@ -665,6 +729,7 @@ ALL_CASES = [
     ("tile_kernel_variant", case_tile_kernel_variant),
     ("list_every_step_variant", case_list_every_step_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
+    ("tile_list_bitwise", case_tile_list_is_bitwise_the_global_rows),
     ("graph_replay", case_graph_replay_is_bitwise_the_plain_launches),
     ("error_paths", case_error_paths),
 ]
