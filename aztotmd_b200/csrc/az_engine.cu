@@ -126,6 +126,7 @@ static bool dd_overlap(const az_engine* e);
 static bool dd_peer_halo(const az_engine* e);
 static bool dd_fused(const az_engine* e);
 static bool dd_direct(const az_engine* e);
+static int dd_n_owned_cells(const az_engine* e);
 static int dd_put_direct(az_engine* e, int c, AzPairArgs* A);
 static int dd_order_blocks(az_engine* e);
 static int dd_join_put(az_engine* e);
@@ -454,13 +455,30 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     // cell tiles only, 2 = list, 3 = warp-per-atom sweep
     e->warp_nblocks = (capo + (AZ_WARP_TPB / 32) - 1) / (AZ_WARP_TPB / 32);
     e->use_warp = !e->use_list && pv != 1;
+    // ... or one thread per atom (pair_variant 4 only: measured slower than the warp sweep even where it should shine, az_pair.cuh)
+    e->thread_nblocks = (capo + AZ_THREAD_TPB - 1) / AZ_THREAD_TPB;
+    e->use_thread = !e->use_list && pv == 4;
+    if (e->use_thread) e->use_warp = false;
     const bool ewald_rec = d->elec_kind == AZ_ELEC_EWALD && (d->ewald_k[0] > 0 || d->ewald_k[1] > 0 || d->ewald_k[2] > 0);
     e->fuse_pair = e->use_list && !e->use_therm && !e->P.has_efield && !ewald_rec; // the k-space forces come after the pair pass
     if (e->fuse_pair) { AZ_ALLOC(e, e->pos_alt, capt); AZ_ALLOC(e, e->vel_alt, capt); }
     { int np = e->pair_nblocks > e->list_nblocks ? e->pair_nblocks : e->list_nblocks; // partials serve all pair kernels
       if (e->warp_nblocks > np) np = e->warp_nblocks;
+      if (e->thread_nblocks > np) np = e->thread_nblocks;
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
+    if (e->use_warp) { // the stencil of every owned cell, once (az_k_stencil_table)
+        const AzGrid& g = e->P.g;
+        const int S = (2 * g.sten[0] + 1) * (2 * g.sten[1] + 1) * (2 * g.sten[2] + 1);
+        const int noc = e->dd ? dd_n_owned_cells(e) : g.ncell_local;
+        const long long ent = (long long)noc * S;
+        if (g.sten[0] < AZ_STEN_OFF && g.sten[1] < AZ_STEN_OFF && g.sten[2] < AZ_STEN_OFF && ent * (long long)sizeof(int2) <= (256ll << 20)) {
+            AZ_ALLOC(e, e->stenTab, (size_t)ent);
+            e->stenS = S;
+            AZ_LAUNCH(az_k_stencil_table, (unsigned)((ent + 255) / 256), 256, 0, e->stream, e->P, noc, S, e->stenTab);
+            AZ_CUDA(e, cudaGetLastError());
+        }
+    }
     if (e->use_graph) { AZ_ALLOC(e, e->step0_dev, 1); e->P.step_base = e->step0_dev; }
     AZ_ALLOC(e, e->table, e->h_table.size());
     AZ_CUDA(e, cudaMemcpy(e->table, e->h_table.data(), e->h_table.size() * sizeof(AzVdw), cudaMemcpyHostToDevice));
@@ -613,7 +631,7 @@ extern "C" void az_engine_destroy(az_engine* e)
     cudaFree(e->ew_ak); cudaFree(e->ew_pairs); cudaFree(e->ew_runs); cudaFree(e->ew_part); cudaFree(e->ew_T); cudaFree(e->ew_Sd);
     cudaFree(e->frc); cudaFree(e->pos_alt); cudaFree(e->vel_alt); cudaFree(e->cellOf); cudaFree(e->slotOf); cudaFree(e->cellSorted); cudaFree(e->keyTmp);
     cudaFree(e->cellCount); cudaFree(e->first); cudaFree(e->tileSum);
-    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount); cudaFree(e->nbr16); cudaFree(e->tileHdr); cudaFree(e->tileRuns); cudaFree(e->tlStat);
+    cudaFree(e->partKE); cudaFree(e->partU); cudaFree(e->partV); cudaFree(e->partC); cudaFree(e->partN); cudaFree(e->stage2[0]); cudaFree(e->stage2[1]); cudaFree(e->nbr); cudaFree(e->nbrCount); cudaFree(e->stenTab); cudaFree(e->nbr16); cudaFree(e->tileHdr); cudaFree(e->tileRuns); cudaFree(e->tlStat);
     cudaFree(e->rdf_hist); cudaFree(e->sc); cudaFree(e->table); cudaFree(e->photons); cudaFree(e->uv);
     cudaFree(e->whereId); cudaFree(e->bStart); cudaFree(e->aStart); cudaFree(e->bEnt); cudaFree(e->aEnt); cudaFree(e->bTypes); cudaFree(e->aTypes);
     cudaFree(e->partBond); cudaFree(e->partAngle); cudaFree(e->dl_buf);
@@ -792,7 +810,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const bool eq_step = is_eq_step(e, step);
     const int nb = e->n_atom_blocks;
     int c = e->cur;
-    const int n_pp = e->use_list ? e->list_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks); // live pair partials this step
+    const int n_pp = e->use_list ? e->list_nblocks : (e->use_thread ? e->thread_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks)); // live pair partials this step
     const int slot = (int)(e->steps_done & 1);
     const int ks = P.step_base ? step - e->call_first : step; // what the kernels get: relative when *step_base supplies the rest
 
@@ -864,7 +882,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const bool split = !rebuild && !fusedh && !directh && dd_overlap(e);
     dd_note_step_buffer(e, c); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
     { // K4: pair forces
-        const int pair_mode = e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
+        const int pair_mode = e->use_thread ? AZ_PAIR_MODE_THREAD : e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
         Timer t(e, pair_timer);
         AzPairArgs A;
@@ -876,6 +894,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         A.nbr = e->nbr; A.nbrCount = e->nbrCount; A.nbr_stride = e->nbr_stride; A.nbr_cap = e->nbr_cap; A.dbg = e->list_dbg; A.r2_safe = e->r2_safe;
         A.nbr16 = e->nbr16; A.tileHdr = e->tileHdr; A.tileRuns = e->tileRuns; A.tlStat = e->tlStat; A.tl_rows_smem = e->tl_rows_smem; A.tl_foot_cap = e->tl_foot_cap; A.tl_stride = e->tl_stride;
         A.n_total = e->dd ? e->cap_total_dd : e->n;
+        A.stenTab = e->stenTab; A.stenS = e->stenS;
         A.prune = (e->warp_prune && rebuild) ? 1 : 0; // the atom-to-cell distance test needs cells that are exact for this step's positions
         A.blockFlag = dd_block_flags(e);
         if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
@@ -1596,6 +1615,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
+    if (!strcmp(key, "stencil_table")) { if (value == 0.0) { cudaFree(e->stenTab); e->stenTab = nullptr; } return AZ_OK; } // only ever switched off (A/B, tests)
     if (!strcmp(key, "warp_prune")) { e->warp_prune = value != 0.0; return AZ_OK; }         // A/B of the per-atom cell pruning in the warp sweep
     if (!strcmp(key, "tile_list")) { // A/B of the two list formats; before the first step (the next rebuild writes the chosen format)
         if (value != 0.0 && (!e->nbr16 || (long long)(e->tl_foot_cap - 1) * e->tl_stride > 65535 || e->tl_smem_pass > 200 * 1024)) { AZ_SET_ERR(e, "tile lists are not available for this engine"); return AZ_ERR_UNSUPPORTED; }

@@ -46,6 +46,10 @@ struct az_engine {
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
     int warp_nblocks = 0;     // az_k_pair_warp: one warp per owned atom
     bool warp_prune = true;   // az_k_pair_warp: drop the stencil cells an atom cannot reach from where it stands
+    int2* stenTab = nullptr;  // az_k_pair_warp: tabulated stencil of every owned cell
+    int stenS = 0;
+    int thread_nblocks = 0;   // az_k_pair_thread: one thread per owned atom
+    bool use_thread = false;  // ... when every cell edge is at least twice the list radius (dilute / coarse-celled systems)
     bool use_warp = false;    // reference schedule (no list): warp-per-atom sweep instead of the shared-memory tile sweep
     int list_dbg = 0;
     float r2_safe = 3.4e38f; // packed Lennard-Jones list pass: below this r2 the reference's force_autocap clamp can act

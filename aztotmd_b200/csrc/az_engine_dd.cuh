@@ -699,6 +699,7 @@ static int dd_join_halo_stream(az_engine* e)
     AZ_CUDA(e, cudaStreamWaitEvent(e->stream, h->ev_ghosts, 0));
     return AZ_OK;
 }
+static int dd_n_owned_cells(const az_engine* e) { return e->dd ? e->dd->n_owned_cells : 0; }
 static int* dd_block_flags(const az_engine* e) { return e->dd ? e->dd->blockFlag : nullptr; }
 static void dd_set_overlap(az_engine* e, bool on) { if (e->dd) e->dd->overlap = on; }
 

@@ -65,6 +65,8 @@ struct AzPairArgs {
     const int* haloFlags;    // phase 3: arrival flags [27]
     int haloSeq, haloDirs;   // phase 3: the value the flags must reach; bit d set = direction d is in use
     int dbg;                 // diagnostics of the list pass: 1 = synthesise positions (no gathers), 2 = synthesise indices (no list stream)
+    const int2* stenTab;     // warp sweep: the stencil of every owned cell (az_k_stencil_table), stenS entries per cell; NULL = work it out per atom
+    int stenS;
     int prune;               // warp sweep: drop stencil cells the atom itself cannot reach (cells binned this step)
     float r2_safe;           // packed LJ list pass: |F/r| < MX_FRC for every r2 in [r2_safe, gate] (+inf: always take the clamped form)
     int zc;                  // z-run length per CTA
@@ -1027,6 +1029,94 @@ __device__ __forceinline__ void az_warp_stencil_ranges(const AzGrid& g, const in
 }
 
 
+// The stencil of every owned cell, tabulated once at create time (the grid never changes): entry c of cell ci = what lane c of
+// az_warp_stencil_ranges works out for that cell -- storage id of the neighbour cell (-1: no such cell pair), image code, and the
+// three offsets (for the per-atom pruning).  The reference keeps the same kind of table (init_bypass6, src/cuCellList.cu:506-555);
+// here it serves the warp-per-atom sweep only, where the per-atom bookkeeping was more than half of the instructions
+// (ncu on B200, case study 1: 536 warp instructions per atom, 68 % issue utilisation).
+#define AZ_STEN_OFF 8 // offsets are stored + 8 in four bits each
+static __global__ void __launch_bounds__(256)
+az_k_stencil_table(const __grid_constant__ AzParams P, int n_owned_cells, int S, int2* __restrict__ tab)
+{
+    const AzGrid& g = P.g;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_owned_cells * S) return;
+    const int ci = (int)(t / S), c = (int)(t - (long long)ci * S);
+    const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+    const int cxy = ci / onz;
+    const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+    const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+    const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+    const int wy = 2 * g.sten[1] + 1, wz = 2 * g.sten[2] + 1;
+    const int oz = c % wz - g.sten[2], tt = c / wz;
+    const int oy = tt % wy - g.sten[1], ox = tt / wy - g.sten[0];
+    int2 ent = make_int2(-1, 0);
+    int sx, sy, sz, shxi, shyi, shzi;
+    if (az_neighbor(g, 0, gcx, ox, sx, shxi) && az_neighbor(g, 1, gcy, oy, sy, shyi) && az_neighbor(g, 2, gcz, oz, sz, shzi)) {
+        const int aox = ox < 0 ? -ox : ox, aoy = oy < 0 ? -oy : oy, aoz = oz < 0 ? -oz : oz;
+        const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+        const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+        const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+        const float mxy2 = mx * mx + my * my;
+        if (mxy2 <= P.r2list && mxy2 + mz * mz <= P.r2list) {
+            ent.x = az_cell_id(g, (sx * g.nl[1] + sy) * g.nl[2] + sz);
+            ent.y = az_shift_code(shxi, shyi, shzi) | ((ox + AZ_STEN_OFF) << 6) | ((oy + AZ_STEN_OFF) << 10) | ((oz + AZ_STEN_OFF) << 14);
+        }
+    }
+    tab[t] = ent;
+}
+
+// az_warp_stencil_ranges with the cell-level work read from the table: same cells, same order, same merged ranges.
+// (A FLAT hand-out of the candidates -- warp prefix sum over the 32 cell populations of a chunk, two candidates per lane
+// whatever cell they come from -- was measured on B200 and dropped: case study 2, whose 2.7 A cells hold 2 atoms, went
+// from 61.8 to 65.8 us per step, the 40 000-atom gas and a 32 000-atom liquid gained 2-4 %; the pair function, executed by
+// the whole warp whenever one lane has a partner in range, dominates either way.)
+template <class F>
+__device__ __forceinline__ void az_warp_table_ranges(const AzGrid& g, const int2* __restrict__ tab, int S, float r2lim, int ci, int gcx, int gcy, int gcz,
+                                                     const int* __restrict__ first, const int* __restrict__ count, int lane, F&& sweep,
+                                                     bool prune, float px, float py, float pz)
+{
+    const int2* __restrict__ row = tab + (size_t)ci * S;
+    for (int c0 = 0; c0 < S; c0 += 32) {
+        const int c = c0 + lane;
+        int jb = -1, je = -1, code = 0;
+        if (c < S) {
+            const int2 ent = __ldg(row + c);
+            bool keep = ent.x >= 0;
+            if (keep && prune) { // distance from the atom to the box of the (unwrapped) neighbour cell, per axis
+                const int ox = ((ent.y >> 6) & 15) - AZ_STEN_OFF, oy = ((ent.y >> 10) & 15) - AZ_STEN_OFF, oz = ((ent.y >> 14) & 15) - AZ_STEN_OFF;
+                auto gap = [&](int o, int gc, float x, float cs) {
+                    const float d = o > 0 ? (float)(gc + o) * cs - x : (o < 0 ? x - (float)(gc + o + 1) * cs : 0.f);
+                    return fmaxf(0.f, d - 1e-4f * cs);
+                };
+                const float gx = gap(ox, gcx, px, g.csize[0]), gy = gap(oy, gcy, py, g.csize[1]), gz = gap(oz, gcz, pz, g.csize[2]);
+                keep = gx * gx + gy * gy + gz * gz <= r2lim;
+            }
+            if (keep) {
+                jb = first[ent.x];
+                je = jb + count[ent.x];
+                code = ent.y & 63;
+            }
+        }
+        const bool valid = je > jb;
+        // continuation: this lane's range starts where the previous lane's ends, same image
+        const int pje = __shfl_up_sync(0xffffffffu, je, 1), pcode = __shfl_up_sync(0xffffffffu, code, 1);
+        const int pvalid = __shfl_up_sync(0xffffffffu, (int)valid, 1);
+        const bool cont = valid && lane > 0 && pvalid && pje == jb && pcode == code;
+        const unsigned contmask = __ballot_sync(0xffffffffu, cont);
+        unsigned heads = __ballot_sync(0xffffffffu, valid && !cont);
+        const unsigned behind = lane < 31 ? (contmask >> (lane + 1)) : 0u;
+        const int runlen = __ffs((int)~behind) - 1; // consecutive ones from bit 0
+        const int je_run = __shfl_sync(0xffffffffu, je, min(31, lane + runlen));
+        while (heads) {
+            const int h = __ffs((int)heads) - 1;
+            heads &= heads - 1;
+            const int rb = __shfl_sync(0xffffffffu, jb, h), re = __shfl_sync(0xffffffffu, je_run, h), rcode = __shfl_sync(0xffffffffu, code, h);
+            sweep(rb, re, rcode);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // az_k_pair_warp: the reference schedule (bin + sort every step, no list) with one WARP per atom.  The lanes
 // stride over the atoms of the stencil cells straight from the sorted stream (coalesced float4 loads; z-adjacent
@@ -1069,40 +1159,42 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
         const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
 
+        // one candidate per lane: delta, gate, and -- only if some lane has a partner in range -- the pair term
+        auto cand = [&](const float4 pj, const int j, const bool valid, const int code) {
+            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            if (code) { // (x_i - x_j) - shift, exactly like the reference's secShifts
+                dx -= ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
+                dy -= ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
+                dz -= ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
+            }
+            const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+            const bool in = valid & (r2 <= gate) & (j != i);
+            // dilute systems (case study 1: 490 candidates per atom, almost no pair inside 4 A): skip the pair term
+            // when no lane has a partner in range
+            if (!__any_sync(0xffffffffu, in)) return;
+            const int tj = __float_as_int(pj.w);
+            float radj = 0.f;
+            if (RADII) radj = A.therm[valid ? j : i].y;
+            float e1 = 0.f, e2 = 0.f, f;
+            if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+            else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+            f = in ? f : 0.f;
+            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+            if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
+        };
         auto sweep = [&](const int rb, const int re, const int code) {
-            const float shx = ((float)((code >> 1) & 1) - (float)(code & 1)) * P.L[0];
-            const float shy = ((float)((code >> 3) & 1) - (float)((code >> 2) & 1)) * P.L[1];
-            const float shz = ((float)((code >> 5) & 1) - (float)((code >> 4) & 1)) * P.L[2];
-            // one candidate per lane: delta, gate, and -- only if some lane has a partner in range -- the pair term
-            auto cand = [&](const float4 pj, const int j, const bool valid) {
-                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                if (code) { dx -= shx; dy -= shy; dz -= shz; } // (x_i - x_j) - shift, exactly like the reference's secShifts
-                const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
-                const bool in = valid & (r2 <= gate) & (j != i);
-                // dilute systems (case study 1: 490 candidates per atom, almost no pair inside 4 A): skip the pair term
-                // when no lane has a partner in range
-                if (!__any_sync(0xffffffffu, in)) return;
-                const int tj = __float_as_int(pj.w);
-                float radj = 0.f;
-                if (RADII) radj = A.therm[valid ? j : rb].y;
-                float e1 = 0.f, e2 = 0.f, f;
-                if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
-                else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
-                f = in ? f : 0.f;
-                fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
-                if (ENERGY) { ev += in ? e1 : 0.f; ec += in ? e2 : 0.f; hits += in ? 1 : 0; }
-            };
             // uniform trip count (the vote needs the whole warp), two loads in flight per lane: the step of the small
             // decks is bound by the latency of these loads, not by arithmetic
             for (int j0 = rb; j0 < re; j0 += 64) {
                 const int ja = j0 + lane, jb = ja + 32;
                 const bool va = ja < re, vb = jb < re;
                 const float4 pa = __ldg(A.pos + (va ? ja : rb)), pb = __ldg(A.pos + (vb ? jb : rb));
-                cand(pa, ja, va);
-                if (j0 + 32 < re) cand(pb, jb, vb);
+                cand(pa, ja, va, code);
+                if (j0 + 32 < re) cand(pb, jb, vb, code);
             }
         };
-        az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep, A.prune != 0, pi.x, pi.y, pi.z);
+        if (A.stenTab) az_warp_table_ranges(g, A.stenTab, A.stenS, P.r2list, ci, gcx, gcy, gcz, A.first, A.count, lane, sweep, A.prune != 0, pi.x, pi.y, pi.z);
+        else az_warp_stencil_ranges(g, g.sten, P.r2list, gcx, gcy, gcz, A.first, A.count, lane, sweep, A.prune != 0, pi.x, pi.y, pi.z);
     }
     // the 32 shares of atom i (all lanes of a warp belong to the same atom, so the whole warp is in or out)
 #pragma unroll
@@ -1112,6 +1204,114 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
         fz += __shfl_down_sync(0xffffffffu, fz, o);
     }
     if (act && lane == 0) {
+        const float q = P.charge[ti];
+        A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
+    }
+    if (ENERGY) {
+        double vv[3] = { 0.5 * (double)ev, 0.5 * (double)ec, (double)hits };
+        az_block_sum<3>(vv, s_red);
+        if (tid == 0) { A.partV[blockIdx.x] = vv[0]; A.partC[blockIdx.x] = vv[1]; A.partN[blockIdx.x] = (unsigned long long)(vv[2] + 0.5); }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// az_k_pair_thread: the reference schedule with one THREAD per atom, for systems whose cells are much wider than the cut-off
+// (case study 1 of the reference: a dilute gas, 4 A cut-off binned into 87.8 A cells, 18 atoms per cell).  There an atom
+// reaches 1-2 of its 27 stencil cells (the same atom-to-cell distance test as az_k_pair_warp's `prune`), i.e. ~25
+// candidates: a warp per atom spends its time on the stencil bookkeeping and the shuffle tree (28 us per step at 40 000
+// atoms), a thread per atom walks the few cells itself.  Same cell-pair rules (az_neighbor, cell_dist_int), same pair
+// arithmetic and per-cell-pair image shift as the other sweeps.  MEASURED AND REJECTED as a default (B200, 40 000 atoms, case study
+// 1 geometry, profiles/r2/bench_cs1_thread_sweep.json): 39.6 us per launch against 28 us for the warp sweep -- the 32 atoms of a
+// warp keep DIFFERENT stencil cells (each face neighbour is kept by 4.5 % of the atoms, i.e. by some lane of 77 % of the
+// warps), so a warp walks the union, ~6 cells instead of 1.3, with one or two lanes active.  pair_variant 4 selects it.
+#define AZ_THREAD_TPB 128
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+__global__ void __launch_bounds__(AZ_THREAD_TPB)
+az_k_pair_thread(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
+{
+    __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
+    __shared__ double s_red[96];
+    const AzGrid& g = P.g;
+    const int tid = threadIdx.x;
+    if (!SINGLE) {
+        for (int k = tid; k < P.nspec * P.nspec; k += AZ_THREAD_TPB) s_tab[k] = A.table[k];
+        __syncthreads();
+    }
+    const int i = blockIdx.x * AZ_THREAD_TPB + tid;
+    const bool act = i < az_n_owned(P);
+    float ev = 0.f, ec = 0.f;
+    int hits = 0;
+    if (act) {
+        const float4 pi = A.pos[i];
+        const int ti = __float_as_int(pi.w);
+        float radi = 0.f;
+        if (RADII) radi = A.therm[i].y;
+        const int ony = g.ohi[1] - g.olo[1], onz = g.ohi[2] - g.olo[2];
+        const int ci = A.cellOfSorted[i];
+        const int cxy = ci / onz;
+        const int gcz = g.olo[2] + (ci - cxy * onz) + g.goff[2];
+        const int gcy = g.olo[1] + cxy % ony + g.goff[1];
+        const int gcx = g.olo[0] + cxy / ony + g.goff[0];
+        constexpr bool FOLD = SINGLE && CK == AZ_ELEC_NONE;
+        const float gate = FOLD ? fminf(P.r2max, A.single.r2cut) : P.r2max;
+        const bool prune = A.prune != 0;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        // distance from the atom to the box of the (unwrapped) neighbour cell along one axis, 1e-4 of a cell edge of margin
+        auto gap = [&](const int o, const int gc, const float x, const float cs) {
+            const float d = o > 0 ? (float)(gc + o) * cs - x : (o < 0 ? x - (float)(gc + o + 1) * cs : 0.f);
+            return fmaxf(0.f, d - 1e-4f * cs);
+        };
+        for (int ox = -g.sten[0]; ox <= g.sten[0]; ox++) {
+            int sx, shxi;
+            if (!az_neighbor(g, 0, gcx, ox, sx, shxi)) continue;
+            const int aox = ox < 0 ? -ox : ox;
+            const float mx = aox ? (float)(aox - 1) * g.csize[0] : 0.f;
+            const float gx = prune ? gap(ox, gcx, pi.x, g.csize[0]) : 0.f;
+            if (gx * gx > P.r2list) continue;
+            for (int oy = -g.sten[1]; oy <= g.sten[1]; oy++) {
+                int sy, shyi;
+                if (!az_neighbor(g, 1, gcy, oy, sy, shyi)) continue;
+                const int aoy = oy < 0 ? -oy : oy;
+                const float my = aoy ? (float)(aoy - 1) * g.csize[1] : 0.f;
+                const float mxy2 = mx * mx + my * my;
+                if (mxy2 > P.r2list) continue;
+                const float gy = prune ? gap(oy, gcy, pi.y, g.csize[1]) : 0.f;
+                const float gxy2 = gx * gx + gy * gy;
+                if (gxy2 > P.r2list) continue;
+                const int colbase = (sx * g.nl[1] + sy) * g.nl[2];
+                for (int oz = -g.sten[2]; oz <= g.sten[2]; oz++) {
+                    int sz, shzi;
+                    if (!az_neighbor(g, 2, gcz, oz, sz, shzi)) continue;
+                    const int aoz = oz < 0 ? -oz : oz;
+                    const float mz = aoz ? (float)(aoz - 1) * g.csize[2] : 0.f;
+                    if (mxy2 + mz * mz > P.r2list) continue;
+                    const float gz = prune ? gap(oz, gcz, pi.z, g.csize[2]) : 0.f;
+                    if (gxy2 + gz * gz > P.r2list) continue;
+                    const int cid = az_cell_id(g, colbase + sz);
+                    const int jb = A.first[cid], je = jb + A.count[cid];
+                    const bool img = (shxi | shyi | shzi) != 0;
+                    const float shx = (float)shxi * P.L[0], shy = (float)shyi * P.L[1], shz = (float)shzi * P.L[2];
+#pragma unroll 2
+                    for (int j = jb; j < je; j++) {
+                        const float4 pj = __ldg(A.pos + j);
+                        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                        if (img) { dx -= shx; dy -= shy; dz -= shz; } // (x_i - x_j) - shift, exactly like the reference's secShifts
+                        const float r2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                        const bool in = (r2 <= gate) & (j != i);
+                        if (!in) continue; // dilute: most candidates are out of range, and there is no warp-wide work to keep uniform
+                        const int tj = __float_as_int(pj.w);
+                        float radj = 0.f;
+                        if (RADII) radj = A.therm[j].y;
+                        float e1 = 0.f, e2 = 0.f, f;
+                        if (SINGLE) f = az_pair<VK, CK, FOLD>(P, A.single, r2, radi, radj, true, e1, e2);
+                        else f = az_pair<VK, CK, false>(P, s_tab[ti * P.nspec + tj], r2, radi, radj, ti == tj, e1, e2);
+                        fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+                        if (ENERGY) { ev += e1; ec += e2; hits++; }
+                    }
+                }
+            }
+        }
         const float q = P.charge[ti];
         A.frc[i] = make_float4(-q * P.efield[0] + fx, -q * P.efield[1] + fy, -q * P.efield[2] + fz, 0.f);
     }

@@ -8,6 +8,7 @@
 #define AZ_PAIR_MODE_TILE_LIST 1
 #define AZ_PAIR_MODE_LIST 2
 #define AZ_PAIR_MODE_WARP 3
+#define AZ_PAIR_MODE_THREAD 4 // cell sweep with one thread per atom (cells much wider than the cut-off)
 
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_go(az_engine* e, const AzPairArgs& A)
@@ -91,9 +92,18 @@ static int az_pair_warp_go(az_engine* e, const AzPairArgs& A)
     return AZ_OK;
 }
 
+template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
+static int az_pair_thread_go(az_engine* e, const AzPairArgs& A)
+{
+    AZ_LAUNCH((az_k_pair_thread<VK, CK, SINGLE, RADII, ENERGY>), e->thread_nblocks, AZ_THREAD_TPB, 0, e->stream, e->P, A);
+    return AZ_OK;
+}
+
 template <int VK, int CK, bool SINGLE, bool RADII>
 static int az_pair_go_e(az_engine* e, const AzPairArgs& A, bool energy, int mode)
 {
+    if (mode == AZ_PAIR_MODE_THREAD)
+        return energy ? az_pair_thread_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_thread_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_WARP)
         return energy ? az_pair_warp_go<VK, CK, SINGLE, RADII, true>(e, A) : az_pair_warp_go<VK, CK, SINGLE, RADII, false>(e, A);
     if (mode == AZ_PAIR_MODE_LIST)

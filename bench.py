@@ -452,9 +452,11 @@ def main():
         if kind == "f32+pos":
             bp = lib.az_host_alloc(3 * 4 * n)
             back = [C.cast(bp + 4 * n * k, fpt) for k in range(3)] + [None, None, None]
-        for _ in range(2):  # warm the path
+        for _ in range(2):  # warm the path (incl. the download's device buffer, allocated at its first call)
             assert up(e._h, *ptr) == 0
             e.step(first, 1); e.stats(); first += 1
+            if back:
+                assert lib.az_engine_download_f32(e._h, *back) == 0
         e.sync()
         t0 = time.perf_counter()
         assert up(e._h, *ptr) == 0            # pinned host memory -> staging buffer on the copy stream

@@ -209,7 +209,8 @@ typedef struct az_cuda_opts {
                             6-7 short kernels; single GPU only; per-section timers (az_engine_profile) switch it off */
     int pair_variant;    /* 0 = auto (Verlet list between rebuilds and for large systems, warp-per-atom cell sweep
                             for small systems on the every-step schedule), 1 = shared-memory cell tiles,
-                            2 = list (rebuilt every step if rebuild_every <= 1), 3 = warp-per-atom sweep */
+                            2 = list (rebuilt every step if rebuild_every <= 1), 3 = warp-per-atom sweep,
+                            4 = thread-per-atom sweep (measured slower, kept for the A/B) */
     int cells_per_block; /* 0 = auto; z-run length a CTA owns in the pair kernel      */
     /* spatial domain decomposition (new functionality) */
     int rank, n_ranks;

@@ -13,8 +13,9 @@ from aztotmd_b200 import abi
 from aztotmd_b200.engine import AzError, Engine, unique_comm_id
 
 
-def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=None, rdf=None, **kw):
-    """Advance `system` on n_ranks bricks; returns per-rank results gathered after the last step."""
+def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=None, rdf=None, one_call=False, **kw):
+    """Advance `system` on n_ranks bricks; returns per-rank results gathered after the last step.  one_call: all steps in ONE
+    az_engine_step call (the integrator then rides on the list kernel and the position streams rotate: the direct halo's route)."""
     if devices is not None and n_ranks > len(devices):
         # one rank per device over NCCL: with fewer devices the ranks that do exist would wait in ncclCommInitRank forever
         pytest.skip("needs %d GPUs, %d available" % (n_ranks, len(devices)))
@@ -38,7 +39,10 @@ def run_bricks(lib, system, n_ranks, pgrid, nsteps, distributed=False, devices=N
             if rdf:
                 e.rdf_begin(*rdf)
             stats = []
-            for k in range(nsteps):
+            if one_call:
+                e.step(0, nsteps)
+                stats = [None] * (nsteps - 1) + [e.stats()]
+            for k in range(0 if one_call else nsteps):
                 e.step(k, 1)
                 stats.append(e.stats())
                 if rdf:
@@ -215,7 +219,62 @@ def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
         for a, b in zip(runs[tag], runs["sendrecv"]):
             assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["dump"]["frc"], b["dump"]["frc"]), tag
             assert np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
+    # the same four ways with all steps in ONE call: the integrator rides on the list kernel, the position streams rotate, and
+    # the direct halo really stores into the neighbours' streams (single-step calls drift in place and take the staged route)
+    calls = {}
+    for tag, env in (("direct", {}), ("fused", {"AZTOT_NO_DIRECT_HALO": "1"}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
+        os.environ.update(env)
+        try:
+            calls[tag] = run_bricks(lib, s, 2, (2, 1, 1), 11, devices=devices, one_call=True, rebuild_every=4, skin=0.8)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for tag in ("direct", "fused", "peer"):
+        for a, b in zip(calls[tag], calls["sendrecv"]):
+            assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
+            if tag == "fused" and devices is None:
+                # emulator build only: the ghost-touching blocks of the fused form take the scalar row loop, everybody else the
+                # packed one (two partial sums per component) -- equal to rounding there, bitwise on the GPU
+                assert np.abs(a["dump"]["frc"] - b["dump"]["frc"]).max() <= 1e-5 * np.abs(b["dump"]["frc"]).max()
+            else:
+                assert np.array_equal(a["dump"]["frc"], b["dump"]["frc"]) and a["stats"][-1].engVdW_d == b["stats"][-1].engVdW_d, tag
+    e1 = Engine(s, lib=lib, rebuild_every=4, skin=0.8)
+    e1.step(0, 11)
+    s1 = e1.stats()
+    for r in calls["direct"]:
+        assert r["stats"][-1].n_pairs == s1.n_pairs and abs(r["stats"][-1].engVdW_d - s1.engVdW_d) <= 1e-5 * abs(s1.engVdW_d)
+    e1.close()
     print("peer_halo:", [r["info"].peer_halo for r in runs["direct"]], [r["info"].peer_halo for r in runs["fused"]], [r["info"].peer_halo for r in runs["peer"]])
+
+
+def case_eight_bricks_list_direct_halo(lib, devices=None):
+    """2 x 2 x 2 bricks on the Verlet-list schedule, all steps in one call: every rank has all 26 directions in use (each
+    neighbour along an axis is the same rank twice), the direct halo stores into seven different ranks' position streams,
+    migration and ghost re-selection happen at the rebuilds in between.  Against ONE engine holding the whole box."""
+    s = azt.lj_system(ncell=(8, 8, 8), seed=91, cell_size=9.3, temperature=300.0)
+    kw = dict(rebuild_every=4, skin=0.8)
+    for n_ranks, pgrid in ((8, (2, 2, 2)), (4, (1, 2, 2))):
+        res = run_bricks(lib, s, n_ranks, pgrid, 10, devices=devices, one_call=True, **kw)
+        e1 = Engine(s, lib=lib, **kw)
+        e1.step(0, 10)
+        s1 = e1.stats()
+        n = len(s.pos)
+        frc, pos, vel, seen = gather_by_id(res, n)
+        assert (seen == 1).all()
+        for r in res:
+            st = r["stats"][-1]
+            assert st.n_pairs == s1.n_pairs, (st.n_pairs, s1.n_pairs)
+            assert abs(st.engVdW_d - s1.engVdW_d) <= 2e-5 * abs(s1.engVdW_d) and abs(st.engKin_d - s1.engKin_d) <= 2e-5 * abs(s1.engKin_d)
+            if devices is None:
+                assert r["info"].peer_halo == 3
+        d1 = azt.sort_by_id(e1.dump())
+        assert np.abs(frc - d1["frc"]).max() <= 1e-4 * np.abs(d1["frc"]).max()
+        a1 = e1.download(abi.ORDER_ORIGINAL)
+        L = np.asarray(s.box)
+        dp = np.abs(pos - a1["pos"])
+        dp = np.minimum(dp, L - dp)
+        assert dp.max() <= 1e-4
+        e1.close()
 
 
 def case_bricks_migration_hot_atoms(lib, devices=None):

@@ -233,6 +233,7 @@ static inline int __ldg(const int* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
 static inline float2 __ldg(const float2* p) { return *p; }
 static inline int4 __ldg(const int4* p) { return *p; }
+static inline int2 __ldg(const int2* p) { return *p; }
 using std::min; using std::max;
 
 // ----------------------------------------------------------------------------- host runtime

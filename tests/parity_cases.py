@@ -497,6 +497,52 @@ def case_tile_kernel_variant(lib):
     e.close()
 
 
+def case_thread_kernel_variant(lib):
+    """pair_variant = 4: the cell sweep with one thread per atom (az_k_pair_thread), what systems with cells much wider than
+    the cut-off use automatically (case study 1 of the reference) -- same parity bars, with and without the per-atom
+    pruning of stencil cells, on every pair-kernel instantiation."""
+    o, e = run_parity(lib, azt.lj_system(ncell=(6, 6, 6), seed=63), nsteps=2, pair_variant=4)
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(6, 6, 6), seed=64, cell_size=17.0), nsteps=3, pair_variant=4)   # wide cells: pruning drops most of the stencil
+    e.close()
+    o, e = run_parity(lib, azt.lj_system(ncell=(5, 5, 5), seed=65, cell_size=2.9), nsteps=1, pair_variant=4)     # wide stencil
+    e.close()
+    o, e = run_parity(lib, azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_FENNEL), nsteps=2, pair_variant=4)
+    e.close()
+    o, e = run_parity(lib, azt.surk_system(n_side=6, n_equil=4, eq_freq=2), nsteps=3, thermo=True, state_tol=1e-4, later_force_tol=1e-4, pair_variant=4)
+    e.close()
+    # the same trajectory as the warp-per-atom sweep (to rounding: the summation order differs), with the pruning switched off too
+    s = azt.lj_system(ncell=(6, 6, 6), seed=66, cell_size=20.0, temperature=300.0)
+    a, b, c = Engine(s, lib=lib, pair_variant=3), Engine(s, lib=lib, pair_variant=4), Engine(s, lib=lib, pair_variant=4)
+    c.set_option("warp_prune", 0)
+    for x in (a, b, c):
+        x.step(0, 4)
+    da, db, dc = a.dump(), b.dump(), c.dump()
+    assert np.array_equal(da["ids"], db["ids"]) and np.array_equal(da["cell"], db["cell"])
+    scale = np.abs(da["frc"]).max()
+    assert np.abs(da["frc"] - db["frc"]).max() <= 1e-5 * scale and np.abs(dc["frc"] - db["frc"]).max() <= 1e-5 * scale
+    assert a.stats().n_pairs == b.stats().n_pairs == c.stats().n_pairs
+    a.close(); b.close(); c.close()
+
+
+def case_stencil_table_is_bitwise_the_per_atom_stencil(lib):
+    """The warp-per-atom sweep reads the stencil of a cell from a table built at create time (az_k_stencil_table) instead of
+    working it out for every atom: same cells, same order, same merged ranges -- bitwise the same trajectory, with pruning
+    (wide cells), wide stencils, periodic images in tiny grids, and species tables."""
+    systems = [azt.lj_system(ncell=(6, 6, 6), seed=71), azt.lj_system(ncell=(6, 6, 6), seed=72, cell_size=17.0),
+               azt.lj_system(ncell=(5, 5, 5), seed=73, cell_size=2.9), azt.lj_system(ncell=(3, 3, 3), seed=74),
+               azt.nacl_system(ncell=(5, 5, 5), elec=abi.ELEC_FENNEL), azt.surk_system(n_side=6, n_equil=4, eq_freq=2)]
+    for s in systems:
+        a, b = Engine(s, lib=lib, pair_variant=3), Engine(s, lib=lib, pair_variant=3)
+        b.set_option("stencil_table", 0)
+        a.step(0, 4); b.step(0, 4)
+        da, db = a.dump(), b.dump()
+        for key in ("pos", "vel", "frc", "ids", "cell"):
+            assert np.array_equal(da[key], db[key]), key
+        assert a.stats().n_pairs == b.stats().n_pairs and a.stats().engVdW_d == b.stats().engVdW_d
+        a.close(); b.close()
+
+
 def case_list_every_step_variant(lib):
     """pair_variant = 2 on the every-step schedule (what large systems use automatically): the Verlet list is
     rebuilt every step with radius rc, so the recorded set IS the in-range set -- same parity bars."""
@@ -730,6 +776,8 @@ ALL_CASES = [
     ("list_every_step_variant", case_list_every_step_variant),
     ("fused_kick_drift", case_fused_kick_drift_is_bitwise_the_separate_kernels),
     ("tile_list_bitwise", case_tile_list_is_bitwise_the_global_rows),
+    ("thread_kernel_variant", case_thread_kernel_variant),
+    ("stencil_table_bitwise", case_stencil_table_is_bitwise_the_per_atom_stencil),
     ("graph_replay", case_graph_replay_is_bitwise_the_plain_launches),
     ("error_paths", case_error_paths),
 ]
