@@ -341,6 +341,9 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     e->n_ranks = (o && o->n_ranks > 1) ? o->n_ranks : 1;
     e->rank = o ? o->rank : 0;
     AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    AZ_CUDA(e, cudaStreamCreateWithFlags(&e->fin_stream, cudaStreamNonBlocking));
+    AZ_CUDA(e, cudaEventCreateWithFlags(&e->ev_fin_fork, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) AZ_CUDA(e, cudaEventCreateWithFlags(&e->ev_fin[k], cudaEventDisableTiming));
     for (int k = 0; k < 2 * AZ_N_TIMERS; k++) AZ_CUDA(e, cudaEventCreate(&e->ev[k]));
     for (int k = 0; k < 2; k++) AZ_CUDA(e, cudaEventCreate(&e->ev_step[k]));
     int rc = build_params(e, d, o);
@@ -370,7 +373,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
     AZ_ALLOC(e, e->tileSum, e->n_scan_tiles);
     e->n_atom_blocks = (capo + AZ_TPB - 1) / AZ_TPB;
     e->n_ke_blocks = std::max(e->n_atom_blocks, (capo + AZ_LIST_TPB - 1) / AZ_LIST_TPB); // the list kernel may host the integrator
-    AZ_ALLOC(e, e->partKE, e->n_ke_blocks); AZ_ALLOC(e, e->partU, e->n_ke_blocks);
+    AZ_ALLOC(e, e->partKE, (size_t)2 * e->n_ke_blocks); AZ_ALLOC(e, e->partU, e->n_ke_blocks); // (kinetic-energy partials: by step parity)
     // Verlet list between rebuilds (pair_variant: 0 auto, 1 cell tiles only, 2 list)
     // Pair path (pair_variant 0 = auto): between rebuilds always the Verlet list.  On the every-step schedule a large
     // system also goes through the list (build + force pass per step: 1.9 ms at 4 M atoms against 3.6 ms for the
@@ -640,6 +643,9 @@ extern "C" void az_engine_destroy(az_engine* e)
     for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (int k = 0; k < 2; k++) { if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]); if (e->ev_unpacked[k]) cudaEventDestroy(e->ev_unpacked[k]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->fin_stream) { cudaStreamSynchronize(e->fin_stream); cudaStreamDestroy(e->fin_stream); }
+    if (e->ev_fin_fork) cudaEventDestroy(e->ev_fin_fork);
+    for (int k = 0; k < 2; k++) if (e->ev_fin[k]) cudaEventDestroy(e->ev_fin[k]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -691,6 +697,15 @@ struct Timer {
 #define AZ_COUNT(e, k, nl) do { (e)->launches += (nl); (e)->t_launch[k] += (nl); } while (0)
 
 #include "az_engine_dd.cuh"
+
+// everything on the engine's stream from here on comes behind the finalize kernels that ran beside the list passes
+static int fin_join(az_engine* e)
+{
+    if (e->fin_last >= 0 && e->fin_rec[e->fin_last]) AZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_fin[e->fin_last], 0));
+    e->fin_rec[0] = e->fin_rec[1] = false;
+    e->fin_last = -1;
+    return AZ_OK;
+}
 
 static bool step_rebuilds(const az_engine* e) { return !e->binned || e->rebuild_every <= 1 || e->since_rebuild + 1 >= e->rebuild_every; }
 
@@ -811,7 +826,17 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const int nb = e->n_atom_blocks;
     int c = e->cur;
     const int n_pp = e->use_list ? e->list_nblocks : (e->use_thread ? e->thread_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks)); // live pair partials this step
-    const int slot = (int)(e->steps_done & 1);
+    const int slot = (int)(e->steps_done % 3); // pending momenta / speed bound of the step in flight (three slots: az_kernels.cuh)
+    // az_k_finalize of a step whose integrator rode on the list pass has nothing the next pass waits for: it runs on its own
+    // stream beside the pass of step n + 1 (it was 16 us of every 570 us step, one block reducing 31 250 partials).  What the
+    // two share is double- or triple-buffered: the kinetic-energy partials by step parity, the pending momenta and the speed
+    // bound by step % 3; az_k_finalize writes back only its own fields.  The pass of step n + 2 waits for finalize(n).  Every
+    // step that does anything else with the scalars (no rider, energies, thermostats, bonds, graph capture) first
+    // joins the finalize stream, and the last step of a call never rides, so nothing is pending when a call returns.
+    const int kpar = (int)(e->steps_done & 1);
+    double* const pke = e->partKE + (size_t)kpar * e->n_ke_blocks;
+    const bool ovl = e->fin_overlap && fuse_next && e->fuse_pair && !is_eq_step(e, step) && !want_energy && !e->bonded && !e->use_graph && e->profile != 1;
+    if (!ovl) { int rcj = fin_join(e); if (rcj) return rcj; }
     const int ks = P.step_base ? step - e->call_first : step; // what the kernels get: relative when *step_base supplies the rest
 
     const bool nose = (P.tstat == AZ_TSTAT_NOSE);
@@ -881,6 +906,10 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const bool fusedh = !rebuild && dd_fused(e);  // peer-memory halo: one list launch, ghost-touching blocks last, waiting on arrival flags
     const bool split = !rebuild && !fusedh && !directh && dd_overlap(e);
     dd_note_step_buffer(e, c); // the ghost refresh runs on the halo stream, beside the list blocks that see no ghost
+    if (ovl && e->fin_rec[kpar]) { // this pass's rider overwrites the partials and the slot that finalize(n - 2) worked on
+        AZ_CUDA(e, cudaStreamWaitEvent(st, e->ev_fin[kpar], 0));
+        e->fin_rec[kpar] = false;
+    }
     { // K4: pair forces
         const int pair_mode = e->use_thread ? AZ_PAIR_MODE_THREAD : e->use_warp ? AZ_PAIR_MODE_WARP : (!e->use_list ? AZ_PAIR_MODE_TILE : (rebuild ? AZ_PAIR_MODE_TILE_LIST : AZ_PAIR_MODE_LIST));
         const int pair_timer = pair_mode == AZ_PAIR_MODE_LIST ? AZ_TIMER_PAIR_LIST : AZ_TIMER_PAIR;
@@ -900,9 +929,9 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         if (ride) { // second half kick of this step + kick/drift of the next one inside the list kernel
             const bool rb_next = step_rebuilds(e);
             A.fuse = 1 + (rb_next ? (e->dd ? AZ_IA_WRAP : AZ_IA_BIN) : AZ_IA_STALE);
-            A.slot_next = 1 - slot;
+            A.slot_next = (slot + 1) % 3;
             A.vel = e->vel[c]; A.pos_next = e->pos_alt; A.vel_next = e->vel_alt;
-            A.cellOf = e->cellOf; A.slotOf = e->slotOf; A.cellCount = e->cellCount; A.sc = e->sc; A.partKE = e->partKE;
+            A.cellOf = e->cellOf; A.slotOf = e->slotOf; A.cellCount = e->cellCount; A.sc = e->sc; A.partKE = pke;
             e->clear_counts_bytes = (rb_next && !e->dd) ? sizeof(int) * (size_t)(nc + 1) : 0; // clear_clist for the next step's binning
         }
         int rc;
@@ -967,9 +996,18 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         AZ_LAUNCH(az_k_bonded_reduce, 1, 256, 0, st, e->partBond, e->partAngle, nb, e->sc);
         AZ_COUNT(e, AZ_TIMER_PAIR, 2);
     }
-    if (ride) {
+    if (ride && ovl) { // finalize on its own stream, behind this step's pass
+        AZ_CUDA(e, cudaEventRecord(e->ev_fin_fork, st));
+        AZ_CUDA(e, cudaStreamWaitEvent(e->fin_stream, e->ev_fin_fork, 0));
+        // (not timed as a section: events around a kernel that shares the GPU with the next pass measure the pass)
+        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, e->fin_stream, P, ks, slot, 1 | 16 | (rebuild ? 32 : 64), pke, e->list_nblocks, e->partV, e->partC, n_pp,
+                  e->partU, 0, e->partN, e->pos[c], e->sc, e->revArea[0], e->revArea[1], e->revArea[2]);
+        AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1);
+        AZ_CUDA(e, cudaEventRecord(e->ev_fin[kpar], e->fin_stream));
+        e->fin_rec[kpar] = true; e->fin_last = kpar;
+    } else if (ride) {
         Timer t(e, AZ_TIMER_INTEGRATE_B);
-        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), e->partKE, e->list_nblocks, e->partV, e->partC, n_pp,
+        AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (want_energy ? 2 : 0) | 16 | (rebuild ? 32 : 64), pke, e->list_nblocks, e->partV, e->partC, n_pp,
                   e->partU, 0, e->partN, e->pos[c], e->sc, e->revArea[0], e->revArea[1], e->revArea[2]);
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1);
     } else
@@ -985,9 +1023,9 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             if (fuse_next) {
                 // the next step's kick + drift rides on this pass; its mode follows the next step's schedule
                 const bool rb_next = step_rebuilds(e);
-                const int ns = 1 - slot;
+                const int ns = (slot + 1) % 3;
 #define AZ_BA(TS, MODE) AZ_LAUNCH((az_k_integrate_ba<TS, MODE>), nb, AZ_TPB, 0, st, P, ks, ns, e->pos[c], e->vel[c], e->frc, e->id[c], th, ph, uv, \
-                                  e->partKE, e->partU, e->cellOf, e->slotOf, e->cellCount, e->sc)
+                                  pke, e->partU, e->cellOf, e->slotOf, e->cellCount, e->sc)
                 if (rb_next && e->dd) { if (radi) AZ_BA(true, AZ_IA_WRAP); else AZ_BA(false, AZ_IA_WRAP); }
                 else if (rb_next) {
                     AZ_CUDA(e, cudaMemsetAsync(e->cellCount, 0, sizeof(int) * (nc + 1), st)); // clear_clist (the pair pass has read the counts)
@@ -995,32 +1033,32 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
                 } else { if (radi) AZ_BA(true, AZ_IA_STALE); else AZ_BA(false, AZ_IA_STALE); }
 #undef AZ_BA
             } else if (reset_now) { // zero_vel instead of verlet_2stage (src/main.cu:372-374); apply_tstat still runs the thermostat
-                AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
+                AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], pke);
                 if (radi) { AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 0); AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1); }
             } else if (radi) {
-                AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_integrate_b<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], e->therm[c], e->photons, e->uv, pke, e->partU);
             } else {
-                AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
+                AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, pke, e->partU);
             }
             const int radi_mode = radi ? 4 : 0;
             if (nose) { // second application of the step (apply_tstat): needs this step's kinetic energy, then the quantities
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | drift_mode, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
                 if (e->dd) { int rc = dd_global_nose(e); if (rc) return rc; }
                 else AZ_LAUNCH(az_k_nose_scalars, 1, 1, 0, st, P, e->sc, (const double*)nullptr, 0);
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
-                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 16, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 3);
             } else
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | radi_mode | 16 | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | radi_mode | 16 | drift_mode, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
         } else {
             // equilibration step: the scale factor needs this step's kinetic energy first
-            if (reset_now) AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], e->partKE);
-            else AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, e->partKE, e->partU);
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            if (reset_now) AZ_LAUNCH(az_k_zero_vel, nb, AZ_TPB, 0, st, P, e->vel[c], pke);
+            else AZ_LAUNCH(az_k_integrate_b<false>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->frc, e->id[c], (float2*)nullptr, (const float*)nullptr, (const float*)nullptr, pke, e->partU);
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | (e->dd ? 0 : 8) | emode | drift_mode, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             if (e->dd) { int rc = dd_global_tscale(e); if (rc) return rc; }
             if (radi) AZ_LAUNCH(az_k_tscale<true>, nb, AZ_TPB, 0, st, P, ks, e->pos[c], e->vel[c], e->id[c], e->therm[c], e->photons, e->uv, e->sc, e->partU, 1);
@@ -1030,7 +1068,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
                 AZ_LAUNCH(az_k_vscale, nb, AZ_TPB, 0, st, P, e->vel[c], e->sc);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 2);
             }
-            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, (radi ? 4 : 0) | 16, e->partKE, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+            AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, (radi ? 4 : 0) | 16, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
             AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 4);
         }
@@ -1068,7 +1106,7 @@ static unsigned long long graph_key(const az_engine* e, int first_step, int nste
 {
     unsigned long long h = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
-    mix((unsigned long long)nsteps); mix((unsigned long long)e->since_rebuild); mix(e->binned ? 1 : 0); mix((unsigned long long)(e->steps_done & 1));
+    mix((unsigned long long)nsteps); mix((unsigned long long)e->since_rebuild); mix(e->binned ? 1 : 0); mix((unsigned long long)(e->steps_done % 3));
     mix((unsigned long long)e->cur); mix(e->energy_every_step ? 1 : 0); mix(e->fuse_integrate ? 1 : 0);
     mix((unsigned long long)(uintptr_t)e->pos[0]); mix((unsigned long long)(uintptr_t)e->pos[1]); mix((unsigned long long)(uintptr_t)e->pos_alt);
     mix((unsigned long long)(uintptr_t)e->vel[0]); mix((unsigned long long)(uintptr_t)e->vel[1]); mix((unsigned long long)(uintptr_t)e->vel_alt);
@@ -1615,6 +1653,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "fuse_integrate")) { e->fuse_integrate = value != 0.0; return AZ_OK; }
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
+    if (!strcmp(key, "finalize_overlap")) { int rc = fin_join(e); if (rc) return rc; e->fin_overlap = value != 0.0; return AZ_OK; } // A/B
     if (!strcmp(key, "stencil_table")) { if (value == 0.0) { cudaFree(e->stenTab); e->stenTab = nullptr; } return AZ_OK; } // only ever switched off (A/B, tests)
     if (!strcmp(key, "warp_prune")) { e->warp_prune = value != 0.0; return AZ_OK; }         // A/B of the per-atom cell pruning in the warp sweep
     if (!strcmp(key, "tile_list")) { // A/B of the two list formats; before the first step (the next rebuild writes the chosen format)

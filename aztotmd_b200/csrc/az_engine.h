@@ -69,6 +69,11 @@ struct az_engine {
     std::vector<AzVdw> h_table;
     // device state
     cudaStream_t stream = nullptr;
+    // az_k_finalize beside the next step's list pass (az_engine.cu one_step)
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t ev_fin_fork = nullptr, ev_fin[2] = { nullptr, nullptr };
+    bool fin_rec[2] = { false, false }, fin_overlap = true;
+    int fin_last = -1;
     cudaStream_t pair_stream = nullptr; // fused halo: where the ghost-touching blocks of the list pass are launched (the halo stream)
     cudaEvent_t ev[2 * AZ_N_TIMERS] = {};
     cudaEvent_t ev_step[2] = {};

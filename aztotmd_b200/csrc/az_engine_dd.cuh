@@ -47,7 +47,13 @@ struct AzDDHost {
     int* remoteSlot = nullptr;            // [gs total] where my k-th atom for direction d sits in that neighbour's streams
     int* blockOrder = nullptr;            // launch order of the list blocks: ghost-free ones first
     int slot_epoch = 0;                   // rebuilds so far; the same on all ranks
-    int prev_step_buf = -1;               // number of the position stream the previous step's force pass read
+    int prev_step_buf = -1;
+    // a rebuild's messages (migration, ghost selection) over peer memory too: no NCCL call on the whole stepping path
+    bool peer_rebuild = false;
+    AzPeerArr<AzMigRec> peerMig;
+    AzPeerArr<float4> peerGPos;
+    AzPeerArr<float2> peerGAux;
+    AzPeerArr<int> peerFlags;               // number of the position stream the previous step's force pass read
     float4* pos_bufs[3] = { nullptr, nullptr, nullptr }; // my three position streams by number
     bool pos_ghosts_stale = false;        // pos[] still holds the ghost positions of the last scatter (rebuild or dd_sync_ghosts)
     int halo_dirs = 0;
@@ -425,24 +431,32 @@ static int dd_alloc(az_engine* e)
     const char* no_p2p = getenv("AZTOT_NO_PEER_HALO");
     if (!(no_p2p && no_p2p[0] == '1')) {
         AZ_ALLOC(e, h->stagePos, (size_t)2 * D.gr[AZ_NDIR]); AZ_ALLOC(e, h->stageAux, (size_t)2 * D.gr[AZ_NDIR]);
-        AZ_ALLOC(e, h->haloFlags, 2 * AZ_NDIR); AZ_ALLOC(e, h->putDone, 2);
+        AZ_ALLOC(e, h->haloFlags, 4 * AZ_NDIR); AZ_ALLOC(e, h->putDone, 4);
         AZ_ALLOC(e, h->remoteSlot, D.gs[AZ_NDIR] > 0 ? D.gs[AZ_NDIR] : 1);
         AZ_ALLOC(e, h->blockOrder, e->list_nblocks > 0 ? e->list_nblocks : 1);
         h->pos_bufs[0] = e->pos[0]; h->pos_bufs[1] = e->pos[1]; h->pos_bufs[2] = e->pos_alt ? e->pos_alt : e->pos[0];
-        void* local[7] = { h->stagePos, h->stageAux, h->haloFlags, h->remoteSlot, h->pos_bufs[0], h->pos_bufs[1], h->pos_bufs[2] };
+        const int NSH = 10;
+        void* local[NSH] = { h->stagePos, h->stageAux, h->haloFlags, h->remoteSlot, h->pos_bufs[0], h->pos_bufs[1], h->pos_bufs[2], h->mRecv, h->gRecvPos, h->gRecvAux };
         std::vector<void*> remote;
-        const int rc = h->comm->share(local, 7, &remote);
+        memset(&h->peerMig, 0, sizeof(h->peerMig)); memset(&h->peerGPos, 0, sizeof(h->peerGPos));
+        memset(&h->peerGAux, 0, sizeof(h->peerGAux)); memset(&h->peerFlags, 0, sizeof(h->peerFlags));
+        const int rc = h->comm->share(local, NSH, &remote);
         if (rc == AZ_OK) {
             for (int dir = 0; dir < AZ_NDIR; dir++) {
                 const int pr = h->peer[dir];
                 if (pr < 0) continue;
-                h->peerPtr.pos[dir] = (float4*)remote[(size_t)pr * 7 + 0];
-                h->peerPtr.aux[dir] = (float2*)remote[(size_t)pr * 7 + 1];
-                h->peerPtr.flags[dir] = (int*)remote[(size_t)pr * 7 + 2];
-                h->peerPtr.slot[dir] = (int*)remote[(size_t)pr * 7 + 3];
-                for (int b = 0; b < 3; b++) h->peerPtr.pbuf[dir][b] = (float4*)remote[(size_t)pr * 7 + 4 + b];
+                h->peerPtr.pos[dir] = (float4*)remote[(size_t)pr * NSH + 0];
+                h->peerPtr.aux[dir] = (float2*)remote[(size_t)pr * NSH + 1];
+                h->peerPtr.flags[dir] = (int*)remote[(size_t)pr * NSH + 2];
+                h->peerPtr.slot[dir] = (int*)remote[(size_t)pr * NSH + 3];
+                for (int b = 0; b < 3; b++) h->peerPtr.pbuf[dir][b] = (float4*)remote[(size_t)pr * NSH + 4 + b];
+                h->peerMig.p[dir] = (AzMigRec*)remote[(size_t)pr * NSH + 7];
+                h->peerGPos.p[dir] = (float4*)remote[(size_t)pr * NSH + 8];
+                h->peerGAux.p[dir] = (float2*)remote[(size_t)pr * NSH + 9];
+                h->peerFlags.p[dir] = (int*)remote[(size_t)pr * NSH + 2];
             }
             h->p2p = true;
+            { const char* no_pr = getenv("AZTOT_NO_PEER_REBUILD"); h->peer_rebuild = !(no_pr && no_pr[0] == '1'); }
             for (int dir = 0; dir < AZ_NDIR; dir++) if (h->peer[dir] >= 0) h->halo_dirs |= 1 << dir;
             // the fused single-launch list pass: needs the list (per-block ghost flags) and positions only (radii travel in the aux stream)
             const char* no_fuse = getenv("AZTOT_NO_FUSED_HALO");
@@ -498,20 +512,39 @@ static int dd_rebuild(az_engine* e, int c)
         AZ_LAUNCH(az_k_mig_classify, nbo, AZ_TPB, 0, st, P, D, e->pos[c], h->migList, h->stay, flags);
         AZ_LAUNCH(az_k_mig_pack, blocks(D.ms[AZ_NDIR]), AZ_TPB, 0, st, D, h->migList, e->pos[c], e->vel[c], e->id[c], th, h->mSend);
         std::vector<AzP2P> ops;
-        dd_add_ops(h, ops, h->mSend, D.ms, h->mRecv, D.mr, sizeof(AzMigRec));
-        int rc = dd_exchange(e, ops);
-        if (rc) return rc;
-        AZ_LAUNCH(az_k_mig_unpack, blocks(D.mr[AZ_NDIR]), AZ_TPB, 0, st, D, h->mRecv, e->pos[c], e->vel[c], e->id[c], th, h->stay, flags);
+        int rc;
+        const bool pr = h->peer_rebuild;
+        const int epoch = h->slot_epoch + 1; // (advanced below, with the slot tables)
+        const int* wait = pr ? h->haloFlags : nullptr;
+        AzOffsets om, og, omr, ogr;
+        memcpy(om.o, D.ms, sizeof(om.o)); memcpy(og.o, D.gs, sizeof(og.o)); memcpy(omr.o, D.mr, sizeof(omr.o)); memcpy(ogr.o, D.gr, sizeof(ogr.o));
+        if (pr) {
+            AzPeerArr<float2> none; memset(&none, 0, sizeof(none));
+            AZ_LAUNCH((az_k_peer_send<AzMigRec, float2>), blocks(D.ms[AZ_NDIR]), AZ_TPB, 0, st, om, omr, h->cnt->migCount, h->mSend, h->peerMig, (const float2*)nullptr, none,
+                      h->peerFlags, 2 * AZ_NDIR, epoch, h->putDone + 2);
+        } else {
+            dd_add_ops(h, ops, h->mSend, D.ms, h->mRecv, D.mr, sizeof(AzMigRec));
+            rc = dd_exchange(e, ops);
+            if (rc) return rc;
+        }
+        AZ_LAUNCH(az_k_mig_unpack, blocks(D.mr[AZ_NDIR]), AZ_TPB, 0, st, D, h->mRecv, e->pos[c], e->vel[c], e->id[c], th, h->stay, flags,
+                  wait ? wait + 2 * AZ_NDIR : nullptr, epoch, h->halo_dirs);
         AZ_LAUNCH(az_k_ghost_select, nbo, AZ_TPB, 0, st, P, D, e->pos[c], h->stay, h->sendList, flags);
         AZ_LAUNCH(az_k_ghost_pack<true>, blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, D, h->sendList, e->pos[c], e->id[c], th, h->gSendPos, h->gSendAux);
-        ops.clear();
-        dd_add_ops(h, ops, h->gSendPos, D.gs, h->gRecvPos, D.gr, sizeof(float4));
-        std::vector<AzP2P> ops2;
-        dd_add_ops(h, ops2, h->gSendAux, D.gs, h->gRecvAux, D.gr, sizeof(float2));
-        ops.insert(ops.end(), ops2.begin(), ops2.end());
-        rc = dd_exchange(e, ops);
-        if (rc) return rc;
-        AZ_LAUNCH(az_k_ghost_append, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->gRecvPos, h->gRecvAux, e->pos[c], e->vel[c], e->id[c], th, h->stay, flags);
+        if (pr) {
+            AZ_LAUNCH((az_k_peer_send<float4, float2>), blocks(D.gs[AZ_NDIR]), AZ_TPB, 0, st, og, ogr, h->cnt->sendCount, h->gSendPos, h->peerGPos, (const float2*)h->gSendAux, h->peerGAux,
+                      h->peerFlags, 3 * AZ_NDIR, epoch, h->putDone + 3);
+        } else {
+            ops.clear();
+            dd_add_ops(h, ops, h->gSendPos, D.gs, h->gRecvPos, D.gr, sizeof(float4));
+            std::vector<AzP2P> ops2;
+            dd_add_ops(h, ops2, h->gSendAux, D.gs, h->gRecvAux, D.gr, sizeof(float2));
+            ops.insert(ops.end(), ops2.begin(), ops2.end());
+            rc = dd_exchange(e, ops);
+            if (rc) return rc;
+        }
+        AZ_LAUNCH(az_k_ghost_append, blocks(D.gr[AZ_NDIR]), AZ_TPB, 0, st, D, h->gRecvPos, h->gRecvAux, e->pos[c], e->vel[c], e->id[c], th, h->stay, flags,
+                  wait ? wait + 3 * AZ_NDIR : nullptr, epoch, h->halo_dirs);
         AZ_COUNT(e, AZ_TIMER_MIGRATE, 7);
     }
     const int nc = P.g.ncell_local;

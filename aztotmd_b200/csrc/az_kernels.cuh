@@ -44,7 +44,7 @@ __device__ __forceinline__ void az_block_sum(double (&v)[NV], double* smem /* [N
 // Device-resident step scalars (what reset_quantities / calc_quantities keep in cudaMD).
 struct AzScalars {
     double posMom[3], negMom[3];              // cumulative (src/cuMDfunc.cu:72-104)
-    double posMomPend[2][3], negMomPend[2][3]; // crossings of the step in flight (slot = step parity); az_k_finalize folds them in
+    double posMomPend[3][3], negMomPend[3][3]; // crossings of the step in flight (slot = step % 3); az_k_finalize folds them in
     int acPos[AZ_MAX_SPECIES][3], acNeg[AZ_MAX_SPECIES][3];
     double engElecField;                      // per step
     double engKin, engVdW, engCoul1, engTemp; // per step, reduced
@@ -63,8 +63,9 @@ struct AzScalars {
     float x_first; // pos[0].x at publish time (print_stat's x1)
     unsigned long long nPairs; // unique in-range pairs of the last energy-reducing force pass
     unsigned long long nVisits; // the same, counted from both sides (a brick sees cross-brick pairs from one side only)
-    unsigned vmax2_bits[2]; // max |v|^2 of a stale-cell step (float bits), slot = step & 1: the fused kick+drift kernel
-                            // writes the next step's slot before this step's az_k_finalize has consumed its own
+    unsigned vmax2_bits[3]; // max |v|^2 of a stale-cell step (float bits), slot = step % 3: the fused kick+drift kernel writes
+                            // the next step's slot before this step's az_k_finalize has consumed its own, and az_k_finalize of
+                            // step n may still be running (on its own stream) while the pass of step n + 1 writes slot n + 2
     float drift;         // upper bound of any atom's displacement since the last rebuild
 };
 #define AZ_FLAG_SKIN 1
@@ -508,6 +509,7 @@ az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode
         az_block_sum<1>(c, sm);
         if (threadIdx.x == 0) { sc->nPairs = (unsigned long long)(0.5 * c[0] + 0.25); sc->nVisits = (unsigned long long)(c[0] + 0.5); }
     }
+    int new_flags = 0, ring_idx = -1;
     if (threadIdx.x == 0) {
     if (mode & (32 | 64)) { // this step's face crossings join the cumulative momenta (put_periodic, src/cuMDfunc.cu:72-104)
         for (int a = 0; a < 3; a++) {
@@ -519,9 +521,9 @@ az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode
     if (mode & 64) { // stale-cell step: every atom moved by at most vmax*dt
         sc->drift += sqrtf(__uint_as_float(sc->vmax2_bits[slot])) * P.tSt;
         sc->vmax2_bits[slot] = 0u;
-        if (2.f * sc->drift > P.skin) sc->overflow |= AZ_FLAG_SKIN;
+        if (2.f * sc->drift > P.skin) new_flags |= AZ_FLAG_SKIN;
     }
-    if ((mode & 1) && !(v[0] == v[0])) sc->overflow |= AZ_FLAG_NAN;
+    if ((mode & 1) && !(v[0] == v[0])) new_flags |= AZ_FLAG_NAN;
     if (mode & 1) { sc->engKin = v[0]; sc->engKin_f = (float)v[0]; }
     if (mode & 2) { sc->engVdW = v[1]; sc->engCoul1 = v[2]; }
     if (mode & 4) sc->engTemp = v[3];
@@ -550,23 +552,39 @@ az_k_finalize(const __grid_constant__ AzParams P, int step_k, int slot, int mode
                 np[a] = k * (nm[a] - sc->negMomBuf[i][a]) * ra[a];
             }
             i--; if (i < 0) i = AZ_N_MOM - 1;
+            ring_idx = i;
             for (int a = 0; a < 3; a++) { sc->posMomBuf[i][a] = pm[a]; sc->negMomBuf[i][a] = nm[a]; }
             sc->iMom++; if (sc->iMom >= AZ_N_MOM) sc->iMom = 0;
             tot = (pp[0] + pp[1] + pp[2] + np[0] + np[1] + np[2]) / 6.f;
             sc->pressure = tot;
         } else if (step >= 0) {
+            ring_idx = step;
             for (int a = 0; a < 3; a++) { sc->posMomBuf[step][a] = pm[a]; sc->negMomBuf[step][a] = nm[a]; }
         }
         sc->step = step;
         sc->x_first = pos[0].x;
     }
+    // Write back ONLY what this kernel owns.  Counters and flags that other kernels update with atomics (face-crossing
+    // counters, the pending momenta and the speed bound of OTHER slots, the sticky flags, the list diagnostics) are left
+    // alone: the pass of the next step may be running beside this kernel (az_engine.cu: finalize on its own stream).
+    if (mode & (32 | 64)) {
+        for (int a = 0; a < 3; a++) {
+            gsc->posMom[a] = sc->posMom[a]; gsc->negMom[a] = sc->negMom[a];
+            gsc->posMomPend[slot][a] = 0.0; gsc->negMomPend[slot][a] = 0.0;
+        }
+        gsc->drift = sc->drift; gsc->vmax2_bits[slot] = 0u;
     }
-    __syncthreads();
-    {
-        const int nw = (int)(sizeof(AzScalars) / sizeof(int));
-        const int* src = reinterpret_cast<const int*>(&ssc);
-        int* dst = reinterpret_cast<int*>(gsc);
-        for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
+    if (new_flags) atomicOr(&gsc->overflow, new_flags);
+    if (mode & (1 | 8)) { gsc->engKin = sc->engKin; gsc->engKin_f = sc->engKin_f; }
+    if (mode & 2) { gsc->engVdW = sc->engVdW; gsc->engCoul1 = sc->engCoul1; gsc->nPairs = sc->nPairs; gsc->nVisits = sc->nVisits; }
+    if (mode & 4) gsc->engTemp = sc->engTemp;
+    if (mode & 8) gsc->tscale_k = sc->tscale_k;
+    if (mode & 16) {
+        gsc->engPot = sc->engPot; gsc->engTot = sc->engTot; gsc->pressure = sc->pressure; gsc->iMom = sc->iMom;
+        gsc->step = sc->step; gsc->x_first = sc->x_first;
+        if (ring_idx >= 0)
+            for (int a = 0; a < 3; a++) { gsc->posMomBuf[ring_idx][a] = sc->posMomBuf[ring_idx][a]; gsc->negMomBuf[ring_idx][a] = sc->negMomBuf[ring_idx][a]; }
+    }
     }
 }
 
