@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--list-dbg", type=int, default=0, help="diagnostic variants of the list pass (results are NOT physical)")
     ap.add_argument("--no-halo-overlap", action="store_true", help="multi-GPU: refresh the ghosts on the engine's stream (A/B of the overlap)")
     ap.add_argument("--cell-div", type=int, default=1, help="cell_list = (rc + skin) / cell_div")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-halo-check", action="store_true", help="multi-GPU: skip the comparison with a single-GPU run of the same lattice")
     ap.add_argument("--no-small-deck", action="store_true", help="skip the 40 000-atom case-study-1 leg of the default run")
