@@ -835,8 +835,13 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     // joins the finalize stream, and the last step of a call never rides, so nothing is pending when a call returns.
     const int kpar = (int)(e->steps_done & 1);
     double* const pke = e->partKE + (size_t)kpar * e->n_ke_blocks;
-    const bool ovl = e->fin_overlap && fuse_next && e->fuse_pair && !is_eq_step(e, step) && !want_energy && !e->bonded && !e->use_graph && e->profile != 1;
-    if (!ovl) { int rcj = fin_join(e); if (rcj) return rcj; }
+    const bool ovl_ok = e->fin_overlap && fuse_next && !is_eq_step(e, step) && !want_energy && !e->bonded && e->profile != 1;
+    const bool ovl = ovl_ok && e->fuse_pair && !e->use_graph;
+    // ... and without a rider (the small decks: bin + sort + sweep every step): az_k_finalize is the last of the step's six short
+    // kernels; on its own stream it runs beside scan / sort / pair sweep of the next step and is joined before that step's
+    // az_k_integrate_ba (the next kernel that touches the scalars and the partials), also inside a captured graph
+    const bool ovl2 = ovl_ok && !e->fuse_pair && P.tstat != AZ_TSTAT_NOSE && e->reset_vels <= 0 && !P.has_efield && !e->ew.nk && !e->dd;
+    if (!ovl && !ovl2) { int rcj = fin_join(e); if (rcj) return rcj; }
     const int ks = P.step_base ? step - e->call_first : step; // what the kernels get: relative when *step_base supplies the rest
 
     const bool nose = (P.tstat == AZ_TSTAT_NOSE);
@@ -1012,6 +1017,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 1);
     } else
     { // K5: half kick + KE (+ thermostat) + derived quantities
+        { int rcj = fin_join(e); if (rcj) return rcj; } // (the previous step's finalize, if it ran beside this step's sweep)
         Timer t(e, AZ_TIMER_INTEGRATE_B);
         const int drift_mode = rebuild ? 32 : 64;
         const int emode = want_energy ? 2 : 0;
@@ -1050,6 +1056,13 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
                 AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 16, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                           e->revArea[0], e->revArea[1], e->revArea[2]);
                 AZ_COUNT(e, AZ_TIMER_INTEGRATE_B, 3);
+            } else if (ovl2) { // beside the next step's scan / sort / sweep
+                AZ_CUDA(e, cudaEventRecord(e->ev_fin_fork, st));
+                AZ_CUDA(e, cudaStreamWaitEvent(e->fin_stream, e->ev_fin_fork, 0));
+                AZ_LAUNCH(az_k_finalize, 1, 1024, 0, e->fin_stream, P, ks, slot, 1 | emode | radi_mode | 16 | drift_mode, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
+                          e->revArea[0], e->revArea[1], e->revArea[2]);
+                AZ_CUDA(e, cudaEventRecord(e->ev_fin[kpar], e->fin_stream));
+                e->fin_rec[kpar] = true; e->fin_last = kpar;
             } else
             AZ_LAUNCH(az_k_finalize, 1, 1024, 0, st, P, ks, slot, 1 | emode | radi_mode | 16 | drift_mode, pke, nb, e->partV, e->partC, n_pp, e->partU, nb, e->partN, e->pos[c], e->sc,
                       e->revArea[0], e->revArea[1], e->revArea[2]);
