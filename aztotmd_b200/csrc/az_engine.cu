@@ -1226,6 +1226,7 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         e->launches = before.launches;
         for (int k = 0; k < AZ_N_TIMERS; k++) e->t_launch[k] = before.t_launch[k];
         e->steps_done = steps_before; e->last_step = last_before; e->energy_valid = evalid_before;
+        e->fin_rec[0] = e->fin_rec[1] = false; e->fin_last = -1; // (a call starts and ends with the finalize stream joined)
     };
     AZ_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
     int rc = run_steps(e, first_step, nsteps);

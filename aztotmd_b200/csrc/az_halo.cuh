@@ -181,28 +181,41 @@ az_k_ghost_select(const __grid_constant__ AzParams P, const __grid_constant__ Az
                   const int* __restrict__ stay, int* __restrict__ sendList, int* __restrict__ flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(D.cnt->n_owned + D.cnt->n_arrived, D.cap_owned) || !stay[i]) return;
-    int ci[3];
-    az_global_cell(P, pos[i], ci);
-    bool lo[3], hi[3];
+    const bool live = i < min(D.cnt->n_owned + D.cnt->n_arrived, D.cap_owned) && stay[i];
+    bool lo[3] = { false, false, false }, hi[3] = { false, false, false };
+    if (live) {
+        int ci[3];
+        az_global_cell(P, pos[i], ci);
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        const int owned = P.g.ohi[a] - P.g.olo[a];
-        const int rel = az_rel_cell(P.g, a, ci[a]);
-        lo[a] = P.g.dec[a] && rel < P.g.sten[a];
-        hi[a] = P.g.dec[a] && rel >= owned - P.g.sten[a];
+        for (int a = 0; a < 3; a++) {
+            const int owned = P.g.ohi[a] - P.g.olo[a];
+            const int rel = az_rel_cell(P.g, a, ci[a]);
+            lo[a] = P.g.dec[a] && rel < P.g.sten[a];
+            hi[a] = P.g.dec[a] && rel >= owned - P.g.sten[a];
+        }
     }
-    if (!(lo[0] | hi[0] | lo[1] | hi[1] | lo[2] | hi[2])) return;
+    const bool any = live && (lo[0] | hi[0] | lo[1] | hi[1] | lo[2] | hi[2]);
+    if (!__any_sync(0xffffffffu, any)) return; // (whole warps of interior atoms leave here)
+    const int lane = threadIdx.x & 31;
     for (int dir = 0; dir < AZ_NDIR; dir++) {
         const int capacity = D.gs[dir + 1] - D.gs[dir] - 1;
         if (dir == AZ_DIR_SELF || capacity <= 0) continue;
         const int d[3] = { dir / 9 - 1, (dir / 3) % 3 - 1, dir % 3 - 1 };
-        bool ok = true;
+        bool ok = any;
 #pragma unroll
         for (int a = 0; a < 3; a++) ok = ok && (d[a] == 0 || (d[a] < 0 ? lo[a] : hi[a]));
-        if (!ok) continue;
-        const int slot = atomicAdd(&D.cnt->sendCount[dir], 1);
-        if (slot < capacity) sendList[D.gs[dir] + 1 + slot] = i; else atomicOr(flags, AZ_FLAG_HALO);
+        // one atomic per warp and direction: the atoms of a warp (neighbours in the sorted stream) get CONSECUTIVE entries, so
+        // the puts of the following steps store runs of consecutive ghost slots on the neighbour (its sort keeps the order of
+        // mine) -- whole 128-byte lines over NVLink instead of one 16-byte packet per atom
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (!m) continue;
+        int base = 0;
+        if (lane == __ffs((int)m) - 1) base = atomicAdd(&D.cnt->sendCount[dir], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+        if (ok) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < capacity) sendList[D.gs[dir] + 1 + slot] = i; else atomicOr(flags, AZ_FLAG_HALO);
+        }
     }
 }
 
