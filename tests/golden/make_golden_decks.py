@@ -11,7 +11,7 @@ cs2 (4 000 atoms, surk + radiative thermostat, 10 000 steps): no build of the re
     CPU restatement's (oracle/az_oracle.c, pinned on the reference's device source) window statistics over 10 000
     steps -> tests/golden/deck_cs2_oracle_windows.json
 
-usage: python tests/golden/make_golden_decks.py [cs1] [cs2]
+usage: python tests/golden/make_golden_decks.py [cs1] [cs2] [drift]
 """
 import ctypes as C
 import json
@@ -70,6 +70,33 @@ def make_cs1():
     print("  ->", out, os.path.getsize(out), "bytes")
 
 
+def make_drift():
+    """The NVE energy series of the reference's serial build (double precision) on the 4 000-atom LJ deck of
+    tests/test_gpu_long.py::test_host_driver_lj_deck_outputs (decks.lj_argon_deck(10, seed 7), rc without a shift): the
+    energy is not conserved there either -- every pair that crosses rc changes E by |U(rc)| -- and the engine's drift
+    (from step 50 on, like this series) is judged against this one, not against zero -> tests/golden/deck_lj4000_ref_serial_drift.json"""
+    from aztotmd_b200 import decks
+    from make_golden import run
+    steps = list(range(0, 401, 50))
+    series = []
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "lj4000")
+        os.makedirs(d)
+        info = decks.lj_argon_deck(d, 10, nstep=400, stat=50, cell_list=8.488 + 0.5, seed=7)
+        open(os.path.join(d, "control.txt"), "a").write("\nhist 100000\n")
+        for n in steps[1:]:
+            dumps, line = run(d, n, "fast")
+            series.append((n, dumps["final"]["engKin"], dumps["final"]["engVdW"]))  # (the harness has no kinetic energy before the first step)
+    e = np.array([k + v for _, k, v in series])
+    out = os.path.join(HERE, "deck_lj4000_ref_serial_drift.json")
+    json.dump({"deck": "decks.lj_argon_deck(ncell=10, nstep=400, stat=50, cell_list=8.988, seed=7): 4000 Ar, rc = 2.5 sigma unshifted, dt 1 fs, init_vel gaus under srand(1)",
+               "steps": [s for s, _, _ in series], "engKin": [k for _, k, _ in series], "engVdW": [v for _, _, v in series],
+               "max_abs_dE": float(np.abs(e - e[0]).max()), "max_abs_dE_over_KE0": float(np.abs(e - e[0]).max() / series[0][1]),
+               "source": "oracle/_ref/ref_serial_harness (the reference's own serial sources, double precision)"}, open(out, "w"), indent=1)
+    print("drift", [round(float(x - e[0]), 6) for x in e], "max |dE| / KE0 = %.3g" % (np.abs(e - e[0]).max() / series[0][1]))
+    print("  ->", out)
+
+
 def make_cs2():
     import azt
     from aztotmd_b200 import abi
@@ -119,3 +146,5 @@ if __name__ == "__main__":
         make_cs1()
     if "cs2" in what:
         make_cs2()
+    if "drift" in what:
+        make_drift()
