@@ -277,6 +277,22 @@ def case_eight_bricks_list_direct_halo(lib, devices=None):
         e1.close()
 
 
+def case_bricks_tile_lists(lib, devices=None):
+    """list_format 2 (tile lists, az_tlist.cuh) on bricks: footprints that contain ghost atoms, the ghost-touching tiles waiting on
+    the arrival flags of the direct halo -- against one engine (single-step calls) and against the global rows (one call)."""
+    s = azt.lj_system(ncell=(8, 5, 5), seed=25, cell_size=9.3)
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=7, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices, list_format=2)
+    a = run_bricks(lib, s, 2, (2, 1, 1), 10, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=2)
+    b = run_bricks(lib, s, 2, (2, 1, 1), 10, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=1)
+    for x, y in zip(a, b):
+        assert x["info"].tile_list == 1 and y["info"].tile_list == 0
+        assert x["stats"][-1].n_pairs == y["stats"][-1].n_pairs and np.array_equal(x["dump"]["ids"], y["dump"]["ids"])
+        if devices is None:  # (emulator: the global rows take the packed row loop, equal to rounding)
+            assert np.abs(x["dump"]["frc"] - y["dump"]["frc"]).max() <= 1e-5 * np.abs(y["dump"]["frc"]).max()
+        else:
+            assert np.array_equal(x["dump"]["frc"], y["dump"]["frc"]) and np.array_equal(x["atoms"]["pos"], y["atoms"]["pos"])
+
+
 def case_bricks_migration_hot_atoms(lib, devices=None):
     # hot and fast: atoms cross brick faces every few steps
     s = azt.lj_system(ncell=(8, 5, 5), seed=26, temperature=3000.0)
