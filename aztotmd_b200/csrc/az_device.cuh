@@ -10,12 +10,31 @@
 #define AZ_DYN_SMEM(T, name) T* name = (T*)az_emu_dyn_smem()
 #define AZ_LAUNCH(kern, grid, block, smem, stream, ...) \
     az_emu_launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#define AZ_LAUNCH_PDL(on, kern, grid, block, smem, stream, ...) AZ_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__)
+static inline void az_pdl_trigger() {}
+static inline void az_pdl_wait() {}
 #else
 #include <cuda_runtime.h>
 #define AZ_DYN_SMEM(T, name) \
     extern __shared__ __align__(16) unsigned char az_dyn_smem_raw[]; \
     T* name = reinterpret_cast<T*>(az_dyn_smem_raw)
 #define AZ_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// Programmatic dependent launch (sm_90+): the kernel may be brought onto the SMs while its predecessor on the stream is still
+// running -- every block of the predecessor has called az_pdl_trigger() -- and parks in az_pdl_wait() until the predecessor has
+// finished and its writes are visible.  What it removes is the launch latency between the short kernels of the small decks
+// (also as an edge of a captured graph).  `on` = false is the plain launch.
+#define AZ_LAUNCH_PDL(on, kern, grid, block, smem, strm_, ...) do { \
+        if (on) { \
+            cudaLaunchConfig_t cfg_ = {}; \
+            cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = (strm_); \
+            cudaLaunchAttribute at_[1]; \
+            at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at_[0].val.programmaticStreamSerializationAllowed = 1; \
+            cfg_.attrs = at_; cfg_.numAttrs = 1; \
+            cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__); \
+        } else kern<<<(grid), (block), (smem), (strm_)>>>(__VA_ARGS__); \
+    } while (0)
+__device__ __forceinline__ void az_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void az_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 #include <stdint.h>
 #include "../../include/aztot_b200.h"

@@ -470,6 +470,7 @@ int az_engine_init(az_engine* e, const az_system_desc* d, const az_cuda_opts* o)
       if (e->thread_nblocks > np) np = e->thread_nblocks;
       AZ_ALLOC(e, e->partV, np); AZ_ALLOC(e, e->partC, np); AZ_ALLOC(e, e->partN, np); e->n_pair_partials = np; }
     AZ_ALLOC(e, e->sc, 1);
+    { const char* no_pdl = getenv("AZTOT_NO_PDL"); e->pdl = !e->dd && capo <= 200000 && !(no_pdl && no_pdl[0] == '1'); }
     if (e->use_warp) { // the stencil of every owned cell, once (az_k_stencil_table)
         const AzGrid& g = e->P.g;
         const int S = (2 * g.sten[0] + 1) * (2 * g.sten[1] + 1) * (2 * g.sten[2] + 1);
@@ -821,6 +822,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const int n = e->n, nc = P.g.ncell_local;
     cudaStream_t st = e->stream;
     const bool rebuild = step_rebuilds(e);
+    const bool pdl = e->pdl && e->profile == 0;
     const bool radi = (P.tstat == AZ_TSTAT_RADI);
     const bool eq_step = is_eq_step(e, step);
     const int nb = e->n_atom_blocks;
@@ -874,7 +876,7 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         {
             Timer t(e, AZ_TIMER_SCAN);
             if (e->n_scan_tiles <= AZ_SCAN_ONE_LAUNCH) {
-                AZ_LAUNCH(az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, (const int*)nullptr, e->first);
+                AZ_LAUNCH_PDL(pdl, az_k_scan_apply, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, (const int*)e->cellCount, nc, (const int*)nullptr, e->first);
                 AZ_COUNT(e, AZ_TIMER_SCAN, 1);
             } else {
                 AZ_LAUNCH(az_k_scan_tiles, e->n_scan_tiles, AZ_SCAN_TPB, 0, st, e->cellCount, nc, e->tileSum);
@@ -884,13 +886,15 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
         }
         {
             Timer t(e, AZ_TIMER_SORT);
-            AZ_LAUNCH(az_k_sort_keys, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
+            AZ_LAUNCH_PDL(pdl, az_k_sort_keys, nb, AZ_TPB, 0, st, n, (const int*)nullptr, (const int*)e->cellOf, (const int*)e->slotOf, (const int*)e->first, (const int*)e->id[c], e->keyTmp);
             if (e->use_therm)
-                AZ_LAUNCH(az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, (int*)nullptr, e->whereId);
+                AZ_LAUNCH_PDL(pdl, az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, (const int*)e->cellOf, (const int*)e->first, (const int*)e->cellCount, (const int*)e->keyTmp,
+                              (const float4*)e->pos[c], (const float4*)e->vel[c], (const int*)e->id[c], (const float2*)e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c],
+                              e->cellSorted, (int*)nullptr, e->whereId);
             else
-                AZ_LAUNCH(az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                          e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, (int*)nullptr, e->whereId);
+                AZ_LAUNCH_PDL(pdl, az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, (const int*)e->cellOf, (const int*)e->first, (const int*)e->cellCount, (const int*)e->keyTmp,
+                              (const float4*)e->pos[c], (const float4*)e->vel[c], (const int*)e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr,
+                              e->cellSorted, (int*)nullptr, e->whereId);
             AZ_COUNT(e, AZ_TIMER_SORT, 2);
         }
         c = e->cur = 1 - c; // refresh_arrays (src/cuSort.cu:74-100): host-side ping-pong
@@ -1668,6 +1672,7 @@ extern "C" int az_engine_set_option(az_engine* e, const char* key, double value)
     if (!strcmp(key, "list_dbg")) { e->list_dbg = (int)value; return AZ_OK; }
     if (!strcmp(key, "list_fast")) { if (value == 0.0) e->list_fast = false; return AZ_OK; } // only ever switched off (tests)
     if (!strcmp(key, "finalize_overlap")) { int rc = fin_join(e); if (rc) return rc; e->fin_overlap = value != 0.0; return AZ_OK; } // A/B
+    if (!strcmp(key, "pdl")) { e->pdl = value != 0.0 && !e->dd; return AZ_OK; } // A/B of the programmatic dependent launches
     if (!strcmp(key, "stencil_table")) { if (value == 0.0) { cudaFree(e->stenTab); e->stenTab = nullptr; } return AZ_OK; } // only ever switched off (A/B, tests)
     if (!strcmp(key, "warp_prune")) { e->warp_prune = value != 0.0; return AZ_OK; }         // A/B of the per-atom cell pruning in the warp sweep
     if (!strcmp(key, "tile_list")) { // A/B of the two list formats; before the first step (the next rebuild writes the chosen format)

@@ -46,6 +46,7 @@ struct az_engine {
     int list_nblocks = 0, nbr_cap = 0, nbr_stride = 0;
     int warp_nblocks = 0;     // az_k_pair_warp: one warp per owned atom
     bool warp_prune = true;   // az_k_pair_warp: drop the stencil cells an atom cannot reach from where it stands
+    bool pdl = false;         // small systems: scan / sort / sweep are programmatic dependent launches (az_device.cuh)
     int2* stenTab = nullptr;  // az_k_pair_warp: tabulated stencil of every owned cell
     int stenS = 0;
     int thread_nblocks = 0;   // az_k_pair_thread: one thread per owned atom

@@ -202,6 +202,7 @@ az_k_scan_apply(const int* __restrict__ count, int n, const int* __restrict__ ti
 {
     __shared__ int sm[32];
     __shared__ int s_off;
+    az_pdl_trigger(); az_pdl_wait(); // (programmatic dependent launch: no-ops on a plain launch)
     // offset of this tile = sum of the tile sums before it
     int off = 0;
     if (tileSum) { for (int k = threadIdx.x; k < (int)blockIdx.x; k += AZ_SCAN_TPB) off += tileSum[k]; }
@@ -244,6 +245,7 @@ static __global__ void __launch_bounds__(AZ_TPB)
 az_k_sort_keys(int n, const int* __restrict__ n_dyn, const int* __restrict__ cellOf, const int* __restrict__ slotOf,
                const int* __restrict__ first, const int* __restrict__ id, int* __restrict__ keyTmp)
 {
+    az_pdl_trigger(); az_pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dyn) n = *n_dyn;
     if (i < n && cellOf[i] >= 0) keyTmp[first[cellOf[i]] + slotOf[i]] = id[i]; // cell -1: the atom left this brick
@@ -258,6 +260,7 @@ az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ 
                   float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o,
                   float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex, int* __restrict__ whereId)
 {
+    az_pdl_trigger(); az_pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dyn) n = *n_dyn;
     if (i >= n) return;
@@ -399,6 +402,7 @@ az_k_integrate_ba(const __grid_constant__ AzParams P, int step_k, int slot_next,
                   double* __restrict__ partU, int* __restrict__ cellOf, int* __restrict__ slotOf, int* __restrict__ cellCount,
                   AzScalars* __restrict__ sc)
 {
+    az_pdl_trigger(); // (the scan behind this kernel may be brought in early; it parks until the binning is complete)
     const int step = AZ_STEP(P, step_k);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0, ut = 0.0, eF = 0.0;

@@ -1135,6 +1135,7 @@ az_k_pair_warp(const __grid_constant__ AzParams P, const __grid_constant__ AzPai
 {
     __shared__ AzVdw s_tab[SINGLE ? 1 : AZ_MAX_SPECIES * AZ_MAX_SPECIES];
     __shared__ double s_red[96];
+    az_pdl_wait(); // (programmatic dependent launch behind the sort: a no-op on a plain launch)
     const AzGrid& g = P.g;
     const int tid = threadIdx.x, lane = tid & 31;
     if (!SINGLE) {

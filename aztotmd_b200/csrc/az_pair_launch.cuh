@@ -88,7 +88,7 @@ static int az_pair_list_go(az_engine* e, const AzPairArgs& A)
 template <int VK, int CK, bool SINGLE, bool RADII, bool ENERGY>
 static int az_pair_warp_go(az_engine* e, const AzPairArgs& A)
 {
-    AZ_LAUNCH((az_k_pair_warp<VK, CK, SINGLE, RADII, ENERGY>), e->warp_nblocks, AZ_WARP_TPB, 0, e->stream, e->P, A);
+    AZ_LAUNCH_PDL(e->pdl && e->profile == 0, (az_k_pair_warp<VK, CK, SINGLE, RADII, ENERGY>), e->warp_nblocks, AZ_WARP_TPB, 0, e->stream, e->P, A);
     return AZ_OK;
 }
 
