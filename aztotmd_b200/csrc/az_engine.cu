@@ -828,14 +828,17 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
     const int nb = e->n_atom_blocks;
     int c = e->cur;
     const int n_pp = e->use_list ? e->list_nblocks : (e->use_thread ? e->thread_nblocks : (e->use_warp ? e->warp_nblocks : e->pair_nblocks)); // live pair partials this step
-    const int slot = (int)(e->steps_done % 3); // pending momenta / speed bound of the step in flight (three slots: az_kernels.cuh)
+    // pending momenta / speed bound of the step in flight: three slots (az_kernels.cuh), numbered by the step's place INSIDE the
+    // call -- nothing is pending across calls (the last step of a call does not kick the next one), so the launch sequence of a
+    // call does not depend on how many steps ran before it (one captured graph per call shape, not three)
+    const int slot = e->call_rel % 3;
     // az_k_finalize of a step whose integrator rode on the list pass has nothing the next pass waits for: it runs on its own
     // stream beside the pass of step n + 1 (it was 16 us of every 570 us step, one block reducing 31 250 partials).  What the
     // two share is double- or triple-buffered: the kinetic-energy partials by step parity, the pending momenta and the speed
     // bound by step % 3; az_k_finalize writes back only its own fields.  The pass of step n + 2 waits for finalize(n).  Every
     // step that does anything else with the scalars (no rider, energies, thermostats, bonds, graph capture) first
     // joins the finalize stream, and the last step of a call never rides, so nothing is pending when a call returns.
-    const int kpar = (int)(e->steps_done & 1);
+    const int kpar = e->call_rel & 1;
     double* const pke = e->partKE + (size_t)kpar * e->n_ke_blocks;
     const bool ovl_ok = e->fin_overlap && fuse_next && !is_eq_step(e, step) && !want_energy && !e->bonded && e->profile != 1;
     const bool ovl = ovl_ok && e->fuse_pair && !e->use_graph;
@@ -1107,6 +1110,7 @@ static int run_steps(az_engine* e, int first_step, int nsteps)
         // so downloads and statistics always see the state "after step n".
         const bool fuse = e->fuse_integrate && k + 1 < nsteps && !is_eq_step(e, step) && !e->P.has_efield && e->P.tstat != AZ_TSTAT_NOSE && e->reset_vels == 0;
         // potential energies are reduced on the last step of the call (the one az_engine_stats reports)
+        e->call_rel = k;
         int rc = one_step(e, step, e->energy_every_step || k == nsteps - 1, a_done, fuse);
         if (rc) return rc;
         a_done = fuse;
@@ -1123,7 +1127,7 @@ static unsigned long long graph_key(const az_engine* e, int first_step, int nste
 {
     unsigned long long h = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
-    mix((unsigned long long)nsteps); mix((unsigned long long)e->since_rebuild); mix(e->binned ? 1 : 0); mix((unsigned long long)(e->steps_done % 3));
+    mix((unsigned long long)nsteps); mix((unsigned long long)e->since_rebuild); mix(e->binned ? 1 : 0);
     mix((unsigned long long)e->cur); mix(e->energy_every_step ? 1 : 0); mix(e->fuse_integrate ? 1 : 0);
     mix((unsigned long long)(uintptr_t)e->pos[0]); mix((unsigned long long)(uintptr_t)e->pos[1]); mix((unsigned long long)(uintptr_t)e->pos_alt);
     mix((unsigned long long)(uintptr_t)e->vel[0]); mix((unsigned long long)(uintptr_t)e->vel[1]); mix((unsigned long long)(uintptr_t)e->vel_alt);
@@ -1188,7 +1192,24 @@ extern "C" int az_engine_step(az_engine* e, int first_step, int nsteps)
         if (!e->tl_tuned && e->binned && nsteps > 0) { rc = tl_autotune(e, true); if (rc) return rc; }
         return AZ_OK;
     }
-    // graph mode: the kernels take their step from the device (*step0_dev + index inside the call)
+    // graph mode: the kernels take their step from the device (*step0_dev + index inside the call).
+    // A long call is replayed in pieces of ~48 steps (a multiple of the rebuild interval): recording and instantiating a graph
+    // costs ~80 us per kernel node -- a second for a 2 000-step call of a six-kernel step, more than the steps themselves --
+    // while a piece is recorded in 25 ms, once, and replayed for every later piece of every later call.  The trajectory is the
+    // one of the caller stepping in such pieces itself (bitwise the same: case_fused_kick_drift..., case_graph_replay...).
+    {
+        const int R = e->rebuild_every > 1 ? e->rebuild_every : 1;
+        const int G = R * ((48 + R - 1) / R);
+        if (nsteps > G + G / 2) {
+            int done = 0;
+            while (nsteps - done > G + G / 2) {
+                int rc = az_engine_step(e, first_step + done, G);
+                if (rc) return rc;
+                done += G;
+            }
+            return az_engine_step(e, first_step + done, nsteps - done);
+        }
+    }
     e->call_first = first_step;
     AZ_LAUNCH(az_k_set_int, 1, 1, 0, e->stream, e->step0_dev, first_step);
     e->launches++;

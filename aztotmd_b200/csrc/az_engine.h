@@ -25,6 +25,7 @@ struct az_engine {
     struct PendingEv { cudaEvent_t a, b; int k; };
     std::vector<PendingEv> pending;
     int last_step = -1;
+    int call_rel = 0; // index of the step in flight inside the current az_engine_step call
     long long steps_done = 0;
     bool fuse_integrate = true; // second half kick of step n and kick + drift of step n+1 in one pass
     // az_cuda_opts.use_graph: az_engine_step(first, n) is captured once per call shape as a CUDA graph and replayed (the

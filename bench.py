@@ -200,8 +200,9 @@ def small_deck_line(lib, name="cs1", steps=2000, warmup=200):
     if lib.az_deck_load(d.encode(), 12345, C.byref(h)) != 0:
         return {"unavailable": "deck does not parse"}
     desc = lib.az_deck_desc(h).contents
-    out = {"workload": "shipped case study 1 (tests/golden/decks/cs1): 40,000 Ar, LJ rc 4 A, radiative thermostat 298 K, rebuild every step",
-           "n_atoms": int(desc.n_atoms), "steps": steps}
+    what = {"cs1": "shipped case study 1 (tests/golden/decks/cs1): 40,000 Ar, LJ rc 4 A, radiative thermostat 298 K, rebuild every step",
+            "cs2": "shipped case study 2 (tests/golden/decks/cs2): 4,000 atoms, radius/temperature-dependent surk potential + radiative thermostat 500 K, rebuild every step"}
+    out = {"workload": what.get(name, name), "n_atoms": int(desc.n_atoms), "steps": steps}
     for tag, graph in (("plain", 0), ("graph", 1)):
         opts = abi.az_cuda_opts.from_buffer_copy(bytes(lib.az_deck_opts(h).contents))
         opts.use_graph = graph
@@ -215,6 +216,23 @@ def small_deck_line(lib, name="cs1", steps=2000, warmup=200):
         out[tag] = {"us_per_step": ms / steps * 1e3, "atom_steps_per_s": desc.n_atoms * steps / (ms * 1e-3)}
         e.close()
     lib.az_deck_free(h)
+    return out
+
+
+def ionic_line(steps=40, warmup=10):
+    """BASELINE config 4: synthetic NaCl-like ionic melt, 1 M ions, Buckingham + real-space (DSF) Coulomb, list rebuilt every 5 steps."""
+    from aztotmd_b200.engine import Engine
+    ncell, desc = WORKLOADS["nacl1m"]
+    s = ionic_system(-ncell, 5, 0.6)  # (ionic workloads carry their cell count negated)
+    e = Engine(s, rebuild_every=5, skin=0.6)
+    e.step(0, warmup)
+    e.stats()
+    ms = e.step_timed(warmup, steps)
+    st = e.stats()
+    n = len(s.pos)
+    out = {"workload": desc + "; rebuild every 5 steps, skin 0.6 A", "n_atoms": n, "steps": steps, "ms_per_step": ms / steps,
+           "atom_steps_per_s": n * steps / (ms * 1e-3), "pairs_in_cutoff": int(st.n_pairs)}
+    e.close()
     return out
 
 
@@ -513,6 +531,8 @@ def main():
     e.close()
     if args.workload == "lj4m" and not args.no_small_deck:
         out["cs1"] = small_deck_line(lib)
+        # the other single-GPU configurations of BASELINE.json, so that one driver-run line covers them all
+        out["other_configs"] = {"cs2": small_deck_line(lib, "cs2"), "nacl1m": ionic_line()}
     rc = ref_cuda_baseline()
     if rc:
         out["ref_cuda_baseline"] = rc
