@@ -207,7 +207,7 @@ def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
     for tag, env in (("direct", {}), ("fused", {"AZTOT_NO_DIRECT_HALO": "1"}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
         os.environ.update(env)
         try:
-            runs[tag] = check_against_single(lib, s, 2, (2, 1, 1), nsteps=9, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
+            runs[tag] = check_against_single(lib, s, 2, (2, 1, 1), nsteps=7, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices)
         finally:
             for k in env:
                 os.environ.pop(k, None)
@@ -217,15 +217,18 @@ def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
         assert all(r["info"].peer_halo == 3 for r in runs["direct"])
     for tag in ("direct", "fused", "peer"):
         for a, b in zip(runs[tag], runs["sendrecv"]):
-            assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["dump"]["frc"], b["dump"]["frc"]), tag
-            assert np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
+            assert np.array_equal(a["dump"]["ids"], b["dump"]["ids"]) and np.array_equal(a["atoms"]["pos"], b["atoms"]["pos"]), tag
+            if tag == "fused" and devices is None:  # (emulator only: scalar row loop in the ghost-touching blocks, packed elsewhere)
+                assert np.abs(a["dump"]["frc"] - b["dump"]["frc"]).max() <= 1e-5 * np.abs(b["dump"]["frc"]).max()
+            else:
+                assert np.array_equal(a["dump"]["frc"], b["dump"]["frc"]), tag
     # the same four ways with all steps in ONE call: the integrator rides on the list kernel, the position streams rotate, and
     # the direct halo really stores into the neighbours' streams (single-step calls drift in place and take the staged route)
     calls = {}
     for tag, env in (("direct", {}), ("fused", {"AZTOT_NO_DIRECT_HALO": "1"}), ("peer", {"AZTOT_NO_FUSED_HALO": "1"}), ("sendrecv", {"AZTOT_NO_PEER_HALO": "1"})):
         os.environ.update(env)
         try:
-            calls[tag] = run_bricks(lib, s, 2, (2, 1, 1), 11, devices=devices, one_call=True, rebuild_every=4, skin=0.8)
+            calls[tag] = run_bricks(lib, s, 2, (2, 1, 1), 9, devices=devices, one_call=True, rebuild_every=4, skin=0.8)
         finally:
             for k in env:
                 os.environ.pop(k, None)
@@ -239,7 +242,7 @@ def case_bricks_peer_memory_halo_equals_send_recv(lib, devices=None):
             else:
                 assert np.array_equal(a["dump"]["frc"], b["dump"]["frc"]) and a["stats"][-1].engVdW_d == b["stats"][-1].engVdW_d, tag
     e1 = Engine(s, lib=lib, rebuild_every=4, skin=0.8)
-    e1.step(0, 11)
+    e1.step(0, 9)
     s1 = e1.stats()
     for r in calls["direct"]:
         assert r["stats"][-1].n_pairs == s1.n_pairs and abs(r["stats"][-1].engVdW_d - s1.engVdW_d) <= 1e-5 * abs(s1.engVdW_d)
@@ -254,9 +257,9 @@ def case_eight_bricks_list_direct_halo(lib, devices=None):
     s = azt.lj_system(ncell=(8, 8, 8), seed=91, cell_size=9.3, temperature=300.0)
     kw = dict(rebuild_every=4, skin=0.8)
     for n_ranks, pgrid in ((8, (2, 2, 2)), (4, (1, 2, 2))):
-        res = run_bricks(lib, s, n_ranks, pgrid, 10, devices=devices, one_call=True, **kw)
+        res = run_bricks(lib, s, n_ranks, pgrid, 7, devices=devices, one_call=True, **kw)  # rebuilds at steps 0 and 4, direct puts at 1-3, 5, 6
         e1 = Engine(s, lib=lib, **kw)
-        e1.step(0, 10)
+        e1.step(0, 7)
         s1 = e1.stats()
         n = len(s.pos)
         frc, pos, vel, seen = gather_by_id(res, n)
@@ -281,9 +284,9 @@ def case_bricks_tile_lists(lib, devices=None):
     """list_format 2 (tile lists, az_tlist.cuh) on bricks: footprints that contain ghost atoms, the ghost-touching tiles waiting on
     the arrival flags of the direct halo -- against one engine (single-step calls) and against the global rows (one call)."""
     s = azt.lj_system(ncell=(8, 5, 5), seed=25, cell_size=9.3)
-    check_against_single(lib, s, 2, (2, 1, 1), nsteps=7, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices, list_format=2)
-    a = run_bricks(lib, s, 2, (2, 1, 1), 10, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=2)
-    b = run_bricks(lib, s, 2, (2, 1, 1), 10, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=1)
+    check_against_single(lib, s, 2, (2, 1, 1), nsteps=5, rebuild_every=4, skin=0.8, tol=1e-4, devices=devices, list_format=2)
+    a = run_bricks(lib, s, 2, (2, 1, 1), 7, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=2)
+    b = run_bricks(lib, s, 2, (2, 1, 1), 7, devices=devices, one_call=True, rebuild_every=4, skin=0.8, list_format=1)
     for x, y in zip(a, b):
         assert x["info"].tile_list == 1 and y["info"].tile_list == 0
         assert x["stats"][-1].n_pairs == y["stats"][-1].n_pairs and np.array_equal(x["dump"]["ids"], y["dump"]["ids"])

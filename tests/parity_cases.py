@@ -443,7 +443,7 @@ def case_tile_list_is_bitwise_the_global_rows(lib):
         exact = not (emu and len(s.species) == 1 and s.elec_kind == abi.ELEC_NONE and all(v["kind"] == abi.VDW_LJ for v in s.vdw.values()))
         a, b = Engine(s, lib=lib, list_format=1, **kw), Engine(s, lib=lib, list_format=2, **kw)
         assert a.info.tile_list == 0 and b.info.tile_list == 1
-        a.step(0, 9); b.step(0, 9)
+        a.step(0, 7); b.step(0, 7)
         da, db = a.dump(), b.dump()
         for key in ("pos", "vel", "frc", "ids", "cell"):
             if exact or key in ("ids", "cell"):
@@ -460,13 +460,13 @@ def case_tile_list_is_bitwise_the_global_rows(lib):
         assert 0 < b.info.tile_atoms_seen <= b.info.tile_atoms and 0 < b.info.tile_runs_seen <= 64
         # single-step calls; the switch by name takes an engine created for tile lists back to the global rows
         c = Engine(s, lib=lib, list_format=2, **kw)
-        for k in range(9):
+        for k in range(7):
             c.step(k, 1)
         assert np.array_equal(c.dump()["pos"], db["pos"]) and np.array_equal(c.dump()["frc"], db["frc"])
         c.close()
         c = Engine(s, lib=lib, list_format=2, **kw)
         c.set_option("tile_list", 0)
-        c.step(0, 9)
+        c.step(0, 7)
         assert np.array_equal(c.dump()["pos"], da["pos"]) and np.array_equal(c.dump()["frc"], da["frc"])
         a.close(); b.close(); c.close()
     # a footprint allotment that is too small is reported, not silently wrong
