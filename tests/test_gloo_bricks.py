@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_two_ranks_over_gloo():
     azt.emu_lib()  # build once, before two processes race for it
-    env = dict(os.environ, OMP_NUM_THREADS="1", AZ_EMU_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="1", AZ_EMU_THREADS="4")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29577", os.path.join(ROOT, "tests", "gloo_brick_worker.py")],
                        capture_output=True, text=True, timeout=900, env=env)
