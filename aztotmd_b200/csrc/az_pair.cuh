@@ -336,8 +336,11 @@ __device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)
 // cell-to-cell distance of the reference (cell_dist_int), NOT by the atom's own position: measured on B200, pruning
 // per atom makes the lanes of a warp (atoms of one cell) walk different ranges, which costs more in divergence
 // and lost L1 broadcasts (22 active lanes per instruction instead of 30) than the 30 % fewer candidates save.
+#ifndef AZ_BUILD_MINB
+#define AZ_BUILD_MINB 1 // resident blocks asked of ptxas for the list build (A/B knob)
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(AZ_LIST_TPB)
+__global__ void __launch_bounds__(AZ_LIST_TPB, AZ_BUILD_MINB)
 az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     const AzGrid& g = P.g;
