@@ -336,11 +336,18 @@ __device__ __forceinline__ size_t az_nbr_base(int i, int cap) { return ((size_t)
 // cell-to-cell distance of the reference (cell_dist_int), NOT by the atom's own position: measured on B200, pruning
 // per atom makes the lanes of a warp (atoms of one cell) walk different ranges, which costs more in divergence
 // and lost L1 broadcasts (22 active lanes per instruction instead of 30) than the 30 % fewer candidates save.
-#ifndef AZ_BUILD_MINB
-#define AZ_BUILD_MINB 1 // resident blocks asked of ptxas for the list build (A/B knob)
+#ifndef AZ_BUILD_UNROLL
+#define AZ_BUILD_UNROLL 2 // candidate pairs per trip of the list build's inner loop (A/B knob)
+#endif
+// A/B knob: resident blocks asked of ptxas for the list build.  Left undefined by default -- naming even 1 block makes ptxas
+// spend 66 registers instead of 56 on this kernel.
+#ifdef AZ_BUILD_MINB
+#define AZ_BUILD_BOUNDS __launch_bounds__(AZ_LIST_TPB, AZ_BUILD_MINB)
+#else
+#define AZ_BUILD_BOUNDS __launch_bounds__(AZ_LIST_TPB)
 #endif
 template <bool FAST>
-__global__ void __launch_bounds__(AZ_LIST_TPB, AZ_BUILD_MINB)
+__global__ void AZ_BUILD_BOUNDS
 az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPairArgs A)
 {
     const AzGrid& g = P.g;
@@ -376,7 +383,15 @@ az_k_build_list(const __grid_constant__ AzParams P, const __grid_constant__ AzPa
                 // the loop body is the distance test and a predicated store + pointer bump.  Two candidates per FADD2 / FFMA2;
                 // each half is rounded like the scalar fmaf chain of the force pass, so the recorded set is the same.
                 int j = rb, o = nA * 32; // o: offset of the next free row, in ints (one IMAD.WIDE + ST + IADD per hit)
+#if AZ_BUILD_UNROLL == 1
+#pragma unroll 1
+#elif AZ_BUILD_UNROLL == 3
+#pragma unroll 3
+#elif AZ_BUILD_UNROLL == 4
+#pragma unroll 4
+#else
 #pragma unroll 2
+#endif
                 for (; j + 2 <= re; j += 2) {
                     const float4 pa = __ldg(A.pos + j), pb = __ldg(A.pos + j + 1);
                     const az_f2 dx = az_pk(pi.x - pa.x, pi.x - pb.x), dy = az_pk(pi.y - pa.y, pi.y - pb.y), dz = az_pk(pi.z - pa.z, pi.z - pb.z);
