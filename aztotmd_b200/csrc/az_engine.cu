@@ -112,6 +112,11 @@ template <class T> static int dev_alloc(az_engine* e, T** p, size_t count)
 }
 #define AZ_ALLOC(e, p, n) do { int rc_ = dev_alloc(e, &(p), (size_t)(n)); if (rc_) return rc_; } while (0)
 
+#ifdef AZ_PROBE_MORTON // probe build only: sub-cell scale of the Morton in-cell order (az_k_sort_scatter)
+#define AZ_PROBE_SORT_ARGS , 4.f * e->P.g.crev[0], 4.f * e->P.g.crev[1], 4.f * e->P.g.crev[2]
+#else
+#define AZ_PROBE_SORT_ARGS
+#endif
 static int dd_setup(az_engine* e, const az_system_desc* d, const az_cuda_opts* o);
 static int ewald_setup(az_engine* e, const az_system_desc* d, double qs[2]);
 static int bonded_setup(az_engine* e, const az_system_desc* d);
@@ -893,11 +898,11 @@ static int one_step(az_engine* e, int step, bool want_energy, bool skip_a, bool 
             if (e->use_therm)
                 AZ_LAUNCH_PDL(pdl, az_k_sort_scatter<true>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, (const int*)e->cellOf, (const int*)e->first, (const int*)e->cellCount, (const int*)e->keyTmp,
                               (const float4*)e->pos[c], (const float4*)e->vel[c], (const int*)e->id[c], (const float2*)e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c],
-                              e->cellSorted, (int*)nullptr, e->whereId);
+                              e->cellSorted, (int*)nullptr, e->whereId AZ_PROBE_SORT_ARGS);
             else
                 AZ_LAUNCH_PDL(pdl, az_k_sort_scatter<false>, nb, AZ_TPB, 0, st, n, (const int*)nullptr, (const int*)e->cellOf, (const int*)e->first, (const int*)e->cellCount, (const int*)e->keyTmp,
                               (const float4*)e->pos[c], (const float4*)e->vel[c], (const int*)e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr,
-                              e->cellSorted, (int*)nullptr, e->whereId);
+                              e->cellSorted, (int*)nullptr, e->whereId AZ_PROBE_SORT_ARGS);
             AZ_COUNT(e, AZ_TIMER_SORT, 2);
         }
         c = e->cur = 1 - c; // refresh_arrays (src/cuSort.cu:74-100): host-side ping-pong

@@ -562,10 +562,10 @@ static int dd_rebuild(az_engine* e, int c)
         AZ_LAUNCH(az_k_sort_keys, nbt, AZ_TPB, 0, st, D.cap_total, ntot, e->cellOf, e->slotOf, e->first, e->id[c], e->keyTmp);
         if (e->use_therm)
             AZ_LAUNCH(az_k_sort_scatter<true>, nbt, AZ_TPB, 0, st, D.cap_total, ntot, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                      e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, h->newIndex, (int*)nullptr);
+                      e->id[c], e->therm[c], e->pos[1 - c], e->vel[1 - c], e->id[1 - c], e->therm[1 - c], e->cellSorted, h->newIndex, (int*)nullptr AZ_PROBE_SORT_ARGS);
         else
             AZ_LAUNCH(az_k_sort_scatter<false>, nbt, AZ_TPB, 0, st, D.cap_total, ntot, e->cellOf, e->first, e->cellCount, e->keyTmp, e->pos[c], e->vel[c],
-                      e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, h->newIndex, (int*)nullptr);
+                      e->id[c], (const float2*)nullptr, e->pos[1 - c], e->vel[1 - c], e->id[1 - c], (float2*)nullptr, e->cellSorted, h->newIndex, (int*)nullptr AZ_PROBE_SORT_ARGS);
         const int nmax = D.gs[AZ_NDIR] > D.gr[AZ_NDIR] ? D.gs[AZ_NDIR] : D.gr[AZ_NDIR];
         h->slot_epoch++;
         AZ_LAUNCH(az_k_dd_remap, blocks(nmax), AZ_TPB, 0, st, D, h->newIndex, h->sendList, h->ghostSlot, h->peerPtr, h->direct ? 1 : 0, h->slot_epoch, h->putDone + 1);

@@ -248,7 +248,11 @@ az_k_sort_keys(int n, const int* __restrict__ n_dyn, const int* __restrict__ cel
     az_pdl_trigger(); az_pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dyn) n = *n_dyn;
+#ifdef AZ_PROBE_MORTON // probe build only (profiles/r2): the cell's members are ranked by a sub-cell Morton code, ties by id
+    if (i < n && cellOf[i] >= 0) keyTmp[first[cellOf[i]] + slotOf[i]] = i;
+#else
     if (i < n && cellOf[i] >= 0) keyTmp[first[cellOf[i]] + slotOf[i]] = id[i]; // cell -1: the atom left this brick
+#endif
 }
 
 template <bool THERM>
@@ -258,7 +262,11 @@ az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ 
                   const float4* __restrict__ pos, const float4* __restrict__ vel,
                   const int* __restrict__ id, const float2* __restrict__ therm,
                   float4* __restrict__ pos_o, float4* __restrict__ vel_o, int* __restrict__ id_o,
-                  float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex, int* __restrict__ whereId)
+                  float2* __restrict__ therm_o, int* __restrict__ cell_o, int* __restrict__ newIndex, int* __restrict__ whereId
+#ifdef AZ_PROBE_MORTON
+                  , float subx, float suby, float subz
+#endif
+                  )
 {
     az_pdl_trigger(); az_pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,7 +277,20 @@ az_k_sort_scatter(int n, const int* __restrict__ n_dyn, const int* __restrict__ 
     int b = first[c], m = count[c];
     int my = id[i];
     int rank = 0;
+#ifdef AZ_PROBE_MORTON
+    auto code = [&](const float4 p) {
+        const int a = (int)(p.x * subx) & 3, bb = (int)(p.y * suby) & 3, cc = (int)(p.z * subz) & 3;
+        return ((cc >> 1) << 5) | ((bb >> 1) << 4) | ((a >> 1) << 3) | ((cc & 1) << 2) | ((bb & 1) << 1) | (a & 1);
+    };
+    const int mc = code(pos[i]);
+    for (int k = 0; k < m; k++) {
+        const int o = keyTmp[b + k];
+        const int oc = code(pos[o]), oid = id[o];
+        rank += (oc < mc) | ((oc == mc) & (oid < my));
+    }
+#else
     for (int k = 0; k < m; k++) rank += (keyTmp[b + k] < my);
+#endif
     int d = b + rank;
     pos_o[d] = pos[i];
     vel_o[d] = vel[i];
