@@ -77,3 +77,32 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "az_oracle" not in text and "libaz_oracle" not in text and "oracle/_ref" not in text, os.path.join(dirpath, f)
+
+
+def _adapter_block():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```cpp\n(// az_adapter\.cpp.*?)```", doc, re.S)
+    assert m, "INTEGRATION.md section B lost its adapter block"
+    return m.group(1)
+
+
+def test_reference_adapter_in_the_docs_is_the_checked_file():
+    """INTEGRATION.md section B and oracle/az_adapter.cpp hold the same text (the file is what gets compiled below)."""
+    src = open(os.path.join(ROOT, "oracle", "az_adapter.cpp")).read()
+    marker = "// ---- INTEGRATION.md section B ----\n"
+    assert marker in src
+    assert src.split(marker, 1)[1] == _adapter_block()
+
+
+REF_SRC = os.environ.get("AZ_REFERENCE_SRC", "/root/reference/src")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF_SRC, "dataStruct.h")), reason="the reference tree is not on this box")
+def test_reference_adapter_compiles_against_the_reference_headers():
+    """The binding a maintainer would add against the reference's own structs
+    (src/dataStruct.h Atoms / Field / Sim / Box / Elec / Spec / VdW, src/temperature.h TStat, src/elec.h tpElec*)
+    and include/aztot_b200.h: every field it names exists with a convertible type."""
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "oracle", "shim"), "-I", REF_SRC,
+           "-I", os.path.join(ROOT, "include"), "-include", "cstdio", os.path.join(ROOT, "oracle", "az_adapter.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
